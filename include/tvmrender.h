@@ -1,0 +1,177 @@
+/*
+ * tvmrender.h -- C ABI of libtvmrender.so: the TensoRF-VM per-ray rendering hot path of
+ * tensorf-myc (FREDZEL2020/jittor-MYC-NeRFs), rebuilt as hand-written sm_100a CUDA kernels.
+ *
+ * Reference interface this library replaces (paths relative to the reference's tensorf-myc/):
+ *   renderer.py:12-27                 OctreeRender_trilinear_fast   -> tvm_forward over all rays
+ *   models/tensorBase.py:476-536      TensorBase.execute            -> tvm_forward / tvm_backward
+ *   models/tensorBase.py:340-360      sample_ray                    -> march stage of tvm_forward
+ *   models/tensorBase.py:39-59        AlphaGridMask.sample_alpha    -> tvm_pack_alpha + march stage
+ *   models/tensoRF.py:209-244         compute_density/appfeature    -> gather stages
+ *   models/tensorBase.py:62-86        MLPRender_Fea                 -> appearance stage
+ *   models/tensorBase.py:17-24        raw2alpha                     -> composite stage
+ *   models/tensorBase.py:451-473      compute_alpha                 -> tvm_density_alpha
+ *   train.py:228,260                  loss.backward (Jittor autograd over the ops above) -> tvm_backward
+ * The reference has no C ABI of its own; its only native-plugin idiom is Jittor's
+ * jt.code(cuda_header=..., cuda_src=...) with raw inK_p/outK_p device pointers
+ * (jnerf-myc/python/jnerf/models/samplers/density_grid_sampler/calc_rgb.py:35-75), which is what
+ * binds to these symbols.
+ *
+ * Conventions: every pointer is a DEVICE pointer unless the name ends in _host; all floating point
+ * is IEEE fp32; the caller owns every buffer; the library keeps no global state besides a
+ * thread-local error string; every entry point takes the CUDA stream (as void*) it enqueues on and
+ * never synchronises; return value 0 = ok, negative = error (tvm_last_error() explains).
+ * There is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef TVMRENDER_H_
+#define TVMRENDER_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TVM_ABI_VERSION 3
+
+/* flags for tvm_forward / tvm_backward */
+#define TVM_WHITE_BG      0x1u  /* rgb_map += 1 - acc_map          (tensorBase.py:523-524) */
+#define TVM_NO_ERT        0x2u  /* disable early ray termination (march every in-box sample) */
+#define TVM_MLP_FP32      0x0u  /* appearance head in fp32 FMA (parity 1e-4)                */
+#define TVM_MLP_BF16      0x10u /* appearance head on tcgen05 tensor cores, bf16 x bf16 -> fp32 (parity 1e-2) */
+#define TVM_MLP_BF16X3    0x20u /* tcgen05, 3-term split-bf16 (near-fp32; parity 1e-4)       */
+#define TVM_MLP_MASK      0x30u
+
+/* activation (tensorBase.py:444-448) */
+#define TVM_ACT_SOFTPLUS  0
+#define TVM_ACT_RELU      1
+
+/* Host-side descriptor of one model; device pointers refer to the PACKED layouts written by
+ * tvm_pack_grid / tvm_pack_alpha / tvm_pack_linear (channels-last grids, bit-packed alpha volume,
+ * [in][out] linear weights).  Plain-old-data, passed by pointer, copied by value into the launch. */
+typedef struct TvmModel {
+  /* scalars derived exactly as TensorBase.update_stepSize does (tensorBase.py:197-209) */
+  float aabb[6];            /* xmin ymin zmin xmax ymax zmax                     */
+  float inv_aabb_size[3];   /* 2.0 / aabbSize                (tensorBase.py:201) */
+  int32_t grid[3];          /* gridSize Gx Gy Gz                                  */
+  float step_size;          /* mean(units) * step_ratio      (tensorBase.py:204) */
+  float near_, far_;        /* near_far                                           */
+  float density_shift;      /* tensorBase.py:446                                  */
+  float distance_scale;     /* tensorBase.py:511                                  */
+  float weight_thres;       /* rayMarch_weight_thres (always 1e-4 in the reference) */
+  int32_t act;              /* TVM_ACT_*                                          */
+  int32_t n_density;        /* channels per density component (16)                */
+  int32_t n_app;            /* channels per appearance component (48)             */
+  int32_t app_dim;          /* basis_mat outputs (27)                             */
+  int32_t view_pe, fea_pe;  /* positional-encoding frequencies (2, 2)             */
+  int32_t feature_c;        /* MLP width (128)                                    */
+  /* factor grids, channels-last: plane k is [G[m1]][G[m0]][C], line k is [G[v]][C]
+   * with matMode [[0,1],[0,2],[1,2]], vecMode [2,1,0] (tensorBase.py:168-169)    */
+  const float* density_plane[3];
+  const float* density_line[3];
+  const float* app_plane[3];
+  const float* app_line[3];
+  /* appearance head, [in][out_padded] layouts from tvm_pack_linear              */
+  const float* basis_t;     /* [3*n_app][32]        basis_mat.weight^T, zero padded      */
+  const float* w1_t;        /* [in_mlp_c][feature_c] renderModule.mlp.0.weight^T          */
+  const float* b1;          /* [feature_c]                                                */
+  const float* w2_t;        /* [feature_c][feature_c]                                     */
+  const float* b2;          /* [feature_c]                                                */
+  const float* w3;          /* [3][feature_c]        renderModule.mlp.4.weight (as is)    */
+  const float* b3;          /* [3]                                                        */
+  /* alpha mask (NULL = no mask): bit (z*H + y)*W + x of a little-endian uint32 stream    */
+  const uint32_t* alpha_bits;
+  int32_t alpha_grid[3];    /* W(x) H(y) D(z)                                             */
+  float alpha_aabb_min[3];  /* AlphaGridMask.aabb[0]          (tensorBase.py:44)          */
+  float alpha_inv_size[3];  /* 1.0 / aabbSize * 2             (tensorBase.py:46)          */
+  /* optional tensor-core operand images written by tvm_pack_mlp_tc (NULL = not packed)   */
+  const void* tc_weights;
+} TvmModel;
+
+/* Optional per-sample outputs for parity tests (any member may be NULL).  Requesting aux
+ * disables early ray termination so that every mask bit is produced.                         */
+typedef struct TvmAux {
+  uint32_t* bbox_bits;      /* [n][ceil(S/32)]  in-bbox mask of sample_ray (tensorBase.py:358)      */
+  uint32_t* valid_bits;     /* [n][ceil(S/32)]  ray_valid after the alpha mask (tensorBase.py:491-496) */
+  uint32_t* app_bits;       /* [n][ceil(S/32)]  app_mask = weight > thres (tensorBase.py:513)       */
+  float* sigma;             /* [n][S]                                                                */
+  float* weight;            /* [n][S]                                                                */
+  float* rgb;               /* [n][S][3]        per-sample colour (0 where !app_mask)                */
+  float* acc_map;           /* [n]                                                                   */
+} TvmAux;
+
+/* Gradient targets of tvm_backward: same PACKED layouts as TvmModel; accumulated with
+ * atomics (red.global.add.f32); the caller zeroes them.                                       */
+typedef struct TvmGrads {
+  float* density_plane[3];
+  float* density_line[3];
+  float* app_plane[3];
+  float* app_line[3];
+  float* basis_t;           /* [3*n_app][32]  */
+  float* w1_t;              /* [in_mlp_c][feature_c] */
+  float* b1;
+  float* w2_t;
+  float* b2;
+  float* w3;                /* [3][feature_c] */
+  float* b3;
+} TvmGrads;
+
+/* Work counters filled by tvm_forward (device memory, 8 x uint64): see TVM_CNT_*              */
+#define TVM_CNT_M_IN   0    /* samples inside the bbox that were marched                        */
+#define TVM_CNT_M_V    1    /* samples whose density was gathered (passed the alpha mask)       */
+#define TVM_CNT_M_A    2    /* samples with weight > thres (appearance evaluated)               */
+#define TVM_CNT_RAYS   3    /* rays with at least one gathered sample                           */
+#define TVM_CNT_WORDS  8
+
+const char* tvm_last_error(void);
+int tvm_abi_version(void);
+/* number of CUDA devices visible, or negative on error (no CPU fallback exists) */
+int tvm_device_count(void);
+
+/* ---- parameter upload (replaces nothing in the reference: Jittor owns NCHW Vars) ------------ */
+/* NCHW [1,C,H,W] -> channels-last [H][W][C]; lines are the W==1 case.                          */
+int tvm_pack_grid(const float* nchw, int C, int H, int W, float* out_hwc, void* stream);
+/* inverse of tvm_pack_grid (used on gradients so the host optimiser sees NCHW)                */
+int tvm_unpack_grid(const float* hwc, int C, int H, int W, float* out_nchw, void* stream);
+/* Linear weight [out][in] -> [in][out_pad] (zero padded columns)                              */
+int tvm_pack_linear(const float* w_out_in, int out_c, int in_c, int out_pad, float* out_t, void* stream);
+int tvm_unpack_linear(const float* w_t, int out_c, int in_c, int out_pad, float* out_w, void* stream);
+/* {0,1} fp32 volume [D][H][W] -> bit stream (bit set iff value > 0); n_words = ceil(D*H*W/32)  */
+int tvm_pack_alpha(const float* volume, int D, int H, int W, uint32_t* bits, void* stream);
+/* bytes of the tensor-core operand image for (in_mlp_c, feature_c, app_dim, n_app)            */
+size_t tvm_tc_weights_bytes(const TvmModel* m_host);
+/* builds the bf16 (hi, mid) K-major UMMA operand images of basis/W1/W2 from the packed fp32 weights */
+int tvm_pack_mlp_tc(const TvmModel* m_host, void* tc_weights_out, void* stream);
+
+/* ---- the hot path --------------------------------------------------------------------------- */
+/* bytes of scratch tvm_forward needs for n rays x n_samples (worst case: every sample weighted) */
+int tvm_workspace_bytes(int n_rays, int n_samples, size_t* out_bytes);
+
+/* TensorBase.execute for n rays (tensorBase.py:476-536, ndc_ray=False):
+ *   rays [n][6] (origin, unit direction), jitter [n] or NULL (is_train: rng += U[0,1) per ray,
+ *   tensorBase.py:351-353), rgb_map [n][3], depth_map [n], counters [TVM_CNT_WORDS] uint64 or NULL
+ *   (accumulated, caller zeroes).  The workspace keeps what tvm_backward needs until the next call. */
+int tvm_forward(const TvmModel* m_host, const float* rays, int n_rays, int n_samples,
+                const float* jitter, uint32_t flags, float* rgb_map, float* depth_map,
+                const TvmAux* aux_host, uint64_t* counters, void* ws, size_t ws_bytes, void* stream);
+
+/* Backward of tvm_forward w.r.t. every parameter, given d_rgb_map [n][3] = dL/d rgb_map
+ * (row a12 of SURVEY §8a; coordinates are detached, depth carries no gradient).  Must follow a
+ * tvm_forward with the same arguments on the same workspace.                                     */
+int tvm_backward(const TvmModel* m_host, const float* rays, int n_rays, int n_samples,
+                 const float* jitter, uint32_t flags, const float* rgb_map, const float* d_rgb_map,
+                 const TvmGrads* grads_host, void* ws, size_t ws_bytes, void* stream);
+
+/* TensorBase.compute_alpha (tensorBase.py:451-473): alpha = 1 - exp(-sigma(xyz) * length)       */
+int tvm_density_alpha(const TvmModel* m_host, const float* xyz, int n_pts, float length,
+                      float* alpha_out, void* stream);
+
+/* MSE loss head of train.py:228: loss = mean((rgb_map - target)^2), d_rgb_map = 2 (rgb_map - target) / (3 n) * scale */
+int tvm_mse_loss(const float* rgb_map, const float* target, int n_rays, float grad_scale,
+                 float* loss_out, float* d_rgb_map, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TVMRENDER_H_ */

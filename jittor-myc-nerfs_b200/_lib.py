@@ -1,0 +1,124 @@
+"""ctypes binding of libtvmrender.so (include/tvmrender.h).
+
+The shared library is the product; this file only marshals pointers.  There is deliberately no
+fallback: if the library is missing or no CUDA device is present, every compute call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtvmrender.so")
+ABI_VERSION = 3
+
+# flags (tvmrender.h)
+WHITE_BG = 0x1
+NO_ERT = 0x2
+MLP_FP32 = 0x0
+MLP_BF16 = 0x10
+MLP_BF16X3 = 0x20
+ACT_SOFTPLUS, ACT_RELU = 0, 1
+CNT_M_IN, CNT_M_V, CNT_M_A, CNT_RAYS, CNT_WORDS = 0, 1, 2, 3, 8
+
+_f3 = C.c_float * 3
+_f6 = C.c_float * 6
+_i3 = C.c_int32 * 3
+_p3 = C.c_void_p * 3
+
+
+class TvmModel(C.Structure):
+    _fields_ = [
+        ("aabb", _f6), ("inv_aabb_size", _f3), ("grid", _i3),
+        ("step_size", C.c_float), ("near_", C.c_float), ("far_", C.c_float),
+        ("density_shift", C.c_float), ("distance_scale", C.c_float), ("weight_thres", C.c_float),
+        ("act", C.c_int32), ("n_density", C.c_int32), ("n_app", C.c_int32), ("app_dim", C.c_int32),
+        ("view_pe", C.c_int32), ("fea_pe", C.c_int32), ("feature_c", C.c_int32),
+        ("density_plane", _p3), ("density_line", _p3), ("app_plane", _p3), ("app_line", _p3),
+        ("basis_t", C.c_void_p), ("w1_t", C.c_void_p), ("b1", C.c_void_p), ("w2_t", C.c_void_p),
+        ("b2", C.c_void_p), ("w3", C.c_void_p), ("b3", C.c_void_p),
+        ("alpha_bits", C.c_void_p), ("alpha_grid", _i3), ("alpha_aabb_min", _f3), ("alpha_inv_size", _f3),
+        ("tc_weights", C.c_void_p),
+    ]
+
+
+class TvmAux(C.Structure):
+    _fields_ = [("bbox_bits", C.c_void_p), ("valid_bits", C.c_void_p), ("app_bits", C.c_void_p),
+                ("sigma", C.c_void_p), ("weight", C.c_void_p), ("rgb", C.c_void_p), ("acc_map", C.c_void_p)]
+
+
+class TvmGrads(C.Structure):
+    _fields_ = [("density_plane", _p3), ("density_line", _p3), ("app_plane", _p3), ("app_line", _p3),
+                ("basis_t", C.c_void_p), ("w1_t", C.c_void_p), ("b1", C.c_void_p), ("w2_t", C.c_void_p),
+                ("b2", C.c_void_p), ("w3", C.c_void_p), ("b3", C.c_void_p)]
+
+
+EXPORTS = [
+    "tvm_last_error", "tvm_abi_version", "tvm_device_count", "tvm_pack_grid", "tvm_unpack_grid",
+    "tvm_pack_linear", "tvm_unpack_linear", "tvm_pack_alpha", "tvm_tc_weights_bytes", "tvm_pack_mlp_tc",
+    "tvm_workspace_bytes", "tvm_forward", "tvm_backward", "tvm_density_alpha", "tvm_mse_loss",
+]
+
+
+class TvmError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """dlopen libtvmrender.so; raises (never falls back) when it is missing or stale."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise TvmError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                       f"or `make -C {os.path.join(_HERE, 'csrc')}`; there is no CPU fallback")
+    lib = C.CDLL(LIB_PATH)
+    for name in EXPORTS:
+        if not hasattr(lib, name):
+            raise TvmError(f"libtvmrender.so does not export {name}")
+    vp, i32, u32, f32 = C.c_void_p, C.c_int, C.c_uint32, C.c_float
+    lib.tvm_last_error.restype = C.c_char_p
+    lib.tvm_last_error.argtypes = []
+    lib.tvm_abi_version.restype = i32
+    lib.tvm_device_count.restype = i32
+    lib.tvm_pack_grid.argtypes = [vp, i32, i32, i32, vp, vp]
+    lib.tvm_unpack_grid.argtypes = [vp, i32, i32, i32, vp, vp]
+    lib.tvm_pack_linear.argtypes = [vp, i32, i32, i32, vp, vp]
+    lib.tvm_unpack_linear.argtypes = [vp, i32, i32, i32, vp, vp]
+    lib.tvm_pack_alpha.argtypes = [vp, i32, i32, i32, vp, vp]
+    lib.tvm_tc_weights_bytes.restype = C.c_size_t
+    lib.tvm_tc_weights_bytes.argtypes = [C.POINTER(TvmModel)]
+    lib.tvm_pack_mlp_tc.argtypes = [C.POINTER(TvmModel), vp, vp]
+    lib.tvm_workspace_bytes.argtypes = [i32, i32, C.POINTER(C.c_size_t)]
+    lib.tvm_forward.argtypes = [C.POINTER(TvmModel), vp, i32, i32, vp, u32, vp, vp, C.POINTER(TvmAux), vp, vp,
+                                C.c_size_t, vp]
+    lib.tvm_backward.argtypes = [C.POINTER(TvmModel), vp, i32, i32, vp, u32, vp, vp, C.POINTER(TvmGrads), vp,
+                                 C.c_size_t, vp]
+    lib.tvm_density_alpha.argtypes = [C.POINTER(TvmModel), vp, i32, f32, vp, vp]
+    lib.tvm_mse_loss.argtypes = [vp, vp, i32, f32, vp, vp, vp]
+    for name in EXPORTS:
+        if name not in ("tvm_last_error", "tvm_tc_weights_bytes"):
+            getattr(lib, name).restype = i32
+    if lib.tvm_abi_version() != ABI_VERSION:
+        raise TvmError(f"libtvmrender.so ABI {lib.tvm_abi_version()} != binding ABI {ABI_VERSION}: rebuild")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = load().tvm_last_error().decode("utf-8", "replace")
+        raise TvmError(f"{what} failed (rc={rc}): {msg}")
+
+
+def require_cuda():
+    """Fail loudly when there is no GPU: the product path has no CPU implementation."""
+    lib = load()
+    n = lib.tvm_device_count()
+    if n <= 0:
+        raise TvmError("no CUDA device visible to libtvmrender.so "
+                       f"({lib.tvm_last_error().decode('utf-8', 'replace')}); there is no CPU fallback")
+    return n

@@ -1,0 +1,117 @@
+// Shared declarations of libtvmrender's translation units (workspace carve-up, launch params).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "tvm_math.cuh"
+
+namespace tvm {
+
+void set_error(const char* fmt, ...);
+
+#define TVM_CHECK_CUDA(expr)                                                         \
+  do {                                                                               \
+    cudaError_t _e = (expr);                                                         \
+    if (_e != cudaSuccess) {                                                         \
+      tvm::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return -2;                                                                     \
+    }                                                                                \
+  } while (0)
+
+#define TVM_REQUIRE(cond, ...)        \
+  do {                                \
+    if (!(cond)) {                    \
+      tvm::set_error(__VA_ARGS__);    \
+      return -1;                      \
+    }                                 \
+  } while (0)
+
+constexpr int kMaxAppDim = 32;     // basis outputs are padded to 32 columns
+constexpr int kFeatureC = 128;     // MLP width the kernels are specialised for
+constexpr float kErtEps = 1e-7f;   // early ray termination: remaining weight mass < 1e-7
+
+// Scratch layout for n rays x S samples (all offsets 256-byte aligned).  Entries are the samples
+// with weight > thres, appended block-of-32-samples at a time; (blk_mask, blk_base) map a
+// (ray, sample-block) back to its entries so that compositing and the backward pass stay in
+// ray/sample order without a sort.
+struct Workspace {
+  uint32_t* n_entries;   // [1] (+ padding)
+  uint32_t* blk_mask;    // [n][NB]   app_mask bits of each 32-sample block
+  uint32_t* blk_base;    // [n][NB]   first entry index of the block
+  uint2* ent;            // [cap]     (ray, sample index)
+  float* ent_w;          // [cap]     weight
+  float* ent_rgb;        // [cap][3]  per-sample colour written by the appearance stage
+  float* acc;            // [n]       acc_map
+  float* rgb_sum;        // [n][3]    sum_s w * rgb (before white background / clamp)
+  float* bwd_scratch;    // [n][4]    per-ray scratch of the backward pass
+  uint32_t cap;
+  int NB;
+  size_t bytes;
+};
+
+inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+inline Workspace carve_workspace(void* base, int n, int S) {
+  Workspace w;
+  char* p = (char*)base;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    char* r = p ? p + off : nullptr;
+    off += align256(bytes);
+    return r;
+  };
+  w.NB = (S + 31) / 32;
+  w.cap = (uint32_t)((size_t)n * (size_t)S);
+  w.n_entries = (uint32_t*)take(256);
+  w.blk_mask = (uint32_t*)take((size_t)n * w.NB * 4);
+  w.blk_base = (uint32_t*)take((size_t)n * w.NB * 4);
+  w.ent = (uint2*)take((size_t)w.cap * 8);
+  w.ent_w = (float*)take((size_t)w.cap * 4);
+  w.ent_rgb = (float*)take((size_t)w.cap * 12);
+  w.acc = (float*)take((size_t)n * 4);
+  w.rgb_sum = (float*)take((size_t)n * 12);
+  w.bwd_scratch = (float*)take((size_t)n * 16);
+  w.bytes = off;
+  return w;
+}
+
+struct FwdParams {
+  TvmModel m;
+  const float* rays;
+  const float* jitter;
+  int n, S, NB;
+  uint32_t flags;
+  Workspace ws;
+  float* rgb_map;
+  float* depth_map;
+  TvmAux aux;
+  unsigned long long* counters;
+  int in_mlp_c;   // 2*view_pe*3 + 2*fea_pe*app_dim + 3 + app_dim
+  int hs, xs;     // smem row strides of the appearance tile
+};
+
+inline int in_mlp_c(const TvmModel& m) { return 2 * m.view_pe * 3 + 2 * m.fea_pe * m.app_dim + 3 + m.app_dim; }
+
+int validate_model(const TvmModel& m);
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Entry (ray, k) -> un-normalised grid coordinates, with exactly the arithmetic of the march kernel.
+__device__ __forceinline__ void entry_coords(const TvmModel& m, const float* rays, const float* jitter,
+                                             uint32_t ray, uint32_t k, float u[3], float dir[3]) {
+  RayMarch r;
+  ray_setup(m, rays + 6 * (size_t)ray, jitter ? jitter[ray] : 0.0f, r);
+  float z = sample_z(m, r, (int)k);
+  float p[3];
+  sample_point(m, r, z, p);
+  grid_coords(m, p, u);
+  dir[0] = r.d[0];
+  dir[1] = r.d[1];
+  dir[2] = r.d[2];
+}
+
+}  // namespace tvm

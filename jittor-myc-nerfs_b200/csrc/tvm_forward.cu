@@ -1,0 +1,460 @@
+// Forward pass of the TensoRF-VM ray renderer (TensorBase.execute, tensorf-myc/models/tensorBase.py:476-536).
+//
+//   k_march      one warp per ray, lanes = 32 consecutive samples: sample_ray (:340-360), bbox mask,
+//                AlphaGridMask test on the bit-packed volume (:39-59), density gather over the three
+//                plane x line factors (tensoRF.py:209-225), softplus (:444-448), raw2alpha with a warp
+//                prefix product (:17-24), weight threshold (:513), acc/depth reductions (:520-531), early
+//                ray termination, and appends the weighted samples to the appearance entry list.
+//   k_app_simt   appearance head in fp32 for a tile of 64 entries: 48-channel gathers
+//                (tensoRF.py:228-244), basis_mat, positional encoding and MLPRender_Fea (:62-86, 9-15).
+//   k_composite  one warp per ray: rgb_map = clamp(sum w*rgb + (1-acc)) in sample order (:521-528).
+//
+// The tcgen05 tensor-core appearance head lives in tvm_mlp_tc.cu and replaces k_app_simt when
+// TVM_MLP_BF16 / TVM_MLP_BF16X3 is requested.
+#include "tvm_common.cuh"
+
+namespace tvm {
+
+constexpr int kMarchWarps = 8;
+
+// ------------------------------------------------------------------------------------------------
+// k_march
+// ------------------------------------------------------------------------------------------------
+template <bool AUX>
+__global__ void __launch_bounds__(kMarchWarps * 32) k_march(const FwdParams P) {
+  __shared__ float s_u[kMarchWarps][32][3];
+  __shared__ float s_f[kMarchWarps][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ray = blockIdx.x * kMarchWarps + warp;
+  if (ray >= P.n) return;
+  const TvmModel& m = P.m;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+
+  RayMarch r;
+  ray_setup(m, P.rays + 6 * (size_t)ray, P.jitter ? P.jitter[ray] : 0.0f, r);
+
+  const int C = m.n_density;
+  const int S = P.S;
+  const bool ert = !AUX && !(P.flags & TVM_NO_ERT);
+  float T = 1.0f, acc = 0.0f, dep = 0.0f;
+  bool seen = false;
+  uint32_t c_in = 0, c_v = 0, c_a = 0;
+
+  for (int b = 0; b < P.NB; ++b) {
+    const int k = b * 32 + lane;
+    const float z = sample_z(m, r, k);
+    float p[3];
+    bool inside = sample_point(m, r, z, p) && (k < S);
+    const uint32_t in_bits = __ballot_sync(0xffffffffu, inside);
+    if (AUX && lane == 0 && P.aux.bbox_bits) P.aux.bbox_bits[(size_t)ray * P.NB + b] = in_bits;
+    if (in_bits == 0) {
+      // per-axis monotonicity of o + d*z in k makes the in-box samples one contiguous run:
+      // an empty block after a non-empty one means the ray has left the box for good.
+      if (seen) break;
+      continue;
+    }
+    seen = true;
+    c_in += __popc(in_bits);
+
+    bool valid = inside;
+    if (m.alpha_bits != nullptr && inside) valid = alpha_mask_test(m, m.alpha_bits, p);
+    const uint32_t v_bits = __ballot_sync(0xffffffffu, valid);
+    if (AUX && lane == 0 && P.aux.valid_bits) P.aux.valid_bits[(size_t)ray * P.NB + b] = v_bits;
+
+    float sigma = 0.0f;
+    if (v_bits != 0) {
+      const int nv = __popc(v_bits);
+      c_v += nv;
+      const int rank = __popc(v_bits & lt_mask);
+      if (valid) {
+        float u[3];
+        grid_coords(m, p, u);
+        s_u[warp][rank][0] = u[0];
+        s_u[warp][rank][1] = u[1];
+        s_u[warp][rank][2] = u[2];
+      }
+      __syncwarp();
+      // 4 lanes per sample, one float4 of channels each: a tap is one 64-byte segment
+      const int q = lane & 3;
+      for (int g = 0; g < nv; g += 8) {
+        const int j = g + (lane >> 2);
+        float part = 0.0f;
+        if (j < nv) {
+          Axis ax[3];
+#pragma unroll
+          for (int i = 0; i < 3; ++i) ax[i] = axis_taps(s_u[warp][j][i], m.grid[i]);
+#pragma unroll
+          for (int kk = 0; kk < 3; ++kk) {
+            const VmTaps t = vm_taps(m, ax, kk);
+            for (int c = q * 4; c < C; c += 16) {
+              float4 pv, lv;
+              vm_sample4(m.density_plane[kk], m.density_line[kk], t, C, c, pv, lv);
+              part += pv.x * lv.x + pv.y * lv.y + pv.z * lv.z + pv.w * lv.w;
+            }
+          }
+        }
+        part += __shfl_xor_sync(0xffffffffu, part, 1);
+        part += __shfl_xor_sync(0xffffffffu, part, 2);
+        if (j < nv && q == 0) s_f[warp][j] = part;
+      }
+      __syncwarp();
+      if (valid) sigma = feature2density(m, s_f[warp][rank]);
+      __syncwarp();
+    }
+
+    // raw2alpha: dists = z[k+1]-z[k] (last sample 0), scaled by distance_scale (:488, :511)
+    const float z1 = sample_z(m, r, k + 1);
+    const float dist = (k < S - 1) ? TVM_MUL(TVM_SUB(z1, z), m.distance_scale) : 0.0f;
+    const float alpha = TVM_SUB(1.0f, expf(TVM_MUL(-sigma, dist)));
+    const float v = TVM_ADD(TVM_SUB(1.0f, alpha), 1e-10f);
+    float pref = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      float t = __shfl_up_sync(0xffffffffu, pref, o);
+      if (lane >= o) pref *= t;
+    }
+    float excl = __shfl_up_sync(0xffffffffu, pref, 1);
+    if (lane == 0) excl = 1.0f;
+    const float w = alpha * (T * excl);
+    T = T * __shfl_sync(0xffffffffu, pref, 31);
+    acc += w;
+    dep += w * z;
+
+    const bool app = w > m.weight_thres;
+    const uint32_t a_bits = __ballot_sync(0xffffffffu, app);
+    if (a_bits != 0) {
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(P.ws.n_entries, (uint32_t)__popc(a_bits));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (app) {
+        const uint32_t e = base + __popc(a_bits & lt_mask);
+        P.ws.ent[e] = make_uint2((uint32_t)ray, (uint32_t)k);
+        P.ws.ent_w[e] = w;
+      }
+      if (lane == 0) {
+        P.ws.blk_mask[(size_t)ray * P.NB + b] = a_bits;
+        P.ws.blk_base[(size_t)ray * P.NB + b] = base;
+      }
+      c_a += __popc(a_bits);
+    }
+    if (AUX) {
+      if (k < S) {
+        if (P.aux.sigma) P.aux.sigma[(size_t)ray * S + k] = sigma;
+        if (P.aux.weight) P.aux.weight[(size_t)ray * S + k] = w;
+      }
+      if (lane == 0 && P.aux.app_bits) P.aux.app_bits[(size_t)ray * P.NB + b] = a_bits;
+    }
+    if (ert && T < kErtEps) break;
+    if (!(in_bits >> 31)) break;  // last lane already outside: the run of in-box samples has ended
+  }
+
+  acc = warp_sum(acc);
+  dep = warp_sum(dep);
+  if (lane == 0) {
+    P.ws.acc[ray] = acc;
+    // depth_map = sum(w*z) + (1-acc) * rays_chunk[..., -1]  -- column 5 (d_z), reference quirk (:531)
+    P.depth_map[ray] = dep + (1.0f - acc) * r.d[2];
+    if (AUX && P.aux.acc_map) P.aux.acc_map[ray] = acc;
+    if (P.counters) {
+      atomicAdd(&P.counters[TVM_CNT_M_IN], (unsigned long long)c_in);
+      atomicAdd(&P.counters[TVM_CNT_M_V], (unsigned long long)c_v);
+      atomicAdd(&P.counters[TVM_CNT_M_A], (unsigned long long)c_a);
+      if (c_v) atomicAdd(&P.counters[TVM_CNT_RAYS], 1ull);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_app_simt: appearance head, fp32 FMA path (parity mode)
+// ------------------------------------------------------------------------------------------------
+constexpr int kAppTile = 64;
+constexpr int kAppThreads = 256;
+
+__device__ __forceinline__ void fma4(float* acc, float x, const float4 w) {
+  acc[0] = fmaf(x, w.x, acc[0]);
+  acc[1] = fmaf(x, w.y, acc[1]);
+  acc[2] = fmaf(x, w.z, acc[2]);
+  acc[3] = fmaf(x, w.w, acc[3]);
+}
+
+// Gathers the 3*Ca appearance product vector of one tile into H (row stride hs) and the view
+// directions into X[.., app_dim .. app_dim+3).  8 warps x 8 entries, 4 lanes per entry.
+__device__ __forceinline__ void app_gather_tile(const FwdParams& P, uint32_t tile_base, uint32_t n_ent,
+                                                float* H, float* X) {
+  const TvmModel& m = P.m;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int Ca = m.n_app;
+  const int row = warp * 8 + (lane >> 2), q = lane & 3;
+  const uint32_t e = tile_base + row;
+  float* h = H + row * P.hs;
+  if (e < n_ent) {
+    const uint2 en = P.ws.ent[e];
+    float u[3], dir[3];
+    entry_coords(m, P.rays, P.jitter, en.x, en.y, u, dir);
+    Axis ax[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) ax[i] = axis_taps(u[i], m.grid[i]);
+#pragma unroll
+    for (int kk = 0; kk < 3; ++kk) {
+      const VmTaps t = vm_taps(m, ax, kk);
+      for (int c = q * 4; c < Ca; c += 16) {
+        float4 pv, lv;
+        vm_sample4(m.app_plane[kk], m.app_line[kk], t, Ca, c, pv, lv);
+        float* o = h + kk * Ca + c;
+        o[0] = pv.x * lv.x;
+        o[1] = pv.y * lv.y;
+        o[2] = pv.z * lv.z;
+        o[3] = pv.w * lv.w;
+      }
+    }
+    if (q < 3) X[row * P.xs + m.app_dim + q] = dir[q];
+  } else {
+    for (int c = q; c < 3 * Ca; c += 4) h[c] = 0.0f;
+    if (q < 3) X[row * P.xs + m.app_dim + q] = 0.0f;
+  }
+}
+
+// basis_mat + positional encoding: thread (row, part) owns basis outputs [part*8, part*8+8)
+__device__ __forceinline__ void app_basis_pe(const FwdParams& P, const float* H, float* X) {
+  const TvmModel& m = P.m;
+  const int row = threadIdx.x & (kAppTile - 1), part = threadIdx.x >> 6;
+  const int K = 3 * m.n_app;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
+  const float* h = H + row * P.hs;
+  const float* bt = m.basis_t + part * 8;
+  for (int j = 0; j < K; ++j) {
+    const float x = h[j];
+    fma4(acc, x, ldg4(bt + j * kMaxAppDim));
+    fma4(acc + 4, x, ldg4(bt + j * kMaxAppDim + 4));
+  }
+  float* xr = X + row * P.xs;
+  const int pe_f = m.app_dim + 3;                       // start of sin(PE(features))
+  const int pe_v = pe_f + 2 * m.fea_pe * m.app_dim;     // start of sin(PE(viewdirs))
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int o = part * 8 + i;
+    if (o < m.app_dim) {
+      const float f = acc[i];
+      xr[o] = f;
+      float fr = 1.0f;
+      for (int q = 0; q < m.fea_pe; ++q, fr *= 2.0f) {
+        const float s = f * fr;
+        xr[pe_f + o * m.fea_pe + q] = sinf(s);
+        xr[pe_f + m.fea_pe * m.app_dim + o * m.fea_pe + q] = cosf(s);
+      }
+    }
+  }
+  if (part == 3) {
+    for (int c = 0; c < 3; ++c) {
+      const float d = xr[m.app_dim + c];
+      float fr = 1.0f;
+      for (int q = 0; q < m.view_pe; ++q, fr *= 2.0f) {
+        const float s = d * fr;
+        xr[pe_v + c * m.view_pe + q] = sinf(s);
+        xr[pe_v + 3 * m.view_pe + c * m.view_pe + q] = cosf(s);
+      }
+    }
+  }
+}
+
+// y[row][part*32 .. +32) = relu(x[row][0..K) @ Wt[K][128] + b): thread (row, part)
+__device__ __forceinline__ void app_dense_relu(const float* __restrict__ Wt, const float* __restrict__ bias,
+                                               const float* xin, int xstride, int K, float* yout, int ystride) {
+  const int row = threadIdx.x & (kAppTile - 1), part = threadIdx.x >> 6;
+  float acc[32];
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {
+    const float4 b = ldg4(bias + part * 32 + i);
+    acc[i] = b.x; acc[i + 1] = b.y; acc[i + 2] = b.z; acc[i + 3] = b.w;
+  }
+  const float* x = xin + row * xstride;
+  const float* w = Wt + part * 32;
+  for (int j = 0; j < K; ++j) {
+    const float xv = x[j];
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) fma4(acc + i, xv, ldg4(w + (size_t)j * kFeatureC + i));
+  }
+  float* y = yout + row * ystride + part * 32;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) y[i] = fmaxf(acc[i], 0.0f);
+}
+
+__global__ void __launch_bounds__(kAppThreads) k_app_simt(const FwdParams P) {
+  extern __shared__ float smem[];
+  float* H = smem;                       // [64][hs]: appearance vector, then layer-1 output
+  float* X = smem + kAppTile * P.hs;     // [64][xs]: MLP input, then layer-2 output
+  const TvmModel& m = P.m;
+  const uint32_t n_ent = *P.ws.n_entries;
+  const uint32_t n_tiles = (n_ent + kAppTile - 1) / kAppTile;
+  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const uint32_t tile_base = tile * kAppTile;
+    app_gather_tile(P, tile_base, n_ent, H, X);
+    __syncthreads();
+    app_basis_pe(P, H, X);
+    __syncthreads();
+    app_dense_relu(m.w1_t, m.b1, X, P.xs, P.in_mlp_c, H, P.hs);
+    __syncthreads();
+    app_dense_relu(m.w2_t, m.b2, H, P.hs, kFeatureC, X, P.xs);
+    __syncthreads();
+    {
+      const int row = threadIdx.x & (kAppTile - 1), part = threadIdx.x >> 6;
+      const uint32_t e = tile_base + row;
+      if (part < 3 && e < n_ent) {
+        float a = m.b3[part];
+        const float* x = X + row * P.xs;
+        const float* w = m.w3 + part * kFeatureC;
+        for (int j = 0; j < kFeatureC; ++j) a = fmaf(x[j], __ldg(w + j), a);
+        P.ws.ent_rgb[(size_t)e * 3 + part] = 1.0f / (1.0f + expf(-a));
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_composite
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_composite(const FwdParams P) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ray = blockIdx.x * 8 + warp;
+  if (ray >= P.n) return;
+  float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f;
+  for (int b = lane; b < P.NB; b += 32) {
+    uint32_t bits = P.ws.blk_mask[(size_t)ray * P.NB + b];
+    if (bits == 0) continue;
+    uint32_t e = P.ws.blk_base[(size_t)ray * P.NB + b];
+    while (bits) {
+      const int s = __ffs(bits) - 1;
+      bits &= bits - 1;
+      const float w = P.ws.ent_w[e];
+      const float r = P.ws.ent_rgb[(size_t)e * 3 + 0];
+      const float g = P.ws.ent_rgb[(size_t)e * 3 + 1];
+      const float bl = P.ws.ent_rgb[(size_t)e * 3 + 2];
+      s0 = fmaf(w, r, s0);
+      s1 = fmaf(w, g, s1);
+      s2 = fmaf(w, bl, s2);
+      if (P.aux.rgb) {
+        float* o = P.aux.rgb + ((size_t)ray * P.S + (size_t)b * 32 + s) * 3;
+        o[0] = r; o[1] = g; o[2] = bl;
+      }
+      ++e;
+    }
+  }
+  s0 = warp_sum(s0);
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  if (lane == 0) {
+    const float acc = P.ws.acc[ray];
+    P.ws.rgb_sum[(size_t)ray * 3 + 0] = s0;
+    P.ws.rgb_sum[(size_t)ray * 3 + 1] = s1;
+    P.ws.rgb_sum[(size_t)ray * 3 + 2] = s2;
+    const float bg = (P.flags & TVM_WHITE_BG) ? (1.0f - acc) : 0.0f;
+    P.rgb_map[(size_t)ray * 3 + 0] = fminf(fmaxf(s0 + bg, 0.0f), 1.0f);
+    P.rgb_map[(size_t)ray * 3 + 1] = fminf(fmaxf(s1 + bg, 0.0f), 1.0f);
+    P.rgb_map[(size_t)ray * 3 + 2] = fminf(fmaxf(s2 + bg, 0.0f), 1.0f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+int launch_app_tc(const FwdParams& P, int num_sms, cudaStream_t stream);   // tvm_mlp_tc.cu
+
+int fill_fwd_params(FwdParams& P, const TvmModel* m, const float* rays, int n, int S, const float* jitter,
+                    uint32_t flags, void* ws, size_t ws_bytes) {
+  TVM_REQUIRE(m && rays && ws, "null argument");
+  TVM_REQUIRE(n > 0 && S > 0, "n_rays and n_samples must be positive");
+  if (int rc = validate_model(*m)) return rc;
+  P.m = *m;
+  P.rays = rays;
+  P.jitter = jitter;
+  P.n = n;
+  P.S = S;
+  P.flags = flags;
+  P.ws = carve_workspace(ws, n, S);
+  TVM_REQUIRE(P.ws.bytes <= ws_bytes, "workspace too small: need %zu bytes, got %zu", P.ws.bytes, ws_bytes);
+  TVM_REQUIRE(((uintptr_t)ws & 255) == 0, "workspace must be 256-byte aligned");
+  P.NB = P.ws.NB;
+  P.in_mlp_c = in_mlp_c(*m);
+  int hs = max(3 * m->n_app, kFeatureC) + 1;
+  int xs = max(P.in_mlp_c, kFeatureC) + 1;
+  P.hs = hs | 1;
+  P.xs = xs | 1;
+  P.counters = nullptr;
+  P.aux = TvmAux{};
+  return 0;
+}
+
+static int device_sms() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+}  // namespace tvm
+
+using namespace tvm;
+
+extern "C" int tvm_workspace_bytes(int n_rays, int n_samples, size_t* out_bytes) {
+  TVM_REQUIRE(out_bytes && n_rays > 0 && n_samples > 0, "bad arguments");
+  TVM_REQUIRE((double)n_rays * n_samples < 4.0e9, "n_rays*n_samples must fit 32 bits; split the rays");
+  *out_bytes = carve_workspace(nullptr, n_rays, n_samples).bytes;
+  return 0;
+}
+
+extern "C" int tvm_forward(const TvmModel* m_host, const float* rays, int n_rays, int n_samples,
+                           const float* jitter, uint32_t flags, float* rgb_map, float* depth_map,
+                           const TvmAux* aux_host, uint64_t* counters, void* ws, size_t ws_bytes,
+                           void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  FwdParams P;
+  if (int rc = fill_fwd_params(P, m_host, rays, n_rays, n_samples, jitter, flags, ws, ws_bytes)) return rc;
+  TVM_REQUIRE(rgb_map && depth_map, "null output");
+  P.rgb_map = rgb_map;
+  P.depth_map = depth_map;
+  P.counters = (unsigned long long*)counters;
+  const bool has_aux = aux_host != nullptr;
+  if (has_aux) P.aux = *aux_host;
+  const size_t nb_bytes = (size_t)n_rays * P.NB * 4;
+  TVM_CHECK_CUDA(cudaMemsetAsync(P.ws.n_entries, 0, 256, stream));
+  TVM_CHECK_CUDA(cudaMemsetAsync(P.ws.blk_mask, 0, nb_bytes, stream));
+  if (has_aux) {
+    if (P.aux.bbox_bits) TVM_CHECK_CUDA(cudaMemsetAsync(P.aux.bbox_bits, 0, nb_bytes, stream));
+    if (P.aux.valid_bits) TVM_CHECK_CUDA(cudaMemsetAsync(P.aux.valid_bits, 0, nb_bytes, stream));
+    if (P.aux.app_bits) TVM_CHECK_CUDA(cudaMemsetAsync(P.aux.app_bits, 0, nb_bytes, stream));
+    if (P.aux.sigma) TVM_CHECK_CUDA(cudaMemsetAsync(P.aux.sigma, 0, (size_t)n_rays * n_samples * 4, stream));
+    if (P.aux.weight) TVM_CHECK_CUDA(cudaMemsetAsync(P.aux.weight, 0, (size_t)n_rays * n_samples * 4, stream));
+    if (P.aux.rgb) TVM_CHECK_CUDA(cudaMemsetAsync(P.aux.rgb, 0, (size_t)n_rays * n_samples * 12, stream));
+  }
+  const int march_blocks = (n_rays + kMarchWarps - 1) / kMarchWarps;
+  if (has_aux)
+    k_march<true><<<march_blocks, kMarchWarps * 32, 0, stream>>>(P);
+  else
+    k_march<false><<<march_blocks, kMarchWarps * 32, 0, stream>>>(P);
+  TVM_CHECK_CUDA(cudaGetLastError());
+
+  const uint32_t mlp = flags & TVM_MLP_MASK;
+  if (mlp == TVM_MLP_FP32) {
+    const size_t smem = (size_t)kAppTile * (P.hs + P.xs) * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+      TVM_CHECK_CUDA(cudaFuncSetAttribute(k_app_simt, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr_set = true;
+    }
+    TVM_REQUIRE(smem <= 200 * 1024, "appearance tile does not fit shared memory");
+    k_app_simt<<<device_sms() * 2, kAppThreads, smem, stream>>>(P);
+    TVM_CHECK_CUDA(cudaGetLastError());
+  } else {
+    if (int rc = launch_app_tc(P, device_sms(), stream)) return rc;
+  }
+  k_composite<<<(n_rays + 7) / 8, 256, 0, stream>>>(P);
+  TVM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

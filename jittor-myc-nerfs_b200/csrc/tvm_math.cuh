@@ -1,0 +1,217 @@
+// Per-sample arithmetic of the TensoRF-VM ray path, shared by every kernel.
+//
+// Everything that decides an INTEGER result (in-bbox mask, alpha-mask bit, tap indices) is written
+// with explicitly rounded fp32 operations (no FMA contraction) in exactly the operation order of the
+// reference python (tensorf-myc/models/tensorBase.py:340-360, 39-59, 223-224 and Jittor's
+// grid_sample index arithmetic, assumption A1 of SURVEY.md §8c), so that mask bits and gathered
+// texel indices are bit-identical to the oracle.  The functions are __host__ __device__ so that
+// tests/host_emul can exercise the same source on the CPU-only build container.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include "../../include/tvmrender.h"
+
+#if defined(__CUDACC__)
+#define TVM_HD __host__ __device__ __forceinline__
+#else
+#define TVM_HD static inline
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define TVM_ADD(a, b) __fadd_rn((a), (b))
+#define TVM_SUB(a, b) __fsub_rn((a), (b))
+#define TVM_MUL(a, b) __fmul_rn((a), (b))
+#define TVM_DIV(a, b) __fdiv_rn((a), (b))
+#else
+// host build is compiled with -ffp-contract=off; plain operators are single IEEE roundings
+#define TVM_ADD(a, b) ((float)((float)(a) + (float)(b)))
+#define TVM_SUB(a, b) ((float)((float)(a) - (float)(b)))
+#define TVM_MUL(a, b) ((float)((float)(a) * (float)(b)))
+#define TVM_DIV(a, b) ((float)((float)(a) / (float)(b)))
+#endif
+
+namespace tvm {
+
+// matMode / vecMode of tensorBase.py:168-169: plane k spans axes (M0[k] -> W, M1[k] -> H), line k axis V[k]
+TVM_HD int mat0(int k) { return k == 2 ? 1 : 0; }
+TVM_HD int mat1(int k) { return k == 0 ? 1 : 2; }
+TVM_HD int vecax(int k) { return 2 - k; }
+
+struct RayMarch {
+  float o[3], d[3];
+  float t_min;   // entry distance clamped to [near, far]      (tensorBase.py:345-348)
+  float jit;     // per-ray jitter (0 when !is_train)           (tensorBase.py:351-353)
+};
+
+// tensorBase.py:344-348
+TVM_HD void ray_setup(const TvmModel& m, const float* ray6, float jit, RayMarch& r) {
+  float t = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    r.o[i] = ray6[i];
+    r.d[i] = ray6[3 + i];
+    float vec = (r.d[i] == 0.0f) ? 1e-6f : r.d[i];
+    float ra = TVM_DIV(TVM_SUB(m.aabb[3 + i], r.o[i]), vec);
+    float rb = TVM_DIV(TVM_SUB(m.aabb[i], r.o[i]), vec);
+    float mn = fminf(ra, rb);
+    t = fmaxf(t, mn);
+  }
+  t = fminf(fmaxf(t, m.near_), m.far_);
+  r.t_min = t;
+  r.jit = jit;
+}
+
+// z_k = t_min + stepSize * (k + jitter)                        (tensorBase.py:350-355)
+TVM_HD float sample_z(const TvmModel& m, const RayMarch& r, int k) {
+  float rng = TVM_ADD((float)k, r.jit);
+  return TVM_ADD(r.t_min, TVM_MUL(m.step_size, rng));
+}
+
+// pts = o + d * z ; returns true when the point is inside the bbox (strict > on both faces)
+TVM_HD bool sample_point(const TvmModel& m, const RayMarch& r, float z, float p[3]) {
+  bool out = false;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    p[i] = TVM_ADD(r.o[i], TVM_MUL(r.d[i], z));
+    out = out || (m.aabb[i] > p[i]) || (p[i] > m.aabb[3 + i]);
+  }
+  return !out;
+}
+
+// grid_sample index arithmetic (A1, align_corners=True): u = ((c + 1) / 2) * (size - 1)
+TVM_HD float unnormalize(float c, int size) {
+  return TVM_MUL(TVM_MUL(TVM_ADD(c, 1.0f), 0.5f), (float)(size - 1));
+}
+
+// One interpolation axis: lower/upper tap index (clamped into range) and their weights;
+// a tap that falls outside [0,size-1] gets weight 0 (zeros padding).
+struct Axis {
+  int i0, i1;
+  float w0, w1;
+};
+TVM_HD Axis axis_taps(float u, int size) {
+  Axis a;
+  float f = floorf(u);
+  a.w0 = TVM_SUB(TVM_ADD(f, 1.0f), u);
+  a.w1 = TVM_SUB(u, f);
+  int i = (int)f;
+  if (i < 0 || i > size - 1) a.w0 = 0.0f;
+  if (i + 1 < 0 || i + 1 > size - 1) a.w1 = 0.0f;
+  a.i0 = min(max(i, 0), size - 1);
+  a.i1 = min(max(i + 1, 0), size - 1);
+  return a;
+}
+
+// AlphaGridMask.sample_alpha(...) > 0                          (tensorBase.py:50-59, 491-493)
+// With a non-negative volume the trilinear value is > 0 iff some in-range corner with a non-zero
+// product weight has its bit set (the product cannot underflow: each factor is 0 or >= 2^-25*(size-1)).
+TVM_HD bool alpha_mask_test(const TvmModel& m, const uint32_t* __restrict__ bits, const float p[3]) {
+  Axis ax[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    float c = TVM_SUB(TVM_MUL(TVM_SUB(p[i], m.alpha_aabb_min[i]), m.alpha_inv_size[i]), 1.0f);
+    ax[i] = axis_taps(unnormalize(c, m.alpha_grid[i]), m.alpha_grid[i]);
+  }
+  const int W = m.alpha_grid[0], H = m.alpha_grid[1];
+  bool hit = false;
+#pragma unroll
+  for (int cz = 0; cz < 2; ++cz) {
+    float wz = cz ? ax[2].w1 : ax[2].w0;
+    int z = cz ? ax[2].i1 : ax[2].i0;
+#pragma unroll
+    for (int cy = 0; cy < 2; ++cy) {
+      float wy = cy ? ax[1].w1 : ax[1].w0;
+      int y = cy ? ax[1].i1 : ax[1].i0;
+#pragma unroll
+      for (int cx = 0; cx < 2; ++cx) {
+        float wx = cx ? ax[0].w1 : ax[0].w0;
+        int x = cx ? ax[0].i1 : ax[0].i0;
+        bool w_nz = (wx > 0.0f) && (wy > 0.0f) && (wz > 0.0f);
+        uint32_t idx = ((uint32_t)z * (uint32_t)H + (uint32_t)y) * (uint32_t)W + (uint32_t)x;
+        uint32_t word = bits[idx >> 5];
+        hit = hit || (w_nz && ((word >> (idx & 31u)) & 1u));
+      }
+    }
+  }
+  return hit;
+}
+
+// normalize_coord + unnormalize for the model grids             (tensorBase.py:223-224)
+TVM_HD void grid_coords(const TvmModel& m, const float p[3], float u[3]) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    float c = TVM_SUB(TVM_MUL(TVM_SUB(p[i], m.aabb[i]), m.inv_aabb_size[i]), 1.0f);
+    u[i] = unnormalize(c, m.grid[i]);
+  }
+}
+
+// feature2density                                               (tensorBase.py:444-448; A3)
+TVM_HD float feature2density(const TvmModel& m, float f) {
+  if (m.act == TVM_ACT_RELU) return fmaxf(f, 0.0f);
+  float x = f + m.density_shift;
+  return logf(1.0f + expf(fminf(x, 20.0f))) + fmaxf(x - 20.0f, 0.0f);
+}
+// d softplus / dx of the formula above
+TVM_HD float feature2density_grad(const TvmModel& m, float f) {
+  if (m.act == TVM_ACT_RELU) return f > 0.0f ? 1.0f : 0.0f;
+  float x = f + m.density_shift;
+  if (x > 20.0f) return 1.0f;
+  float e = expf(x);
+  return e / (1.0f + e);
+}
+
+// 16-byte read-only load (texel segments are 16-byte aligned: channel counts are multiples of 4)
+TVM_HD float4 ldg4(const float* p) {
+#if defined(__CUDA_ARCH__)
+  return __ldg(reinterpret_cast<const float4*>(p));
+#else
+  return *reinterpret_cast<const float4*>(p);
+#endif
+}
+
+// Bilinear plane x linear line product for 4 consecutive channels starting at c.
+struct VmTaps {
+  int o00, o01, o10, o11;   // plane texel offsets (in texels)
+  float nw, ne, sw, se;     // (x0,y0) (x1,y0) (x0,y1) (x1,y1) weights, products formed first (A1)
+  int l0, l1;               // line rows
+  float lw0, lw1;
+};
+TVM_HD VmTaps vm_taps(const TvmModel& m, const Axis ax[3], int k) {
+  const Axis& aw = ax[mat0(k)];
+  const Axis& ah = ax[mat1(k)];
+  const Axis& al = ax[vecax(k)];
+  const int W = m.grid[mat0(k)];
+  VmTaps t;
+  t.o00 = ah.i0 * W + aw.i0;
+  t.o01 = ah.i0 * W + aw.i1;
+  t.o10 = ah.i1 * W + aw.i0;
+  t.o11 = ah.i1 * W + aw.i1;
+  t.nw = TVM_MUL(aw.w0, ah.w0);
+  t.ne = TVM_MUL(aw.w1, ah.w0);
+  t.sw = TVM_MUL(aw.w0, ah.w1);
+  t.se = TVM_MUL(aw.w1, ah.w1);
+  t.l0 = al.i0;
+  t.l1 = al.i1;
+  t.lw0 = al.w0;
+  t.lw1 = al.w1;
+  return t;
+}
+TVM_HD void vm_sample4(const float* __restrict__ plane, const float* __restrict__ line,
+                                           const VmTaps& t, int C, int c, float4& pv, float4& lv) {
+  float4 a = ldg4(plane + (size_t)t.o00 * C + c);
+  float4 b = ldg4(plane + (size_t)t.o01 * C + c);
+  float4 cc = ldg4(plane + (size_t)t.o10 * C + c);
+  float4 d = ldg4(plane + (size_t)t.o11 * C + c);
+  float4 l0 = ldg4(line + (size_t)t.l0 * C + c);
+  float4 l1 = ldg4(line + (size_t)t.l1 * C + c);
+  pv.x = a.x * t.nw + b.x * t.ne + cc.x * t.sw + d.x * t.se;
+  pv.y = a.y * t.nw + b.y * t.ne + cc.y * t.sw + d.y * t.se;
+  pv.z = a.z * t.nw + b.z * t.ne + cc.z * t.sw + d.z * t.se;
+  pv.w = a.w * t.nw + b.w * t.ne + cc.w * t.sw + d.w * t.se;
+  lv.x = l0.x * t.lw0 + l1.x * t.lw1;
+  lv.y = l0.y * t.lw0 + l1.y * t.lw1;
+  lv.z = l0.z * t.lw0 + l1.z * t.lw1;
+  lv.w = l0.w * t.lw0 + l1.w * t.lw1;
+}
+
+}  // namespace tvm

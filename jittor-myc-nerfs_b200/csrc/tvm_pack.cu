@@ -1,0 +1,200 @@
+// Parameter upload / layout conversion and small utility entry points of libtvmrender.
+//
+// The reference keeps parameters as Jittor NCHW Vars (tensorf-myc/models/tensoRF.py:154-164); the
+// kernels want channels-last grids (one 64 B / 192 B segment per texel), a bit-packed alpha volume
+// (the reference itself stores it bit-packed on disk, tensorBase.py:253-264) and [in][out] linear
+// weights.  These kernels are pure bandwidth: coalesced on the write side, strided on the read side
+// through a 32x33 shared-memory transpose tile.
+#include <stdarg.h>
+#include <string.h>
+#include "tvm_common.cuh"
+
+namespace tvm {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int validate_model(const TvmModel& m) {
+  TVM_REQUIRE(m.n_density > 0 && m.n_density % 4 == 0, "n_density must be a positive multiple of 4");
+  TVM_REQUIRE(m.n_app > 0 && m.n_app % 4 == 0, "n_app must be a positive multiple of 4");
+  TVM_REQUIRE(m.app_dim > 0 && m.app_dim <= kMaxAppDim, "app_dim must be in 1..32");
+  TVM_REQUIRE(m.feature_c == kFeatureC, "featureC must be 128");
+  TVM_REQUIRE(m.view_pe >= 0 && m.fea_pe >= 0 && m.view_pe <= 8 && m.fea_pe <= 8, "pe out of range");
+  for (int i = 0; i < 3; ++i) {
+    TVM_REQUIRE(m.grid[i] >= 2, "gridSize must be >= 2");
+    TVM_REQUIRE(m.density_plane[i] && m.density_line[i] && m.app_plane[i] && m.app_line[i], "null grid pointer");
+  }
+  TVM_REQUIRE(m.basis_t && m.w1_t && m.b1 && m.w2_t && m.b2 && m.w3 && m.b3, "null MLP pointer");
+  if (m.alpha_bits) {
+    for (int i = 0; i < 3; ++i) TVM_REQUIRE(m.alpha_grid[i] >= 2, "alpha grid must be >= 2");
+  }
+  return 0;
+}
+
+// [C][HW] -> [HW][C]
+__global__ void k_transpose(const float* __restrict__ in, float* __restrict__ out, int rows, int cols) {
+  __shared__ float tile[32][33];
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int r = by + j, c = bx + threadIdx.x;
+    if (r < rows && c < cols) tile[j][threadIdx.x] = in[(size_t)r * cols + c];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = bx + j, r = by + threadIdx.x;
+    if (r < rows && c < cols) out[(size_t)c * rows + r] = tile[threadIdx.x][j];
+  }
+}
+
+static int transpose(const float* in, float* out, int rows, int cols, cudaStream_t s) {
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+  TVM_REQUIRE(grid.y <= 65535, "too many rows for transpose");
+  k_transpose<<<grid, block, 0, s>>>(in, out, rows, cols);
+  TVM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// [out][in] -> [in][out_pad] with zero padding
+__global__ void k_pack_linear(const float* __restrict__ w, int out_c, int in_c, int out_pad, float* __restrict__ t) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= in_c * out_pad) return;
+  const int j = i / out_pad, o = i % out_pad;
+  t[i] = o < out_c ? w[(size_t)o * in_c + j] : 0.0f;
+}
+__global__ void k_unpack_linear(const float* __restrict__ t, int out_c, int in_c, int out_pad, float* __restrict__ w) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= in_c * out_c) return;
+  const int o = i / in_c, j = i % in_c;
+  w[i] = t[(size_t)j * out_pad + o];
+}
+
+// one warp per output word: bit = volume > 0
+__global__ void k_pack_alpha(const float* __restrict__ vol, size_t n_vox, uint32_t* __restrict__ bits) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool on = i < n_vox && vol[i] > 0.0f;
+  const uint32_t word = __ballot_sync(0xffffffffu, on);
+  if ((threadIdx.x & 31) == 0 && (i >> 5) < (n_vox + 31) / 32) bits[i >> 5] = word;
+}
+
+// TensorBase.compute_alpha on arbitrary points (tensorBase.py:451-473): one thread per point.
+__global__ void k_density_alpha(const TvmModel m, const float* __restrict__ xyz, int n, float length,
+                                float* __restrict__ alpha) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float p[3] = {xyz[3 * (size_t)i], xyz[3 * (size_t)i + 1], xyz[3 * (size_t)i + 2]};
+  bool ok = true;
+  if (m.alpha_bits) ok = alpha_mask_test(m, m.alpha_bits, p);
+  float sigma = 0.0f;
+  if (ok) {
+    float u[3];
+    grid_coords(m, p, u);
+    Axis ax[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) ax[a] = axis_taps(u[a], m.grid[a]);
+    float f = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const VmTaps t = vm_taps(m, ax, k);
+      for (int c = 0; c < m.n_density; c += 4) {
+        float4 pv, lv;
+        vm_sample4(m.density_plane[k], m.density_line[k], t, m.n_density, c, pv, lv);
+        f += pv.x * lv.x + pv.y * lv.y + pv.z * lv.z + pv.w * lv.w;
+      }
+    }
+    sigma = feature2density(m, f);
+  }
+  alpha[i] = 1.0f - expf(-sigma * length);
+}
+
+// train.py:228: loss = mean((rgb_map - target)^2); d_rgb_map = grad_scale * 2 (rgb_map - target) / (3n)
+__global__ void k_mse(const float* __restrict__ rgb, const float* __restrict__ tgt, int n3, float gscale,
+                      float* __restrict__ loss, float* __restrict__ d_rgb) {
+  float part = 0.0f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n3; i += gridDim.x * blockDim.x) {
+    const float d = rgb[i] - tgt[i];
+    part += d * d;
+    if (d_rgb) d_rgb[i] = gscale * 2.0f * d / (float)n3;
+  }
+  part = warp_sum(part);
+  if ((threadIdx.x & 31) == 0 && loss) atomicAdd(loss, part / (float)n3);
+}
+
+}  // namespace tvm
+
+using namespace tvm;
+
+extern "C" const char* tvm_last_error(void) { return g_err; }
+extern "C" int tvm_abi_version(void) { return TVM_ABI_VERSION; }
+
+extern "C" int tvm_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    set_error("cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    return -2;
+  }
+  return n;
+}
+
+extern "C" int tvm_pack_grid(const float* nchw, int C, int H, int W, float* out_hwc, void* stream) {
+  TVM_REQUIRE(nchw && out_hwc && C > 0 && H > 0 && W > 0, "bad arguments");
+  return transpose(nchw, out_hwc, C, H * W, (cudaStream_t)stream);
+}
+
+extern "C" int tvm_unpack_grid(const float* hwc, int C, int H, int W, float* out_nchw, void* stream) {
+  TVM_REQUIRE(hwc && out_nchw && C > 0 && H > 0 && W > 0, "bad arguments");
+  return transpose(hwc, out_nchw, H * W, C, (cudaStream_t)stream);
+}
+
+extern "C" int tvm_pack_linear(const float* w, int out_c, int in_c, int out_pad, float* out_t, void* stream) {
+  TVM_REQUIRE(w && out_t && out_c > 0 && in_c > 0 && out_pad >= out_c, "bad arguments");
+  const int n = in_c * out_pad;
+  k_pack_linear<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, out_c, in_c, out_pad, out_t);
+  TVM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tvm_unpack_linear(const float* w_t, int out_c, int in_c, int out_pad, float* out_w, void* stream) {
+  TVM_REQUIRE(w_t && out_w && out_c > 0 && in_c > 0 && out_pad >= out_c, "bad arguments");
+  const int n = in_c * out_c;
+  k_unpack_linear<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w_t, out_c, in_c, out_pad, out_w);
+  TVM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tvm_pack_alpha(const float* volume, int D, int H, int W, uint32_t* bits, void* stream) {
+  TVM_REQUIRE(volume && bits && D > 0 && H > 0 && W > 0, "bad arguments");
+  const size_t n = (size_t)D * H * W;
+  const size_t n_pad = (n + 31) / 32 * 32;
+  k_pack_alpha<<<(unsigned)((n_pad + 255) / 256), 256, 0, (cudaStream_t)stream>>>(volume, n, bits);
+  TVM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tvm_density_alpha(const TvmModel* m_host, const float* xyz, int n_pts, float length,
+                                 float* alpha_out, void* stream) {
+  TVM_REQUIRE(m_host && xyz && alpha_out && n_pts > 0, "bad arguments");
+  if (int rc = validate_model(*m_host)) return rc;
+  k_density_alpha<<<(n_pts + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*m_host, xyz, n_pts, length, alpha_out);
+  TVM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tvm_mse_loss(const float* rgb_map, const float* target, int n_rays, float grad_scale,
+                            float* loss_out, float* d_rgb_map, void* stream) {
+  TVM_REQUIRE(rgb_map && target && n_rays > 0, "bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (loss_out) TVM_CHECK_CUDA(cudaMemsetAsync(loss_out, 0, 4, s));
+  const int n3 = n_rays * 3;
+  int blocks = (n3 + 255) / 256;
+  if (blocks > 1184) blocks = 1184;
+  k_mse<<<blocks, 256, 0, s>>>(rgb_map, target, n3, grad_scale, loss_out, d_rgb_map);
+  TVM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

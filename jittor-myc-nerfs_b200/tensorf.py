@@ -1,0 +1,504 @@
+"""Host-side mirror of tensorf-myc's TensorVMSplit / AlphaGridMask for the ray-rendering hot path.
+
+Same constructor keywords, attribute names, parameter names/shapes and call signature as the
+reference (tensorf-myc/models/tensorBase.py:140-176, 476-536; models/tensoRF.py:141-174), so the
+reference's driver code (train.py:167-173, renderer.py:12-27) can hold this object instead.
+All arithmetic happens in libtvmrender.so (hand-written sm_100a kernels, include/tvmrender.h);
+torch is used for device memory, streams and autograd bookkeeping only.  No CPU path exists.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+MAT_MODE = [[0, 1], [0, 2], [1, 2]]   # tensorBase.py:168
+VEC_MODE = [2, 1, 0]                  # tensorBase.py:169
+
+_MLP_FLAGS = {"fp32": L.MLP_FP32, "bf16": L.MLP_BF16, "bf16x3": L.MLP_BF16X3}
+
+
+def derive_march_scalars(aabb, gridSize, step_ratio):
+    """TensorBase.update_stepSize (tensorBase.py:197-209) in fp32, op for op."""
+    f32 = np.float32
+    aabb = np.asarray(aabb, dtype=f32).reshape(2, 3)
+    aabbSize = aabb[1] - aabb[0]
+    invaabbSize = f32(2.0) / aabbSize
+    g = np.asarray([int(i) for i in gridSize], dtype=np.int32)
+    units = aabbSize / (g - 1).astype(f32)
+    stepSize = f32(np.mean(units, dtype=f32) * f32(step_ratio))
+    aabbDiag = np.sqrt(np.sum(np.power(aabbSize, f32(2)), dtype=f32), dtype=f32)
+    nSamples = int(f32(aabbDiag / stepSize)) + 1
+    return dict(aabbSize=aabbSize, invaabbSize=invaabbSize.astype(f32), gridSize=g, units=units,
+                stepSize=stepSize, aabbDiag=aabbDiag, nSamples=nSamples)
+
+
+def _stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class AlphaGridMask:
+    """tensorBase.py:39-59.  Keeps the reference's float volume view and a bit-packed device copy."""
+
+    def __init__(self, device, aabb, alpha_volume):
+        self.device = device
+        self.aabb = torch.as_tensor(np.asarray(aabb.detach().cpu() if torch.is_tensor(aabb) else aabb),
+                                    dtype=torch.float32).reshape(2, 3)
+        a = self.aabb.numpy().astype(np.float32)
+        self.aabbSize = a[1] - a[0]
+        self.invgridSize = (np.float32(1.0) / self.aabbSize * np.float32(2)).astype(np.float32)  # tensorBase.py:46
+        vol = torch.as_tensor(alpha_volume, dtype=torch.float32)
+        self.alpha_volume = vol.reshape(1, 1, *vol.shape[-3:]).to(device).contiguous()
+        D, H, W = self.alpha_volume.shape[-3:]
+        self.gridSize = torch.tensor([W, H, D], dtype=torch.int32)
+        n_words = (D * H * W + 31) // 32
+        self.bits = torch.empty(n_words + 8, dtype=torch.int32, device=device)
+        lib = L.load()
+        L.check(lib.tvm_pack_alpha(_ptr(self.alpha_volume), D, H, W, _ptr(self.bits), _stream_ptr()),
+                "tvm_pack_alpha")
+
+
+class _Linear(torch.nn.Module):
+    """Parameter holder with torch.nn.Linear's names (weight [out,in], bias [out])."""
+
+    def __init__(self, in_c, out_c, bias=True):
+        super().__init__()
+        b = 1.0 / math.sqrt(in_c)
+        self.weight = torch.nn.Parameter(torch.empty(out_c, in_c).uniform_(-b, b))
+        self.bias = torch.nn.Parameter(torch.empty(out_c).uniform_(-b, b)) if bias else None
+
+
+class MLPRender_Fea(torch.nn.Module):
+    """Parameter container with the reference's names (tensorBase.py:62-74): mlp.0 / mlp.2 / mlp.4."""
+
+    def __init__(self, inChanel, viewpe=6, feape=6, featureC=128):
+        super().__init__()
+        self.in_mlpC = 2 * viewpe * 3 + 2 * feape * inChanel + 3 + inChanel
+        self.viewpe, self.feape = viewpe, feape
+        self.mlp = torch.nn.ModuleList([_Linear(self.in_mlpC, featureC), torch.nn.Identity(),
+                                        _Linear(featureC, featureC), torch.nn.Identity(),
+                                        _Linear(featureC, 3)])
+        torch.nn.init.constant_(self.mlp[-1].bias, 0)
+
+
+class _RenderFn(torch.autograd.Function):
+    """Autograd node: tvm_forward / tvm_backward; gradients come back in the parameters' NCHW shapes."""
+
+    @staticmethod
+    def forward(ctx, model, rays, jitter, flags, S, *params):
+        rgb, depth = model._forward_raw(rays, jitter, flags, S)
+        ctx.model, ctx.flags, ctx.S = model, flags, S
+        ctx.save_for_backward(rays, jitter if jitter is not None else torch.empty(0, device=rays.device), rgb)
+        ctx.mark_non_differentiable(depth)
+        return rgb, depth
+
+    @staticmethod
+    def backward(ctx, d_rgb, _d_depth):
+        rays, jitter, rgb = ctx.saved_tensors
+        grads = ctx.model._backward_raw(rays, jitter if jitter.numel() else None, ctx.flags, ctx.S, rgb,
+                                        d_rgb.contiguous())
+        return (None, None, None, None, None, *grads)
+
+
+class TensorVMSplit(torch.nn.Module):
+    def __init__(self, aabb, gridSize, device, density_n_comp=8, appearance_n_comp=24, app_dim=27,
+                 shadingMode='MLP_PE', alphaMask=None, near_far=[2.0, 20.0],
+                 density_shift=-10, alphaMask_thres=0.001, distance_scale=25, rayMarch_weight_thres=0.0001,
+                 pos_pe=6, view_pe=6, fea_pe=6, featureC=128, step_ratio=2.0,
+                 fea2denseAct='softplus'):
+        super().__init__()
+        L.require_cuda()
+        if shadingMode != 'MLP_Fea':
+            raise NotImplementedError("only shadingMode='MLP_Fea' (the mode of all shipped configs) is on the hot path")
+        if isinstance(density_n_comp, int):
+            density_n_comp = [density_n_comp] * 3
+        if isinstance(appearance_n_comp, int):
+            appearance_n_comp = [appearance_n_comp] * 3
+        if len(set(density_n_comp)) != 1 or len(set(appearance_n_comp)) != 1:
+            raise NotImplementedError("per-component channel counts must be equal")
+        self.density_n_comp = list(density_n_comp)
+        self.app_n_comp = list(appearance_n_comp)
+        self.app_dim = app_dim
+        self.device = device
+        self.aabb = torch.as_tensor(np.asarray(aabb.detach().cpu() if torch.is_tensor(aabb) else aabb),
+                                    dtype=torch.float32).reshape(2, 3)
+        self.alphaMask = alphaMask
+        self.density_shift = density_shift
+        self.alphaMask_thres = alphaMask_thres
+        self.distance_scale = distance_scale
+        self.rayMarch_weight_thres = rayMarch_weight_thres
+        self.fea2denseAct = fea2denseAct
+        self.near_far = near_far
+        self.step_ratio = step_ratio
+        self.update_stepSize(gridSize)
+        self.matMode = MAT_MODE
+        self.vecMode = VEC_MODE
+        self.comp_w = [1, 1, 1]
+        self.init_svd_volume(gridSize[0], device)
+        self.shadingMode, self.pos_pe, self.view_pe, self.fea_pe, self.featureC = \
+            shadingMode, pos_pe, view_pe, fea_pe, featureC
+        self.renderModule = MLPRender_Fea(self.app_dim, view_pe, fea_pe, featureC).to(device)
+        # --- engine state -------------------------------------------------------------------
+        self.mlp_mode = os.environ.get("TVM_MLP_MODE", "fp32")
+        self.early_termination = True
+        self.collect_counters = False
+        self.counters = torch.zeros(L.CNT_WORDS, dtype=torch.int64, device=device)
+        self.ws_budget_bytes = int(float(os.environ.get("TVM_WS_GIB", "6")) * (1 << 30))
+        self._ws = None
+        self._packed = None
+        self._packed_versions = None
+        self._packed_grid = None
+        self._tc = None
+
+    # ---- reference API: parameters --------------------------------------------------------
+    def update_stepSize(self, gridSize):
+        s = derive_march_scalars(self.aabb.numpy(), gridSize, self.step_ratio)
+        self.aabbSize = torch.from_numpy(s["aabbSize"].copy())
+        self.invaabbSize = torch.from_numpy(s["invaabbSize"].copy())
+        self.gridSize = torch.from_numpy(s["gridSize"].copy())
+        self.units = torch.from_numpy(s["units"].copy())
+        self.stepSize = torch.tensor(s["stepSize"])
+        self.aabbDiag = torch.tensor(s["aabbDiag"])
+        self.nSamples = s["nSamples"]
+        self._packed_grid = None
+
+    def init_svd_volume(self, res, device):
+        self.density_plane, self.density_line = self.init_one_svd(self.density_n_comp, self.gridSize, 0.1, device)
+        self.app_plane, self.app_line = self.init_one_svd(self.app_n_comp, self.gridSize, 0.1, device)
+        self.basis_mat = _Linear(sum(self.app_n_comp), self.app_dim, bias=False).to(device)
+
+    def init_one_svd(self, n_component, gridSize, scale, device):
+        plane_coef, line_coef = [], []
+        for i in range(len(self.vecMode)):
+            vec_id = self.vecMode[i]
+            mat_id_0, mat_id_1 = self.matMode[i]
+            plane_coef.append(torch.nn.Parameter(scale * torch.randn(
+                (1, n_component[i], int(gridSize[mat_id_1]), int(gridSize[mat_id_0])), device=device)))
+            line_coef.append(torch.nn.Parameter(scale * torch.randn(
+                (1, n_component[i], int(gridSize[vec_id]), 1), device=device)))
+        return torch.nn.ParameterList(plane_coef), torch.nn.ParameterList(line_coef)
+
+    def get_optparam_groups(self, lr_init_spatialxyz=0.02, lr_init_network=0.001):
+        """tensoRF.py:168-174."""
+        return [{'params': self.density_line, 'lr': lr_init_spatialxyz},
+                {'params': self.density_plane, 'lr': lr_init_spatialxyz},
+                {'params': self.app_line, 'lr': lr_init_spatialxyz},
+                {'params': self.app_plane, 'lr': lr_init_spatialxyz},
+                {'params': self.basis_mat.parameters(), 'lr': lr_init_network},
+                {'params': self.renderModule.parameters(), 'lr': lr_init_network}]
+
+    def set_nerfplusplus(self, bg_freq=4, bg_view_freq=2, bg_D=4, radii=20):
+        """tensorBase.py:538-539: a no-op for non-NeRF++ classes."""
+        pass
+
+    def load_numpy_params(self, p):
+        """Copy an oracle.fixtures.ModelParams (numpy, reference shapes) into the parameters."""
+        with torch.no_grad():
+            for k in range(3):
+                self.density_plane[k].copy_(torch.from_numpy(p.density_plane[k]))
+                self.density_line[k].copy_(torch.from_numpy(p.density_line[k]))
+                self.app_plane[k].copy_(torch.from_numpy(p.app_plane[k]))
+                self.app_line[k].copy_(torch.from_numpy(p.app_line[k]))
+            self.basis_mat.weight.copy_(torch.from_numpy(p.basis_mat))
+            for i, li in enumerate((0, 2, 4)):
+                self.renderModule.mlp[li].weight.copy_(torch.from_numpy(p.mlp_w[i]))
+                self.renderModule.mlp[li].bias.copy_(torch.from_numpy(p.mlp_b[i]))
+
+    def _param_list(self):
+        m = self.renderModule.mlp
+        return [*self.density_plane, *self.density_line, *self.app_plane, *self.app_line, self.basis_mat.weight,
+                m[0].weight, m[0].bias, m[2].weight, m[2].bias, m[4].weight, m[4].bias]
+
+    # ---- packed device image ----------------------------------------------------------------
+    def _layout(self):
+        """Offsets (in floats) of every packed tensor inside the flat parameter / gradient buffers."""
+        G = [int(g) for g in self.gridSize]
+        Cd, Ca = self.density_n_comp[0], self.app_n_comp[0]
+        F, in_c = self.featureC, self.renderModule.in_mlpC
+        items, off = {}, 0
+
+        def add(name, n):
+            nonlocal off
+            items[name] = (off, n)
+            off += (n + 63) // 64 * 64   # 256-byte alignment
+
+        for k in range(3):
+            m0, m1 = MAT_MODE[k]
+            add(f"dp{k}", G[m1] * G[m0] * Cd)
+        for k in range(3):
+            add(f"dl{k}", G[VEC_MODE[k]] * Cd)
+        for k in range(3):
+            m0, m1 = MAT_MODE[k]
+            add(f"ap{k}", G[m1] * G[m0] * Ca)
+        for k in range(3):
+            add(f"al{k}", G[VEC_MODE[k]] * Ca)
+        add("basis_t", 3 * Ca * 32)
+        add("w1_t", in_c * F)
+        add("b1", F)
+        add("w2_t", F * F)
+        add("b2", F)
+        add("w3", 3 * F)
+        add("b3", 64)
+        return items, off
+
+    def _struct_for(self, buf, cls):
+        items, _ = self._layout()
+        base = buf.data_ptr()
+        at = lambda name: base + 4 * items[name][0]
+        s = cls()
+        for k in range(3):
+            s.density_plane[k] = at(f"dp{k}")
+            s.density_line[k] = at(f"dl{k}")
+            s.app_plane[k] = at(f"ap{k}")
+            s.app_line[k] = at(f"al{k}")
+        for name in ("basis_t", "w1_t", "b1", "w2_t", "b2", "w3", "b3"):
+            setattr(s, name, at(name))
+        return s
+
+    def _pack(self, force=False):
+        """(Re)build the channels-last / transposed device image when a parameter changed."""
+        params = self._param_list()
+        versions = tuple((p.data_ptr(), p._version) for p in params)
+        grid_key = tuple(int(g) for g in self.gridSize)
+        if not force and self._packed is not None and versions == self._packed_versions \
+                and self._packed_grid == grid_key:
+            return
+        lib = L.load()
+        items, total = self._layout()
+        if self._packed is None or self._packed.numel() != total:
+            self._packed = torch.zeros(total, dtype=torch.float32, device=self.device)
+            self._grads_packed = None
+        st = _stream_ptr()
+        base = self._packed.data_ptr()
+        at = lambda name: C.c_void_p(base + 4 * items[name][0])
+        Cd, Ca, F = self.density_n_comp[0], self.app_n_comp[0], self.featureC
+        in_c = self.renderModule.in_mlpC
+        for k in range(3):
+            for pref, plist, llist, c in (("d", self.density_plane, self.density_line, Cd),
+                                          ("a", self.app_plane, self.app_line, Ca)):
+                p, l = plist[k].detach(), llist[k].detach()
+                assert p.is_contiguous() and l.is_contiguous() and p.dtype == torch.float32
+                L.check(lib.tvm_pack_grid(_ptr(p), c, p.shape[2], p.shape[3], at(f"{pref}p{k}"), st), "tvm_pack_grid")
+                L.check(lib.tvm_pack_grid(_ptr(l), c, l.shape[2], 1, at(f"{pref}l{k}"), st), "tvm_pack_grid")
+        m = self.renderModule.mlp
+        L.check(lib.tvm_pack_linear(_ptr(self.basis_mat.weight.detach()), self.app_dim, 3 * Ca, 32, at("basis_t"), st),
+                "tvm_pack_linear")
+        L.check(lib.tvm_pack_linear(_ptr(m[0].weight.detach()), F, in_c, F, at("w1_t"), st), "tvm_pack_linear")
+        L.check(lib.tvm_pack_linear(_ptr(m[2].weight.detach()), F, F, F, at("w2_t"), st), "tvm_pack_linear")
+        n = lambda name: items[name][1]
+        self._packed[items["b1"][0]:items["b1"][0] + F].copy_(m[0].bias.detach())
+        self._packed[items["b2"][0]:items["b2"][0] + F].copy_(m[2].bias.detach())
+        self._packed[items["w3"][0]:items["w3"][0] + 3 * F].copy_(m[4].weight.detach().reshape(-1))
+        self._packed[items["b3"][0]:items["b3"][0] + 3].copy_(m[4].bias.detach())
+        self._packed_versions = versions
+        self._packed_grid = grid_key
+        self._model_struct = None
+        self._tc_stale = True
+
+    def _model(self):
+        """The TvmModel descriptor (host POD) for the current parameters / mask."""
+        self._pack()
+        mask_key = id(self.alphaMask)
+        if getattr(self, "_model_struct", None) is not None and self._model_mask_key == mask_key \
+                and not (self._tc_stale and self.mlp_mode != "fp32"):
+            return self._model_struct
+        s = self._struct_for(self._packed, L.TvmModel)
+        a = self.aabb.numpy().astype(np.float32)
+        for i in range(3):
+            s.aabb[i] = float(a[0, i])
+            s.aabb[3 + i] = float(a[1, i])
+            s.inv_aabb_size[i] = float(self.invaabbSize[i])
+            s.grid[i] = int(self.gridSize[i])
+        s.step_size = float(self.stepSize)
+        s.near_, s.far_ = float(self.near_far[0]), float(self.near_far[1])
+        s.density_shift = float(self.density_shift)
+        s.distance_scale = float(self.distance_scale)
+        s.weight_thres = float(self.rayMarch_weight_thres)
+        s.act = L.ACT_SOFTPLUS if self.fea2denseAct == "softplus" else L.ACT_RELU
+        s.n_density, s.n_app, s.app_dim = self.density_n_comp[0], self.app_n_comp[0], self.app_dim
+        s.view_pe, s.fea_pe, s.feature_c = self.view_pe, self.fea_pe, self.featureC
+        if self.alphaMask is not None:
+            am = self.alphaMask
+            s.alpha_bits = am.bits.data_ptr()
+            a0 = am.aabb.numpy().astype(np.float32)
+            for i in range(3):
+                s.alpha_grid[i] = int(am.gridSize[i])
+                s.alpha_aabb_min[i] = float(a0[0, i])
+                s.alpha_inv_size[i] = float(am.invgridSize[i])
+        else:
+            s.alpha_bits = None
+        s.tc_weights = None
+        if self.mlp_mode != "fp32":
+            lib = L.load()
+            nbytes = lib.tvm_tc_weights_bytes(C.byref(s))
+            if nbytes == 0:
+                raise L.TvmError("tensor-core appearance head unavailable in this libtvmrender.so")
+            if self._tc is None or self._tc.numel() < nbytes:
+                self._tc = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            L.check(lib.tvm_pack_mlp_tc(C.byref(s), _ptr(self._tc), _stream_ptr()), "tvm_pack_mlp_tc")
+            s.tc_weights = self._tc.data_ptr()
+            self._tc_stale = False
+        self._model_struct, self._model_mask_key = s, mask_key
+        return s
+
+    # ---- workspace ------------------------------------------------------------------------------
+    def workspace_bytes(self, n, S):
+        out = C.c_size_t(0)
+        L.check(L.load().tvm_workspace_bytes(int(n), int(S), C.byref(out)), "tvm_workspace_bytes")
+        return out.value
+
+    def max_rays_per_launch(self, S):
+        per_ray = self.workspace_bytes(1024, S) / 1024.0
+        return max(1024, int(self.ws_budget_bytes / per_ray) // 1024 * 1024)
+
+    def _workspace(self, n, S):
+        need = self.workspace_bytes(n, S)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    # ---- raw engine calls -----------------------------------------------------------------------
+    def _flags(self, white_bg):
+        f = _MLP_FLAGS[self.mlp_mode]
+        if white_bg:
+            f |= L.WHITE_BG
+        if not self.early_termination:
+            f |= L.NO_ERT
+        return f
+
+    def _forward_raw(self, rays, jitter, flags, S, aux=None, out=None):
+        lib = L.load()
+        n = rays.shape[0]
+        assert rays.is_cuda and rays.dtype == torch.float32 and rays.is_contiguous() and rays.shape[1] == 6
+        model = self._model()
+        ws = self._workspace(n, S)
+        if out is None:
+            rgb = torch.empty((n, 3), dtype=torch.float32, device=rays.device)
+            depth = torch.empty((n,), dtype=torch.float32, device=rays.device)
+        else:
+            rgb, depth = out
+        L.check(lib.tvm_forward(C.byref(model), _ptr(rays), n, int(S), _ptr(jitter), flags, _ptr(rgb), _ptr(depth),
+                                C.byref(aux) if aux is not None else None,
+                                _ptr(self.counters) if self.collect_counters else None,
+                                _ptr(ws), ws.numel(), _stream_ptr()), "tvm_forward")
+        return rgb, depth
+
+    def _backward_raw(self, rays, jitter, flags, S, rgb, d_rgb):
+        lib = L.load()
+        n = rays.shape[0]
+        model = self._model()
+        items, total = self._layout()
+        if getattr(self, "_grads_packed", None) is None or self._grads_packed.numel() != total:
+            self._grads_packed = torch.empty(total, dtype=torch.float32, device=self.device)
+        gp = self._grads_packed
+        gp.zero_()
+        gs = self._struct_for(gp, L.TvmGrads)
+        ws = self._workspace(n, S)
+        L.check(lib.tvm_backward(C.byref(model), _ptr(rays), n, int(S), _ptr(jitter), flags, _ptr(rgb), _ptr(d_rgb),
+                                 C.byref(gs), _ptr(ws), ws.numel(), _stream_ptr()), "tvm_backward")
+        return self._unpack_grads(gp, items)
+
+    def _unpack_grads(self, gp, items):
+        lib = L.load()
+        st = _stream_ptr()
+        base = gp.data_ptr()
+        at = lambda name: C.c_void_p(base + 4 * items[name][0])
+        Cd, Ca, F = self.density_n_comp[0], self.app_n_comp[0], self.featureC
+        in_c = self.renderModule.in_mlpC
+        out = {}
+        for k in range(3):
+            for pref, plist, llist, c in (("d", self.density_plane, self.density_line, Cd),
+                                          ("a", self.app_plane, self.app_line, Ca)):
+                gpl, gl = torch.empty_like(plist[k]), torch.empty_like(llist[k])
+                L.check(lib.tvm_unpack_grid(at(f"{pref}p{k}"), c, gpl.shape[2], gpl.shape[3], _ptr(gpl), st),
+                        "tvm_unpack_grid")
+                L.check(lib.tvm_unpack_grid(at(f"{pref}l{k}"), c, gl.shape[2], 1, _ptr(gl), st), "tvm_unpack_grid")
+                out[f"{pref}p{k}"], out[f"{pref}l{k}"] = gpl, gl
+        m = self.renderModule.mlp
+        g_basis = torch.empty_like(self.basis_mat.weight)
+        g_w1, g_w2 = torch.empty_like(m[0].weight), torch.empty_like(m[2].weight)
+        L.check(lib.tvm_unpack_linear(at("basis_t"), self.app_dim, 3 * Ca, 32, _ptr(g_basis), st), "tvm_unpack_linear")
+        L.check(lib.tvm_unpack_linear(at("w1_t"), F, in_c, F, _ptr(g_w1), st), "tvm_unpack_linear")
+        L.check(lib.tvm_unpack_linear(at("w2_t"), F, F, F, _ptr(g_w2), st), "tvm_unpack_linear")
+        sl = lambda name, n: gp[items[name][0]:items[name][0] + n].clone()
+        return [*(out[f"dp{k}"] for k in range(3)), *(out[f"dl{k}"] for k in range(3)),
+                *(out[f"ap{k}"] for k in range(3)), *(out[f"al{k}"] for k in range(3)), g_basis,
+                g_w1, sl("b1", F), g_w2, sl("b2", F), sl("w3", 3 * F).reshape(3, F), sl("b3", 3)]
+
+    # ---- reference API: the per-chunk call ----------------------------------------------------
+    def forward(self, rays_chunk, white_bg=True, is_train=False, ndc_ray=False, N_samples=-1,
+                additional_output=False, jitter=None):
+        """TensorBase.execute (tensorBase.py:476-536): returns (rgb_map [n,3], depth_map [n])."""
+        if ndc_ray:
+            raise NotImplementedError("ndc_ray sampling is outside the hot path (SURVEY.md §2.1)")
+        if additional_output:
+            raise NotImplementedError("additional_output is only consumed by the NeRF++ variant")
+        S = int(N_samples) if N_samples > 0 else self.nSamples
+        rays = rays_chunk.contiguous()
+        if is_train and jitter is None:
+            jitter = torch.rand(rays.shape[0], dtype=torch.float32, device=rays.device)   # tensorBase.py:353
+        if not is_train:
+            jitter = None
+        flags = self._flags(white_bg)
+        n, nmax = rays.shape[0], self.max_rays_per_launch(S)
+        needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self._param_list())
+        if needs_grad:
+            if n > nmax:
+                raise ValueError(f"training chunk of {n} rays exceeds the workspace budget ({nmax} rays)")
+            return _RenderFn.apply(self, rays, jitter, flags, S, *self._param_list())
+        if n <= nmax:
+            return self._forward_raw(rays, jitter, flags, S)
+        rgb = torch.empty((n, 3), dtype=torch.float32, device=rays.device)
+        depth = torch.empty((n,), dtype=torch.float32, device=rays.device)
+        for s in range(0, n, nmax):
+            e = min(n, s + nmax)
+            self._forward_raw(rays[s:e], None if jitter is None else jitter[s:e], flags, S, out=(rgb[s:e], depth[s:e]))
+        return rgb, depth
+
+    execute = forward
+
+    # ---- parity instrumentation -------------------------------------------------------------------
+    def forward_with_aux(self, rays, white_bg=True, N_samples=-1, jitter=None, want_rgb=True):
+        """tvm_forward with every per-sample output requested (tests only; disables ERT)."""
+        S = int(N_samples) if N_samples > 0 else self.nSamples
+        rays = rays.contiguous()
+        n, NB = rays.shape[0], (S + 31) // 32
+        dev = rays.device
+        bits = lambda: torch.empty((n, NB), dtype=torch.int32, device=dev)
+        o = dict(bbox_bits=bits(), valid_bits=bits(), app_bits=bits(),
+                 sigma=torch.empty((n, S), dtype=torch.float32, device=dev),
+                 weight=torch.empty((n, S), dtype=torch.float32, device=dev),
+                 rgb=torch.empty((n, S, 3), dtype=torch.float32, device=dev) if want_rgb else None,
+                 acc_map=torch.empty((n,), dtype=torch.float32, device=dev))
+        aux = L.TvmAux()
+        for k, v in o.items():
+            setattr(aux, k, v.data_ptr() if v is not None else None)
+        rgb_map, depth_map = self._forward_raw(rays, jitter, self._flags(white_bg), S, aux=aux)
+        o.update(rgb_map=rgb_map, depth_map=depth_map)
+        return o
+
+    def compute_alpha(self, xyz_locs, length=1):
+        """tensorBase.py:451-473."""
+        xyz = xyz_locs.contiguous().view(-1, 3)
+        out = torch.empty(xyz.shape[0], dtype=torch.float32, device=xyz.device)
+        model = self._model()
+        L.check(L.load().tvm_density_alpha(C.byref(model), _ptr(xyz), xyz.shape[0], float(length), _ptr(out),
+                                           _stream_ptr()), "tvm_density_alpha")
+        return out.view(xyz_locs.shape[:-1])
+
+
+def unpack_bits(bits: torch.Tensor, S: int) -> np.ndarray:
+    """[n, NB] int32 device words -> [n, S] bool numpy (bit j of word b = sample 32*b + j)."""
+    w = bits.detach().cpu().numpy().view(np.uint32)
+    b = np.unpackbits(w.view(np.uint8).reshape(w.shape[0], -1), axis=1, bitorder="little")
+    return b[:, :S].astype(bool)

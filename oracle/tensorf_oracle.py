@@ -1,0 +1,436 @@
+"""CPU oracle: an op-for-op restatement of tensorf-myc's TensoRF-VM per-ray renderer.
+
+TEST INFRASTRUCTURE -- NOT PRODUCT CODE.  Only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs may import this file.  The product path
+(jittor-myc-nerfs_b200/) never imports it and has no CPU fallback.
+
+PARITY STATUS: "parity unpinned" with respect to Jittor itself.  The reference runs on Jittor,
+which is absent from this image and cannot be installed (no network), and the reference ships no
+tests or golden vectors for this path.  What pins this file instead:
+  * tests/golden/make_golden.py executes the reference's UNMODIFIED python modules
+    (/root/reference/tensorf-myc/models/tensorBase.py, tensoRF.py) over oracle/jt_shim (a torch-CPU
+    stand-in for the ~40 Jittor calls they make) and commits the outputs as tests/golden/*.npz;
+    tests/test_oracle_golden.py checks this restatement against those vectors (bit-exact masks,
+    <=1e-6 on colour).  That pins the reference's own python logic (op order, indexing, quirks);
+  * Jittor's op numerics remain ASSUMED (A1-A3 below, each one a switch);
+  * a second, independent evaluation through torch.nn.functional.grid_sample / torch.cumprod /
+    F.softplus (OracleOptions.torch_native()) must agree with the explicit restatement.
+
+Every function cites the reference lines it follows (paths relative to /root/reference/tensorf-myc/).
+
+Assumptions about Jittor:
+  A1 nn.grid_sample(bilinear, zeros, align_corners=True): u = ((c+1)/2)*(size-1); f = floor(u);
+     weights (f+1-u) and (u-f) per axis, products formed first, out-of-range taps read 0.
+  A2 jt.cumprod(x, dim) = exp(cumsum(log(x), dim)).
+  A3 nn.softplus(x, beta=1, threshold=20) = log(1 + exp(min(x,20))) + max(x-20, 0)
+     (older 1.3.x: log(1 + exp(x)); identical for x <= 20).
+  A4 nn.Linear: y = x @ W.T + b with W [out,in].
+  A5 boolean-mask get/set-item compacts in row-major (ray-major, sample-minor) order.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+MAT_MODE = ((0, 1), (0, 2), (1, 2))  # models/tensorBase.py:168
+VEC_MODE = (2, 1, 0)                 # models/tensorBase.py:169
+
+
+@dataclass
+class OracleOptions:
+    grid_sample: str = "explicit"   # "explicit" (A1 spelled out) | "torch" (F.grid_sample)
+    cumprod: str = "logspace"       # "logspace" (A2) | "product" (running product, torch.cumprod)
+    softplus: str = "jittor"        # "jittor" (A3 clamped) | "naive" (log(1+exp x)) | "log1p" (torch F.softplus)
+
+    @staticmethod
+    def torch_native() -> "OracleOptions":
+        return OracleOptions(grid_sample="torch", cumprod="product", softplus="log1p")
+
+
+# --------------------------------------------------------------------------------------------
+# Jittor op restatements
+# --------------------------------------------------------------------------------------------
+def _unnormalize(c, size):
+    # A1, align_corners=True
+    return ((c + 1) / 2) * (size - 1)
+
+
+def grid_sample_2d(img, gx, gy, impl="explicit"):
+    """img [C,H,W]; gx -> W axis, gy -> H axis, both [N] in [-1,1]. Returns [C,N]."""
+    C, H, W = img.shape
+    if impl == "torch":
+        grid = torch.stack([gx, gy], -1).view(1, -1, 1, 2)
+        return F.grid_sample(img[None], grid, mode="bilinear", padding_mode="zeros",
+                             align_corners=True).view(C, -1)
+    ix = _unnormalize(gx, W)
+    iy = _unnormalize(gy, H)
+    x0 = torch.floor(ix)
+    y0 = torch.floor(iy)
+    x1 = x0 + 1
+    y1 = y0 + 1
+    nw = (x1 - ix) * (y1 - iy)
+    ne = (ix - x0) * (y1 - iy)
+    sw = (x1 - ix) * (iy - y0)
+    se = (ix - x0) * (iy - y0)
+
+    def tap(xi, yi):
+        inb = (xi >= 0) & (xi <= W - 1) & (yi >= 0) & (yi <= H - 1)
+        v = img[:, yi.clamp(0, H - 1).long(), xi.clamp(0, W - 1).long()]
+        return v * inb.to(img.dtype)
+
+    return tap(x0, y0) * nw + tap(x1, y0) * ne + tap(x0, y1) * sw + tap(x1, y1) * se
+
+
+def grid_sample_3d(vol, gx, gy, gz, impl="explicit"):
+    """vol [D,H,W]; gx->W, gy->H, gz->D. Returns [N]."""
+    D, H, W = vol.shape
+    if impl == "torch":
+        grid = torch.stack([gx, gy, gz], -1).view(1, -1, 1, 1, 3)
+        return F.grid_sample(vol[None, None], grid, mode="bilinear", padding_mode="zeros",
+                             align_corners=True).view(-1)
+    ix = _unnormalize(gx, W)
+    iy = _unnormalize(gy, H)
+    iz = _unnormalize(gz, D)
+    x0, y0, z0 = torch.floor(ix), torch.floor(iy), torch.floor(iz)
+    out = torch.zeros_like(ix)
+    for cz in (0, 1):
+        wz = (z0 + 1 - iz) if cz == 0 else (iz - z0)
+        for cy in (0, 1):
+            wy = (y0 + 1 - iy) if cy == 0 else (iy - y0)
+            for cx in (0, 1):
+                wx = (x0 + 1 - ix) if cx == 0 else (ix - x0)
+                xi, yi, zi = x0 + cx, y0 + cy, z0 + cz
+                inb = (xi >= 0) & (xi <= W - 1) & (yi >= 0) & (yi <= H - 1) & (zi >= 0) & (zi <= D - 1)
+                v = vol[zi.clamp(0, D - 1).long(), yi.clamp(0, H - 1).long(), xi.clamp(0, W - 1).long()]
+                out = out + (v * inb.to(vol.dtype)) * (wx * wy * wz)
+    return out
+
+
+def jt_cumprod(x, dim, impl="logspace"):
+    if impl == "logspace":                       # A2
+        return torch.exp(torch.cumsum(torch.log(x), dim))
+    return torch.cumprod(x, dim)
+
+
+def jt_softplus(x, impl="jittor"):
+    if impl == "jittor":                         # A3 (clamped variant)
+        return torch.log(1 + torch.exp(torch.clamp(x, max=20.0))) + torch.clamp(x - 20.0, min=0.0)
+    if impl == "naive":
+        return torch.log(1 + torch.exp(x))
+    return F.softplus(x)
+
+
+def positional_encoding(positions, freqs):
+    """models/tensorBase.py:9-15 -- channel-major, frequency-minor; [sin | cos]."""
+    freq_bands = (2 ** torch.arange(freqs)).to(positions.dtype)
+    pts = (positions[..., None] * freq_bands).reshape(positions.shape[:-1] + (freqs * positions.shape[-1],))
+    return torch.cat([torch.sin(pts), torch.cos(pts)], dim=-1)
+
+
+def raw2alpha(sigma, dist, cumprod_impl="logspace"):
+    """models/tensorBase.py:17-24."""
+    alpha = 1. - torch.exp(-sigma * dist)
+    T = jt_cumprod(torch.cat([torch.ones((alpha.shape[0], 1), dtype=alpha.dtype), 1. - alpha + 1e-10], -1), -1,
+                   cumprod_impl)
+    weights = alpha * T[:, :-1]
+    return alpha, weights, T[:, -1:]
+
+
+class AlphaGridMask:
+    """models/tensorBase.py:39-59."""
+
+    def __init__(self, aabb, alpha_volume, dtype=torch.float32, impl="explicit"):
+        self.aabb = torch.as_tensor(np.asarray(aabb), dtype=dtype)
+        self.aabbSize = self.aabb[1] - self.aabb[0]
+        self.invgridSize = 1.0 / self.aabbSize * 2
+        self.alpha_volume = torch.as_tensor(np.asarray(alpha_volume), dtype=dtype)
+        self.alpha_volume = self.alpha_volume.view(*self.alpha_volume.shape[-3:])
+        self.gridSize = [self.alpha_volume.shape[-1], self.alpha_volume.shape[-2], self.alpha_volume.shape[-3]]
+        self.impl = impl
+
+    def normalize_coord(self, xyz):
+        return (xyz - self.aabb[0]) * self.invgridSize - 1
+
+    def sample_alpha(self, xyz):
+        c = self.normalize_coord(xyz)
+        if c.shape[0] == 0:
+            return torch.zeros((0,), dtype=c.dtype)
+        return grid_sample_3d(self.alpha_volume, c[:, 0], c[:, 1], c[:, 2], self.impl)
+
+
+class OracleTensorVMSplit:
+    """TensorVMSplit + TensorBase.execute (models/tensoRF.py:141-244, models/tensorBase.py:140-224,340-360,444-536)."""
+
+    def __init__(self, params, alpha_volume=None, alpha_aabb=None, dtype=torch.float32,
+                 opts: OracleOptions | None = None, requires_grad=False):
+        self.opts = opts or OracleOptions()
+        self.dtype = dtype
+        p = params
+        t = lambda a: torch.tensor(np.asarray(a), dtype=dtype)
+        self.aabb = t(p.aabb)
+        self.near_far = p.near_far
+        self.density_shift = p.density_shift
+        self.distance_scale = p.distance_scale
+        self.rayMarch_weight_thres = p.rayMarch_weight_thres
+        self.step_ratio = p.step_ratio
+        self.view_pe, self.fea_pe = p.view_pe, p.fea_pe
+        self.fea2denseAct = p.fea2denseAct
+        self.density_plane = [t(a) for a in p.density_plane]
+        self.density_line = [t(a) for a in p.density_line]
+        self.app_plane = [t(a) for a in p.app_plane]
+        self.app_line = [t(a) for a in p.app_line]
+        self.basis_mat = t(p.basis_mat)
+        self.mlp_w = [t(a) for a in p.mlp_w]
+        self.mlp_b = [t(a) for a in p.mlp_b]
+        if requires_grad:
+            for x in self.parameters():
+                x.requires_grad_(True)
+        self.update_stepSize(p.gridSize)
+        self.alphaMask = None
+        if alpha_volume is not None:
+            self.alphaMask = AlphaGridMask(alpha_aabb if alpha_aabb is not None else p.aabb, alpha_volume,
+                                           dtype=dtype, impl=self.opts.grid_sample)
+
+    # -- bookkeeping ------------------------------------------------------------------------
+    def named_parameters(self):
+        out = {}
+        for k in range(3):
+            out[f"density_plane.{k}"] = self.density_plane[k]
+            out[f"density_line.{k}"] = self.density_line[k]
+            out[f"app_plane.{k}"] = self.app_plane[k]
+            out[f"app_line.{k}"] = self.app_line[k]
+        out["basis_mat.weight"] = self.basis_mat
+        for i, li in enumerate((0, 2, 4)):
+            out[f"renderModule.mlp.{li}.weight"] = self.mlp_w[i]
+            out[f"renderModule.mlp.{li}.bias"] = self.mlp_b[i]
+        return out
+
+    def parameters(self):
+        return list(self.named_parameters().values())
+
+    def update_stepSize(self, gridSize):
+        """models/tensorBase.py:197-209."""
+        self.aabbSize = self.aabb[1] - self.aabb[0]
+        self.invaabbSize = 2.0 / self.aabbSize
+        self.gridSize = torch.tensor([int(g) for g in gridSize], dtype=torch.int32)
+        self.units = self.aabbSize / (self.gridSize - 1)
+        self.stepSize = torch.mean(self.units) * self.step_ratio
+        self.aabbDiag = torch.sqrt(torch.sum(torch.pow(self.aabbSize, 2)))
+        self.nSamples = int((self.aabbDiag / self.stepSize).item()) + 1
+
+    def normalize_coord(self, xyz):
+        """models/tensorBase.py:223-224."""
+        return (xyz - self.aabb[0]) * self.invaabbSize - 1
+
+    # -- sampling ---------------------------------------------------------------------------
+    def sample_ray(self, rays_o, rays_d, is_train=True, N_samples=-1, jitter=None):
+        """models/tensorBase.py:340-360. `jitter` [n] replaces jt.rand_like(rng[:, [0]])."""
+        N_samples = N_samples if N_samples > 0 else self.nSamples
+        stepsize = self.stepSize
+        near, far = self.near_far
+        vec = torch.where(rays_d == 0, torch.full_like(rays_d, 1e-6), rays_d)
+        rate_a = (self.aabb[1] - rays_o) / vec
+        rate_b = (self.aabb[0] - rays_o) / vec
+        t_min = torch.minimum(rate_a, rate_b).amax(-1).clamp(min=near, max=far)
+        rng = torch.arange(N_samples)[None].to(self.dtype)
+        if is_train:
+            rng = rng.repeat(rays_d.shape[-2], 1)
+            rng = rng + jitter.to(self.dtype).view(-1, 1)
+        step = stepsize * rng
+        interpx = (t_min[..., None] + step)
+        rays_pts = rays_o[..., None, :] + rays_d[..., None, :] * interpx[..., None]
+        mask_outbbox = ((self.aabb[0] > rays_pts) | (rays_pts > self.aabb[1])).any(dim=-1)
+        return rays_pts, interpx, ~mask_outbbox
+
+    # -- factor-grid gathers ----------------------------------------------------------------
+    def _coords(self, xyz):
+        cp = [(xyz[..., MAT_MODE[k][0]], xyz[..., MAT_MODE[k][1]]) for k in range(3)]
+        cl = [xyz[..., VEC_MODE[k]] for k in range(3)]
+        return cp, cl
+
+    def compute_densityfeature(self, xyz):
+        """models/tensoRF.py:209-225."""
+        cp, cl = self._coords(xyz.detach())
+        g = self.opts.grid_sample
+        sigma_feature = torch.zeros((xyz.shape[0],), dtype=self.dtype)
+        for k in range(3):
+            plane = grid_sample_2d(self.density_plane[k][0], cp[k][0], cp[k][1], g)
+            line = grid_sample_2d(self.density_line[k][0], torch.zeros_like(cl[k]), cl[k], g)
+            sigma_feature = sigma_feature + torch.sum(plane * line, dim=0)
+        return sigma_feature
+
+    def compute_app_vector(self, xyz):
+        """The [M,144] product vector fed to basis_mat (models/tensoRF.py:228-243)."""
+        cp, cl = self._coords(xyz.detach())
+        g = self.opts.grid_sample
+        planes, lines = [], []
+        for k in range(3):
+            planes.append(grid_sample_2d(self.app_plane[k][0], cp[k][0], cp[k][1], g))
+            lines.append(grid_sample_2d(self.app_line[k][0], torch.zeros_like(cl[k]), cl[k], g))
+        return (torch.cat(planes) * torch.cat(lines)).T
+
+    def compute_appfeature(self, xyz):
+        """models/tensoRF.py:228-244; basis_mat = Linear(144, 27, bias=False) (A4)."""
+        return self.compute_app_vector(xyz) @ self.basis_mat.T
+
+    def feature2density(self, f):
+        """models/tensorBase.py:444-448."""
+        if self.fea2denseAct == "softplus":
+            return jt_softplus(f + self.density_shift, self.opts.softplus)
+        return torch.relu(f)
+
+    def renderModule(self, pts, viewdirs, features):
+        """MLPRender_Fea.execute, models/tensorBase.py:76-86."""
+        indata = [features, viewdirs]
+        if self.fea_pe > 0:
+            indata += [positional_encoding(features, self.fea_pe)]
+        if self.view_pe > 0:
+            indata += [positional_encoding(viewdirs, self.view_pe)]
+        x = torch.cat(indata, dim=-1)
+        x = torch.relu(x @ self.mlp_w[0].T + self.mlp_b[0])
+        x = torch.relu(x @ self.mlp_w[1].T + self.mlp_b[1])
+        x = x @ self.mlp_w[2].T + self.mlp_b[2]
+        return torch.sigmoid(x)
+
+    # -- the per-chunk pipeline -------------------------------------------------------------
+    def execute(self, rays_chunk, white_bg=True, is_train=False, ndc_ray=False, N_samples=-1,
+                jitter=None, stages=None):
+        """models/tensorBase.py:476-536 (ndc_ray=False branch). `stages` (dict) collects intermediates."""
+        assert not ndc_ray
+        rays_chunk = rays_chunk.to(self.dtype)
+        viewdirs = rays_chunk[:, 3:6]
+        xyz_sampled, z_vals, ray_valid = self.sample_ray(rays_chunk[:, :3], viewdirs, is_train=is_train,
+                                                         N_samples=N_samples, jitter=jitter)
+        dists = torch.cat((z_vals[:, 1:] - z_vals[:, :-1], torch.zeros_like(z_vals[:, :1])), dim=-1)
+        if dists.shape[0] != xyz_sampled.shape[0]:
+            dists = dists.expand(xyz_sampled.shape[0], -1)
+        viewdirs = viewdirs.view(-1, 1, 3).expand(xyz_sampled.shape)
+        if stages is not None:
+            stages["bbox_valid"] = ray_valid.clone()
+            stages["z_vals"] = z_vals.expand(xyz_sampled.shape[0], -1).clone()
+
+        if self.alphaMask is not None:
+            alphas = self.alphaMask.sample_alpha(xyz_sampled[ray_valid])
+            alpha_mask = alphas > 0
+            ray_invalid = ~ray_valid
+            tmp = ray_invalid[ray_valid]
+            tmp |= (~alpha_mask)
+            ray_invalid[ray_valid] = tmp
+            ray_valid = ~ray_invalid
+
+        sigma = torch.zeros(xyz_sampled.shape[:-1], dtype=self.dtype)
+        rgb = torch.zeros((*xyz_sampled.shape[:2], 3), dtype=self.dtype)
+
+        if ray_valid.any():
+            xyz_sampled = self.normalize_coord(xyz_sampled)
+            sigma_feature = self.compute_densityfeature(xyz_sampled[ray_valid])
+            validsigma = self.feature2density(sigma_feature)
+            sigma = sigma.index_put((ray_valid,), validsigma)
+
+        alpha, weight, bg_weight = raw2alpha(sigma, dists * self.distance_scale, self.opts.cumprod)
+        app_mask = weight > self.rayMarch_weight_thres
+
+        if app_mask.any():
+            app_features = self.compute_appfeature(xyz_sampled[app_mask])
+            valid_rgbs = self.renderModule(xyz_sampled[app_mask], viewdirs[app_mask], app_features)
+            rgb = rgb.index_put((app_mask,), valid_rgbs)
+
+        acc_map = torch.sum(weight, -1)
+        rgb_map_raw = torch.sum(weight[..., None] * rgb, -2)
+        if white_bg:
+            rgb_map_raw = rgb_map_raw + (1. - acc_map[..., None])
+        rgb_map = rgb_map_raw.clamp(0, 1)
+
+        with torch.no_grad():
+            depth_map = torch.sum(weight * z_vals, -1)
+            depth_map = depth_map + (1. - acc_map) * rays_chunk[..., -1]   # column 5 = d_z: reference quirk
+
+        if stages is not None:
+            stages.update(ray_valid=ray_valid, sigma=sigma.detach(), alpha=alpha.detach(), weight=weight.detach(),
+                          bg_weight=bg_weight.detach(), app_mask=app_mask, rgb=rgb.detach(),
+                          acc_map=acc_map.detach(), rgb_map_raw=rgb_map_raw.detach())
+        return rgb_map, depth_map
+
+    __call__ = execute
+
+    # -- §8f-1: dense alpha on arbitrary points ------------------------------------------------
+    def compute_alpha(self, xyz_locs, length=1.0):
+        """models/tensorBase.py:451-473."""
+        xyz_locs = xyz_locs.to(self.dtype)
+        if self.alphaMask is not None:
+            alpha_mask = self.alphaMask.sample_alpha(xyz_locs) > 0
+        else:
+            alpha_mask = torch.ones_like(xyz_locs[:, 0]).bool()
+        sigma = torch.zeros(xyz_locs.shape[:-1], dtype=self.dtype)
+        if alpha_mask.any():
+            xyz_sampled = self.normalize_coord(xyz_locs[alpha_mask])
+            sigma[alpha_mask] = self.feature2density(self.compute_densityfeature(xyz_sampled))
+        return 1 - torch.exp(-sigma * length).view(xyz_locs.shape[:-1])
+
+
+def OctreeRender_trilinear_fast(rays, tensorf, chunk=4096, N_samples=-1, ndc_ray=False, white_bg=True,
+                                is_train=False, device="cpu", jitter=None):
+    """renderer.py:12-27 (the jt.sync_all()/jt.gc() per chunk have no CPU counterpart)."""
+    rgbs, depth_maps = [], []
+    N_rays_all = rays.shape[0]
+    for chunk_idx in range(N_rays_all // chunk + int(N_rays_all % chunk > 0)):
+        sl = slice(chunk_idx * chunk, (chunk_idx + 1) * chunk)
+        rgb_map, depth_map = tensorf(rays[sl], is_train=is_train, white_bg=white_bg, ndc_ray=ndc_ray,
+                                     N_samples=N_samples, jitter=None if jitter is None else jitter[sl])
+        rgbs.append(rgb_map)
+        depth_maps.append(depth_map)
+    return torch.cat(rgbs), None, torch.cat(depth_maps), None, None
+
+
+# --------------------------------------------------------------------------------------------
+# helpers used by tests / bench
+# --------------------------------------------------------------------------------------------
+def run_case(case, dtype=torch.float32, opts=None, N_samples=-1, white_bg=True, want_stages=True,
+             chunk=4096):
+    """Forward a fixtures.make_case() dict; returns dict of numpy outputs (+ per-sample stages)."""
+    m = OracleTensorVMSplit(case["model"], case["alpha_volume"], case["alpha_aabb"], dtype=dtype, opts=opts)
+    rays = torch.from_numpy(case["rays"])
+    jit = None if case.get("jitter") is None else torch.from_numpy(case["jitter"])
+    is_train = jit is not None
+    outs, st_all = [], []
+    for s in range(0, rays.shape[0], chunk):
+        st = {} if want_stages else None
+        with torch.no_grad():
+            rgb, depth = m(rays[s:s + chunk], white_bg=white_bg, is_train=is_train, N_samples=N_samples,
+                           jitter=None if jit is None else jit[s:s + chunk], stages=st)
+        outs.append((rgb, depth))
+        st_all.append(st)
+    res = dict(rgb_map=torch.cat([o[0] for o in outs]).numpy(), depth_map=torch.cat([o[1] for o in outs]).numpy(),
+               nSamples=m.nSamples, stepSize=float(m.stepSize))
+    if want_stages:
+        for k in st_all[0]:
+            res[k] = torch.cat([s[k] for s in st_all]).numpy()
+    return res
+
+
+def work_counts(stages):
+    """M_in / M_v / M_a of SURVEY.md §8d from a stages dict."""
+    return dict(n=int(stages["bbox_valid"].shape[0]), M_in=int(stages["bbox_valid"].sum()),
+                M_v=int(stages["ray_valid"].sum()), M_a=int(stages["app_mask"].sum()))
+
+
+def backward_case(case, d_rgb_map=None, dtype=torch.float64, opts=None, N_samples=-1, white_bg=True):
+    """Gradients of sum(rgb_map * d_rgb_map) (or of train.py:228's MSE against case['target'] when
+    d_rgb_map is None) w.r.t. every parameter, in the reference's NCHW shapes (row a12)."""
+    m = OracleTensorVMSplit(case["model"], case["alpha_volume"], case["alpha_aabb"], dtype=dtype, opts=opts,
+                            requires_grad=True)
+    rays = torch.from_numpy(case["rays"])
+    jit = None if case.get("jitter") is None else torch.from_numpy(case["jitter"])
+    rgb, depth = m(rays, white_bg=white_bg, is_train=jit is not None, N_samples=N_samples, jitter=jit)
+    if d_rgb_map is None:
+        tgt = torch.from_numpy(case["target"]).to(dtype)
+        loss = torch.mean((rgb - tgt) ** 2)
+    else:
+        loss = torch.sum(rgb * torch.as_tensor(d_rgb_map, dtype=dtype))
+    loss.backward()
+    grads = {k: (v.grad.detach().numpy() if v.grad is not None else np.zeros(v.shape)) for k, v in
+             m.named_parameters().items()}
+    return dict(loss=float(loss), rgb_map=rgb.detach().numpy(), grads=grads)
