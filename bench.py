@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py -- TensoRF-VM per-ray rendering hot path on B200.
+
+One "step" = one pass of the hot path over one full 800x800 frame (640,000 rays) of BASELINE.json
+configs[1]: 300^3 grid, 200^3 alpha mask, S = nSamples = 1036, white background, synthetic rays and
+random-init grids (oracle/fixtures.py, seed 20211202).  With N GPUs every rank renders its own frame
+of the 8-azimuth orbit (configs[4], weak scaling, no data-path collective).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--regime R1|R2] [--mlp fp32|bf16|bf16x3]
+  python bench.py --impl reference ...     # the CPU restatement of the reference on the host cores
+
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+METRIC = "TensoRF-VM rays/sec (800x800 frame render, 300^3 grid, alphaMask on)"
+UNIT = "rays/s"
+FRAME = 800
+GRID = 300
+MASK_RES = 200
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--regime", default="R1", choices=["R0", "R1", "R2"])
+    ap.add_argument("--mlp", default=os.environ.get("TVM_MLP_MODE", "fp32"), choices=["fp32", "bf16", "bf16x3"])
+    ap.add_argument("--grid", type=int, default=GRID)
+    ap.add_argument("--rays", type=int, default=FRAME * FRAME, help="rays per step (default: the full frame)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-chunks", type=int, default=16)
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop_ev = index, [], threading.Event()
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop_ev.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                if out.returncode == 0 and out.stdout.strip():
+                    self.rows.append([x.strip() for x in out.stdout.strip().splitlines()[0].split(",")])
+            except Exception:
+                pass
+            self.stop_ev.wait(0.1)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop_ev.set()
+        self.t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = sorted(float(r[0]) for r in self.rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def make_case(args, rank):
+    from oracle import fixtures as fx
+    reg = fx.REGIMES[args.regime]
+    model = fx.make_model(args.grid, density_shift=reg["density_shift"])
+    rays = fx.frame_rays(azimuth=0.7 + rank * np.pi / 4)       # 8-azimuth orbit of SURVEY §8d
+    if args.rays < rays.shape[0]:
+        rays = np.ascontiguousarray(rays[:args.rays])
+    vol = fx.ball_alpha_volume(MASK_RES if args.grid > 128 else 128) if reg["mask"] else None
+    return dict(model=model, rays=rays, alpha_volume=vol, alpha_aabb=model.aabb.copy(), jitter=None, target=None)
+
+
+def workload_name(args):
+    return (f"configs[1]: 800x800 frame ({args.rays} rays), {args.grid}^3 grid, alphaMask "
+            f"{MASK_RES if args.grid > 128 else 128}^3 ball r=3.5, regime {args.regime} "
+            f"(density_shift={'0' if args.regime == 'R1' else '-3' if args.regime == 'R2' else '-10'}), white_bg")
+
+
+def cpu_sample(case, n_chunks, chunk=1024):
+    """A bounded sample of the frame: n_chunks x 1024 consecutive rays evenly spread over the image."""
+    rays = case["rays"]
+    n = rays.shape[0]
+    n_chunks = max(1, min(n_chunks, n // chunk))
+    starts = np.linspace(0, n - chunk, n_chunks).astype(np.int64) // chunk * chunk
+    return np.concatenate([rays[s:s + chunk] for s in starts]), f"{n_chunks} chunks x {chunk} rays evenly spread over the frame"
+
+
+def time_cpu_reference(case, n_chunks, repeats=1):
+    """The oracle in its reference-shaped mode (dense [n,S,3] points, boolean-mask compaction, 12
+    grid_sample calls, renderer.py's chunk loop with chunk=1024 as renderer.py:50) on all host cores."""
+    from oracle import tensorf_oracle as orc
+    torch.set_num_threads(os.cpu_count())
+    sample, desc = cpu_sample(case, n_chunks)
+    m = orc.OracleTensorVMSplit(case["model"], case["alpha_volume"], case["alpha_aabb"],
+                                opts=orc.OracleOptions.torch_native())
+    rays = torch.from_numpy(sample)
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            orc.OctreeRender_trilinear_fast(rays, m, chunk=1024, N_samples=-1, white_bg=True, is_train=False)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return sample.shape[0] / best, best, desc
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    case = make_case(args, 0)
+    n_chunks = max(2, args.cpu_sample_chunks // 2)
+    for _ in range(args.warmup and 1):
+        time_cpu_reference(case, 1)
+    vals = []
+    t_total = 0.0
+    for _ in range(args.steps):
+        v, dt, desc = time_cpu_reference(case, n_chunks)
+        vals.append(v)
+        t_total += dt
+    n_sample = n_chunks * 1024
+    value = n_sample * len(vals) / t_total
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t_total / len(vals), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": {"workload": workload_name(args), "note": "CPU restatement of the reference (torch CPU, "
+                       "reference op sequence); NOT Jittor (absent from the image); each step = " + desc},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": desc},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    import jittor_myc_nerfs_b200 as pkg
+    L = pkg._lib
+    L.require_cuda()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    case = make_case(args, rank)
+    model = pkg.model_from_params(case["model"], f"cuda:{local_rank}", case["alpha_volume"], case["alpha_aabb"], args.mlp)
+    n = case["rays"].shape[0]
+    S = model.nSamples
+    rays_host = torch.from_numpy(case["rays"]).pin_memory()
+    rays_dev = rays_host.to(dev)
+    rgb_host = torch.empty((n, 3), dtype=torch.float32).pin_memory()
+    depth_host = torch.empty((n,), dtype=torch.float32).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def step_resident():
+        with torch.no_grad():
+            return pkg.OctreeRender_trilinear_fast(rays_dev, model, chunk=1024, N_samples=-1, white_bg=True,
+                                                   is_train=False, device=dev)
+
+    def step_e2e():
+        with torch.no_grad():
+            r = rays_host.to(dev, non_blocking=True)
+            rgb, _, depth, _, _ = pkg.OctreeRender_trilinear_fast(r, model, chunk=1024, N_samples=-1,
+                                                                  white_bg=True, is_train=False, device=dev)
+            rgb_host.copy_(rgb, non_blocking=True)
+            depth_host.copy_(depth, non_blocking=True)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        """K steps, each bracketed by CUDA events on the launching stream, L2 flushed before each."""
+        evs = []
+        barrier()
+        for _ in range(steps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            evs.append((a, b))
+        barrier()
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+        step_e2e()
+    torch.cuda.synchronize()
+
+    with ClockSampler(local_rank) as clk:
+        ms_total = timed(step_resident, args.steps)
+        ms_e2e = timed(step_e2e, args.steps)
+    clocks = clk.summary()
+
+    # roofline leg: the same K steps with per-kernel events (tvm_profile_*) and work counters
+    model.collect_counters = True
+    model.counters.zero_()
+    L.profile_enable(True)
+    L.profile_collect()
+    timed(step_resident, args.steps)
+    stage_ms, stage_cnt = L.profile_collect()
+    L.profile_enable(False)
+    model.collect_counters = False
+    cnt = model.counters.cpu().numpy().astype(np.float64) / args.steps
+    M_in, M_v, M_a = cnt[L.CNT_M_IN], cnt[L.CNT_M_V], cnt[L.CNT_M_A]
+
+    # correctness of what was timed: a slice of the frame against the oracle (outside the timed region)
+    check = None
+    if rank == 0:
+        from oracle import tensorf_oracle as orc
+        sl = slice(n // 2, n // 2 + 512)
+        sub = dict(case, rays=case["rays"][sl])
+        ref = orc.run_case(sub, want_stages=False)
+        got = step_resident()
+        check = float(np.abs(got[0][sl].cpu().numpy() - ref["rgb_map"]).max())
+
+    total_rays = n * world
+    value = total_rays / (ms_total / args.steps * 1e-3)
+    e2e_value = total_rays / (ms_e2e / args.steps * 1e-3)
+    hbm_peak, peak_src = peaks()
+    # algorithmic bytes per launch of the dominant kernel (k_march), DESIGN.md §roofline:
+    #   24 B ray + 4 B depth + 4 B acc per ray, 1 B alpha-mask bits per in-box sample (8 taps x 1 bit; the
+    #   reference's fp32 volume would be 32 B), 1152 B of factor taps per gathered sample, 12 B per entry.
+    launches_march = max(1, stage_cnt["march"])
+    march_ms = stage_ms["march"] / launches_march
+    bytes_march_step = 32.0 * n + 1.0 * M_in + 1152.0 * M_v + 12.0 * M_a
+    bytes_per_launch = bytes_march_step * args.steps / launches_march
+    achieved = bytes_per_launch / (march_ms * 1e-3) / 1e9
+    bytes_app_step = 3456.0 * M_a
+    app_ms = stage_ms["app"] / max(1, stage_cnt["app"])
+    roof = {"bound": "hbm", "kernel": "k_march (march+mask+density gather+composite)", "achieved": achieved,
+            "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+            "peak_source": peak_src, "ms_per_launch": march_ms, "launches_per_step": launches_march / args.steps,
+            "algorithmic_bytes_per_launch": bytes_per_launch,
+            "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items() if v},
+            "app_stage": {"algorithmic_gather_GBps": bytes_app_step * args.steps / max(1, stage_cnt["app"]) /
+                          (app_ms * 1e-3) / 1e9 if app_ms else None,
+                          "dense_TFLOPs": 79712.0 * M_a * args.steps / max(1, stage_cnt["app"]) / (app_ms * 1e-3) / 1e12
+                          if app_ms else None},
+            "reference_equivalent_bytes_per_step": 40.0 * n + 32.0 * M_in + 1152.0 * M_v + 3456.0 * M_a}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if args.mlp == "fp32" else f"f32 gather/composite + {args.mlp} tensor-core MLP",
+            "data": "synthetic",
+            "config": {"workload": workload_name(args), "n_samples": S, "rays_per_step_per_gpu": n,
+                       "mlp": args.mlp, "early_ray_termination": True, "l2": "flushed before every timed step "
+                       "(256 MiB write)", "parallelism": f"one frame per rank x {world}",
+                       "samples_per_s_marched": value * S, "samples_per_s_gathered": M_v * world / (ms_total / args.steps * 1e-3),
+                       "per_step_counts": {"M_in": M_in, "M_v_gathered": M_v, "M_a": M_a}},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(rays_host.numel() * 4),
+                    "d2h_bytes_per_step": int(rgb_host.numel() * 4 + depth_host.numel() * 4),
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(sum(stage_cnt.values())),
+            "clocks": clocks, "roofline": roof, "max_abs_err_vs_oracle_512rays": check}
+
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            v, dt, desc = time_cpu_reference(case, args.cpu_sample_chunks)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                                    "sample": desc + f" ({dt:.1f} s)", "note": "oracle restatement of the reference "
+                                    "(torch CPU, reference op sequence); Jittor itself is absent from the image"}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

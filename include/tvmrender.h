@@ -171,6 +171,20 @@ int tvm_density_alpha(const TvmModel* m_host, const float* xyz, int n_pts, float
 int tvm_mse_loss(const float* rgb_map, const float* target, int n_rays, float grad_scale,
                  float* loss_out, float* d_rgb_map, void* stream);
 
+/* ---- measurement hooks (bench.py's roofline leg; off by default) ------------------------------ */
+/* When enabled, every kernel tvm_forward / tvm_backward launches is bracketed by cudaEvents on the
+ * caller's stream.  Stages: see TVM_STAGE_*.  Process-global, not thread-safe: benchmarking only. */
+#define TVM_STAGE_MARCH      0
+#define TVM_STAGE_APP        1
+#define TVM_STAGE_COMPOSITE  2
+#define TVM_STAGE_BWD_APP    3
+#define TVM_STAGE_BWD_MARCH  4
+#define TVM_STAGE_COUNT      8
+int tvm_profile_enable(int on);
+/* waits for the recorded events, adds per-stage milliseconds / launch counts into the two
+ * [TVM_STAGE_COUNT] host arrays and clears the records */
+int tvm_profile_collect(float* ms_by_stage_host, int* launches_by_stage_host);
+
 #ifdef __cplusplus
 }
 #endif

@@ -20,6 +20,8 @@ MLP_BF16 = 0x10
 MLP_BF16X3 = 0x20
 ACT_SOFTPLUS, ACT_RELU = 0, 1
 CNT_M_IN, CNT_M_V, CNT_M_A, CNT_RAYS, CNT_WORDS = 0, 1, 2, 3, 8
+STAGE_NAMES = ["march", "app", "composite", "bwd_app", "bwd_march"]
+STAGE_COUNT = 8
 
 _f3 = C.c_float * 3
 _f6 = C.c_float * 6
@@ -57,6 +59,7 @@ EXPORTS = [
     "tvm_last_error", "tvm_abi_version", "tvm_device_count", "tvm_pack_grid", "tvm_unpack_grid",
     "tvm_pack_linear", "tvm_unpack_linear", "tvm_pack_alpha", "tvm_tc_weights_bytes", "tvm_pack_mlp_tc",
     "tvm_workspace_bytes", "tvm_forward", "tvm_backward", "tvm_density_alpha", "tvm_mse_loss",
+    "tvm_profile_enable", "tvm_profile_collect",
 ]
 
 
@@ -99,6 +102,8 @@ def load() -> C.CDLL:
                                  C.c_size_t, vp]
     lib.tvm_density_alpha.argtypes = [C.POINTER(TvmModel), vp, i32, f32, vp, vp]
     lib.tvm_mse_loss.argtypes = [vp, vp, i32, f32, vp, vp, vp]
+    lib.tvm_profile_enable.argtypes = [i32]
+    lib.tvm_profile_collect.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_int)]
     for name in EXPORTS:
         if name not in ("tvm_last_error", "tvm_tc_weights_bytes"):
             getattr(lib, name).restype = i32
@@ -122,3 +127,15 @@ def require_cuda():
         raise TvmError("no CUDA device visible to libtvmrender.so "
                        f"({lib.tvm_last_error().decode('utf-8', 'replace')}); there is no CPU fallback")
     return n
+
+
+def profile_enable(on: bool):
+    check(load().tvm_profile_enable(1 if on else 0), "tvm_profile_enable")
+
+
+def profile_collect():
+    """-> ({stage: ms}, {stage: launches}) accumulated since the last collect."""
+    ms = (C.c_float * STAGE_COUNT)()
+    cnt = (C.c_int * STAGE_COUNT)()
+    check(load().tvm_profile_collect(ms, cnt), "tvm_profile_collect")
+    return ({n: float(ms[i]) for i, n in enumerate(STAGE_NAMES)}, {n: int(cnt[i]) for i, n in enumerate(STAGE_NAMES)})

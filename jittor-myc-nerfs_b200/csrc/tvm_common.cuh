@@ -94,6 +94,17 @@ inline int in_mlp_c(const TvmModel& m) { return 2 * m.view_pe * 3 + 2 * m.fea_pe
 
 int validate_model(const TvmModel& m);
 
+// measurement hooks (tvm_profile_enable): RAII bracket of one kernel launch with cudaEvents
+bool profile_on();
+void profile_begin(int stage, cudaStream_t s);
+void profile_end(cudaStream_t s);
+struct ProfileScope {
+  cudaStream_t s;
+  bool on;
+  ProfileScope(int stage, cudaStream_t s_) : s(s_), on(profile_on()) { if (on) profile_begin(stage, s); }
+  ~ProfileScope() { if (on) profile_end(s); }
+};
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -434,27 +434,33 @@ extern "C" int tvm_forward(const TvmModel* m_host, const float* rays, int n_rays
     if (P.aux.rgb) TVM_CHECK_CUDA(cudaMemsetAsync(P.aux.rgb, 0, (size_t)n_rays * n_samples * 12, stream));
   }
   const int march_blocks = (n_rays + kMarchWarps - 1) / kMarchWarps;
-  if (has_aux)
-    k_march<true><<<march_blocks, kMarchWarps * 32, 0, stream>>>(P);
-  else
-    k_march<false><<<march_blocks, kMarchWarps * 32, 0, stream>>>(P);
+  {
+    ProfileScope prof(TVM_STAGE_MARCH, stream);
+    if (has_aux)
+      k_march<true><<<march_blocks, kMarchWarps * 32, 0, stream>>>(P);
+    else
+      k_march<false><<<march_blocks, kMarchWarps * 32, 0, stream>>>(P);
+  }
   TVM_CHECK_CUDA(cudaGetLastError());
 
   const uint32_t mlp = flags & TVM_MLP_MASK;
   if (mlp == TVM_MLP_FP32) {
     const size_t smem = (size_t)kAppTile * (P.hs + P.xs) * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
-      TVM_CHECK_CUDA(cudaFuncSetAttribute(k_app_simt, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      attr_set = true;
-    }
+    TVM_CHECK_CUDA(cudaFuncSetAttribute(k_app_simt, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     TVM_REQUIRE(smem <= 200 * 1024, "appearance tile does not fit shared memory");
-    k_app_simt<<<device_sms() * 2, kAppThreads, smem, stream>>>(P);
+    {
+      ProfileScope prof(TVM_STAGE_APP, stream);
+      k_app_simt<<<device_sms() * 2, kAppThreads, smem, stream>>>(P);
+    }
     TVM_CHECK_CUDA(cudaGetLastError());
   } else {
+    ProfileScope prof(TVM_STAGE_APP, stream);
     if (int rc = launch_app_tc(P, device_sms(), stream)) return rc;
   }
-  k_composite<<<(n_rays + 7) / 8, 256, 0, stream>>>(P);
+  {
+    ProfileScope prof(TVM_STAGE_COMPOSITE, stream);
+    k_composite<<<(n_rays + 7) / 8, 256, 0, stream>>>(P);
+  }
   TVM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -7,6 +7,7 @@
 // through a 32x33 shared-memory transpose tile.
 #include <stdarg.h>
 #include <string.h>
+#include <vector>
 #include "tvm_common.cuh"
 
 namespace tvm {
@@ -19,6 +20,24 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+
+struct ProfRec { int stage; cudaEvent_t a, b; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static std::vector<cudaEvent_t> g_ev_pool;
+static cudaEvent_t get_event() {
+  if (!g_ev_pool.empty()) { cudaEvent_t e = g_ev_pool.back(); g_ev_pool.pop_back(); return e; }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+bool profile_on() { return g_prof_on; }
+void profile_begin(int stage, cudaStream_t s) {
+  ProfRec r{stage, get_event(), get_event()};
+  cudaEventRecord(r.a, s);
+  g_prof.push_back(r);
+}
+void profile_end(cudaStream_t s) { cudaEventRecord(g_prof.back().b, s); }
 
 int validate_model(const TvmModel& m) {
   TVM_REQUIRE(m.n_density > 0 && m.n_density % 4 == 0, "n_density must be a positive multiple of 4");
@@ -131,6 +150,28 @@ using namespace tvm;
 
 extern "C" const char* tvm_last_error(void) { return g_err; }
 extern "C" int tvm_abi_version(void) { return TVM_ABI_VERSION; }
+
+extern "C" int tvm_profile_enable(int on) {
+  g_prof_on = on != 0;
+  return 0;
+}
+
+extern "C" int tvm_profile_collect(float* ms_by_stage, int* launches_by_stage) {
+  TVM_REQUIRE(ms_by_stage && launches_by_stage, "bad arguments");
+  for (auto& r : g_prof) {
+    TVM_CHECK_CUDA(cudaEventSynchronize(r.b));
+    float ms = 0.0f;
+    TVM_CHECK_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+    if (r.stage >= 0 && r.stage < TVM_STAGE_COUNT) {
+      ms_by_stage[r.stage] += ms;
+      launches_by_stage[r.stage] += 1;
+    }
+    g_ev_pool.push_back(r.a);
+    g_ev_pool.push_back(r.b);
+  }
+  g_prof.clear();
+  return 0;
+}
 
 extern "C" int tvm_device_count(void) {
   int n = 0;

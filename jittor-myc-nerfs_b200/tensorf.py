@@ -497,6 +497,21 @@ class TensorVMSplit(torch.nn.Module):
         return out.view(xyz_locs.shape[:-1])
 
 
+def model_from_params(p, device="cuda:0", alpha_volume=None, alpha_aabb=None, mlp_mode="fp32"):
+    """TensorVMSplit from a parameter record with the reference's shapes (e.g. oracle.fixtures.ModelParams)."""
+    dev = torch.device(device)
+    m = TensorVMSplit(p.aabb, p.gridSize, dev, density_n_comp=list(p.density_n_comp),
+                      appearance_n_comp=list(p.app_n_comp), app_dim=p.app_dim, near_far=list(p.near_far),
+                      shadingMode="MLP_Fea", density_shift=p.density_shift, distance_scale=p.distance_scale,
+                      rayMarch_weight_thres=p.rayMarch_weight_thres, view_pe=p.view_pe, fea_pe=p.fea_pe,
+                      featureC=p.featureC, step_ratio=p.step_ratio, fea2denseAct=p.fea2denseAct)
+    m.load_numpy_params(p)
+    if alpha_volume is not None:
+        m.alphaMask = AlphaGridMask(dev, alpha_aabb if alpha_aabb is not None else p.aabb, alpha_volume)
+    m.mlp_mode = mlp_mode
+    return m
+
+
 def unpack_bits(bits: torch.Tensor, S: int) -> np.ndarray:
     """[n, NB] int32 device words -> [n, S] bool numpy (bit j of word b = sample 32*b + j)."""
     w = bits.detach().cpu().numpy().view(np.uint32)

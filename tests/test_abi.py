@@ -1,0 +1,59 @@
+"""The C-ABI library loads and exports every symbol include/tvmrender.h declares (no compute calls)."""
+import ctypes
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "tvmrender.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(tvm_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported(built_lib):
+    syms = _declared_symbols()
+    assert len(syms) >= 14
+    lib = ctypes.CDLL(built_lib.LIB_PATH)
+    missing = [s for s in syms if not hasattr(lib, s)]
+    assert not missing, missing
+    assert sorted(built_lib._lib.EXPORTS) == syms
+
+
+def test_abi_version_and_struct_sizes(built_lib):
+    lib = built_lib._lib.load()
+    assert lib.tvm_abi_version() == built_lib._lib.ABI_VERSION
+    # the ctypes mirrors must match the C layout: compile a tiny probe with the real header
+    import subprocess, tempfile
+    probe = r'''
+#include <stdio.h>
+#include "tvmrender.h"
+int main(){ printf("%zu %zu %zu\n", sizeof(TvmModel), sizeof(TvmAux), sizeof(TvmGrads)); return 0; }
+'''
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "p.c"), "w").write(probe)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "p"),
+                               os.path.join(d, "p.c")])
+        out = subprocess.check_output([os.path.join(d, "p")]).split()
+    L = built_lib._lib
+    assert [int(x) for x in out] == [ctypes.sizeof(L.TvmModel), ctypes.sizeof(L.TvmAux), ctypes.sizeof(L.TvmGrads)]
+
+
+def test_fails_loudly_without_gpu(built_lib):
+    """On a box without a CUDA device the product path must raise, not fall back."""
+    import pytest
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(built_lib.TvmError):
+        built_lib.TensorVMSplit([[-1, -1, -1], [1, 1, 1]], [8, 8, 8], "cuda", shadingMode="MLP_Fea")
+
+
+def test_workspace_bytes(built_lib):
+    lib = built_lib._lib.load()
+    out = ctypes.c_size_t(0)
+    assert lib.tvm_workspace_bytes(4096, 440, ctypes.byref(out)) == 0
+    assert out.value >= 4096 * 440 * 24
+    assert lib.tvm_workspace_bytes(0, 440, ctypes.byref(out)) != 0
+    assert b"bad arguments" in lib.tvm_last_error()

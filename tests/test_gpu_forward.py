@@ -1,0 +1,135 @@
+"""GPU parity of tvm_forward (through the C ABI) against the CPU oracle.
+
+Tolerances (BASELINE.json north_star): valid-sample indices and alpha-mask decisions bit-exact;
+rgb/depth within 1e-4 abs with the fp32 appearance head; PSNR delta < 0.01 dB."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+RGB_TOL = 1e-4      # north_star: rgb within 1e-4 abs in fp32
+DEPTH_TOL = 1e-4    # north_star: depth within 1e-4 abs
+
+
+@pytest.fixture(scope="module")
+def env(built_lib):
+    import torch
+    from oracle import fixtures as fx, tensorf_oracle as orc
+    built_lib._lib.require_cuda()
+    return built_lib, torch, fx, orc
+
+
+def _check_aux(pkg, torch, orc, case, white_bg=True, S=-1):
+    from util import gpu_model
+    model = gpu_model(pkg, case)
+    rays = torch.from_numpy(case["rays"]).cuda()
+    jit = None if case["jitter"] is None else torch.from_numpy(case["jitter"]).cuda()
+    ref = orc.run_case(case, N_samples=S, white_bg=white_bg)
+    Sx = ref["nSamples"] if S <= 0 else S
+    out = model.forward_with_aux(rays, white_bg=white_bg, N_samples=S, jitter=jit)
+    torch.cuda.synchronize()
+    bbox = pkg.unpack_bits(out["bbox_bits"], Sx)
+    valid = pkg.unpack_bits(out["valid_bits"], Sx)
+    app = pkg.unpack_bits(out["app_bits"], Sx)
+    assert np.array_equal(bbox, ref["bbox_valid"]), "in-bbox mask differs"
+    assert np.array_equal(valid, ref["ray_valid"]), "ray_valid (alpha-mask decisions) differs"
+    n_app_mis = int((app != ref["app_mask"]).sum())
+    # app_mask is a float threshold (weight > 1e-4), not in the bit-exact set: allow ulp-level flips
+    assert n_app_mis <= max(2, int(2e-4 * max(1, ref["app_mask"].sum()))), f"{n_app_mis} app_mask mismatches"
+    sig = out["sigma"].cpu().numpy()
+    assert np.allclose(sig, ref["sigma"], rtol=2e-5, atol=1e-7)
+    assert np.abs(out["weight"].cpu().numpy() - ref["weight"]).max() <= 2e-6
+    both = app & ref["app_mask"]
+    rgb_s = out["rgb"].cpu().numpy()
+    assert np.abs(rgb_s[both] - ref["rgb"][both]).max(initial=0) <= 2e-5
+    assert np.abs(out["rgb_map"].cpu().numpy() - ref["rgb_map"]).max() <= RGB_TOL
+    d_err = np.abs(out["depth_map"].cpu().numpy() - ref["depth_map"]).max()
+    assert d_err <= DEPTH_TOL, d_err
+    return model, rays, jit, ref, out
+
+
+@pytest.mark.parametrize("regime", ["R0", "R1", "R2"])
+def test_forward_aux_parity_128(env, regime):
+    pkg, torch, fx, orc = env
+    case = fx.make_case(128, 2048, regime)
+    _check_aux(pkg, torch, orc, case)
+
+
+def test_forward_train_jitter_and_black_bg(env):
+    pkg, torch, fx, orc = env
+    case = fx.make_case(128, 1024, "R2", train=True)
+    _check_aux(pkg, torch, orc, case, white_bg=False, S=443)   # cal_n_samples value used in training
+
+
+def test_forward_ert_path_matches(env):
+    """The production path (no aux, early ray termination on) against the oracle, and chunk invariance."""
+    pkg, torch, fx, orc = env
+    from util import gpu_model, psnr
+    for regime in ("R1", "R2"):
+        case = fx.make_case(128, 4096, regime)
+        ref = orc.run_case(case, want_stages=False)
+        model = gpu_model(pkg, case)
+        rays = torch.from_numpy(case["rays"]).cuda()
+        with torch.no_grad():
+            rgb, _, depth, _, _ = pkg.OctreeRender_trilinear_fast(rays, model, chunk=4096, N_samples=-1,
+                                                                  white_bg=True, is_train=False)
+            model.early_termination = False
+            rgb2, depth2 = model(rays)
+            model.early_termination = True
+            rgb3 = torch.cat([model(rays[s:s + 1000])[0] for s in range(0, 4096, 1000)])
+        rgb, depth, rgb2 = rgb.cpu().numpy(), depth.cpu().numpy(), rgb2.cpu().numpy()
+        assert np.abs(rgb - ref["rgb_map"]).max() <= RGB_TOL
+        assert np.abs(rgb2 - ref["rgb_map"]).max() <= RGB_TOL
+        assert np.abs(depth - ref["depth_map"]).max() <= DEPTH_TOL
+        assert np.array_equal(rgb3.cpu().numpy(), rgb), "result depends on the chunking"
+        # PSNR delta < 0.01 dB against a random target image
+        tgt = fx.target_rgb(4096)
+        assert abs(psnr(rgb, tgt) - psnr(ref["rgb_map"], tgt)) < 0.01
+
+
+def test_forward_300_grid_mask200(env):
+    pkg, torch, fx, orc = env
+    case = fx.make_case(300, 1024, "R1")
+    _check_aux(pkg, torch, orc, case)
+
+
+def test_edge_cases(env):
+    """Ragged ray counts, rays that miss the box, axis-aligned rays (d component == 0 -> 1e-6 rule),
+    a ray starting inside the box, S not a multiple of 32, non-cubic grid."""
+    pkg, torch, fx, orc = env
+    case = fx.make_case((64, 80, 100), 37, "R2", mask_res=(50, 60, 70))
+    rays = case["rays"].copy()
+    rays[0] = [0.3, 0.2, 12.0, 0, 0, -1]          # straight down the z axis: two zero components
+    rays[1] = [12.0, 0.1, -0.2, -1, 0, 0]
+    rays[2] = [0.0, 0.0, 0.0, 0.6, 0.8, 0.0]      # starts inside the box (t_min clamps to near)
+    rays[3] = [20.0, 20.0, 20.0, 0.0, 0.0, 1.0]   # misses the box
+    rays[4] = [5.0, 0.0, 12.0, 0, 0, -1]          # grazes the x = +5 face exactly (strict > keeps it inside)
+    rays[5] = [-12.0, 5.0, 5.0, 1, 0, 0]          # runs along an edge
+    case["rays"] = rays
+    for S in (-1, 33, 95, 1):
+        _check_aux(pkg, torch, orc, case, S=S)
+    one = dict(case, rays=rays[:1].copy())
+    _check_aux(pkg, torch, orc, one)
+
+
+def test_no_cpu_fallback(env):
+    pkg, torch, fx, orc = env
+    from util import gpu_model
+    case = fx.make_case(32, 8, "R0")
+    model = gpu_model(pkg, case)
+    with pytest.raises(Exception):
+        model(torch.from_numpy(case["rays"]))     # host tensor: must not be silently computed on the CPU
+
+
+def test_compute_alpha(env):
+    pkg, torch, fx, orc = env
+    from util import gpu_model
+    case = fx.make_case(64, 8, "R2", mask_res=64)
+    model = gpu_model(pkg, case)
+    rng = np.random.default_rng(5)
+    xyz = rng.uniform(-5, 5, (5000, 3)).astype(np.float32)
+    o = orc.OracleTensorVMSplit(case["model"], case["alpha_volume"], case["alpha_aabb"])
+    ref = o.compute_alpha(torch.from_numpy(xyz), float(o.stepSize)).numpy()
+    got = model.compute_alpha(torch.from_numpy(xyz).cuda(), float(model.stepSize)).cpu().numpy()
+    assert np.array_equal(got > 0, ref > 0)
+    assert np.allclose(got, ref, rtol=2e-5, atol=1e-7)
