@@ -1,15 +1,417 @@
-// tcgen05 tensor-core appearance head (placeholder until the UMMA path lands).
+// Appearance head on the 5th-generation tensor cores (tcgen05 / TMEM), sm_100a only.
+//
+// Replaces k_app_simt for TVM_MLP_BF16: per tile of 128 weighted samples
+//   gather   48-channel plane x line products (tensoRF.py:228-243)      -> A0 [128 x 144] bf16 in smem
+//   GEMM0    A0 . basis_mat^T  (tensoRF.py:244)                         -> TMEM [128 x 32] fp32
+//   epi0     positional encoding of features / view dir (tensorBase.py:9-15,76-83) -> A1 [128 x 160] bf16
+//   GEMM1    A1 . W1^T, epi1: +b1, ReLU                                 -> A2 [128 x 128] bf16
+//   GEMM2    A2 . W2^T, epi2: +b2, ReLU, 128->3 layer on CUDA cores, sigmoid (tensorBase.py:84-86)
+// Operands live in shared memory in the UMMA K-major no-swizzle ("interleaved") canonical layout:
+// 8-row x 16-byte core matrices; element (r, k) of a [R x K] bf16 operand sits at
+//   (k/8) * (R*16) + r*16 + (k%8)*2        (LBO = R*16 bytes between K-chunks, SBO = 128 bytes between 8-row groups)
+// so that one thread (= one row) writes whole 16-byte chunks, conflict-free.  Accumulators are read
+// back with tcgen05.ld (32x32b: thread t of warp w owns TMEM lane 32*(w%4)+t = tile row).
+// One thread issues the MMAs; completion is signalled through tcgen05.commit -> mbarrier.
+#include <cuda_bf16.h>
 #include "tvm_common.cuh"
+
 namespace tvm {
-int launch_app_tc(const FwdParams& P, int num_sms, cudaStream_t stream) {
-  (void)P; (void)num_sms; (void)stream;
-  set_error("tensor-core appearance head not built in this library");
-  return -3;
+
+namespace tc {
+
+constexpr int kRows = 128;          // UMMA M
+constexpr int kThreads = 256;
+constexpr int kTmemCols = 256;      // [0,128): layer accumulators, [128,160): basis accumulator
+constexpr int kColBasis = 128;
+
+// ---- PTX wrappers ----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(a), "r"(parity)
+        : "memory");
+    if (spin > (1u << 24)) __trap();   // a lost tcgen05.commit must fail the launch, not hang the GPU
+  }
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols));
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols));
+}
+__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem]^T, kind::f16 (bf16 inputs, fp32 accumulate), M=128, K=16
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread t gets lane (base lane + t)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, no swizzle: LBO = byte distance between K-adjacent core matrices, SBO = between 8-row groups
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) |
+         ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
+}
+// bf16 x bf16 -> f32, both operands K-major
+__host__ __device__ constexpr uint32_t instr_desc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// Byte layout of the weight image built by tvm_pack_mlp_tc (copied verbatim into shared memory)
+struct Image {
+  int K0, K1;                    // padded reduction lengths of GEMM0 / GEMM1 (multiples of 16)
+  uint32_t off_b0, off_b1, off_b2, off_f32, bytes;
+  __host__ __device__ Image(int n_app, int in_c) {
+    K0 = 3 * n_app;
+    K1 = (in_c + 15) / 16 * 16;
+    off_b0 = 0;
+    off_b1 = off_b0 + (uint32_t)K0 * 32 * 2;
+    off_b2 = off_b1 + (uint32_t)K1 * 128 * 2;
+    off_f32 = off_b2 + 128u * 128 * 2;
+    bytes = off_f32 + (128 + 128 + 3 * 128 + 4) * 4;
+  }
+};
+
+}  // namespace tc
+
+using namespace tc;
+
+// fp32 [K][ldw] (row j = input j) -> bf16 UMMA image [(K_pad/8)][N][8]; out-of-range entries are 0
+__global__ void k_pack_umma_b(const float* __restrict__ w_t, int K, int K_pad, int N_real, int N, int ldw,
+                              __nv_bfloat16* __restrict__ img) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= K_pad * N) return;
+  const int kc = i / (N * 8), rem = i % (N * 8), n = rem / 8, kk = rem % 8;
+  const int k = kc * 8 + kk;
+  const float v = (k < K && n < N_real) ? w_t[(size_t)k * ldw + n] : 0.0f;
+  img[i] = __float2bfloat16_rn(v);
+}
+__global__ void k_pack_tc_f32(const TvmModel m, float* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 128) dst[i] = m.b1[i];
+  else if (i < 256) dst[i] = m.b2[i - 128];
+  else if (i < 640) dst[i] = m.w3[i - 256];
+  else if (i < 644) dst[i] = (i - 640) < 3 ? m.b3[i - 640] : 0.0f;
+}
+
+// ------------------------------------------------------------------------------------------------
+template <int CA, int APP_DIM, int FEA_PE, int VIEW_PE>
+__global__ void __launch_bounds__(kThreads, 1) k_app_tc(const FwdParams P) {
+  constexpr int IN_C = 2 * VIEW_PE * 3 + 2 * FEA_PE * APP_DIM + 3 + APP_DIM;
+  constexpr int K0 = 3 * CA;
+  constexpr int K1 = (IN_C + 15) / 16 * 16;
+  constexpr int KA = (K0 > K1 ? K0 : K1) > 128 ? (K0 > K1 ? K0 : K1) : 128;
+  static_assert(FEA_PE == 2 && VIEW_PE == 2, "the register-resident PE builder is written for 2 frequencies");
+  static_assert(K0 % 16 == 0 && APP_DIM <= 32, "unsupported shape");
+
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const Image img(CA, IN_C);
+  uint8_t* sW = smem;                                   // weight image (bf16 operands + fp32 tail)
+  uint8_t* sA = smem + ((img.bytes + 1023) & ~1023u);   // activation operand [128 x KA] bf16
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sA + kRows * KA * 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 2);
+  const float* sB1 = reinterpret_cast<const float*>(sW + img.off_f32);
+  const float* sB2 = sB1 + 128;
+  const float* sW3 = sB2 + 128;
+  const float* sB3 = sW3 + 3 * 128;
+
+  const TvmModel& m = P.m;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  // ---- one-time setup: weights -> smem, barrier, TMEM --------------------------------------------
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(m.tc_weights);
+    uint4* dst = reinterpret_cast<uint4*>(sW);
+    for (uint32_t i = tid; i < img.bytes / 16; i += kThreads) dst[i] = __ldg(src + i);
+  }
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, kTmemCols);
+  fence_async_smem();
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem = *tmem_slot;
+  uint32_t phase = 0;
+
+  const uint32_t aA = smem_u32(sA);
+  const uint32_t aB0 = smem_u32(sW + img.off_b0), aB1 = smem_u32(sW + img.off_b1), aB2 = smem_u32(sW + img.off_b2);
+  constexpr uint32_t LBO_A = kRows * 16, LBO_B0 = 32 * 16, LBO_B = 128 * 16, SBO = 128;
+  constexpr uint32_t IDESC_N32 = instr_desc(128, 32), IDESC_N128 = instr_desc(128, 128);
+
+  const uint32_t n_ent = *P.ws.n_entries;
+  const uint32_t n_tiles = (n_ent + kRows - 1) / kRows;
+
+  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const uint32_t tile_base = tile * kRows;
+
+    // ---- gather: 8 warps x 16 rows, 4 lanes per row, bf16 straight into the GEMM0 operand -------
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+      const int row = warp * 16 + pass * 8 + (lane >> 2), q = lane & 3;
+      const uint32_t e = tile_base + row;
+      uint8_t* arow = sA + row * 16;
+      if (e < n_ent) {
+        const uint2 en = P.ws.ent[e];
+        float u[3], dir[3];
+        entry_coords(m, P.rays, P.jitter, en.x, en.y, u, dir);
+        Axis ax[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) ax[i] = axis_taps(u[i], m.grid[i]);
+#pragma unroll
+        for (int kk = 0; kk < 3; ++kk) {
+          const VmTaps t = vm_taps(m, ax, kk);
+#pragma unroll
+          for (int c = q * 4; c < CA; c += 16) {
+            float4 pv, lv;
+            vm_sample4(m.app_plane[kk], m.app_line[kk], t, CA, c, pv, lv);
+            const int k = kk * CA + c;
+            uint2 packed = make_uint2(pack_bf16(pv.x * lv.x, pv.y * lv.y), pack_bf16(pv.z * lv.z, pv.w * lv.w));
+            *reinterpret_cast<uint2*>(arow + (k >> 3) * LBO_A + (k & 7) * 2) = packed;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int kk = 0; kk < 3; ++kk)
+#pragma unroll
+          for (int c = q * 4; c < CA; c += 16) {
+            const int k = kk * CA + c;
+            *reinterpret_cast<uint2*>(arow + (k >> 3) * LBO_A + (k & 7) * 2) = make_uint2(0u, 0u);
+          }
+      }
+    }
+    fence_async_smem();
+    __syncthreads();
+
+    // ---- GEMM0: feat = A0 . basis^T ---------------------------------------------------------------
+    if (tid == 0) {
+      fence_after();
+#pragma unroll
+      for (int k = 0; k < K0 / 16; ++k)
+        umma_bf16(tmem + kColBasis, smem_desc(aA + k * 2 * LBO_A, LBO_A, SBO),
+                  smem_desc(aB0 + k * 2 * LBO_B0, LBO_B0, SBO), IDESC_N32, k > 0);
+      umma_commit(bar);
+    }
+
+    // view directions of this thread's row (threads 0..127 own one row each from here on)
+    const int row = tid & (kRows - 1);
+    const uint32_t e = tile_base + row;
+    const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    if (tid < kRows) {
+      float dir[3] = {0.0f, 0.0f, 0.0f};
+      if (e < n_ent) {
+        const uint32_t ray = P.ws.ent[e].x;
+        dir[0] = P.rays[6 * (size_t)ray + 3];
+        dir[1] = P.rays[6 * (size_t)ray + 4];
+        dir[2] = P.rays[6 * (size_t)ray + 5];
+      }
+      mbar_wait(bar, phase);
+      fence_after();
+      // ---- epi0: features -> [feat, view, sin/cos PE] as bf16, K-chunk by K-chunk ---------------
+      float x[32];
+      tmem_ld32(lane_addr + kColBasis, x);
+      // column c of the MLP input (tensorBase.py:76-83, 9-15): generated on the fly from feat / dir
+      float s1[APP_DIM + 3], c1[APP_DIM + 3];
+#pragma unroll
+      for (int o = 0; o < APP_DIM; ++o) __sincosf(x[o], &s1[o], &c1[o]);
+#pragma unroll
+      for (int o = 0; o < 3; ++o) __sincosf(dir[o], &s1[APP_DIM + o], &c1[APP_DIM + o]);
+      auto column = [&](int c) -> float {
+        constexpr int PF = APP_DIM + 3, NF = FEA_PE * APP_DIM, PV = PF + 2 * NF, NV = VIEW_PE * 3;
+        if (c < APP_DIM) return x[c];
+        if (c < PF) return dir[c - APP_DIM];
+        if (c < PF + NF) { const int o = (c - PF) >> 1; return ((c - PF) & 1) ? 2.0f * s1[o] * c1[o] : s1[o]; }
+        if (c < PV) { const int o = (c - PF - NF) >> 1; return ((c - PF - NF) & 1) ? 1.0f - 2.0f * s1[o] * s1[o] : c1[o]; }
+        if (c < PV + NV) { const int o = APP_DIM + ((c - PV) >> 1); return ((c - PV) & 1) ? 2.0f * s1[o] * c1[o] : s1[o]; }
+        if (c < PV + 2 * NV) { const int o = APP_DIM + ((c - PV - NV) >> 1); return ((c - PV - NV) & 1) ? 1.0f - 2.0f * s1[o] * s1[o] : c1[o]; }
+        return 0.0f;
+      };
+      uint8_t* arow = sA + row * 16;
+#pragma unroll
+      for (int kc = 0; kc < K1 / 8; ++kc) {
+        uint4 v;
+        v.x = pack_bf16(column(kc * 8 + 0), column(kc * 8 + 1));
+        v.y = pack_bf16(column(kc * 8 + 2), column(kc * 8 + 3));
+        v.z = pack_bf16(column(kc * 8 + 4), column(kc * 8 + 5));
+        v.w = pack_bf16(column(kc * 8 + 6), column(kc * 8 + 7));
+        *reinterpret_cast<uint4*>(arow + kc * LBO_A) = v;
+      }
+      fence_async_smem();
+      fence_before();
+    }
+    phase ^= 1;
+    __syncthreads();
+
+    // ---- GEMM1: A1 . W1^T ---------------------------------------------------------------------------
+    if (tid == 0) {
+      fence_after();
+#pragma unroll
+      for (int k = 0; k < K1 / 16; ++k)
+        umma_bf16(tmem, smem_desc(aA + k * 2 * LBO_A, LBO_A, SBO), smem_desc(aB1 + k * 2 * LBO_B, LBO_B, SBO),
+                  IDESC_N128, k > 0);
+      umma_commit(bar);
+    }
+    if (tid < kRows) {
+      mbar_wait(bar, phase);
+      fence_after();
+      // ---- epi1: +b1, ReLU -> A2 (bf16) -----------------------------------------------------------
+      uint8_t* arow = sA + row * 16;
+#pragma unroll
+      for (int cb = 0; cb < 4; ++cb) {
+        float y[32];
+        tmem_ld32(lane_addr + cb * 32, y);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j] + sB1[cb * 32 + j], 0.0f);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 v;
+          v.x = pack_bf16(y[g * 8 + 0], y[g * 8 + 1]);
+          v.y = pack_bf16(y[g * 8 + 2], y[g * 8 + 3]);
+          v.z = pack_bf16(y[g * 8 + 4], y[g * 8 + 5]);
+          v.w = pack_bf16(y[g * 8 + 6], y[g * 8 + 7]);
+          *reinterpret_cast<uint4*>(arow + (cb * 4 + g) * LBO_A) = v;
+        }
+      }
+      fence_async_smem();
+      fence_before();
+    }
+    phase ^= 1;
+    __syncthreads();
+
+    // ---- GEMM2: A2 . W2^T ---------------------------------------------------------------------------
+    if (tid == 0) {
+      fence_after();
+#pragma unroll
+      for (int k = 0; k < 128 / 16; ++k)
+        umma_bf16(tmem, smem_desc(aA + k * 2 * LBO_A, LBO_A, SBO), smem_desc(aB2 + k * 2 * LBO_B, LBO_B, SBO),
+                  IDESC_N128, k > 0);
+      umma_commit(bar);
+    }
+    if (tid < kRows) {
+      mbar_wait(bar, phase);
+      fence_after();
+      // ---- epi2: +b2, ReLU, 128 -> 3 on CUDA cores, sigmoid ---------------------------------------
+      float o0 = sB3[0], o1 = sB3[1], o2 = sB3[2];
+#pragma unroll
+      for (int cb = 0; cb < 4; ++cb) {
+        float y[32];
+        tmem_ld32(lane_addr + cb * 32, y);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float h = fmaxf(y[j] + sB2[cb * 32 + j], 0.0f);
+          o0 = fmaf(h, sW3[cb * 32 + j], o0);
+          o1 = fmaf(h, sW3[128 + cb * 32 + j], o1);
+          o2 = fmaf(h, sW3[256 + cb * 32 + j], o2);
+        }
+      }
+      if (e < n_ent) {
+        P.ws.ent_rgb[(size_t)e * 3 + 0] = 1.0f / (1.0f + __expf(-o0));
+        P.ws.ent_rgb[(size_t)e * 3 + 1] = 1.0f / (1.0f + __expf(-o1));
+        P.ws.ent_rgb[(size_t)e * 3 + 2] = 1.0f / (1.0f + __expf(-o2));
+      }
+      fence_before();
+    }
+    phase ^= 1;
+    __syncthreads();   // A operand and TMEM are free for the next tile
+  }
+
+  fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, kTmemCols);
+}
+
+// ------------------------------------------------------------------------------------------------
+static bool tc_supported(const TvmModel& m) {
+  return m.n_app == 48 && m.app_dim == 27 && m.fea_pe == 2 && m.view_pe == 2 && m.feature_c == 128;
+}
+
+int launch_app_tc(const FwdParams& P, int num_sms, cudaStream_t stream) {
+  TVM_REQUIRE((P.flags & TVM_MLP_MASK) == TVM_MLP_BF16, "only TVM_MLP_BF16 is implemented on the tensor-core path");
+  TVM_REQUIRE(tc_supported(P.m), "tensor-core appearance head supports n_app=48, app_dim=27, fea_pe=view_pe=2, "
+                                 "featureC=128 (all shipped configs); use TVM_MLP_FP32 otherwise");
+  TVM_REQUIRE(P.m.tc_weights != nullptr, "TvmModel.tc_weights is NULL: call tvm_pack_mlp_tc first");
+  const Image img(P.m.n_app, P.in_mlp_c);
+  const int KA = max(max(img.K0, img.K1), 128);
+  const size_t smem = ((img.bytes + 1023) & ~1023u) + (size_t)kRows * KA * 2 + 64 + 1024;
+  auto kern = k_app_tc<48, 27, 2, 2>;
+  TVM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<num_sms, kThreads, smem, stream>>>(P);
+  TVM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace tvm
-extern "C" size_t tvm_tc_weights_bytes(const TvmModel* m_host) { (void)m_host; return 0; }
-extern "C" int tvm_pack_mlp_tc(const TvmModel* m_host, void* out, void* stream) {
-  (void)m_host; (void)out; (void)stream;
-  tvm::set_error("tensor-core appearance head not built in this library");
-  return -3;
+
+using namespace tvm;
+
+extern "C" size_t tvm_tc_weights_bytes(const TvmModel* m_host) {
+  if (m_host == nullptr) return Image(48, 150).bytes;   // probe: "is the tensor-core path built?"
+  if (!tc_supported(*m_host)) return 0;
+  return Image(m_host->n_app, in_mlp_c(*m_host)).bytes;
+}
+
+extern "C" int tvm_pack_mlp_tc(const TvmModel* m_host, void* out, void* stream_) {
+  TVM_REQUIRE(m_host && out, "bad arguments");
+  if (int rc = validate_model(*m_host)) return rc;
+  TVM_REQUIRE(tc_supported(*m_host), "unsupported shape for the tensor-core appearance head");
+  cudaStream_t s = (cudaStream_t)stream_;
+  const int in_c = in_mlp_c(*m_host);
+  const Image img(m_host->n_app, in_c);
+  uint8_t* o = (uint8_t*)out;
+  auto launch = [&](const float* w_t, int K, int K_pad, int N_real, int N, int ldw, uint32_t off) {
+    const int n = K_pad * N;
+    k_pack_umma_b<<<(n + 255) / 256, 256, 0, s>>>(w_t, K, K_pad, N_real, N, ldw, (__nv_bfloat16*)(o + off));
+  };
+  launch(m_host->basis_t, img.K0, img.K0, m_host->app_dim, 32, kMaxAppDim, img.off_b0);
+  launch(m_host->w1_t, in_c, img.K1, 128, 128, kFeatureC, img.off_b1);
+  launch(m_host->w2_t, 128, 128, 128, 128, kFeatureC, img.off_b2);
+  k_pack_tc_f32<<<3, 256, 0, s>>>(*m_host, (float*)(o + img.off_f32));
+  TVM_CHECK_CUDA(cudaGetLastError());
+  return 0;
 }
