@@ -37,7 +37,8 @@ def _check_aux(pkg, torch, orc, case, white_bg=True, S=-1):
     # app_mask is a float threshold (weight > 1e-4), not in the bit-exact set: allow ulp-level flips
     assert n_app_mis <= max(2, int(2e-4 * max(1, ref["app_mask"].sum()))), f"{n_app_mis} app_mask mismatches"
     sig = out["sigma"].cpu().numpy()
-    assert np.allclose(sig, ref["sigma"], rtol=2e-5, atol=1e-7)
+    # log(1+exp(x)) (A3) quantises sigma to 2^-23 steps near x ~ -10: one expf ulp can move it a step
+    assert np.allclose(sig, ref["sigma"], rtol=2e-5, atol=2.5e-7)
     assert np.abs(out["weight"].cpu().numpy() - ref["weight"]).max() <= 2e-6
     both = app & ref["app_mask"]
     rgb_s = out["rgb"].cpu().numpy()
@@ -132,4 +133,33 @@ def test_compute_alpha(env):
     ref = o.compute_alpha(torch.from_numpy(xyz), float(o.stepSize)).numpy()
     got = model.compute_alpha(torch.from_numpy(xyz).cuda(), float(model.stepSize)).cpu().numpy()
     assert np.array_equal(got > 0, ref > 0)
-    assert np.allclose(got, ref, rtol=2e-5, atol=1e-7)
+    assert np.allclose(got, ref, rtol=2e-5, atol=2.5e-7)
+
+
+def test_tensor_core_mlp_bf16(env):
+    """TVM_MLP_BF16: tcgen05 appearance head; north_star tolerance 1e-2 on rgb, PSNR delta < 0.01 dB."""
+    pkg, torch, fx, orc = env
+    from util import gpu_model, psnr
+    for regime, G in (("R1", 128), ("R2", 128), ("R1", 300)):
+        case = fx.make_case(G, 2048, regime)
+        ref = orc.run_case(case, want_stages=False)
+        model = gpu_model(pkg, case, mlp_mode="bf16")
+        rays = torch.from_numpy(case["rays"]).cuda()
+        with torch.no_grad():
+            rgb, depth = model(rays)
+            model.mlp_mode = "fp32"
+            rgb32, _ = model(rays)
+        torch.cuda.synchronize()
+        rgb, rgb32 = rgb.cpu().numpy(), rgb32.cpu().numpy()
+        err = np.abs(rgb - ref["rgb_map"]).max()
+        print(f"bf16 MLP {regime} G={G}: max|rgb-oracle|={err:.3e} max|rgb-fp32 path|={np.abs(rgb - rgb32).max():.3e}")
+        assert err <= 1e-2
+        assert np.abs(depth.cpu().numpy() - ref["depth_map"]).max() <= DEPTH_TOL
+        tgt = fx.target_rgb(2048)
+        assert abs(psnr(rgb, tgt) - psnr(ref["rgb_map"], tgt)) < 0.01
+    # ragged tile (entries not a multiple of 128) and a single ray
+    case = fx.make_case(64, 3, "R2", mask_res=64)
+    ref = orc.run_case(case, want_stages=False)
+    model = gpu_model(pkg, case, mlp_mode="bf16")
+    rgb, _ = model(torch.from_numpy(case["rays"]).cuda())
+    assert np.abs(rgb.cpu().numpy() - ref["rgb_map"]).max() <= 1e-2
