@@ -1,8 +1,504 @@
-// Backward pass (placeholder).
-#include "tvm_common.cuh"
+// Backward pass of the TensoRF-VM ray renderer: d rgb_map -> gradients of every parameter
+// (row a12 of SURVEY.md §8a; the reference gets this from Jittor autograd, train.py:228,260).
+//
+// Recompute-based: nothing per-sample is saved by the forward pass except the appearance entry list
+// (ray, sample, weight, rgb).  Coordinates are detached (tensoRF.py:212-214,231-233) and depth_map is
+// built under no_grad (tensorBase.py:529-531), so only plane/line/basis/MLP parameters get gradients.
+//
+//   k_bwd_prep   per ray: clamp mask of d rgb_map, S = sum_k dL/dw_k * w_k (closed form from the forward sums)
+//   k_app_bwd    per tile of 64 entries: recompute the fp32 head, back-propagate through
+//                sigmoid / MLP / positional encoding / basis_mat, accumulate weight gradients
+//                (tile-level products, then red.global.add.v4.f32), scatter into app planes/lines
+//   k_march_bwd  per ray (one warp, same march as k_march): dL/dw -> dL/dalpha through the transmittance
+//                product with ONE forward sweep (suffix sums = total - prefix), -> dL/dsigma -> softplus'
+//                -> scatter into density planes/lines with vector atomics
+#include "tvm_app_simt.cuh"
+
+namespace tvm {
+
+struct BwdParams {
+  FwdParams f;
+  const float* d_rgb_map;
+  TvmGrads g;
+};
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void k_bwd_prep(const BwdParams B) {
+  const int ray = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ray >= B.f.n) return;
+  const float acc = B.f.ws.acc[ray];
+  const float bg = (B.f.flags & TVM_WHITE_BG) ? 1.0f - acc : 0.0f;
+  float g[3], tot = 0.0f, gs = 0.0f;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float s = B.f.ws.rgb_sum[(size_t)ray * 3 + c];
+    const float raw = s + bg;
+    g[c] = (raw >= 0.0f && raw <= 1.0f) ? B.d_rgb_map[(size_t)ray * 3 + c] : 0.0f;   // clamp(0,1) (tensorBase.py:527)
+    tot = fmaf(g[c], s, tot);
+    gs += g[c];
+  }
+  if (!(B.f.flags & TVM_WHITE_BG)) gs = 0.0f;
+  // sum_k dL/dw_k * w_k with dL/dw_k = g . rgb_k - gs   (rgb_map = sum w rgb + 1 - sum w)
+  float4 o = make_float4(g[0], g[1], g[2], tot - gs * acc);
+  reinterpret_cast<float4*>(B.f.ws.bwd_scratch)[ray] = o;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_app_bwd helpers
+// ------------------------------------------------------------------------------------------------
+// out[K][ldo] += A[64][0..K)^T . Bm[64][0..128)   (weight gradient of one dense layer for this tile)
+__device__ __forceinline__ void wgrad_tile_128(const float* A, const float* Bm, int st, int K, float* out, int ldo) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int o4 = lane * 4;
+  for (int j0 = warp * 4; j0 < K; j0 += 32) {
+    float acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[a][b] = 0.0f;
+#pragma unroll 4
+    for (int row = 0; row < kAppTile; ++row) {
+      const float4 bv = lds4(Bm + row * st + o4);
+      const float4 av = lds4(A + row * st + j0);     // broadcast; columns >= K are zero padding
+      fma4(acc[0], av.x, bv);
+      fma4(acc[1], av.y, bv);
+      fma4(acc[2], av.z, bv);
+      fma4(acc[3], av.w, bv);
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+      if (j0 + a < K) red_add_v4(out + (size_t)(j0 + a) * ldo + o4, acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
+  }
+}
+// out[K][32] += A[64][0..K)^T . Bm[64][0..32): one thread per j
+__device__ __forceinline__ void wgrad_tile_32(const float* A, const float* Bm, int st, int K, float* out) {
+  const int j = threadIdx.x;
+  if (j >= K) return;
+  float acc[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) acc[i] = 0.0f;
+  for (int row = 0; row < kAppTile; ++row) {
+    const float a = A[row * st + j];
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) fma4(acc + i, a, lds4(Bm + row * st + i));
+  }
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) red_add_v4(out + (size_t)j * kMaxAppDim + i, acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
+}
+// bias gradient: out[o] += sum_rows Bm[row][o], o < 128
+__device__ __forceinline__ void bgrad_tile(const float* Bm, int st, float* out) {
+  const int o = threadIdx.x;
+  if (o >= kFeatureC) return;
+  float a = 0.0f;
+  for (int row = 0; row < kAppTile; ++row) a += Bm[row * st + o];
+  atomicAdd(out + o, a);
+}
+// dIn[row][j] = sum_o dz[row][o] * Wt[j][o] for j in [0,K); optional ReLU mask from act (may alias dst).
+template <bool MASK>
+__device__ __forceinline__ void app_dense_bwd(const float* __restrict__ Wt, const float* dz, int K, float* dst,
+                                              const float* act, int st) {
+  const int row = threadIdx.x & (kAppTile - 1), part = threadIdx.x >> 6;
+  const int JP = ((K + 3) / 4 + 7) / 8 * 8;        // columns per part, multiple of 8
+  const int jbeg = part * JP, jend = min(K, jbeg + JP);
+  const float* d = dz + row * st;
+  for (int j0 = jbeg; j0 < jend; j0 += 8) {
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
+    for (int o = 0; o < kFeatureC; o += 4) {
+      const float4 dv = lds4(d + o);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (j0 + i < jend) {   // warp-uniform
+          const float4 w = ldg4(Wt + (size_t)(j0 + i) * kFeatureC + o);
+          acc[i] = fmaf(dv.x, w.x, fmaf(dv.y, w.y, fmaf(dv.z, w.z, fmaf(dv.w, w.w, acc[i]))));
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (j0 + i < jend) {
+        float v = acc[i];
+        if (MASK) v = act[row * st + j0 + i] > 0.0f ? v : 0.0f;
+        dst[row * st + j0 + i] = v;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kAppThreads) k_app_bwd(const BwdParams B) {
+  extern __shared__ __align__(16) float smem[];
+  const FwdParams& P = B.f;
+  const TvmModel& m = P.m;
+  const int st = P.st;
+  float* H = smem;                        // appearance vector h            -> later d h
+  float* X = smem + kAppTile * st;        // MLP input x
+  float* Y1 = smem + 2 * kAppTile * st;   // layer-1 output                 -> dz1 -> d feat
+  float* Y2 = smem + 3 * kAppTile * st;   // layer-2 output                 -> dz2 -> d x
+  float* D3 = smem + 4 * kAppTile * st;   // [64][4] dz3
+  const int tid = threadIdx.x;
+  const int row = tid & (kAppTile - 1), part = tid >> 6;
+  const int Ca = m.n_app, K0 = 3 * Ca;
+  const uint32_t n_ent = *P.ws.n_entries;
+  const uint32_t n_tiles = (n_ent + kAppTile - 1) / kAppTile;
+  const float4* gray = reinterpret_cast<const float4*>(P.ws.bwd_scratch);
+
+  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const uint32_t tile_base = tile * kAppTile;
+    const uint32_t e = tile_base + row;
+    // ---- forward recompute ---------------------------------------------------------------------
+    app_gather_tile(P, tile_base, n_ent, H, X, st);
+    __syncthreads();
+    app_basis_pe(P, H, X, st);
+    __syncthreads();
+    app_dense<true>(m.w1_t, m.b1, X, P.in_mlp_c, Y1, st);
+    __syncthreads();
+    app_dense<true>(m.w2_t, m.b2, Y1, kFeatureC, Y2, st);
+    __syncthreads();
+    if (part < 3) {
+      float dz = 0.0f;
+      if (e < n_ent) {
+        const float s = 1.0f / (1.0f + expf(-app_out_logit(m, Y2, st, row, part)));
+        const float4 g = gray[P.ws.ent[e].x];
+        const float gc = part == 0 ? g.x : (part == 1 ? g.y : g.z);
+        dz = P.ws.ent_w[e] * gc * s * (1.0f - s);     // d/d logit of w * rgb . g
+      }
+      D3[row * 4 + part] = dz;
+    }
+    __syncthreads();
+    // ---- layer 3: dW3, db3, dY2 -> dz2 (in place of Y2) ----------------------------------------------
+    {
+      const int j = tid & (kFeatureC - 1);
+      const int o_lo = (tid >> 7) ? 2 : 0, o_hi = (tid >> 7) ? 3 : 2;
+      float a0 = 0.0f, a1 = 0.0f;
+      for (int r = 0; r < kAppTile; ++r) {
+        const float y = Y2[r * st + j];
+        a0 = fmaf(D3[r * 4 + o_lo], y, a0);
+        if (o_hi - o_lo == 2) a1 = fmaf(D3[r * 4 + o_lo + 1], y, a1);
+      }
+      atomicAdd(B.g.w3 + o_lo * kFeatureC + j, a0);
+      if (o_hi - o_lo == 2) atomicAdd(B.g.w3 + (o_lo + 1) * kFeatureC + j, a1);
+      if (tid < 3) {
+        float a = 0.0f;
+        for (int r = 0; r < kAppTile; ++r) a += D3[r * 4 + tid];
+        atomicAdd(B.g.b3 + tid, a);
+      }
+    }
+    __syncthreads();
+    {
+      const float d0 = D3[row * 4 + 0], d1 = D3[row * 4 + 1], d2 = D3[row * 4 + 2];
+      float* y = Y2 + row * st + part * 32;
+      const float* w = m.w3 + part * 32;
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        const float4 yv = lds4(y + i);
+        const float4 w0 = ldg4(w + i), w1 = ldg4(w + kFeatureC + i), w2 = ldg4(w + 2 * kFeatureC + i);
+        float4 o;
+        o.x = yv.x > 0.0f ? fmaf(d0, w0.x, fmaf(d1, w1.x, d2 * w2.x)) : 0.0f;
+        o.y = yv.y > 0.0f ? fmaf(d0, w0.y, fmaf(d1, w1.y, d2 * w2.y)) : 0.0f;
+        o.z = yv.z > 0.0f ? fmaf(d0, w0.z, fmaf(d1, w1.z, d2 * w2.z)) : 0.0f;
+        o.w = yv.w > 0.0f ? fmaf(d0, w0.w, fmaf(d1, w1.w, d2 * w2.w)) : 0.0f;
+        *reinterpret_cast<float4*>(y + i) = o;
+      }
+    }
+    __syncthreads();
+    // ---- layer 2: dW2, db2, dY1 -> dz1 (in place of Y1) ----------------------------------------------
+    wgrad_tile_128(Y1, Y2, st, kFeatureC, B.g.w2_t, kFeatureC);
+    bgrad_tile(Y2, st, B.g.b2);
+    __syncthreads();
+    app_dense_bwd<true>(m.w2_t, Y2, kFeatureC, Y1, Y1, st);
+    __syncthreads();
+    // ---- layer 1: dW1, db1, d x (into Y2) ----------------------------------------------------------
+    wgrad_tile_128(X, Y1, st, P.in_mlp_c, B.g.w1_t, kFeatureC);
+    bgrad_tile(Y1, st, B.g.b1);
+    app_dense_bwd<false>(m.w1_t, Y1, P.in_mlp_c, Y2, nullptr, st);
+    __syncthreads();
+    // ---- positional encoding: d feat (into Y1[.., 0..32)) ---------------------------------------------
+    {
+      const float* x = X + row * st;
+      const float* dx = Y2 + row * st;
+      const int pe_f = m.app_dim + 3;
+      const int n_f = m.fea_pe * m.app_dim;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int o = part * 8 + i;
+        float df = 0.0f;
+        if (o < m.app_dim) {
+          df = dx[o];
+          float fr = 1.0f;
+          for (int q = 0; q < m.fea_pe; ++q, fr *= 2.0f) {
+            const int si = pe_f + o * m.fea_pe + q, ci = si + n_f;
+            df += fr * (dx[si] * x[ci] - dx[ci] * x[si]);     // d sin = cos, d cos = -sin
+          }
+        }
+        Y1[row * st + o] = df;
+      }
+    }
+    __syncthreads();
+    // ---- basis_mat: d basis, d h (into X) -------------------------------------------------------------
+    wgrad_tile_32(H, Y1, st, K0, B.g.basis_t);
+    {
+      float df[32];
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        const float4 v = lds4(Y1 + row * st + i);
+        df[i] = v.x; df[i + 1] = v.y; df[i + 2] = v.z; df[i + 3] = v.w;
+      }
+      const int JP = (K0 / 4 + 3) & ~3;
+      const int jbeg = part * JP, jend = min(K0, jbeg + JP);
+      for (int j = jbeg; j < jend; ++j) {
+        const float* bt = m.basis_t + j * kMaxAppDim;
+        float a = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const float4 w = ldg4(bt + i);
+          a = fmaf(df[i], w.x, fmaf(df[i + 1], w.y, fmaf(df[i + 2], w.z, fmaf(df[i + 3], w.w, a))));
+        }
+        X[row * st + j] = a;
+      }
+    }
+    __syncthreads();
+    // ---- scatter d h into the appearance planes / lines (4 lanes per entry, as in the gather) ----------
+    {
+      const int warp = tid >> 5, lane = tid & 31;
+      const int grow = warp * 8 + (lane >> 2), q = lane & 3;
+      const uint32_t ge = tile_base + grow;
+      if (ge < n_ent) {
+        const uint2 en = P.ws.ent[ge];
+        float u[3], dir[3];
+        entry_coords(m, P.rays, P.jitter, en.x, en.y, u, dir);
+        Axis ax[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) ax[i] = axis_taps(u[i], m.grid[i]);
+        const float* dh = X + grow * st;
+#pragma unroll
+        for (int kk = 0; kk < 3; ++kk) {
+          const VmTaps t = vm_taps(m, ax, kk);
+          float* gp = B.g.app_plane[kk];
+          float* gl = B.g.app_line[kk];
+          for (int c = q * 4; c < Ca; c += 16) {
+            float4 pv, lv;
+            vm_sample4(m.app_plane[kk], m.app_line[kk], t, Ca, c, pv, lv);
+            const float4 d = lds4(dh + kk * Ca + c);
+            const float px = d.x * lv.x, py = d.y * lv.y, pz = d.z * lv.z, pw = d.w * lv.w;   // d plane value
+            const float lx = d.x * pv.x, ly = d.y * pv.y, lz = d.z * pv.z, lw = d.w * pv.w;   // d line value
+            red_add_v4(gp + (size_t)t.o00 * Ca + c, px * t.nw, py * t.nw, pz * t.nw, pw * t.nw);
+            red_add_v4(gp + (size_t)t.o01 * Ca + c, px * t.ne, py * t.ne, pz * t.ne, pw * t.ne);
+            red_add_v4(gp + (size_t)t.o10 * Ca + c, px * t.sw, py * t.sw, pz * t.sw, pw * t.sw);
+            red_add_v4(gp + (size_t)t.o11 * Ca + c, px * t.se, py * t.se, pz * t.se, pw * t.se);
+            red_add_v4(gl + (size_t)t.l0 * Ca + c, lx * t.lw0, ly * t.lw0, lz * t.lw0, lw * t.lw0);
+            red_add_v4(gl + (size_t)t.l1 * Ca + c, lx * t.lw1, ly * t.lw1, lz * t.lw1, lw * t.lw1);
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_march_bwd: same march / control flow as k_march (tvm_forward.cu), one warp per ray
+// ------------------------------------------------------------------------------------------------
+constexpr int kMarchWarps = 8;
+
+__global__ void __launch_bounds__(kMarchWarps * 32) k_march_bwd(const BwdParams B) {
+  __shared__ float s_u[kMarchWarps][32][3];
+  __shared__ float s_f[kMarchWarps][32];
+  const FwdParams& P = B.f;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ray = blockIdx.x * kMarchWarps + warp;
+  if (ray >= P.n) return;
+  const TvmModel& m = P.m;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+
+  RayMarch r;
+  ray_setup(m, P.rays + 6 * (size_t)ray, P.jitter ? P.jitter[ray] : 0.0f, r);
+  const float4 g = reinterpret_cast<const float4*>(P.ws.bwd_scratch)[ray];
+  const float gs = (P.flags & TVM_WHITE_BG) ? g.x + g.y + g.z : 0.0f;
+  const float total = g.w;
+  if (g.x == 0.0f && g.y == 0.0f && g.z == 0.0f) return;   // nothing flows into this ray
+
+  const int C = m.n_density, S = P.S;
+  const bool ert = !(P.flags & TVM_NO_ERT);
+  const int q = lane & 3;
+  float T = 1.0f, carry = 0.0f;
+  bool seen = false;
+
+  for (int b = 0; b < P.NB; ++b) {
+    const int k = b * 32 + lane;
+    const float z = sample_z(m, r, k);
+    float p[3];
+    bool inside = sample_point(m, r, z, p) && (k < S);
+    const uint32_t in_bits = __ballot_sync(0xffffffffu, inside);
+    if (in_bits == 0) {
+      if (seen) break;
+      continue;
+    }
+    seen = true;
+    bool valid = inside;
+    if (m.alpha_bits != nullptr && inside) valid = alpha_mask_test(m, m.alpha_bits, p);
+    const uint32_t v_bits = __ballot_sync(0xffffffffu, valid);
+    const int nv = __popc(v_bits);
+    const int rank = __popc(v_bits & lt_mask);
+
+    float f = 0.0f, sigma = 0.0f;
+    if (v_bits != 0) {
+      if (valid) {
+        float u[3];
+        grid_coords(m, p, u);
+        s_u[warp][rank][0] = u[0];
+        s_u[warp][rank][1] = u[1];
+        s_u[warp][rank][2] = u[2];
+      }
+      __syncwarp();
+      for (int gi = 0; gi < nv; gi += 8) {
+        const int j = gi + (lane >> 2);
+        float part = 0.0f;
+        if (j < nv) {
+          Axis ax[3];
+#pragma unroll
+          for (int i = 0; i < 3; ++i) ax[i] = axis_taps(s_u[warp][j][i], m.grid[i]);
+#pragma unroll
+          for (int kk = 0; kk < 3; ++kk) {
+            const VmTaps t = vm_taps(m, ax, kk);
+            for (int c = q * 4; c < C; c += 16) {
+              float4 pv, lv;
+              vm_sample4(m.density_plane[kk], m.density_line[kk], t, C, c, pv, lv);
+              part += pv.x * lv.x + pv.y * lv.y + pv.z * lv.z + pv.w * lv.w;
+            }
+          }
+        }
+        part += __shfl_xor_sync(0xffffffffu, part, 1);
+        part += __shfl_xor_sync(0xffffffffu, part, 2);
+        if (j < nv && q == 0) s_f[warp][j] = part;
+      }
+      __syncwarp();
+      if (valid) {
+        f = s_f[warp][rank];
+        sigma = feature2density(m, f);
+      }
+      __syncwarp();
+    }
+
+    const float z1 = sample_z(m, r, k + 1);
+    const float dist = (k < S - 1) ? TVM_MUL(TVM_SUB(z1, z), m.distance_scale) : 0.0f;
+    const float alpha = TVM_SUB(1.0f, expf(TVM_MUL(-sigma, dist)));
+    const float v = TVM_ADD(TVM_SUB(1.0f, alpha), 1e-10f);
+    float pref = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      float t = __shfl_up_sync(0xffffffffu, pref, o);
+      if (lane >= o) pref *= t;
+    }
+    float excl = __shfl_up_sync(0xffffffffu, pref, 1);
+    if (lane == 0) excl = 1.0f;
+    const float Tk = T * excl;
+    const float w = alpha * Tk;
+    T = T * __shfl_sync(0xffffffffu, pref, 31);
+
+    // dL/dw_k = g . rgb_k (weighted samples only) - gs
+    const uint32_t a_bits = P.ws.blk_mask[(size_t)ray * P.NB + b];
+    float dw = -gs;
+    if ((a_bits >> lane) & 1u) {
+      const uint32_t e = P.ws.blk_base[(size_t)ray * P.NB + b] + __popc(a_bits & lt_mask);
+      const float* c3 = P.ws.ent_rgb + (size_t)e * 3;
+      dw += g.x * c3[0] + g.y * c3[1] + g.z * c3[2];
+    }
+    // inclusive prefix of dw*w; the suffix sum_{j>k} dw_j w_j is total - prefix
+    float ps = dw * w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      float t = __shfl_up_sync(0xffffffffu, ps, o);
+      if (lane >= o) ps += t;
+    }
+    const float suffix = total - (carry + ps);
+    carry += __shfl_sync(0xffffffffu, ps, 31);
+    const float dalpha = dw * Tk - suffix / v;
+    const float dsigma = dalpha * dist * (1.0f - alpha);
+    const float dfeat = valid ? dsigma * feature2density_grad(m, f) : 0.0f;
+
+    if (v_bits != 0) {
+      if (valid) s_f[warp][rank] = dfeat;
+      __syncwarp();
+      for (int gi = 0; gi < nv; gi += 8) {
+        const int j = gi + (lane >> 2);
+        if (j < nv) {
+          const float d = s_f[warp][j];
+          if (d != 0.0f) {
+            Axis ax[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) ax[i] = axis_taps(s_u[warp][j][i], m.grid[i]);
+#pragma unroll
+            for (int kk = 0; kk < 3; ++kk) {
+              const VmTaps t = vm_taps(m, ax, kk);
+              float* gp = B.g.density_plane[kk];
+              float* gl = B.g.density_line[kk];
+              for (int c = q * 4; c < C; c += 16) {
+                float4 pv, lv;
+                vm_sample4(m.density_plane[kk], m.density_line[kk], t, C, c, pv, lv);
+                const float px = d * lv.x, py = d * lv.y, pz = d * lv.z, pw = d * lv.w;
+                const float lx = d * pv.x, ly = d * pv.y, lz = d * pv.z, lw = d * pv.w;
+                red_add_v4(gp + (size_t)t.o00 * C + c, px * t.nw, py * t.nw, pz * t.nw, pw * t.nw);
+                red_add_v4(gp + (size_t)t.o01 * C + c, px * t.ne, py * t.ne, pz * t.ne, pw * t.ne);
+                red_add_v4(gp + (size_t)t.o10 * C + c, px * t.sw, py * t.sw, pz * t.sw, pw * t.sw);
+                red_add_v4(gp + (size_t)t.o11 * C + c, px * t.se, py * t.se, pz * t.se, pw * t.se);
+                red_add_v4(gl + (size_t)t.l0 * C + c, lx * t.lw0, ly * t.lw0, lz * t.lw0, lw * t.lw0);
+                red_add_v4(gl + (size_t)t.l1 * C + c, lx * t.lw1, ly * t.lw1, lz * t.lw1, lw * t.lw1);
+              }
+            }
+          }
+        }
+      }
+      __syncwarp();
+    }
+    if (ert && T < kErtEps) break;
+    if (!(in_bits >> 31)) break;
+  }
+}
+
+int fill_fwd_params(FwdParams& P, const TvmModel* m, const float* rays, int n, int S, const float* jitter,
+                    uint32_t flags, void* ws, size_t ws_bytes);   // tvm_forward.cu
+
+}  // namespace tvm
+
+using namespace tvm;
+
 extern "C" int tvm_backward(const TvmModel* m_host, const float* rays, int n_rays, int n_samples,
-                 const float* jitter, uint32_t flags, const float* rgb_map, const float* d_rgb_map,
-                 const TvmGrads* grads_host, void* ws, size_t ws_bytes, void* stream) {
-  tvm::set_error("backward not built in this library");
-  return -3;
+                            const float* jitter, uint32_t flags, const float* rgb_map, const float* d_rgb_map,
+                            const TvmGrads* grads_host, void* ws, size_t ws_bytes, void* stream_) {
+  (void)rgb_map;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  BwdParams B;
+  if (int rc = fill_fwd_params(B.f, m_host, rays, n_rays, n_samples, jitter, flags, ws, ws_bytes)) return rc;
+  TVM_REQUIRE(d_rgb_map && grads_host, "null argument");
+  B.d_rgb_map = d_rgb_map;
+  B.g = *grads_host;
+  for (int k = 0; k < 3; ++k)
+    TVM_REQUIRE(B.g.density_plane[k] && B.g.density_line[k] && B.g.app_plane[k] && B.g.app_line[k], "null gradient pointer");
+  TVM_REQUIRE(B.g.basis_t && B.g.w1_t && B.g.b1 && B.g.w2_t && B.g.b2 && B.g.w3 && B.g.b3, "null gradient pointer");
+
+  k_bwd_prep<<<(n_rays + 255) / 256, 256, 0, stream>>>(B);
+  TVM_CHECK_CUDA(cudaGetLastError());
+  {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const size_t smem = ((size_t)kAppTile * 4 * B.f.st + kAppTile * 4) * sizeof(float);
+    TVM_REQUIRE(smem <= 220 * 1024, "appearance backward tile does not fit shared memory");
+    TVM_CHECK_CUDA(cudaFuncSetAttribute(k_app_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ProfileScope prof(TVM_STAGE_BWD_APP, stream);
+    k_app_bwd<<<sms, kAppThreads, smem, stream>>>(B);
+  }
+  TVM_CHECK_CUDA(cudaGetLastError());
+  {
+    ProfileScope prof(TVM_STAGE_BWD_MARCH, stream);
+    k_march_bwd<<<(n_rays + kMarchWarps - 1) / kMarchWarps, kMarchWarps * 32, 0, stream>>>(B);
+  }
+  TVM_CHECK_CUDA(cudaGetLastError());
+  return 0;
 }

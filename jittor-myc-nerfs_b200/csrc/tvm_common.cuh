@@ -87,7 +87,7 @@ struct FwdParams {
   TvmAux aux;
   unsigned long long* counters;
   int in_mlp_c;   // 2*view_pe*3 + 2*fea_pe*app_dim + 3 + app_dim
-  int hs, xs;     // smem row strides of the appearance tile
+  int st;         // smem row stride (floats) of the fp32 appearance tiles
 };
 
 inline int in_mlp_c(const TvmModel& m) { return 2 * m.view_pe * 3 + 2 * m.fea_pe * m.app_dim + 3 + m.app_dim; }

@@ -11,7 +11,7 @@
 //
 // The tcgen05 tensor-core appearance head lives in tvm_mlp_tc.cu and replaces k_app_simt when
 // TVM_MLP_BF16 / TVM_MLP_BF16X3 is requested.
-#include "tvm_common.cuh"
+#include "tvm_app_simt.cuh"
 
 namespace tvm {
 
@@ -165,149 +165,31 @@ __global__ void __launch_bounds__(kMarchWarps * 32) k_march(const FwdParams P) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_app_simt: appearance head, fp32 FMA path (parity mode)
+// k_app_simt: appearance head, fp32 FMA path (parity mode); building blocks in tvm_app_simt.cuh
 // ------------------------------------------------------------------------------------------------
-constexpr int kAppTile = 64;
-constexpr int kAppThreads = 256;
-
-__device__ __forceinline__ void fma4(float* acc, float x, const float4 w) {
-  acc[0] = fmaf(x, w.x, acc[0]);
-  acc[1] = fmaf(x, w.y, acc[1]);
-  acc[2] = fmaf(x, w.z, acc[2]);
-  acc[3] = fmaf(x, w.w, acc[3]);
-}
-
-// Gathers the 3*Ca appearance product vector of one tile into H (row stride hs) and the view
-// directions into X[.., app_dim .. app_dim+3).  8 warps x 8 entries, 4 lanes per entry.
-__device__ __forceinline__ void app_gather_tile(const FwdParams& P, uint32_t tile_base, uint32_t n_ent,
-                                                float* H, float* X) {
-  const TvmModel& m = P.m;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int Ca = m.n_app;
-  const int row = warp * 8 + (lane >> 2), q = lane & 3;
-  const uint32_t e = tile_base + row;
-  float* h = H + row * P.hs;
-  if (e < n_ent) {
-    const uint2 en = P.ws.ent[e];
-    float u[3], dir[3];
-    entry_coords(m, P.rays, P.jitter, en.x, en.y, u, dir);
-    Axis ax[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) ax[i] = axis_taps(u[i], m.grid[i]);
-#pragma unroll
-    for (int kk = 0; kk < 3; ++kk) {
-      const VmTaps t = vm_taps(m, ax, kk);
-      for (int c = q * 4; c < Ca; c += 16) {
-        float4 pv, lv;
-        vm_sample4(m.app_plane[kk], m.app_line[kk], t, Ca, c, pv, lv);
-        float* o = h + kk * Ca + c;
-        o[0] = pv.x * lv.x;
-        o[1] = pv.y * lv.y;
-        o[2] = pv.z * lv.z;
-        o[3] = pv.w * lv.w;
-      }
-    }
-    if (q < 3) X[row * P.xs + m.app_dim + q] = dir[q];
-  } else {
-    for (int c = q; c < 3 * Ca; c += 4) h[c] = 0.0f;
-    if (q < 3) X[row * P.xs + m.app_dim + q] = 0.0f;
-  }
-}
-
-// basis_mat + positional encoding: thread (row, part) owns basis outputs [part*8, part*8+8)
-__device__ __forceinline__ void app_basis_pe(const FwdParams& P, const float* H, float* X) {
-  const TvmModel& m = P.m;
-  const int row = threadIdx.x & (kAppTile - 1), part = threadIdx.x >> 6;
-  const int K = 3 * m.n_app;
-  float acc[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
-  const float* h = H + row * P.hs;
-  const float* bt = m.basis_t + part * 8;
-  for (int j = 0; j < K; ++j) {
-    const float x = h[j];
-    fma4(acc, x, ldg4(bt + j * kMaxAppDim));
-    fma4(acc + 4, x, ldg4(bt + j * kMaxAppDim + 4));
-  }
-  float* xr = X + row * P.xs;
-  const int pe_f = m.app_dim + 3;                       // start of sin(PE(features))
-  const int pe_v = pe_f + 2 * m.fea_pe * m.app_dim;     // start of sin(PE(viewdirs))
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int o = part * 8 + i;
-    if (o < m.app_dim) {
-      const float f = acc[i];
-      xr[o] = f;
-      float fr = 1.0f;
-      for (int q = 0; q < m.fea_pe; ++q, fr *= 2.0f) {
-        const float s = f * fr;
-        xr[pe_f + o * m.fea_pe + q] = sinf(s);
-        xr[pe_f + m.fea_pe * m.app_dim + o * m.fea_pe + q] = cosf(s);
-      }
-    }
-  }
-  if (part == 3) {
-    for (int c = 0; c < 3; ++c) {
-      const float d = xr[m.app_dim + c];
-      float fr = 1.0f;
-      for (int q = 0; q < m.view_pe; ++q, fr *= 2.0f) {
-        const float s = d * fr;
-        xr[pe_v + c * m.view_pe + q] = sinf(s);
-        xr[pe_v + 3 * m.view_pe + c * m.view_pe + q] = cosf(s);
-      }
-    }
-  }
-}
-
-// y[row][part*32 .. +32) = relu(x[row][0..K) @ Wt[K][128] + b): thread (row, part)
-__device__ __forceinline__ void app_dense_relu(const float* __restrict__ Wt, const float* __restrict__ bias,
-                                               const float* xin, int xstride, int K, float* yout, int ystride) {
-  const int row = threadIdx.x & (kAppTile - 1), part = threadIdx.x >> 6;
-  float acc[32];
-#pragma unroll
-  for (int i = 0; i < 32; i += 4) {
-    const float4 b = ldg4(bias + part * 32 + i);
-    acc[i] = b.x; acc[i + 1] = b.y; acc[i + 2] = b.z; acc[i + 3] = b.w;
-  }
-  const float* x = xin + row * xstride;
-  const float* w = Wt + part * 32;
-  for (int j = 0; j < K; ++j) {
-    const float xv = x[j];
-#pragma unroll
-    for (int i = 0; i < 32; i += 4) fma4(acc + i, xv, ldg4(w + (size_t)j * kFeatureC + i));
-  }
-  float* y = yout + row * ystride + part * 32;
-#pragma unroll
-  for (int i = 0; i < 32; ++i) y[i] = fmaxf(acc[i], 0.0f);
-}
-
 __global__ void __launch_bounds__(kAppThreads) k_app_simt(const FwdParams P) {
-  extern __shared__ float smem[];
-  float* H = smem;                       // [64][hs]: appearance vector, then layer-1 output
-  float* X = smem + kAppTile * P.hs;     // [64][xs]: MLP input, then layer-2 output
+  extern __shared__ __align__(16) float smem[];
+  const int st = P.st;
+  float* H = smem;                    // [64][st]: appearance vector, then layer-1 output
+  float* X = smem + kAppTile * st;    // [64][st]: MLP input, then layer-2 output
   const TvmModel& m = P.m;
   const uint32_t n_ent = *P.ws.n_entries;
   const uint32_t n_tiles = (n_ent + kAppTile - 1) / kAppTile;
   for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const uint32_t tile_base = tile * kAppTile;
-    app_gather_tile(P, tile_base, n_ent, H, X);
+    app_gather_tile(P, tile_base, n_ent, H, X, st);
     __syncthreads();
-    app_basis_pe(P, H, X);
+    app_basis_pe(P, H, X, st);
     __syncthreads();
-    app_dense_relu(m.w1_t, m.b1, X, P.xs, P.in_mlp_c, H, P.hs);
+    app_dense<true>(m.w1_t, m.b1, X, P.in_mlp_c, H, st);
     __syncthreads();
-    app_dense_relu(m.w2_t, m.b2, H, P.hs, kFeatureC, X, P.xs);
+    app_dense<true>(m.w2_t, m.b2, H, kFeatureC, X, st);
     __syncthreads();
     {
       const int row = threadIdx.x & (kAppTile - 1), part = threadIdx.x >> 6;
       const uint32_t e = tile_base + row;
-      if (part < 3 && e < n_ent) {
-        float a = m.b3[part];
-        const float* x = X + row * P.xs;
-        const float* w = m.w3 + part * kFeatureC;
-        for (int j = 0; j < kFeatureC; ++j) a = fmaf(x[j], __ldg(w + j), a);
-        P.ws.ent_rgb[(size_t)e * 3 + part] = 1.0f / (1.0f + expf(-a));
-      }
+      if (part < 3 && e < n_ent)
+        P.ws.ent_rgb[(size_t)e * 3 + part] = 1.0f / (1.0f + expf(-app_out_logit(m, X, st, row, part)));
     }
     __syncthreads();
   }
@@ -378,10 +260,7 @@ int fill_fwd_params(FwdParams& P, const TvmModel* m, const float* rays, int n, i
   TVM_REQUIRE(((uintptr_t)ws & 255) == 0, "workspace must be 256-byte aligned");
   P.NB = P.ws.NB;
   P.in_mlp_c = in_mlp_c(*m);
-  int hs = max(3 * m->n_app, kFeatureC) + 1;
-  int xs = max(P.in_mlp_c, kFeatureC) + 1;
-  P.hs = hs | 1;
-  P.xs = xs | 1;
+  P.st = app_tile_stride(m->n_app, P.in_mlp_c);
   P.counters = nullptr;
   P.aux = TvmAux{};
   return 0;
@@ -445,7 +324,7 @@ extern "C" int tvm_forward(const TvmModel* m_host, const float* rays, int n_rays
 
   const uint32_t mlp = flags & TVM_MLP_MASK;
   if (mlp == TVM_MLP_FP32) {
-    const size_t smem = (size_t)kAppTile * (P.hs + P.xs) * sizeof(float);
+    const size_t smem = (size_t)kAppTile * 2 * P.st * sizeof(float);
     TVM_CHECK_CUDA(cudaFuncSetAttribute(k_app_simt, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     TVM_REQUIRE(smem <= 200 * 1024, "appearance tile does not fit shared memory");
     {
