@@ -41,7 +41,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--regime", default="R1", choices=["R0", "R1", "R2"])
-    ap.add_argument("--mlp", default=os.environ.get("TVM_MLP_MODE", "fp32"), choices=["fp32", "bf16", "bf16x3"])
+    ap.add_argument("--mlp", default=os.environ.get("TVM_MLP_MODE", "bf16"), choices=["fp32", "bf16", "bf16x3"],
+                    help="appearance head: bf16 tcgen05 (rgb tolerance 1e-2, default) or fp32 FMA (1e-4)")
     ap.add_argument("--grid", type=int, default=GRID)
     ap.add_argument("--rays", type=int, default=FRAME * FRAME, help="rays per step (default: the full frame)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -304,7 +305,10 @@ def main():
                     "d2h_bytes_per_step": int(rgb_host.numel() * 4 + depth_host.numel() * 4),
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(sum(stage_cnt.values())),
-            "clocks": clocks, "roofline": roof, "max_abs_err_vs_oracle_512rays": check}
+            "clocks": clocks, "roofline": roof, "max_abs_err_vs_oracle_512rays": check,
+            "rgb_tolerance": 1e-4 if args.mlp != "bf16" else 1e-2}
+    if rank == 0 and check is not None and check > line["rgb_tolerance"]:
+        raise SystemExit(f"bench: rendered colours differ from the oracle by {check} > {line['rgb_tolerance']}")
 
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:

@@ -4,6 +4,7 @@ from . import _lib
 from ._lib import TvmError, LIB_PATH
 from .tensorf import TensorVMSplit, AlphaGridMask, MLPRender_Fea, derive_march_scalars, unpack_bits, model_from_params
 from .renderer import OctreeRender_trilinear_fast
+from . import dist
 
 __all__ = ["TensorVMSplit", "AlphaGridMask", "MLPRender_Fea", "OctreeRender_trilinear_fast",
            "derive_march_scalars", "unpack_bits", "model_from_params", "TvmError", "LIB_PATH"]

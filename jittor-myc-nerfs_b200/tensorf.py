@@ -153,6 +153,8 @@ class TensorVMSplit(torch.nn.Module):
         self.collect_counters = False
         self.counters = torch.zeros(L.CNT_WORDS, dtype=torch.int64, device=device)
         self.ws_budget_bytes = int(float(os.environ.get("TVM_WS_GIB", "6")) * (1 << 30))
+        self.grad_sync = False          # set True (after dist.init_from_env) for data-parallel training
+        self.grad_sync_group = None
         self._ws = None
         self._packed = None
         self._packed_versions = None
@@ -406,6 +408,10 @@ class TensorVMSplit(torch.nn.Module):
         ws = self._workspace(n, S)
         L.check(lib.tvm_backward(C.byref(model), _ptr(rays), n, int(S), _ptr(jitter), flags, _ptr(rgb), _ptr(d_rgb),
                                  C.byref(gs), _ptr(ws), ws.numel(), _stream_ptr()), "tvm_backward")
+        if self.grad_sync:
+            # data-parallel training: ONE all-reduce over the flat packed gradient buffer
+            from .dist import allreduce_flat_
+            allreduce_flat_(gp, group=self.grad_sync_group, average=True)
         return self._unpack_grads(gp, items)
 
     def _unpack_grads(self, gp, items):
