@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define TVM_ABI_VERSION 3
+#define TVM_ABI_VERSION 4
 
 /* flags for tvm_forward / tvm_backward */
 #define TVM_WHITE_BG      0x1u  /* rgb_map += 1 - acc_map          (tensorBase.py:523-524) */
@@ -85,6 +85,9 @@ typedef struct TvmModel {
   int32_t alpha_grid[3];    /* W(x) H(y) D(z)                                             */
   float alpha_aabb_min[3];  /* AlphaGridMask.aabb[0]          (tensorBase.py:44)          */
   float alpha_inv_size[3];  /* 1.0 / aabbSize * 2             (tensorBase.py:46)          */
+  /* optional empty-space index from tvm_pack_alpha_bricks (NULL = none): one bit per 8x8x8-voxel
+   * brick, bit (bz*BH + by)*BW + bx with B* = ceil(dim/8); set iff any voxel of the brick is set  */
+  const uint32_t* alpha_bricks;
   /* optional tensor-core operand images written by tvm_pack_mlp_tc (NULL = not packed)   */
   const void* tc_weights;
 } TvmModel;
@@ -139,6 +142,8 @@ int tvm_pack_linear(const float* w_out_in, int out_c, int in_c, int out_pad, flo
 int tvm_unpack_linear(const float* w_t, int out_c, int in_c, int out_pad, float* out_w, void* stream);
 /* {0,1} fp32 volume [D][H][W] -> bit stream (bit set iff value > 0); n_words = ceil(D*H*W/32)  */
 int tvm_pack_alpha(const float* volume, int D, int H, int W, uint32_t* bits, void* stream);
+/* brick index of a packed alpha volume; n_words = ceil(ceil(D/8)*ceil(H/8)*ceil(W/8) / 32)        */
+int tvm_pack_alpha_bricks(const uint32_t* bits, int D, int H, int W, uint32_t* bricks, void* stream);
 /* bytes of the tensor-core operand image for (in_mlp_c, feature_c, app_dim, n_app)            */
 size_t tvm_tc_weights_bytes(const TvmModel* m_host);
 /* builds the bf16 (hi, mid) K-major UMMA operand images of basis/W1/W2 from the packed fp32 weights */

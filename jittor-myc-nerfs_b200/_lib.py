@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libtvmrender.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # flags (tvmrender.h)
 WHITE_BG = 0x1
@@ -40,7 +40,7 @@ class TvmModel(C.Structure):
         ("basis_t", C.c_void_p), ("w1_t", C.c_void_p), ("b1", C.c_void_p), ("w2_t", C.c_void_p),
         ("b2", C.c_void_p), ("w3", C.c_void_p), ("b3", C.c_void_p),
         ("alpha_bits", C.c_void_p), ("alpha_grid", _i3), ("alpha_aabb_min", _f3), ("alpha_inv_size", _f3),
-        ("tc_weights", C.c_void_p),
+        ("alpha_bricks", C.c_void_p), ("tc_weights", C.c_void_p),
     ]
 
 
@@ -57,7 +57,7 @@ class TvmGrads(C.Structure):
 
 EXPORTS = [
     "tvm_last_error", "tvm_abi_version", "tvm_device_count", "tvm_pack_grid", "tvm_unpack_grid",
-    "tvm_pack_linear", "tvm_unpack_linear", "tvm_pack_alpha", "tvm_tc_weights_bytes", "tvm_pack_mlp_tc",
+    "tvm_pack_linear", "tvm_unpack_linear", "tvm_pack_alpha", "tvm_pack_alpha_bricks", "tvm_tc_weights_bytes", "tvm_pack_mlp_tc",
     "tvm_workspace_bytes", "tvm_forward", "tvm_backward", "tvm_density_alpha", "tvm_mse_loss",
     "tvm_profile_enable", "tvm_profile_collect",
 ]
@@ -92,6 +92,7 @@ def load() -> C.CDLL:
     lib.tvm_pack_linear.argtypes = [vp, i32, i32, i32, vp, vp]
     lib.tvm_unpack_linear.argtypes = [vp, i32, i32, i32, vp, vp]
     lib.tvm_pack_alpha.argtypes = [vp, i32, i32, i32, vp, vp]
+    lib.tvm_pack_alpha_bricks.argtypes = [vp, i32, i32, i32, vp, vp]
     lib.tvm_tc_weights_bytes.restype = C.c_size_t
     lib.tvm_tc_weights_bytes.argtypes = [C.POINTER(TvmModel)]
     lib.tvm_pack_mlp_tc.argtypes = [C.POINTER(TvmModel), vp, vp]

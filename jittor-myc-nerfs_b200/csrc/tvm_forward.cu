@@ -21,7 +21,7 @@ constexpr int kMarchWarps = 8;
 // k_march
 // ------------------------------------------------------------------------------------------------
 template <bool AUX>
-__global__ void __launch_bounds__(kMarchWarps * 32) k_march(const FwdParams P) {
+__global__ void __launch_bounds__(kMarchWarps * 32, 3) k_march(const FwdParams P) {
   __shared__ float s_u[kMarchWarps][32][3];
   __shared__ float s_f[kMarchWarps][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -40,7 +40,25 @@ __global__ void __launch_bounds__(kMarchWarps * 32) k_march(const FwdParams P) {
   bool seen = false;
   uint32_t c_in = 0, c_v = 0, c_a = 0;
 
-  for (int b = 0; b < P.NB; ++b) {
+  // coarse pass (one lane per 32-sample block): blocks that cannot hold a valid sample are never visited
+  const bool use_visit = !AUX && P.NB <= 64;
+  unsigned long long visit = 0ull;
+  if (use_visit) {
+    for (int b0 = 0; b0 < P.NB; b0 += 32) {
+      const int bb = b0 + lane;
+      const bool maybe = bb < P.NB && block_maybe(m, r, bb, S);
+      visit |= (unsigned long long)__ballot_sync(0xffffffffu, maybe) << b0;
+    }
+  }
+  int b = -1;
+  while (true) {
+    if (use_visit) {
+      if (!visit) break;
+      b = __ffsll((long long)visit) - 1;
+      visit &= visit - 1;
+    } else if (++b >= P.NB) {
+      break;
+    }
     const int k = b * 32 + lane;
     const float z = sample_z(m, r, k);
     float p[3];

@@ -136,6 +136,50 @@ TVM_HD bool alpha_mask_test(const TvmModel& m, const uint32_t* __restrict__ bits
   return hit;
 }
 
+// Conservative empty-space test for a run of consecutive samples whose end points are p0 and p1:
+// the mask-space coordinate of every sample in between lies between the end points' (each step of the
+// coordinate arithmetic is monotone in k), so the voxels any of them can touch are [min floor, max floor + 1]
+// per axis.  Returns false only if every 8^3 brick overlapping that box is empty => no sample of the
+// run can pass alpha_mask_test.  Used to skip whole 32-sample blocks; never changes a mask decision.
+TVM_HD bool bricks_maybe(const TvmModel& m, const uint32_t* __restrict__ bricks, const float p0[3], const float p1[3]) {
+  int lo[3], hi[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const float c0 = TVM_SUB(TVM_MUL(TVM_SUB(p0[i], m.alpha_aabb_min[i]), m.alpha_inv_size[i]), 1.0f);
+    const float c1 = TVM_SUB(TVM_MUL(TVM_SUB(p1[i], m.alpha_aabb_min[i]), m.alpha_inv_size[i]), 1.0f);
+    const float f0 = floorf(unnormalize(c0, m.alpha_grid[i])), f1 = floorf(unnormalize(c1, m.alpha_grid[i]));
+    const float a = fminf(f0, f1), b = fmaxf(f0, f1) + 1.0f;
+    const float va = fmaxf(a, 0.0f), vb = fminf(b, (float)(m.alpha_grid[i] - 1));
+    if (!(va <= vb)) return false;      // the run touches no voxel on this axis (also catches NaN)
+    lo[i] = (int)va >> 3;
+    hi[i] = (int)vb >> 3;
+  }
+  const int BW = (m.alpha_grid[0] + 7) >> 3, BH = (m.alpha_grid[1] + 7) >> 3;
+  for (int z = lo[2]; z <= hi[2]; ++z)
+    for (int y = lo[1]; y <= hi[1]; ++y)
+      for (int x = lo[0]; x <= hi[0]; ++x) {
+        const uint32_t idx = ((uint32_t)z * BH + y) * BW + x;
+        if ((bricks[idx >> 5] >> (idx & 31u)) & 1u) return true;
+      }
+  return false;
+}
+
+// Which 32-sample blocks of a ray can contain a sample that passes the bbox test and the alpha mask?
+// Block b is dropped when both of its end samples lie beyond the same bbox face (monotonicity => so do
+// all samples in between) or when bricks_maybe() is false.  Lane l decides block b0 + l.
+TVM_HD bool block_maybe(const TvmModel& m, const RayMarch& r, int b, int S) {
+  const int k0 = b * 32, k1 = min(b * 32 + 31, S - 1);
+  float p0[3], p1[3];
+  sample_point(m, r, sample_z(m, r, k0), p0);
+  sample_point(m, r, sample_z(m, r, k1), p1);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    if ((p0[i] < m.aabb[i] && p1[i] < m.aabb[i]) || (p0[i] > m.aabb[3 + i] && p1[i] > m.aabb[3 + i])) return false;
+  }
+  if (m.alpha_bits != nullptr && m.alpha_bricks != nullptr) return bricks_maybe(m, m.alpha_bricks, p0, p1);
+  return true;
+}
+
 // normalize_coord + unnormalize for the model grids             (tensorBase.py:223-224)
 TVM_HD void grid_coords(const TvmModel& m, const float p[3], float u[3]) {
 #pragma unroll

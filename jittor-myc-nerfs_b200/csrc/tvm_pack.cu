@@ -101,6 +101,25 @@ __global__ void k_pack_alpha(const float* __restrict__ vol, size_t n_vox, uint32
   if ((threadIdx.x & 31) == 0 && (i >> 5) < (n_vox + 31) / 32) bits[i >> 5] = word;
 }
 
+// one thread per 8x8x8 brick: OR of its voxels' bits; one warp writes one output word
+__global__ void k_pack_bricks(const uint32_t* __restrict__ bits, int D, int H, int W, int n_bricks,
+                              uint32_t* __restrict__ bricks) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int BW = (W + 7) >> 3, BH = (H + 7) >> 3;
+  bool on = false;
+  if (i < n_bricks) {
+    const int bx = i % BW, by = (i / BW) % BH, bz = i / (BW * BH);
+    for (int z = bz * 8; z < min(D, bz * 8 + 8) && !on; ++z)
+      for (int y = by * 8; y < min(H, by * 8 + 8) && !on; ++y)
+        for (int x = bx * 8; x < min(W, bx * 8 + 8); ++x) {
+          const uint32_t idx = ((uint32_t)z * H + y) * W + x;
+          if ((bits[idx >> 5] >> (idx & 31u)) & 1u) { on = true; break; }
+        }
+  }
+  const uint32_t word = __ballot_sync(0xffffffffu, on);
+  if ((threadIdx.x & 31) == 0 && (i >> 5) < (n_bricks + 31) / 32) bricks[i >> 5] = word;
+}
+
 // TensorBase.compute_alpha on arbitrary points (tensorBase.py:451-473): one thread per point.
 __global__ void k_density_alpha(const TvmModel m, const float* __restrict__ xyz, int n, float length,
                                 float* __restrict__ alpha) {
@@ -214,6 +233,15 @@ extern "C" int tvm_pack_alpha(const float* volume, int D, int H, int W, uint32_t
   const size_t n = (size_t)D * H * W;
   const size_t n_pad = (n + 31) / 32 * 32;
   k_pack_alpha<<<(unsigned)((n_pad + 255) / 256), 256, 0, (cudaStream_t)stream>>>(volume, n, bits);
+  TVM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tvm_pack_alpha_bricks(const uint32_t* bits, int D, int H, int W, uint32_t* bricks, void* stream) {
+  TVM_REQUIRE(bits && bricks && D > 0 && H > 0 && W > 0, "bad arguments");
+  const int n = ((D + 7) / 8) * ((H + 7) / 8) * ((W + 7) / 8);
+  const int n_pad = (n + 31) / 32 * 32;
+  k_pack_bricks<<<(n_pad + 127) / 128, 128, 0, (cudaStream_t)stream>>>(bits, D, H, W, n, bricks);
   TVM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

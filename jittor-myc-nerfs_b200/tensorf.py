@@ -65,6 +65,10 @@ class AlphaGridMask:
         lib = L.load()
         L.check(lib.tvm_pack_alpha(_ptr(self.alpha_volume), D, H, W, _ptr(self.bits), _stream_ptr()),
                 "tvm_pack_alpha")
+        n_bricks = ((D + 7) // 8) * ((H + 7) // 8) * ((W + 7) // 8)
+        self.bricks = torch.empty((n_bricks + 31) // 32 + 8, dtype=torch.int32, device=device)
+        L.check(lib.tvm_pack_alpha_bricks(_ptr(self.bits), D, H, W, _ptr(self.bricks), _stream_ptr()),
+                "tvm_pack_alpha_bricks")
 
 
 class _Linear(torch.nn.Module):
@@ -150,6 +154,7 @@ class TensorVMSplit(torch.nn.Module):
         # --- engine state -------------------------------------------------------------------
         self.mlp_mode = os.environ.get("TVM_MLP_MODE", "fp32")
         self.early_termination = True
+        self.empty_space_skipping = True
         self.collect_counters = False
         self.counters = torch.zeros(L.CNT_WORDS, dtype=torch.int64, device=device)
         self.ws_budget_bytes = int(float(os.environ.get("TVM_WS_GIB", "6")) * (1 << 30))
@@ -309,7 +314,7 @@ class TensorVMSplit(torch.nn.Module):
     def _model(self):
         """The TvmModel descriptor (host POD) for the current parameters / mask."""
         self._pack()
-        mask_key = id(self.alphaMask)
+        mask_key = (id(self.alphaMask), self.empty_space_skipping)
         if getattr(self, "_model_struct", None) is not None and self._model_mask_key == mask_key \
                 and not (self._tc_stale and self.mlp_mode != "fp32"):
             return self._model_struct
@@ -331,6 +336,7 @@ class TensorVMSplit(torch.nn.Module):
         if self.alphaMask is not None:
             am = self.alphaMask
             s.alpha_bits = am.bits.data_ptr()
+            s.alpha_bricks = am.bricks.data_ptr() if self.empty_space_skipping else None
             a0 = am.aabb.numpy().astype(np.float32)
             for i in range(3):
                 s.alpha_grid[i] = int(am.gridSize[i])
@@ -338,6 +344,7 @@ class TensorVMSplit(torch.nn.Module):
                 s.alpha_inv_size[i] = float(am.invgridSize[i])
         else:
             s.alpha_bits = None
+            s.alpha_bricks = None
         s.tc_weights = None
         if self.mlp_mode != "fp32":
             lib = L.load()

@@ -101,3 +101,34 @@ def emul_forward(pkg, case, S=-1, white_bg=True):
     assert rc == 0
     out["S"] = S
     return out
+
+
+def pack_bricks(volume):
+    """numpy restatement of tvm_pack_alpha_bricks: one bit per 8x8x8 brick, set iff any voxel is set."""
+    v = np.asarray(volume) > 0
+    D, H, W = v.shape
+    BD, BH, BW = (D + 7) // 8, (H + 7) // 8, (W + 7) // 8
+    pad = np.zeros((BD * 8, BH * 8, BW * 8), bool)
+    pad[:D, :H, :W] = v
+    b = pad.reshape(BD, 8, BH, 8, BW, 8).any(axis=(1, 3, 5)).reshape(-1).astype(np.uint8)
+    b = np.concatenate([b, np.zeros((-b.size) % 32 + 256, np.uint8)])
+    return np.packbits(b, bitorder="little").view(np.uint32).copy()
+
+
+def emul_block_maybe(pkg, case, S=-1):
+    lib = build_emul()
+    m, keep, s = host_model(pkg, case["model"], case["alpha_volume"], case["alpha_aabb"])
+    if case["alpha_volume"] is not None:
+        bricks = pack_bricks(case["alpha_volume"])
+        keep.append(bricks)
+        m.alpha_bricks = bricks.ctypes.data
+    S = s["nSamples"] if S <= 0 else S
+    rays = np.ascontiguousarray(case["rays"], np.float32)
+    n, NB = rays.shape[0], (S + 31) // 32
+    jit = case.get("jitter")
+    visit = np.zeros((n, NB), np.uint8)
+    lib.emul_block_maybe.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    rc = lib.emul_block_maybe(C.byref(m), C.c_void_p(rays.ctypes.data), n, S,
+                              C.c_void_p(jit.ctypes.data) if jit is not None else None, C.c_void_p(visit.ctypes.data))
+    assert rc == 0
+    return visit.astype(bool), S

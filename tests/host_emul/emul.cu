@@ -115,3 +115,15 @@ extern "C" int emul_forward(const TvmModel* mp, const float* rays, int n, int S,
   }
   return 0;
 }
+
+// visit[ray][b] = block_maybe(...) for every 32-sample block (the kernels' coarse empty-space pass)
+extern "C" int emul_block_maybe(const TvmModel* mp, const float* rays, int n, int S, const float* jitter, uint8_t* visit) {
+  const TvmModel& m = *mp;
+  const int NB = (S + 31) / 32;
+  for (int ray = 0; ray < n; ++ray) {
+    RayMarch r;
+    ray_setup(m, rays + 6 * (size_t)ray, jitter ? jitter[ray] : 0.0f, r);
+    for (int b = 0; b < NB; ++b) visit[(size_t)ray * NB + b] = block_maybe(m, r, b, S);
+  }
+  return 0;
+}

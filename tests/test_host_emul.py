@@ -39,3 +39,26 @@ def test_emulated_edge_rays(built_lib):
         assert np.array_equal(e["bbox"].astype(bool), r["bbox_valid"])
         assert np.array_equal(e["valid"].astype(bool), r["ray_valid"])
         assert np.abs(e["rgb_map"] - r["rgb_map"]).max() <= 1e-5
+
+
+@pytest.mark.parametrize("regime,train,G,mres", [("R1", False, 64, 64), ("R2", True, (24, 40, 32), (20, 30, 25)),
+                                                 ("R0", False, 32, None)])
+def test_coarse_block_skip_is_conservative(built_lib, regime, train, G, mres):
+    """The brick / bbox block test may only drop 32-sample blocks that hold no valid sample."""
+    from oracle import fixtures as fx, tensorf_oracle as orc
+    import emul_util as eu
+    case = fx.make_case(G, 400, regime, train=train, mask_res=mres)
+    rays = case["rays"]
+    rays[0] = [0.3, 0.2, 12.0, 0, 0, -1]
+    rays[1] = [5.0, 0.0, 12.0, 0, 0, -1]
+    rays[2] = [0.0, 0.0, 0.0, 0.6, 0.8, 0.0]
+    visit, S = eu.emul_block_maybe(built_lib, case)
+    r = orc.run_case(case)
+    valid = r["ray_valid"]
+    NB = visit.shape[1]
+    pad = np.zeros((valid.shape[0], NB * 32), bool)
+    pad[:, :S] = valid
+    has_valid = pad.reshape(valid.shape[0], NB, 32).any(-1)
+    assert not (has_valid & ~visit).any(), "a block holding a valid sample was skipped"
+    if mres == 64:
+        assert visit.sum() < 0.6 * visit.size       # and the test does skip most empty blocks
