@@ -139,21 +139,38 @@ __global__ void k_pack_tc_f32(const TvmModel m, float* __restrict__ dst) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Warp-specialised persistent kernel: warps 0-3 ("MLP group", thread = tile row) issue the MMAs and run
+// the three epilogues; warps 4.. ("gather group") produce the GEMM0 operand of the NEXT tile into a
+// double-buffered A0 while the MLP group works on the current one.  full[s]/empty[s] mbarriers hand
+// the two A0 stages back and forth; tcgen05.commit arrives on empty[s] when GEMM0 has consumed A0[s].
+constexpr int kMlpWarps = 4;
+constexpr int kGatherWarps = 8;
+constexpr int kThreadsV2 = (kMlpWarps + kGatherWarps) * 32;
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mlp_group_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
 template <int CA, int APP_DIM, int FEA_PE, int VIEW_PE>
-__global__ void __launch_bounds__(kThreads, 1) k_app_tc(const FwdParams P) {
+__global__ void __launch_bounds__(kThreadsV2, 1) k_app_tc(const FwdParams P) {
   constexpr int IN_C = 2 * VIEW_PE * 3 + 2 * FEA_PE * APP_DIM + 3 + APP_DIM;
   constexpr int K0 = 3 * CA;
   constexpr int K1 = (IN_C + 15) / 16 * 16;
-  constexpr int KA = (K0 > K1 ? K0 : K1) > 128 ? (K0 > K1 ? K0 : K1) : 128;
+  constexpr int KA = K1 > 128 ? K1 : 128;
   static_assert(FEA_PE == 2 && VIEW_PE == 2, "the register-resident PE builder is written for 2 frequencies");
   static_assert(K0 % 16 == 0 && APP_DIM <= 32, "unsupported shape");
 
   extern __shared__ __align__(1024) uint8_t smem[];
   const Image img(CA, IN_C);
-  uint8_t* sW = smem;                                   // weight image (bf16 operands + fp32 tail)
-  uint8_t* sA = smem + ((img.bytes + 1023) & ~1023u);   // activation operand [128 x KA] bf16
-  uint64_t* bar = reinterpret_cast<uint64_t*>(sA + kRows * KA * 2);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 2);
+  uint8_t* sW = smem;                                          // weight image (bf16 operands + fp32 tail)
+  uint8_t* sA0 = smem + ((img.bytes + 1023) & ~1023u);         // 2 stages of the GEMM0 operand [128 x K0] bf16
+  uint8_t* sA = sA0 + 2 * kRows * K0 * 2;                      // GEMM1/GEMM2 operand [128 x KA] bf16
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + kRows * KA * 2);   // full[2], empty[2], mma
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + 2;
+  uint64_t* mma_bar = bars + 4;
   const float* sB1 = reinterpret_cast<const float*>(sW + img.off_f32);
   const float* sB2 = sB1 + 128;
   const float* sW3 = sB2 + 128;
@@ -162,14 +179,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_app_tc(const FwdParams P) {
   const TvmModel& m = P.m;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  // ---- one-time setup: weights -> smem, barrier, TMEM --------------------------------------------
+  // ---- one-time setup: weights -> smem, barriers, TMEM -------------------------------------------
   {
     const uint4* src = reinterpret_cast<const uint4*>(m.tc_weights);
     uint4* dst = reinterpret_cast<uint4*>(sW);
-    for (uint32_t i = tid; i < img.bytes / 16; i += kThreads) dst[i] = __ldg(src + i);
+    for (uint32_t i = tid; i < img.bytes / 16; i += kThreadsV2) dst[i] = __ldg(src + i);
   }
   if (tid == 0) {
-    mbar_init(bar, 1);
+    mbar_init(&full[0], kGatherWarps);
+    mbar_init(&full[1], kGatherWarps);
+    mbar_init(&empty[0], 1);
+    mbar_init(&empty[1], 1);
+    mbar_init(mma_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) tmem_alloc(tmem_slot, kTmemCols);
@@ -178,72 +199,75 @@ __global__ void __launch_bounds__(kThreads, 1) k_app_tc(const FwdParams P) {
   __syncthreads();
   fence_after();
   const uint32_t tmem = *tmem_slot;
-  uint32_t phase = 0;
 
-  const uint32_t aA = smem_u32(sA);
-  const uint32_t aB0 = smem_u32(sW + img.off_b0), aB1 = smem_u32(sW + img.off_b1), aB2 = smem_u32(sW + img.off_b2);
   constexpr uint32_t LBO_A = kRows * 16, LBO_B0 = 32 * 16, LBO_B = 128 * 16, SBO = 128;
   constexpr uint32_t IDESC_N32 = instr_desc(128, 32), IDESC_N128 = instr_desc(128, 128);
+  constexpr uint32_t A0_STAGE = kRows * K0 * 2;
 
   const uint32_t n_ent = *P.ws.n_entries;
   const uint32_t n_tiles = (n_ent + kRows - 1) / kRows;
 
-  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const uint32_t tile_base = tile * kRows;
-
-    // ---- gather: 8 warps x 16 rows, 4 lanes per row, bf16 straight into the GEMM0 operand -------
+  if (warp >= kMlpWarps) {
+    // =============================== gather group ================================================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
+    const int gw = warp - kMlpWarps;
+    constexpr int ROWS_PER_WARP = kRows / kGatherWarps;
+    uint32_t it = 0;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const uint32_t s = it & 1u, use = it >> 1;
+      mbar_wait(&empty[s], (use & 1u) ^ 1u);          // stage free (first use of a stage passes at once)
+      const uint32_t tile_base = tile * kRows;
+      uint8_t* stage = sA0 + s * A0_STAGE;
 #pragma unroll 1
-    for (int pass = 0; pass < 2; ++pass) {
-      const int row = warp * 16 + pass * 8 + (lane >> 2), q = lane & 3;
-      const uint32_t e = tile_base + row;
-      uint8_t* arow = sA + row * 16;
-      if (e < n_ent) {
-        const uint2 en = P.ws.ent[e];
-        float u[3], dir[3];
-        entry_coords(m, P.rays, P.jitter, en.x, en.y, u, dir);
-        Axis ax[3];
+      for (int pass = 0; pass < ROWS_PER_WARP / 8; ++pass) {
+        const int row = gw * ROWS_PER_WARP + pass * 8 + (lane >> 2), q = lane & 3;
+        const uint32_t e = tile_base + row;
+        uint8_t* arow = stage + row * 16;
+        if (e < n_ent) {
+          const uint2 en = P.ws.ent[e];
+          float u[3], dir[3];
+          entry_coords(m, P.rays, P.jitter, en.x, en.y, u, dir);
+          Axis ax[3];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) ax[i] = axis_taps(u[i], m.grid[i]);
+          for (int i = 0; i < 3; ++i) ax[i] = axis_taps(u[i], m.grid[i]);
 #pragma unroll
-        for (int kk = 0; kk < 3; ++kk) {
-          const VmTaps t = vm_taps(m, ax, kk);
+          for (int kk = 0; kk < 3; ++kk) {
+            const VmTaps t = vm_taps(m, ax, kk);
 #pragma unroll
-          for (int c = q * 4; c < CA; c += 16) {
-            float4 pv, lv;
-            vm_sample4(m.app_plane[kk], m.app_line[kk], t, CA, c, pv, lv);
-            const int k = kk * CA + c;
-            uint2 packed = make_uint2(pack_bf16(pv.x * lv.x, pv.y * lv.y), pack_bf16(pv.z * lv.z, pv.w * lv.w));
-            *reinterpret_cast<uint2*>(arow + (k >> 3) * LBO_A + (k & 7) * 2) = packed;
+            for (int c = q * 4; c < CA; c += 16) {
+              float4 pv, lv;
+              vm_sample4(m.app_plane[kk], m.app_line[kk], t, CA, c, pv, lv);
+              const int k = kk * CA + c;
+              uint2 packed = make_uint2(pack_bf16(pv.x * lv.x, pv.y * lv.y), pack_bf16(pv.z * lv.z, pv.w * lv.w));
+              *reinterpret_cast<uint2*>(arow + (k >> 3) * LBO_A + (k & 7) * 2) = packed;
+            }
           }
+        } else {
+#pragma unroll
+          for (int kk = 0; kk < 3; ++kk)
+#pragma unroll
+            for (int c = q * 4; c < CA; c += 16) {
+              const int k = kk * CA + c;
+              *reinterpret_cast<uint2*>(arow + (k >> 3) * LBO_A + (k & 7) * 2) = make_uint2(0u, 0u);
+            }
         }
-      } else {
-#pragma unroll
-        for (int kk = 0; kk < 3; ++kk)
-#pragma unroll
-          for (int c = q * 4; c < CA; c += 16) {
-            const int k = kk * CA + c;
-            *reinterpret_cast<uint2*>(arow + (k >> 3) * LBO_A + (k & 7) * 2) = make_uint2(0u, 0u);
-          }
       }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[s]);
     }
-    fence_async_smem();
-    __syncthreads();
-
-    // ---- GEMM0: feat = A0 . basis^T ---------------------------------------------------------------
-    if (tid == 0) {
-      fence_after();
-#pragma unroll
-      for (int k = 0; k < K0 / 16; ++k)
-        umma_bf16(tmem + kColBasis, smem_desc(aA + k * 2 * LBO_A, LBO_A, SBO),
-                  smem_desc(aB0 + k * 2 * LBO_B0, LBO_B0, SBO), IDESC_N32, k > 0);
-      umma_commit(bar);
-    }
-
-    // view directions of this thread's row (threads 0..127 own one row each from here on)
-    const int row = tid & (kRows - 1);
-    const uint32_t e = tile_base + row;
-    const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    if (tid < kRows) {
+  } else {
+    // =============================== MLP group =====================================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    const int row = tid;                                   // 0..127 = tile row = TMEM lane
+    const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t aA = smem_u32(sA);
+    const uint32_t aB0 = smem_u32(sW + img.off_b0), aB1 = smem_u32(sW + img.off_b1), aB2 = smem_u32(sW + img.off_b2);
+    uint8_t* arow = sA + row * 16;
+    uint32_t it = 0, mma_phase = 0;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const uint32_t s = it & 1u, use = it >> 1;
+      const uint32_t e = tile * kRows + row;
       float dir[3] = {0.0f, 0.0f, 0.0f};
       if (e < n_ent) {
         const uint32_t ray = P.ws.ent[e].x;
@@ -251,63 +275,78 @@ __global__ void __launch_bounds__(kThreads, 1) k_app_tc(const FwdParams P) {
         dir[1] = P.rays[6 * (size_t)ray + 4];
         dir[2] = P.rays[6 * (size_t)ray + 5];
       }
-      mbar_wait(bar, phase);
+      // ---- GEMM0: feat = A0[s] . basis^T ----------------------------------------------------------
+      if (tid == 0) {
+        mbar_wait(&full[s], use & 1u);
+        fence_after();
+        const uint32_t a0 = smem_u32(sA0 + s * A0_STAGE);
+#pragma unroll
+        for (int k = 0; k < K0 / 16; ++k)
+          umma_bf16(tmem + kColBasis, smem_desc(a0 + k * 2 * LBO_A, LBO_A, SBO),
+                    smem_desc(aB0 + k * 2 * LBO_B0, LBO_B0, SBO), IDESC_N32, k > 0);
+        umma_commit(&empty[s]);     // A0[s] may be refilled once these MMAs have read it
+        umma_commit(mma_bar);
+      }
+      mbar_wait(mma_bar, mma_phase);
+      mma_phase ^= 1;
       fence_after();
-      // ---- epi0: features -> [feat, view, sin/cos PE] as bf16, K-chunk by K-chunk ---------------
-      float x[32];
-      tmem_ld32(lane_addr + kColBasis, x);
-      // column c of the MLP input (tensorBase.py:76-83, 9-15): generated on the fly from feat / dir
-      float s1[APP_DIM + 3], c1[APP_DIM + 3];
+      {
+        // ---- epi0: features -> [feat, view, sin/cos PE] as bf16 (tensorBase.py:76-83, 9-15) -------
+        float x[32];
+        tmem_ld32(lane_addr + kColBasis, x);
+        float s1[APP_DIM + 3], c1[APP_DIM + 3];
 #pragma unroll
-      for (int o = 0; o < APP_DIM; ++o) __sincosf(x[o], &s1[o], &c1[o]);
+        for (int o = 0; o < APP_DIM; ++o) __sincosf(x[o], &s1[o], &c1[o]);
 #pragma unroll
-      for (int o = 0; o < 3; ++o) __sincosf(dir[o], &s1[APP_DIM + o], &c1[APP_DIM + o]);
-      auto column = [&](int c) -> float {
-        constexpr int PF = APP_DIM + 3, NF = FEA_PE * APP_DIM, PV = PF + 2 * NF, NV = VIEW_PE * 3;
-        if (c < APP_DIM) return x[c];
-        if (c < PF) return dir[c - APP_DIM];
-        if (c < PF + NF) { const int o = (c - PF) >> 1; return ((c - PF) & 1) ? 2.0f * s1[o] * c1[o] : s1[o]; }
-        if (c < PV) { const int o = (c - PF - NF) >> 1; return ((c - PF - NF) & 1) ? 1.0f - 2.0f * s1[o] * s1[o] : c1[o]; }
-        if (c < PV + NV) { const int o = APP_DIM + ((c - PV) >> 1); return ((c - PV) & 1) ? 2.0f * s1[o] * c1[o] : s1[o]; }
-        if (c < PV + 2 * NV) { const int o = APP_DIM + ((c - PV - NV) >> 1); return ((c - PV - NV) & 1) ? 1.0f - 2.0f * s1[o] * s1[o] : c1[o]; }
-        return 0.0f;
-      };
-      uint8_t* arow = sA + row * 16;
+        for (int o = 0; o < 3; ++o) __sincosf(dir[o], &s1[APP_DIM + o], &c1[APP_DIM + o]);
+        auto column = [&](int c) -> float {
+          constexpr int PF = APP_DIM + 3, NF = FEA_PE * APP_DIM, PV = PF + 2 * NF, NV = VIEW_PE * 3;
+          if (c < APP_DIM) return x[c];
+          if (c < PF) return dir[c - APP_DIM];
+          if (c < PF + NF) { const int o = (c - PF) >> 1; return ((c - PF) & 1) ? 2.0f * s1[o] * c1[o] : s1[o]; }
+          if (c < PV) { const int o = (c - PF - NF) >> 1; return ((c - PF - NF) & 1) ? 1.0f - 2.0f * s1[o] * s1[o] : c1[o]; }
+          if (c < PV + NV) { const int o = APP_DIM + ((c - PV) >> 1); return ((c - PV) & 1) ? 2.0f * s1[o] * c1[o] : s1[o]; }
+          if (c < PV + 2 * NV) { const int o = APP_DIM + ((c - PV - NV) >> 1); return ((c - PV - NV) & 1) ? 1.0f - 2.0f * s1[o] * s1[o] : c1[o]; }
+          return 0.0f;
+        };
 #pragma unroll
-      for (int kc = 0; kc < K1 / 8; ++kc) {
-        uint4 v;
-        v.x = pack_bf16(column(kc * 8 + 0), column(kc * 8 + 1));
-        v.y = pack_bf16(column(kc * 8 + 2), column(kc * 8 + 3));
-        v.z = pack_bf16(column(kc * 8 + 4), column(kc * 8 + 5));
-        v.w = pack_bf16(column(kc * 8 + 6), column(kc * 8 + 7));
-        *reinterpret_cast<uint4*>(arow + kc * LBO_A) = v;
+        for (int kc = 0; kc < K1 / 8; ++kc) {
+          uint4 v;
+          v.x = pack_bf16(column(kc * 8 + 0), column(kc * 8 + 1));
+          v.y = pack_bf16(column(kc * 8 + 2), column(kc * 8 + 3));
+          v.z = pack_bf16(column(kc * 8 + 4), column(kc * 8 + 5));
+          v.w = pack_bf16(column(kc * 8 + 6), column(kc * 8 + 7));
+          *reinterpret_cast<uint4*>(arow + kc * LBO_A) = v;
+        }
       }
       fence_async_smem();
       fence_before();
-    }
-    phase ^= 1;
-    __syncthreads();
-
-    // ---- GEMM1: A1 . W1^T ---------------------------------------------------------------------------
-    if (tid == 0) {
-      fence_after();
+      mlp_group_sync();
+      // ---- GEMM1: A1 . W1^T -------------------------------------------------------------------------
+      if (tid == 0) {
+        fence_after();
 #pragma unroll
-      for (int k = 0; k < K1 / 16; ++k)
-        umma_bf16(tmem, smem_desc(aA + k * 2 * LBO_A, LBO_A, SBO), smem_desc(aB1 + k * 2 * LBO_B, LBO_B, SBO),
-                  IDESC_N128, k > 0);
-      umma_commit(bar);
-    }
-    if (tid < kRows) {
-      mbar_wait(bar, phase);
+        for (int k = 0; k < K1 / 16; ++k)
+          umma_bf16(tmem, smem_desc(aA + k * 2 * LBO_A, LBO_A, SBO), smem_desc(aB1 + k * 2 * LBO_B, LBO_B, SBO),
+                    IDESC_N128, k > 0);
+        umma_commit(mma_bar);
+      }
+      mbar_wait(mma_bar, mma_phase);
+      mma_phase ^= 1;
       fence_after();
-      // ---- epi1: +b1, ReLU -> A2 (bf16) -----------------------------------------------------------
-      uint8_t* arow = sA + row * 16;
+      // ---- epi1: +b1, ReLU -> A2 (bf16) ----------------------------------------------------------------
 #pragma unroll
       for (int cb = 0; cb < 4; ++cb) {
         float y[32];
         tmem_ld32(lane_addr + cb * 32, y);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j] + sB1[cb * 32 + j], 0.0f);
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b = *reinterpret_cast<const float4*>(sB1 + cb * 32 + j);
+          y[j] = fmaxf(y[j] + b.x, 0.0f);
+          y[j + 1] = fmaxf(y[j + 1] + b.y, 0.0f);
+          y[j + 2] = fmaxf(y[j + 2] + b.z, 0.0f);
+          y[j + 3] = fmaxf(y[j + 3] + b.w, 0.0f);
+        }
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           uint4 v;
@@ -320,34 +359,36 @@ __global__ void __launch_bounds__(kThreads, 1) k_app_tc(const FwdParams P) {
       }
       fence_async_smem();
       fence_before();
-    }
-    phase ^= 1;
-    __syncthreads();
-
-    // ---- GEMM2: A2 . W2^T ---------------------------------------------------------------------------
-    if (tid == 0) {
-      fence_after();
+      mlp_group_sync();
+      // ---- GEMM2: A2 . W2^T -------------------------------------------------------------------------
+      if (tid == 0) {
+        fence_after();
 #pragma unroll
-      for (int k = 0; k < 128 / 16; ++k)
-        umma_bf16(tmem, smem_desc(aA + k * 2 * LBO_A, LBO_A, SBO), smem_desc(aB2 + k * 2 * LBO_B, LBO_B, SBO),
-                  IDESC_N128, k > 0);
-      umma_commit(bar);
-    }
-    if (tid < kRows) {
-      mbar_wait(bar, phase);
+        for (int k = 0; k < 128 / 16; ++k)
+          umma_bf16(tmem, smem_desc(aA + k * 2 * LBO_A, LBO_A, SBO), smem_desc(aB2 + k * 2 * LBO_B, LBO_B, SBO),
+                    IDESC_N128, k > 0);
+        umma_commit(mma_bar);
+      }
+      mbar_wait(mma_bar, mma_phase);
+      mma_phase ^= 1;
       fence_after();
-      // ---- epi2: +b2, ReLU, 128 -> 3 on CUDA cores, sigmoid ---------------------------------------
+      // ---- epi2: +b2, ReLU, 128 -> 3 on CUDA cores, sigmoid ----------------------------------------------
       float o0 = sB3[0], o1 = sB3[1], o2 = sB3[2];
 #pragma unroll
       for (int cb = 0; cb < 4; ++cb) {
         float y[32];
         tmem_ld32(lane_addr + cb * 32, y);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float h = fmaxf(y[j] + sB2[cb * 32 + j], 0.0f);
-          o0 = fmaf(h, sW3[cb * 32 + j], o0);
-          o1 = fmaf(h, sW3[128 + cb * 32 + j], o1);
-          o2 = fmaf(h, sW3[256 + cb * 32 + j], o2);
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b = *reinterpret_cast<const float4*>(sB2 + cb * 32 + j);
+          const float4 w0 = *reinterpret_cast<const float4*>(sW3 + cb * 32 + j);
+          const float4 w1 = *reinterpret_cast<const float4*>(sW3 + 128 + cb * 32 + j);
+          const float4 w2 = *reinterpret_cast<const float4*>(sW3 + 256 + cb * 32 + j);
+          const float h0 = fmaxf(y[j] + b.x, 0.0f), h1 = fmaxf(y[j + 1] + b.y, 0.0f);
+          const float h2 = fmaxf(y[j + 2] + b.z, 0.0f), h3 = fmaxf(y[j + 3] + b.w, 0.0f);
+          o0 = fmaf(h0, w0.x, fmaf(h1, w0.y, fmaf(h2, w0.z, fmaf(h3, w0.w, o0))));
+          o1 = fmaf(h0, w1.x, fmaf(h1, w1.y, fmaf(h2, w1.z, fmaf(h3, w1.w, o1))));
+          o2 = fmaf(h0, w2.x, fmaf(h1, w2.y, fmaf(h2, w2.z, fmaf(h3, w2.w, o2))));
         }
       }
       if (e < n_ent) {
@@ -356,9 +397,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_app_tc(const FwdParams P) {
         P.ws.ent_rgb[(size_t)e * 3 + 2] = 1.0f / (1.0f + __expf(-o2));
       }
       fence_before();
+      mlp_group_sync();     // TMEM columns and the A operand are free for the next tile
     }
-    phase ^= 1;
-    __syncthreads();   // A operand and TMEM are free for the next tile
   }
 
   fence_before();
@@ -377,11 +417,11 @@ int launch_app_tc(const FwdParams& P, int num_sms, cudaStream_t stream) {
                                  "featureC=128 (all shipped configs); use TVM_MLP_FP32 otherwise");
   TVM_REQUIRE(P.m.tc_weights != nullptr, "TvmModel.tc_weights is NULL: call tvm_pack_mlp_tc first");
   const Image img(P.m.n_app, P.in_mlp_c);
-  const int KA = max(max(img.K0, img.K1), 128);
-  const size_t smem = ((img.bytes + 1023) & ~1023u) + (size_t)kRows * KA * 2 + 64 + 1024;
+  const int KA = max(img.K1, 128);
+  const size_t smem = ((img.bytes + 1023) & ~1023u) + 2 * (size_t)kRows * img.K0 * 2 + (size_t)kRows * KA * 2 + 128 + 1024;
   auto kern = k_app_tc<48, 27, 2, 2>;
   TVM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<num_sms, kThreads, smem, stream>>>(P);
+  kern<<<num_sms, kThreadsV2, smem, stream>>>(P);
   TVM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
