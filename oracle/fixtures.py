@@ -59,8 +59,9 @@ class ModelParams:
 def make_model(G, seed: int = SEED_BASE, density_shift: float = -10.0,
                cd: int = 16, ca: int = 48, app_dim: int = 27, featureC: int = 128,
                view_pe: int = 2, fea_pe: int = 2, bbox: float = 5.0,
-               near_far=(5.0, 40.0), grid_scale: float = 0.1) -> ModelParams:
-    """Random-init TensorVMSplit parameters (seed+0)."""
+               near_far=(5.0, 40.0), grid_scale: float = 0.1, variant: str = "vm") -> ModelParams:
+    """Random-init TensorVMSplit parameters (seed+0).  variant="ref" adds REFTensoRF's four heads
+    (models/REFTensoRF.py:80-95) and widens the MLP input by the dot-product column (:9)."""
     if isinstance(G, int):
         G = (G, G, G)
     G = tuple(int(g) for g in G)
@@ -87,12 +88,17 @@ def make_model(G, seed: int = SEED_BASE, density_shift: float = -10.0,
         return w, bb
 
     basis, _ = lin(app_dim, 3 * ca, bias=False)
-    in_mlpC = 2 * view_pe * 3 + 2 * fea_pe * app_dim + 3 + app_dim
+    in_mlpC = 2 * view_pe * 3 + 2 * fea_pe * app_dim + 3 + app_dim + (1 if variant == "ref" else 0)
     w1, b1 = lin(featureC, in_mlpC)
     w2, b2 = lin(featureC, featureC)
     w3, b3 = lin(3, featureC)
     b3 = np.zeros_like(b3)  # tensorBase.py:74
-    return ModelParams(aabb=aabb, gridSize=G, density_plane=dp, density_line=dl, app_plane=ap, app_line=al,
+    extra = {"variant": variant}
+    if variant == "ref":
+        for name, oc in (("normal", 3), ("diffuse", 3), ("specular", 1), ("rho", 1)):
+            w, b = lin(oc, 3 * ca)
+            extra[name + "_w"], extra[name + "_b"] = w, b
+    return ModelParams(extra=extra, aabb=aabb, gridSize=G, density_plane=dp, density_line=dl, app_plane=ap, app_line=al,
                        basis_mat=basis, mlp_w=[w1, w2, w3], mlp_b=[b1, b2, b3], near_far=tuple(near_far),
                        density_shift=density_shift, view_pe=view_pe, fea_pe=fea_pe, app_dim=app_dim,
                        featureC=featureC, density_n_comp=(cd,) * 3, app_n_comp=(ca,) * 3)

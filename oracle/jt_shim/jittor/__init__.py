@@ -146,6 +146,28 @@ def split(x, size, dim=0):
     return [_v(t) for t in torch.split(x, size, dim)]
 
 
+def normalize(input, p=2, dim=1, eps=1e-30):
+    """jittor/misc.py (as recalled): input / input.norm(p, dim, keepdims=True, eps)."""
+    return input / torch.sqrt(torch.clamp(torch.sum(input * input, dim, keepdim=True), min=eps))
+
+
+def broadcast(x, shape, dims=()):
+    """jt.broadcast(x, shape, dims): insert the listed dims, then expand to `shape`."""
+    nd = len(shape)
+    for d in sorted(d % nd for d in dims):
+        x = x.unsqueeze(d)
+    return x.expand(*shape)
+
+
+def clamp(x, min_v=None, max_v=None):
+    return torch.clamp(x, min=min_v, max=max_v)
+
+
+def sqr(x):
+    return x * x
+
+
+multiply = torch.mul
 zeros_like = torch.zeros_like
 ones_like = torch.ones_like
 full_like = torch.full_like

@@ -334,8 +334,7 @@ class OracleTensorVMSplit:
         app_mask = weight > self.rayMarch_weight_thres
 
         if app_mask.any():
-            app_features = self.compute_appfeature(xyz_sampled[app_mask])
-            valid_rgbs = self.renderModule(xyz_sampled[app_mask], viewdirs[app_mask], app_features)
+            valid_rgbs = self.shade(xyz_sampled[app_mask], viewdirs[app_mask], weight[app_mask])
             rgb = rgb.index_put((app_mask,), valid_rgbs)
 
         acc_map = torch.sum(weight, -1)
@@ -354,7 +353,13 @@ class OracleTensorVMSplit:
                           acc_map=acc_map.detach(), rgb_map_raw=rgb_map_raw.detach())
         return rgb_map, depth_map
 
-    __call__ = execute
+    def __call__(self, *a, **k):
+        return self.execute(*a, **k)
+
+    def shade(self, xyz, viewdirs, weight):
+        """models/tensorBase.py:516-517: appearance features -> MLPRender_Fea."""
+        app_features = self.compute_appfeature(xyz)
+        return self.renderModule(xyz, viewdirs, app_features)
 
     # -- §8f-1: dense alpha on arbitrary points ------------------------------------------------
     def compute_alpha(self, xyz_locs, length=1.0):
@@ -369,6 +374,66 @@ class OracleTensorVMSplit:
             xyz_sampled = self.normalize_coord(xyz_locs[alpha_mask])
             sigma[alpha_mask] = self.feature2density(self.compute_densityfeature(xyz_sampled))
         return 1 - torch.exp(-sigma * length).view(xyz_locs.shape[:-1])
+
+
+def jt_normalize(x, dim=-1, eps=1e-30):
+    """A7: jt.normalize(x, p=2, dim) = x / sqrt(max(sum(x^2, dim), eps)) (jittor/misc.py, as recalled)."""
+    return x / torch.sqrt(torch.clamp(torch.sum(x * x, dim, keepdim=True), min=eps))
+
+
+class OracleREFTensoRF(OracleTensorVMSplit):
+    """REFTensoRF (models/REFTensoRF.py:64-256): Ref-NeRF style heads on the 144-vector, reflected view
+    direction into MLPRender_Fea_Ref (:5-29), rgb = tint * clamp(rgb_s, 0) + rgb_d, normal penalty."""
+
+    def __init__(self, params, *a, **k):
+        super().__init__(params, *a, **k)
+        t = lambda a_: torch.tensor(np.asarray(a_), dtype=self.dtype)
+        e = params.extra
+        self.heads = {n: (t(e[n + "_w"]), t(e[n + "_b"])) for n in ("normal", "diffuse", "specular", "rho")}
+        if self.basis_mat.requires_grad:
+            for w, b in self.heads.values():
+                w.requires_grad_(True)
+                b.requires_grad_(True)
+        self.penalty = torch.zeros((), dtype=self.dtype)
+
+    def named_parameters(self):
+        out = super().named_parameters()
+        for n, (w, b) in getattr(self, "heads", {}).items():
+            out[f"{n}_linear.weight"], out[f"{n}_linear.bias"] = w, b
+        return out
+
+    def shade(self, xyz, viewdirs, weight):
+        """REFTensoRF.compute_appfeature (:107-133) + execute (:216-238)."""
+        h = self.compute_app_vector(xyz)
+        lin = lambda n: h @ self.heads[n][0].T + self.heads[n][1]
+        app_features = h @ self.basis_mat.T
+        normal_vector, rgb_d = lin("normal"), lin("diffuse")
+        specular_tint = torch.relu(lin("specular"))
+        rho = torch.relu(lin("rho"))                     # only ever passed on as k = 1/rho, which the MLP ignores
+        normal_vector = jt_normalize(normal_vector, dim=-1)
+        d = -viewdirs
+        dot_product = (d * normal_vector).sum(dim=1)[:, None]
+        reflection = 2 * dot_product * normal_vector - d
+        # MLPRender_Fea_Ref.execute(pts, viewdirs=reflection, features, dot_product=-dot, k)
+        indata = [-dot_product, app_features, reflection]
+        if self.fea_pe > 0:
+            indata += [positional_encoding(app_features, self.fea_pe)]
+        if self.view_pe > 0:
+            indata += [positional_encoding(reflection, self.view_pe)]
+        x = torch.cat(indata, dim=-1)
+        x = torch.relu(x @ self.mlp_w[0].T + self.mlp_b[0])
+        x = torch.relu(x @ self.mlp_w[1].T + self.mlp_b[1])
+        rgb_s = torch.sigmoid(x @ self.mlp_w[2].T + self.mlp_b[2])
+        valid_rgbs = specular_tint * torch.clamp(rgb_s, min=0) + rgb_d
+        penalty = torch.relu(-dot_product) ** 2
+        self.penalty = torch.sum(weight * penalty.squeeze(-1), -1)
+        return valid_rgbs
+
+
+def make_oracle(case, dtype=torch.float32, opts=None, requires_grad=False):
+    cls = OracleREFTensoRF if case["model"].extra.get("variant") == "ref" else OracleTensorVMSplit
+    return cls(case["model"], case["alpha_volume"], case["alpha_aabb"], dtype=dtype, opts=opts,
+               requires_grad=requires_grad)
 
 
 def OctreeRender_trilinear_fast(rays, tensorf, chunk=4096, N_samples=-1, ndc_ray=False, white_bg=True,
@@ -391,11 +456,12 @@ def OctreeRender_trilinear_fast(rays, tensorf, chunk=4096, N_samples=-1, ndc_ray
 def run_case(case, dtype=torch.float32, opts=None, N_samples=-1, white_bg=True, want_stages=True,
              chunk=4096):
     """Forward a fixtures.make_case() dict; returns dict of numpy outputs (+ per-sample stages)."""
-    m = OracleTensorVMSplit(case["model"], case["alpha_volume"], case["alpha_aabb"], dtype=dtype, opts=opts)
+    m = make_oracle(case, dtype=dtype, opts=opts)
     rays = torch.from_numpy(case["rays"])
     jit = None if case.get("jitter") is None else torch.from_numpy(case["jitter"])
     is_train = jit is not None
     outs, st_all = [], []
+    penalty = 0.0
     for s in range(0, rays.shape[0], chunk):
         st = {} if want_stages else None
         with torch.no_grad():
@@ -403,7 +469,8 @@ def run_case(case, dtype=torch.float32, opts=None, N_samples=-1, white_bg=True, 
                            jitter=None if jit is None else jit[s:s + chunk], stages=st)
         outs.append((rgb, depth))
         st_all.append(st)
-    res = dict(rgb_map=torch.cat([o[0] for o in outs]).numpy(), depth_map=torch.cat([o[1] for o in outs]).numpy(),
+        penalty += float(getattr(m, "penalty", 0.0))
+    res = dict(penalty=penalty, rgb_map=torch.cat([o[0] for o in outs]).numpy(), depth_map=torch.cat([o[1] for o in outs]).numpy(),
                nSamples=m.nSamples, stepSize=float(m.stepSize))
     if want_stages:
         for k in st_all[0]:
@@ -420,8 +487,7 @@ def work_counts(stages):
 def backward_case(case, d_rgb_map=None, dtype=torch.float64, opts=None, N_samples=-1, white_bg=True):
     """Gradients of sum(rgb_map * d_rgb_map) (or of train.py:228's MSE against case['target'] when
     d_rgb_map is None) w.r.t. every parameter, in the reference's NCHW shapes (row a12)."""
-    m = OracleTensorVMSplit(case["model"], case["alpha_volume"], case["alpha_aabb"], dtype=dtype, opts=opts,
-                            requires_grad=True)
+    m = make_oracle(case, dtype=dtype, opts=opts, requires_grad=True)
     rays = torch.from_numpy(case["rays"])
     jit = None if case.get("jitter") is None else torch.from_numpy(case["jitter"])
     rgb, depth = m(rays, white_bg=white_bg, is_train=jit is not None, N_samples=N_samples, jitter=jit)

@@ -27,6 +27,7 @@ from oracle import fixtures as fx
 
 with contextlib.redirect_stdout(io.StringIO()):
     from models.tensoRF import TensorVMSplit, AlphaGridMask      # the reference, unmodified
+    from models.REFTensoRF import REFTensoRF
 
 CASES = {
     # name: (G, n_rays, regime, train, mask_res, white_bg, N_samples)
@@ -34,13 +35,17 @@ CASES = {
     "g48_R1_eval": (48, 96, "R1", False, 48, True, -1),
     "g48_R2_train_blackbg": (48, 96, "R2", True, 40, False, 167),
     "g32x40x48_R2_eval": ((32, 40, 48), 64, "R2", False, (30, 36, 44), True, -1),
+    # REFTensoRF variant (models/REFTensoRF.py): 8th field = variant
+    "ref_g40_R2_eval": (40, 96, "R2", False, 40, True, -1, "ref"),
+    "ref_g40_R1_train": (40, 96, "R1", True, 32, True, 139, "ref"),
 }
 
 
 def build_reference_model(case):
     p = case["model"]
     with contextlib.redirect_stdout(io.StringIO()):
-        m = TensorVMSplit(jt.Var(p.aabb), list(p.gridSize), "cpu", density_n_comp=list(p.density_n_comp),
+        cls = REFTensoRF if p.extra.get("variant") == "ref" else TensorVMSplit
+        m = cls(jt.Var(p.aabb), list(p.gridSize), "cpu", density_n_comp=list(p.density_n_comp),
                           appearance_n_comp=list(p.app_n_comp), app_dim=p.app_dim, near_far=list(p.near_far),
                           shadingMode="MLP_Fea", alphaMask_thres=0.001, density_shift=p.density_shift,
                           distance_scale=p.distance_scale, pos_pe=6, view_pe=p.view_pe, fea_pe=p.fea_pe,
@@ -55,14 +60,20 @@ def build_reference_model(case):
         for i, li in enumerate((0, 2, 4)):
             m.renderModule.mlp[li].weight.copy_(torch.from_numpy(p.mlp_w[i]))
             m.renderModule.mlp[li].bias.copy_(torch.from_numpy(p.mlp_b[i]))
+        if p.extra.get("variant") == "ref":
+            for n in ("normal", "diffuse", "specular", "rho"):
+                getattr(m, n + "_linear").weight.copy_(torch.from_numpy(p.extra[n + "_w"]))
+                getattr(m, n + "_linear").bias.copy_(torch.from_numpy(p.extra[n + "_b"]))
     if case["alpha_volume"] is not None:
         m.alphaMask = AlphaGridMask("cpu", jt.Var(case["alpha_aabb"]), jt.Var(case["alpha_volume"]))
     return m
 
 
 def main():
-    for name, (G, n, regime, train, mask_res, white_bg, S) in CASES.items():
-        case = fx.make_case(G, n, regime, mask_res=mask_res, train=train)
+    for name, spec in CASES.items():
+        G, n, regime, train, mask_res, white_bg, S = spec[:7]
+        variant = spec[7] if len(spec) > 7 else "vm"
+        case = fx.make_case(G, n, regime, mask_res=mask_res, train=train, variant=variant)
         m = build_reference_model(case)
         rays = jt.Var(case["rays"])
         if train:
@@ -80,7 +91,8 @@ def main():
                    bbox_valid=bbox_valid.numpy(), ray_valid=(sigma.numpy() > 0), app_mask=app_mask.numpy(),
                    z_vals=np.broadcast_to(z_vals.numpy(), weight.shape).copy(),
                    nSamples=np.int64(m.nSamples), stepSize=np.float32(m.stepSize.item()),
-                   args=np.array([str(G), str(n), regime, str(train), str(mask_res), str(white_bg), str(S)]))
+                   penalty=np.float32(float(m.penalty.sum())) if variant == "ref" else np.float32(0),
+                   args=np.array([str(G), str(n), regime, str(train), str(mask_res), str(white_bg), str(S), variant]))
         path = os.path.join(HERE, name + ".npz")
         np.savez_compressed(path, **out)
         print(name, "->", os.path.getsize(path) // 1024, "KiB; M_v", int(out["ray_valid"].sum()), "M_a",

@@ -15,14 +15,16 @@ GOLD = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)),
 
 def load_case(path):
     g = np.load(path)
-    G, n, regime, train, mask_res, white_bg, S = [str(x) for x in g["args"]]
+    a = [str(x) for x in g["args"]]
+    G, n, regime, train, mask_res, white_bg, S = a[:7]
+    variant = a[7] if len(a) > 7 else "vm"
     case = fx.make_case(ast.literal_eval(G), int(n), regime, mask_res=ast.literal_eval(mask_res),
-                        train=(train == "True"))
+                        train=(train == "True"), variant=variant)
     return g, case, white_bg == "True", int(S)
 
 
 def test_golden_files_present():
-    assert len(GOLD) >= 4
+    assert len(GOLD) >= 6
 
 
 @pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[:-4] for p in GOLD])
@@ -42,3 +44,5 @@ def test_oracle_matches_reference_python(path):
     assert np.abs(r["rgb_map"] - g["rgb_map"]).max() <= 1e-5
     assert np.abs(r["depth_map"] - g["depth_map"]).max() <= 1e-4
     assert np.abs(r["bg_weight"] - g["bg_weight"]).max() <= 1e-6
+    if "penalty" in g.files and float(g["penalty"]) != 0:
+        assert abs(r["penalty"] - float(g["penalty"])) <= 1e-5 * max(1.0, abs(float(g["penalty"])))
