@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define TVM_ABI_VERSION 4
+#define TVM_ABI_VERSION 5
 
 /* flags for tvm_forward / tvm_backward */
 #define TVM_WHITE_BG      0x1u  /* rgb_map += 1 - acc_map          (tensorBase.py:523-524) */
@@ -42,6 +42,11 @@ extern "C" {
 #define TVM_MLP_BF16      0x10u /* appearance head on tcgen05 tensor cores, bf16 x bf16 -> fp32 (parity 1e-2) */
 #define TVM_MLP_BF16X3    0x20u /* tcgen05, 3-term split-bf16 (near-fp32; parity 1e-4)       */
 #define TVM_MLP_MASK      0x30u
+
+/* model variant */
+#define TVM_VARIANT_VM    0     /* TensorVMSplit + MLPRender_Fea          (tensoRF.py:141, tensorBase.py:62) */
+#define TVM_VARIANT_REF   1     /* REFTensoRF + MLPRender_Fea_Ref         (REFTensoRF.py:64, :5)             */
+#define TVM_REF_HEAD_LD   48    /* basis_t row length for TVM_VARIANT_REF: [basis app_dim | normal 3 | diffuse 3 | specular 1 | rho 1 | 0...] */
 
 /* activation (tensorBase.py:444-448) */
 #define TVM_ACT_SOFTPLUS  0
@@ -73,7 +78,10 @@ typedef struct TvmModel {
   const float* app_plane[3];
   const float* app_line[3];
   /* appearance head, [in][out_padded] layouts from tvm_pack_linear              */
-  const float* basis_t;     /* [3*n_app][32]        basis_mat.weight^T, zero padded      */
+  int32_t variant;          /* TVM_VARIANT_*                                              */
+  const float* basis_t;     /* [3*n_app][32] basis_mat.weight^T, zero padded; TVM_VARIANT_REF: [3*n_app][48] =
+                               (basis_mat | normal_linear | diffuse_linear | specular_linear | rho_linear)^T  */
+  const float* head_bias;   /* TVM_VARIANT_REF: [48] biases of the stacked heads (0 for basis_mat); else NULL */
   const float* w1_t;        /* [in_mlp_c][feature_c] renderModule.mlp.0.weight^T          */
   const float* b1;          /* [feature_c]                                                */
   const float* w2_t;        /* [feature_c][feature_c]                                     */
@@ -102,6 +110,8 @@ typedef struct TvmAux {
   float* weight;            /* [n][S]                                                                */
   float* rgb;               /* [n][S][3]        per-sample colour (0 where !app_mask)                */
   float* acc_map;           /* [n]                                                                   */
+  float* penalty;           /* [1] TVM_VARIANT_REF: += sum w[app] * relu(-d.n)^2 (REFTensoRF.py:236-238); does not
+                               by itself select the parity (no-ERT) instantiation                                   */
 } TvmAux;
 
 /* Gradient targets of tvm_backward: same PACKED layouts as TvmModel; accumulated with

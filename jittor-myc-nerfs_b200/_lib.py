@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libtvmrender.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 # flags (tvmrender.h)
 WHITE_BG = 0x1
@@ -19,6 +19,7 @@ MLP_FP32 = 0x0
 MLP_BF16 = 0x10
 MLP_BF16X3 = 0x20
 ACT_SOFTPLUS, ACT_RELU = 0, 1
+VARIANT_VM, VARIANT_REF, REF_HEAD_LD = 0, 1, 48
 CNT_M_IN, CNT_M_V, CNT_M_A, CNT_RAYS, CNT_WORDS = 0, 1, 2, 3, 8
 STAGE_NAMES = ["march", "app", "composite", "bwd_app", "bwd_march"]
 STAGE_COUNT = 8
@@ -37,7 +38,7 @@ class TvmModel(C.Structure):
         ("act", C.c_int32), ("n_density", C.c_int32), ("n_app", C.c_int32), ("app_dim", C.c_int32),
         ("view_pe", C.c_int32), ("fea_pe", C.c_int32), ("feature_c", C.c_int32),
         ("density_plane", _p3), ("density_line", _p3), ("app_plane", _p3), ("app_line", _p3),
-        ("basis_t", C.c_void_p), ("w1_t", C.c_void_p), ("b1", C.c_void_p), ("w2_t", C.c_void_p),
+        ("variant", C.c_int32), ("basis_t", C.c_void_p), ("head_bias", C.c_void_p), ("w1_t", C.c_void_p), ("b1", C.c_void_p), ("w2_t", C.c_void_p),
         ("b2", C.c_void_p), ("w3", C.c_void_p), ("b3", C.c_void_p),
         ("alpha_bits", C.c_void_p), ("alpha_grid", _i3), ("alpha_aabb_min", _f3), ("alpha_inv_size", _f3),
         ("alpha_bricks", C.c_void_p), ("tc_weights", C.c_void_p),
@@ -46,7 +47,8 @@ class TvmModel(C.Structure):
 
 class TvmAux(C.Structure):
     _fields_ = [("bbox_bits", C.c_void_p), ("valid_bits", C.c_void_p), ("app_bits", C.c_void_p),
-                ("sigma", C.c_void_p), ("weight", C.c_void_p), ("rgb", C.c_void_p), ("acc_map", C.c_void_p)]
+                ("sigma", C.c_void_p), ("weight", C.c_void_p), ("rgb", C.c_void_p), ("acc_map", C.c_void_p),
+                ("penalty", C.c_void_p)]
 
 
 class TvmGrads(C.Structure):

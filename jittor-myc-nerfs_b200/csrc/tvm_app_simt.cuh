@@ -52,56 +52,86 @@ __device__ __forceinline__ void app_gather_tile(const FwdParams& P, uint32_t til
         *reinterpret_cast<float4*>(h + kk * Ca + c) = make_float4(pv.x * lv.x, pv.y * lv.y, pv.z * lv.z, pv.w * lv.w);
       }
     }
-    if (q < 3) X[row * st + m.app_dim + q] = dir[q];
+    if (q < 3) X[row * st + col_dir(m) + q] = dir[q];
   } else {
     for (int c = q * 4; c < 3 * Ca; c += 16) *reinterpret_cast<float4*>(h + c) = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (q < 3) X[row * st + m.app_dim + q] = 0.0f;
+    if (q < 3) X[row * st + col_dir(m) + q] = 0.0f;
   }
 }
 
-// basis_mat + positional encoding (tensoRF.py:244; tensorBase.py:9-15,76-83):
-// thread (row, part) owns basis outputs [part*8, part*8+8); zero-fills the padding columns of X.
-__device__ __forceinline__ void app_basis_pe(const FwdParams& P, const float* H, float* X, int st) {
+// basis_mat (+ REFTensoRF heads) and positional encoding (tensoRF.py:244; tensorBase.py:9-15,76-83;
+// REFTensoRF.py:107-133,216-232).  Thread (row, part) owns head outputs [part*NH/4, (part+1)*NH/4);
+// NH = 32 (basis only) or 48 (basis | normal | diffuse | specular | rho).  HD [64][8] is a side buffer:
+// in: raw head outputs of the REF variant; out: {rgb_d[3], tint, .., ..} for the final colour.
+template <int NH>
+__device__ __forceinline__ void app_basis_pe(const FwdParams& P, const float* H, float* X, float* HD, int st,
+                                             uint32_t tile_base, uint32_t n_ent) {
+  constexpr int NP = NH / 4;
   const TvmModel& m = P.m;
+  const bool ref = NH == TVM_REF_HEAD_LD;
   const int row = threadIdx.x & (kAppTile - 1), part = threadIdx.x >> 6;
   const int K = 3 * m.n_app;
-  float acc[8];
+  float acc[NP];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
+  for (int i = 0; i < NP; ++i) acc[i] = 0.0f;
   const float* h = H + row * st;
-  const float* bt = m.basis_t + part * 8;
+  const float* bt = m.basis_t + part * NP;
   for (int j = 0; j < K; j += 4) {
     const float4 x = lds4(h + j);
     const float xs[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
-    for (int jj = 0; jj < 4; ++jj) {
-      fma4(acc, xs[jj], ldg4(bt + (j + jj) * kMaxAppDim));
-      fma4(acc + 4, xs[jj], ldg4(bt + (j + jj) * kMaxAppDim + 4));
-    }
+    for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+      for (int i = 0; i < NP; i += 4) fma4(acc + i, xs[jj], ldg4(bt + (j + jj) * NH + i));
   }
   float* xr = X + row * st;
-  const int pe_f = m.app_dim + 3;                       // start of sin(PE(features))
-  const int pe_v = pe_f + 2 * m.fea_pe * m.app_dim;     // start of sin(PE(viewdirs))
+  const int c_feat = col_feat(m), c_dir = col_dir(m);
+  const int pe_f = c_dir + 3;                            // start of sin(PE(features))
+  const int pe_v = pe_f + 2 * m.fea_pe * m.app_dim;      // start of sin(PE(direction))
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int o = part * 8 + i;
+  for (int i = 0; i < NP; ++i) {
+    const int o = part * NP + i;
     if (o < m.app_dim) {
       const float f = acc[i];
-      xr[o] = f;
+      xr[c_feat + o] = f;
       float fr = 1.0f;
       for (int q = 0; q < m.fea_pe; ++q, fr *= 2.0f) {
         const float s = f * fr;
         xr[pe_f + o * m.fea_pe + q] = sinf(s);
         xr[pe_f + m.fea_pe * m.app_dim + o * m.fea_pe + q] = cosf(s);
       }
+    } else if (ref && o < m.app_dim + 8) {
+      HD[row * 8 + (o - m.app_dim)] = acc[i] + __ldg(m.head_bias + o);
     }
   }
+  if (ref) __syncthreads();
   if (part == 3) {
+    float d[3] = {xr[c_dir], xr[c_dir + 1], xr[c_dir + 2]};     // view direction left there by the gather
+    if (ref) {
+      // normal = normalize(normal_linear(h)); d = -view; dot = d.n; reflection = 2 dot n - d
+      float* hd = HD + row * 8;
+      float nx = hd[0], ny = hd[1], nz = hd[2];
+      const float inv = 1.0f / sqrtf(fmaxf(nx * nx + ny * ny + nz * nz, 1e-30f));
+      nx *= inv; ny *= inv; nz *= inv;
+      const float dx = -d[0], dy = -d[1], dz = -d[2];
+      const float dot = dx * nx + dy * ny + dz * nz;
+      d[0] = 2.0f * dot * nx - dx;
+      d[1] = 2.0f * dot * ny - dy;
+      d[2] = 2.0f * dot * nz - dz;
+      xr[0] = -dot;
+      xr[c_dir] = d[0]; xr[c_dir + 1] = d[1]; xr[c_dir + 2] = d[2];
+      const float r0 = hd[3], r1 = hd[4], r2 = hd[5], tint = fmaxf(hd[6], 0.0f);
+      hd[0] = r0; hd[1] = r1; hd[2] = r2; hd[3] = tint;
+      const uint32_t e = tile_base + row;
+      if (P.aux.penalty && e < n_ent) {
+        const float pen = fmaxf(-dot, 0.0f);
+        atomicAdd(P.aux.penalty, P.ws.ent_w[e] * pen * pen);
+      }
+    }
     for (int c = 0; c < 3; ++c) {
-      const float d = xr[m.app_dim + c];
       float fr = 1.0f;
       for (int q = 0; q < m.view_pe; ++q, fr *= 2.0f) {
-        const float s = d * fr;
+        const float s = d[c] * fr;
         xr[pe_v + c * m.view_pe + q] = sinf(s);
         xr[pe_v + 3 * m.view_pe + c * m.view_pe + q] = cosf(s);
       }

@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(kAppThreads) k_app_bwd(const BwdParams B) {
     // ---- forward recompute ---------------------------------------------------------------------
     app_gather_tile(P, tile_base, n_ent, H, X, st);
     __syncthreads();
-    app_basis_pe(P, H, X, st);
+    app_basis_pe<32>(P, H, X, D3, st, tile_base, n_ent);
     __syncthreads();
     app_dense<true>(m.w1_t, m.b1, X, P.in_mlp_c, Y1, st);
     __syncthreads();
@@ -494,6 +494,7 @@ extern "C" int tvm_backward(const TvmModel* m_host, const float* rays, int n_ray
   BwdParams B;
   if (int rc = fill_fwd_params(B.f, m_host, rays, n_rays, n_samples, jitter, flags, ws, ws_bytes)) return rc;
   TVM_REQUIRE(d_rgb_map && grads_host, "null argument");
+  TVM_REQUIRE(m_host->variant == TVM_VARIANT_VM, "tvm_backward supports TVM_VARIANT_VM only (REFTensoRF backward is not built)");
   B.d_rgb_map = d_rgb_map;
   B.g = *grads_host;
   for (int k = 0; k < 3; ++k)

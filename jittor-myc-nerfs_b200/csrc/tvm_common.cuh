@@ -86,11 +86,17 @@ struct FwdParams {
   float* depth_map;
   TvmAux aux;
   unsigned long long* counters;
-  int in_mlp_c;   // 2*view_pe*3 + 2*fea_pe*app_dim + 3 + app_dim
+  int in_mlp_c;   // 2*view_pe*3 + 2*fea_pe*app_dim + 3 + app_dim (+1 for TVM_VARIANT_REF)
   int st;         // smem row stride (floats) of the fp32 appearance tiles
 };
 
-inline int in_mlp_c(const TvmModel& m) { return 2 * m.view_pe * 3 + 2 * m.fea_pe * m.app_dim + 3 + m.app_dim; }
+inline int in_mlp_c(const TvmModel& m) {
+  return 2 * m.view_pe * 3 + 2 * m.fea_pe * m.app_dim + 3 + m.app_dim + (m.variant == TVM_VARIANT_REF ? 1 : 0);
+}
+// MLP input column layout (tensorBase.py:76-83 / REFTensoRF.py:19-25): [(-dot)] feat dir PE(feat) PE(dir)
+__host__ __device__ inline int col_feat(const TvmModel& m) { return m.variant == TVM_VARIANT_REF ? 1 : 0; }
+__host__ __device__ inline int col_dir(const TvmModel& m) { return col_feat(m) + m.app_dim; }
+__host__ __device__ inline int head_ld(const TvmModel& m) { return m.variant == TVM_VARIANT_REF ? TVM_REF_HEAD_LD : 32; }
 
 int validate_model(const TvmModel& m);
 

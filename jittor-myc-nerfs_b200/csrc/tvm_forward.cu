@@ -185,11 +185,13 @@ __global__ void __launch_bounds__(kMarchWarps * 32, 3) k_march(const FwdParams P
 // ------------------------------------------------------------------------------------------------
 // k_app_simt: appearance head, fp32 FMA path (parity mode); building blocks in tvm_app_simt.cuh
 // ------------------------------------------------------------------------------------------------
+template <int NH>
 __global__ void __launch_bounds__(kAppThreads) k_app_simt(const FwdParams P) {
   extern __shared__ __align__(16) float smem[];
   const int st = P.st;
   float* H = smem;                    // [64][st]: appearance vector, then layer-1 output
   float* X = smem + kAppTile * st;    // [64][st]: MLP input, then layer-2 output
+  float* HD = smem + 2 * kAppTile * st;   // [64][8]: REFTensoRF head outputs -> {rgb_d, tint}
   const TvmModel& m = P.m;
   const uint32_t n_ent = *P.ws.n_entries;
   const uint32_t n_tiles = (n_ent + kAppTile - 1) / kAppTile;
@@ -197,7 +199,7 @@ __global__ void __launch_bounds__(kAppThreads) k_app_simt(const FwdParams P) {
     const uint32_t tile_base = tile * kAppTile;
     app_gather_tile(P, tile_base, n_ent, H, X, st);
     __syncthreads();
-    app_basis_pe(P, H, X, st);
+    app_basis_pe<NH>(P, H, X, HD, st, tile_base, n_ent);
     __syncthreads();
     app_dense<true>(m.w1_t, m.b1, X, P.in_mlp_c, H, st);
     __syncthreads();
@@ -206,8 +208,12 @@ __global__ void __launch_bounds__(kAppThreads) k_app_simt(const FwdParams P) {
     {
       const int row = threadIdx.x & (kAppTile - 1), part = threadIdx.x >> 6;
       const uint32_t e = tile_base + row;
-      if (part < 3 && e < n_ent)
-        P.ws.ent_rgb[(size_t)e * 3 + part] = 1.0f / (1.0f + expf(-app_out_logit(m, X, st, row, part)));
+      if (part < 3 && e < n_ent) {
+        float c = 1.0f / (1.0f + expf(-app_out_logit(m, X, st, row, part)));
+        // REFTensoRF.py:232: rgb = specular_tint * clamp(rgb_s, 0) + rgb_d
+        if (NH == TVM_REF_HEAD_LD) c = HD[row * 8 + 3] * fmaxf(c, 0.0f) + HD[row * 8 + part];
+        P.ws.ent_rgb[(size_t)e * 3 + part] = c;
+      }
     }
     __syncthreads();
   }
@@ -317,8 +323,10 @@ extern "C" int tvm_forward(const TvmModel* m_host, const float* rays, int n_rays
   P.rgb_map = rgb_map;
   P.depth_map = depth_map;
   P.counters = (unsigned long long*)counters;
-  const bool has_aux = aux_host != nullptr;
-  if (has_aux) P.aux = *aux_host;
+  if (aux_host) P.aux = *aux_host;
+  // the parity instantiation (no ERT, every mask bit written) is selected by the per-sample outputs only
+  const bool has_aux = aux_host && (P.aux.bbox_bits || P.aux.valid_bits || P.aux.app_bits || P.aux.sigma ||
+                                    P.aux.weight || P.aux.rgb || P.aux.acc_map);
   const size_t nb_bytes = (size_t)n_rays * P.NB * 4;
   TVM_CHECK_CUDA(cudaMemsetAsync(P.ws.n_entries, 0, 256, stream));
   TVM_CHECK_CUDA(cudaMemsetAsync(P.ws.blk_mask, 0, nb_bytes, stream));
@@ -342,12 +350,13 @@ extern "C" int tvm_forward(const TvmModel* m_host, const float* rays, int n_rays
 
   const uint32_t mlp = flags & TVM_MLP_MASK;
   if (mlp == TVM_MLP_FP32) {
-    const size_t smem = (size_t)kAppTile * 2 * P.st * sizeof(float);
-    TVM_CHECK_CUDA(cudaFuncSetAttribute(k_app_simt, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    const size_t smem = ((size_t)kAppTile * 2 * P.st + kAppTile * 8) * sizeof(float);
+    auto kern = P.m.variant == TVM_VARIANT_REF ? k_app_simt<TVM_REF_HEAD_LD> : k_app_simt<32>;
+    TVM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     TVM_REQUIRE(smem <= 200 * 1024, "appearance tile does not fit shared memory");
     {
       ProfileScope prof(TVM_STAGE_APP, stream);
-      k_app_simt<<<device_sms() * 2, kAppThreads, smem, stream>>>(P);
+      kern<<<device_sms() * 2, kAppThreads, smem, stream>>>(P);
     }
     TVM_CHECK_CUDA(cudaGetLastError());
   } else {

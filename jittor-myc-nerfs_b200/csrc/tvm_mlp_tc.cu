@@ -20,7 +20,7 @@ namespace tvm {
 namespace tc {
 
 constexpr int kRows = 128;          // UMMA M
-constexpr int kThreads = 256;
+
 constexpr int kTmemCols = 256;      // [0,128): layer accumulators, [128,160): basis accumulator
 constexpr int kColBasis = 128;
 
@@ -103,16 +103,18 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 
 // Byte layout of the weight image built by tvm_pack_mlp_tc (copied verbatim into shared memory)
 struct Image {
-  int K0, K1;                    // padded reduction lengths of GEMM0 / GEMM1 (multiples of 16)
+  int K0, K1, NH;                // padded reduction lengths of GEMM0 / GEMM1 (multiples of 16); GEMM0 width
   uint32_t off_b0, off_b1, off_b2, off_f32, bytes;
-  __host__ __device__ Image(int n_app, int in_c) {
+  // fp32 tail: b1[128] b2[128] w3[3][128] b3[4] head_bias[48]
+  __host__ __device__ Image(int n_app, int in_c, int nh) {
     K0 = 3 * n_app;
     K1 = (in_c + 15) / 16 * 16;
+    NH = nh;
     off_b0 = 0;
-    off_b1 = off_b0 + (uint32_t)K0 * 32 * 2;
+    off_b1 = off_b0 + (uint32_t)K0 * NH * 2;
     off_b2 = off_b1 + (uint32_t)K1 * 128 * 2;
     off_f32 = off_b2 + 128u * 128 * 2;
-    bytes = off_f32 + (128 + 128 + 3 * 128 + 4) * 4;
+    bytes = off_f32 + (128 + 128 + 3 * 128 + 4 + 48) * 4;
   }
 };
 
@@ -136,6 +138,7 @@ __global__ void k_pack_tc_f32(const TvmModel m, float* __restrict__ dst) {
   else if (i < 256) dst[i] = m.b2[i - 128];
   else if (i < 640) dst[i] = m.w3[i - 256];
   else if (i < 644) dst[i] = (i - 640) < 3 ? m.b3[i - 640] : 0.0f;
+  else if (i < 692) dst[i] = m.head_bias ? m.head_bias[i - 644] : 0.0f;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -152,17 +155,33 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 __device__ __forceinline__ void mlp_group_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
-template <int CA, int APP_DIM, int FEA_PE, int VIEW_PE>
+// 16 more columns (REF heads live in basis columns 32..47)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+template <int CA, int APP_DIM, int FEA_PE, int VIEW_PE, bool REF>
 __global__ void __launch_bounds__(kThreadsV2, 1) k_app_tc(const FwdParams P) {
-  constexpr int IN_C = 2 * VIEW_PE * 3 + 2 * FEA_PE * APP_DIM + 3 + APP_DIM;
+  constexpr int NH = REF ? TVM_REF_HEAD_LD : 32;
+  constexpr int C0 = REF ? 1 : 0;                       // REF: column 0 of the MLP input is -dot (REFTensoRF.py:20)
+  constexpr int IN_C = 2 * VIEW_PE * 3 + 2 * FEA_PE * APP_DIM + 3 + APP_DIM + C0;
   constexpr int K0 = 3 * CA;
   constexpr int K1 = (IN_C + 15) / 16 * 16;
   constexpr int KA = K1 > 128 ? K1 : 128;
   static_assert(FEA_PE == 2 && VIEW_PE == 2, "the register-resident PE builder is written for 2 frequencies");
-  static_assert(K0 % 16 == 0 && APP_DIM <= 32, "unsupported shape");
+  static_assert(K0 % 16 == 0 && APP_DIM <= 32 && (!REF || APP_DIM + 8 <= NH), "unsupported shape");
 
   extern __shared__ __align__(1024) uint8_t smem[];
-  const Image img(CA, IN_C);
+  const Image img(CA, IN_C, NH);
   uint8_t* sW = smem;                                          // weight image (bf16 operands + fp32 tail)
   uint8_t* sA0 = smem + ((img.bytes + 1023) & ~1023u);         // 2 stages of the GEMM0 operand [128 x K0] bf16
   uint8_t* sA = sA0 + 2 * kRows * K0 * 2;                      // GEMM1/GEMM2 operand [128 x KA] bf16
@@ -175,6 +194,7 @@ __global__ void __launch_bounds__(kThreadsV2, 1) k_app_tc(const FwdParams P) {
   const float* sB2 = sB1 + 128;
   const float* sW3 = sB2 + 128;
   const float* sB3 = sW3 + 3 * 128;
+  const float* sHB = sB3 + 4;                                  // REF head biases [48]
 
   const TvmModel& m = P.m;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -200,8 +220,8 @@ __global__ void __launch_bounds__(kThreadsV2, 1) k_app_tc(const FwdParams P) {
   fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  constexpr uint32_t LBO_A = kRows * 16, LBO_B0 = 32 * 16, LBO_B = 128 * 16, SBO = 128;
-  constexpr uint32_t IDESC_N32 = instr_desc(128, 32), IDESC_N128 = instr_desc(128, 128);
+  constexpr uint32_t LBO_A = kRows * 16, LBO_B0 = NH * 16, LBO_B = 128 * 16, SBO = 128;
+  constexpr uint32_t IDESC_N32 = instr_desc(128, NH), IDESC_N128 = instr_desc(128, 128);
   constexpr uint32_t A0_STAGE = kRows * K0 * 2;
 
   const uint32_t n_ent = *P.ws.n_entries;
@@ -290,17 +310,42 @@ __global__ void __launch_bounds__(kThreadsV2, 1) k_app_tc(const FwdParams P) {
       mbar_wait(mma_bar, mma_phase);
       mma_phase ^= 1;
       fence_after();
+      float rgb_d0 = 0.0f, rgb_d1 = 0.0f, rgb_d2 = 0.0f, tint = 1.0f;
       {
         // ---- epi0: features -> [feat, view, sin/cos PE] as bf16 (tensorBase.py:76-83, 9-15) -------
         float x[32];
         tmem_ld32(lane_addr + kColBasis, x);
+        float ndot = 0.0f;
+        if (REF) {
+          // REFTensoRF.py:216-232: heads -> unit normal, reflected direction, -dot, diffuse colour, tint
+          float hx[16];
+          tmem_ld16(lane_addr + kColBasis + 32, hx);
+          float nx = x[APP_DIM] + sHB[APP_DIM], ny = x[APP_DIM + 1] + sHB[APP_DIM + 1], nz = x[APP_DIM + 2] + sHB[APP_DIM + 2];
+          auto head = [&](int o) { return (o < 32 ? x[o] : hx[o - 32]) + sHB[o]; };
+          rgb_d0 = head(APP_DIM + 3); rgb_d1 = head(APP_DIM + 4); rgb_d2 = head(APP_DIM + 5);
+          tint = fmaxf(head(APP_DIM + 6), 0.0f);
+          const float inv = rsqrtf(fmaxf(nx * nx + ny * ny + nz * nz, 1e-30f));
+          nx *= inv; ny *= inv; nz *= inv;
+          const float dx = -dir[0], dy = -dir[1], dz = -dir[2];
+          const float dot = dx * nx + dy * ny + dz * nz;
+          dir[0] = 2.0f * dot * nx - dx;
+          dir[1] = 2.0f * dot * ny - dy;
+          dir[2] = 2.0f * dot * nz - dz;
+          ndot = -dot;
+          if (P.aux.penalty && e < n_ent) {
+            const float pen = fmaxf(-dot, 0.0f);
+            atomicAdd(P.aux.penalty, P.ws.ent_w[e] * pen * pen);
+          }
+        }
         float s1[APP_DIM + 3], c1[APP_DIM + 3];
 #pragma unroll
         for (int o = 0; o < APP_DIM; ++o) __sincosf(x[o], &s1[o], &c1[o]);
 #pragma unroll
         for (int o = 0; o < 3; ++o) __sincosf(dir[o], &s1[APP_DIM + o], &c1[APP_DIM + o]);
-        auto column = [&](int c) -> float {
+        auto column = [&](int cc) -> float {
           constexpr int PF = APP_DIM + 3, NF = FEA_PE * APP_DIM, PV = PF + 2 * NF, NV = VIEW_PE * 3;
+          if (REF && cc == 0) return ndot;
+          const int c = cc - C0;
           if (c < APP_DIM) return x[c];
           if (c < PF) return dir[c - APP_DIM];
           if (c < PF + NF) { const int o = (c - PF) >> 1; return ((c - PF) & 1) ? 2.0f * s1[o] * c1[o] : s1[o]; }
@@ -392,9 +437,10 @@ __global__ void __launch_bounds__(kThreadsV2, 1) k_app_tc(const FwdParams P) {
         }
       }
       if (e < n_ent) {
-        P.ws.ent_rgb[(size_t)e * 3 + 0] = 1.0f / (1.0f + __expf(-o0));
-        P.ws.ent_rgb[(size_t)e * 3 + 1] = 1.0f / (1.0f + __expf(-o1));
-        P.ws.ent_rgb[(size_t)e * 3 + 2] = 1.0f / (1.0f + __expf(-o2));
+        // REF: rgb = tint * clamp(rgb_s, 0) + rgb_d (REFTensoRF.py:232); VM: tint = 1, rgb_d = 0
+        P.ws.ent_rgb[(size_t)e * 3 + 0] = tint / (1.0f + __expf(-o0)) + rgb_d0;
+        P.ws.ent_rgb[(size_t)e * 3 + 1] = tint / (1.0f + __expf(-o1)) + rgb_d1;
+        P.ws.ent_rgb[(size_t)e * 3 + 2] = tint / (1.0f + __expf(-o2)) + rgb_d2;
       }
       fence_before();
       mlp_group_sync();     // TMEM columns and the A operand are free for the next tile
@@ -416,10 +462,11 @@ int launch_app_tc(const FwdParams& P, int num_sms, cudaStream_t stream) {
   TVM_REQUIRE(tc_supported(P.m), "tensor-core appearance head supports n_app=48, app_dim=27, fea_pe=view_pe=2, "
                                  "featureC=128 (all shipped configs); use TVM_MLP_FP32 otherwise");
   TVM_REQUIRE(P.m.tc_weights != nullptr, "TvmModel.tc_weights is NULL: call tvm_pack_mlp_tc first");
-  const Image img(P.m.n_app, P.in_mlp_c);
+  const bool ref = P.m.variant == TVM_VARIANT_REF;
+  const Image img(P.m.n_app, P.in_mlp_c, head_ld(P.m));
   const int KA = max(img.K1, 128);
   const size_t smem = ((img.bytes + 1023) & ~1023u) + 2 * (size_t)kRows * img.K0 * 2 + (size_t)kRows * KA * 2 + 128 + 1024;
-  auto kern = k_app_tc<48, 27, 2, 2>;
+  auto kern = ref ? k_app_tc<48, 27, 2, 2, true> : k_app_tc<48, 27, 2, 2, false>;
   TVM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<num_sms, kThreadsV2, smem, stream>>>(P);
   TVM_CHECK_CUDA(cudaGetLastError());
@@ -431,9 +478,9 @@ int launch_app_tc(const FwdParams& P, int num_sms, cudaStream_t stream) {
 using namespace tvm;
 
 extern "C" size_t tvm_tc_weights_bytes(const TvmModel* m_host) {
-  if (m_host == nullptr) return Image(48, 150).bytes;   // probe: "is the tensor-core path built?"
+  if (m_host == nullptr) return Image(48, 150, 32).bytes;   // probe: "is the tensor-core path built?"
   if (!tc_supported(*m_host)) return 0;
-  return Image(m_host->n_app, in_mlp_c(*m_host)).bytes;
+  return Image(m_host->n_app, in_mlp_c(*m_host), head_ld(*m_host)).bytes;
 }
 
 extern "C" int tvm_pack_mlp_tc(const TvmModel* m_host, void* out, void* stream_) {
@@ -442,13 +489,14 @@ extern "C" int tvm_pack_mlp_tc(const TvmModel* m_host, void* out, void* stream_)
   TVM_REQUIRE(tc_supported(*m_host), "unsupported shape for the tensor-core appearance head");
   cudaStream_t s = (cudaStream_t)stream_;
   const int in_c = in_mlp_c(*m_host);
-  const Image img(m_host->n_app, in_c);
+  const int nh = head_ld(*m_host);
+  const Image img(m_host->n_app, in_c, nh);
   uint8_t* o = (uint8_t*)out;
   auto launch = [&](const float* w_t, int K, int K_pad, int N_real, int N, int ldw, uint32_t off) {
     const int n = K_pad * N;
     k_pack_umma_b<<<(n + 255) / 256, 256, 0, s>>>(w_t, K, K_pad, N_real, N, ldw, (__nv_bfloat16*)(o + off));
   };
-  launch(m_host->basis_t, img.K0, img.K0, m_host->app_dim, 32, kMaxAppDim, img.off_b0);
+  launch(m_host->basis_t, img.K0, img.K0, nh, nh, nh, img.off_b0);
   launch(m_host->w1_t, in_c, img.K1, 128, 128, kFeatureC, img.off_b1);
   launch(m_host->w2_t, 128, 128, 128, 128, kFeatureC, img.off_b2);
   k_pack_tc_f32<<<3, 256, 0, s>>>(*m_host, (float*)(o + img.off_f32));

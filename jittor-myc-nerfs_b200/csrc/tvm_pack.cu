@@ -50,6 +50,11 @@ int validate_model(const TvmModel& m) {
     TVM_REQUIRE(m.density_plane[i] && m.density_line[i] && m.app_plane[i] && m.app_line[i], "null grid pointer");
   }
   TVM_REQUIRE(m.basis_t && m.w1_t && m.b1 && m.w2_t && m.b2 && m.w3 && m.b3, "null MLP pointer");
+  TVM_REQUIRE(m.variant == TVM_VARIANT_VM || m.variant == TVM_VARIANT_REF, "unknown variant");
+  if (m.variant == TVM_VARIANT_REF) {
+    TVM_REQUIRE(m.head_bias != nullptr, "TVM_VARIANT_REF needs head_bias");
+    TVM_REQUIRE(m.app_dim + 8 <= TVM_REF_HEAD_LD, "app_dim + 8 heads must fit 48 columns");
+  }
   if (m.alpha_bits) {
     for (int i = 0; i < 3; ++i) TVM_REQUIRE(m.alpha_grid[i] >= 2, "alpha grid must be >= 2");
   }

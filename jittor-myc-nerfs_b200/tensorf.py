@@ -84,9 +84,9 @@ class _Linear(torch.nn.Module):
 class MLPRender_Fea(torch.nn.Module):
     """Parameter container with the reference's names (tensorBase.py:62-74): mlp.0 / mlp.2 / mlp.4."""
 
-    def __init__(self, inChanel, viewpe=6, feape=6, featureC=128):
+    def __init__(self, inChanel, viewpe=6, feape=6, featureC=128, extra_in=0):
         super().__init__()
-        self.in_mlpC = 2 * viewpe * 3 + 2 * feape * inChanel + 3 + inChanel
+        self.in_mlpC = 2 * viewpe * 3 + 2 * feape * inChanel + 3 + inChanel + extra_in
         self.viewpe, self.feape = viewpe, feape
         self.mlp = torch.nn.ModuleList([_Linear(self.in_mlpC, featureC), torch.nn.Identity(),
                                         _Linear(featureC, featureC), torch.nn.Identity(),
@@ -114,6 +114,8 @@ class _RenderFn(torch.autograd.Function):
 
 
 class TensorVMSplit(torch.nn.Module):
+    VARIANT = L.VARIANT_VM
+
     def __init__(self, aabb, gridSize, device, density_n_comp=8, appearance_n_comp=24, app_dim=27,
                  shadingMode='MLP_PE', alphaMask=None, near_far=[2.0, 20.0],
                  density_shift=-10, alphaMask_thres=0.001, distance_scale=25, rayMarch_weight_thres=0.0001,
@@ -150,7 +152,7 @@ class TensorVMSplit(torch.nn.Module):
         self.init_svd_volume(gridSize[0], device)
         self.shadingMode, self.pos_pe, self.view_pe, self.fea_pe, self.featureC = \
             shadingMode, pos_pe, view_pe, fea_pe, featureC
-        self.renderModule = MLPRender_Fea(self.app_dim, view_pe, fea_pe, featureC).to(device)
+        self.init_render_func(shadingMode, pos_pe, view_pe, fea_pe, featureC, device)
         # --- engine state -------------------------------------------------------------------
         self.mlp_mode = os.environ.get("TVM_MLP_MODE", "fp32")
         self.early_termination = True
@@ -177,6 +179,12 @@ class TensorVMSplit(torch.nn.Module):
         self.aabbDiag = torch.tensor(s["aabbDiag"])
         self.nSamples = s["nSamples"]
         self._packed_grid = None
+
+    def init_render_func(self, shadingMode, pos_pe, view_pe, fea_pe, featureC, device):
+        self.renderModule = MLPRender_Fea(self.app_dim, view_pe, fea_pe, featureC).to(device)
+
+    def head_dim(self):
+        return 32
 
     def init_svd_volume(self, res, device):
         self.density_plane, self.density_line = self.init_one_svd(self.density_n_comp, self.gridSize, 0.1, device)
@@ -248,7 +256,8 @@ class TensorVMSplit(torch.nn.Module):
             add(f"ap{k}", G[m1] * G[m0] * Ca)
         for k in range(3):
             add(f"al{k}", G[VEC_MODE[k]] * Ca)
-        add("basis_t", 3 * Ca * 32)
+        add("basis_t", 3 * Ca * self.head_dim())
+        add("head_bias", 64)
         add("w1_t", in_c * F)
         add("b1", F)
         add("w2_t", F * F)
@@ -269,6 +278,9 @@ class TensorVMSplit(torch.nn.Module):
             s.app_line[k] = at(f"al{k}")
         for name in ("basis_t", "w1_t", "b1", "w2_t", "b2", "w3", "b3"):
             setattr(s, name, at(name))
+        if cls is L.TvmModel:
+            s.variant = self.VARIANT
+            s.head_bias = at("head_bias") if self.VARIANT == L.VARIANT_REF else None
         return s
 
     def _pack(self, force=False):
@@ -297,8 +309,7 @@ class TensorVMSplit(torch.nn.Module):
                 L.check(lib.tvm_pack_grid(_ptr(p), c, p.shape[2], p.shape[3], at(f"{pref}p{k}"), st), "tvm_pack_grid")
                 L.check(lib.tvm_pack_grid(_ptr(l), c, l.shape[2], 1, at(f"{pref}l{k}"), st), "tvm_pack_grid")
         m = self.renderModule.mlp
-        L.check(lib.tvm_pack_linear(_ptr(self.basis_mat.weight.detach()), self.app_dim, 3 * Ca, 32, at("basis_t"), st),
-                "tvm_pack_linear")
+        self._pack_heads(lib, at, items, st)
         L.check(lib.tvm_pack_linear(_ptr(m[0].weight.detach()), F, in_c, F, at("w1_t"), st), "tvm_pack_linear")
         L.check(lib.tvm_pack_linear(_ptr(m[2].weight.detach()), F, F, F, at("w2_t"), st), "tvm_pack_linear")
         n = lambda name: items[name][1]
@@ -310,6 +321,11 @@ class TensorVMSplit(torch.nn.Module):
         self._packed_grid = grid_key
         self._model_struct = None
         self._tc_stale = True
+
+    def _pack_heads(self, lib, at, items, st):
+        Ca = self.app_n_comp[0]
+        L.check(lib.tvm_pack_linear(_ptr(self.basis_mat.weight.detach()), self.app_dim, 3 * Ca, 32, at("basis_t"), st),
+                "tvm_pack_linear")
 
     def _model(self):
         """The TvmModel descriptor (host POD) for the current parameters / mask."""
@@ -496,6 +512,9 @@ class TensorVMSplit(torch.nn.Module):
         aux = L.TvmAux()
         for k, v in o.items():
             setattr(aux, k, v.data_ptr() if v is not None else None)
+        if self.VARIANT == L.VARIANT_REF:
+            self.penalty.zero_()
+            aux.penalty = self.penalty.data_ptr()
         rgb_map, depth_map = self._forward_raw(rays, jitter, self._flags(white_bg), S, aux=aux)
         o.update(rgb_map=rgb_map, depth_map=depth_map)
         return o
@@ -510,10 +529,79 @@ class TensorVMSplit(torch.nn.Module):
         return out.view(xyz_locs.shape[:-1])
 
 
+class REFTensoRF(TensorVMSplit):
+    """REFTensoRF (models/REFTensoRF.py:64-256): normal / diffuse / specular-tint / rho heads on the
+    144-vector, reflected direction into MLPRender_Fea_Ref, side output `penalty` (train.py:253-257).
+    Forward only in this build (tvm_backward rejects TVM_VARIANT_REF)."""
+    VARIANT = L.VARIANT_REF
+
+    def init_render_func(self, shadingMode, pos_pe, view_pe, fea_pe, featureC, device):
+        self.renderModule = MLPRender_Fea(self.app_dim, view_pe, fea_pe, featureC, extra_in=1).to(device)   # MLPRender_Fea_Ref
+        self.penalty = torch.zeros(1, dtype=torch.float32, device=device)
+
+    def head_dim(self):
+        return L.REF_HEAD_LD
+
+    def init_svd_volume(self, res, device):
+        super().init_svd_volume(res, device)
+        k = sum(self.app_n_comp)
+        self.normal_linear = _Linear(k, 3).to(device)
+        self.diffuse_linear = _Linear(k, 3).to(device)
+        self.specular_linear = _Linear(k, 1).to(device)
+        self.rho_linear = _Linear(k, 1).to(device)
+
+    def _heads(self):
+        return [self.normal_linear, self.diffuse_linear, self.specular_linear, self.rho_linear]
+
+    def get_optparam_groups(self, lr_init_spatialxyz=0.02, lr_init_network=0.001):
+        g = super().get_optparam_groups(lr_init_spatialxyz, lr_init_network)
+        return g + [{'params': h.parameters(), 'lr': lr_init_network} for h in
+                    (self.normal_linear, self.diffuse_linear, self.rho_linear, self.specular_linear)]
+
+    def _param_list(self):
+        extra = []
+        for h in self._heads():
+            extra += [h.weight, h.bias]
+        return super()._param_list() + extra
+
+    def load_numpy_params(self, p):
+        super().load_numpy_params(p)
+        with torch.no_grad():
+            for n in ("normal", "diffuse", "specular", "rho"):
+                getattr(self, n + "_linear").weight.copy_(torch.from_numpy(p.extra[n + "_w"]))
+                getattr(self, n + "_linear").bias.copy_(torch.from_numpy(p.extra[n + "_b"]))
+
+    def _pack_heads(self, lib, at, items, st):
+        Ca = self.app_n_comp[0]
+        w = torch.cat([self.basis_mat.weight.detach()] + [h.weight.detach() for h in self._heads()], 0).contiguous()
+        self._heads_w = w          # keep alive until the pack kernel has run
+        L.check(lib.tvm_pack_linear(_ptr(w), w.shape[0], 3 * Ca, L.REF_HEAD_LD, at("basis_t"), st), "tvm_pack_linear")
+        b = torch.cat([torch.zeros(self.app_dim, device=w.device)] + [h.bias.detach() for h in self._heads()])
+        off = items["head_bias"][0]
+        self._packed[off:off + 64].zero_()
+        self._packed[off:off + b.numel()].copy_(b)
+
+    def forward(self, rays_chunk, white_bg=True, is_train=False, ndc_ray=False, N_samples=-1,
+                additional_output=False, jitter=None):
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self._param_list()):
+            raise NotImplementedError("REFTensoRF backward is not built: call under torch.no_grad()")
+        return super().forward(rays_chunk, white_bg, is_train, ndc_ray, N_samples, additional_output, jitter)
+
+    execute = forward
+
+    def _forward_raw(self, rays, jitter, flags, S, aux=None, out=None):
+        if aux is None:
+            aux = L.TvmAux()
+            self.penalty.zero_()
+            aux.penalty = self.penalty.data_ptr()
+        return super()._forward_raw(rays, jitter, flags, S, aux=aux, out=out)
+
+
 def model_from_params(p, device="cuda:0", alpha_volume=None, alpha_aabb=None, mlp_mode="fp32"):
-    """TensorVMSplit from a parameter record with the reference's shapes (e.g. oracle.fixtures.ModelParams)."""
+    """TensorVMSplit / REFTensoRF from a parameter record with the reference's shapes (e.g. oracle.fixtures.ModelParams)."""
     dev = torch.device(device)
-    m = TensorVMSplit(p.aabb, p.gridSize, dev, density_n_comp=list(p.density_n_comp),
+    cls = REFTensoRF if getattr(p, "extra", {}).get("variant") == "ref" else TensorVMSplit
+    m = cls(p.aabb, p.gridSize, dev, density_n_comp=list(p.density_n_comp),
                       appearance_n_comp=list(p.app_n_comp), app_dim=p.app_dim, near_far=list(p.near_far),
                       shadingMode="MLP_Fea", density_shift=p.density_shift, distance_scale=p.distance_scale,
                       rayMarch_weight_thres=p.rayMarch_weight_thres, view_pe=p.view_pe, fea_pe=p.fea_pe,

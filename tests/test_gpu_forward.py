@@ -164,3 +164,32 @@ def test_tensor_core_mlp_bf16(env):
     with torch.no_grad():
         rgb, _ = model(torch.from_numpy(case["rays"]).cuda())
     assert np.abs(rgb.cpu().numpy() - ref["rgb_map"]).max() <= 1e-2
+
+
+@pytest.mark.parametrize("mode,tol", [("fp32", RGB_TOL), ("bf16", 1e-2)])
+def test_reftensorf_variant(env, mode, tol):
+    """REFTensoRF (models/REFTensoRF.py): extra heads, reflected direction, tint*rgb_s + rgb_d, penalty."""
+    pkg, torch, fx, orc = env
+    from util import gpu_model
+    for regime, train in (("R2", False), ("R1", True)):
+        case = fx.make_case(64, 1024, regime, mask_res=64, train=train, variant="ref")
+        ref = orc.run_case(case)
+        model = gpu_model(pkg, case, mlp_mode=mode)
+        assert isinstance(model, pkg.REFTensoRF)
+        rays = torch.from_numpy(case["rays"]).cuda()
+        jit = None if not train else torch.from_numpy(case["jitter"]).cuda()
+        with torch.no_grad():
+            rgb, depth = model(rays, is_train=train, jitter=jit)
+        torch.cuda.synchronize()
+        err = np.abs(rgb.cpu().numpy() - ref["rgb_map"]).max()
+        pen = float(model.penalty.item())
+        print(f"REF {mode} {regime}: max|rgb-oracle|={err:.3e} penalty {pen:.5f} vs {ref['penalty']:.5f}")
+        assert err <= tol
+        assert np.abs(depth.cpu().numpy() - ref["depth_map"]).max() <= DEPTH_TOL
+        assert abs(pen - ref["penalty"]) <= (1e-4 if mode == "fp32" else 2e-2) * max(1.0, abs(ref["penalty"]))
+        if mode == "fp32":
+            out = model.forward_with_aux(rays, jitter=jit)
+            S = ref["nSamples"]
+            assert np.array_equal(pkg.unpack_bits(out["valid_bits"], S), ref["ray_valid"])
+            both = pkg.unpack_bits(out["app_bits"], S) & ref["app_mask"]
+            assert np.abs(out["rgb"].cpu().numpy()[both] - ref["rgb"][both]).max() <= 2e-5
