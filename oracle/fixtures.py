@@ -94,6 +94,20 @@ def make_model(G, seed: int = SEED_BASE, density_shift: float = -10.0,
     w3, b3 = lin(3, featureC)
     b3 = np.zeros_like(b3)  # tensorBase.py:74
     extra = {"variant": variant}
+    if variant == "npp":
+        # NerfPlusPlus.set_nerfplusplus (models/nerfplusplus.py:147-160) with configs/Scarf.txt:12-15
+        bg_freq, bg_view_freq, bg_D, radii, W = 2, 2, 3, 28.0, 128
+        pos_dim, dir_dim = 4 + 4 * bg_freq * 2, 3 + 3 * bg_view_freq * 2
+        skips = [int(bg_D / 2)]
+        base, dim = [], pos_dim
+        for i in range(bg_D):                       # MLPNet.__init__ (models/nerfplusplus.py:84-92)
+            base.append(lin(W, dim))
+            dim = W
+            if i in skips and i != bg_D - 1:
+                dim += pos_dim
+        extra.update(bg_freq=bg_freq, bg_view_freq=bg_view_freq, bg_D=bg_D, radii=radii, bg_base=base,
+                     bg_sigma=lin(1, dim), bg_remap=lin(256, dim), bg_rgb0=lin(W // 2, 256 + dir_dim),
+                     bg_rgb1=lin(3, W // 2))
     if variant == "ref":
         for name, oc in (("normal", 3), ("diffuse", 3), ("specular", 1), ("rho", 1)):
             w, b = lin(oc, 3 * ca)
@@ -164,6 +178,12 @@ def ball_alpha_volume(res, radius: float = 3.5, bbox: float = 5.0) -> np.ndarray
 def jitter(n: int, seed: int = SEED_BASE) -> np.ndarray:
     """U[0,1) per-ray march jitter (seed+2), stands in for jt.rand_like(rng[:, [0]]) tensorBase.py:353."""
     return _rng(2, seed).random(n, dtype=np.float32)
+
+
+def npp_rand(n: int, S: int, seed: int = SEED_BASE):
+    """U[0,1) draws consumed by NerfPlusPlus.perturb_samples (models/nerfplusplus.py:196-205):
+    foreground [n,S] (seed+4) and background [n,512] (seed+5); the reference jitters even at eval."""
+    return _rng(4, seed).random((n, S), dtype=np.float32), _rng(5, seed).random((n, 512), dtype=np.float32)
 
 
 def target_rgb(n: int, seed: int = SEED_BASE) -> np.ndarray:

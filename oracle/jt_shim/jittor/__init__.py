@@ -167,6 +167,15 @@ def sqr(x):
     return x * x
 
 
+def cross(a, b, dim=-1):
+    return torch.cross(a, b, dim=dim)
+
+
+def flip(x, dim=0):
+    return torch.flip(x, [dim] if isinstance(dim, int) else list(dim))
+
+
+asin = torch.asin
 multiply = torch.mul
 zeros_like = torch.zeros_like
 ones_like = torch.ones_like
@@ -245,6 +254,8 @@ def Parameter(x, requires_grad=True):
 nn.Module = Module
 nn.Linear = Linear
 nn.ReLU = torch.nn.ReLU
+nn.Sigmoid = torch.nn.Sigmoid
+nn.ModuleList = torch.nn.ModuleList
 nn.Sequential = torch.nn.Sequential
 nn.Parameter = Parameter
 nn.ParameterList = torch.nn.ParameterList

@@ -430,8 +430,132 @@ class OracleREFTensoRF(OracleTensorVMSplit):
         return valid_rgbs
 
 
+HUGE_NUMBER = 1e10     # models/nerfplusplus.py:3-4
+TINY_NUMBER = 1e-6
+
+
+class OracleNerfPlusPlus(OracleTensorVMSplit):
+    """NerfPlusPlus (models/nerfplusplus.py:143-318): sphere-bounded, always-jittered foreground sampling and a
+    512-sample inverted-sphere background MLP (Embedder :7-56, MLPNet :66-140).  The U[0,1) draws of
+    perturb_samples are injected: `fg_rand` [n,S] and `bg_rand` [n,512]."""
+
+    def __init__(self, params, *a, **k):
+        super().__init__(params, *a, **k)
+        e = params.extra
+        t = lambda x: torch.tensor(np.asarray(x), dtype=self.dtype)
+        self.radii, self.bg_freq, self.bg_view_freq, self.bg_D = e["radii"], e["bg_freq"], e["bg_view_freq"], e["bg_D"]
+        self.bg = {k_: [(t(w), t(b)) for w, b in (v if isinstance(v, list) else [v])]
+                   for k_, v in (("base", e["bg_base"]), ("sigma", e["bg_sigma"]), ("remap", e["bg_remap"]),
+                                 ("rgb0", e["bg_rgb0"]), ("rgb1", e["bg_rgb1"]))}
+        self.skips = [int(self.bg_D / 2)]
+        self.fg_rand = self.bg_rand = None
+
+    @staticmethod
+    def embed(x, n_freqs):
+        """Embedder.execute (:40-56): [x, sin(x f0), cos(x f0), sin(x f1), ...] with f = 2**linspace(0, N-1, N)."""
+        out = [x]
+        for f in (2.0 ** torch.linspace(0.0, n_freqs - 1, n_freqs)).tolist():
+            out += [torch.sin(x * f), torch.cos(x * f)]
+        return torch.cat(out, -1)
+
+    def intersect_sphere(self, ray_o, ray_d, radii):
+        """:178-194 (radii is passed squared by the caller, :241)."""
+        d1 = -torch.sum(ray_d * ray_o, dim=-1) / torch.sum(ray_d * ray_d, dim=-1)
+        p = ray_o + d1.unsqueeze(-1) * ray_d
+        ray_d_cos = 1. / torch.norm(ray_d, dim=-1)
+        p_norm_sq = torch.sum(p * p, dim=-1)
+        d2 = torch.sqrt(radii - p_norm_sq) * ray_d_cos
+        return d1 + d2
+
+    @staticmethod
+    def perturb_samples(z_vals, t_rand):
+        """:196-205."""
+        mids = .5 * (z_vals[..., 1:] + z_vals[..., :-1])
+        upper = torch.cat([mids, z_vals[..., -1:]], dim=-1)
+        lower = torch.cat([z_vals[..., 0:1], mids], dim=-1)
+        return lower + (upper - lower) * t_rand
+
+    def depth2pts_outside(self, ray_o, ray_d, depth, radii):
+        """:207-237."""
+        d1 = -torch.sum(ray_d * ray_o, dim=-1) / torch.sum(ray_d * ray_d, dim=-1)
+        p_mid = ray_o + d1.unsqueeze(-1) * ray_d
+        p_mid_norm = torch.norm(p_mid, dim=-1)
+        ray_d_cos = 1. / torch.norm(ray_d, dim=-1)
+        d2 = torch.sqrt(radii * radii - p_mid_norm * p_mid_norm) * ray_d_cos
+        p_sphere = ray_o + (d1 + d2).unsqueeze(-1) * ray_d
+        rot_axis = torch.cross(ray_o, p_sphere, dim=-1)
+        rot_axis = rot_axis / torch.norm(rot_axis, dim=-1, keepdim=True)
+        phi = torch.asin(p_mid_norm / radii)
+        theta = torch.asin(p_mid_norm * depth / (radii * radii))
+        rot_angle = (phi - theta).unsqueeze(-1)
+        p_sphere_new = p_sphere * torch.cos(rot_angle) + \
+            torch.cross(rot_axis, p_sphere, dim=-1) * torch.sin(rot_angle) + \
+            rot_axis * torch.sum(rot_axis * p_sphere, dim=-1, keepdim=True) * (1. - torch.cos(rot_angle))
+        return torch.cat((p_sphere_new, depth.unsqueeze(-1)), dim=-1)
+
+    def sample_ray(self, rays_o, rays_d, is_train=True, N_samples=-1, jitter=None):
+        """:239-269: depths linear from `near` to the sphere exit, always stratified-jittered."""
+        N_samples = N_samples if N_samples > 0 else self.nSamples
+        fg_far_depth = self.intersect_sphere(rays_o, rays_d, radii=self.radii * self.radii)
+        near, far = self.near_far
+        step = (fg_far_depth - near) / (N_samples - 1)
+        fg_depth = torch.stack([near + i * step for i in range(N_samples)], dim=-1)
+        interpx = self.perturb_samples(fg_depth, self.fg_rand.to(self.dtype))
+        rays_pts = rays_o[..., None, :] + rays_d[..., None, :] * interpx[..., None]
+        mask_outbbox = ((self.aabb[0] > rays_pts) | (rays_pts > self.aabb[1])).any(dim=-1)
+        return rays_pts, interpx, ~mask_outbbox
+
+    def bg_net(self, inp, pos_dim, dir_dim):
+        """MLPNet.execute (:115-140)."""
+        input_pts = inp[..., :pos_dim]
+        lin = lambda x, wb: x @ wb[0].T + wb[1]
+        base = torch.relu(lin(input_pts, self.bg["base"][0]))
+        for i in range(len(self.bg["base"]) - 1):
+            if i in self.skips:
+                base = torch.cat((input_pts, base), dim=-1)
+            base = torch.relu(lin(base, self.bg["base"][i + 1]))
+        sigma = torch.abs(lin(base, self.bg["sigma"][0])).squeeze(-1)
+        base_remap = lin(base, self.bg["remap"][0])
+        x = torch.relu(lin(torch.cat((base_remap, inp[..., -dir_dim:]), dim=-1), self.bg["rgb0"][0]))
+        return torch.sigmoid(lin(x, self.bg["rgb1"][0])), sigma
+
+    def execute(self, rays_chunk, white_bg=False, is_train=False, ndc_ray=False, N_samples=-1, jitter=None,
+                stages=None, fg_rand=None, bg_rand=None):
+        """:272-318.  white_bg is ignored: the foreground always renders on black (:274)."""
+        N_samples = N_samples if N_samples > 0 else self.nSamples
+        self.fg_rand, bg_rand = fg_rand, bg_rand.to(self.dtype)
+        st = {} if stages is None else stages
+        rgb_map, depth_map = super().execute(rays_chunk, False, is_train, ndc_ray, N_samples, stages=st)
+        alpha = st["alpha"]
+        bg_lambda = jt_cumprod(1. - alpha + TINY_NUMBER, -1, self.opts.cumprod)[..., -1]
+        rays_chunk = rays_chunk.to(self.dtype)
+        ray_o, ray_d = rays_chunk[:, :3], rays_chunk[:, 3:6]
+        viewdirs = ray_d / torch.norm(ray_d, dim=-1, keepdim=True)
+        n, NB = ray_d.shape[0], 512
+        bg_z_vals = torch.linspace(0., self.radii, NB).to(self.dtype).view(1, NB).expand(n, NB)
+        bg_z_vals = self.perturb_samples(bg_z_vals, bg_rand)
+        bg_pts = self.depth2pts_outside(ray_o.unsqueeze(-2).expand(n, NB, 3), ray_d.unsqueeze(-2).expand(n, NB, 3),
+                                        bg_z_vals, radii=self.radii)
+        pos = self.embed(bg_pts, self.bg_freq)
+        dirs = self.embed(viewdirs.unsqueeze(-2).expand(n, NB, 3), self.bg_view_freq)
+        inp = torch.flip(torch.cat((pos, dirs), dim=-1), [-2])
+        bg_z_vals = torch.flip(bg_z_vals, [-1])
+        bg_dists = bg_z_vals[..., :-1] - bg_z_vals[..., 1:]
+        bg_dists = torch.cat((bg_dists, HUGE_NUMBER * torch.ones_like(bg_dists[..., 0:1])), dim=-1)
+        bg_rgb, bg_sigma = self.bg_net(inp, pos.shape[-1], dirs.shape[-1])
+        bg_alpha = 1. - torch.exp(-bg_sigma * bg_dists)
+        T = jt_cumprod(1. - bg_alpha + TINY_NUMBER, -1, self.opts.cumprod)[..., :-1]
+        T = torch.cat((torch.ones_like(T[..., 0:1]), T), dim=-1)
+        bg_weights = bg_alpha * T
+        bg_rgb_map = torch.sum(bg_weights.unsqueeze(-1) * bg_rgb, dim=-2)
+        bg_lambda = torch.where(bg_lambda > 0.1, bg_lambda, torch.zeros_like(bg_lambda))
+        st.update(bg_lambda=bg_lambda.detach(), bg_rgb_map=bg_rgb_map.detach(), fg_rgb_map=rgb_map.detach())
+        return rgb_map + bg_lambda.unsqueeze(-1) * bg_rgb_map, depth_map
+
+
 def make_oracle(case, dtype=torch.float32, opts=None, requires_grad=False):
-    cls = OracleREFTensoRF if case["model"].extra.get("variant") == "ref" else OracleTensorVMSplit
+    v = case["model"].extra.get("variant")
+    cls = {"ref": OracleREFTensoRF, "npp": OracleNerfPlusPlus}.get(v, OracleTensorVMSplit)
     return cls(case["model"], case["alpha_volume"], case["alpha_aabb"], dtype=dtype, opts=opts,
                requires_grad=requires_grad)
 
@@ -464,9 +588,13 @@ def run_case(case, dtype=torch.float32, opts=None, N_samples=-1, white_bg=True, 
     penalty = 0.0
     for s in range(0, rays.shape[0], chunk):
         st = {} if want_stages else None
+        kw = {}
+        if case.get("fg_rand") is not None:
+            kw = dict(fg_rand=torch.from_numpy(case["fg_rand"][s:s + chunk]),
+                      bg_rand=torch.from_numpy(case["bg_rand"][s:s + chunk]))
         with torch.no_grad():
             rgb, depth = m(rays[s:s + chunk], white_bg=white_bg, is_train=is_train, N_samples=N_samples,
-                           jitter=None if jit is None else jit[s:s + chunk], stages=st)
+                           jitter=None if jit is None else jit[s:s + chunk], stages=st, **kw)
         outs.append((rgb, depth))
         st_all.append(st)
         penalty += float(getattr(m, "penalty", 0.0))

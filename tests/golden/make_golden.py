@@ -28,6 +28,7 @@ from oracle import fixtures as fx
 with contextlib.redirect_stdout(io.StringIO()):
     from models.tensoRF import TensorVMSplit, AlphaGridMask      # the reference, unmodified
     from models.REFTensoRF import REFTensoRF
+    from models.nerfplusplus import NerfPlusPlus
 
 CASES = {
     # name: (G, n_rays, regime, train, mask_res, white_bg, N_samples)
@@ -38,13 +39,16 @@ CASES = {
     # REFTensoRF variant (models/REFTensoRF.py): 8th field = variant
     "ref_g40_R2_eval": (40, 96, "R2", False, 40, True, -1, "ref"),
     "ref_g40_R1_train": (40, 96, "R1", True, 32, True, 139, "ref"),
+    # NerfPlusPlus variant (models/nerfplusplus.py): fg always jittered, 512-sample background MLP
+    "npp_g40_R2": (40, 48, "R2", False, 40, False, 120, "npp"),
+    "npp_g40_R1": (40, 48, "R1", False, 32, False, 97, "npp"),
 }
 
 
 def build_reference_model(case):
     p = case["model"]
     with contextlib.redirect_stdout(io.StringIO()):
-        cls = REFTensoRF if p.extra.get("variant") == "ref" else TensorVMSplit
+        cls = {"ref": REFTensoRF, "npp": NerfPlusPlus}.get(p.extra.get("variant"), TensorVMSplit)
         m = cls(jt.Var(p.aabb), list(p.gridSize), "cpu", density_n_comp=list(p.density_n_comp),
                           appearance_n_comp=list(p.app_n_comp), app_dim=p.app_dim, near_far=list(p.near_far),
                           shadingMode="MLP_Fea", alphaMask_thres=0.001, density_shift=p.density_shift,
@@ -60,6 +64,16 @@ def build_reference_model(case):
         for i, li in enumerate((0, 2, 4)):
             m.renderModule.mlp[li].weight.copy_(torch.from_numpy(p.mlp_w[i]))
             m.renderModule.mlp[li].bias.copy_(torch.from_numpy(p.mlp_b[i]))
+        if p.extra.get("variant") == "npp":
+            e = p.extra
+            m.set_nerfplusplus(bg_freq=e["bg_freq"], bg_view_freq=e["bg_view_freq"], bg_D=e["bg_D"], radii=e["radii"])
+            cp = lambda lin, wb: (lin.weight.copy_(torch.from_numpy(wb[0])), lin.bias.copy_(torch.from_numpy(wb[1])))
+            for i, wb in enumerate(e["bg_base"]):
+                cp(m.bg_net.base_layers[i][0], wb)
+            cp(m.bg_net.sigma_layers[0], e["bg_sigma"])
+            cp(m.bg_net.base_remap_layers[0], e["bg_remap"])
+            cp(m.bg_net.rgb_layers[0], e["bg_rgb0"])
+            cp(m.bg_net.rgb_layers[2], e["bg_rgb1"])
         if p.extra.get("variant") == "ref":
             for n in ("normal", "diffuse", "specular", "rho"):
                 getattr(m, n + "_linear").weight.copy_(torch.from_numpy(p.extra[n + "_w"]))
@@ -76,6 +90,19 @@ def main():
         case = fx.make_case(G, n, regime, mask_res=mask_res, train=train, variant=variant)
         m = build_reference_model(case)
         rays = jt.Var(case["rays"])
+        if variant == "npp":
+            fg_rand, bg_rand = fx.npp_rand(n, S)
+            jt._rand_queue += [fg_rand, bg_rand]
+            with torch.no_grad():
+                rgb_map, depth_map = m(rays, white_bg=white_bg, is_train=train, ndc_ray=False, N_samples=S)
+                jt._rand_queue += [fg_rand]
+                xyz, z_vals, bbox_valid = m.sample_ray(rays[:, :3], rays[:, 3:6], is_train=train, N_samples=S)
+            np.savez_compressed(os.path.join(HERE, name + ".npz"), rgb_map=rgb_map.numpy(), depth_map=depth_map.numpy(),
+                                bbox_valid=bbox_valid.numpy(), z_vals=z_vals.numpy(), nSamples=np.int64(S),
+                                stepSize=np.float32(m.stepSize.item()),
+                                args=np.array([str(G), str(n), regime, str(train), str(mask_res), str(white_bg), str(S), variant]))
+            print(name, "-> rgb mean", rgb_map.numpy().mean(0))
+            continue
         if train:
             jt._rand_queue.append(case["jitter"].reshape(-1, 1))
         with torch.no_grad():
