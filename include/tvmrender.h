@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define TVM_ABI_VERSION 5
+#define TVM_ABI_VERSION 6
 
 /* flags for tvm_forward / tvm_backward */
 #define TVM_WHITE_BG      0x1u  /* rgb_map += 1 - acc_map          (tensorBase.py:523-524) */
@@ -47,6 +47,12 @@ extern "C" {
 #define TVM_VARIANT_VM    0     /* TensorVMSplit + MLPRender_Fea          (tensoRF.py:141, tensorBase.py:62) */
 #define TVM_VARIANT_REF   1     /* REFTensoRF + MLPRender_Fea_Ref         (REFTensoRF.py:64, :5)             */
 #define TVM_REF_HEAD_LD   48    /* basis_t row length for TVM_VARIANT_REF: [basis app_dim | normal 3 | diffuse 3 | specular 1 | rho 1 | 0...] */
+
+/* sample placement along the ray */
+#define TVM_SAMPLING_UNIFORM 0  /* TensorBase.sample_ray            (tensorBase.py:340-360)   */
+#define TVM_SAMPLING_NPP     1  /* NerfPlusPlus.sample_ray          (nerfplusplus.py:239-269): depths linear from near to
+                                   the exit of the radii-sphere, ALWAYS stratified-jittered; `jitter` is then [n][S]       */
+#define TVM_NPP_BG_SAMPLES 512  /* nerfplusplus.py:285 */
 
 /* activation (tensorBase.py:444-448) */
 #define TVM_ACT_SOFTPLUS  0
@@ -98,7 +104,29 @@ typedef struct TvmModel {
   const uint32_t* alpha_bricks;
   /* optional tensor-core operand images written by tvm_pack_mlp_tc (NULL = not packed)   */
   const void* tc_weights;
+  int32_t sampling;         /* TVM_SAMPLING_*                                                            */
+  float radii;              /* TVM_SAMPLING_NPP: radius of the bounding sphere (configs/Scarf.txt:14)    */
 } TvmModel;
+
+/* NerfPlusPlus background network (nerfplusplus.py:66-140 with bg_D=3, W=128, skips=[1], bg_freq=2,
+ * bg_view_freq=2: position embedding 20, view embedding 15), fp32, [in][out] layouts.  The 128->256
+ * base_remap layer has no activation, so it is folded into the first rgb layer by tvm_bg_fold
+ * (a weights-only product): rgb_layers.0(cat(remap(x), v)) = (W_a W_r) x + W_v v + (W_a b_r + b).     */
+typedef struct TvmBgNet {
+  const float* w0_t;        /* [20][128]   base_layers.0.0.weight^T                                    */
+  const float* b0;          /* [128]                                                                    */
+  const float* w1_t;        /* [128][128]  base_layers.1.0                                              */
+  const float* b1;
+  const float* w2_t;        /* [148][128]  base_layers.2.0: rows 0..19 input_pts, 20..147 base (skip)   */
+  const float* b2;
+  const float* w_sigma;     /* [128]       sigma_layers.0.weight                                        */
+  const float* b_sigma;     /* [1]                                                                      */
+  const float* wf_t;        /* [128][64]   (rgb_layers.0.weight[:, :256] @ base_remap_layers.0.weight)^T */
+  const float* bf;          /* [64]        rgb_layers.0.weight[:, :256] @ base_remap.bias + rgb_layers.0.bias */
+  const float* wv_t;        /* [15][64]    rgb_layers.0.weight[:, 256:271]^T                            */
+  const float* w_rgb;       /* [3][64]     rgb_layers.2.weight                                          */
+  const float* b_rgb;       /* [3]                                                                      */
+} TvmBgNet;
 
 /* Optional per-sample outputs for parity tests (any member may be NULL).  Requesting aux
  * disables early ray termination so that every mask bit is produced.                         */
@@ -110,6 +138,8 @@ typedef struct TvmAux {
   float* weight;            /* [n][S]                                                                */
   float* rgb;               /* [n][S][3]        per-sample colour (0 where !app_mask)                */
   float* acc_map;           /* [n]                                                                   */
+  float* bg_lambda;         /* [n]    tvm_forward_npp: gated foreground transmittance (nerfplusplus.py:277-278,313)  */
+  float* bg_rgb_map;        /* [n][3] tvm_forward_npp: background colour before the bg_lambda factor                 */
   float* penalty;           /* [1] TVM_VARIANT_REF: += sum w[app] * relu(-d.n)^2 (REFTensoRF.py:236-238); does not
                                by itself select the parity (no-ERT) instantiation                                   */
 } TvmAux;
@@ -171,6 +201,18 @@ int tvm_forward(const TvmModel* m_host, const float* rays, int n_rays, int n_sam
                 const float* jitter, uint32_t flags, float* rgb_map, float* depth_map,
                 const TvmAux* aux_host, uint64_t* counters, void* ws, size_t ws_bytes, void* stream);
 
+/* NerfPlusPlus.execute (nerfplusplus.py:272-318): foreground = tvm_forward on black with TVM_SAMPLING_NPP
+ * (fg_rand [n][S]); bg_lambda = prod(1 - alpha + 1e-6), zeroed when <= 0.1; background = 512 inverse-depth
+ * samples per ray (bg_rand [n][512]) through the bg MLP, composited front to back;
+ * rgb_map += bg_lambda * bg_rgb_map.  Rays with bg_lambda == 0 skip the background entirely.            */
+int tvm_forward_npp(const TvmModel* m_host, const TvmBgNet* bg_host, const float* rays, int n_rays, int n_samples,
+                    const float* fg_rand, const float* bg_rand, uint32_t flags, float* rgb_map, float* depth_map,
+                    const TvmAux* aux_host, uint64_t* counters, void* ws, size_t ws_bytes, void* stream);
+/* weights-only fold of base_remap into rgb_layers.0 (see TvmBgNet)                                       */
+int tvm_bg_fold(const float* remap_w /*[256][128]*/, const float* remap_b /*[256]*/, const float* rgb0_w /*[64][271]*/,
+                const float* rgb0_b /*[64]*/, float* wf_t /*[128][64]*/, float* bf /*[64]*/, float* wv_t /*[15][64]*/,
+                void* stream);
+
 /* Backward of tvm_forward w.r.t. every parameter, given d_rgb_map [n][3] = dL/d rgb_map
  * (row a12 of SURVEY §8a; coordinates are detached, depth carries no gradient).  Must follow a
  * tvm_forward with the same arguments on the same workspace.                                     */
@@ -194,6 +236,7 @@ int tvm_mse_loss(const float* rgb_map, const float* target, int n_rays, float gr
 #define TVM_STAGE_COMPOSITE  2
 #define TVM_STAGE_BWD_APP    3
 #define TVM_STAGE_BWD_MARCH  4
+#define TVM_STAGE_BG         5
 #define TVM_STAGE_COUNT      8
 int tvm_profile_enable(int on);
 /* waits for the recorded events, adds per-stage milliseconds / launch counts into the two

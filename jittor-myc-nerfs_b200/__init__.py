@@ -2,9 +2,9 @@
 OctreeRender_trilinear_fast over libtvmrender.so (hand-written sm_100a CUDA, include/tvmrender.h)."""
 from . import _lib
 from ._lib import TvmError, LIB_PATH
-from .tensorf import TensorVMSplit, REFTensoRF, AlphaGridMask, MLPRender_Fea, derive_march_scalars, unpack_bits, model_from_params
+from .tensorf import TensorVMSplit, REFTensoRF, NerfPlusPlus, AlphaGridMask, MLPRender_Fea, derive_march_scalars, unpack_bits, model_from_params
 from .renderer import OctreeRender_trilinear_fast
 from . import dist
 
-__all__ = ["TensorVMSplit", "REFTensoRF", "AlphaGridMask", "MLPRender_Fea", "OctreeRender_trilinear_fast",
+__all__ = ["TensorVMSplit", "REFTensoRF", "NerfPlusPlus", "AlphaGridMask", "MLPRender_Fea", "OctreeRender_trilinear_fast",
            "derive_march_scalars", "unpack_bits", "model_from_params", "TvmError", "LIB_PATH"]

@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libtvmrender.so")
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 # flags (tvmrender.h)
 WHITE_BG = 0x1
@@ -21,7 +21,8 @@ MLP_BF16X3 = 0x20
 ACT_SOFTPLUS, ACT_RELU = 0, 1
 VARIANT_VM, VARIANT_REF, REF_HEAD_LD = 0, 1, 48
 CNT_M_IN, CNT_M_V, CNT_M_A, CNT_RAYS, CNT_WORDS = 0, 1, 2, 3, 8
-STAGE_NAMES = ["march", "app", "composite", "bwd_app", "bwd_march"]
+STAGE_NAMES = ["march", "app", "composite", "bwd_app", "bwd_march", "bg"]
+SAMPLING_UNIFORM, SAMPLING_NPP = 0, 1
 STAGE_COUNT = 8
 
 _f3 = C.c_float * 3
@@ -41,14 +42,19 @@ class TvmModel(C.Structure):
         ("variant", C.c_int32), ("basis_t", C.c_void_p), ("head_bias", C.c_void_p), ("w1_t", C.c_void_p), ("b1", C.c_void_p), ("w2_t", C.c_void_p),
         ("b2", C.c_void_p), ("w3", C.c_void_p), ("b3", C.c_void_p),
         ("alpha_bits", C.c_void_p), ("alpha_grid", _i3), ("alpha_aabb_min", _f3), ("alpha_inv_size", _f3),
-        ("alpha_bricks", C.c_void_p), ("tc_weights", C.c_void_p),
+        ("alpha_bricks", C.c_void_p), ("tc_weights", C.c_void_p), ("sampling", C.c_int32), ("radii", C.c_float),
     ]
 
 
 class TvmAux(C.Structure):
     _fields_ = [("bbox_bits", C.c_void_p), ("valid_bits", C.c_void_p), ("app_bits", C.c_void_p),
                 ("sigma", C.c_void_p), ("weight", C.c_void_p), ("rgb", C.c_void_p), ("acc_map", C.c_void_p),
-                ("penalty", C.c_void_p)]
+                ("bg_lambda", C.c_void_p), ("bg_rgb_map", C.c_void_p), ("penalty", C.c_void_p)]
+
+
+class TvmBgNet(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("w0_t", "b0", "w1_t", "b1", "w2_t", "b2", "w_sigma", "b_sigma", "wf_t", "bf",
+                                           "wv_t", "w_rgb", "b_rgb")]
 
 
 class TvmGrads(C.Structure):
@@ -60,7 +66,7 @@ class TvmGrads(C.Structure):
 EXPORTS = [
     "tvm_last_error", "tvm_abi_version", "tvm_device_count", "tvm_pack_grid", "tvm_unpack_grid",
     "tvm_pack_linear", "tvm_unpack_linear", "tvm_pack_alpha", "tvm_pack_alpha_bricks", "tvm_tc_weights_bytes", "tvm_pack_mlp_tc",
-    "tvm_workspace_bytes", "tvm_forward", "tvm_backward", "tvm_density_alpha", "tvm_mse_loss",
+    "tvm_workspace_bytes", "tvm_forward", "tvm_forward_npp", "tvm_bg_fold", "tvm_backward", "tvm_density_alpha", "tvm_mse_loss",
     "tvm_profile_enable", "tvm_profile_collect",
 ]
 
@@ -101,6 +107,9 @@ def load() -> C.CDLL:
     lib.tvm_workspace_bytes.argtypes = [i32, i32, C.POINTER(C.c_size_t)]
     lib.tvm_forward.argtypes = [C.POINTER(TvmModel), vp, i32, i32, vp, u32, vp, vp, C.POINTER(TvmAux), vp, vp,
                                 C.c_size_t, vp]
+    lib.tvm_forward_npp.argtypes = [C.POINTER(TvmModel), C.POINTER(TvmBgNet), vp, i32, i32, vp, vp, u32, vp, vp,
+                                    C.POINTER(TvmAux), vp, vp, C.c_size_t, vp]
+    lib.tvm_bg_fold.argtypes = [vp] * 8
     lib.tvm_backward.argtypes = [C.POINTER(TvmModel), vp, i32, i32, vp, u32, vp, vp, C.POINTER(TvmGrads), vp,
                                  C.c_size_t, vp]
     lib.tvm_density_alpha.argtypes = [C.POINTER(TvmModel), vp, i32, f32, vp, vp]

@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(kAppThreads) k_app_bwd(const BwdParams B) {
       if (ge < n_ent) {
         const uint2 en = P.ws.ent[ge];
         float u[3], dir[3];
-        entry_coords(m, P.rays, P.jitter, en.x, en.y, u, dir);
+        entry_coords(m, P.rays, P.jitter, en.x, en.y, P.S, u, dir);
         Axis ax[3];
 #pragma unroll
         for (int i = 0; i < 3; ++i) ax[i] = axis_taps(u[i], m.grid[i]);
@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(kMarchWarps * 32) k_march_bwd(const BwdParams 
   const uint32_t lt_mask = (1u << lane) - 1u;
 
   RayMarch r;
-  ray_setup(m, P.rays + 6 * (size_t)ray, P.jitter ? P.jitter[ray] : 0.0f, r);
+  ray_setup(m, P.rays + 6 * (size_t)ray, P.jitter, ray, P.S, r);
   const float4 g = reinterpret_cast<const float4*>(P.ws.bwd_scratch)[ray];
   const float gs = (P.flags & TVM_WHITE_BG) ? g.x + g.y + g.z : 0.0f;
   const float total = g.w;

@@ -44,6 +44,8 @@ struct Workspace {
   float* acc;            // [n]       acc_map
   float* rgb_sum;        // [n][3]    sum_s w * rgb (before white background / clamp)
   float* bwd_scratch;    // [n][4]    per-ray scratch of the backward pass
+  float* bg_lambda;      // [n]       NeRF++: prod(1 - alpha + 1e-6) of the foreground, 0 when <= 0.1
+  uint32_t* bg_list;     // [n]       NeRF++: rays whose background is evaluated (bg_lambda > 0.1); count at n_entries[1]
   uint32_t cap;
   int NB;
   size_t bytes;
@@ -71,6 +73,8 @@ inline Workspace carve_workspace(void* base, int n, int S) {
   w.acc = (float*)take((size_t)n * 4);
   w.rgb_sum = (float*)take((size_t)n * 12);
   w.bwd_scratch = (float*)take((size_t)n * 16);
+  w.bg_lambda = (float*)take((size_t)n * 4);
+  w.bg_list = (uint32_t*)take((size_t)n * 4);
   w.bytes = off;
   return w;
 }
@@ -88,6 +92,9 @@ struct FwdParams {
   unsigned long long* counters;
   int in_mlp_c;   // 2*view_pe*3 + 2*fea_pe*app_dim + 3 + app_dim (+1 for TVM_VARIANT_REF)
   int st;         // smem row stride (floats) of the fp32 appearance tiles
+  // NeRF++ background (tvm_forward_npp)
+  const float* bg_rand;   // [n][512]
+  TvmBgNet bg;
 };
 
 inline int in_mlp_c(const TvmModel& m) {
@@ -119,9 +126,9 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // Entry (ray, k) -> un-normalised grid coordinates, with exactly the arithmetic of the march kernel.
 __device__ __forceinline__ void entry_coords(const TvmModel& m, const float* rays, const float* jitter,
-                                             uint32_t ray, uint32_t k, float u[3], float dir[3]) {
+                                             uint32_t ray, uint32_t k, int S, float u[3], float dir[3]) {
   RayMarch r;
-  ray_setup(m, rays + 6 * (size_t)ray, jitter ? jitter[ray] : 0.0f, r);
+  ray_setup(m, rays + 6 * (size_t)ray, jitter, (int)ray, S, r);
   float z = sample_z(m, r, (int)k);
   float p[3];
   sample_point(m, r, z, p);

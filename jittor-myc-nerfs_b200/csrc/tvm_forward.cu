@@ -31,12 +31,16 @@ __global__ void __launch_bounds__(kMarchWarps * 32, 3) k_march(const FwdParams P
   const uint32_t lt_mask = (1u << lane) - 1u;
 
   RayMarch r;
-  ray_setup(m, P.rays + 6 * (size_t)ray, P.jitter ? P.jitter[ray] : 0.0f, r);
+  ray_setup(m, P.rays + 6 * (size_t)ray, P.jitter, ray, P.S, r);
 
   const int C = m.n_density;
   const int S = P.S;
   const bool ert = !AUX && !(P.flags & TVM_NO_ERT);
   float T = 1.0f, acc = 0.0f, dep = 0.0f;
+  // NeRF++: bg_lambda = prod_k (1 - alpha_k + 1e-6) over ALL S samples (nerfplusplus.py:277-278)
+  const bool npp = m.sampling == TVM_SAMPLING_NPP;
+  float Tbg = 1.0f;
+  int n_proc = 0;
   bool seen = false;
   uint32_t c_in = 0, c_v = 0, c_a = 0;
 
@@ -135,6 +139,13 @@ __global__ void __launch_bounds__(kMarchWarps * 32, 3) k_march(const FwdParams P
     if (lane == 0) excl = 1.0f;
     const float w = alpha * (T * excl);
     T = T * __shfl_sync(0xffffffffu, pref, 31);
+    if (npp) {
+      float v6 = (k < S) ? TVM_ADD(TVM_SUB(1.0f, alpha), 1e-6f) : 1.0f;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v6 *= __shfl_xor_sync(0xffffffffu, v6, o);
+      Tbg *= v6;
+      n_proc += min(32, S - b * 32);
+    }
     acc += w;
     dep += w * z;
 
@@ -170,6 +181,14 @@ __global__ void __launch_bounds__(kMarchWarps * 32, 3) k_march(const FwdParams P
   dep = warp_sum(dep);
   if (lane == 0) {
     P.ws.acc[ray] = acc;
+    if (npp) {
+      // samples of blocks that were never visited have alpha = 0: each contributes fl(1 + 1e-6)
+      float lam = Tbg * powf(TVM_ADD(1.0f, 1e-6f), (float)(S - n_proc));
+      lam = lam > 0.1f ? lam : 0.0f;                                   // nerfplusplus.py:313
+      P.ws.bg_lambda[ray] = lam;
+      if (lam > 0.0f) P.ws.bg_list[atomicAdd(P.ws.n_entries + 1, 1u)] = (uint32_t)ray;
+      if (P.aux.bg_lambda) P.aux.bg_lambda[ray] = lam;
+    }
     // depth_map = sum(w*z) + (1-acc) * rays_chunk[..., -1]  -- column 5 (d_z), reference quirk (:531)
     P.depth_map[ray] = dep + (1.0f - acc) * r.d[2];
     if (AUX && P.aux.acc_map) P.aux.acc_map[ray] = acc;
@@ -287,6 +306,8 @@ int fill_fwd_params(FwdParams& P, const TvmModel* m, const float* rays, int n, i
   P.st = app_tile_stride(m->n_app, P.in_mlp_c);
   P.counters = nullptr;
   P.aux = TvmAux{};
+  P.bg_rand = nullptr;
+  P.bg = TvmBgNet{};
   return 0;
 }
 
@@ -312,14 +333,26 @@ extern "C" int tvm_workspace_bytes(int n_rays, int n_samples, size_t* out_bytes)
   return 0;
 }
 
-extern "C" int tvm_forward(const TvmModel* m_host, const float* rays, int n_rays, int n_samples,
-                           const float* jitter, uint32_t flags, float* rgb_map, float* depth_map,
-                           const TvmAux* aux_host, uint64_t* counters, void* ws, size_t ws_bytes,
-                           void* stream_) {
+namespace tvm {
+int launch_bg(const FwdParams& P, int num_sms, cudaStream_t stream);   // tvm_bg.cu
+}
+
+// shared body of tvm_forward (bg_host == NULL) and tvm_forward_npp
+static int forward_impl(const TvmModel* m_host, const TvmBgNet* bg_host, const float* rays, int n_rays, int n_samples,
+                        const float* jitter, const float* bg_rand, uint32_t flags, float* rgb_map, float* depth_map,
+                        const TvmAux* aux_host, uint64_t* counters, void* ws, size_t ws_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   FwdParams P;
   if (int rc = fill_fwd_params(P, m_host, rays, n_rays, n_samples, jitter, flags, ws, ws_bytes)) return rc;
   TVM_REQUIRE(rgb_map && depth_map, "null output");
+  TVM_REQUIRE((m_host->sampling == TVM_SAMPLING_NPP) == (bg_host != nullptr),
+              "TVM_SAMPLING_NPP models go through tvm_forward_npp, all others through tvm_forward");
+  P.bg_rand = bg_rand;
+  if (bg_host) {
+    TVM_REQUIRE(jitter && bg_rand && n_samples >= 2, "tvm_forward_npp needs fg_rand [n][S], bg_rand [n][512], S >= 2");
+    P.bg = *bg_host;
+    P.flags = flags & ~TVM_WHITE_BG;          // the foreground always renders on black (nerfplusplus.py:274)
+  }
   P.rgb_map = rgb_map;
   P.depth_map = depth_map;
   P.counters = (unsigned long long*)counters;
@@ -368,5 +401,26 @@ extern "C" int tvm_forward(const TvmModel* m_host, const float* rays, int n_rays
     k_composite<<<(n_rays + 7) / 8, 256, 0, stream>>>(P);
   }
   TVM_CHECK_CUDA(cudaGetLastError());
+  if (bg_host) {
+    ProfileScope prof(TVM_STAGE_BG, stream);
+    if (int rc = launch_bg(P, device_sms(), stream)) return rc;
+  }
   return 0;
+}
+
+extern "C" int tvm_forward(const TvmModel* m_host, const float* rays, int n_rays, int n_samples,
+                           const float* jitter, uint32_t flags, float* rgb_map, float* depth_map,
+                           const TvmAux* aux_host, uint64_t* counters, void* ws, size_t ws_bytes,
+                           void* stream_) {
+  return forward_impl(m_host, nullptr, rays, n_rays, n_samples, jitter, nullptr, flags, rgb_map, depth_map, aux_host,
+                      counters, ws, ws_bytes, stream_);
+}
+
+extern "C" int tvm_forward_npp(const TvmModel* m_host, const TvmBgNet* bg_host, const float* rays, int n_rays,
+                               int n_samples, const float* fg_rand, const float* bg_rand, uint32_t flags,
+                               float* rgb_map, float* depth_map, const TvmAux* aux_host, uint64_t* counters, void* ws,
+                               size_t ws_bytes, void* stream_) {
+  TVM_REQUIRE(bg_host != nullptr, "null TvmBgNet");
+  return forward_impl(m_host, bg_host, rays, n_rays, n_samples, fg_rand, bg_rand, flags, rgb_map, depth_map, aux_host,
+                      counters, ws, ws_bytes, stream_);
 }

@@ -39,17 +39,49 @@ TVM_HD int vecax(int k) { return 2 - k; }
 
 struct RayMarch {
   float o[3], d[3];
-  float t_min;   // entry distance clamped to [near, far]      (tensorBase.py:345-348)
+  float t_min;   // entry distance clamped to [near, far]      (tensorBase.py:345-348); NeRF++: near
   float jit;     // per-ray jitter (0 when !is_train)           (tensorBase.py:351-353)
+  // TVM_SAMPLING_NPP (NerfPlusPlus.sample_ray, nerfplusplus.py:239-269)
+  float step;          // (far - near) / (S - 1), far = exit of the radii-sphere
+  const float* rnd;    // this ray's S draws of perturb_samples' U[0,1)
+  int S;
 };
 
-// tensorBase.py:344-348
-TVM_HD void ray_setup(const TvmModel& m, const float* ray6, float jit, RayMarch& r) {
-  float t = -INFINITY;
+// 3-term dot product in the reduction order of a sum over the last axis: (a0 b0 + a1 b1) + a2 b2
+TVM_HD float dot3_seq(const float a[3], const float b[3]) {
+  return TVM_ADD(TVM_ADD(TVM_MUL(a[0], b[0]), TVM_MUL(a[1], b[1])), TVM_MUL(a[2], b[2]));
+}
+
+// tensorBase.py:344-348 (uniform marching) / nerfplusplus.py:178-194,239-247 (sphere-bounded)
+// `jitter` is [n] (uniform sampling, NULL = eval) or [n][S] (TVM_SAMPLING_NPP, required).
+TVM_HD void ray_setup(const TvmModel& m, const float* ray6, const float* jitter, int ray, int S, RayMarch& r) {
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     r.o[i] = ray6[i];
     r.d[i] = ray6[3 + i];
+  }
+  r.S = S;
+  r.rnd = nullptr;
+  r.step = 0.0f;
+  if (m.sampling == TVM_SAMPLING_NPP) {
+    // intersect_sphere(rays_o, rays_d, radii^2): d1 = -sum(d*o)/sum(d*d); p = o + d1 d; d2 = sqrt(R^2 - |p|^2) / |d|
+    const float dd = dot3_seq(r.d, r.d);
+    const float d1 = TVM_DIV(-dot3_seq(r.d, r.o), dd);
+    float p[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) p[i] = TVM_ADD(r.o[i], TVM_MUL(d1, r.d[i]));
+    const float cosd = TVM_DIV(1.0f, sqrtf(dd));
+    const float d2 = TVM_MUL(sqrtf(TVM_SUB(TVM_MUL(m.radii, m.radii), dot3_seq(p, p))), cosd);
+    const float far = TVM_ADD(d1, d2);
+    r.t_min = m.near_;
+    r.step = TVM_DIV(TVM_SUB(far, m.near_), (float)(S - 1));
+    r.jit = 0.0f;
+    r.rnd = jitter + (size_t)ray * S;
+    return;
+  }
+  float t = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
     float vec = (r.d[i] == 0.0f) ? 1e-6f : r.d[i];
     float ra = TVM_DIV(TVM_SUB(m.aabb[3 + i], r.o[i]), vec);
     float rb = TVM_DIV(TVM_SUB(m.aabb[i], r.o[i]), vec);
@@ -58,11 +90,21 @@ TVM_HD void ray_setup(const TvmModel& m, const float* ray6, float jit, RayMarch&
   }
   t = fminf(fmaxf(t, m.near_), m.far_);
   r.t_min = t;
-  r.jit = jit;
+  r.jit = jitter ? jitter[ray] : 0.0f;
 }
 
 // z_k = t_min + stepSize * (k + jitter)                        (tensorBase.py:350-355)
+// NeRF++: fg_i = near + i*step; stratum [lower_i, upper_i] from the mid points; z_i = lower + (upper-lower) t_i
+//                                                              (nerfplusplus.py:196-205, 248-251)
 TVM_HD float sample_z(const TvmModel& m, const RayMarch& r, int k) {
+  if (m.sampling == TVM_SAMPLING_NPP) {
+    const int kc = min(max(k, 0), r.S - 1);      // callers probe k = S for the last dist, which is unused
+    const float f0 = TVM_ADD(r.t_min, TVM_MUL((float)kc, r.step));
+    float lower = f0, upper = f0;
+    if (kc > 0) lower = TVM_MUL(0.5f, TVM_ADD(f0, TVM_ADD(r.t_min, TVM_MUL((float)(kc - 1), r.step))));
+    if (kc < r.S - 1) upper = TVM_MUL(0.5f, TVM_ADD(TVM_ADD(r.t_min, TVM_MUL((float)(kc + 1), r.step)), f0));
+    return TVM_ADD(lower, TVM_MUL(TVM_SUB(upper, lower), r.rnd[kc]));
+  }
   float rng = TVM_ADD((float)k, r.jit);
   return TVM_ADD(r.t_min, TVM_MUL(m.step_size, rng));
 }

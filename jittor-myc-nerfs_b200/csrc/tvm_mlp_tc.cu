@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(kThreadsV2, 1) k_app_tc(const FwdParams P) {
         if (e < n_ent) {
           const uint2 en = P.ws.ent[e];
           float u[3], dir[3];
-          entry_coords(m, P.rays, P.jitter, en.x, en.y, u, dir);
+          entry_coords(m, P.rays, P.jitter, en.x, en.y, P.S, u, dir);
           Axis ax[3];
 #pragma unroll
           for (int i = 0; i < 3; ++i) ax[i] = axis_taps(u[i], m.grid[i]);

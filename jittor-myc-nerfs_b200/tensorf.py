@@ -372,8 +372,14 @@ class TensorVMSplit(torch.nn.Module):
             L.check(lib.tvm_pack_mlp_tc(C.byref(s), _ptr(self._tc), _stream_ptr()), "tvm_pack_mlp_tc")
             s.tc_weights = self._tc.data_ptr()
             self._tc_stale = False
+        s.sampling, s.radii = L.SAMPLING_UNIFORM, 0.0
+        self._finish_model(s)
         self._model_struct, self._model_mask_key = s, mask_key
         return s
+
+    def _finish_model(self, s):
+        """Hook for variants to fill further TvmModel fields."""
+        pass
 
     # ---- workspace ------------------------------------------------------------------------------
     def workspace_bytes(self, n, S):
@@ -597,10 +603,155 @@ class REFTensoRF(TensorVMSplit):
         return super()._forward_raw(rays, jitter, flags, S, aux=aux, out=out)
 
 
+class _Seq(torch.nn.ModuleList):
+    """Positional container so that parameter names match the reference's nn.Sequential indices."""
+
+
+class _BgNet(torch.nn.Module):
+    """Parameter container mirroring MLPNet (models/nerfplusplus.py:66-113) for D=3, W=128, skips=[1]."""
+
+    def __init__(self, pos_dim, dir_dim, D=3, W=128):
+        super().__init__()
+        skips = [int(D / 2)]
+        layers, dim = [], pos_dim
+        for i in range(D):
+            layers.append(_Seq([_Linear(dim, W), torch.nn.Identity()]))
+            dim = W
+            if i in skips and i != D - 1:
+                dim += pos_dim
+        self.base_layers = torch.nn.ModuleList(layers)
+        self.sigma_layers = _Seq([_Linear(dim, 1)])
+        self.base_remap_layers = _Seq([_Linear(dim, 256)])
+        self.rgb_layers = _Seq([_Linear(256 + dir_dim, W // 2), torch.nn.Identity(), _Linear(W // 2, 3), torch.nn.Identity()])
+
+
+class NerfPlusPlus(TensorVMSplit):
+    """NerfPlusPlus (models/nerfplusplus.py:143-318): sphere-bounded always-jittered foreground sampling plus a
+    512-sample inverted-sphere background MLP.  Forward only (tvm_forward_npp); the U[0,1) draws of
+    perturb_samples come from torch.rand on the device unless `fg_rand` / `bg_rand` are injected."""
+
+    def set_nerfplusplus(self, bg_freq=4, bg_view_freq=2, bg_D=4, radii=20):
+        if (bg_freq, bg_view_freq, bg_D) != (2, 2, 3):
+            raise NotImplementedError("the background kernels are built for bg_freq=2, bg_view_freq=2, bg_D=3 "
+                                      "(configs/Scarf.txt:12-15)")
+        self.bg_freq, self.bg_view_freq, self.bg_D, self.radii = bg_freq, bg_view_freq, bg_D, radii
+        self.bg_net = _BgNet(4 + 4 * bg_freq * 2, 3 + 3 * bg_view_freq * 2, bg_D).to(self.device)
+        self._bg_packed = None
+        self._bg_versions = None
+        self._model_struct = None
+
+    def get_optparam_groups(self, lr_init_spatialxyz=0.02, lr_init_network=0.001):
+        return super().get_optparam_groups(lr_init_spatialxyz, lr_init_network) + \
+            [{'params': self.bg_net.parameters(), 'lr': lr_init_network}]
+
+    def load_numpy_params(self, p):
+        super().load_numpy_params(p)
+        e = p.extra
+        if not hasattr(self, "bg_net"):
+            self.set_nerfplusplus(e["bg_freq"], e["bg_view_freq"], e["bg_D"], e["radii"])
+        with torch.no_grad():
+            def cp(lin, wb):
+                lin.weight.copy_(torch.from_numpy(wb[0]))
+                lin.bias.copy_(torch.from_numpy(wb[1]))
+            for i, wb in enumerate(e["bg_base"]):
+                cp(self.bg_net.base_layers[i][0], wb)
+            cp(self.bg_net.sigma_layers[0], e["bg_sigma"])
+            cp(self.bg_net.base_remap_layers[0], e["bg_remap"])
+            cp(self.bg_net.rgb_layers[0], e["bg_rgb0"])
+            cp(self.bg_net.rgb_layers[2], e["bg_rgb1"])
+
+    def _finish_model(self, s):
+        s.sampling, s.radii = L.SAMPLING_NPP, float(self.radii)
+
+    def _bg_struct(self):
+        """TvmBgNet over a packed fp32 buffer; re-packed (and re-folded) when a bg parameter changed."""
+        lib = L.load()
+        n = self.bg_net
+        params = list(n.parameters())
+        versions = tuple((p.data_ptr(), p._version) for p in params)
+        sizes = dict(w0_t=20 * 128, b0=128, w1_t=128 * 128, b1=128, w2_t=148 * 128, b2=128, w_sigma=128, b_sigma=64,
+                     wf_t=128 * 64, bf=64, wv_t=15 * 64, w_rgb=3 * 64, b_rgb=64)
+        if self._bg_packed is None or versions != self._bg_versions:
+            offs, off = {}, 0
+            for k, v in sizes.items():
+                offs[k] = off
+                off += (v + 63) // 64 * 64
+            if self._bg_packed is None:
+                self._bg_packed = torch.zeros(off, dtype=torch.float32, device=self.device)
+            buf, st = self._bg_packed, _stream_ptr()
+            at = lambda k: C.c_void_p(buf.data_ptr() + 4 * offs[k])
+            for i, (wk, bk) in enumerate((("w0_t", "b0"), ("w1_t", "b1"), ("w2_t", "b2"))):
+                lin = n.base_layers[i][0]
+                w = lin.weight.detach()
+                L.check(lib.tvm_pack_linear(_ptr(w), w.shape[0], w.shape[1], w.shape[0], at(wk), st), "tvm_pack_linear")
+                buf[offs[bk]:offs[bk] + 128].copy_(lin.bias.detach())
+            buf[offs["w_sigma"]:offs["w_sigma"] + 128].copy_(n.sigma_layers[0].weight.detach().reshape(-1))
+            buf[offs["b_sigma"]:offs["b_sigma"] + 1].copy_(n.sigma_layers[0].bias.detach())
+            r, g0, g1 = n.base_remap_layers[0], n.rgb_layers[0], n.rgb_layers[2]
+            L.check(lib.tvm_bg_fold(_ptr(r.weight.detach()), _ptr(r.bias.detach()), _ptr(g0.weight.detach()),
+                                    _ptr(g0.bias.detach()), at("wf_t"), at("bf"), at("wv_t"), st), "tvm_bg_fold")
+            buf[offs["w_rgb"]:offs["w_rgb"] + 192].copy_(g1.weight.detach().reshape(-1))
+            buf[offs["b_rgb"]:offs["b_rgb"] + 3].copy_(g1.bias.detach())
+            s = L.TvmBgNet()
+            for k in sizes:
+                setattr(s, k, buf.data_ptr() + 4 * offs[k])
+            self._bg_struct_c, self._bg_versions = s, versions
+        return self._bg_struct_c
+
+    def forward(self, rays_chunk, white_bg=False, is_train=False, ndc_ray=False, N_samples=-1,
+                additional_output=True, fg_rand=None, bg_rand=None, aux=None):
+        if ndc_ray:
+            raise NotImplementedError("ndc_ray sampling is outside the hot path")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError("NerfPlusPlus backward is not built: call under torch.no_grad()")
+        lib = L.load()
+        S = int(N_samples) if N_samples > 0 else self.nSamples
+        rays = rays_chunk.contiguous()
+        n, nmax = rays.shape[0], self.max_rays_per_launch(S)
+        dev = rays.device
+        if fg_rand is None:
+            fg_rand = torch.rand((n, S), dtype=torch.float32, device=dev)       # perturb_samples, :204
+        if bg_rand is None:
+            bg_rand = torch.rand((n, 512), dtype=torch.float32, device=dev)
+        model, bg = self._model(), self._bg_struct()
+        rgb = torch.empty((n, 3), dtype=torch.float32, device=dev)
+        depth = torch.empty((n,), dtype=torch.float32, device=dev)
+        flags = self._flags(False)
+        for s in range(0, n, nmax):
+            e = min(n, s + nmax)
+            ws = self._workspace(e - s, S)
+            L.check(lib.tvm_forward_npp(C.byref(model), C.byref(bg), _ptr(rays[s:e]), e - s, S, _ptr(fg_rand[s:e]),
+                                        _ptr(bg_rand[s:e]), flags, _ptr(rgb[s:e]), _ptr(depth[s:e]),
+                                        C.byref(aux) if aux is not None else None,
+                                        _ptr(self.counters) if self.collect_counters else None, _ptr(ws), ws.numel(),
+                                        _stream_ptr()), "tvm_forward_npp")
+        return rgb, depth
+
+    execute = forward
+
+    def forward_with_aux(self, rays, N_samples=-1, fg_rand=None, bg_rand=None, **_):
+        """Parity instrumentation: per-sample masks of the foreground plus bg_lambda / bg_rgb_map."""
+        S = int(N_samples) if N_samples > 0 else self.nSamples
+        n, NB, dev = rays.shape[0], (S + 31) // 32, rays.device
+        bits = lambda: torch.empty((n, NB), dtype=torch.int32, device=dev)
+        o = dict(bbox_bits=bits(), valid_bits=bits(), app_bits=bits(),
+                 sigma=torch.empty((n, S), dtype=torch.float32, device=dev),
+                 weight=torch.empty((n, S), dtype=torch.float32, device=dev),
+                 bg_lambda=torch.zeros(n, dtype=torch.float32, device=dev),
+                 bg_rgb_map=torch.zeros((n, 3), dtype=torch.float32, device=dev))
+        aux = L.TvmAux()
+        for k, v in o.items():
+            setattr(aux, k, v.data_ptr())
+        with torch.no_grad():
+            rgb_map, depth_map = self.forward(rays, N_samples=S, fg_rand=fg_rand, bg_rand=bg_rand, aux=aux)
+        o.update(rgb_map=rgb_map, depth_map=depth_map)
+        return o
+
+
 def model_from_params(p, device="cuda:0", alpha_volume=None, alpha_aabb=None, mlp_mode="fp32"):
     """TensorVMSplit / REFTensoRF from a parameter record with the reference's shapes (e.g. oracle.fixtures.ModelParams)."""
     dev = torch.device(device)
-    cls = REFTensoRF if getattr(p, "extra", {}).get("variant") == "ref" else TensorVMSplit
+    cls = {"ref": REFTensoRF, "npp": NerfPlusPlus}.get(getattr(p, "extra", {}).get("variant"), TensorVMSplit)
     m = cls(p.aabb, p.gridSize, dev, density_n_comp=list(p.density_n_comp),
                       appearance_n_comp=list(p.app_n_comp), app_dim=p.app_dim, near_far=list(p.near_far),
                       shadingMode="MLP_Fea", density_shift=p.density_shift, distance_scale=p.distance_scale,

@@ -89,6 +89,10 @@ def emul_forward(pkg, case, S=-1, white_bg=True):
     rays = np.ascontiguousarray(case["rays"], np.float32)
     n = rays.shape[0]
     jit = case.get("jitter")
+    if case.get("fg_rand") is not None:            # NerfPlusPlus sampling: `jitter` is the [n][S] draw array
+        m.sampling, m.radii = pkg._lib.SAMPLING_NPP, float(case["model"].extra["radii"])
+        jit = np.ascontiguousarray(case["fg_rand"], np.float32)
+        assert jit.shape == (n, S)
     u8 = lambda: np.zeros((n, S), np.uint8)
     f = lambda *sh: np.zeros(sh, np.float32)
     out = dict(bbox=u8(), valid=u8(), app=u8(), sigma=f(n, S), weight=f(n, S), rgb=f(n, S, 3),

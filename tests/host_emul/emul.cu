@@ -19,7 +19,7 @@ extern "C" int emul_forward(const TvmModel* mp, const float* rays, int n, int S,
   std::vector<float> h(K), x(in_c), y1(F), y2(F);
   for (int ray = 0; ray < n; ++ray) {
     RayMarch r;
-    ray_setup(m, rays + 6 * (size_t)ray, jitter ? jitter[ray] : 0.0f, r);
+    ray_setup(m, rays + 6 * (size_t)ray, jitter, ray, S, r);
     float T = 1.0f, acc = 0.0f, dep = 0.0f, c0 = 0, c1 = 0, c2 = 0;
     for (int k = 0; k < S; ++k) {
       const size_t idx = (size_t)ray * S + k;
@@ -122,7 +122,7 @@ extern "C" int emul_block_maybe(const TvmModel* mp, const float* rays, int n, in
   const int NB = (S + 31) / 32;
   for (int ray = 0; ray < n; ++ray) {
     RayMarch r;
-    ray_setup(m, rays + 6 * (size_t)ray, jitter ? jitter[ray] : 0.0f, r);
+    ray_setup(m, rays + 6 * (size_t)ray, jitter, ray, S, r);
     for (int b = 0; b < NB; ++b) visit[(size_t)ray * NB + b] = block_maybe(m, r, b, S);
   }
   return 0;

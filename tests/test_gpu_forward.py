@@ -193,3 +193,36 @@ def test_reftensorf_variant(env, mode, tol):
             assert np.array_equal(pkg.unpack_bits(out["valid_bits"], S), ref["ray_valid"])
             both = pkg.unpack_bits(out["app_bits"], S) & ref["app_mask"]
             assert np.abs(out["rgb"].cpu().numpy()[both] - ref["rgb"][both]).max() <= 2e-5
+
+
+def test_nerfplusplus_variant(env):
+    """NerfPlusPlus (models/nerfplusplus.py): sphere-bounded jittered fg sampling, bg_lambda gate, 512-sample bg MLP."""
+    pkg, torch, fx, orc = env
+    from util import gpu_model
+    for regime, S, G in (("R2", 150, 64), ("R1", 217, 64), ("R0", 100, 32)):
+        n = 512
+        case = fx.make_case(G, n, regime, mask_res=G, variant="npp")
+        case["fg_rand"], case["bg_rand"] = fx.npp_rand(n, S)
+        ref = orc.run_case(case, N_samples=S, white_bg=False)
+        model = gpu_model(pkg, case)
+        assert isinstance(model, pkg.NerfPlusPlus)
+        rays = torch.from_numpy(case["rays"]).cuda()
+        fg, bg = torch.from_numpy(case["fg_rand"]).cuda(), torch.from_numpy(case["bg_rand"]).cuda()
+        out = model.forward_with_aux(rays, N_samples=S, fg_rand=fg, bg_rand=bg)
+        torch.cuda.synchronize()
+        assert np.array_equal(pkg.unpack_bits(out["bbox_bits"], S), ref["bbox_valid"])
+        assert np.array_equal(pkg.unpack_bits(out["valid_bits"], S), ref["ray_valid"])
+        lam = out["bg_lambda"].cpu().numpy()
+        gate = (lam > 0) != (ref["bg_lambda"] > 0)
+        assert gate.sum() <= 1                                     # 0.1 threshold is a float compare
+        assert np.abs(lam - ref["bg_lambda"])[~gate].max() <= 1e-5
+        act = (lam > 0) & ~gate
+        assert np.abs(out["bg_rgb_map"].cpu().numpy()[act] - ref["bg_rgb_map"][act]).max(initial=0) <= RGB_TOL
+        err = np.abs(out["rgb_map"].cpu().numpy() - ref["rgb_map"])[~gate].max()
+        print(f"NeRF++ {regime}: active bg rays {int(act.sum())}/{n}, max|rgb-oracle|={err:.3e}")
+        assert err <= RGB_TOL
+        assert np.abs(out["depth_map"].cpu().numpy() - ref["depth_map"]).max() <= DEPTH_TOL
+        # production path (ERT on, device-side random draws replaced by the injected ones)
+        with torch.no_grad():
+            rgb, _ = model(rays, N_samples=S, fg_rand=fg, bg_rand=bg)
+        assert np.abs(rgb.cpu().numpy() - ref["rgb_map"])[~gate].max() <= RGB_TOL

@@ -62,3 +62,18 @@ def test_coarse_block_skip_is_conservative(built_lib, regime, train, G, mres):
     assert not (has_valid & ~visit).any(), "a block holding a valid sample was skipped"
     if mres == 64:
         assert visit.sum() < 0.6 * visit.size       # and the test does skip most empty blocks
+
+
+def test_emulated_nerfpp_sampling(built_lib):
+    """NerfPlusPlus.sample_ray (sphere-bounded, stratified) in the kernels' arithmetic: masks bit-exact."""
+    from oracle import fixtures as fx, tensorf_oracle as orc
+    import emul_util as eu
+    S = 75
+    case = fx.make_case(32, 200, "R2", mask_res=32, variant="npp")
+    case["fg_rand"], case["bg_rand"] = fx.npp_rand(200, S)
+    e = eu.emul_forward(built_lib, case, S=S, white_bg=False)
+    r = orc.run_case(case, N_samples=S, white_bg=False)
+    assert np.array_equal(e["bbox"].astype(bool), r["bbox_valid"])
+    assert np.array_equal(e["valid"].astype(bool), r["ray_valid"])
+    assert np.abs(e["weight"] - r["weight"]).max() <= 1e-6
+    assert np.abs(e["rgb_map"] - r["fg_rgb_map"]).max() <= 1e-5
