@@ -12,94 +12,11 @@
 // so that one thread (= one row) writes whole 16-byte chunks, conflict-free.  Accumulators are read
 // back with tcgen05.ld (32x32b: thread t of warp w owns TMEM lane 32*(w%4)+t = tile row).
 // One thread issues the MMAs; completion is signalled through tcgen05.commit -> mbarrier.
-#include <cuda_bf16.h>
-#include "tvm_common.cuh"
+#include "tvm_tc.cuh"
 
 namespace tvm {
 
 namespace tc {
-
-constexpr int kRows = 128;          // UMMA M
-
-constexpr int kTmemCols = 256;      // [0,128): layer accumulators, [128,160): basis accumulator
-constexpr int kColBasis = 128;
-
-// ---- PTX wrappers ----------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t a = smem_u32(bar);
-  uint32_t done = 0;
-  for (uint32_t spin = 0; !done; ++spin) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.b32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(a), "r"(parity)
-        : "memory");
-    if (spin > (1u << 24)) __trap();   // a lost tcgen05.commit must fail the launch, not hang the GPU
-  }
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols));
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols));
-}
-__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-// D[tmem] (+)= A[smem] * B[smem]^T, kind::f16 (bf16 inputs, fp32 accumulate), M=128, K=16
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-// 32 lanes x 32 consecutive fp32 columns: thread t gets lane (base lane + t)
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// K-major, no swizzle: LBO = byte distance between K-adjacent core matrices, SBO = between 8-row groups
-__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) |
-         ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
-}
-// bf16 x bf16 -> f32, both operands K-major
-__host__ __device__ constexpr uint32_t instr_desc(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
 
 // Byte layout of the weight image built by tvm_pack_mlp_tc (copied verbatim into shared memory)
 struct Image {
@@ -122,16 +39,19 @@ struct Image {
 
 using namespace tc;
 
-// fp32 [K][ldw] (row j = input j) -> bf16 UMMA image [(K_pad/8)][N][8]; out-of-range entries are 0
+namespace tc {
 __global__ void k_pack_umma_b(const float* __restrict__ w_t, int K, int K_pad, int N_real, int N, int ldw,
-                              __nv_bfloat16* __restrict__ img) {
+                              __nv_bfloat16* __restrict__ img, int split, int split_pad) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= K_pad * N) return;
   const int kc = i / (N * 8), rem = i % (N * 8), n = rem / 8, kk = rem % 8;
   const int k = kc * 8 + kk;
-  const float v = (k < K && n < N_real) ? w_t[(size_t)k * ldw + n] : 0.0f;
+  int src = k;
+  if (k >= split) src = k < split_pad ? -1 : split + (k - split_pad);
+  const float v = (src >= 0 && src < K && n < N_real) ? w_t[(size_t)src * ldw + n] : 0.0f;
   img[i] = __float2bfloat16_rn(v);
 }
+}  // namespace tc
 __global__ void k_pack_tc_f32(const TvmModel m, float* __restrict__ dst) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < 128) dst[i] = m.b1[i];
@@ -494,7 +414,7 @@ extern "C" int tvm_pack_mlp_tc(const TvmModel* m_host, void* out, void* stream_)
   uint8_t* o = (uint8_t*)out;
   auto launch = [&](const float* w_t, int K, int K_pad, int N_real, int N, int ldw, uint32_t off) {
     const int n = K_pad * N;
-    k_pack_umma_b<<<(n + 255) / 256, 256, 0, s>>>(w_t, K, K_pad, N_real, N, ldw, (__nv_bfloat16*)(o + off));
+    k_pack_umma_b<<<(n + 255) / 256, 256, 0, s>>>(w_t, K, K_pad, N_real, N, ldw, (__nv_bfloat16*)(o + off), K_pad, K_pad);
   };
   launch(m_host->basis_t, img.K0, img.K0, nh, nh, nh, img.off_b0);
   launch(m_host->w1_t, in_c, img.K1, 128, 128, kFeatureC, img.off_b1);
