@@ -46,7 +46,12 @@ def parse():
     ap.add_argument("--grid", type=int, default=GRID)
     ap.add_argument("--rays", type=int, default=FRAME * FRAME, help="rays per step (default: the full frame)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample-chunks", type=int, default=16)
+    ap.add_argument("--cpu-sample-chunks", type=int, default=256,
+                    help="chunks of 1024 rays the CPU baseline renders (256 = 41%% of the frame, 10-30 s of CPU work)")
+    ap.add_argument("--workload", default="frame", choices=["frame", "train", "npp", "ref"],
+                    help="frame = BASELINE configs[1] (the contract line); train = configs[2] (4096-ray fwd+bwd step, "
+                         "128^3 grid); npp / ref = configs[3] (NeRF++ background / Ref-NeRF appearance, full frame). "
+                         "The non-default workloads print the same JSON shape for profiles/, not for the driver.")
     return ap.parse_args()
 
 
@@ -169,8 +174,97 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def run_side_workload(args):
+    """configs[2] (training step) and configs[3] (variants, full frame): same timing rules as the contract
+    line (warm-up >= 3, L2 flushed before every timed step, CUDA events on the launching stream)."""
+    import jittor_myc_nerfs_b200 as pkg
+    from oracle import fixtures as fx
+    L = pkg._lib
+    L.require_cuda()
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    reg = fx.REGIMES[args.regime]
+    train = args.workload == "train"
+    G = args.grid if (args.grid != GRID or not train) else 128
+    variant = {"npp": "npp", "ref": "ref"}.get(args.workload, "vm")
+    mp = fx.make_model(G, density_shift=reg["density_shift"], variant=variant)
+    vol = fx.ball_alpha_volume(MASK_RES if G > 128 else 128) if reg["mask"] else None
+    model = pkg.model_from_params(mp, "cuda:0", vol, mp.aabb.copy(), "fp32" if train else args.mlp)
+    if train:
+        n = 4096 if args.rays == FRAME * FRAME else args.rays
+        rays_np = fx.subset_rays(n)
+        S = int(np.linalg.norm(np.asarray(mp.gridSize, dtype=np.float64)) / mp.step_ratio)     # cal_n_samples, utils.py:61-62
+        tgt = torch.from_numpy(fx.target_rgb(n)).to(dev)
+        jit = torch.from_numpy(fx.jitter(n)).to(dev)
+    else:
+        rays_np = fx.frame_rays()[:args.rays]
+        n, S = rays_np.shape[0], model.nSamples
+    rays = torch.from_numpy(np.ascontiguousarray(rays_np)).to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    extra = {}
+    if args.workload == "npp":
+        fg, bg = fx.npp_rand(1, 1)      # shapes only; the draws themselves come from the device RNG below
+        g = torch.Generator(device=dev).manual_seed(fx.SEED_BASE)
+        extra = dict(fg_rand=torch.rand((n, S), device=dev, generator=g), bg_rand=torch.rand((n, 512), device=dev, generator=g))
+
+    def step():
+        if train:
+            for p in model.parameters():
+                p.grad = None
+            rgb, _ = model(rays, is_train=True, white_bg=True, N_samples=S, jitter=jit)
+            loss = torch.mean((rgb - tgt) ** 2)
+            loss.backward()
+            return loss
+        with torch.no_grad():
+            if args.workload == "npp":
+                return model(rays, N_samples=S, **extra)
+            return model(rays, white_bg=True, is_train=False, N_samples=S)
+
+    def timed(steps):
+        evs = []
+        torch.cuda.synchronize()
+        for _ in range(steps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            step()
+            b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in evs)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    with ClockSampler(0) as clk:
+        ms = timed(args.steps)
+    model.collect_counters = True
+    model.counters.zero_()
+    L.profile_enable(True)
+    L.profile_collect()
+    timed(args.steps)
+    stage_ms, stage_cnt = L.profile_collect()
+    L.profile_enable(False)
+    cnt = model.counters.cpu().numpy().astype(np.float64) / args.steps
+    name = {"train": f"configs[2]: training step fwd+bwd (MSE), {n} rays, {G}^3 grid, S={S}, fp32",
+            "npp": f"configs[3]: NerfPlusPlus full frame ({n} rays), {G}^3 grid, 512 background samples/ray",
+            "ref": f"configs[3]: REFTensoRF full frame ({n} rays), {G}^3 grid"}[args.workload]
+    line = {"metric": f"TensoRF-VM rays/sec ({args.workload})", "value": n / (ms / args.steps * 1e-3), "unit": UNIT,
+            "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if train or args.mlp == "fp32" else f"f32 + {args.mlp} tensor-core MLP", "data": "synthetic",
+            "config": {"workload": name + f", regime {args.regime}", "n_samples": S,
+                       "l2": "flushed before every timed step (256 MiB write)",
+                       "per_step_counts": {"M_in": cnt[L.CNT_M_IN], "M_v_gathered": cnt[L.CNT_M_V], "M_a": cnt[L.CNT_M_A]}},
+            "gpu_launches": int(sum(stage_cnt.values())), "clocks": clk.summary(),
+            "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items() if v},
+            "stage_launches_per_step": {k: v / args.steps for k, v in stage_cnt.items() if v}}
+    print(json.dumps(line))
+
+
 def main():
     args = parse()
+    if args.workload != "frame":
+        return run_side_workload(args)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -280,8 +374,15 @@ def main():
     achieved = bytes_per_launch / (march_ms * 1e-3) / 1e9
     bytes_app_step = 3456.0 * M_a
     app_ms = stage_ms["app"] / max(1, stage_cnt["app"])
+    # DRAM bytes per launch of the same kernel from the committed `ncu --set full` capture (profiles/traffic.json)
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath) and args.grid == GRID and args.rays == FRAME * FRAME and args.regime == "R1":
+        tj = json.load(open(tpath))["k_march"]
+        traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
     roof = {"bound": "hbm", "kernel": "k_march (march+mask+density gather+composite)", "achieved": achieved,
-            "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+            "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
+            "traffic_source": traffic_src,
             "peak_source": peak_src, "ms_per_launch": march_ms, "launches_per_step": launches_march / args.steps,
             "algorithmic_bytes_per_launch": bytes_per_launch,
             "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items() if v},

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define TVM_ABI_VERSION 6
+#define TVM_ABI_VERSION 7
 
 /* flags for tvm_forward / tvm_backward */
 #define TVM_WHITE_BG      0x1u  /* rgb_map += 1 - acc_map          (tensorBase.py:523-524) */
@@ -126,6 +126,8 @@ typedef struct TvmBgNet {
   const float* wv_t;        /* [15][64]    rgb_layers.0.weight[:, 256:271]^T                            */
   const float* w_rgb;       /* [3][64]     rgb_layers.2.weight                                          */
   const float* b_rgb;       /* [3]                                                                      */
+  const void* tc_weights;   /* optional bf16 tensor-core operand image written by tvm_pack_bg_tc (NULL = not packed;
+                               required when tvm_forward_npp runs with TVM_MLP_BF16)                    */
 } TvmBgNet;
 
 /* Optional per-sample outputs for parity tests (any member may be NULL).  Requesting aux
@@ -189,6 +191,10 @@ size_t tvm_tc_weights_bytes(const TvmModel* m_host);
 /* builds the bf16 (hi, mid) K-major UMMA operand images of basis/W1/W2 from the packed fp32 weights */
 int tvm_pack_mlp_tc(const TvmModel* m_host, void* tc_weights_out, void* stream);
 
+/* NeRF++ background network on the tensor cores: bytes of / builder for TvmBgNet.tc_weights (16-byte aligned) */
+size_t tvm_bg_tc_bytes(void);
+int tvm_pack_bg_tc(const TvmBgNet* bg_host, void* tc_weights_out, void* stream);
+
 /* ---- the hot path --------------------------------------------------------------------------- */
 /* bytes of scratch tvm_forward needs for n rays x n_samples (worst case: every sample weighted) */
 int tvm_workspace_bytes(int n_rays, int n_samples, size_t* out_bytes);
@@ -204,7 +210,8 @@ int tvm_forward(const TvmModel* m_host, const float* rays, int n_rays, int n_sam
 /* NerfPlusPlus.execute (nerfplusplus.py:272-318): foreground = tvm_forward on black with TVM_SAMPLING_NPP
  * (fg_rand [n][S]); bg_lambda = prod(1 - alpha + 1e-6), zeroed when <= 0.1; background = 512 inverse-depth
  * samples per ray (bg_rand [n][512]) through the bg MLP, composited front to back;
- * rgb_map += bg_lambda * bg_rgb_map.  Rays with bg_lambda == 0 skip the background entirely.            */
+ * rgb_map += bg_lambda * bg_rgb_map.  Rays with bg_lambda == 0 skip the background entirely.
+ * TVM_MLP_FP32: background MLP in fp32 FMA; TVM_MLP_BF16: on tcgen05 tensor cores (bg_host->tc_weights).  */
 int tvm_forward_npp(const TvmModel* m_host, const TvmBgNet* bg_host, const float* rays, int n_rays, int n_samples,
                     const float* fg_rand, const float* bg_rand, uint32_t flags, float* rgb_map, float* depth_map,
                     const TvmAux* aux_host, uint64_t* counters, void* ws, size_t ws_bytes, void* stream);

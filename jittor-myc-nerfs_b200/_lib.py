@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libtvmrender.so")
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 # flags (tvmrender.h)
 WHITE_BG = 0x1
@@ -54,7 +54,7 @@ class TvmAux(C.Structure):
 
 class TvmBgNet(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("w0_t", "b0", "w1_t", "b1", "w2_t", "b2", "w_sigma", "b_sigma", "wf_t", "bf",
-                                           "wv_t", "w_rgb", "b_rgb")]
+                                           "wv_t", "w_rgb", "b_rgb", "tc_weights")]
 
 
 class TvmGrads(C.Structure):
@@ -66,7 +66,7 @@ class TvmGrads(C.Structure):
 EXPORTS = [
     "tvm_last_error", "tvm_abi_version", "tvm_device_count", "tvm_pack_grid", "tvm_unpack_grid",
     "tvm_pack_linear", "tvm_unpack_linear", "tvm_pack_alpha", "tvm_pack_alpha_bricks", "tvm_tc_weights_bytes", "tvm_pack_mlp_tc",
-    "tvm_workspace_bytes", "tvm_forward", "tvm_forward_npp", "tvm_bg_fold", "tvm_backward", "tvm_density_alpha", "tvm_mse_loss",
+    "tvm_workspace_bytes", "tvm_forward", "tvm_forward_npp", "tvm_bg_fold", "tvm_bg_tc_bytes", "tvm_pack_bg_tc", "tvm_backward", "tvm_density_alpha", "tvm_mse_loss",
     "tvm_profile_enable", "tvm_profile_collect",
 ]
 
@@ -103,6 +103,8 @@ def load() -> C.CDLL:
     lib.tvm_pack_alpha_bricks.argtypes = [vp, i32, i32, i32, vp, vp]
     lib.tvm_tc_weights_bytes.restype = C.c_size_t
     lib.tvm_tc_weights_bytes.argtypes = [C.POINTER(TvmModel)]
+    lib.tvm_bg_tc_bytes.restype = C.c_size_t
+    lib.tvm_bg_tc_bytes.argtypes = []
     lib.tvm_pack_mlp_tc.argtypes = [C.POINTER(TvmModel), vp, vp]
     lib.tvm_workspace_bytes.argtypes = [i32, i32, C.POINTER(C.c_size_t)]
     lib.tvm_forward.argtypes = [C.POINTER(TvmModel), vp, i32, i32, vp, u32, vp, vp, C.POINTER(TvmAux), vp, vp,
@@ -117,7 +119,7 @@ def load() -> C.CDLL:
     lib.tvm_profile_enable.argtypes = [i32]
     lib.tvm_profile_collect.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_int)]
     for name in EXPORTS:
-        if name not in ("tvm_last_error", "tvm_tc_weights_bytes"):
+        if name not in ("tvm_last_error", "tvm_tc_weights_bytes", "tvm_bg_tc_bytes"):
             getattr(lib, name).restype = i32
     if lib.tvm_abi_version() != ABI_VERSION:
         raise TvmError(f"libtvmrender.so ABI {lib.tvm_abi_version()} != binding ABI {ABI_VERSION}: rebuild")

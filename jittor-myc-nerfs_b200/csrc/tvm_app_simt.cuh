@@ -123,9 +123,11 @@ __device__ __forceinline__ void app_basis_pe(const FwdParams& P, const float* H,
       const float r0 = hd[3], r1 = hd[4], r2 = hd[5], tint = fmaxf(hd[6], 0.0f);
       hd[0] = r0; hd[1] = r1; hd[2] = r2; hd[3] = tint;
       const uint32_t e = tile_base + row;
-      if (P.aux.penalty && e < n_ent) {
+      if (P.aux.penalty) {
+        // part == 3 is two whole warps: one atomic per warp instead of one per entry (single-address contention)
         const float pen = fmaxf(-dot, 0.0f);
-        atomicAdd(P.aux.penalty, P.ws.ent_w[e] * pen * pen);
+        const float v = warp_sum(e < n_ent ? P.ws.ent_w[e] * pen * pen : 0.0f);
+        if ((threadIdx.x & 31) == 0 && v != 0.0f) atomicAdd(P.aux.penalty, v);
       }
     }
     for (int c = 0; c < 3; ++c) {

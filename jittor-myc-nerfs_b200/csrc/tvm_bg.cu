@@ -8,55 +8,9 @@
 //               the ray stops once it falls below 1e-6.
 //   k_bg_fold   weights-only product that folds base_remap (no activation) into rgb_layers.0.
 #include "tvm_app_simt.cuh"
+#include "tvm_bg.cuh"
 
 namespace tvm {
-
-constexpr int kBgSamples = TVM_NPP_BG_SAMPLES;
-constexpr int kPosDim = 20, kDirDim = 15, kBgHid = 64;
-
-struct BgRay {
-  float p_sphere[3], axis[3], cross_ap[3];   // point on the sphere, rotation axis, axis x p_sphere
-  float axis_dot;                            // axis . p_sphere
-  float pmn, phi;                            // |p_mid|, asin(|p_mid| / R)
-};
-
-// per-ray part of depth2pts_outside (nerfplusplus.py:212-225)
-__device__ __forceinline__ void bg_ray_setup(const float* ray6, float R, BgRay& g) {
-  const float o[3] = {ray6[0], ray6[1], ray6[2]}, d[3] = {ray6[3], ray6[4], ray6[5]};
-  const float dd = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
-  const float d1 = -(d[0] * o[0] + d[1] * o[1] + d[2] * o[2]) / dd;
-  float pm[3];
-#pragma unroll
-  for (int i = 0; i < 3; ++i) pm[i] = o[i] + d1 * d[i];
-  g.pmn = sqrtf(pm[0] * pm[0] + pm[1] * pm[1] + pm[2] * pm[2]);
-  const float cosd = 1.0f / sqrtf(dd);
-  const float d2 = sqrtf(R * R - g.pmn * g.pmn) * cosd;
-#pragma unroll
-  for (int i = 0; i < 3; ++i) g.p_sphere[i] = o[i] + (d1 + d2) * d[i];
-  float ax[3] = {o[1] * g.p_sphere[2] - o[2] * g.p_sphere[1], o[2] * g.p_sphere[0] - o[0] * g.p_sphere[2],
-                 o[0] * g.p_sphere[1] - o[1] * g.p_sphere[0]};
-  const float inv = 1.0f / sqrtf(ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2]);
-#pragma unroll
-  for (int i = 0; i < 3; ++i) g.axis[i] = ax[i] * inv;
-  g.cross_ap[0] = g.axis[1] * g.p_sphere[2] - g.axis[2] * g.p_sphere[1];
-  g.cross_ap[1] = g.axis[2] * g.p_sphere[0] - g.axis[0] * g.p_sphere[2];
-  g.cross_ap[2] = g.axis[0] * g.p_sphere[1] - g.axis[1] * g.p_sphere[0];
-  g.axis_dot = g.axis[0] * g.p_sphere[0] + g.axis[1] * g.p_sphere[1] + g.axis[2] * g.p_sphere[2];
-  g.phi = asinf(g.pmn / R);
-}
-
-// torch.linspace(0, R, 512)[i] (symmetric evaluation) and perturb_samples (nerfplusplus.py:196-205)
-__device__ __forceinline__ float bg_lin(int i, float R) {
-  const float step = R / (float)(kBgSamples - 1);
-  return i < kBgSamples / 2 ? (float)i * step : R - (float)(kBgSamples - 1 - i) * step;
-}
-__device__ __forceinline__ float bg_depth(int i, float R, const float* rnd) {
-  const float f0 = bg_lin(i, R);
-  float lower = f0, upper = f0;
-  if (i > 0) lower = 0.5f * (f0 + bg_lin(i - 1, R));
-  if (i < kBgSamples - 1) upper = 0.5f * (bg_lin(i + 1, R) + f0);
-  return lower + (upper - lower) * rnd[i];
-}
 
 // y[row][part*16 .. +16) = relu(x[row][0..128) @ Wt[128][64] + vbias): thread (row, part)
 __device__ __forceinline__ void bg_hidden(const float* __restrict__ Wt, const float* vbias, const float* xin,
@@ -249,12 +203,15 @@ __global__ void k_bg_fold(const float* __restrict__ remap_w, const float* __rest
   }
 }
 
+int launch_bg_tc(const FwdParams& P, int num_sms, cudaStream_t stream);   // tvm_bg_tc.cu
+
 int launch_bg(const FwdParams& P, int num_sms, cudaStream_t stream) {
   const TvmBgNet& b = P.bg;
   TVM_REQUIRE(b.w0_t && b.b0 && b.w1_t && b.b1 && b.w2_t && b.b2 && b.w_sigma && b.b_sigma && b.wf_t && b.bf &&
               b.wv_t && b.w_rgb && b.b_rgb, "null TvmBgNet pointer");
   TVM_REQUIRE(P.m.radii > 0.0f, "radii must be positive");
   if (P.aux.bg_rgb_map) TVM_CHECK_CUDA(cudaMemsetAsync(P.aux.bg_rgb_map, 0, (size_t)P.n * 12, stream));
+  if ((P.flags & TVM_MLP_MASK) == TVM_MLP_BF16) return launch_bg_tc(P, num_sms, stream);
   const size_t smem = ((size_t)kAppTile * 2 * P.st + kAppTile * 4 + kAppTile + kBgHid + 4) * sizeof(float);
   TVM_CHECK_CUDA(cudaFuncSetAttribute(k_bg_simt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_bg_simt<<<num_sms * 2, kAppThreads, smem, stream>>>(P);

@@ -205,6 +205,7 @@ __global__ void __launch_bounds__(kThreadsV2, 1) k_app_tc(const FwdParams P) {
     const uint32_t aB0 = smem_u32(sW + img.off_b0), aB1 = smem_u32(sW + img.off_b1), aB2 = smem_u32(sW + img.off_b2);
     uint8_t* arow = sA + row * 16;
     uint32_t it = 0, mma_phase = 0;
+    float pen_acc = 0.0f;
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const uint32_t s = it & 1u, use = it >> 1;
       const uint32_t e = tile * kRows + row;
@@ -254,7 +255,7 @@ __global__ void __launch_bounds__(kThreadsV2, 1) k_app_tc(const FwdParams P) {
           ndot = -dot;
           if (P.aux.penalty && e < n_ent) {
             const float pen = fmaxf(-dot, 0.0f);
-            atomicAdd(P.aux.penalty, P.ws.ent_w[e] * pen * pen);
+            pen_acc = fmaf(P.ws.ent_w[e], pen * pen, pen_acc);     // one atomic per warp at the end of the CTA
           }
         }
         float s1[APP_DIM + 3], c1[APP_DIM + 3];
@@ -364,6 +365,10 @@ __global__ void __launch_bounds__(kThreadsV2, 1) k_app_tc(const FwdParams P) {
       }
       fence_before();
       mlp_group_sync();     // TMEM columns and the A operand are free for the next tile
+    }
+    if (REF && P.aux.penalty) {
+      pen_acc = warp_sum(pen_acc);
+      if (lane == 0 && pen_acc != 0.0f) atomicAdd(P.aux.penalty, pen_acc);
     }
   }
 

@@ -695,8 +695,18 @@ class NerfPlusPlus(TensorVMSplit):
             s = L.TvmBgNet()
             for k in sizes:
                 setattr(s, k, buf.data_ptr() + 4 * offs[k])
+            s.tc_weights = None
             self._bg_struct_c, self._bg_versions = s, versions
-        return self._bg_struct_c
+            self._bg_tc_stale = True
+        s = self._bg_struct_c
+        if self.mlp_mode != "fp32" and self._bg_tc_stale:
+            # bf16 operand image of the background network for the tcgen05 kernel (k_bg_tc)
+            if getattr(self, "_bg_tc", None) is None:
+                self._bg_tc = torch.empty(lib.tvm_bg_tc_bytes(), dtype=torch.uint8, device=self.device)
+            L.check(lib.tvm_pack_bg_tc(C.byref(s), _ptr(self._bg_tc), _stream_ptr()), "tvm_pack_bg_tc")
+            s.tc_weights = self._bg_tc.data_ptr()
+            self._bg_tc_stale = False
+        return s
 
     def forward(self, rays_chunk, white_bg=False, is_train=False, ndc_ray=False, N_samples=-1,
                 additional_output=True, fg_rand=None, bg_rand=None, aux=None):
