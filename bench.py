@@ -254,10 +254,19 @@ def run_side_workload(args):
             "dtype": "f32" if train or args.mlp == "fp32" else f"f32 + {args.mlp} tensor-core MLP", "data": "synthetic",
             "config": {"workload": name + f", regime {args.regime}", "n_samples": S,
                        "l2": "flushed before every timed step (256 MiB write)",
-                       "per_step_counts": {"M_in": cnt[L.CNT_M_IN], "M_v_gathered": cnt[L.CNT_M_V], "M_a": cnt[L.CNT_M_A]}},
+                       "per_step_counts": {"M_in": cnt[L.CNT_M_IN], "M_v_gathered": cnt[L.CNT_M_V], "M_a": cnt[L.CNT_M_A],
+                                           "bg_rays": cnt[L.CNT_BG_RAYS], "bg_samples": cnt[L.CNT_BG_SAMPLES]}},
             "gpu_launches": int(sum(stage_cnt.values())), "clocks": clk.summary(),
             "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items() if v},
             "stage_launches_per_step": {k: v / args.steps for k, v in stage_cnt.items() if v}}
+    if args.workload == "npp" and stage_ms.get("bg"):
+        # dense FLOPs of the background network as issued on the tensor cores (padded K/N), per sample
+        flop = 2.0 * 128 * (32 + 144 + 160) + 2.0 * 128 * 80 + 2.0 * 64 * 16
+        tf = flop * cnt[L.CNT_BG_SAMPLES] / (stage_ms["bg"] / args.steps * 1e-3) / 1e12
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+        peak = float(pk.get("bf16_tflops_sustained", pk.get("bf16_tflops", 1355.0)))
+        line["roofline"] = {"bound": "tensor", "kernel": "k_bg_tc", "achieved": tf, "peak": peak, "unit": "TFLOP/s",
+                            "frac": tf / peak, "traffic": None, "flop_per_sample_issued": flop}
     print(json.dumps(line))
 
 

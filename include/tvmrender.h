@@ -167,6 +167,8 @@ typedef struct TvmGrads {
 #define TVM_CNT_M_V    1    /* samples whose density was gathered (passed the alpha mask)       */
 #define TVM_CNT_M_A    2    /* samples with weight > thres (appearance evaluated)               */
 #define TVM_CNT_RAYS   3    /* rays with at least one gathered sample                           */
+#define TVM_CNT_BG_RAYS 4   /* tvm_forward_npp: rays whose background was evaluated (bg_lambda > 0.1) */
+#define TVM_CNT_BG_SAMPLES 5 /* tvm_forward_npp: background samples pushed through the bg MLP       */
 #define TVM_CNT_WORDS  8
 
 const char* tvm_last_error(void);

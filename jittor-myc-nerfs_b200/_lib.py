@@ -21,6 +21,7 @@ MLP_BF16X3 = 0x20
 ACT_SOFTPLUS, ACT_RELU = 0, 1
 VARIANT_VM, VARIANT_REF, REF_HEAD_LD = 0, 1, 48
 CNT_M_IN, CNT_M_V, CNT_M_A, CNT_RAYS, CNT_WORDS = 0, 1, 2, 3, 8
+CNT_BG_RAYS, CNT_BG_SAMPLES = 4, 5
 STAGE_NAMES = ["march", "app", "composite", "bwd_app", "bwd_march", "bg"]
 SAMPLING_UNIFORM, SAMPLING_NPP = 0, 1
 STAGE_COUNT = 8

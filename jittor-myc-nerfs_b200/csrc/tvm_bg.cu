@@ -76,10 +76,12 @@ __global__ void __launch_bounds__(kAppThreads) k_bg_simt(const FwdParams P) {
     }
     if (tid == 0) FLAG[0] = 1.0f;
     float T = 1.0f, c0 = 0.0f, c1 = 0.0f, c2 = 0.0f;     // warp 0 only
+    int tiles_done = 0;
     __syncthreads();
 
     for (int tile = 0; tile < kBgSamples / kAppTile; ++tile) {
       if (FLAG[0] < 1e-6f) break;                        // uniform: remaining weight mass < 1e-6
+      ++tiles_done;
       // ---- geometry + embedding: flipped order j (near the sphere first), original index i = 511 - j
       if (part == 0) {
         const int j = tile * kAppTile + row, i = kBgSamples - 1 - j;
@@ -165,6 +167,10 @@ __global__ void __launch_bounds__(kAppThreads) k_bg_simt(const FwdParams P) {
       c1 = warp_sum(c1);
       c2 = warp_sum(c2);
       if (lane == 0) {
+        if (P.counters) {
+          atomicAdd(&P.counters[TVM_CNT_BG_RAYS], 1ull);
+          atomicAdd(&P.counters[TVM_CNT_BG_SAMPLES], (unsigned long long)(tiles_done * kAppTile));
+        }
         const float lam = P.ws.bg_lambda[ray];
         P.rgb_map[(size_t)ray * 3 + 0] += lam * c0;       // nerfplusplus.py:314-317 (no clamp after the sum)
         P.rgb_map[(size_t)ray * 3 + 1] += lam * c1;

@@ -2,8 +2,8 @@
 // (tcgen05 / TMEM), sm_100a only.  Replaces k_bg_simt when TVM_MLP_BF16 is requested.
 //
 // One persistent CTA per SM holds the whole network (five bf16 B operands, 106 KB) in shared memory and
-// runs TWO independent 128-thread pipelines (thread = sample = TMEM lane), so that the MMAs of one
-// pipeline overlap the epilogue of the other.  A pipeline takes one active ray at a time (dynamic
+// runs THREE independent 128-thread pipelines (thread = sample = TMEM lane), so that the MMAs of one
+// pipeline overlap the epilogues of the others (3 x 40 KB A operands: the 227 KB of shared memory are full).  A pipeline takes one active ray at a time (dynamic
 // scheduling through a global counter) and walks its 512 samples front to back in 4 tiles of 128:
 //
 //   geometry  depth2pts_outside + Embedder (:207-237, :40-56)  -> A[:, 0:32)   = [emb 20 | 1.0 | 0...]  bf16
@@ -25,7 +25,7 @@ namespace bgtc {
 
 using namespace tc;
 
-constexpr int kPipes = 2;
+constexpr int kPipes = 3;
 constexpr int kPipeThreads = 128;
 constexpr int kThreads = kPipes * kPipeThreads;
 constexpr int kPosK = 32;               // position block of the A operand (20 embedding columns, padded)
@@ -34,7 +34,7 @@ constexpr int kAK = kPosK + kFeatureC;  // 160 columns
 constexpr int kN3 = 80;                 // 64 hidden rgb units + sigma + padding (N % 16 == 0)
 constexpr int kN4 = 16;                 // 3 colour channels, padded
 constexpr int kK1 = kFeatureC + 16;     // hidden + the 16 position columns that hold the one-column
-constexpr int kTmemColsBg = 256;        // 128 accumulator columns per pipeline
+constexpr int kTmemColsBg = 512;        // 128 accumulator columns per pipeline (power of two >= 3 * 128)
 
 constexpr uint32_t kLboA = kRows * 16;
 constexpr uint32_t kABytes = kRows * kAK * 2;
@@ -98,15 +98,15 @@ __device__ __forceinline__ void issue_steps(uint32_t tmem_d, uint32_t a_base, ui
 }
 
 __global__ void __launch_bounds__(kThreads, 1) k_bg_tc(const FwdParams P) {
-  extern __shared__ __align__(1024) uint8_t smem[];
+  extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sW = smem;
-  uint8_t* sA = smem + ((kImageBytes + 1023) & ~1023u);              // kPipes x [128 x 160] bf16
+  uint8_t* sA = smem + kImageBytes;                                  // kPipes x [128 x 160] bf16
   float* sVB = reinterpret_cast<float*>(sA + kPipes * kABytes);      // [kPipes][64] per-ray bias of the hidden rgb layer
+  float* sCS = sVB;                                                  // per-warp colour sums alias VB[0..15] (VB is dead by then)
   float* sWP = sVB + kPipes * kBgHid;                                // [kPipes][4] per-warp transmittance products
-  float* sCS = sWP + kPipes * 4;                                     // [kPipes][4][4] per-warp colour sums
-  uint32_t* sRay = reinterpret_cast<uint32_t*>(sCS + kPipes * 16);   // [kPipes] ray index handed out by the scheduler
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sRay + 2 * kPipes);   // [kPipes] MMA completion
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kPipes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sWP + kPipes * 4);    // [kPipes] MMA completion
+  uint32_t* sRay = reinterpret_cast<uint32_t*>(bars + kPipes);       // [kPipes] ray index handed out by the scheduler
+  uint32_t* tmem_slot = sRay + kPipes;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int pipe = tid / kPipeThreads, ptid = tid % kPipeThreads, pwarp = ptid >> 5;
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_bg_tc(const FwdParams P) {
   uint32_t phase = 0;
   float* VB = sVB + pipe * kBgHid;
   float* WP = sWP + pipe * 4;
-  float* CS = sCS + pipe * 16;
+  float* CS = sCS + pipe * kBgHid;
   const uint32_t n_active = P.ws.n_entries[1];
 
   auto mma_wait = [&]() {
@@ -187,38 +187,42 @@ __global__ void __launch_bounds__(kThreads, 1) k_bg_tc(const FwdParams P) {
       VB[ptid] = a;
     }
     float T = 1.0f, c0 = 0.0f, c1 = 0.0f, c2 = 0.0f;
+    int tiles_done = 0;
+    // geometry + embedding of one sample: flipped order j (nearest the sphere first), original index i = 511 - j
+    float nxt_dz;
+    uint4 nxt_e0, nxt_e1, nxt_e2;
+    auto geometry = [&](int tile) {
+      const int j = tile * kRows + ptid, i = kBgSamples - 1 - j;
+      const float z = bg_depth(i, R, rnd);
+      nxt_dz = (i > 0) ? z - bg_depth(i - 1, R, rnd) : 1e10f;             // bg_dists, HUGE_NUMBER last (:299-300)
+      const float theta = asinf(g.pmn * z / (R * R));
+      float sa, ca;
+      __sincosf(g.phi - theta, &sa, &ca);
+      float x[4], s1[4], cc1[4], s2[4], cc2[4];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) x[c] = g.p_sphere[c] * ca + g.cross_ap[c] * sa + g.axis[c] * g.axis_dot * (1.0f - ca);
+      x[3] = z;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        __sincosf(x[c], &s1[c], &cc1[c]);
+        s2[c] = 2.0f * s1[c] * cc1[c];
+        cc2[c] = 1.0f - 2.0f * s1[c] * s1[c];
+      }
+      nxt_e0 = make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(s1[0], s1[1]), pack_bf16(s1[2], s1[3]));
+      nxt_e1 = make_uint4(pack_bf16(cc1[0], cc1[1]), pack_bf16(cc1[2], cc1[3]), pack_bf16(s2[0], s2[1]), pack_bf16(s2[2], s2[3]));
+      nxt_e2 = make_uint4(pack_bf16(cc2[0], cc2[1]), pack_bf16(cc2[2], cc2[3]), pack_bf16(1.0f, 0.0f), 0u);
+    };
+    geometry(0);
 
 #pragma unroll 1
     for (int tile = 0; tile < kBgSamples / kRows; ++tile) {
-      // ---- geometry + embedding: flipped order j (nearest the sphere first), original index i = 511 - j --------
-      const int j = tile * kRows + ptid, i = kBgSamples - 1 - j;
-      const float z = bg_depth(i, R, rnd);
-      const float dz = (i > 0) ? z - bg_depth(i - 1, R, rnd) : 1e10f;      // bg_dists, HUGE_NUMBER last (:299-300)
-      {
-        const float theta = asinf(g.pmn * z / (R * R));
-        float sa, ca;
-        sincosf(g.phi - theta, &sa, &ca);
-        float x[4], s1[4], cc1[4];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) x[c] = g.p_sphere[c] * ca + g.cross_ap[c] * sa + g.axis[c] * g.axis_dot * (1.0f - ca);
-        x[3] = z;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) sincosf(x[c], &s1[c], &cc1[c]);
-        float s2[4], cc2[4];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          s2[c] = 2.0f * s1[c] * cc1[c];
-          cc2[c] = 1.0f - 2.0f * s1[c] * s1[c];
-        }
-        uint4 v;
-        v.x = pack_bf16(x[0], x[1]);   v.y = pack_bf16(x[2], x[3]);   v.z = pack_bf16(s1[0], s1[1]);  v.w = pack_bf16(s1[2], s1[3]);
-        *reinterpret_cast<uint4*>(arow + 0 * kLboA) = v;
-        v.x = pack_bf16(cc1[0], cc1[1]); v.y = pack_bf16(cc1[2], cc1[3]); v.z = pack_bf16(s2[0], s2[1]); v.w = pack_bf16(s2[2], s2[3]);
-        *reinterpret_cast<uint4*>(arow + 1 * kLboA) = v;
-        v.x = pack_bf16(cc2[0], cc2[1]); v.y = pack_bf16(cc2[2], cc2[3]); v.z = pack_bf16(1.0f, 0.0f);   v.w = 0u;
-        *reinterpret_cast<uint4*>(arow + 2 * kLboA) = v;
-        *reinterpret_cast<uint4*>(arow + 3 * kLboA) = make_uint4(0u, 0u, 0u, 0u);
-      }
+      ++tiles_done;
+      // ---- position block of this tile (prefetched during the previous tile's L4) ------------------------------------
+      const float dz = nxt_dz;
+      *reinterpret_cast<uint4*>(arow + 0 * kLboA) = nxt_e0;
+      *reinterpret_cast<uint4*>(arow + 1 * kLboA) = nxt_e1;
+      *reinterpret_cast<uint4*>(arow + 2 * kLboA) = nxt_e2;
+      *reinterpret_cast<uint4*>(arow + 3 * kLboA) = make_uint4(0u, 0u, 0u, 0u);
       publish_A();
       // ---- L0 ------------------------------------------------------------------------------------------------
       if (ptid == 0) {
@@ -287,6 +291,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_bg_tc(const FwdParams P) {
         issue_steps(tmem, aAh, aW4, kN4 * 16, kBgHid / 16, ID16, false);
         umma_commit(mma_bar);
       }
+      if (tile + 1 < kBgSamples / kRows) geometry(tile + 1);       // overlaps the L4 round trip
       mma_wait();
       float rgb[3];
       {
@@ -329,6 +334,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_bg_tc(const FwdParams P) {
       CS[pwarp * 4 + 2] = c2;
     }
     pipe_sync(pipe);
+    if (ptid == 3 && P.counters) {
+      atomicAdd(&P.counters[TVM_CNT_BG_RAYS], 1ull);
+      atomicAdd(&P.counters[TVM_CNT_BG_SAMPLES], (unsigned long long)(tiles_done * kRows));
+    }
     if (ptid < 3) {
       const float c = (CS[ptid] + CS[4 + ptid]) + (CS[8 + ptid] + CS[12 + ptid]);
       const float lam = P.ws.bg_lambda[ray];
@@ -387,8 +396,9 @@ __global__ void k_pack_bg_tc(const TvmBgNet b, uint8_t* __restrict__ out) {
 int launch_bg_tc(const FwdParams& P, int num_sms, cudaStream_t stream) {
   using namespace bgtc;
   TVM_REQUIRE(P.bg.tc_weights != nullptr, "TvmBgNet.tc_weights is NULL: call tvm_pack_bg_tc first");
-  const size_t smem = ((kImageBytes + 1023) & ~1023u) + kPipes * kABytes + kPipes * (kBgHid + 4 + 16) * 4 + 2 * kPipes * 4 +
-                      kPipes * 8 + 16 + 1024;
+  const size_t smem = kImageBytes + kPipes * kABytes + kPipes * (kBgHid + 4) * 4 + kPipes * 8 + kPipes * 4 + 16;
+  static_assert(kImageBytes % 16 == 0 && (kPipes * 4 * 4) % 8 == 0, "shared-memory carve-up alignment");
+  TVM_REQUIRE(smem <= 227 * 1024, "k_bg_tc shared memory");
   TVM_CHECK_CUDA(cudaFuncSetAttribute(k_bg_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_bg_tc<<<num_sms, kThreads, smem, stream>>>(P);
   TVM_CHECK_CUDA(cudaGetLastError());
