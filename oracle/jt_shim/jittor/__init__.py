@@ -175,6 +175,8 @@ def flip(x, dim=0):
     return torch.flip(x, [dim] if isinstance(dim, int) else list(dim))
 
 
+float32 = torch.float32
+int64 = torch.int64
 asin = torch.asin
 multiply = torch.mul
 zeros_like = torch.zeros_like
