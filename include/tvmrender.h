@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define TVM_ABI_VERSION 7
+#define TVM_ABI_VERSION 8
 
 /* flags for tvm_forward / tvm_backward */
 #define TVM_WHITE_BG      0x1u  /* rgb_map += 1 - acc_map          (tensorBase.py:523-524) */
@@ -236,6 +236,45 @@ int tvm_density_alpha(const TvmModel* m_host, const float* xyz, int n_pts, float
 /* MSE loss head of train.py:228: loss = mean((rgb_map - target)^2), d_rgb_map = 2 (rgb_map - target) / (3 n) * scale */
 int tvm_mse_loss(const float* rgb_map, const float* target, int n_rays, float grad_scale,
                  float* loss_out, float* d_rgb_map, void* stream);
+
+/* ---- callers either side of the ray path ------------------------------------------------- */
+/* TensorBase.getDenseAlpha (tensorBase.py:366-384) on a lattice of grid_host = {Gx, Gy, Gz} nodes spanning the model aabb:
+ * alpha = compute_alpha(node, length), clamped to [0,1] and written transposed as updateAlphaMask wants it, [Gz][Gy][Gx].   */
+int tvm_dense_alpha(const TvmModel* m_host, const int32_t* grid_host, float length, float* alpha_zyx, void* stream);
+/* TensorBase.updateAlphaMask (tensorBase.py:386-409) after getDenseAlpha: max_pool3d(k=3, pad=1), >= thres -> {0,1};
+ * bits_out = bit-packed volume (layout of tvm_pack_alpha), volume_out = the same as fp32 [Gz][Gy][Gx] or NULL,
+ * bbox_idx[6] = {min x,y,z, max x,y,z} voxel indices of the set voxels ({INT_MAX.., -1..} when none), n_set = their count. */
+int tvm_alpha_mask_from_dense(const float* alpha_zyx, const int32_t* grid_host, float thres, float* volume_out,
+                              uint32_t* bits_out, int32_t* bbox_idx, uint64_t* n_set, void* stream);
+/* TensorBase.filtering_rays (tensorBase.py:411-441): mask_out[i] = 1 iff ray i is kept.  bbox_only: t_max > t_min of the slab
+ * test (:424-429); else any of n_samples uniform samples has sample_alpha > 0 (:432-433; no bbox gate, as the reference).      */
+int tvm_filter_rays(const TvmModel* m_host, const float* rays, int n_rays, int n_samples, int bbox_only,
+                    uint8_t* mask_out, void* stream);
+/* get_ray_directions / get_ray_directions_blender + get_rays (dataLoader/ray_utils.py:81-153), optional unit
+ * normalisation of the camera-space direction (dataLoader/blender.py:75); c2w_host is a HOST [3][4] matrix; rays_out [H*W][6]. */
+int tvm_generate_rays(const float* c2w_host, int H, int W, float fx, float fy, float cx, float cy, int blender,
+                      int normalize, float* rays_out, void* stream);
+/* up_sampling_VM (tensoRF.py:248-262): F.interpolate(bilinear, align_corners=True) of one NCHW grid [C][H][W] -> [C][H2][W2]   */
+int tvm_upsample_grid(const float* src_nchw, int C, int H, int W, float* dst_nchw, int H2, int W2, void* stream);
+
+/* Regularisers of train.py:233-251, value and gradient in one pass: *loss_accum += weight * f(x) (device scalar, may be NULL),
+ * grad += weight * df/dx (same shape as x, may be NULL).  TVLoss (utils.py:123-142) of one plane [1][C][H][W];
+ * density_L1's mean |x| (tensoRF.py:191-195); vectorDiffs (tensoRF.py:177-186) of one line [1][C][L][1].                        */
+int tvm_tv_loss(const float* plane_nchw, int C, int H, int W, float weight, float* loss_accum, float* grad_nchw, void* stream);
+int tvm_l1_loss(const float* x, size_t n, float weight, float* loss_accum, float* grad, void* stream);
+int tvm_vector_diffs(const float* line_cl, int C, int L, float weight, float* loss_accum, float* grad, void* stream);
+/* jt.optim.Adam.step (train.py:187,261) over n_tensors parameter tensors in one launch per TVM_ADAM_MAX_TENSORS:
+ * m = b0 m + (1-b0) g; v = b1 v + (1-b1) g^2; p -= m * (lr sqrt(1-b1^step)/(1-b0^step)) / (sqrt(v) + eps); step is 1-based.    */
+#define TVM_ADAM_MAX_TENSORS 32
+typedef struct TvmAdamTensor {
+  float* p;          /* parameter (updated in place)  */
+  const float* g;    /* gradient                      */
+  float* m;          /* first moment                  */
+  float* v;          /* second moment                 */
+  size_t n;          /* elements                      */
+  float lr;          /* learning rate of its group    */
+} TvmAdamTensor;
+int tvm_adam_step(const TvmAdamTensor* tensors_host, int n_tensors, float beta0, float beta1, float eps, int step, void* stream);
 
 /* ---- measurement hooks (bench.py's roofline leg; off by default) ------------------------------ */
 /* When enabled, every kernel tvm_forward / tvm_backward launches is bracketed by cudaEvents on the

@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libtvmrender.so")
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 # flags (tvmrender.h)
 WHITE_BG = 0x1
@@ -58,6 +58,13 @@ class TvmBgNet(C.Structure):
                                            "wv_t", "w_rgb", "b_rgb", "tc_weights")]
 
 
+class TvmAdamTensor(C.Structure):
+    _fields_ = [("p", C.c_void_p), ("g", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p), ("n", C.c_size_t), ("lr", C.c_float)]
+
+
+ADAM_MAX_TENSORS = 32
+
+
 class TvmGrads(C.Structure):
     _fields_ = [("density_plane", _p3), ("density_line", _p3), ("app_plane", _p3), ("app_line", _p3),
                 ("basis_t", C.c_void_p), ("w1_t", C.c_void_p), ("b1", C.c_void_p), ("w2_t", C.c_void_p),
@@ -69,6 +76,8 @@ EXPORTS = [
     "tvm_pack_linear", "tvm_unpack_linear", "tvm_pack_alpha", "tvm_pack_alpha_bricks", "tvm_tc_weights_bytes", "tvm_pack_mlp_tc",
     "tvm_workspace_bytes", "tvm_forward", "tvm_forward_npp", "tvm_bg_fold", "tvm_bg_tc_bytes", "tvm_pack_bg_tc", "tvm_backward", "tvm_density_alpha", "tvm_mse_loss",
     "tvm_profile_enable", "tvm_profile_collect",
+    "tvm_dense_alpha", "tvm_alpha_mask_from_dense", "tvm_filter_rays", "tvm_generate_rays", "tvm_upsample_grid",
+    "tvm_tv_loss", "tvm_l1_loss", "tvm_vector_diffs", "tvm_adam_step",
 ]
 
 
@@ -113,6 +122,17 @@ def load() -> C.CDLL:
     lib.tvm_forward_npp.argtypes = [C.POINTER(TvmModel), C.POINTER(TvmBgNet), vp, i32, i32, vp, vp, u32, vp, vp,
                                     C.POINTER(TvmAux), vp, vp, C.c_size_t, vp]
     lib.tvm_bg_fold.argtypes = [vp] * 8
+    lib.tvm_pack_bg_tc.argtypes = [C.POINTER(TvmBgNet), vp, vp]
+    i3 = C.POINTER(C.c_int32)
+    lib.tvm_dense_alpha.argtypes = [C.POINTER(TvmModel), i3, f32, vp, vp]
+    lib.tvm_alpha_mask_from_dense.argtypes = [vp, i3, f32, vp, vp, vp, vp, vp]
+    lib.tvm_filter_rays.argtypes = [C.POINTER(TvmModel), vp, i32, i32, i32, vp, vp]
+    lib.tvm_generate_rays.argtypes = [C.POINTER(C.c_float), i32, i32, f32, f32, f32, f32, i32, i32, vp, vp]
+    lib.tvm_upsample_grid.argtypes = [vp, i32, i32, i32, vp, i32, i32, vp]
+    lib.tvm_tv_loss.argtypes = [vp, i32, i32, i32, f32, vp, vp, vp]
+    lib.tvm_l1_loss.argtypes = [vp, C.c_size_t, f32, vp, vp, vp]
+    lib.tvm_vector_diffs.argtypes = [vp, i32, i32, f32, vp, vp, vp]
+    lib.tvm_adam_step.argtypes = [C.POINTER(TvmAdamTensor), i32, f32, f32, f32, i32, vp]
     lib.tvm_backward.argtypes = [C.POINTER(TvmModel), vp, i32, i32, vp, u32, vp, vp, C.POINTER(TvmGrads), vp,
                                  C.c_size_t, vp]
     lib.tvm_density_alpha.argtypes = [C.POINTER(TvmModel), vp, i32, f32, vp, vp]

@@ -1,0 +1,185 @@
+// Training-step remainder: the whole-grid passes that follow the ray path in train.py:233-261.
+// Each regulariser kernel produces the loss value AND adds its gradient in one sweep over the NCHW parameter, so the
+// step reads every grid once instead of Jittor's forward + backward graph.  References relative to tensorf-myc/:
+//
+//   k_tv_loss        utils.TVLoss.execute (utils.py:123-142) as used by TV_loss_density / TV_loss_app (models/tensoRF.py:197-207)
+//   k_l1_loss        density_L1 (models/tensoRF.py:191-195): mean |x|
+//   k_vector_diffs   vectorDiffs (models/tensoRF.py:177-186): mean |off-diagonal of V V^T|
+//   k_adam_multi     jt.optim.Adam(betas=(0.9, 0.99)).step over every parameter tensor in ONE launch (train.py:187,260-261;
+//                    update rule: assumption A11 of oracle/maintain_oracle.py)
+#include "tvm_common.cuh"
+
+namespace tvm {
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = 0.0f;
+  if (warp == 0) {
+    t = lane < (int)(blockDim.x >> 5) ? red[lane] : 0.0f;
+    t = warp_sum(t);
+  }
+  __syncthreads();
+  return t;       // valid in warp 0
+}
+
+// x [C][H][W]; loss += scale_h * sum dh^2 + scale_w * sum dw^2; grad += d loss / d x
+__global__ void __launch_bounds__(256) k_tv_loss(const float* __restrict__ x, int C, int H, int W, float scale_h,
+                                                 float scale_w, float* __restrict__ loss, float* __restrict__ grad) {
+  __shared__ float red[8];
+  const size_t total = (size_t)C * H * W;
+  float part = 0.0f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int xx = (int)(i % W), yy = (int)((i / W) % H);
+    const float c = x[i];
+    const float dn = yy + 1 < H ? x[i + W] - c : 0.0f;       // x[y+1] - x[y]
+    const float rt = xx + 1 < W ? x[i + 1] - c : 0.0f;       // x[x+1] - x[x]
+    part += scale_h * dn * dn + scale_w * rt * rt;
+    if (grad) {
+      const float up = yy > 0 ? c - x[i - W] : 0.0f;
+      const float lf = xx > 0 ? c - x[i - 1] : 0.0f;
+      grad[i] += 2.0f * (scale_h * (up - dn) + scale_w * (lf - rt));
+    }
+  }
+  const float t = block_sum(part, red);
+  if (threadIdx.x == 0 && loss) atomicAdd(loss, t);
+}
+
+__global__ void __launch_bounds__(256) k_l1_loss(const float* __restrict__ x, size_t n, float scale, float* __restrict__ loss,
+                                                 float* __restrict__ grad) {
+  __shared__ float red[8];
+  float part = 0.0f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    part += fabsf(v);
+    if (grad) grad[i] += v > 0.0f ? scale : (v < 0.0f ? -scale : 0.0f);
+  }
+  const float t = block_sum(part, red);
+  if (threadIdx.x == 0 && loss) atomicAdd(loss, scale * t);
+}
+
+// v [C][L] (C <= 64); one CTA.  loss += scale * sum_{i != j} |<v_i, v_j>|, grad_i += 2 scale sum_{j != i} sign(<v_i, v_j>) v_j
+__global__ void __launch_bounds__(256) k_vector_diffs(const float* __restrict__ v, int C, int L, float scale,
+                                                      float* __restrict__ loss, float* __restrict__ grad) {
+  __shared__ float sgn[64 * 64];
+  __shared__ float red[8];
+  float part = 0.0f;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int pr = warp; pr < C * C; pr += 8) {         // one warp per (i, j) dot product
+    const int i = pr / C, j = pr % C;
+    float d = 0.0f;
+    for (int l = lane; l < L; l += 32) d = fmaf(v[(size_t)i * L + l], v[(size_t)j * L + l], d);
+    d = warp_sum(d);
+    if (lane == 0) {
+      sgn[pr] = (i == j) ? 0.0f : (d > 0.0f ? 1.0f : (d < 0.0f ? -1.0f : 0.0f));
+      if (i != j) part += fabsf(d);
+    }
+  }
+  const float t = block_sum(part, red);          // includes the __syncthreads that publishes sgn
+  if (threadIdx.x == 0 && loss) atomicAdd(loss, scale * t);
+  if (!grad) return;
+  for (int e = threadIdx.x; e < C * L; e += blockDim.x) {
+    const int i = e / L, l = e % L;
+    float g = 0.0f;
+    for (int j = 0; j < C; ++j) g = fmaf(sgn[i * C + j], v[(size_t)j * L + l], g);
+    grad[e] += 2.0f * scale * g;
+  }
+}
+
+// ---- Adam over up to TVM_ADAM_MAX_TENSORS tensors in one launch --------------------------------------------------------------
+struct AdamTable {
+  TvmAdamTensor t[TVM_ADAM_MAX_TENSORS];
+  unsigned first_block[TVM_ADAM_MAX_TENSORS + 1];      // blocks [first_block[k], first_block[k+1]) belong to tensor k
+  int n;
+  float b0, b1, eps, c_step;                           // c_step = sqrt(1 - b1^n) / (1 - b0^n)
+};
+constexpr int kAdamPerBlock = 256 * 16;
+
+__global__ void __launch_bounds__(256) k_adam_multi(const AdamTable T) {
+  int k = 0;
+  while (k + 1 < T.n && blockIdx.x >= T.first_block[k + 1]) ++k;
+  const TvmAdamTensor t = T.t[k];
+  const size_t base = (size_t)(blockIdx.x - T.first_block[k]) * kAdamPerBlock;
+  const float step_size = t.lr * T.c_step;
+  const bool vec = ((((uintptr_t)t.p | (uintptr_t)t.g | (uintptr_t)t.m | (uintptr_t)t.v) & 15) == 0);
+  auto upd = [&](float& p, float g, float& m, float& v) {
+    m = T.b0 * m + (1.0f - T.b0) * g;
+    v = T.b1 * v + (1.0f - T.b1) * g * g;
+    p = p - m * step_size / (sqrtf(v) + T.eps);
+  };
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const size_t i = base + ((size_t)it * 256 + threadIdx.x) * 4;
+    if (i >= t.n) break;
+    if (vec && i + 4 <= t.n) {
+      float4 p = *reinterpret_cast<float4*>(t.p + i), m = *reinterpret_cast<float4*>(t.m + i),
+             v = *reinterpret_cast<float4*>(t.v + i);
+      const float4 g = *reinterpret_cast<const float4*>(t.g + i);
+      upd(p.x, g.x, m.x, v.x); upd(p.y, g.y, m.y, v.y); upd(p.z, g.z, m.z, v.z); upd(p.w, g.w, m.w, v.w);
+      *reinterpret_cast<float4*>(t.p + i) = p;
+      *reinterpret_cast<float4*>(t.m + i) = m;
+      *reinterpret_cast<float4*>(t.v + i) = v;
+    } else {
+      for (size_t j = i; j < i + 4 && j < t.n; ++j) upd(t.p[j], t.g[j], t.m[j], t.v[j]);
+    }
+  }
+}
+
+static int stream_grid(size_t total) {
+  size_t b = (total + 255) / 256;
+  const size_t cap = 148 * 8;
+  return (int)(b < cap ? (b ? b : 1) : cap);
+}
+
+}  // namespace tvm
+
+using namespace tvm;
+
+extern "C" int tvm_tv_loss(const float* plane_nchw, int C, int H, int W, float weight, float* loss_accum, float* grad_nchw,
+                           void* stream) {
+  TVM_REQUIRE(plane_nchw && C > 0 && H > 0 && W > 0, "bad arguments");
+  // TVLoss (batch 1): weight * 2 * (h_tv / count_h + w_tv / count_w), count_h = C (H-1) W, count_w = C H (W-1)
+  const double ch = (double)C * (H - 1) * W, cw = (double)C * H * (W - 1);
+  const float sh = ch > 0 ? (float)(2.0 * weight / ch) : 0.0f, sw = cw > 0 ? (float)(2.0 * weight / cw) : 0.0f;
+  k_tv_loss<<<stream_grid((size_t)C * H * W), 256, 0, (cudaStream_t)stream>>>(plane_nchw, C, H, W, sh, sw, loss_accum, grad_nchw);
+  TVM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tvm_l1_loss(const float* x, size_t n, float weight, float* loss_accum, float* grad, void* stream) {
+  TVM_REQUIRE(x && n > 0, "bad arguments");
+  k_l1_loss<<<stream_grid(n), 256, 0, (cudaStream_t)stream>>>(x, n, (float)(weight / (double)n), loss_accum, grad);
+  TVM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tvm_vector_diffs(const float* line_cl, int C, int L, float weight, float* loss_accum, float* grad, void* stream) {
+  TVM_REQUIRE(line_cl && C > 1 && C <= 64 && L > 0, "vector_diffs supports 2..64 components");
+  k_vector_diffs<<<1, 256, 0, (cudaStream_t)stream>>>(line_cl, C, L, (float)(weight / ((double)C * (C - 1))), loss_accum, grad);
+  TVM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tvm_adam_step(const TvmAdamTensor* tensors_host, int n_tensors, float beta0, float beta1, float eps, int step,
+                             void* stream) {
+  TVM_REQUIRE(tensors_host && n_tensors > 0 && step >= 1, "bad arguments");
+  for (int s0 = 0; s0 < n_tensors; s0 += TVM_ADAM_MAX_TENSORS) {
+    AdamTable T;
+    T.n = n_tensors - s0 < TVM_ADAM_MAX_TENSORS ? n_tensors - s0 : TVM_ADAM_MAX_TENSORS;
+    unsigned blocks = 0;
+    for (int k = 0; k < T.n; ++k) {
+      T.t[k] = tensors_host[s0 + k];
+      TVM_REQUIRE(T.t[k].p && T.t[k].g && T.t[k].m && T.t[k].v && T.t[k].n > 0, "null / empty Adam tensor");
+      T.first_block[k] = blocks;
+      blocks += (unsigned)((T.t[k].n + kAdamPerBlock - 1) / kAdamPerBlock);
+    }
+    T.first_block[T.n] = blocks;
+    T.b0 = beta0; T.b1 = beta1; T.eps = eps;
+    T.c_step = (float)(sqrt(1.0 - pow((double)beta1, step)) / (1.0 - pow((double)beta0, step)));
+    k_adam_multi<<<blocks, 256, 0, (cudaStream_t)stream>>>(T);
+    TVM_CHECK_CUDA(cudaGetLastError());
+  }
+  return 0;
+}

@@ -16,6 +16,8 @@ import numpy as np
 import torch
 
 from . import _lib as L
+from .maintain import MaintainMixin
+from .train_ops import RegularizerMixin
 
 MAT_MODE = [[0, 1], [0, 2], [1, 2]]   # tensorBase.py:168
 VEC_MODE = [2, 1, 0]                  # tensorBase.py:169
@@ -49,7 +51,7 @@ def _ptr(t):
 class AlphaGridMask:
     """tensorBase.py:39-59.  Keeps the reference's float volume view and a bit-packed device copy."""
 
-    def __init__(self, device, aabb, alpha_volume):
+    def __init__(self, device, aabb, alpha_volume, packed_bits=None):
         self.device = device
         self.aabb = torch.as_tensor(np.asarray(aabb.detach().cpu() if torch.is_tensor(aabb) else aabb),
                                     dtype=torch.float32).reshape(2, 3)
@@ -61,10 +63,14 @@ class AlphaGridMask:
         D, H, W = self.alpha_volume.shape[-3:]
         self.gridSize = torch.tensor([W, H, D], dtype=torch.int32)
         n_words = (D * H * W + 31) // 32
-        self.bits = torch.empty(n_words + 8, dtype=torch.int32, device=device)
         lib = L.load()
-        L.check(lib.tvm_pack_alpha(_ptr(self.alpha_volume), D, H, W, _ptr(self.bits), _stream_ptr()),
-                "tvm_pack_alpha")
+        if packed_bits is not None:          # updateAlphaMask already produced the bit stream (tvm_alpha_mask_from_dense)
+            assert packed_bits.numel() >= n_words and packed_bits.dtype == torch.int32
+            self.bits = packed_bits
+        else:
+            self.bits = torch.empty(n_words + 8, dtype=torch.int32, device=device)
+            L.check(lib.tvm_pack_alpha(_ptr(self.alpha_volume), D, H, W, _ptr(self.bits), _stream_ptr()),
+                    "tvm_pack_alpha")
         n_bricks = ((D + 7) // 8) * ((H + 7) // 8) * ((W + 7) // 8)
         self.bricks = torch.empty((n_bricks + 31) // 32 + 8, dtype=torch.int32, device=device)
         L.check(lib.tvm_pack_alpha_bricks(_ptr(self.bits), D, H, W, _ptr(self.bricks), _stream_ptr()),
@@ -113,7 +119,7 @@ class _RenderFn(torch.autograd.Function):
         return (None, None, None, None, None, *grads)
 
 
-class TensorVMSplit(torch.nn.Module):
+class TensorVMSplit(MaintainMixin, RegularizerMixin, torch.nn.Module):
     VARIANT = L.VARIANT_VM
 
     def __init__(self, aabb, gridSize, device, density_n_comp=8, appearance_n_comp=24, app_dim=27,
@@ -326,6 +332,11 @@ class TensorVMSplit(torch.nn.Module):
         Ca = self.app_n_comp[0]
         L.check(lib.tvm_pack_linear(_ptr(self.basis_mat.weight.detach()), self.app_dim, 3 * Ca, 32, at("basis_t"), st),
                 "tvm_pack_linear")
+
+    def _invalidate_packed(self):
+        """Grids were replaced (upsample / shrink): force a re-pack and a fresh TvmModel."""
+        self._packed_versions = None
+        self._model_struct = None
 
     def _model(self):
         """The TvmModel descriptor (host POD) for the current parameters / mask."""
