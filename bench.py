@@ -48,7 +48,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-chunks", type=int, default=256,
                     help="chunks of 1024 rays the CPU baseline renders (256 = 41%% of the frame, 10-30 s of CPU work)")
-    ap.add_argument("--workload", default="frame", choices=["frame", "train", "npp", "ref"],
+    ap.add_argument("--workload", default="frame", choices=["frame", "train", "npp", "ref", "maintain"],
                     help="frame = BASELINE configs[1] (the contract line); train = configs[2] (4096-ray fwd+bwd step, "
                          "128^3 grid); npp / ref = configs[3] (NeRF++ background / Ref-NeRF appearance, full frame). "
                          "The non-default workloads print the same JSON shape for profiles/, not for the driver.")
@@ -174,6 +174,90 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def run_maintain(args):
+    """SURVEY §8f rows at BASELINE sizes (300^3 grids, 200^3 alpha lattice, 800x800 frame): per-call device time through the
+    reference-named host methods and the HBM fraction of each kernel's algorithmic bytes."""
+    import jittor_myc_nerfs_b200 as pkg
+    from oracle import fixtures as fx
+    pkg._lib.require_cuda()
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    G = args.grid
+    mp = fx.make_model(G, density_shift=-3.0, grid_scale=0.5)
+    model = pkg.model_from_params(mp, "cuda:0", fx.ball_alpha_volume(MASK_RES), mp.aabb.copy(), "fp32")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    hbm, _ = peaks()
+
+    def timed(fn, reps=args.steps):
+        fn()
+        ms = 0.0
+        for _ in range(reps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ms += a.elapsed_time(b)
+        return ms / reps
+
+    rows = {}
+
+    def row(name, ms, nbytes, note):
+        rows[name] = {"ms": ms, "algorithmic_GB": nbytes / 1e9, "GBps": nbytes / (ms * 1e-3) / 1e9,
+                      "hbm_frac": nbytes / (ms * 1e-3) / 1e9 / hbm, "note": note}
+
+    nvox = MASK_RES ** 3
+    ms = timed(lambda: model.updateAlphaMask((MASK_RES,) * 3))
+    row("updateAlphaMask_200^3", ms, nvox * (1152.0 + 4 + 4 * 27 + 4 + 0.125),
+        "per lattice node: 1152 B of density taps + alpha write + 27-tap pool read + volume write + 1 bit")
+    model.alphaMask = pkg.AlphaGridMask(dev, mp.aabb, fx.ball_alpha_volume(MASK_RES))
+    model._model_struct = None
+    rays = pkg.get_rays_frame(fx.camera_pose(0.7, 0.5), FRAME, FRAME, 0.5 * FRAME / np.tan(0.5 * 0.6911))
+    rgbs = torch.zeros((rays.shape[0], 3), device=dev)
+    n = rays.shape[0]
+    ms = timed(lambda: pkg.get_rays_frame(fx.camera_pose(0.7, 0.5), FRAME, FRAME, 0.5 * FRAME / np.tan(0.5 * 0.6911)))
+    row("get_rays_800x800", ms, n * 24.0, "24 B written per ray")
+    ms = timed(lambda: model.filtering_mask(rays, bbox_only=True))
+    row("filtering_rays_bbox_only", ms, n * 25.0, "24 B ray + 1 B mask")
+    ms = timed(lambda: model.filtering_mask(rays, N_samples=256))
+    row("filtering_rays_alpha_256", ms, n * (25.0 + 256), "24 B ray + 1 B mask + 256 samples x 8 one-bit taps")
+    ms = timed(lambda: model.filtering_rays(rays, rgbs, N_samples=256))
+    row("filtering_rays_alpha_256_with_compaction", ms, n * (25.0 + 256 + 2 * 36), "as above + torch boolean compaction of rays/rgbs")
+    tv = pkg.TVLoss()
+    nd, na = 3 * 16 * G * G, 3 * 48 * G * G
+
+    def tv_step():
+        for p in model.parameters():
+            p.grad = None
+        (model.TV_loss_density(tv) + model.TV_loss_app(tv)).backward()
+    ms = timed(tv_step)
+    row("TV_loss_density+app_value_and_grad", ms, (nd + na) * 4.0 * 4, "read x, write fused grad, autograd scale + accumulate into .grad")
+    opt = pkg.Adam(model.get_optparam_groups(0.02, 0.001), betas=(0.9, 0.99))
+    for p in model.parameters():
+        p.grad = torch.ones_like(p)
+    npar = sum(p.numel() for p in model.parameters())
+    ms = timed(lambda: opt.step())
+    row("Adam_step_all_parameters", ms, npar * 4.0 * 7, "read p,g,m,v + write p,m,v")
+    m128 = pkg.model_from_params(fx.make_model(128), "cuda:0", None, None, "fp32")
+
+    def up():
+        m128.upsample_volume_grid((G, G, G))
+        m128.gridSize = torch.tensor([128] * 3, dtype=torch.int32)
+    planes = [(p.detach().clone(), l.detach().clone()) for p, l in zip(m128.density_plane, m128.density_line)]
+    src = {k: [t.detach().clone() for t in getattr(m128, k)] for k in ("density_plane", "density_line", "app_plane", "app_line")}
+
+    def up_fresh():
+        for k, v in src.items():
+            setattr(m128, k, torch.nn.ParameterList([torch.nn.Parameter(t) for t in v]))
+        m128.upsample_volume_grid((G, G, G))
+    ms = timed(up_fresh)
+    row("upsample_volume_grid_128_to_%d" % G, ms, (nd + na) * 4.0 + 3 * 64 * 128 * 128 * 4.0, "write new planes + read old ones")
+    print(json.dumps({"metric": "SURVEY 8f rows, device ms per call", "unit": "ms", "n_gpus": 1, "steps": args.steps,
+                      "config": {"workload": f"maintain: {G}^3 grids, {MASK_RES}^3 alpha lattice, {FRAME}x{FRAME} frame",
+                                 "l2": "flushed before every timed call"}, "hbm_peak_GBps": hbm, "rows": rows}))
+
+
 def run_side_workload(args):
     """configs[2] (training step) and configs[3] (variants, full frame): same timing rules as the contract
     line (warm-up >= 3, L2 flushed before every timed step, CUDA events on the launching stream)."""
@@ -207,13 +291,23 @@ def run_side_workload(args):
         g = torch.Generator(device=dev).manual_seed(fx.SEED_BASE)
         extra = dict(fg_rand=torch.rand((n, S), device=dev, generator=g), bg_rand=torch.rand((n, 512), device=dev, generator=g))
 
+    full = {"on": False}
+    if train:
+        # train.py:187 optimiser and the regulariser weights of configs/Scar.txt:38-39 (TV 2.0 / 2.0; L1 and ortho are 0 there)
+        opt = pkg.Adam(model.get_optparam_groups(0.02, 0.001), betas=(0.9, 0.99))
+        tvreg = pkg.TVLoss()
+
     def step():
         if train:
             for p in model.parameters():
                 p.grad = None
             rgb, _ = model(rays, is_train=True, white_bg=True, N_samples=S, jitter=jit)
             loss = torch.mean((rgb - tgt) ** 2)
+            if full["on"]:
+                loss = loss + model.TV_loss_density(tvreg) * 2.0 + model.TV_loss_app(tvreg) * 2.0
             loss.backward()
+            if full["on"]:
+                opt.step()
             return loss
         with torch.no_grad():
             if args.workload == "npp":
@@ -259,6 +353,16 @@ def run_side_workload(args):
             "gpu_launches": int(sum(stage_cnt.values())), "clocks": clk.summary(),
             "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items() if v},
             "stage_launches_per_step": {k: v / args.steps for k, v in stage_cnt.items() if v}}
+    if train:
+        # the whole optimisation step of train.py:218-261: + TV regularisers (fused value+grad sweeps) + multi-tensor Adam
+        # + re-pack of the updated parameters on the next forward
+        full["on"] = True
+        for _ in range(3):
+            step()
+        ms_full = timed(args.steps)
+        line["full_step"] = {"ms_per_step": ms_full / args.steps, "rays_per_s": n / (ms_full / args.steps * 1e-3),
+                             "includes": "fwd + bwd + TV_loss_density + TV_loss_app (weights 2.0, configs/Scar.txt) + Adam over "
+                                         "all parameter tensors + re-pack of the updated grids"}
     if args.workload == "npp" and stage_ms.get("bg"):
         # dense FLOPs of the background network as issued on the tensor cores (padded K/N), per sample
         flop = 2.0 * 128 * (32 + 144 + 160) + 2.0 * 128 * 80 + 2.0 * 64 * 16
@@ -272,6 +376,8 @@ def run_side_workload(args):
 
 def main():
     args = parse()
+    if args.workload == "maintain":
+        return run_maintain(args)
     if args.workload != "frame":
         return run_side_workload(args)
     if args.impl == "reference":

@@ -276,6 +276,11 @@ typedef struct TvmAdamTensor {
 } TvmAdamTensor;
 int tvm_adam_step(const TvmAdamTensor* tensors_host, int n_tensors, float beta0, float beta1, float eps, int step, void* stream);
 
+/* Known-answer self-test of the tcgen05 shared-memory descriptor conventions (K-major and MN-major reads of one image);
+ * P [128][128], Q [128][160], W [128][128] fp32 -> D1 = P^T Q [128][160], D2 = P W [128][128], D3 = P W^T [128][128].
+ * Test hook: no reference counterpart.                                                                              */
+int tvm_selftest_umma(const float* P, const float* Q, const float* W, float* D1, float* D2, float* D3, void* stream);
+
 /* ---- measurement hooks (bench.py's roofline leg; off by default) ------------------------------ */
 /* When enabled, every kernel tvm_forward / tvm_backward launches is bracketed by cudaEvents on the
  * caller's stream.  Stages: see TVM_STAGE_*.  Process-global, not thread-safe: benchmarking only. */

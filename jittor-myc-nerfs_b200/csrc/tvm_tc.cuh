@@ -86,6 +86,10 @@ __host__ __device__ constexpr uint32_t instr_desc(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// operand read "transposed" (MN-major): the reduction index runs over the image ROWS; LBO = 128, SBO = rows * 16
+constexpr uint32_t kIdescAMajorMN = 1u << 15;
+constexpr uint32_t kIdescBMajorMN = 1u << 16;
+
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);

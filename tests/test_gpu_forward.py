@@ -235,3 +235,21 @@ def test_nerfplusplus_variant(env):
         print(f"NeRF++ {regime} bf16/tcgen05: max|bg_rgb-oracle|={e_bg:.3e}, max|rgb-oracle|={e_rgb:.3e}")
         assert e_bg <= 1e-2 and e_rgb <= 1e-2
         model.mlp_mode = "fp32"
+
+
+def test_umma_descriptor_conventions(env):
+    """tcgen05 known-answer test: K-major and MN-major ("transposed") reads of one core-matrix image."""
+    pkg, torch, fx, orc = env
+    import ctypes as C
+    lib = pkg._lib.load()
+    g = torch.Generator().manual_seed(5)
+    mk = lambda *s: (torch.randint(-8, 9, s, generator=g).float() / 8.0).cuda()      # exactly representable in bf16
+    P, Q, W = mk(128, 128), mk(128, 160), mk(128, 128)
+    D1, D2, D3 = torch.zeros(128, 160).cuda(), torch.zeros(128, 128).cuda(), torch.zeros(128, 128).cuda()
+    p = lambda t: C.c_void_p(t.data_ptr())
+    pkg._lib.check(lib.tvm_selftest_umma(p(P), p(Q), p(W), p(D1), p(D2), p(D3),
+                                         C.c_void_p(torch.cuda.current_stream().cuda_stream)), "tvm_selftest_umma")
+    torch.cuda.synchronize()
+    assert torch.equal(D3, P @ W.T), "K-major (forward) convention"
+    assert torch.equal(D2, P @ W), "MN-major B operand"
+    assert torch.equal(D1, P.T @ Q), "MN-major A and B operands"
