@@ -273,7 +273,7 @@ def run_side_workload(args):
     variant = {"npp": "npp", "ref": "ref"}.get(args.workload, "vm")
     mp = fx.make_model(G, density_shift=reg["density_shift"], variant=variant)
     vol = fx.ball_alpha_volume(MASK_RES if G > 128 else 128) if reg["mask"] else None
-    model = pkg.model_from_params(mp, "cuda:0", vol, mp.aabb.copy(), "fp32" if train else args.mlp)
+    model = pkg.model_from_params(mp, "cuda:0", vol, mp.aabb.copy(), args.mlp)
     if train:
         n = 4096 if args.rays == FRAME * FRAME else args.rays
         rays_np = fx.subset_rays(n)
@@ -339,13 +339,13 @@ def run_side_workload(args):
     stage_ms, stage_cnt = L.profile_collect()
     L.profile_enable(False)
     cnt = model.counters.cpu().numpy().astype(np.float64) / args.steps
-    name = {"train": f"configs[2]: training step fwd+bwd (MSE), {n} rays, {G}^3 grid, S={S}, fp32",
+    name = {"train": f"configs[2]: training step fwd+bwd (MSE), {n} rays, {G}^3 grid, S={S}, mlp {args.mlp}",
             "npp": f"configs[3]: NerfPlusPlus full frame ({n} rays), {G}^3 grid, 512 background samples/ray",
             "ref": f"configs[3]: REFTensoRF full frame ({n} rays), {G}^3 grid"}[args.workload]
     line = {"metric": f"TensoRF-VM rays/sec ({args.workload})", "value": n / (ms / args.steps * 1e-3), "unit": UNIT,
             "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if train or args.mlp == "fp32" else f"f32 + {args.mlp} tensor-core MLP", "data": "synthetic",
+            "dtype": "f32" if args.mlp == "fp32" else f"f32 + {args.mlp} tensor-core MLP (forward and backward)", "data": "synthetic",
             "config": {"workload": name + f", regime {args.regime}", "n_samples": S,
                        "l2": "flushed before every timed step (256 MiB write)",
                        "per_step_counts": {"M_in": cnt[L.CNT_M_IN], "M_v_gathered": cnt[L.CNT_M_V], "M_a": cnt[L.CNT_M_A],

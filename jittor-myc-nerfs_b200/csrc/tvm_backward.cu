@@ -13,18 +13,9 @@
 //                product with ONE forward sweep (suffix sums = total - prefix), -> dL/dsigma -> softplus'
 //                -> scatter into density planes/lines with vector atomics
 #include "tvm_app_simt.cuh"
+#include "tvm_bwd.cuh"
 
 namespace tvm {
-
-struct BwdParams {
-  FwdParams f;
-  const float* d_rgb_map;
-  TvmGrads g;
-};
-
-__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
 
 // ------------------------------------------------------------------------------------------------
 __global__ void k_bwd_prep(const BwdParams B) {
@@ -481,6 +472,7 @@ __global__ void __launch_bounds__(kMarchWarps * 32) k_march_bwd(const BwdParams 
 
 int fill_fwd_params(FwdParams& P, const TvmModel* m, const float* rays, int n, int S, const float* jitter,
                     uint32_t flags, void* ws, size_t ws_bytes);   // tvm_forward.cu
+int launch_app_bwd_tc(const BwdParams& B, int num_sms, cudaStream_t stream);   // tvm_bwd_tc.cu
 
 }  // namespace tvm
 
@@ -503,10 +495,14 @@ extern "C" int tvm_backward(const TvmModel* m_host, const float* rays, int n_ray
 
   k_bwd_prep<<<(n_rays + 255) / 256, 256, 0, stream>>>(B);
   TVM_CHECK_CUDA(cudaGetLastError());
-  {
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if ((flags & TVM_MLP_MASK) == TVM_MLP_BF16) {
+    // appearance backward on the tensor cores (bf16 operands, fp32 accumulation; gradients to ~1e-2 relative)
+    ProfileScope prof(TVM_STAGE_BWD_APP, stream);
+    if (int rc = launch_app_bwd_tc(B, sms, stream)) return rc;
+  } else {
     const size_t smem = ((size_t)kAppTile * 4 * B.f.st + kAppTile * 4) * sizeof(float);
     TVM_REQUIRE(smem <= 220 * 1024, "appearance backward tile does not fit shared memory");
     TVM_CHECK_CUDA(cudaFuncSetAttribute(k_app_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

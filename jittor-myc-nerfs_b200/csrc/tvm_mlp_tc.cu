@@ -16,27 +16,6 @@
 
 namespace tvm {
 
-namespace tc {
-
-// Byte layout of the weight image built by tvm_pack_mlp_tc (copied verbatim into shared memory)
-struct Image {
-  int K0, K1, NH;                // padded reduction lengths of GEMM0 / GEMM1 (multiples of 16); GEMM0 width
-  uint32_t off_b0, off_b1, off_b2, off_f32, bytes;
-  // fp32 tail: b1[128] b2[128] w3[3][128] b3[4] head_bias[48]
-  __host__ __device__ Image(int n_app, int in_c, int nh) {
-    K0 = 3 * n_app;
-    K1 = (in_c + 15) / 16 * 16;
-    NH = nh;
-    off_b0 = 0;
-    off_b1 = off_b0 + (uint32_t)K0 * NH * 2;
-    off_b2 = off_b1 + (uint32_t)K1 * 128 * 2;
-    off_f32 = off_b2 + 128u * 128 * 2;
-    bytes = off_f32 + (128 + 128 + 3 * 128 + 4 + 48) * 4;
-  }
-};
-
-}  // namespace tc
-
 using namespace tc;
 
 namespace tc {
@@ -74,20 +53,6 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mlp_group_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
-
-// 16 more columns (REF heads live in basis columns 32..47)
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
 
 template <int CA, int APP_DIM, int FEA_PE, int VIEW_PE, bool REF>
 __global__ void __launch_bounds__(kThreadsV2, 1) k_app_tc(const FwdParams P) {

@@ -76,6 +76,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 32 lanes x 16 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // K-major, no swizzle: LBO = byte distance between K-adjacent core matrices, SBO = between 8-row groups
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) |
@@ -95,6 +109,23 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+
+// Byte layout of the weight image built by tvm_pack_mlp_tc (copied verbatim into shared memory)
+struct Image {
+  int K0, K1, NH;                // padded reduction lengths of GEMM0 / GEMM1 (multiples of 16); GEMM0 width
+  uint32_t off_b0, off_b1, off_b2, off_f32, bytes;
+  // fp32 tail: b1[128] b2[128] w3[3][128] b3[4] head_bias[48]
+  __host__ __device__ Image(int n_app, int in_c, int nh) {
+    K0 = 3 * n_app;
+    K1 = (in_c + 15) / 16 * 16;
+    NH = nh;
+    off_b0 = 0;
+    off_b1 = off_b0 + (uint32_t)K0 * NH * 2;
+    off_b2 = off_b1 + (uint32_t)K1 * 128 * 2;
+    off_f32 = off_b2 + 128u * 128 * 2;
+    bytes = off_f32 + (128 + 128 + 3 * 128 + 4 + 48) * 4;
+  }
+};
 
 // fp32 [K][ldw] (row j = input j) -> bf16 UMMA image [(K_pad/8)][N][8]; out-of-range entries are 0.
 // Image column k reads source row k for k < split, nothing for split <= k < split_pad, and row
