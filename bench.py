@@ -363,6 +363,24 @@ def run_side_workload(args):
         line["full_step"] = {"ms_per_step": ms_full / args.steps, "rays_per_s": n / (ms_full / args.steps * 1e-3),
                              "includes": "fwd + bwd + TV_loss_density + TV_loss_app (weights 2.0, configs/Scar.txt) + Adam over "
                                          "all parameter tensors + re-pack of the updated grids"}
+        # the same full step captured once into a CUDA graph (TrainStepGraph) and replayed: no host time between kernels
+        model.collect_counters = False
+        L.profile_enable(False)
+        gstep = pkg.TrainStepGraph(model, opt, n, S, white_bg=True, TV_weight_density=2.0, TV_weight_app=2.0)
+        gstep.step(rays, tgt)
+        torch.cuda.synchronize()
+        evs = []
+        for _ in range(args.steps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            gstep.step(rays, tgt)
+            b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        ms_graph = sum(a.elapsed_time(b) for a, b in evs) / args.steps
+        line["full_step_cuda_graph"] = {"ms_per_step": ms_graph, "rays_per_s": n / (ms_graph * 1e-3),
+                                        "includes": "as full_step, replayed as one CUDA graph (jitter drawn on the device)"}
     if args.workload == "npp" and stage_ms.get("bg"):
         # dense FLOPs of the background network as issued on the tensor cores (padded K/N), per sample
         flop = 2.0 * 128 * (32 + 144 + 160) + 2.0 * 128 * 80 + 2.0 * 64 * 16

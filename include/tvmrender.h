@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define TVM_ABI_VERSION 8
+#define TVM_ABI_VERSION 9
 
 /* flags for tvm_forward / tvm_backward */
 #define TVM_WHITE_BG      0x1u  /* rgb_map += 1 - acc_map          (tensorBase.py:523-524) */
@@ -264,7 +264,9 @@ int tvm_tv_loss(const float* plane_nchw, int C, int H, int W, float weight, floa
 int tvm_l1_loss(const float* x, size_t n, float weight, float* loss_accum, float* grad, void* stream);
 int tvm_vector_diffs(const float* line_cl, int C, int L, float weight, float* loss_accum, float* grad, void* stream);
 /* jt.optim.Adam.step (train.py:187,261) over n_tensors parameter tensors in one launch per TVM_ADAM_MAX_TENSORS:
- * m = b0 m + (1-b0) g; v = b1 v + (1-b1) g^2; p -= m * (lr sqrt(1-b1^step)/(1-b0^step)) / (sqrt(v) + eps); step is 1-based.    */
+ * m = b0 m + (1-b0) g; v = b1 v + (1-b1) g^2; p -= m * (lr sqrt(1-b1^step)/(1-b0^step)) / (sqrt(v) + eps); step is 1-based.
+ * hyper_dev (nullable): DEVICE array {sqrt(1-b1^step)/(1-b0^step), lr[0], lr[1], ...}; when given it overrides `step` and the
+ * tensors' `lr` with hyper_dev[0] and hyper_dev[1 + lr_index], so that a captured CUDA graph can be replayed with new values. */
 #define TVM_ADAM_MAX_TENSORS 32
 typedef struct TvmAdamTensor {
   float* p;          /* parameter (updated in place)  */
@@ -273,8 +275,10 @@ typedef struct TvmAdamTensor {
   float* v;          /* second moment                 */
   size_t n;          /* elements                      */
   float lr;          /* learning rate of its group    */
+  int32_t lr_index;  /* index of its group in hyper_dev */
 } TvmAdamTensor;
-int tvm_adam_step(const TvmAdamTensor* tensors_host, int n_tensors, float beta0, float beta1, float eps, int step, void* stream);
+int tvm_adam_step(const TvmAdamTensor* tensors_host, int n_tensors, float beta0, float beta1, float eps, int step,
+                  const float* hyper_dev, void* stream);
 
 /* Known-answer self-test of the tcgen05 shared-memory descriptor conventions (K-major and MN-major reads of one image);
  * P [128][128], Q [128][160], W [128][128] fp32 -> D1 = P^T Q [128][160], D2 = P W [128][128], D3 = P W^T [128][128].

@@ -4,9 +4,9 @@ from . import _lib
 from ._lib import TvmError, LIB_PATH
 from .tensorf import TensorVMSplit, REFTensoRF, NerfPlusPlus, AlphaGridMask, MLPRender_Fea, derive_march_scalars, unpack_bits, model_from_params
 from .renderer import OctreeRender_trilinear_fast
-from .train_ops import TVLoss, Adam
+from .train_ops import TVLoss, Adam, TrainStepGraph
 from .maintain import get_rays_frame
 from . import dist
 
 __all__ = ["TensorVMSplit", "REFTensoRF", "NerfPlusPlus", "AlphaGridMask", "MLPRender_Fea", "OctreeRender_trilinear_fast",
-           "derive_march_scalars", "unpack_bits", "model_from_params", "TvmError", "LIB_PATH", "TVLoss", "Adam", "get_rays_frame"]
+           "derive_march_scalars", "unpack_bits", "model_from_params", "TvmError", "LIB_PATH", "TVLoss", "Adam", "TrainStepGraph", "get_rays_frame"]

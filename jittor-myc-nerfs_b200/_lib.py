@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libtvmrender.so")
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 # flags (tvmrender.h)
 WHITE_BG = 0x1
@@ -59,7 +59,7 @@ class TvmBgNet(C.Structure):
 
 
 class TvmAdamTensor(C.Structure):
-    _fields_ = [("p", C.c_void_p), ("g", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p), ("n", C.c_size_t), ("lr", C.c_float)]
+    _fields_ = [("p", C.c_void_p), ("g", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p), ("n", C.c_size_t), ("lr", C.c_float), ("lr_index", C.c_int32)]
 
 
 ADAM_MAX_TENSORS = 32
@@ -133,7 +133,7 @@ def load() -> C.CDLL:
     lib.tvm_l1_loss.argtypes = [vp, C.c_size_t, f32, vp, vp, vp]
     lib.tvm_vector_diffs.argtypes = [vp, i32, i32, f32, vp, vp, vp]
     lib.tvm_selftest_umma.argtypes = [vp] * 7
-    lib.tvm_adam_step.argtypes = [C.POINTER(TvmAdamTensor), i32, f32, f32, f32, i32, vp]
+    lib.tvm_adam_step.argtypes = [C.POINTER(TvmAdamTensor), i32, f32, f32, f32, i32, vp, vp]
     lib.tvm_backward.argtypes = [C.POINTER(TvmModel), vp, i32, i32, vp, u32, vp, vp, C.POINTER(TvmGrads), vp,
                                  C.c_size_t, vp]
     lib.tvm_density_alpha.argtypes = [C.POINTER(TvmModel), vp, i32, f32, vp, vp]

@@ -94,6 +94,7 @@ struct AdamTable {
   unsigned first_block[TVM_ADAM_MAX_TENSORS + 1];      // blocks [first_block[k], first_block[k+1]) belong to tensor k
   int n;
   float b0, b1, eps, c_step;                           // c_step = sqrt(1 - b1^n) / (1 - b0^n)
+  const float* hyper;                                  // device {c_step, lr[...]} overriding the host values (graph replay)
 };
 constexpr int kAdamPerBlock = 256 * 16;
 
@@ -102,7 +103,7 @@ __global__ void __launch_bounds__(256) k_adam_multi(const AdamTable T) {
   while (k + 1 < T.n && blockIdx.x >= T.first_block[k + 1]) ++k;
   const TvmAdamTensor t = T.t[k];
   const size_t base = (size_t)(blockIdx.x - T.first_block[k]) * kAdamPerBlock;
-  const float step_size = t.lr * T.c_step;
+  const float step_size = T.hyper ? T.hyper[1 + t.lr_index] * T.hyper[0] : t.lr * T.c_step;
   const bool vec = ((((uintptr_t)t.p | (uintptr_t)t.g | (uintptr_t)t.m | (uintptr_t)t.v) & 15) == 0);
   auto upd = [&](float& p, float g, float& m, float& v) {
     m = T.b0 * m + (1.0f - T.b0) * g;
@@ -163,7 +164,7 @@ extern "C" int tvm_vector_diffs(const float* line_cl, int C, int L, float weight
 }
 
 extern "C" int tvm_adam_step(const TvmAdamTensor* tensors_host, int n_tensors, float beta0, float beta1, float eps, int step,
-                             void* stream) {
+                             const float* hyper_dev, void* stream) {
   TVM_REQUIRE(tensors_host && n_tensors > 0 && step >= 1, "bad arguments");
   for (int s0 = 0; s0 < n_tensors; s0 += TVM_ADAM_MAX_TENSORS) {
     AdamTable T;
@@ -177,6 +178,7 @@ extern "C" int tvm_adam_step(const TvmAdamTensor* tensors_host, int n_tensors, f
     }
     T.first_block[T.n] = blocks;
     T.b0 = beta0; T.b1 = beta1; T.eps = eps;
+    T.hyper = hyper_dev;
     T.c_step = (float)(sqrt(1.0 - pow((double)beta1, step)) / (1.0 - pow((double)beta0, step)));
     k_adam_multi<<<blocks, 256, 0, (cudaStream_t)stream>>>(T);
     TVM_CHECK_CUDA(cudaGetLastError());

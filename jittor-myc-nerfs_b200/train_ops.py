@@ -11,6 +11,7 @@ and scales it by the incoming scalar in backward.
 from __future__ import annotations
 
 import ctypes as C
+import math
 
 import torch
 
@@ -126,32 +127,148 @@ class Adam:
             self.state[id(p)] = s
         return s
 
-    @torch.no_grad()
-    def step(self, loss=None):
-        if loss is not None:
-            self.zero_grad()
-            loss.backward()
+    # -- hyper-parameters live in a small device buffer refreshed from pinned host memory, so that a captured CUDA
+    #    graph (TrainStepGraph) can be replayed with the next step's bias correction / decayed learning rates
+    def _prepare_hyper(self):
+        """Host side of one step: advance the step counter and stage {c_step, lr per group} in pinned memory."""
         self.n_step += 1
+        n = float(self.n_step)
+        if getattr(self, "_hyper_host", None) is None or self._hyper_host.numel() != 1 + len(self.param_groups):
+            self._hyper_host = torch.zeros(1 + len(self.param_groups), dtype=torch.float32).pin_memory()
+            self._hyper_dev = None
+        b0, b1 = self.betas
+        self._hyper_host[0] = math.sqrt(1.0 - b1 ** n) / (1.0 - b0 ** n)
+        for i, g in enumerate(self.param_groups):
+            self._hyper_host[1 + i] = float(g["lr"])
+
+    @torch.no_grad()
+    def _launch(self):
+        """Device side of one step (capturable): refresh the hyper buffer, one multi-tensor kernel per 32 tensors."""
         entries, keep = [], []
-        for g in self.param_groups:
+        dev = None
+        for gi, g in enumerate(self.param_groups):
             for p in g["params"]:
                 if p.grad is None:
                     continue
                 if not (p.is_cuda and p.dtype == torch.float32 and p.data.is_contiguous()):
                     raise L.TvmError("Adam: parameters must be contiguous fp32 CUDA tensors (no CPU fallback)")
+                dev = p.device
                 m, v = self._state(p)
                 gr = p.grad.contiguous()
-                keep.append(gr)
+                keep += [gr, p]
                 e = L.TvmAdamTensor()
-                e.p, e.g, e.m, e.v, e.n, e.lr = p.data.data_ptr(), gr.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), float(g["lr"])
+                e.p, e.g, e.m, e.v, e.n = p.data.data_ptr(), gr.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel()
+                e.lr, e.lr_index = float(g["lr"]), gi
                 entries.append(e)
-                keep.append(p)
         if not entries:
             return
+        if self._hyper_dev is None:
+            self._hyper_dev = torch.zeros_like(self._hyper_host, device=dev)
+        self._hyper_dev.copy_(self._hyper_host, non_blocking=True)
         arr = (L.TvmAdamTensor * len(entries))(*entries)
         L.check(L.load().tvm_adam_step(arr, len(entries), float(self.betas[0]), float(self.betas[1]), float(self.eps),
-                                       int(self.n_step), _stream_ptr()), "tvm_adam_step")
+                                       int(self.n_step), _ptr(self._hyper_dev), _stream_ptr()), "tvm_adam_step")
         # the kernel wrote through raw pointers: bump the version counters so that the packed device image is rebuilt
         for t in keep:
             if isinstance(t, torch.nn.Parameter):
                 torch.autograd.graph.increment_version(t)
+
+    def step(self, loss=None):
+        if loss is not None:
+            self.zero_grad()
+            loss.backward()
+        self._prepare_hyper()
+        self._launch()
+
+
+class TrainStepGraph:
+    """One optimisation step of train.py:218-261 (sample jitter, render, MSE, regularisers, backward, Adam, re-pack of the
+    updated grids) captured ONCE into a CUDA graph and replayed per iteration: the step is launch-bound (~60 kernels of
+    10-100 us), so the graph removes the host time between them.  Per-step scalars (Adam bias correction, decayed learning
+    rates, regulariser weights) reach the graph through a pinned-host -> device copy node.
+
+        g = TrainStepGraph(model, opt, n_rays=4096, N_samples=S, white_bg=True, TV_weight_density=2.0, TV_weight_app=2.0)
+        loss = g.step(rays, rgbs)        # device scalar; call g.set_weights(...) / change opt.param_groups[i]['lr'] freely
+    """
+
+    def __init__(self, model, optimizer, n_rays, N_samples, white_bg=True, TV_weight_density=0.0, TV_weight_app=0.0,
+                 L1_reg_weight=0.0, Ortho_reg_weight=0.0):
+        self.model, self.opt = model, optimizer
+        dev = model.device
+        self.rays = torch.zeros((n_rays, 6), dtype=torch.float32, device=dev)
+        self.target = torch.zeros((n_rays, 3), dtype=torch.float32, device=dev)
+        self.S, self.white_bg = int(N_samples), bool(white_bg)
+        self.use = dict(tv_d=TV_weight_density > 0, tv_a=TV_weight_app > 0, l1=L1_reg_weight > 0, ortho=Ortho_reg_weight > 0)
+        self._w_host = torch.tensor([TV_weight_density, TV_weight_app, L1_reg_weight, Ortho_reg_weight], dtype=torch.float32).pin_memory()
+        self._w_dev = self._w_host.to(dev)
+        self._tv = TVLoss()
+        self.loss = torch.zeros((), dtype=torch.float32, device=dev)
+        self.jitter = None                  # optional static [n] buffer (step(..., jitter=...)); default: torch.rand per step
+        self.graph = None
+
+    def set_weights(self, TV_weight_density=None, TV_weight_app=None, L1_reg_weight=None, Ortho_reg_weight=None):
+        for i, v in enumerate((TV_weight_density, TV_weight_app, L1_reg_weight, Ortho_reg_weight)):
+            if v is not None:
+                self._w_host[i] = float(v)
+
+    def _body(self):
+        m = self.model
+        self.opt.zero_grad()
+        self._w_dev.copy_(self._w_host, non_blocking=True)
+        rgb, _ = m(self.rays, is_train=True, white_bg=self.white_bg, N_samples=self.S, jitter=self.jitter)
+        loss = torch.mean((rgb - self.target) ** 2)
+        total = loss
+        if self.use["tv_d"]:
+            total = total + m.TV_loss_density(self._tv) * self._w_dev[0]
+        if self.use["tv_a"]:
+            total = total + m.TV_loss_app(self._tv) * self._w_dev[1]
+        if self.use["l1"]:
+            total = total + m.density_L1() * self._w_dev[2]
+        if self.use["ortho"]:
+            total = total + m.vector_comp_diffs() * self._w_dev[3]
+        total.backward()
+        self.opt._launch()
+        m._pack(force=True)                       # the next forward (and any render in between) sees the updated grids
+        self.loss.copy_(loss.detach())
+
+    def capture(self):
+        """Warm up on a side stream (torch's capture protocol), then record the step.  The warm-up steps are real
+        optimisation steps on whatever the static buffers hold: parameters and optimiser state are snapshotted and restored."""
+        m, opt = self.model, self.opt
+        params = [p for g in opt.param_groups for p in g["params"]]
+        snap = [p.detach().clone() for p in params]
+        n_step0 = opt.n_step
+        s = torch.cuda.Stream(device=m.device)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                opt._prepare_hyper()
+                self._body()
+        torch.cuda.current_stream().wait_stream(s)
+        self.graph = torch.cuda.CUDAGraph()
+        opt._prepare_hyper()
+        with torch.cuda.graph(self.graph):
+            self._body()
+        with torch.no_grad():
+            for p, q in zip(params, snap):
+                p.copy_(q)
+            for mv in opt.state.values():
+                mv[0].zero_()
+                mv[1].zero_()
+        opt.n_step = n_step0
+        m._pack(force=True)
+
+    def step(self, rays, target, jitter=None):
+        if jitter is not None and self.jitter is None:
+            if self.graph is not None:
+                raise RuntimeError("pass jitter from the first step on (the graph was captured with on-device random jitter)")
+            self.jitter = torch.zeros(self.rays.shape[0], dtype=torch.float32, device=self.rays.device)
+        if self.graph is None:
+            self.capture()
+        if jitter is not None:
+            self.jitter.copy_(jitter, non_blocking=True)
+        self.rays.copy_(rays, non_blocking=True)
+        self.target.copy_(target, non_blocking=True)
+        self.opt._prepare_hyper()
+        self.graph.replay()
+        return self.loss
