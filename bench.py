@@ -265,18 +265,24 @@ def run_side_workload(args):
     from oracle import fixtures as fx
     L = pkg._lib
     L.require_cuda()
-    dev = torch.device("cuda", 0)
+    rank, local_rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
     reg = fx.REGIMES[args.regime]
     train = args.workload == "train"
     G = args.grid if (args.grid != GRID or not train) else 128
     variant = {"npp": "npp", "ref": "ref"}.get(args.workload, "vm")
     mp = fx.make_model(G, density_shift=reg["density_shift"], variant=variant)
     vol = fx.ball_alpha_volume(MASK_RES if G > 128 else 128) if reg["mask"] else None
-    model = pkg.model_from_params(mp, "cuda:0", vol, mp.aabb.copy(), args.mlp)
+    model = pkg.model_from_params(mp, f"cuda:{local_rank}", vol, mp.aabb.copy(), args.mlp)
     if train:
         n = 4096 if args.rays == FRAME * FRAME else args.rays
-        rays_np = fx.subset_rays(n)
+        rays_np = fx.subset_rays(n, azimuth=0.7 + rank * np.pi / 4)     # weak scaling: 4096 rays per rank, one NCCL all-reduce
+        model.grad_sync = world > 1                                     # of the flat gradient buffer per step
         S = int(np.linalg.norm(np.asarray(mp.gridSize, dtype=np.float64)) / mp.step_ratio)     # cal_n_samples, utils.py:61-62
         tgt = torch.from_numpy(fx.target_rgb(n)).to(dev)
         jit = torch.from_numpy(fx.jitter(n)).to(dev)
@@ -314,22 +320,32 @@ def run_side_workload(args):
                 return model(rays, N_samples=S, **extra)
             return model(rays, white_bg=True, is_train=False, N_samples=S)
 
-    def timed(steps):
-        evs = []
+    def barrier():
         torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(steps, fn=None):
+        fn = fn or step
+        evs = []
+        barrier()
         for _ in range(steps):
             flush.zero_()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            step()
+            fn()
             b.record()
             evs.append((a, b))
-        torch.cuda.synchronize()
-        return sum(a.elapsed_time(b) for a, b in evs)
+        barrier()
+        t = torch.tensor([sum(a.elapsed_time(b) for a, b in evs)], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     for _ in range(max(args.warmup, 3)):
         step()
-    with ClockSampler(0) as clk:
+    with ClockSampler(local_rank) as clk:
         ms = timed(args.steps)
     model.collect_counters = True
     model.counters.zero_()
@@ -342,8 +358,8 @@ def run_side_workload(args):
     name = {"train": f"configs[2]: training step fwd+bwd (MSE), {n} rays, {G}^3 grid, S={S}, mlp {args.mlp}",
             "npp": f"configs[3]: NerfPlusPlus full frame ({n} rays), {G}^3 grid, 512 background samples/ray",
             "ref": f"configs[3]: REFTensoRF full frame ({n} rays), {G}^3 grid"}[args.workload]
-    line = {"metric": f"TensoRF-VM rays/sec ({args.workload})", "value": n / (ms / args.steps * 1e-3), "unit": UNIT,
-            "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+    line = {"metric": f"TensoRF-VM rays/sec ({args.workload})", "value": n * world / (ms / args.steps * 1e-3), "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if args.mlp == "fp32" else f"f32 + {args.mlp} tensor-core MLP (forward and backward)", "data": "synthetic",
             "config": {"workload": name + f", regime {args.regime}", "n_samples": S,
@@ -360,7 +376,7 @@ def run_side_workload(args):
         for _ in range(3):
             step()
         ms_full = timed(args.steps)
-        line["full_step"] = {"ms_per_step": ms_full / args.steps, "rays_per_s": n / (ms_full / args.steps * 1e-3),
+        line["full_step"] = {"ms_per_step": ms_full / args.steps, "rays_per_s": n * world / (ms_full / args.steps * 1e-3),
                              "includes": "fwd + bwd + TV_loss_density + TV_loss_app (weights 2.0, configs/Scar.txt) + Adam over "
                                          "all parameter tensors + re-pack of the updated grids"}
         # the same full step captured once into a CUDA graph (TrainStepGraph) and replayed: no host time between kernels
@@ -368,18 +384,8 @@ def run_side_workload(args):
         L.profile_enable(False)
         gstep = pkg.TrainStepGraph(model, opt, n, S, white_bg=True, TV_weight_density=2.0, TV_weight_app=2.0)
         gstep.step(rays, tgt)
-        torch.cuda.synchronize()
-        evs = []
-        for _ in range(args.steps):
-            flush.zero_()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            gstep.step(rays, tgt)
-            b.record()
-            evs.append((a, b))
-        torch.cuda.synchronize()
-        ms_graph = sum(a.elapsed_time(b) for a, b in evs) / args.steps
-        line["full_step_cuda_graph"] = {"ms_per_step": ms_graph, "rays_per_s": n / (ms_graph * 1e-3),
+        ms_graph = timed(args.steps, lambda: gstep.step(rays, tgt)) / args.steps
+        line["full_step_cuda_graph"] = {"ms_per_step": ms_graph, "rays_per_s": n * world / (ms_graph * 1e-3),
                                         "includes": "as full_step, replayed as one CUDA graph (jitter drawn on the device)"}
     if args.workload == "npp" and stage_ms.get("bg"):
         # dense FLOPs of the background network as issued on the tensor cores (padded K/N), per sample
@@ -389,7 +395,11 @@ def run_side_workload(args):
         peak = float(pk.get("bf16_tflops_sustained", pk.get("bf16_tflops", 1355.0)))
         line["roofline"] = {"bound": "tensor", "kernel": "k_bg_tc", "achieved": tf, "peak": peak, "unit": "TFLOP/s",
                             "frac": tf / peak, "traffic": None, "flop_per_sample_issued": flop}
-    print(json.dumps(line))
+    if rank == 0:
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def main():
