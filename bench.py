@@ -396,14 +396,24 @@ def run_side_workload(args):
         line["roofline"] = {"bound": "tensor", "kernel": "k_bg_tc", "achieved": tf, "peak": peak, "unit": "TFLOP/s",
                             "frac": tf / peak, "traffic": None, "flop_per_sample_issued": flop}
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if dist is not None:
+        # NCCL communicators referenced by a captured CUDA graph cannot be torn down cleanly: release the graph, drain the
+        # device, and leave without destroy_process_group (it blocks forever otherwise; measured on 2 x B200)
+        gstep = None
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 def main():
     args = parse()
+    if os.environ.get("BENCH_WATCHDOG"):
+        # debugging aid: dump every thread's stack and exit if the run is still alive after N seconds
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["BENCH_WATCHDOG"]), exit=True)
     if args.workload == "maintain":
         return run_maintain(args)
     if args.workload != "frame":
