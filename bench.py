@@ -450,12 +450,9 @@ def main():
                                                    is_train=False, device=dev)
 
     def step_e2e():
-        with torch.no_grad():
-            r = rays_host.to(dev, non_blocking=True)
-            rgb, _, depth, _, _ = pkg.OctreeRender_trilinear_fast(r, model, chunk=1024, N_samples=-1,
-                                                                  white_bg=True, is_train=False, device=dev)
-            rgb_host.copy_(rgb, non_blocking=True)
-            depth_host.copy_(depth, non_blocking=True)
+        # host rays in, host rgb/depth out: upload, render and download pipelined per workspace chunk
+        pkg.OctreeRender_trilinear_fast(rays_host, model, chunk=1024, N_samples=-1, white_bg=True, is_train=False,
+                                        device=dev, out_host=(rgb_host, depth_host))
 
     def barrier():
         torch.cuda.synchronize()

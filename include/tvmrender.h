@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define TVM_ABI_VERSION 9
+#define TVM_ABI_VERSION 10
 
 /* flags for tvm_forward / tvm_backward */
 #define TVM_WHITE_BG      0x1u  /* rgb_map += 1 - acc_map          (tensorBase.py:523-524) */
@@ -102,6 +102,9 @@ typedef struct TvmModel {
   /* optional empty-space index from tvm_pack_alpha_bricks (NULL = none): one bit per 8x8x8-voxel
    * brick, bit (bz*BH + by)*BW + bx with B* = ceil(dim/8); set iff any voxel of the brick is set  */
   const uint32_t* alpha_bricks;
+  /* optional 2x2x2-dilated copy of alpha_bits from tvm_pack_alpha_dilated (NULL = none): bit (z,y,x) = OR of the eight
+   * corner bits (x..x+1, y..y+1, z..z+1); decides interior samples with one lookup, bit-identically to the 8-tap test    */
+  const uint32_t* alpha_dilated;
   /* optional tensor-core operand images written by tvm_pack_mlp_tc (NULL = not packed)   */
   const void* tc_weights;
   int32_t sampling;         /* TVM_SAMPLING_*                                                            */
@@ -188,6 +191,8 @@ int tvm_unpack_linear(const float* w_t, int out_c, int in_c, int out_pad, float*
 int tvm_pack_alpha(const float* volume, int D, int H, int W, uint32_t* bits, void* stream);
 /* brick index of a packed alpha volume; n_words = ceil(ceil(D/8)*ceil(H/8)*ceil(W/8) / 32)        */
 int tvm_pack_alpha_bricks(const uint32_t* bits, int D, int H, int W, uint32_t* bricks, void* stream);
+/* 2x2x2-dilated copy of a packed alpha volume (same size and bit order as `bits`)                    */
+int tvm_pack_alpha_dilated(const uint32_t* bits, int D, int H, int W, uint32_t* dilated, void* stream);
 /* bytes of the tensor-core operand image for (in_mlp_c, feature_c, app_dim, n_app)            */
 size_t tvm_tc_weights_bytes(const TvmModel* m_host);
 /* builds the bf16 (hi, mid) K-major UMMA operand images of basis/W1/W2 from the packed fp32 weights */

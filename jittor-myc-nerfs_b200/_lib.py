@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libtvmrender.so")
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 # flags (tvmrender.h)
 WHITE_BG = 0x1
@@ -43,7 +43,7 @@ class TvmModel(C.Structure):
         ("variant", C.c_int32), ("basis_t", C.c_void_p), ("head_bias", C.c_void_p), ("w1_t", C.c_void_p), ("b1", C.c_void_p), ("w2_t", C.c_void_p),
         ("b2", C.c_void_p), ("w3", C.c_void_p), ("b3", C.c_void_p),
         ("alpha_bits", C.c_void_p), ("alpha_grid", _i3), ("alpha_aabb_min", _f3), ("alpha_inv_size", _f3),
-        ("alpha_bricks", C.c_void_p), ("tc_weights", C.c_void_p), ("sampling", C.c_int32), ("radii", C.c_float),
+        ("alpha_bricks", C.c_void_p), ("alpha_dilated", C.c_void_p), ("tc_weights", C.c_void_p), ("sampling", C.c_int32), ("radii", C.c_float),
     ]
 
 
@@ -73,7 +73,7 @@ class TvmGrads(C.Structure):
 
 EXPORTS = [
     "tvm_last_error", "tvm_abi_version", "tvm_device_count", "tvm_pack_grid", "tvm_unpack_grid",
-    "tvm_pack_linear", "tvm_unpack_linear", "tvm_pack_alpha", "tvm_pack_alpha_bricks", "tvm_tc_weights_bytes", "tvm_pack_mlp_tc",
+    "tvm_pack_linear", "tvm_unpack_linear", "tvm_pack_alpha", "tvm_pack_alpha_bricks", "tvm_pack_alpha_dilated", "tvm_tc_weights_bytes", "tvm_pack_mlp_tc",
     "tvm_workspace_bytes", "tvm_forward", "tvm_forward_npp", "tvm_bg_fold", "tvm_bg_tc_bytes", "tvm_pack_bg_tc", "tvm_backward", "tvm_density_alpha", "tvm_mse_loss",
     "tvm_profile_enable", "tvm_profile_collect",
     "tvm_dense_alpha", "tvm_alpha_mask_from_dense", "tvm_filter_rays", "tvm_generate_rays", "tvm_upsample_grid",
@@ -111,6 +111,7 @@ def load() -> C.CDLL:
     lib.tvm_unpack_linear.argtypes = [vp, i32, i32, i32, vp, vp]
     lib.tvm_pack_alpha.argtypes = [vp, i32, i32, i32, vp, vp]
     lib.tvm_pack_alpha_bricks.argtypes = [vp, i32, i32, i32, vp, vp]
+    lib.tvm_pack_alpha_dilated.argtypes = [vp, i32, i32, i32, vp, vp]
     lib.tvm_tc_weights_bytes.restype = C.c_size_t
     lib.tvm_tc_weights_bytes.argtypes = [C.POINTER(TvmModel)]
     lib.tvm_bg_tc_bytes.restype = C.c_size_t

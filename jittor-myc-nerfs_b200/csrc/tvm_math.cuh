@@ -155,6 +155,13 @@ TVM_HD bool alpha_mask_test(const TvmModel& m, const uint32_t* __restrict__ bits
     ax[i] = axis_taps(unnormalize(c, m.alpha_grid[i]), m.alpha_grid[i]);
   }
   const int W = m.alpha_grid[0], H = m.alpha_grid[1];
+  if (m.alpha_dilated != nullptr && ax[0].w0 > 0.0f && ax[0].w1 > 0.0f && ax[1].w0 > 0.0f && ax[1].w1 > 0.0f &&
+      ax[2].w0 > 0.0f && ax[2].w1 > 0.0f) {
+    // all 8 taps in range with non-zero weights (a zero weight only arises on a lattice plane or outside the volume):
+    // the decision is the OR of the 8 corner bits, precomputed by tvm_pack_alpha_dilated
+    const uint32_t idx = ((uint32_t)ax[2].i0 * (uint32_t)H + (uint32_t)ax[1].i0) * (uint32_t)W + (uint32_t)ax[0].i0;
+    return (m.alpha_dilated[idx >> 5] >> (idx & 31u)) & 1u;
+  }
   bool hit = false;
 #pragma unroll
   for (int cz = 0; cz < 2; ++cz) {

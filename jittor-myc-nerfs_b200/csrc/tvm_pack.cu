@@ -242,6 +242,36 @@ extern "C" int tvm_pack_alpha(const float* volume, int D, int H, int W, uint32_t
   return 0;
 }
 
+// dil bit (z,y,x) = OR of the 2x2x2 voxel bits at (x..x+1, y..y+1, z..z+1) (clipped at the upper faces): the alpha-mask
+// decision of a sample whose 8 trilinear taps are all in range with non-zero weights, in ONE bit lookup
+__global__ void k_pack_dilated(const uint32_t* __restrict__ bits, int D, int H, int W, uint32_t* __restrict__ dil) {
+  const size_t total = (size_t)D * H * W;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool set = false;
+  if (i < total) {
+    const int x = (int)(i % W), y = (int)((i / W) % H), z = (int)(i / ((size_t)W * H));
+    for (int dz = 0; dz < 2 && !set; ++dz)
+      for (int dy = 0; dy < 2 && !set; ++dy)
+        for (int dx = 0; dx < 2 && !set; ++dx) {
+          const int xx = x + dx, yy = y + dy, zz = z + dz;
+          if (xx < W && yy < H && zz < D) {
+            const size_t j = ((size_t)zz * H + yy) * W + xx;
+            set = (bits[j >> 5] >> (j & 31)) & 1u;
+          }
+        }
+  }
+  const uint32_t word = __ballot_sync(0xffffffffu, set);
+  if ((threadIdx.x & 31) == 0 && (i >> 5) < (total + 31) / 32) dil[i >> 5] = word;
+}
+
+extern "C" int tvm_pack_alpha_dilated(const uint32_t* bits, int D, int H, int W, uint32_t* dilated, void* stream) {
+  TVM_REQUIRE(bits && dilated && D > 0 && H > 0 && W > 0, "bad arguments");
+  const size_t warps = ((size_t)D * H * W + 31) / 32;
+  k_pack_dilated<<<(unsigned)((warps + 3) / 4), 128, 0, (cudaStream_t)stream>>>(bits, D, H, W, dilated);
+  TVM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int tvm_pack_alpha_bricks(const uint32_t* bits, int D, int H, int W, uint32_t* bricks, void* stream) {
   TVM_REQUIRE(bits && bricks && D > 0 && H > 0 && W > 0, "bad arguments");
   const int n = ((D + 7) / 8) * ((H + 7) / 8) * ((W + 7) / 8);

@@ -75,6 +75,9 @@ class AlphaGridMask:
         self.bricks = torch.empty((n_bricks + 31) // 32 + 8, dtype=torch.int32, device=device)
         L.check(lib.tvm_pack_alpha_bricks(_ptr(self.bits), D, H, W, _ptr(self.bricks), _stream_ptr()),
                 "tvm_pack_alpha_bricks")
+        self.dilated = torch.empty(n_words + 8, dtype=torch.int32, device=device)
+        L.check(lib.tvm_pack_alpha_dilated(_ptr(self.bits), D, H, W, _ptr(self.dilated), _stream_ptr()),
+                "tvm_pack_alpha_dilated")
 
 
 class _Linear(torch.nn.Module):
@@ -364,6 +367,7 @@ class TensorVMSplit(MaintainMixin, RegularizerMixin, torch.nn.Module):
             am = self.alphaMask
             s.alpha_bits = am.bits.data_ptr()
             s.alpha_bricks = am.bricks.data_ptr() if self.empty_space_skipping else None
+            s.alpha_dilated = am.dilated.data_ptr() if self.empty_space_skipping else None
             a0 = am.aabb.numpy().astype(np.float32)
             for i in range(3):
                 s.alpha_grid[i] = int(am.gridSize[i])
@@ -372,6 +376,7 @@ class TensorVMSplit(MaintainMixin, RegularizerMixin, torch.nn.Module):
         else:
             s.alpha_bits = None
             s.alpha_bricks = None
+            s.alpha_dilated = None
         s.tc_weights = None
         if self.mlp_mode != "fp32":
             lib = L.load()

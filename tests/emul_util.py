@@ -30,7 +30,20 @@ def pack_bits(volume):
     return np.packbits(flat, bitorder="little").view(np.uint32).copy()
 
 
-def host_model(pkg, params, alpha_volume=None, alpha_aabb=None):
+def pack_dilated(volume):
+    """numpy restatement of tvm_pack_alpha_dilated: bit (z,y,x) = OR of the 2x2x2 corner bits, clipped at the upper faces."""
+    v = np.asarray(volume).reshape(np.asarray(volume).shape[-3:]) > 0
+    pad = np.zeros(tuple(d + 1 for d in v.shape), bool)
+    pad[:-1, :-1, :-1] = v
+    d = np.zeros_like(v)
+    for dz in (0, 1):
+        for dy in (0, 1):
+            for dx in (0, 1):
+                d |= pad[dz:dz + v.shape[0], dy:dy + v.shape[1], dx:dx + v.shape[2]]
+    return pack_bits(d)
+
+
+def host_model(pkg, params, alpha_volume=None, alpha_aabb=None, dilated=True):
     """TvmModel whose pointers are numpy host buffers (kept alive in the returned list)."""
     L = pkg._lib
     s = pkg.derive_march_scalars(params.aabb, params.gridSize, params.step_ratio)
@@ -72,6 +85,10 @@ def host_model(pkg, params, alpha_volume=None, alpha_aabb=None):
         bits = pack_bits(alpha_volume)
         keep.append(bits)
         m.alpha_bits = bits.ctypes.data
+        if dilated:                                  # the one-lookup fast path of alpha_mask_test
+            dil = pack_dilated(alpha_volume)
+            keep.append(dil)
+            m.alpha_dilated = dil.ctypes.data
         D, H, W = alpha_volume.shape[-3:]
         a = np.asarray(alpha_aabb, np.float32).reshape(2, 3)
         inv = (np.float32(1.0) / (a[1] - a[0]) * np.float32(2)).astype(np.float32)

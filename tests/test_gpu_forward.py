@@ -253,3 +253,23 @@ def test_umma_descriptor_conventions(env):
     assert torch.equal(D3, P @ W.T), "K-major (forward) convention"
     assert torch.equal(D2, P @ W), "MN-major B operand"
     assert torch.equal(D1, P.T @ Q), "MN-major A and B operands"
+
+
+def test_streamed_host_render_matches_resident(env):
+    """OctreeRender_trilinear_fast(pinned host rays, out_host=...) pipelines upload / render / download per chunk; the
+    pixels are those of the device-resident call, bit for bit (compositing is deterministic)."""
+    pkg, torch, fx, orc = env
+    from util import gpu_model
+    case = fx.make_case(64, 0, "R1", mask_res=64, full_frame=True)
+    rays = case["rays"][:300000]
+    model = gpu_model(pkg, case, mlp_mode="bf16")
+    rays_host = torch.from_numpy(rays).pin_memory()
+    rgb_host = torch.empty((rays.shape[0], 3)).pin_memory()
+    depth_host = torch.empty((rays.shape[0],)).pin_memory()
+    with torch.no_grad():
+        rgb, _, depth, _, _ = pkg.OctreeRender_trilinear_fast(rays_host.cuda(), model, white_bg=True, is_train=False)
+    out = pkg.OctreeRender_trilinear_fast(rays_host, model, white_bg=True, is_train=False, out_host=(rgb_host, depth_host))
+    torch.cuda.synchronize()
+    assert out[0] is rgb_host and out[2] is depth_host
+    assert torch.equal(rgb_host, rgb.cpu()) and torch.equal(depth_host, depth.cpu())
+    assert float(rgb_host.min()) < 0.99      # the frame is not empty
