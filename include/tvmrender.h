@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define TVM_ABI_VERSION 10
+#define TVM_ABI_VERSION 11
 
 /* flags for tvm_forward / tvm_backward */
 #define TVM_WHITE_BG      0x1u  /* rgb_map += 1 - acc_map          (tensorBase.py:523-524) */
@@ -156,7 +156,8 @@ typedef struct TvmGrads {
   float* density_line[3];
   float* app_plane[3];
   float* app_line[3];
-  float* basis_t;           /* [3*n_app][32]  */
+  float* basis_t;           /* [3*n_app][32]; TVM_VARIANT_REF: [3*n_app][48] (basis_mat | normal | diffuse | specular | rho) */
+  float* head_bias;         /* TVM_VARIANT_REF: [48] biases of the stacked heads; else NULL                                  */
   float* w1_t;              /* [in_mlp_c][feature_c] */
   float* b1;
   float* w2_t;
@@ -229,10 +230,12 @@ int tvm_bg_fold(const float* remap_w /*[256][128]*/, const float* remap_b /*[256
 
 /* Backward of tvm_forward w.r.t. every parameter, given d_rgb_map [n][3] = dL/d rgb_map
  * (row a12 of SURVEY §8a; coordinates are detached, depth carries no gradient).  Must follow a
- * tvm_forward with the same arguments on the same workspace.                                     */
+ * tvm_forward with the same arguments on the same workspace.  TVM_VARIANT_REF: d_penalty is a DEVICE scalar
+ * dL/d penalty (train.py:253-255: normal_vector_penalty_weight) or NULL; the appearance backward of that variant
+ * always runs in fp32.                                                                                   */
 int tvm_backward(const TvmModel* m_host, const float* rays, int n_rays, int n_samples,
                  const float* jitter, uint32_t flags, const float* rgb_map, const float* d_rgb_map,
-                 const TvmGrads* grads_host, void* ws, size_t ws_bytes, void* stream);
+                 const float* d_penalty, const TvmGrads* grads_host, void* ws, size_t ws_bytes, void* stream);
 
 /* TensorBase.compute_alpha (tensorBase.py:451-473): alpha = 1 - exp(-sigma(xyz) * length)       */
 int tvm_density_alpha(const TvmModel* m_host, const float* xyz, int n_pts, float length,

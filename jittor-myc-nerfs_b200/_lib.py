@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libtvmrender.so")
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 # flags (tvmrender.h)
 WHITE_BG = 0x1
@@ -67,7 +67,7 @@ ADAM_MAX_TENSORS = 32
 
 class TvmGrads(C.Structure):
     _fields_ = [("density_plane", _p3), ("density_line", _p3), ("app_plane", _p3), ("app_line", _p3),
-                ("basis_t", C.c_void_p), ("w1_t", C.c_void_p), ("b1", C.c_void_p), ("w2_t", C.c_void_p),
+                ("basis_t", C.c_void_p), ("head_bias", C.c_void_p), ("w1_t", C.c_void_p), ("b1", C.c_void_p), ("w2_t", C.c_void_p),
                 ("b2", C.c_void_p), ("w3", C.c_void_p), ("b3", C.c_void_p)]
 
 
@@ -135,7 +135,7 @@ def load() -> C.CDLL:
     lib.tvm_vector_diffs.argtypes = [vp, i32, i32, f32, vp, vp, vp]
     lib.tvm_selftest_umma.argtypes = [vp] * 7
     lib.tvm_adam_step.argtypes = [C.POINTER(TvmAdamTensor), i32, f32, f32, f32, i32, vp, vp]
-    lib.tvm_backward.argtypes = [C.POINTER(TvmModel), vp, i32, i32, vp, u32, vp, vp, C.POINTER(TvmGrads), vp,
+    lib.tvm_backward.argtypes = [C.POINTER(TvmModel), vp, i32, i32, vp, u32, vp, vp, vp, C.POINTER(TvmGrads), vp,
                                  C.c_size_t, vp]
     lib.tvm_density_alpha.argtypes = [C.POINTER(TvmModel), vp, i32, f32, vp, vp]
     lib.tvm_mse_loss.argtypes = [vp, vp, i32, f32, vp, vp, vp]

@@ -121,8 +121,14 @@ __device__ __forceinline__ void app_basis_pe(const FwdParams& P, const float* H,
       xr[0] = -dot;
       xr[c_dir] = d[0]; xr[c_dir + 1] = d[1]; xr[c_dir + 2] = d[2];
       const float r0 = hd[3], r1 = hd[4], r2 = hd[5], tint = fmaxf(hd[6], 0.0f);
+      const float v0 = hd[0], v1 = hd[1], v2 = hd[2];
       hd[0] = r0; hd[1] = r1; hd[2] = r2; hd[3] = tint;
+      hd[4] = v0; hd[5] = v1; hd[6] = v2; hd[7] = dot;       // raw normal and d.n for the backward pass
       const uint32_t e = tile_base + row;
+      if (e < n_ent) {
+        const float pe = fmaxf(-dot, 0.0f);
+        P.ws.ent_pen[e] = pe * pe;
+      }
       if (P.aux.penalty) {
         // part == 3 is two whole warps: one atomic per warp instead of one per entry (single-address contention)
         const float pen = fmaxf(-dot, 0.0f);

@@ -34,6 +34,8 @@ __global__ void k_bwd_prep(const BwdParams B) {
   }
   if (!(B.f.flags & TVM_WHITE_BG)) gs = 0.0f;
   // sum_k dL/dw_k * w_k with dL/dw_k = g . rgb_k - gs   (rgb_map = sum w rgb + 1 - sum w)
+  // REFTensoRF: + dL/dpenalty * pen_k, penalty = sum w_k pen_k (REFTensoRF.py:236-238)
+  if (B.d_penalty) tot = fmaf(*B.d_penalty, B.f.ws.pen_sum[ray], tot);
   float4 o = make_float4(g[0], g[1], g[2], tot - gs * acc);
   reinterpret_cast<float4*>(B.f.ws.bwd_scratch)[ray] = o;
 }
@@ -65,20 +67,21 @@ __device__ __forceinline__ void wgrad_tile_128(const float* A, const float* Bm, 
       if (j0 + a < K) red_add_v4(out + (size_t)(j0 + a) * ldo + o4, acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
   }
 }
-// out[K][32] += A[64][0..K)^T . Bm[64][0..32): one thread per j
-__device__ __forceinline__ void wgrad_tile_32(const float* A, const float* Bm, int st, int K, float* out) {
+// out[K][NH] += A[64][0..K)^T . Bm[64][0..NH): one thread per j
+template <int NH>
+__device__ __forceinline__ void wgrad_tile_heads(const float* A, const float* Bm, int st, int K, float* out) {
   const int j = threadIdx.x;
   if (j >= K) return;
-  float acc[32];
+  float acc[NH];
 #pragma unroll
-  for (int i = 0; i < 32; ++i) acc[i] = 0.0f;
+  for (int i = 0; i < NH; ++i) acc[i] = 0.0f;
   for (int row = 0; row < kAppTile; ++row) {
     const float a = A[row * st + j];
 #pragma unroll
-    for (int i = 0; i < 32; i += 4) fma4(acc + i, a, lds4(Bm + row * st + i));
+    for (int i = 0; i < NH; i += 4) fma4(acc + i, a, lds4(Bm + row * st + i));
   }
 #pragma unroll
-  for (int i = 0; i < 32; i += 4) red_add_v4(out + (size_t)j * kMaxAppDim + i, acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
+  for (int i = 0; i < NH; i += 4) red_add_v4(out + (size_t)j * NH + i, acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
 }
 // bias gradient: out[o] += sum_rows Bm[row][o], o < 128
 __device__ __forceinline__ void bgrad_tile(const float* Bm, int st, float* out) {
@@ -122,7 +125,9 @@ __device__ __forceinline__ void app_dense_bwd(const float* __restrict__ Wt, cons
 }
 
 // ------------------------------------------------------------------------------------------------
+template <int NH>
 __global__ void __launch_bounds__(kAppThreads) k_app_bwd(const BwdParams B) {
+  constexpr bool REF = NH == TVM_REF_HEAD_LD;
   extern __shared__ __align__(16) float smem[];
   const FwdParams& P = B.f;
   const TvmModel& m = P.m;
@@ -132,6 +137,8 @@ __global__ void __launch_bounds__(kAppThreads) k_app_bwd(const BwdParams B) {
   float* Y1 = smem + 2 * kAppTile * st;   // layer-1 output                 -> dz1 -> d feat
   float* Y2 = smem + 3 * kAppTile * st;   // layer-2 output                 -> dz2 -> d x
   float* D3 = smem + 4 * kAppTile * st;   // [64][4] dz3
+  float* HD = D3 + kAppTile * 4;          // [64][8]  REF: {rgb_d[3], tint, raw normal[3], d.n} from the forward recompute
+  float* HG = HD + kAppTile * 8;          // [64][8]  REF: {w g [3], sigmoid [3], ...}
   const int tid = threadIdx.x;
   const int row = tid & (kAppTile - 1), part = tid >> 6;
   const int Ca = m.n_app, K0 = 3 * Ca;
@@ -145,7 +152,7 @@ __global__ void __launch_bounds__(kAppThreads) k_app_bwd(const BwdParams B) {
     // ---- forward recompute ---------------------------------------------------------------------
     app_gather_tile(P, tile_base, n_ent, H, X, st);
     __syncthreads();
-    app_basis_pe<32>(P, H, X, D3, st, tile_base, n_ent);
+    app_basis_pe<NH>(P, H, X, HD, st, tile_base, n_ent);
     __syncthreads();
     app_dense<true>(m.w1_t, m.b1, X, P.in_mlp_c, Y1, st);
     __syncthreads();
@@ -158,6 +165,15 @@ __global__ void __launch_bounds__(kAppThreads) k_app_bwd(const BwdParams B) {
         const float4 g = gray[P.ws.ent[e].x];
         const float gc = part == 0 ? g.x : (part == 1 ? g.y : g.z);
         dz = P.ws.ent_w[e] * gc * s * (1.0f - s);     // d/d logit of w * rgb . g
+        if (REF) {
+          // rgb = tint * rgb_s + rgb_d (REFTensoRF.py:232; rgb_s = sigmoid > 0, so the clamp is the identity)
+          dz *= HD[row * 8 + 3];
+          HG[row * 8 + part] = P.ws.ent_w[e] * gc;
+          HG[row * 8 + 3 + part] = s;
+        }
+      } else if (REF) {
+        HG[row * 8 + part] = 0.0f;
+        HG[row * 8 + 3 + part] = 0.0f;
       }
       D3[row * 4 + part] = dz;
     }
@@ -209,18 +225,20 @@ __global__ void __launch_bounds__(kAppThreads) k_app_bwd(const BwdParams B) {
     bgrad_tile(Y1, st, B.g.b1);
     app_dense_bwd<false>(m.w1_t, Y1, P.in_mlp_c, Y2, nullptr, st);
     __syncthreads();
-    // ---- positional encoding: d feat (into Y1[.., 0..32)) ---------------------------------------------
+    // ---- positional encoding: d head outputs (into Y1[.., 0..NH)) -------------------------------------------
     {
       const float* x = X + row * st;
       const float* dx = Y2 + row * st;
-      const int pe_f = m.app_dim + 3;
+      const int c_feat = col_feat(m), c_dir = col_dir(m);
+      const int pe_f = c_dir + 3;
       const int n_f = m.fea_pe * m.app_dim;
+      constexpr int NP = NH / 4;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int o = part * 8 + i;
+      for (int i = 0; i < NP; ++i) {
+        const int o = part * NP + i;
         float df = 0.0f;
         if (o < m.app_dim) {
-          df = dx[o];
+          df = dx[c_feat + o];
           float fr = 1.0f;
           for (int q = 0; q < m.fea_pe; ++q, fr *= 2.0f) {
             const int si = pe_f + o * m.fea_pe + q, ci = si + n_f;
@@ -229,24 +247,77 @@ __global__ void __launch_bounds__(kAppThreads) k_app_bwd(const BwdParams B) {
         }
         Y1[row * st + o] = df;
       }
+      if (REF) __syncthreads();
+      if (REF && part == 3) {
+        // REFTensoRF.py:216-238 backwards: reflection, dot product, normalisation, tint / diffuse mix, penalty
+        const uint32_t e = tile_base + row;
+        float dv[3] = {0.0f, 0.0f, 0.0f}, dspec = 0.0f, drd[3] = {0.0f, 0.0f, 0.0f};
+        if (e < n_ent) {
+          const int pe_v = pe_f + 2 * n_f, n_v = 3 * m.view_pe;
+          float dr[3];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            float a = dx[c_dir + c];
+            float fr = 1.0f;
+            for (int q = 0; q < m.view_pe; ++q, fr *= 2.0f) {
+              const int si = pe_v + c * m.view_pe + q, ci = si + n_v;
+              a += fr * (dx[si] * x[ci] - dx[ci] * x[si]);
+            }
+            dr[c] = a;                                        // d reflection
+          }
+          const float* hd = HD + row * 8;
+          const float* hg = HG + row * 8;
+          const float v0 = hd[4], v1 = hd[5], v2 = hd[6], dot = hd[7];
+          const float n2 = v0 * v0 + v1 * v1 + v2 * v2;
+          const float inv = 1.0f / sqrtf(fmaxf(n2, 1e-30f));
+          const float nh[3] = {v0 * inv, v1 * inv, v2 * inv};
+          const uint32_t ray = P.ws.ent[e].x;
+          const float d[3] = {-P.rays[6 * (size_t)ray + 3], -P.rays[6 * (size_t)ray + 4], -P.rays[6 * (size_t)ray + 5]};
+          // x[0] = -dot; reflection = 2 dot n - d; penalty = sum w relu(-dot)^2
+          float ddot = -dx[0] + 2.0f * (nh[0] * dr[0] + nh[1] * dr[1] + nh[2] * dr[2]);
+          if (B.d_penalty) ddot -= *B.d_penalty * P.ws.ent_w[e] * 2.0f * fmaxf(-dot, 0.0f);
+          float dn[3];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) dn[c] = 2.0f * dot * dr[c] + ddot * d[c];
+          const float proj = nh[0] * dn[0] + nh[1] * dn[1] + nh[2] * dn[2];
+          if (n2 > 1e-30f) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) dv[c] = (dn[c] - nh[c] * proj) * inv;
+          }
+          const float dtint = hg[0] * hg[3] + hg[1] * hg[4] + hg[2] * hg[5];
+          dspec = hd[3] > 0.0f ? dtint : 0.0f;                // tint = relu(specular_linear(h))
+          drd[0] = hg[0]; drd[1] = hg[1]; drd[2] = hg[2];     // d rgb_d = w g
+        }
+        float* y = Y1 + row * st + m.app_dim;                 // head order: normal 3 | diffuse 3 | specular | rho
+        y[0] = dv[0]; y[1] = dv[1]; y[2] = dv[2];
+        y[3] = drd[0]; y[4] = drd[1]; y[5] = drd[2];
+        y[6] = dspec;
+        y[7] = 0.0f;                                          // rho only feeds the unused 1/rho argument (REFTensoRF.py:226)
+        for (int o = m.app_dim + 8; o < NH; ++o) Y1[row * st + o] = 0.0f;
+      }
     }
     __syncthreads();
-    // ---- basis_mat: d basis, d h (into X) -------------------------------------------------------------
-    wgrad_tile_32(H, Y1, st, K0, B.g.basis_t);
+    // ---- basis_mat (+ heads): d basis, d head bias, d h (into X) ----------------------------------------------
+    wgrad_tile_heads<NH>(H, Y1, st, K0, B.g.basis_t);
+    if (REF && tid < 8) {
+      float a = 0.0f;
+      for (int r = 0; r < kAppTile; ++r) a += Y1[r * st + m.app_dim + tid];
+      atomicAdd(B.g.head_bias + m.app_dim + tid, a);
+    }
     {
-      float df[32];
+      float df[NH];
 #pragma unroll
-      for (int i = 0; i < 32; i += 4) {
+      for (int i = 0; i < NH; i += 4) {
         const float4 v = lds4(Y1 + row * st + i);
         df[i] = v.x; df[i + 1] = v.y; df[i + 2] = v.z; df[i + 3] = v.w;
       }
       const int JP = (K0 / 4 + 3) & ~3;
       const int jbeg = part * JP, jend = min(K0, jbeg + JP);
       for (int j = jbeg; j < jend; ++j) {
-        const float* bt = m.basis_t + j * kMaxAppDim;
+        const float* bt = m.basis_t + j * NH;
         float a = 0.0f;
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
+        for (int i = 0; i < NH; i += 4) {
           const float4 w = ldg4(bt + i);
           a = fmaf(df[i], w.x, fmaf(df[i + 1], w.y, fmaf(df[i + 2], w.z, fmaf(df[i + 3], w.w, a))));
         }
@@ -312,7 +383,8 @@ __global__ void __launch_bounds__(kMarchWarps * 32) k_march_bwd(const BwdParams 
   const float4 g = reinterpret_cast<const float4*>(P.ws.bwd_scratch)[ray];
   const float gs = (P.flags & TVM_WHITE_BG) ? g.x + g.y + g.z : 0.0f;
   const float total = g.w;
-  if (g.x == 0.0f && g.y == 0.0f && g.z == 0.0f) return;   // nothing flows into this ray
+  const float dpen = B.d_penalty ? *B.d_penalty : 0.0f;
+  if (g.x == 0.0f && g.y == 0.0f && g.z == 0.0f && dpen == 0.0f) return;   // nothing flows into this ray
 
   const int C = m.n_density, S = P.S;
   const bool ert = !(P.flags & TVM_NO_ERT);
@@ -417,6 +489,7 @@ __global__ void __launch_bounds__(kMarchWarps * 32) k_march_bwd(const BwdParams 
       const uint32_t e = P.ws.blk_base[(size_t)ray * P.NB + b] + __popc(a_bits & lt_mask);
       const float* c3 = P.ws.ent_rgb + (size_t)e * 3;
       dw += g.x * c3[0] + g.y * c3[1] + g.z * c3[2];
+      if (dpen != 0.0f) dw = fmaf(dpen, P.ws.ent_pen[e], dw);
     }
     // inclusive prefix of dw*w; the suffix sum_{j>k} dw_j w_j is total - prefix
     float ps = dw * w;
@@ -480,34 +553,37 @@ using namespace tvm;
 
 extern "C" int tvm_backward(const TvmModel* m_host, const float* rays, int n_rays, int n_samples,
                             const float* jitter, uint32_t flags, const float* rgb_map, const float* d_rgb_map,
-                            const TvmGrads* grads_host, void* ws, size_t ws_bytes, void* stream_) {
+                            const float* d_penalty, const TvmGrads* grads_host, void* ws, size_t ws_bytes, void* stream_) {
   (void)rgb_map;
   cudaStream_t stream = (cudaStream_t)stream_;
   BwdParams B;
   if (int rc = fill_fwd_params(B.f, m_host, rays, n_rays, n_samples, jitter, flags, ws, ws_bytes)) return rc;
   TVM_REQUIRE(d_rgb_map && grads_host, "null argument");
-  TVM_REQUIRE(m_host->variant == TVM_VARIANT_VM, "tvm_backward supports TVM_VARIANT_VM only (REFTensoRF backward is not built)");
+  const bool ref = m_host->variant == TVM_VARIANT_REF;
   B.d_rgb_map = d_rgb_map;
+  B.d_penalty = ref ? d_penalty : nullptr;
   B.g = *grads_host;
   for (int k = 0; k < 3; ++k)
     TVM_REQUIRE(B.g.density_plane[k] && B.g.density_line[k] && B.g.app_plane[k] && B.g.app_line[k], "null gradient pointer");
   TVM_REQUIRE(B.g.basis_t && B.g.w1_t && B.g.b1 && B.g.w2_t && B.g.b2 && B.g.w3 && B.g.b3, "null gradient pointer");
+  TVM_REQUIRE(!ref || B.g.head_bias, "TVM_VARIANT_REF needs TvmGrads.head_bias");
 
   k_bwd_prep<<<(n_rays + 255) / 256, 256, 0, stream>>>(B);
   TVM_CHECK_CUDA(cudaGetLastError());
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if ((flags & TVM_MLP_MASK) == TVM_MLP_BF16) {
+  if ((flags & TVM_MLP_MASK) == TVM_MLP_BF16 && !ref) {
     // appearance backward on the tensor cores (bf16 operands, fp32 accumulation; gradients to ~1e-2 relative)
     ProfileScope prof(TVM_STAGE_BWD_APP, stream);
     if (int rc = launch_app_bwd_tc(B, sms, stream)) return rc;
   } else {
-    const size_t smem = ((size_t)kAppTile * 4 * B.f.st + kAppTile * 4) * sizeof(float);
+    const size_t smem = ((size_t)kAppTile * 4 * B.f.st + kAppTile * (4 + 8 + 8)) * sizeof(float);
     TVM_REQUIRE(smem <= 220 * 1024, "appearance backward tile does not fit shared memory");
-    TVM_CHECK_CUDA(cudaFuncSetAttribute(k_app_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto kern = ref ? k_app_bwd<TVM_REF_HEAD_LD> : k_app_bwd<32>;
+    TVM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ProfileScope prof(TVM_STAGE_BWD_APP, stream);
-    k_app_bwd<<<sms, kAppThreads, smem, stream>>>(B);
+    kern<<<sms, kAppThreads, smem, stream>>>(B);
   }
   TVM_CHECK_CUDA(cudaGetLastError());
   {

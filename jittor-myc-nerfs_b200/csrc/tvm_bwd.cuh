@@ -7,6 +7,7 @@ namespace tvm {
 struct BwdParams {
   FwdParams f;
   const float* d_rgb_map;
+  const float* d_penalty;     // TVM_VARIANT_REF: device scalar dL/d penalty, or NULL
   TvmGrads g;
 };
 

@@ -41,6 +41,8 @@ struct Workspace {
   uint2* ent;            // [cap]     (ray, sample index)
   float* ent_w;          // [cap]     weight
   float* ent_rgb;        // [cap][3]  per-sample colour written by the appearance stage
+  float* ent_pen;        // [cap]     TVM_VARIANT_REF: relu(-d.n)^2 of the sample (REFTensoRF.py:236-237)
+  float* pen_sum;        // [n]       TVM_VARIANT_REF: sum_k w_k * pen_k of the ray
   float* acc;            // [n]       acc_map
   float* rgb_sum;        // [n][3]    sum_s w * rgb (before white background / clamp)
   float* bwd_scratch;    // [n][4]    per-ray scratch of the backward pass
@@ -70,6 +72,8 @@ inline Workspace carve_workspace(void* base, int n, int S) {
   w.ent = (uint2*)take((size_t)w.cap * 8);
   w.ent_w = (float*)take((size_t)w.cap * 4);
   w.ent_rgb = (float*)take((size_t)w.cap * 12);
+  w.ent_pen = (float*)take((size_t)w.cap * 4);
+  w.pen_sum = (float*)take((size_t)n * 4);
   w.acc = (float*)take((size_t)n * 4);
   w.rgb_sum = (float*)take((size_t)n * 12);
   w.bwd_scratch = (float*)take((size_t)n * 16);

@@ -245,7 +245,8 @@ __global__ void __launch_bounds__(256) k_composite(const FwdParams P) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ray = blockIdx.x * 8 + warp;
   if (ray >= P.n) return;
-  float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f;
+  float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, sp = 0.0f;
+  const bool ref = P.m.variant == TVM_VARIANT_REF;
   for (int b = lane; b < P.NB; b += 32) {
     uint32_t bits = P.ws.blk_mask[(size_t)ray * P.NB + b];
     if (bits == 0) continue;
@@ -260,6 +261,7 @@ __global__ void __launch_bounds__(256) k_composite(const FwdParams P) {
       s0 = fmaf(w, r, s0);
       s1 = fmaf(w, g, s1);
       s2 = fmaf(w, bl, s2);
+      if (ref) sp = fmaf(w, P.ws.ent_pen[e], sp);
       if (P.aux.rgb) {
         float* o = P.aux.rgb + ((size_t)ray * P.S + (size_t)b * 32 + s) * 3;
         o[0] = r; o[1] = g; o[2] = bl;
@@ -270,7 +272,9 @@ __global__ void __launch_bounds__(256) k_composite(const FwdParams P) {
   s0 = warp_sum(s0);
   s1 = warp_sum(s1);
   s2 = warp_sum(s2);
+  if (ref) sp = warp_sum(sp);
   if (lane == 0) {
+    if (ref) P.ws.pen_sum[ray] = sp;
     const float acc = P.ws.acc[ray];
     P.ws.rgb_sum[(size_t)ray * 3 + 0] = s0;
     P.ws.rgb_sum[(size_t)ray * 3 + 1] = s1;

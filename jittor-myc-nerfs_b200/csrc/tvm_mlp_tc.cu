@@ -218,9 +218,10 @@ __global__ void __launch_bounds__(kThreadsV2, 1) k_app_tc(const FwdParams P) {
           dir[1] = 2.0f * dot * ny - dy;
           dir[2] = 2.0f * dot * nz - dz;
           ndot = -dot;
-          if (P.aux.penalty && e < n_ent) {
+          if (e < n_ent) {
             const float pen = fmaxf(-dot, 0.0f);
-            pen_acc = fmaf(P.ws.ent_w[e], pen * pen, pen_acc);     // one atomic per warp at the end of the CTA
+            P.ws.ent_pen[e] = pen * pen;
+            if (P.aux.penalty) pen_acc = fmaf(P.ws.ent_w[e], pen * pen, pen_acc);     // one atomic per warp at the end of the CTA
           }
         }
         float s1[APP_DIM + 3], c1[APP_DIM + 3];

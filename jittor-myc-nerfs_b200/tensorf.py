@@ -112,13 +112,18 @@ class _RenderFn(torch.autograd.Function):
         ctx.model, ctx.flags, ctx.S = model, flags, S
         ctx.save_for_backward(rays, jitter if jitter is not None else torch.empty(0, device=rays.device), rgb)
         ctx.mark_non_differentiable(depth)
-        return rgb, depth
+        # REFTensoRF: the normal penalty (REFTensoRF.py:236-238) is a third, differentiable output
+        penalty = model._penalty_buf.clone() if model.VARIANT == L.VARIANT_REF else torch.zeros(1, device=rays.device)
+        return rgb, depth, penalty
 
     @staticmethod
-    def backward(ctx, d_rgb, _d_depth):
+    def backward(ctx, d_rgb, _d_depth, d_penalty):
         rays, jitter, rgb = ctx.saved_tensors
-        grads = ctx.model._backward_raw(rays, jitter if jitter.numel() else None, ctx.flags, ctx.S, rgb,
-                                        d_rgb.contiguous())
+        d_pen = None
+        if ctx.model.VARIANT == L.VARIANT_REF and d_penalty is not None:
+            d_pen = d_penalty.reshape(-1)[:1].to(torch.float32).contiguous()
+        d_rgb = torch.zeros_like(rgb) if d_rgb is None else d_rgb.contiguous()
+        grads = ctx.model._backward_raw(rays, jitter if jitter.numel() else None, ctx.flags, ctx.S, rgb, d_rgb, d_pen)
         return (None, None, None, None, None, *grads)
 
 
@@ -168,7 +173,7 @@ class TensorVMSplit(MaintainMixin, RegularizerMixin, torch.nn.Module):
         self.empty_space_skipping = True
         self.collect_counters = False
         self.counters = torch.zeros(L.CNT_WORDS, dtype=torch.int64, device=device)
-        self.ws_budget_bytes = int(float(os.environ.get("TVM_WS_GIB", "6")) * (1 << 30))
+        self.ws_budget_bytes = int(float(os.environ.get("TVM_WS_GIB", "8")) * (1 << 30))
         self.grad_sync = False          # set True (after dist.init_from_env) for data-parallel training
         self.grad_sync_group = None
         self._ws = None
@@ -289,7 +294,7 @@ class TensorVMSplit(MaintainMixin, RegularizerMixin, torch.nn.Module):
             setattr(s, name, at(name))
         if cls is L.TvmModel:
             s.variant = self.VARIANT
-            s.head_bias = at("head_bias") if self.VARIANT == L.VARIANT_REF else None
+        s.head_bias = at("head_bias") if self.VARIANT == L.VARIANT_REF else None
         return s
 
     def _pack(self, force=False):
@@ -440,7 +445,7 @@ class TensorVMSplit(MaintainMixin, RegularizerMixin, torch.nn.Module):
                                 _ptr(ws), ws.numel(), _stream_ptr()), "tvm_forward")
         return rgb, depth
 
-    def _backward_raw(self, rays, jitter, flags, S, rgb, d_rgb):
+    def _backward_raw(self, rays, jitter, flags, S, rgb, d_rgb, d_penalty=None):
         lib = L.load()
         n = rays.shape[0]
         model = self._model()
@@ -452,7 +457,7 @@ class TensorVMSplit(MaintainMixin, RegularizerMixin, torch.nn.Module):
         gs = self._struct_for(gp, L.TvmGrads)
         ws = self._workspace(n, S)
         L.check(lib.tvm_backward(C.byref(model), _ptr(rays), n, int(S), _ptr(jitter), flags, _ptr(rgb), _ptr(d_rgb),
-                                 C.byref(gs), _ptr(ws), ws.numel(), _stream_ptr()), "tvm_backward")
+                                 _ptr(d_penalty), C.byref(gs), _ptr(ws), ws.numel(), _stream_ptr()), "tvm_backward")
         if self.grad_sync:
             # data-parallel training: ONE all-reduce over the flat packed gradient buffer
             from .dist import allreduce_flat_
@@ -478,13 +483,18 @@ class TensorVMSplit(MaintainMixin, RegularizerMixin, torch.nn.Module):
         m = self.renderModule.mlp
         g_basis = torch.empty_like(self.basis_mat.weight)
         g_w1, g_w2 = torch.empty_like(m[0].weight), torch.empty_like(m[2].weight)
-        L.check(lib.tvm_unpack_linear(at("basis_t"), self.app_dim, 3 * Ca, 32, _ptr(g_basis), st), "tvm_unpack_linear")
+        L.check(lib.tvm_unpack_linear(at("basis_t"), self.app_dim, 3 * Ca, self.head_dim(), _ptr(g_basis), st), "tvm_unpack_linear")
         L.check(lib.tvm_unpack_linear(at("w1_t"), F, in_c, F, _ptr(g_w1), st), "tvm_unpack_linear")
         L.check(lib.tvm_unpack_linear(at("w2_t"), F, F, F, _ptr(g_w2), st), "tvm_unpack_linear")
         sl = lambda name, n: gp[items[name][0]:items[name][0] + n].clone()
         return [*(out[f"dp{k}"] for k in range(3)), *(out[f"dl{k}"] for k in range(3)),
                 *(out[f"ap{k}"] for k in range(3)), *(out[f"al{k}"] for k in range(3)), g_basis,
-                g_w1, sl("b1", F), g_w2, sl("b2", F), sl("w3", 3 * F).reshape(3, F), sl("b3", 3)]
+                g_w1, sl("b1", F), g_w2, sl("b2", F), sl("w3", 3 * F).reshape(3, F), sl("b3", 3),
+                *self._unpack_head_grads(gp, items)]
+
+    def _unpack_head_grads(self, gp, items):
+        """Gradients of the parameters `_param_list` appends after the MLP (none for TensorVMSplit)."""
+        return []
 
     # ---- reference API: the per-chunk call ----------------------------------------------------
     def forward(self, rays_chunk, white_bg=True, is_train=False, ndc_ray=False, N_samples=-1,
@@ -506,7 +516,10 @@ class TensorVMSplit(MaintainMixin, RegularizerMixin, torch.nn.Module):
         if needs_grad:
             if n > nmax:
                 raise ValueError(f"training chunk of {n} rays exceeds the workspace budget ({nmax} rays)")
-            return _RenderFn.apply(self, rays, jitter, flags, S, *self._param_list())
+            rgb, depth, penalty = _RenderFn.apply(self, rays, jitter, flags, S, *self._param_list())
+            if self.VARIANT == L.VARIANT_REF:
+                self.penalty = penalty          # train.py:253-257 reads tensorf.penalty and adds it to the loss
+            return rgb, depth
         if n <= nmax:
             return self._forward_raw(rays, jitter, flags, S)
         rgb = torch.empty((n, 3), dtype=torch.float32, device=rays.device)
@@ -535,8 +548,9 @@ class TensorVMSplit(MaintainMixin, RegularizerMixin, torch.nn.Module):
         for k, v in o.items():
             setattr(aux, k, v.data_ptr() if v is not None else None)
         if self.VARIANT == L.VARIANT_REF:
-            self.penalty.zero_()
-            aux.penalty = self.penalty.data_ptr()
+            self._penalty_buf.zero_()
+            aux.penalty = self._penalty_buf.data_ptr()
+            self.penalty = self._penalty_buf
         rgb_map, depth_map = self._forward_raw(rays, jitter, self._flags(white_bg), S, aux=aux)
         o.update(rgb_map=rgb_map, depth_map=depth_map)
         return o
@@ -554,12 +568,13 @@ class TensorVMSplit(MaintainMixin, RegularizerMixin, torch.nn.Module):
 class REFTensoRF(TensorVMSplit):
     """REFTensoRF (models/REFTensoRF.py:64-256): normal / diffuse / specular-tint / rho heads on the
     144-vector, reflected direction into MLPRender_Fea_Ref, side output `penalty` (train.py:253-257).
-    Forward only in this build (tvm_backward rejects TVM_VARIANT_REF)."""
+    The backward pass of this variant runs in fp32 (k_app_bwd<48>) whatever mlp_mode the forward used."""
     VARIANT = L.VARIANT_REF
 
     def init_render_func(self, shadingMode, pos_pe, view_pe, fea_pe, featureC, device):
         self.renderModule = MLPRender_Fea(self.app_dim, view_pe, fea_pe, featureC, extra_in=1).to(device)   # MLPRender_Fea_Ref
-        self.penalty = torch.zeros(1, dtype=torch.float32, device=device)
+        self._penalty_buf = torch.zeros(1, dtype=torch.float32, device=device)     # accumulated by the kernels
+        self.penalty = self._penalty_buf                                           # what train.py:253-257 reads
 
     def head_dim(self):
         return L.REF_HEAD_LD
@@ -603,19 +618,28 @@ class REFTensoRF(TensorVMSplit):
         self._packed[off:off + 64].zero_()
         self._packed[off:off + b.numel()].copy_(b)
 
-    def forward(self, rays_chunk, white_bg=True, is_train=False, ndc_ray=False, N_samples=-1,
-                additional_output=False, jitter=None):
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self._param_list()):
-            raise NotImplementedError("REFTensoRF backward is not built: call under torch.no_grad()")
-        return super().forward(rays_chunk, white_bg, is_train, ndc_ray, N_samples, additional_output, jitter)
-
-    execute = forward
+    def _unpack_head_grads(self, gp, items):
+        """[3*Ca][48] packed head gradients -> normal / diffuse / specular / rho weights and biases (order of _param_list)."""
+        lib, st = L.load(), _stream_ptr()
+        Ca = self.app_n_comp[0]
+        n_out = self.app_dim + 8
+        full = torch.empty((n_out, 3 * Ca), dtype=torch.float32, device=gp.device)
+        L.check(lib.tvm_unpack_linear(C.c_void_p(gp.data_ptr() + 4 * items["basis_t"][0]), n_out, 3 * Ca, L.REF_HEAD_LD,
+                                      _ptr(full), st), "tvm_unpack_linear")
+        hb = gp[items["head_bias"][0]:items["head_bias"][0] + n_out]
+        out, o = [], self.app_dim
+        for h in self._heads():
+            k = h.weight.shape[0]
+            out += [full[o:o + k].clone(), hb[o:o + k].clone()]
+            o += k
+        return out
 
     def _forward_raw(self, rays, jitter, flags, S, aux=None, out=None):
         if aux is None:
             aux = L.TvmAux()
-            self.penalty.zero_()
-            aux.penalty = self.penalty.data_ptr()
+            self._penalty_buf.zero_()
+            aux.penalty = self._penalty_buf.data_ptr()
+            self.penalty = self._penalty_buf
         return super()._forward_raw(rays, jitter, flags, S, aux=aux, out=out)
 
 

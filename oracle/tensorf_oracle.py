@@ -612,7 +612,7 @@ def work_counts(stages):
                 M_v=int(stages["ray_valid"].sum()), M_a=int(stages["app_mask"].sum()))
 
 
-def backward_case(case, d_rgb_map=None, dtype=torch.float64, opts=None, N_samples=-1, white_bg=True):
+def backward_case(case, d_rgb_map=None, dtype=torch.float64, opts=None, N_samples=-1, white_bg=True, penalty_weight=0.0):
     """Gradients of sum(rgb_map * d_rgb_map) (or of train.py:228's MSE against case['target'] when
     d_rgb_map is None) w.r.t. every parameter, in the reference's NCHW shapes (row a12)."""
     m = make_oracle(case, dtype=dtype, opts=opts, requires_grad=True)
@@ -624,7 +624,13 @@ def backward_case(case, d_rgb_map=None, dtype=torch.float64, opts=None, N_sample
         loss = torch.mean((rgb - tgt) ** 2)
     else:
         loss = torch.sum(rgb * torch.as_tensor(d_rgb_map, dtype=dtype))
+    penalty = None
+    if penalty_weight:
+        # train.py:253-255: total_loss += normal_vector_penalty_weight * tensorf.penalty (REFTensoRF only)
+        penalty = m.penalty
+        loss = loss + penalty_weight * penalty
     loss.backward()
     grads = {k: (v.grad.detach().numpy() if v.grad is not None else np.zeros(v.shape)) for k, v in
              m.named_parameters().items()}
-    return dict(loss=float(loss), rgb_map=rgb.detach().numpy(), grads=grads)
+    return dict(loss=float(loss), rgb_map=rgb.detach().numpy(), grads=grads,
+                penalty=None if penalty is None else float(penalty.detach()))

@@ -203,3 +203,38 @@ def test_graph_captured_step_matches_eager(env, mode):
     for a, b in zip(params["eager"], params["graph"]):
         assert float((a - b).abs().max()) <= (1e-3 if mode == "fp32" else 2e-2)
         assert float((a - b).abs().mean()) <= (1e-5 if mode == "fp32" else 1e-3)
+
+
+@pytest.mark.parametrize("regime,pw", [("R2", 0.5), ("R1", 0.0)])
+def test_reftensorf_backward(env, regime, pw):
+    """REFTensoRF (configs/Scar.txt: model_name = REFTensoRF, normal_vector_penalty_weight = 0.5): gradients of
+    sum(rgb_map * d) + pw * penalty w.r.t. every parameter incl. the four heads, against the fp64 oracle."""
+    pkg, torch, fx, orc = env
+    from util import gpu_model
+    n, S = 384, 139
+    case = fx.make_case(40, n, regime, mask_res=40, train=True, variant="ref")
+    d_rgb = (fx.target_rgb(n, seed=11) - 0.5).astype(np.float32)
+    ref = orc.backward_case(case, d_rgb_map=d_rgb.astype(np.float64), N_samples=S, white_bg=True, penalty_weight=pw)
+    model = gpu_model(pkg, case)
+    assert isinstance(model, pkg.REFTensoRF)
+    rays = torch.from_numpy(case["rays"]).cuda()
+    jit = torch.from_numpy(case["jitter"]).cuda()
+    rgb, _ = model(rays, is_train=True, white_bg=True, N_samples=S, jitter=jit)
+    loss = (rgb * torch.from_numpy(d_rgb).cuda()).sum()
+    if pw:
+        assert abs(float(model.penalty.detach().sum()) - ref["penalty"]) <= 1e-5 * max(1.0, abs(ref["penalty"]))
+        loss = loss + pw * model.penalty.sum()
+    loss.backward()
+    torch.cuda.synchronize()
+    names = _names(model) + [(f"{h}_linear.{k}", getattr(getattr(model, h + "_linear"), k))
+                             for h in ("normal", "diffuse", "specular") for k in ("weight", "bias")]
+    worst = {}
+    for name, p in names:
+        g, r = p.grad.detach().cpu().numpy().astype(np.float64), ref["grads"][name]
+        scale = np.abs(r).max()
+        assert scale > 0, name
+        worst[name] = np.abs(g - r).max() / scale
+        assert worst[name] <= GRAD_RTOL, f"{name}: {worst[name]:.3e}"
+    # rho only feeds the unused 1/rho argument of the MLP: zero gradient on both sides
+    assert float(model.rho_linear.weight.grad.abs().max()) == 0.0 and np.abs(ref["grads"]["rho_linear.weight"]).max() == 0.0
+    print(f"REF backward {regime} pw={pw}: worst", {k: f"{v:.1e}" for k, v in sorted(worst.items(), key=lambda kv: -kv[1])[:4]})
