@@ -500,6 +500,23 @@ def main():
     cnt = model.counters.cpu().numpy().astype(np.float64) / args.steps
     M_in, M_v, M_a = cnt[L.CNT_M_IN], cnt[L.CNT_M_V], cnt[L.CNT_M_A]
 
+    # L2 gather peak: the density planes (17.3 MB) and the whole model (69.5 MB) fit the 126 MB L2, so the gather
+    # stage is also quoted against pure 64-byte random gathers from an L2-resident buffer of those sizes
+    import ctypes as C
+    l2_peaks = {}
+    sink = torch.zeros(4, device=dev)
+    for name, mb in (("17MB", 17.3), ("70MB", 69.5)):
+        nfl = int(mb * 1e6 / 4) // 16 * 16
+        gbuf = torch.empty(nfl, dtype=torch.float32, device=dev).normal_()
+        groups, iters = 148 * 8 * 64 * 8, 16
+        run = lambda: L.check(L.load().tvm_bench_gather(C.c_void_p(gbuf.data_ptr()), nfl, groups, iters, C.c_void_p(sink.data_ptr()),
+                                                        C.c_void_p(torch.cuda.current_stream().cuda_stream)), "tvm_bench_gather")
+        run(); run()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); run(); b.record(); torch.cuda.synchronize()
+        l2_peaks[name] = groups * iters * 18 * 64.0 / (a.elapsed_time(b) * 1e-3) / 1e9
+        del gbuf
+
     # correctness of what was timed: a slice of the frame against the oracle (outside the timed region)
     check = None
     if rank == 0:
@@ -540,7 +557,11 @@ def main():
                           (app_ms * 1e-3) / 1e9 if app_ms else None,
                           "dense_TFLOPs": 79712.0 * M_a * args.steps / max(1, stage_cnt["app"]) / (app_ms * 1e-3) / 1e12
                           if app_ms else None},
-            "reference_equivalent_bytes_per_step": 40.0 * n + 32.0 * M_in + 1152.0 * M_v + 3456.0 * M_a}
+            "reference_equivalent_bytes_per_step": 40.0 * n + 32.0 * M_in + 1152.0 * M_v + 3456.0 * M_a,
+            "l2_gather_peak_GBps": l2_peaks,
+            "frac_of_l2_gather_peak": {"k_march_vs_17MB": achieved / l2_peaks["17MB"],
+                                       "k_app_vs_70MB": (bytes_app_step * args.steps / max(1, stage_cnt["app"]) / (app_ms * 1e-3) / 1e9 /
+                                                         l2_peaks["70MB"]) if app_ms else None}}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,

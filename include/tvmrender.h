@@ -293,6 +293,11 @@ int tvm_adam_step(const TvmAdamTensor* tensors_host, int n_tensors, float beta0,
  * Test hook: no reference counterpart.                                                                              */
 int tvm_selftest_umma(const float* P, const float* Q, const float* W, float* D1, float* D2, float* D3, void* stream);
 
+/* Measurement: pure 64-byte gathers (4 lanes x 16 B per tap, 18 taps in flight, the access shape of the density gather) at
+ * pseudo-random 64-byte texels of buf[n_floats]; n_groups lane groups x iters x 18 taps x 64 B are read.  With a buffer
+ * that fits L2 this is the "L2 gather peak" bench.py quotes beside the HBM roofline.  No reference counterpart. */
+int tvm_bench_gather(const float* buf, size_t n_floats, int n_groups, int iters, float* sink, void* stream);
+
 /* ---- measurement hooks (bench.py's roofline leg; off by default) ------------------------------ */
 /* When enabled, every kernel tvm_forward / tvm_backward launches is bracketed by cudaEvents on the
  * caller's stream.  Stages: see TVM_STAGE_*.  Process-global, not thread-safe: benchmarking only. */

@@ -77,7 +77,7 @@ EXPORTS = [
     "tvm_workspace_bytes", "tvm_forward", "tvm_forward_npp", "tvm_bg_fold", "tvm_bg_tc_bytes", "tvm_pack_bg_tc", "tvm_backward", "tvm_density_alpha", "tvm_mse_loss",
     "tvm_profile_enable", "tvm_profile_collect",
     "tvm_dense_alpha", "tvm_alpha_mask_from_dense", "tvm_filter_rays", "tvm_generate_rays", "tvm_upsample_grid",
-    "tvm_tv_loss", "tvm_l1_loss", "tvm_vector_diffs", "tvm_adam_step", "tvm_selftest_umma",
+    "tvm_tv_loss", "tvm_l1_loss", "tvm_vector_diffs", "tvm_adam_step", "tvm_selftest_umma", "tvm_bench_gather",
 ]
 
 
@@ -134,6 +134,7 @@ def load() -> C.CDLL:
     lib.tvm_l1_loss.argtypes = [vp, C.c_size_t, f32, vp, vp, vp]
     lib.tvm_vector_diffs.argtypes = [vp, i32, i32, f32, vp, vp, vp]
     lib.tvm_selftest_umma.argtypes = [vp] * 7
+    lib.tvm_bench_gather.argtypes = [vp, C.c_size_t, i32, i32, vp, vp]
     lib.tvm_adam_step.argtypes = [C.POINTER(TvmAdamTensor), i32, f32, f32, f32, i32, vp, vp]
     lib.tvm_backward.argtypes = [C.POINTER(TvmModel), vp, i32, i32, vp, u32, vp, vp, vp, C.POINTER(TvmGrads), vp,
                                  C.c_size_t, vp]

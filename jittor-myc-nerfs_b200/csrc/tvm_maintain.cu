@@ -267,3 +267,36 @@ extern "C" int tvm_upsample_grid(const float* src_nchw, int C, int H, int W, flo
   TVM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
+
+// ---- measurement: L2 gather peak ("report against a measured L2 gather peak") ---------------------------------
+// Pure 64-byte gathers with the access shape of k_march's density taps (4 lanes x float4 per tap, 18 independent taps in
+// flight per lane group) at pseudo-random texel indices of a buffer that fits the 126 MB L2; no arithmetic beyond a checksum.
+namespace tvm {
+__global__ void __launch_bounds__(256) k_gather_peak(const float4* __restrict__ buf, uint32_t n_texels, int iters,
+                                                     float* __restrict__ sink) {
+  const uint32_t group = (blockIdx.x * blockDim.x + threadIdx.x) >> 2, q = threadIdx.x & 3;
+  uint32_t state = group * 747796405u + 2891336453u;
+  float acc = 0.0f;
+  for (int it = 0; it < iters; ++it) {
+    float4 v[18];
+#pragma unroll
+    for (int t = 0; t < 18; ++t) {
+      state = state * 1664525u + 1013904223u;
+      const uint32_t texel = (uint32_t)(((uint64_t)(state >> 4) * n_texels) >> 28);
+      v[t] = __ldg(buf + (size_t)texel * 4 + q);
+    }
+#pragma unroll
+    for (int t = 0; t < 18; ++t) acc += v[t].x + v[t].y + v[t].z + v[t].w;
+  }
+  if (acc == 123.456f) sink[0] = acc;
+}
+}  // namespace tvm
+
+extern "C" int tvm_bench_gather(const float* buf, size_t n_floats, int n_groups, int iters, float* sink, void* stream) {
+  TVM_REQUIRE(buf && sink && n_floats >= 16 && n_groups > 0 && iters > 0, "bad arguments");
+  const uint32_t n_texels = (uint32_t)(n_floats / 16);
+  const int threads = n_groups * 4;
+  k_gather_peak<<<(threads + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const float4*)buf, n_texels, iters, sink);
+  TVM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
