@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(kThreadsV2, 1) k_app_tc(const FwdParams P) {
 
   if (warp >= kMlpWarps) {
     // =============================== gather group ================================================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 128;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
     const int gw = warp - kMlpWarps;
     constexpr int ROWS_PER_WARP = kRows / kGatherWarps;
     uint32_t it = 0;
@@ -123,71 +123,38 @@ __global__ void __launch_bounds__(kThreadsV2, 1) k_app_tc(const FwdParams P) {
       mbar_wait(&empty[s], (use & 1u) ^ 1u);          // stage free (first use of a stage passes at once)
       const uint32_t tile_base = tile * kRows;
       uint8_t* stage = sA0 + s * A0_STAGE;
-      {
-        // each 4-lane group gathers TWO consecutive entries (usually consecutive samples of one ray, half a voxel apart):
-        // when both fall into the same plane cell / line cell the second one reuses the first one's texels from registers
-        static_assert(ROWS_PER_WARP == 16, "two rows per 4-lane group");
-        const int rowA = gw * ROWS_PER_WARP + 2 * (lane >> 2), q = lane & 3;
-        const uint32_t eA = tile_base + rowA, eB = eA + 1;
-        const bool vA = eA < n_ent, vB = eB < n_ent;
-        uint8_t* arowA = stage + rowA * 16;
-        uint8_t* arowB = arowA + 16;
-        Axis axA[3], axB[3];
-        {
+#pragma unroll 1
+      for (int pass = 0; pass < ROWS_PER_WARP / 8; ++pass) {
+        const int row = gw * ROWS_PER_WARP + pass * 8 + (lane >> 2), q = lane & 3;
+        const uint32_t e = tile_base + row;
+        uint8_t* arow = stage + row * 16;
+        if (e < n_ent) {
+          const uint2 en = P.ws.ent[e];
           float u[3], dir[3];
-          if (vA) {
-            const uint2 en = P.ws.ent[eA];
-            entry_coords(m, P.rays, P.jitter, en.x, en.y, P.S, u, dir);
+          entry_coords(m, P.rays, P.jitter, en.x, en.y, P.S, u, dir);
+          Axis ax[3];
 #pragma unroll
-            for (int i = 0; i < 3; ++i) axA[i] = axis_taps(u[i], m.grid[i]);
-          }
-          if (vB) {
-            const uint2 en = P.ws.ent[eB];
-            entry_coords(m, P.rays, P.jitter, en.x, en.y, P.S, u, dir);
+          for (int i = 0; i < 3; ++i) ax[i] = axis_taps(u[i], m.grid[i]);
 #pragma unroll
-            for (int i = 0; i < 3; ++i) axB[i] = axis_taps(u[i], m.grid[i]);
-          }
-        }
+          for (int kk = 0; kk < 3; ++kk) {
+            const VmTaps t = vm_taps(m, ax, kk);
 #pragma unroll
-        for (int kk = 0; kk < 3; ++kk) {
-          VmTaps tA = {}, tB = {};
-          if (vA) tA = vm_taps(m, axA, kk);
-          if (vB) tB = vm_taps(m, axB, kk);
-          const bool same_p = vA && vB && tA.o00 == tB.o00 && tA.o01 == tB.o01 && tA.o10 == tB.o10 && tA.o11 == tB.o11;
-          const bool same_l = vA && vB && tA.l0 == tB.l0 && tA.l1 == tB.l1;
-          const float* pl = m.app_plane[kk];
-          const float* ln = m.app_line[kk];
-#pragma unroll
-          for (int c = q * 4; c < CA; c += 16) {
-            const int k = kk * CA + c;
-            float4 a = {}, b = {}, cc = {}, d = {}, l0 = {}, l1 = {};
-            float4 a2 = {}, b2 = {}, c2 = {}, d2 = {}, l02 = {}, l12 = {};
-            if (vA) {
-              a = ldg4(pl + (size_t)tA.o00 * CA + c);  b = ldg4(pl + (size_t)tA.o01 * CA + c);
-              cc = ldg4(pl + (size_t)tA.o10 * CA + c); d = ldg4(pl + (size_t)tA.o11 * CA + c);
-              l0 = ldg4(ln + (size_t)tA.l0 * CA + c);  l1 = ldg4(ln + (size_t)tA.l1 * CA + c);
+            for (int c = q * 4; c < CA; c += 16) {
+              float4 pv, lv;
+              vm_sample4(m.app_plane[kk], m.app_line[kk], t, CA, c, pv, lv);
+              const int k = kk * CA + c;
+              uint2 packed = make_uint2(pack_bf16(pv.x * lv.x, pv.y * lv.y), pack_bf16(pv.z * lv.z, pv.w * lv.w));
+              *reinterpret_cast<uint2*>(arow + (k >> 3) * LBO_A + (k & 7) * 2) = packed;
             }
-            if (vB && !same_p) {
-              a2 = ldg4(pl + (size_t)tB.o00 * CA + c); b2 = ldg4(pl + (size_t)tB.o01 * CA + c);
-              c2 = ldg4(pl + (size_t)tB.o10 * CA + c); d2 = ldg4(pl + (size_t)tB.o11 * CA + c);
-            }
-            if (vB && !same_l) {
-              l02 = ldg4(ln + (size_t)tB.l0 * CA + c); l12 = ldg4(ln + (size_t)tB.l1 * CA + c);
-            }
-            if (same_p) { a2 = a; b2 = b; c2 = cc; d2 = d; }
-            if (same_l) { l02 = l0; l12 = l1; }
-            auto emit = [&](uint8_t* arow, const VmTaps& t, const float4& A, const float4& B_, const float4& C_, const float4& D_,
-                            const float4& L0, const float4& L1) {
-              const float px = A.x * t.nw + B_.x * t.ne + C_.x * t.sw + D_.x * t.se, py = A.y * t.nw + B_.y * t.ne + C_.y * t.sw + D_.y * t.se;
-              const float pz = A.z * t.nw + B_.z * t.ne + C_.z * t.sw + D_.z * t.se, pw = A.w * t.nw + B_.w * t.ne + C_.w * t.sw + D_.w * t.se;
-              const float lx = L0.x * t.lw0 + L1.x * t.lw1, ly = L0.y * t.lw0 + L1.y * t.lw1;
-              const float lz = L0.z * t.lw0 + L1.z * t.lw1, lw = L0.w * t.lw0 + L1.w * t.lw1;
-              *reinterpret_cast<uint2*>(arow + (k >> 3) * LBO_A + (k & 7) * 2) =
-                  make_uint2(pack_bf16(px * lx, py * ly), pack_bf16(pz * lz, pw * lw));
-            };
-            emit(arowA, tA, a, b, cc, d, l0, l1);        // invalid entries: all-zero taps -> zero row
-            emit(arowB, tB, a2, b2, c2, d2, l02, l12);
           }
+        } else {
+#pragma unroll
+          for (int kk = 0; kk < 3; ++kk)
+#pragma unroll
+            for (int c = q * 4; c < CA; c += 16) {
+              const int k = kk * CA + c;
+              *reinterpret_cast<uint2*>(arow + (k >> 3) * LBO_A + (k & 7) * 2) = make_uint2(0u, 0u);
+            }
         }
       }
       fence_async_smem();
