@@ -273,3 +273,66 @@ def test_streamed_host_render_matches_resident(env):
     assert out[0] is rgb_host and out[2] is depth_host
     assert torch.equal(rgb_host, rgb.cpu()) and torch.equal(depth_host, depth.cpu())
     assert float(rgb_host.min()) < 0.99      # the frame is not empty
+
+
+def test_full_frame_properties(env):
+    """BASELINE configs[1] at full size (800x800 rays, 300^3 grid, 200^3 mask, S = 1036) through size-independent
+    properties: chunking invariance, early-termination error bound, ray-order invariance, background rays, work counters
+    identical between the fp32 and tensor-core heads, colour agreement (north_star: 1e-2 abs, PSNR delta < 0.01 dB), and a
+    slice of the frame against the oracle."""
+    pkg, torch, fx, orc = env
+    from util import gpu_model, psnr
+    case = fx.make_case(300, 0, "R1", full_frame=True)
+    rays_np = case["rays"]
+    n = rays_np.shape[0]
+    assert n == 640000
+    rays = torch.from_numpy(rays_np).cuda()
+    model = gpu_model(pkg, case, mlp_mode="fp32")
+    assert model.nSamples == 1036
+    model.collect_counters = True
+
+    def render(m, r, **kw):
+        m.counters.zero_()
+        with torch.no_grad():
+            rgb, depth = m(r, white_bg=True, is_train=False, **kw)
+        torch.cuda.synchronize()
+        return rgb, depth, m.counters.cpu().numpy().copy()
+
+    rgb32, dep32, cnt32 = render(model, rays)
+    # (a) chunking: the default 3-chunk render equals a 7-chunk render bit for bit
+    model.ws_budget_bytes //= 3
+    rgb_c, dep_c, cnt_c = render(model, rays)
+    model.ws_budget_bytes *= 3
+    assert torch.equal(rgb_c, rgb32) and torch.equal(dep_c, dep32) and np.array_equal(cnt_c[:3], cnt32[:3])
+    # (b) early ray termination changes colours by far less than the fp32 tolerance
+    model.early_termination = False
+    rgb_n, dep_n, cnt_n = render(model, rays)
+    model.early_termination = True
+    assert float((rgb_n - rgb32).abs().max()) <= 2e-6 and cnt_n[pkg._lib.CNT_M_V] >= cnt32[pkg._lib.CNT_M_V]
+    # (c) ray order does not matter
+    perm = torch.randperm(n, generator=torch.Generator().manual_seed(1)).cuda()
+    rgb_p, dep_p, _ = render(model, rays[perm].contiguous())
+    assert torch.equal(rgb_p, rgb32[perm]) and torch.equal(dep_p, dep32[perm])
+    # (d) rays that never meet the mask see the white background exactly; everything stays in [0, 1]
+    miss = ~model.filtering_mask(rays, N_samples=1036)
+    assert int(miss.sum()) > 10000 and torch.all(rgb32[miss] == 1.0)
+    assert float(rgb32.min()) >= 0.0 and float(rgb32.max()) <= 1.0
+    # (e) tensor-core head: same samples, colours within the north_star tolerance
+    m16 = gpu_model(pkg, case, mlp_mode="bf16")
+    m16.collect_counters = True
+    rgb16, dep16, cnt16 = render(m16, rays)
+    assert np.array_equal(cnt16[:4], cnt32[:4])                      # M_in, M_v, M_a, rays: identical masks
+    assert torch.equal(dep16, dep32)
+    err = float((rgb16 - rgb32).abs().max())
+    ps = psnr(rgb16.cpu().numpy(), rgb32.cpu().numpy())
+    # (f) a slice against the oracle, and the PSNR of both heads against it
+    sl = slice(n // 2 + 80, n // 2 + 80 + 640)
+    ref = orc.run_case(dict(case, rays=rays_np[sl]), want_stages=False)
+    e32 = float(np.abs(rgb32[sl].cpu().numpy() - ref["rgb_map"]).max())
+    e16 = float(np.abs(rgb16[sl].cpu().numpy() - ref["rgb_map"]).max())
+    p32, p16 = psnr(rgb32[sl].cpu().numpy(), ref["rgb_map"]), psnr(rgb16[sl].cpu().numpy(), ref["rgb_map"])
+    print(f"full frame: M_in={cnt32[0]} M_v={cnt32[1]} M_a={cnt32[2]}; bf16 vs fp32 max {err:.2e}, PSNR {ps:.1f} dB; "
+          f"vs oracle fp32 {e32:.2e} ({p32:.1f} dB) bf16 {e16:.2e} ({p16:.1f} dB)")
+    assert err <= 1e-2 and ps >= 60.0
+    assert e32 <= 1e-4 and e16 <= 1e-2
+    assert np.abs(dep32[sl].cpu().numpy() - ref["depth_map"]).max() <= 1e-3
