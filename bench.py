@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-chunks", type=int, default=256,
                     help="chunks of 1024 rays the CPU baseline renders (256 = 41%% of the frame, 10-30 s of CPU work)")
+    ap.add_argument("--variant", default="vm", choices=["vm", "ref"], help="model of the train workload (ref = REFTensoRF, "
+                    "configs/Scar.txt, with normal_vector_penalty_weight 0.5)")
     ap.add_argument("--workload", default="frame", choices=["frame", "train", "npp", "ref", "maintain"],
                     help="frame = BASELINE configs[1] (the contract line); train = configs[2] (4096-ray fwd+bwd step, "
                          "128^3 grid); npp / ref = configs[3] (NeRF++ background / Ref-NeRF appearance, full frame). "
@@ -275,7 +277,7 @@ def run_side_workload(args):
     reg = fx.REGIMES[args.regime]
     train = args.workload == "train"
     G = args.grid if (args.grid != GRID or not train) else 128
-    variant = {"npp": "npp", "ref": "ref"}.get(args.workload, "vm")
+    variant = {"npp": "npp", "ref": "ref"}.get(args.workload, args.variant if train else "vm")
     mp = fx.make_model(G, density_shift=reg["density_shift"], variant=variant)
     vol = fx.ball_alpha_volume(MASK_RES if G > 128 else 128) if reg["mask"] else None
     model = pkg.model_from_params(mp, f"cuda:{local_rank}", vol, mp.aabb.copy(), args.mlp)
@@ -309,6 +311,8 @@ def run_side_workload(args):
                 p.grad = None
             rgb, _ = model(rays, is_train=True, white_bg=True, N_samples=S, jitter=jit)
             loss = torch.mean((rgb - tgt) ** 2)
+            if variant == "ref":
+                loss = loss + 0.5 * model.penalty.sum()              # train.py:253-255, configs/Scar.txt:7
             if full["on"]:
                 loss = loss + model.TV_loss_density(tvreg) * 2.0 + model.TV_loss_app(tvreg) * 2.0
             loss.backward()
@@ -355,7 +359,7 @@ def run_side_workload(args):
     stage_ms, stage_cnt = L.profile_collect()
     L.profile_enable(False)
     cnt = model.counters.cpu().numpy().astype(np.float64) / args.steps
-    name = {"train": f"configs[2]: training step fwd+bwd (MSE), {n} rays, {G}^3 grid, S={S}, mlp {args.mlp}",
+    name = {"train": f"configs[2]: training step fwd+bwd (MSE), {n} rays, {G}^3 grid, S={S}, mlp {args.mlp}, model {variant}",
             "npp": f"configs[3]: NerfPlusPlus full frame ({n} rays), {G}^3 grid, 512 background samples/ray",
             "ref": f"configs[3]: REFTensoRF full frame ({n} rays), {G}^3 grid"}[args.workload]
     line = {"metric": f"TensoRF-VM rays/sec ({args.workload})", "value": n * world / (ms / args.steps * 1e-3), "unit": UNIT,
@@ -382,7 +386,8 @@ def run_side_workload(args):
         # the same full step captured once into a CUDA graph (TrainStepGraph) and replayed: no host time between kernels
         model.collect_counters = False
         L.profile_enable(False)
-        gstep = pkg.TrainStepGraph(model, opt, n, S, white_bg=True, TV_weight_density=2.0, TV_weight_app=2.0)
+        gstep = pkg.TrainStepGraph(model, opt, n, S, white_bg=True, TV_weight_density=2.0, TV_weight_app=2.0,
+                                   normal_vector_penalty_weight=0.5 if variant == "ref" else 0.0)
         gstep.step(rays, tgt)
         ms_graph = timed(args.steps, lambda: gstep.step(rays, tgt)) / args.steps
         line["full_step_cuda_graph"] = {"ms_per_step": ms_graph, "rays_per_s": n * world / (ms_graph * 1e-3),

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define TVM_ABI_VERSION 11
+#define TVM_ABI_VERSION 12
 
 /* flags for tvm_forward / tvm_backward */
 #define TVM_WHITE_BG      0x1u  /* rgb_map += 1 - acc_map          (tensorBase.py:523-524) */
@@ -231,8 +231,7 @@ int tvm_bg_fold(const float* remap_w /*[256][128]*/, const float* remap_b /*[256
 /* Backward of tvm_forward w.r.t. every parameter, given d_rgb_map [n][3] = dL/d rgb_map
  * (row a12 of SURVEY §8a; coordinates are detached, depth carries no gradient).  Must follow a
  * tvm_forward with the same arguments on the same workspace.  TVM_VARIANT_REF: d_penalty is a DEVICE scalar
- * dL/d penalty (train.py:253-255: normal_vector_penalty_weight) or NULL; the appearance backward of that variant
- * always runs in fp32.                                                                                   */
+ * dL/d penalty (train.py:253-255: normal_vector_penalty_weight) or NULL.                                  */
 int tvm_backward(const TvmModel* m_host, const float* rays, int n_rays, int n_samples,
                  const float* jitter, uint32_t flags, const float* rgb_map, const float* d_rgb_map,
                  const float* d_penalty, const TvmGrads* grads_host, void* ws, size_t ws_bytes, void* stream);
@@ -266,11 +265,14 @@ int tvm_generate_rays(const float* c2w_host, int H, int W, float fx, float fy, f
 int tvm_upsample_grid(const float* src_nchw, int C, int H, int W, float* dst_nchw, int H2, int W2, void* stream);
 
 /* Regularisers of train.py:233-251, value and gradient in one pass: *loss_accum += weight * f(x) (device scalar, may be NULL),
- * grad += weight * df/dx (same shape as x, may be NULL).  TVLoss (utils.py:123-142) of one plane [1][C][H][W];
+ * grad += weight * df/dx (same shape as x, may be NULL).  weight_dev (nullable): DEVICE scalar multiplied into `weight`
+ * (the per-step weight of a replayed CUDA graph).  TVLoss (utils.py:123-142) of one plane [1][C][H][W];
  * density_L1's mean |x| (tensoRF.py:191-195); vectorDiffs (tensoRF.py:177-186) of one line [1][C][L][1].                        */
-int tvm_tv_loss(const float* plane_nchw, int C, int H, int W, float weight, float* loss_accum, float* grad_nchw, void* stream);
-int tvm_l1_loss(const float* x, size_t n, float weight, float* loss_accum, float* grad, void* stream);
-int tvm_vector_diffs(const float* line_cl, int C, int L, float weight, float* loss_accum, float* grad, void* stream);
+int tvm_tv_loss(const float* plane_nchw, int C, int H, int W, float weight, const float* weight_dev, float* loss_accum,
+                float* grad_nchw, void* stream);
+int tvm_l1_loss(const float* x, size_t n, float weight, const float* weight_dev, float* loss_accum, float* grad, void* stream);
+int tvm_vector_diffs(const float* line_cl, int C, int L, float weight, const float* weight_dev, float* loss_accum, float* grad,
+                     void* stream);
 /* jt.optim.Adam.step (train.py:187,261) over n_tensors parameter tensors in one launch per TVM_ADAM_MAX_TENSORS:
  * m = b0 m + (1-b0) g; v = b1 v + (1-b1) g^2; p -= m * (lr sqrt(1-b1^step)/(1-b0^step)) / (sqrt(v) + eps); step is 1-based.
  * hyper_dev (nullable): DEVICE array {sqrt(1-b1^step)/(1-b0^step), lr[0], lr[1], ...}; when given it overrides `step` and the

@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libtvmrender.so")
-ABI_VERSION = 11
+ABI_VERSION = 12
 
 # flags (tvmrender.h)
 WHITE_BG = 0x1
@@ -130,9 +130,9 @@ def load() -> C.CDLL:
     lib.tvm_filter_rays.argtypes = [C.POINTER(TvmModel), vp, i32, i32, i32, vp, vp]
     lib.tvm_generate_rays.argtypes = [C.POINTER(C.c_float), i32, i32, f32, f32, f32, f32, i32, i32, vp, vp]
     lib.tvm_upsample_grid.argtypes = [vp, i32, i32, i32, vp, i32, i32, vp]
-    lib.tvm_tv_loss.argtypes = [vp, i32, i32, i32, f32, vp, vp, vp]
-    lib.tvm_l1_loss.argtypes = [vp, C.c_size_t, f32, vp, vp, vp]
-    lib.tvm_vector_diffs.argtypes = [vp, i32, i32, f32, vp, vp, vp]
+    lib.tvm_tv_loss.argtypes = [vp, i32, i32, i32, f32, vp, vp, vp, vp]
+    lib.tvm_l1_loss.argtypes = [vp, C.c_size_t, f32, vp, vp, vp, vp]
+    lib.tvm_vector_diffs.argtypes = [vp, i32, i32, f32, vp, vp, vp, vp]
     lib.tvm_selftest_umma.argtypes = [vp] * 7
     lib.tvm_bench_gather.argtypes = [vp, C.c_size_t, i32, i32, vp, vp]
     lib.tvm_adam_step.argtypes = [C.POINTER(TvmAdamTensor), i32, f32, f32, f32, i32, vp, vp]

@@ -573,7 +573,7 @@ extern "C" int tvm_backward(const TvmModel* m_host, const float* rays, int n_ray
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if ((flags & TVM_MLP_MASK) == TVM_MLP_BF16 && !ref) {
+  if ((flags & TVM_MLP_MASK) == TVM_MLP_BF16) {
     // appearance backward on the tensor cores (bf16 operands, fp32 accumulation; gradients to ~1e-2 relative)
     ProfileScope prof(TVM_STAGE_BWD_APP, stream);
     if (int rc = launch_app_bwd_tc(B, sms, stream)) return rc;

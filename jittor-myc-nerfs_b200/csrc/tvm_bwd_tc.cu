@@ -20,9 +20,11 @@
 //   dF   = positional-encoding backward of dX (CUDA cores), written over X[:, 0:32)
 //   dH   = dF basis              A = dF (K),  B = forward basis image (MN)
 //   dBasis^T = H^T dF            A = H (MN, two overlapping 128-row windows of the 144 channels), B = dF (MN); flushed per tile
+//   (REFTensoRF: dF carries the 48 stacked head gradients -- features, normal, diffuse, specular -- after the reflection /
+//    dot-product / normalisation / penalty backward on CUDA cores)
 //   scatter dH into the appearance planes / lines with red.global.add.v4.f32 (all 12 warps, 4 lanes per sample)
 //
-// The persistent accumulators (dW2 128 + dW1 160 + dW3 16 TMEM columns) are flushed once per CTA.
+// The persistent accumulators (dW2 128 + dW1 160 + dW3 16 TMEM columns, after 160 working columns) are flushed once per CTA.
 #include "tvm_bwd.cuh"
 #include "tvm_tc.cuh"
 
@@ -33,40 +35,52 @@ using namespace tc;
 
 constexpr int kRowWarps = 4, kHelperWarps = 8;
 constexpr int kThreads = (kRowWarps + kHelperWarps) * 32;
-constexpr int CA = 48, APP_DIM = 27, K0 = 3 * CA, IN_C = 150, K1 = 160, NH = 32;
-constexpr int PF = APP_DIM + 3, NF = 2 * APP_DIM, PV = PF + 2 * NF, NV = 6;      // column map of X (tensorBase.py:76-83)
-constexpr int kDoChunk = 19, kDoCol = kDoChunk * 8;                                // dO parked in X columns 152..154
+constexpr int CA = 48, APP_DIM = 27, K0 = 3 * CA, K1 = 160;
+constexpr int NF = 2 * APP_DIM, NV = 6;                 // PE widths (fea_pe = view_pe = 2)
+constexpr int kDoChunk = 19, kDoCol = kDoChunk * 8;     // dO parked in X columns 152..154 (padding of the 150/151 real columns)
 
 constexpr uint32_t kLbo = kRows * 16;                  // 2048: next 8 columns of a 128-row image
-// TMEM columns
-constexpr uint32_t cWork = 0, cBasis = 128, cDBt1 = 144, cDBt2 = 176, cDW2 = 208, cDW1 = 336, cDW3 = 496;
+// TMEM columns: [0,160) working accumulators (forward layers, dY1, dX, dH, dBasis^T windows), then the persistent dW2, dW1, dW3
+constexpr uint32_t cWork = 0, cBasis = 0, cDW2 = 160, cDW1 = 288, cDW3 = 448;
 
 __device__ __forceinline__ void row_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 __device__ __forceinline__ float bf_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 
+// REF = REFTensoRF (models/REFTensoRF.py): 48 stacked head outputs (basis | normal | diffuse | specular | rho), MLP input
+// [-d.n, feat, reflection, PE(feat), PE(reflection)], rgb = tint * rgb_s + rgb_d, normal penalty.
+template <bool REF>
 __global__ void __launch_bounds__(kThreads, 1) k_app_bwd_tc(const BwdParams Bp) {
+  constexpr int NH = REF ? TVM_REF_HEAD_LD : 32;
+  constexpr int C0 = REF ? 1 : 0;                                      // REF: column 0 of X is -d.n
+  constexpr int IN_C = 150 + C0;
+  constexpr int PF = C0 + APP_DIM + 3, PV = PF + 2 * NF;               // column map of X (tensorBase.py:76-83, REFTensoRF.py:19-25)
+  constexpr uint32_t cDBt1 = 0, cDBt2 = NH;
   extern __shared__ __align__(128) uint8_t smem[];
   const FwdParams& P = Bp.f;
   const TvmModel& m = P.m;
   const Image img(CA, IN_C, NH);
+  // REF: the 13.8 KB head image leaves no room for the fp32 tail (biases, W3) in shared memory: it is read through L1
+  const uint32_t w_bytes = REF ? img.off_f32 : img.bytes;
   uint8_t* sW = smem;
-  uint8_t* sH = smem + ((img.bytes + 127) & ~127u);      // [128 x 144] bf16: H, later dH
+  uint8_t* sH = smem + ((w_bytes + 127) & ~127u);        // [128 x 144] bf16: H, later dH
   uint8_t* sX = sH + kRows * K0 * 2;                     // [128 x 160] bf16: X (+ dO), later dF in columns 0..31
   uint8_t* sY1 = sX + kRows * K1 * 2;                    // [128 x 128] bf16: Y1, later G1
   uint8_t* sG2 = sY1 + kRows * 128 * 2;                  // [128 x 128] bf16: Y2, later G2
   uint64_t* mma_bar = reinterpret_cast<uint64_t*>(sG2 + kRows * 128 * 2);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
-  const float* sB1 = reinterpret_cast<const float*>(sW + img.off_f32);
+  const float* sB1 = REF ? reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(m.tc_weights) + img.off_f32)
+                         : reinterpret_cast<const float*>(sW + img.off_f32);
   const float* sB2 = sB1 + 128;
   const float* sW3 = sB2 + 128;
   const float* sB3 = sW3 + 3 * 128;
+  const float* sHB = sB3 + 4;                            // REF: biases of the stacked heads [48]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   {
     const uint4* src = reinterpret_cast<const uint4*>(m.tc_weights);
     uint4* dst = reinterpret_cast<uint4*>(sW);
-    for (uint32_t i = tid; i < img.bytes / 16; i += kThreads) dst[i] = __ldg(src + i);
+    for (uint32_t i = tid; i < w_bytes / 16; i += kThreads) dst[i] = __ldg(src + i);
   }
   if (tid == 0) {
     mbar_init(mma_bar, 1);
@@ -93,6 +107,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_app_bwd_tc(const BwdParams Bp) 
   uint32_t phase = 0;
   bool first = true;
   float db3[3] = {0.0f, 0.0f, 0.0f};     // row threads: sum of dO over their rows
+  float dhb[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};   // REF row threads: sum of the head-output gradients
+  const float dpen = (REF && Bp.d_penalty) ? *Bp.d_penalty : 0.0f;
   float dbias = 0.0f;                    // helper threads: column sum of G2 (warps 4-7) / G1 (warps 8-11)
 
   auto mma_wait = [&]() {
@@ -109,7 +125,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_app_bwd_tc(const BwdParams Bp) 
   for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const uint32_t tile_base = tile * kRows;
     // ================================ gather (helper warps) ==============================================
-    float dir[3] = {0.0f, 0.0f, 0.0f}, gw[3] = {0.0f, 0.0f, 0.0f};
+    float dir[3] = {0.0f, 0.0f, 0.0f}, gw[3] = {0.0f, 0.0f, 0.0f}, wgt = 0.0f;
     if (warp >= kRowWarps) {
       const int gwi = warp - kRowWarps;
 #pragma unroll 1
@@ -154,8 +170,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_app_bwd_tc(const BwdParams Bp) 
         dir[1] = P.rays[6 * (size_t)ray + 4];
         dir[2] = P.rays[6 * (size_t)ray + 5];
         const float4 g = gray[ray];
-        const float w = P.ws.ent_w[e];
-        gw[0] = w * g.x; gw[1] = w * g.y; gw[2] = w * g.z;      // d (w rgb . g) / d rgb
+        wgt = P.ws.ent_w[e];
+        gw[0] = wgt * g.x; gw[1] = wgt * g.y; gw[2] = wgt * g.z;      // d (w rgb . g) / d rgb
       }
     }
     fence_async_smem();
@@ -179,22 +195,42 @@ __global__ void __launch_bounds__(kThreads, 1) k_app_bwd_tc(const BwdParams Bp) 
         umma_commit(mma_bar);
       }
       mma_wait();
+      // REF geometry kept for the backward: view d = -dir, raw normal, unit normal, d.n, tint
+      float vd[3] = {-dir[0], -dir[1], -dir[2]}, nraw2 = 0.0f, ninv = 0.0f, nh[3] = {0.0f, 0.0f, 0.0f}, dotp = 0.0f, tint = 1.0f;
       {
-        // ---- epi0: X = [feat, dir, sin/cos PE] (tensorBase.py:76-83, 9-15); columns 150..159 = 0 -----
+        // ---- epi0: X = [(-d.n), feat, dir | reflection, sin/cos PE] (tensorBase.py:76-83, 9-15; REFTensoRF.py:216-232) --
         float x[32];
         tmem_ld32(lane_addr + cBasis, x);
+        float ndot = 0.0f;
+        if (REF) {
+          float hx[16];
+          tmem_ld16(lane_addr + cBasis + 32, hx);
+          auto head = [&](int o) { return (o < 32 ? x[o] : hx[o - 32]) + sHB[o]; };
+          const float v0 = head(APP_DIM), v1 = head(APP_DIM + 1), v2 = head(APP_DIM + 2);
+          tint = fmaxf(head(APP_DIM + 6), 0.0f);
+          nraw2 = v0 * v0 + v1 * v1 + v2 * v2;
+          ninv = rsqrtf(fmaxf(nraw2, 1e-30f));
+          nh[0] = v0 * ninv; nh[1] = v1 * ninv; nh[2] = v2 * ninv;
+          dotp = vd[0] * nh[0] + vd[1] * nh[1] + vd[2] * nh[2];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) dir[c] = 2.0f * dotp * nh[c] - vd[c];      // reflection replaces the view direction
+          ndot = -dotp;
+        }
         float s1[APP_DIM + 3], c1[APP_DIM + 3];
 #pragma unroll
         for (int o = 0; o < APP_DIM; ++o) __sincosf(x[o], &s1[o], &c1[o]);
 #pragma unroll
         for (int o = 0; o < 3; ++o) __sincosf(dir[o], &s1[APP_DIM + o], &c1[APP_DIM + o]);
-        auto column = [&](int c) -> float {
+        auto column = [&](int cc) -> float {
+          if (REF && cc == 0) return ndot;
+          const int c = cc - C0;
+          constexpr int pf = APP_DIM + 3, pv = pf + 2 * NF;
           if (c < APP_DIM) return x[c];
-          if (c < PF) return dir[c - APP_DIM];
-          if (c < PF + NF) { const int o = (c - PF) >> 1; return ((c - PF) & 1) ? 2.0f * s1[o] * c1[o] : s1[o]; }
-          if (c < PV) { const int o = (c - PF - NF) >> 1; return ((c - PF - NF) & 1) ? 1.0f - 2.0f * s1[o] * s1[o] : c1[o]; }
-          if (c < PV + NV) { const int o = APP_DIM + ((c - PV) >> 1); return ((c - PV) & 1) ? 2.0f * s1[o] * c1[o] : s1[o]; }
-          if (c < PV + 2 * NV) { const int o = APP_DIM + ((c - PV - NV) >> 1); return ((c - PV - NV) & 1) ? 1.0f - 2.0f * s1[o] * s1[o] : c1[o]; }
+          if (c < pf) return dir[c - APP_DIM];
+          if (c < pf + NF) { const int o = (c - pf) >> 1; return ((c - pf) & 1) ? 2.0f * s1[o] * c1[o] : s1[o]; }
+          if (c < pv) { const int o = (c - pf - NF) >> 1; return ((c - pf - NF) & 1) ? 1.0f - 2.0f * s1[o] * s1[o] : c1[o]; }
+          if (c < pv + NV) { const int o = APP_DIM + ((c - pv) >> 1); return ((c - pv) & 1) ? 2.0f * s1[o] * c1[o] : s1[o]; }
+          if (c < pv + 2 * NV) { const int o = APP_DIM + ((c - pv - NV) >> 1); return ((c - pv - NV) & 1) ? 1.0f - 2.0f * s1[o] * s1[o] : c1[o]; }
           return 0.0f;
         };
 #pragma unroll
@@ -242,7 +278,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_app_bwd_tc(const BwdParams Bp) 
       }
       mma_wait();
       uint32_t relu2[4];
-      float dO[3];
+      float dO[3], dtint = 0.0f;
       {
         float o0 = sB3[0], o1 = sB3[1], o2 = sB3[2];
 #pragma unroll
@@ -267,9 +303,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_app_bwd_tc(const BwdParams Bp) 
                            pack_bf16(y[g * 8 + 4], y[g * 8 + 5]), pack_bf16(y[g * 8 + 6], y[g * 8 + 7]));
         }
         const float r0 = 1.0f / (1.0f + __expf(-o0)), r1 = 1.0f / (1.0f + __expf(-o1)), r2 = 1.0f / (1.0f + __expf(-o2));
-        dO[0] = gw[0] * r0 * (1.0f - r0);       // d/d logit of w * rgb . g   (gw = 0 on padding rows)
-        dO[1] = gw[1] * r1 * (1.0f - r1);
-        dO[2] = gw[2] * r2 * (1.0f - r2);
+        // rgb = tint * rgb_s + rgb_d (REF; tint = 1, rgb_d = 0 otherwise); gw = 0 on padding rows
+        dO[0] = gw[0] * tint * r0 * (1.0f - r0);       // d/d logit of w * rgb . g
+        dO[1] = gw[1] * tint * r1 * (1.0f - r1);
+        dO[2] = gw[2] * tint * r2 * (1.0f - r2);
+        if (REF) dtint = gw[0] * r0 + gw[1] * r1 + gw[2] * r2;
         db3[0] += dO[0]; db3[1] += dO[1]; db3[2] += dO[2];
         *reinterpret_cast<uint4*>(xrow + kDoChunk * kLbo) = make_uint4(pack_bf16(dO[0], dO[1]), pack_bf16(dO[2], 0.0f), 0u, 0u);
       }
@@ -352,80 +390,120 @@ __global__ void __launch_bounds__(kThreads, 1) k_app_bwd_tc(const BwdParams Bp) 
       }
       mma_wait();
       {
-        // ---- positional-encoding backward: d feat_o = dX[o] + sum_q 2^q (dX[sin_oq] cos_oq - dX[cos_oq] sin_oq) ---------------
-        float df[32];
-        tmem_ld32(lane_addr + cWork, df);            // columns 0..31: feat (0..26), dir (27..29, no parameters), sin_00, sin_01
-        const float d30 = df[30], d31 = df[31];
+        // ---- positional-encoding backward: d feat_o = dX[feat_o] + sum_q 2^q (dX[sin_oq] cos_oq - dX[cos_oq] sin_oq) ----------
+        // (REF: the same for the three reflection components, then the geometry of REFTensoRF.py:216-238 backwards)
+        float df[NH];                                   // gradient of the stacked head outputs (VM: features only)
 #pragma unroll
-        for (int j = APP_DIM; j < 32; ++j) df[j] = 0.0f;
+        for (int j = 0; j < NH; ++j) df[j] = 0.0f;
+        float dr[3] = {0.0f, 0.0f, 0.0f}, dx0 = 0.0f;   // REF: d reflection, d(-d.n)
         // X values of this row, as stored (bf16): 20 chunks of 8 columns
         auto xval = [&](int c) -> float {
           const uint32_t w = *reinterpret_cast<const uint32_t*>(xrow + (c >> 3) * kLbo + (c & 7) / 2 * 4);
           return (c & 1) ? bf_hi(w) : bf_lo(w);
         };
-        auto accum = [&](int c, float dv) {           // c = column of X in [PF, PV): sin block then cos block
+        auto accum = [&](int c, float dv) {             // c = column of X, dv = dL/dX[c]
+          if (REF && c == 0) { dx0 = dv; return; }
+          if (c < C0 + APP_DIM) { df[c - C0] += dv; return; }
+          if (c < PF) { if (REF) dr[c - C0 - APP_DIM] += dv; return; }          // view direction: no parameters (VM)
           if (c < PF + NF) {
             const int o = (c - PF) >> 1, q = (c - PF) & 1;
             df[o] = fmaf(dv * (q ? 2.0f : 1.0f), xval(c + NF), df[o]);
-          } else {
+          } else if (c < PV) {
             const int o = (c - PF - NF) >> 1, q = (c - PF - NF) & 1;
             df[o] = fmaf(-dv * (q ? 2.0f : 1.0f), xval(c - NF), df[o]);
+          } else if (REF && c < PV + NV) {
+            const int o = (c - PV) >> 1, q = (c - PV) & 1;
+            dr[o] = fmaf(dv * (q ? 2.0f : 1.0f), xval(c + NV), dr[o]);
+          } else if (REF && c < PV + 2 * NV) {
+            const int o = (c - PV - NV) >> 1, q = (c - PV - NV) & 1;
+            dr[o] = fmaf(-dv * (q ? 2.0f : 1.0f), xval(c - NV), dr[o]);
           }
         };
-        accum(30, d30);
-        accum(31, d31);
 #pragma unroll
-        for (int cb = 1; cb < 5; ++cb) {
+        for (int cb = 0; cb < 5; ++cb) {
           float d[32];
           tmem_ld32(lane_addr + cWork + cb * 32, d);
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int c = cb * 32 + j;
-            if (c < PV) accum(c, d[j]);
+            if (c < IN_C) accum(c, d[j]);
           }
         }
-        // dF -> X columns 0..31 (bf16), in place
+        if (REF) {
+          // x[0] = -d.n; reflection = 2 (d.n) n - d; penalty = sum w relu(-d.n)^2; n = v / |v|
+          float ddot = -dx0 + 2.0f * (nh[0] * dr[0] + nh[1] * dr[1] + nh[2] * dr[2]);
+          ddot -= dpen * wgt * 2.0f * fmaxf(-dotp, 0.0f);
+          float dn[3];
 #pragma unroll
-        for (int g = 0; g < 4; ++g)
+          for (int c = 0; c < 3; ++c) dn[c] = 2.0f * dotp * dr[c] + ddot * vd[c];
+          const float proj = nh[0] * dn[0] + nh[1] * dn[1] + nh[2] * dn[2];
+          const bool live = nraw2 > 1e-30f;          // degenerate normal: jt.normalize clamps, no gradient (padding rows: all zero)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) df[APP_DIM + c] = live ? (dn[c] - nh[c] * proj) * ninv : 0.0f;
+          df[APP_DIM + 3] = gw[0]; df[APP_DIM + 4] = gw[1]; df[APP_DIM + 5] = gw[2];     // d rgb_d = w g
+          df[APP_DIM + 6] = tint > 0.0f ? dtint : 0.0f;                                  // tint = relu(specular_linear(h))
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dhb[j] += df[APP_DIM + j];
+        }
+        // dF -> X columns 0..NH (bf16), in place
+#pragma unroll
+        for (int g = 0; g < NH / 8; ++g)
           *reinterpret_cast<uint4*>(xrow + g * kLbo) =
               make_uint4(pack_bf16(df[g * 8 + 0], df[g * 8 + 1]), pack_bf16(df[g * 8 + 2], df[g * 8 + 3]),
                          pack_bf16(df[g * 8 + 4], df[g * 8 + 5]), pack_bf16(df[g * 8 + 6], df[g * 8 + 7]));
       }
       publish();
-      // ---- dH = dF basis ; dBasis^T = H^T dF (two windows: channels 0..127 and 16..143) ------------------------------------------
+      // ---- dBasis^T = H^T dF (two windows: channels 0..127 and 16..143), flushed per tile ------------------------------------------
       if (tid == 0) {
         fence_after();
 #pragma unroll
-        for (int s = 0; s < 2; ++s)
-          umma_bf16(tmem + cWork, smem_desc(aX + s * 2 * kLbo, kLbo, 128), smem_desc(aB0 + s * 256, 128, NH * 16),
-                    instr_desc(128, K0) | kIdescBMajorMN, s > 0);
-#pragma unroll
         for (int s = 0; s < 8; ++s)
           umma_bf16(tmem + cDBt1, smem_desc(aH + s * 256, 128, kLbo), smem_desc(aX + s * 256, 128, kLbo),
-                    instr_desc(128, 32) | MN, s > 0);
+                    instr_desc(128, NH) | MN, s > 0);
 #pragma unroll
         for (int s = 0; s < 8; ++s)
           umma_bf16(tmem + cDBt2, smem_desc(aH + 2 * kLbo + s * 256, 128, kLbo), smem_desc(aX + s * 256, 128, kLbo),
-                    instr_desc(128, 32) | MN, s > 0);
+                    instr_desc(128, NH) | MN, s > 0);
         umma_commit(mma_bar);
       }
       mma_wait();
       {
-        // ---- flush dBasis^T: TMEM lane = appearance channel h, columns = basis outputs ------------------------------------------------
+        // TMEM lane = appearance channel h, columns = stacked head outputs
         float v[32];
-        tmem_ld32(lane_addr + cDBt1, v);
-        float* gb = Bp.g.basis_t + (size_t)row * kMaxAppDim;
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) red_add_v4(gb + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+        for (int cb = 0; cb < NH; cb += 16) {
+          tmem_ld16(lane_addr + cDBt1 + cb, v);
+          float* gb = Bp.g.basis_t + (size_t)row * NH + cb;
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) red_add_v4(gb + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+        }
         if (warp == 3) {             // second window: lane l = channel 16 + l; only channels 128..143 (rows >= 112) are new
-          tmem_ld32(lane_addr + cDBt2, v);        // .sync.aligned: the whole warp executes the load
-          if (row >= 112) {
-            gb = Bp.g.basis_t + (size_t)(16 + row) * kMaxAppDim;
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) red_add_v4(gb + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+          for (int cb = 0; cb < NH; cb += 16) {
+            tmem_ld16(lane_addr + cDBt2 + cb, v);        // .sync.aligned: the whole warp executes the load
+            if (row >= 112) {
+              float* gb = Bp.g.basis_t + (size_t)(16 + row) * NH + cb;
+#pragma unroll
+              for (int i = 0; i < 16; i += 4) red_add_v4(gb + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+            }
           }
         }
+      }
+      fence_before();
+      row_sync();                  // every lane has read the dBasis^T windows before dH overwrites those columns
+      // ---- dH = dF basis ------------------------------------------------------------------------------------------------------------
+      if (tid == 0) {
+        fence_after();
+#pragma unroll
+        for (int s = 0; s < NH / 16; ++s)
+          umma_bf16(tmem + cWork, smem_desc(aX + s * 2 * kLbo, kLbo, 128), smem_desc(aB0 + s * 256, 128, NH * 16),
+                    instr_desc(128, K0) | kIdescBMajorMN, s > 0);
+        umma_commit(mma_bar);
+      }
+      mma_wait();
+      {
         // ---- dH -> shared memory (bf16, over H) for the scatter ----------------------------------------------------------------------
+        float v[32];
         uint8_t* hrow = sH + row * 16;
 #pragma unroll
         for (int cb = 0; cb < 4; ++cb) {
@@ -526,6 +604,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_app_bwd_tc(const BwdParams Bp) 
         const float s = warp_sum(db3[j]);
         if (lane == 0) atomicAdd(Bp.g.b3 + j, s);
       }
+      if (REF) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float s = warp_sum(dhb[j]);
+          if (lane == 0) atomicAdd(Bp.g.head_bias + APP_DIM + j, s);
+        }
+      }
     } else {
       const int c = (tid - kRowWarps * 32) & 127;
       atomicAdd((warp < kRowWarps + 4 ? Bp.g.b2 : Bp.g.b1) + c, dbias);
@@ -541,14 +626,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_app_bwd_tc(const BwdParams Bp) 
 int launch_app_bwd_tc(const BwdParams& B, int num_sms, cudaStream_t stream) {
   using namespace bwdtc;
   const TvmModel& m = B.f.m;
-  TVM_REQUIRE(m.variant == TVM_VARIANT_VM && m.n_app == CA && m.app_dim == APP_DIM && m.fea_pe == 2 && m.view_pe == 2 &&
+  TVM_REQUIRE(m.n_app == CA && m.app_dim == APP_DIM && m.fea_pe == 2 && m.view_pe == 2 &&
               m.feature_c == 128, "tensor-core appearance backward supports n_app=48, app_dim=27, fea_pe=view_pe=2, featureC=128");
   TVM_REQUIRE(m.tc_weights != nullptr, "TvmModel.tc_weights is NULL: call tvm_pack_mlp_tc first");
-  const tc::Image img(CA, IN_C, NH);
-  const size_t smem = ((img.bytes + 127) & ~127u) + (size_t)kRows * (K0 + K1 + 128 + 128) * 2 + 64;
+  const bool ref = m.variant == TVM_VARIANT_REF;
+  const tc::Image img(CA, in_mlp_c(m), head_ld(m));
+  const uint32_t w_bytes = ref ? img.off_f32 : img.bytes;
+  const size_t smem = ((w_bytes + 127) & ~127u) + (size_t)kRows * (K0 + K1 + 128 + 128) * 2 + 64;
   TVM_REQUIRE(smem <= 227 * 1024, "k_app_bwd_tc shared memory");
-  TVM_CHECK_CUDA(cudaFuncSetAttribute(k_app_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_app_bwd_tc<<<num_sms, kThreads, smem, stream>>>(B);
+  auto kern = ref ? k_app_bwd_tc<true> : k_app_bwd_tc<false>;
+  TVM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<num_sms, kThreads, smem, stream>>>(B);
   TVM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

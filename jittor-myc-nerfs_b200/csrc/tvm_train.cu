@@ -27,8 +27,10 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 
 // x [C][H][W]; loss += scale_h * sum dh^2 + scale_w * sum dw^2; grad += d loss / d x
 __global__ void __launch_bounds__(256) k_tv_loss(const float* __restrict__ x, int C, int H, int W, float scale_h,
-                                                 float scale_w, float* __restrict__ loss, float* __restrict__ grad) {
+                                                 float scale_w, const float* __restrict__ wdev, float* __restrict__ loss,
+                                                 float* __restrict__ grad) {
   __shared__ float red[8];
+  if (wdev) { scale_h *= *wdev; scale_w *= *wdev; }      // per-step weight of a replayed CUDA graph
   const size_t total = (size_t)C * H * W;
   float part = 0.0f;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -47,9 +49,11 @@ __global__ void __launch_bounds__(256) k_tv_loss(const float* __restrict__ x, in
   if (threadIdx.x == 0 && loss) atomicAdd(loss, t);
 }
 
-__global__ void __launch_bounds__(256) k_l1_loss(const float* __restrict__ x, size_t n, float scale, float* __restrict__ loss,
+__global__ void __launch_bounds__(256) k_l1_loss(const float* __restrict__ x, size_t n, float scale,
+                                                 const float* __restrict__ wdev, float* __restrict__ loss,
                                                  float* __restrict__ grad) {
   __shared__ float red[8];
+  if (wdev) scale *= *wdev;
   float part = 0.0f;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const float v = x[i];
@@ -62,9 +66,11 @@ __global__ void __launch_bounds__(256) k_l1_loss(const float* __restrict__ x, si
 
 // v [C][L] (C <= 64); one CTA.  loss += scale * sum_{i != j} |<v_i, v_j>|, grad_i += 2 scale sum_{j != i} sign(<v_i, v_j>) v_j
 __global__ void __launch_bounds__(256) k_vector_diffs(const float* __restrict__ v, int C, int L, float scale,
-                                                      float* __restrict__ loss, float* __restrict__ grad) {
+                                                      const float* __restrict__ wdev, float* __restrict__ loss,
+                                                      float* __restrict__ grad) {
   __shared__ float sgn[64 * 64];
   __shared__ float red[8];
+  if (wdev) scale *= *wdev;
   float part = 0.0f;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int pr = warp; pr < C * C; pr += 8) {         // one warp per (i, j) dot product
@@ -138,27 +144,29 @@ static int stream_grid(size_t total) {
 
 using namespace tvm;
 
-extern "C" int tvm_tv_loss(const float* plane_nchw, int C, int H, int W, float weight, float* loss_accum, float* grad_nchw,
-                           void* stream) {
+extern "C" int tvm_tv_loss(const float* plane_nchw, int C, int H, int W, float weight, const float* weight_dev,
+                           float* loss_accum, float* grad_nchw, void* stream) {
   TVM_REQUIRE(plane_nchw && C > 0 && H > 0 && W > 0, "bad arguments");
   // TVLoss (batch 1): weight * 2 * (h_tv / count_h + w_tv / count_w), count_h = C (H-1) W, count_w = C H (W-1)
   const double ch = (double)C * (H - 1) * W, cw = (double)C * H * (W - 1);
   const float sh = ch > 0 ? (float)(2.0 * weight / ch) : 0.0f, sw = cw > 0 ? (float)(2.0 * weight / cw) : 0.0f;
-  k_tv_loss<<<stream_grid((size_t)C * H * W), 256, 0, (cudaStream_t)stream>>>(plane_nchw, C, H, W, sh, sw, loss_accum, grad_nchw);
+  k_tv_loss<<<stream_grid((size_t)C * H * W), 256, 0, (cudaStream_t)stream>>>(plane_nchw, C, H, W, sh, sw, weight_dev, loss_accum, grad_nchw);
   TVM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
-extern "C" int tvm_l1_loss(const float* x, size_t n, float weight, float* loss_accum, float* grad, void* stream) {
+extern "C" int tvm_l1_loss(const float* x, size_t n, float weight, const float* weight_dev, float* loss_accum, float* grad,
+                           void* stream) {
   TVM_REQUIRE(x && n > 0, "bad arguments");
-  k_l1_loss<<<stream_grid(n), 256, 0, (cudaStream_t)stream>>>(x, n, (float)(weight / (double)n), loss_accum, grad);
+  k_l1_loss<<<stream_grid(n), 256, 0, (cudaStream_t)stream>>>(x, n, (float)(weight / (double)n), weight_dev, loss_accum, grad);
   TVM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
-extern "C" int tvm_vector_diffs(const float* line_cl, int C, int L, float weight, float* loss_accum, float* grad, void* stream) {
+extern "C" int tvm_vector_diffs(const float* line_cl, int C, int L, float weight, const float* weight_dev, float* loss_accum,
+                                float* grad, void* stream) {
   TVM_REQUIRE(line_cl && C > 1 && C <= 64 && L > 0, "vector_diffs supports 2..64 components");
-  k_vector_diffs<<<1, 256, 0, (cudaStream_t)stream>>>(line_cl, C, L, (float)(weight / ((double)C * (C - 1))), loss_accum, grad);
+  k_vector_diffs<<<1, 256, 0, (cudaStream_t)stream>>>(line_cl, C, L, (float)(weight / ((double)C * (C - 1))), weight_dev, loss_accum, grad);
   TVM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 
 import torch
 
@@ -26,16 +27,18 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
-def _launch(kind, x, weight, loss, grad):
+def _launch(kind, x, weight, loss, grad, weight_dev=None):
+    """One fused value+gradient sweep: *loss += w f(x), grad += w df/dx with w = weight (* *weight_dev)."""
     lib, st = L.load(), _stream_ptr()
     if kind == "tv":
         _, Cc, H, W = x.shape
-        L.check(lib.tvm_tv_loss(_ptr(x), Cc, H, W, float(weight), _ptr(loss), _ptr(grad), st), "tvm_tv_loss")
+        L.check(lib.tvm_tv_loss(_ptr(x), Cc, H, W, float(weight), _ptr(weight_dev), _ptr(loss), _ptr(grad), st), "tvm_tv_loss")
     elif kind == "l1":
-        L.check(lib.tvm_l1_loss(_ptr(x), x.numel(), float(weight), _ptr(loss), _ptr(grad), st), "tvm_l1_loss")
+        L.check(lib.tvm_l1_loss(_ptr(x), x.numel(), float(weight), _ptr(weight_dev), _ptr(loss), _ptr(grad), st), "tvm_l1_loss")
     else:
         _, Cc, Ln, _ = x.shape
-        L.check(lib.tvm_vector_diffs(_ptr(x), Cc, Ln, float(weight), _ptr(loss), _ptr(grad), st), "tvm_vector_diffs")
+        L.check(lib.tvm_vector_diffs(_ptr(x), Cc, Ln, float(weight), _ptr(weight_dev), _ptr(loss), _ptr(grad), st),
+                "tvm_vector_diffs")
 
 
 class _RegFn(torch.autograd.Function):
@@ -182,9 +185,11 @@ class Adam:
 
 
 class TrainStepGraph:
-    """One optimisation step of train.py:218-261 (sample jitter, render, MSE, regularisers, backward, Adam, re-pack of the
+    """One optimisation step of train.py:218-261 (sample jitter, render, MSE, backward, regularisers, Adam, re-pack of the
     updated grids) captured ONCE into a CUDA graph and replayed per iteration: the step is launch-bound (~60 kernels of
-    10-100 us), so the graph removes the host time between them.  Per-step scalars (Adam bias correction, decayed learning
+    10-100 us), so the graph removes the host time between them.  The captured body calls the library directly
+    (tvm_forward, tvm_mse_loss, tvm_backward, the value+gradient regulariser sweeps, tvm_adam_step) -- no autograd engine,
+    hence no second thread touching CUDA during capture.  Per-step scalars (Adam bias correction, decayed learning
     rates, regulariser weights) reach the graph through a pinned-host -> device copy node.
 
         g = TrainStepGraph(model, opt, n_rays=4096, N_samples=S, white_bg=True, TV_weight_density=2.0, TV_weight_app=2.0)
@@ -192,44 +197,63 @@ class TrainStepGraph:
     """
 
     def __init__(self, model, optimizer, n_rays, N_samples, white_bg=True, TV_weight_density=0.0, TV_weight_app=0.0,
-                 L1_reg_weight=0.0, Ortho_reg_weight=0.0):
+                 L1_reg_weight=0.0, Ortho_reg_weight=0.0, normal_vector_penalty_weight=0.0):
         self.model, self.opt = model, optimizer
         dev = model.device
         self.rays = torch.zeros((n_rays, 6), dtype=torch.float32, device=dev)
         self.target = torch.zeros((n_rays, 3), dtype=torch.float32, device=dev)
         self.S, self.white_bg = int(N_samples), bool(white_bg)
-        self.use = dict(tv_d=TV_weight_density > 0, tv_a=TV_weight_app > 0, l1=L1_reg_weight > 0, ortho=Ortho_reg_weight > 0)
-        self._w_host = torch.tensor([TV_weight_density, TV_weight_app, L1_reg_weight, Ortho_reg_weight], dtype=torch.float32).pin_memory()
+        self.use = dict(tv_d=TV_weight_density > 0, tv_a=TV_weight_app > 0, l1=L1_reg_weight > 0, ortho=Ortho_reg_weight > 0,
+                        pen=normal_vector_penalty_weight > 0)
+        self._w_host = torch.tensor([TV_weight_density, TV_weight_app, L1_reg_weight, Ortho_reg_weight,
+                                     normal_vector_penalty_weight], dtype=torch.float32).pin_memory()
         self._w_dev = self._w_host.to(dev)
         self._tv = TVLoss()
-        self.loss = torch.zeros((), dtype=torch.float32, device=dev)
+        self.loss = torch.zeros(1, dtype=torch.float32, device=dev)          # MSE of the step (train.py:228)
+        self.reg_loss = torch.zeros(1, dtype=torch.float32, device=dev)      # sum of the weighted regularisers
         self.jitter = None                  # optional static [n] buffer (step(..., jitter=...)); default: torch.rand per step
         self.graph = None
 
-    def set_weights(self, TV_weight_density=None, TV_weight_app=None, L1_reg_weight=None, Ortho_reg_weight=None):
-        for i, v in enumerate((TV_weight_density, TV_weight_app, L1_reg_weight, Ortho_reg_weight)):
+    def set_weights(self, TV_weight_density=None, TV_weight_app=None, L1_reg_weight=None, Ortho_reg_weight=None,
+                    normal_vector_penalty_weight=None):
+        for i, v in enumerate((TV_weight_density, TV_weight_app, L1_reg_weight, Ortho_reg_weight, normal_vector_penalty_weight)):
             if v is not None:
                 self._w_host[i] = float(v)
 
     def _body(self):
-        m = self.model
-        self.opt.zero_grad()
+        """The step without the autograd engine: every kernel is enqueued by this thread on the capturing stream."""
+        m, lib = self.model, L.load()
         self._w_dev.copy_(self._w_host, non_blocking=True)
-        rgb, _ = m(self.rays, is_train=True, white_bg=self.white_bg, N_samples=self.S, jitter=self.jitter)
-        loss = torch.mean((rgb - self.target) ** 2)
-        total = loss
+        n = self.rays.shape[0]
+        jitter = self.jitter if self.jitter is not None else torch.rand(n, dtype=torch.float32, device=self.rays.device)
+        flags = m._flags(self.white_bg)
+        rgb, _ = m._forward_raw(self.rays, jitter, flags, self.S)
+        d_rgb = torch.empty_like(rgb)
+        L.check(lib.tvm_mse_loss(_ptr(rgb), _ptr(self.target), n, 1.0, _ptr(self.loss), _ptr(d_rgb), _stream_ptr()),
+                "tvm_mse_loss")                                                       # train.py:228
+        d_pen = self._w_dev[4:5] if (self.use["pen"] and m.VARIANT == L.VARIANT_REF) else None
+        grads = m._backward_raw(self.rays, jitter, flags, self.S, rgb, d_rgb, d_pen)
+        params = m._param_list()
+        for p, g in zip(params, grads):
+            p.grad = g
+        # regularisers (train.py:233-251): value + gradient sweeps straight into .grad, weights read from the device
+        reg = self.reg_loss
+        reg.zero_()
+        w = self._w_dev
         if self.use["tv_d"]:
-            total = total + m.TV_loss_density(self._tv) * self._w_dev[0]
+            for p in m.density_plane:
+                _launch("tv", p.detach(), 1e-2, reg, p.grad, w[0:1])
         if self.use["tv_a"]:
-            total = total + m.TV_loss_app(self._tv) * self._w_dev[1]
+            for p in m.app_plane:
+                _launch("tv", p.detach(), 1e-2, reg, p.grad, w[1:2])
         if self.use["l1"]:
-            total = total + m.density_L1() * self._w_dev[2]
+            for p in [*m.density_plane, *m.density_line]:
+                _launch("l1", p.detach(), 1.0, reg, p.grad, w[2:3])
         if self.use["ortho"]:
-            total = total + m.vector_comp_diffs() * self._w_dev[3]
-        total.backward()
+            for p in [*m.density_line, *m.app_line]:
+                _launch("ortho", p.detach(), 1.0, reg, p.grad, w[3:4])
         self.opt._launch()
         m._pack(force=True)                       # the next forward (and any render in between) sees the updated grids
-        self.loss.copy_(loss.detach())
 
     def capture(self):
         """Warm up on a side stream (torch's capture protocol), then record the step.  The warm-up steps are real
@@ -247,7 +271,7 @@ class TrainStepGraph:
         torch.cuda.current_stream().wait_stream(s)
         self.graph = torch.cuda.CUDAGraph()
         opt._prepare_hyper()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, capture_error_mode=os.environ.get("TVM_GRAPH_CAPTURE_MODE", "global")):
             self._body()
         with torch.no_grad():
             for p, q in zip(params, snap):
