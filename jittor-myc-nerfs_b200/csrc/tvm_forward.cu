@@ -20,7 +20,10 @@ constexpr int kMarchWarps = 8;
 // ------------------------------------------------------------------------------------------------
 // k_march
 // ------------------------------------------------------------------------------------------------
-template <bool AUX>
+// AUX: parity instantiation (every mask bit and per-sample output written, no early termination, no block skipping).
+// NPP: NerfPlusPlus sampling (sphere-bounded, stratified) -- the uniform instantiations carry none of that code.
+// CD:  compile-time density channel count (16 = configs/*.txt; 0 = any multiple of 4, read from the model).
+template <bool AUX, bool NPP, int CD>
 __global__ void __launch_bounds__(kMarchWarps * 32, 3) k_march(const FwdParams P) {
   __shared__ float s_u[kMarchWarps][32][3];
   __shared__ float s_f[kMarchWarps][32];
@@ -32,39 +35,46 @@ __global__ void __launch_bounds__(kMarchWarps * 32, 3) k_march(const FwdParams P
 
   RayMarch r;
   ray_setup(m, P.rays + 6 * (size_t)ray, P.jitter, ray, P.S, r);
+  auto z_of = [&](int k) { return NPP ? sample_z(m, r, k) : sample_z_uniform(m, r, k); };
 
-  const int C = m.n_density;
+  const int C = CD ? CD : m.n_density;
   const int S = P.S;
   const bool ert = !AUX && !(P.flags & TVM_NO_ERT);
   float T = 1.0f, acc = 0.0f, dep = 0.0f;
   // NeRF++: bg_lambda = prod_k (1 - alpha_k + 1e-6) over ALL S samples (nerfplusplus.py:277-278)
-  const bool npp = m.sampling == TVM_SAMPLING_NPP;
   float Tbg = 1.0f;
   int n_proc = 0;
   bool seen = false;
   uint32_t c_in = 0, c_v = 0, c_a = 0;
 
-  // coarse pass (one lane per 32-sample block): blocks that cannot hold a valid sample are never visited
-  const bool use_visit = !AUX && P.NB <= 64;
-  unsigned long long visit = 0ull;
-  if (use_visit) {
-    for (int b0 = 0; b0 < P.NB; b0 += 32) {
-      const int bb = b0 + lane;
-      const bool maybe = bb < P.NB && block_maybe(m, r, bb, S);
-      visit |= (unsigned long long)__ballot_sync(0xffffffffu, maybe) << b0;
-    }
+  // Blocks are visited in windows of 32: a coarse pass (one lane per 32-sample block) drops the blocks of the window that
+  // cannot hold a valid sample.  Uniform marching: the ray leaves the box at t_far (slab test), so windows that start
+  // more than two samples beyond it are never looked at (rounding in o + d z is orders of magnitude below one step).
+  int nb_hi = P.NB;
+  if (!AUX && !NPP) {
+    // ray_setup's slab test also yields the exit distance
+    const float kf = __fdividef(r.t_far - r.t_min, m.step_size) + 3.0f;
+    if (kf < (float)S) nb_hi = min(P.NB, max(0, (int)kf) / 32 + 1);     // NaN / inf keep NB
   }
+  uint32_t visit = 0;
+  int win = -32;
   int b = -1;
   while (true) {
-    if (use_visit) {
+    if (!AUX) {
+      while (!visit) {
+        win += 32;
+        if (win >= nb_hi) break;
+        const int bb = win + lane;
+        visit = __ballot_sync(0xffffffffu, bb < nb_hi && block_maybe(m, r, bb, S, !NPP));
+      }
       if (!visit) break;
-      b = __ffsll((long long)visit) - 1;
+      b = win + __ffs(visit) - 1;
       visit &= visit - 1;
     } else if (++b >= P.NB) {
       break;
     }
     const int k = b * 32 + lane;
-    const float z = sample_z(m, r, k);
+    const float z = z_of(k);
     float p[3];
     bool inside = sample_point(m, r, z, p) && (k < S);
     const uint32_t in_bits = __ballot_sync(0xffffffffu, inside);
@@ -96,22 +106,29 @@ __global__ void __launch_bounds__(kMarchWarps * 32, 3) k_march(const FwdParams P
         s_u[warp][rank][2] = u[2];
       }
       __syncwarp();
-      // 4 lanes per sample, one float4 of channels each: a tap is one 64-byte segment
+      // 4 lanes per sample, one float4 of channels each: a tap is one 64-byte segment; the two rows of a plane
+      // footprint and the line pair need one address each (axis_pair: the neighbour texel sits at +C)
       const int q = lane & 3;
       for (int g = 0; g < nv; g += 8) {
         const int j = g + (lane >> 2);
         float part = 0.0f;
         if (j < nv) {
-          Axis ax[3];
+          AxisPair ax[3];
 #pragma unroll
-          for (int i = 0; i < 3; ++i) ax[i] = axis_taps(s_u[warp][j][i], m.grid[i]);
+          for (int i = 0; i < 3; ++i) ax[i] = axis_pair(s_u[warp][j][i], m.grid[i]);
 #pragma unroll
           for (int kk = 0; kk < 3; ++kk) {
-            const VmTaps t = vm_taps(m, ax, kk);
-            for (int c = q * 4; c < C; c += 16) {
+            const VmPair t = vm_pair(m, ax, kk, C);
+            if (CD == 16) {
               float4 pv, lv;
-              vm_sample4(m.density_plane[kk], m.density_line[kk], t, C, c, pv, lv);
+              vm_pair_sample4(m.density_plane[kk], m.density_line[kk], t, 16, q * 4, pv, lv);
               part += pv.x * lv.x + pv.y * lv.y + pv.z * lv.z + pv.w * lv.w;
+            } else {
+              for (int c = q * 4; c < C; c += 16) {
+                float4 pv, lv;
+                vm_pair_sample4(m.density_plane[kk], m.density_line[kk], t, C, c, pv, lv);
+                part += pv.x * lv.x + pv.y * lv.y + pv.z * lv.z + pv.w * lv.w;
+              }
             }
           }
         }
@@ -125,7 +142,7 @@ __global__ void __launch_bounds__(kMarchWarps * 32, 3) k_march(const FwdParams P
     }
 
     // raw2alpha: dists = z[k+1]-z[k] (last sample 0), scaled by distance_scale (:488, :511)
-    const float z1 = sample_z(m, r, k + 1);
+    const float z1 = z_of(k + 1);
     const float dist = (k < S - 1) ? TVM_MUL(TVM_SUB(z1, z), m.distance_scale) : 0.0f;
     const float alpha = TVM_SUB(1.0f, expf(TVM_MUL(-sigma, dist)));
     const float v = TVM_ADD(TVM_SUB(1.0f, alpha), 1e-10f);
@@ -139,7 +156,7 @@ __global__ void __launch_bounds__(kMarchWarps * 32, 3) k_march(const FwdParams P
     if (lane == 0) excl = 1.0f;
     const float w = alpha * (T * excl);
     T = T * __shfl_sync(0xffffffffu, pref, 31);
-    if (npp) {
+    if (NPP) {
       float v6 = (k < S) ? TVM_ADD(TVM_SUB(1.0f, alpha), 1e-6f) : 1.0f;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) v6 *= __shfl_xor_sync(0xffffffffu, v6, o);
@@ -181,7 +198,7 @@ __global__ void __launch_bounds__(kMarchWarps * 32, 3) k_march(const FwdParams P
   dep = warp_sum(dep);
   if (lane == 0) {
     P.ws.acc[ray] = acc;
-    if (npp) {
+    if (NPP) {
       // samples of blocks that were never visited have alpha = 0: each contributes fl(1 + 1e-6)
       float lam = Tbg * powf(TVM_ADD(1.0f, 1e-6f), (float)(S - n_proc));
       lam = lam > 0.1f ? lam : 0.0f;                                   // nerfplusplus.py:313
@@ -378,10 +395,13 @@ static int forward_impl(const TvmModel* m_host, const TvmBgNet* bg_host, const f
   const int march_blocks = (n_rays + kMarchWarps - 1) / kMarchWarps;
   {
     ProfileScope prof(TVM_STAGE_MARCH, stream);
-    if (has_aux)
-      k_march<true><<<march_blocks, kMarchWarps * 32, 0, stream>>>(P);
-    else
-      k_march<false><<<march_blocks, kMarchWarps * 32, 0, stream>>>(P);
+    const bool npp = P.m.sampling == TVM_SAMPLING_NPP, c16 = P.m.n_density == 16;
+    void (*kern)(const FwdParams) =
+        has_aux ? (npp ? (c16 ? k_march<true, true, 16> : k_march<true, true, 0>)
+                       : (c16 ? k_march<true, false, 16> : k_march<true, false, 0>))
+                : (npp ? (c16 ? k_march<false, true, 16> : k_march<false, true, 0>)
+                       : (c16 ? k_march<false, false, 16> : k_march<false, false, 0>));
+    kern<<<march_blocks, kMarchWarps * 32, 0, stream>>>(P);
   }
   TVM_CHECK_CUDA(cudaGetLastError());
 

@@ -40,6 +40,7 @@ TVM_HD int vecax(int k) { return 2 - k; }
 struct RayMarch {
   float o[3], d[3];
   float t_min;   // entry distance clamped to [near, far]      (tensorBase.py:345-348); NeRF++: near
+  float t_far;   // slab-test exit distance (uniform marching only; bounds the block loop, decides no mask bit)
   float jit;     // per-ray jitter (0 when !is_train)           (tensorBase.py:351-353)
   // TVM_SAMPLING_NPP (NerfPlusPlus.sample_ray, nerfplusplus.py:239-269)
   float step;          // (far - near) / (S - 1), far = exit of the radii-sphere
@@ -74,12 +75,13 @@ TVM_HD void ray_setup(const TvmModel& m, const float* ray6, const float* jitter,
     const float d2 = TVM_MUL(sqrtf(TVM_SUB(TVM_MUL(m.radii, m.radii), dot3_seq(p, p))), cosd);
     const float far = TVM_ADD(d1, d2);
     r.t_min = m.near_;
+    r.t_far = far;
     r.step = TVM_DIV(TVM_SUB(far, m.near_), (float)(S - 1));
     r.jit = 0.0f;
     r.rnd = jitter + (size_t)ray * S;
     return;
   }
-  float t = -INFINITY;
+  float t = -INFINITY, tf = INFINITY;
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     float vec = (r.d[i] == 0.0f) ? 1e-6f : r.d[i];
@@ -87,9 +89,11 @@ TVM_HD void ray_setup(const TvmModel& m, const float* ray6, const float* jitter,
     float rb = TVM_DIV(TVM_SUB(m.aabb[i], r.o[i]), vec);
     float mn = fminf(ra, rb);
     t = fmaxf(t, mn);
+    tf = fminf(tf, fmaxf(ra, rb));
   }
   t = fminf(fmaxf(t, m.near_), m.far_);
   r.t_min = t;
+  r.t_far = tf;
   r.jit = jitter ? jitter[ray] : 0.0f;
 }
 
@@ -107,6 +111,10 @@ TVM_HD float sample_z(const TvmModel& m, const RayMarch& r, int k) {
   }
   float rng = TVM_ADD((float)k, r.jit);
   return TVM_ADD(r.t_min, TVM_MUL(m.step_size, rng));
+}
+// the uniform branch alone, for kernels specialised on the sampling mode
+TVM_HD float sample_z_uniform(const TvmModel& m, const RayMarch& r, int k) {
+  return TVM_ADD(r.t_min, TVM_MUL(m.step_size, TVM_ADD((float)k, r.jit)));
 }
 
 // pts = o + d * z ; returns true when the point is inside the bbox (strict > on both faces)
@@ -141,6 +149,26 @@ TVM_HD Axis axis_taps(float u, int size) {
   if (i + 1 < 0 || i + 1 > size - 1) a.w1 = 0.0f;
   a.i0 = min(max(i, 0), size - 1);
   a.i1 = min(max(i + 1, 0), size - 1);
+  return a;
+}
+
+// The same two taps re-expressed on the ADJACENT pair (b, b+1), b = clamp(floor(u), 0, size-2): p0 weighs texel b, p1
+// texel b+1.  In range (0 <= floor(u) <= size-2) this is axis_taps verbatim; at floor(u) = size-1 (a sample exactly on the
+// far face) the in-range tap moves to p1 and the zero-weight clamped tap to p0, at floor(u) = -1 the other way round, so
+// p0 T[b] + p1 T[b+1] has the same non-zero products in the same order (the zero-weight terms add exact zeros).
+// A gather then needs ONE address per row: the neighbour sits at a constant +C offset.  Requires size >= 2.
+struct AxisPair {
+  int b;
+  float p0, p1;
+};
+TVM_HD AxisPair axis_pair(float u, int size) {
+  AxisPair a;
+  const float f = floorf(u);
+  const float w0 = TVM_SUB(TVM_ADD(f, 1.0f), u), w1 = TVM_SUB(u, f);
+  const int i = (int)f;
+  a.b = min(max(i, 0), size - 2);
+  a.p0 = (i == a.b) ? w0 : ((i + 1 == a.b) ? w1 : 0.0f);
+  a.p1 = (i == a.b) ? w1 : ((i == a.b + 1) ? w0 : 0.0f);
   return a;
 }
 
@@ -216,11 +244,12 @@ TVM_HD bool bricks_maybe(const TvmModel& m, const uint32_t* __restrict__ bricks,
 // Which 32-sample blocks of a ray can contain a sample that passes the bbox test and the alpha mask?
 // Block b is dropped when both of its end samples lie beyond the same bbox face (monotonicity => so do
 // all samples in between) or when bricks_maybe() is false.  Lane l decides block b0 + l.
-TVM_HD bool block_maybe(const TvmModel& m, const RayMarch& r, int b, int S) {
+// `uniform` (a compile-time constant at the call site) promises m.sampling != TVM_SAMPLING_NPP.
+TVM_HD bool block_maybe(const TvmModel& m, const RayMarch& r, int b, int S, bool uniform = false) {
   const int k0 = b * 32, k1 = min(b * 32 + 31, S - 1);
   float p0[3], p1[3];
-  sample_point(m, r, sample_z(m, r, k0), p0);
-  sample_point(m, r, sample_z(m, r, k1), p1);
+  sample_point(m, r, uniform ? sample_z_uniform(m, r, k0) : sample_z(m, r, k0), p0);
+  sample_point(m, r, uniform ? sample_z_uniform(m, r, k1) : sample_z(m, r, k1), p1);
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     if ((p0[i] < m.aabb[i] && p1[i] < m.aabb[i]) || (p0[i] > m.aabb[3 + i] && p1[i] > m.aabb[3 + i])) return false;
@@ -297,6 +326,50 @@ TVM_HD void vm_sample4(const float* __restrict__ plane, const float* __restrict_
   float4 d = ldg4(plane + (size_t)t.o11 * C + c);
   float4 l0 = ldg4(line + (size_t)t.l0 * C + c);
   float4 l1 = ldg4(line + (size_t)t.l1 * C + c);
+  pv.x = a.x * t.nw + b.x * t.ne + cc.x * t.sw + d.x * t.se;
+  pv.y = a.y * t.nw + b.y * t.ne + cc.y * t.sw + d.y * t.se;
+  pv.z = a.z * t.nw + b.z * t.ne + cc.z * t.sw + d.z * t.se;
+  pv.w = a.w * t.nw + b.w * t.ne + cc.w * t.sw + d.w * t.se;
+  lv.x = l0.x * t.lw0 + l1.x * t.lw1;
+  lv.y = l0.y * t.lw0 + l1.y * t.lw1;
+  lv.z = l0.z * t.lw0 + l1.z * t.lw1;
+  lv.w = l0.w * t.lw0 + l1.w * t.lw1;
+}
+
+// Pair form of vm_taps + vm_sample4 for 4 consecutive channels starting at c (same expressions, hence the same
+// FMA contraction and the same bits): two row addresses per plane and one per line, neighbours at +C.
+struct VmPair {
+  uint32_t row0, row1, lrow;   // element offsets of (h, w), (h+1, w) in the plane and of row l in the line
+  float nw, ne, sw, se, lw0, lw1;
+};
+TVM_HD VmPair vm_pair(const TvmModel& m, const AxisPair ax[3], int k, int C) {
+  const AxisPair& aw = ax[mat0(k)];
+  const AxisPair& ah = ax[mat1(k)];
+  const AxisPair& al = ax[vecax(k)];
+  const uint32_t W = (uint32_t)m.grid[mat0(k)];
+  VmPair t;
+  t.row0 = ((uint32_t)ah.b * W + (uint32_t)aw.b) * (uint32_t)C;
+  t.row1 = t.row0 + W * (uint32_t)C;
+  t.lrow = (uint32_t)al.b * (uint32_t)C;
+  t.nw = TVM_MUL(aw.p0, ah.p0);
+  t.ne = TVM_MUL(aw.p1, ah.p0);
+  t.sw = TVM_MUL(aw.p0, ah.p1);
+  t.se = TVM_MUL(aw.p1, ah.p1);
+  t.lw0 = al.p0;
+  t.lw1 = al.p1;
+  return t;
+}
+TVM_HD void vm_pair_sample4(const float* __restrict__ plane, const float* __restrict__ line, const VmPair& t, int C, int c,
+                            float4& pv, float4& lv) {
+  const float* r0 = plane + t.row0 + c;
+  const float* r1 = plane + t.row1 + c;
+  const float* lr = line + t.lrow + c;
+  float4 a = ldg4(r0);
+  float4 b = ldg4(r0 + C);
+  float4 cc = ldg4(r1);
+  float4 d = ldg4(r1 + C);
+  float4 l0 = ldg4(lr);
+  float4 l1 = ldg4(lr + C);
   pv.x = a.x * t.nw + b.x * t.ne + cc.x * t.sw + d.x * t.se;
   pv.y = a.y * t.nw + b.y * t.ne + cc.y * t.sw + d.y * t.se;
   pv.z = a.z * t.nw + b.z * t.ne + cc.z * t.sw + d.z * t.se;

@@ -35,12 +35,15 @@ extern "C" int emul_forward(const TvmModel* mp, const float* rays, int n, int S,
       if (ok) {
         grid_coords(m, p, u);
         for (int i = 0; i < 3; ++i) ax[i] = axis_taps(u[i], m.grid[i]);
+        // density: the adjacent-pair form k_march uses (axis_pair / vm_pair); appearance below: the 4-address form
+        AxisPair ap[3];
+        for (int i = 0; i < 3; ++i) ap[i] = axis_pair(u[i], m.grid[i]);
         float f = 0.0f;
         for (int kk = 0; kk < 3; ++kk) {
-          VmTaps t = vm_taps(m, ax, kk);
+          VmPair t = vm_pair(m, ap, kk, Cd);
           for (int c = 0; c < Cd; c += 4) {
             float4 pv, lv;
-            vm_sample4(m.density_plane[kk], m.density_line[kk], t, Cd, c, pv, lv);
+            vm_pair_sample4(m.density_plane[kk], m.density_line[kk], t, Cd, c, pv, lv);
             f += pv.x * lv.x + pv.y * lv.y + pv.z * lv.z + pv.w * lv.w;
           }
         }
@@ -124,6 +127,17 @@ extern "C" int emul_block_maybe(const TvmModel* mp, const float* rays, int n, in
     RayMarch r;
     ray_setup(m, rays + 6 * (size_t)ray, jitter, ray, S, r);
     for (int b = 0; b < NB; ++b) visit[(size_t)ray * NB + b] = block_maybe(m, r, b, S);
+  }
+  return 0;
+}
+
+// axis_pair vs axis_taps: p0 T[b] + p1 T[b+1] must equal w0 T[i0] + w1 T[i1] bit for bit on any table T
+extern "C" int emul_axis_pair_check(const float* u, int n, int size, const float* T, float* out_taps, float* out_pair) {
+  for (int i = 0; i < n; ++i) {
+    const Axis a = axis_taps(u[i], size);
+    const AxisPair p = axis_pair(u[i], size);
+    out_taps[i] = TVM_ADD(TVM_MUL(a.w0, T[a.i0]), TVM_MUL(a.w1, T[a.i1]));
+    out_pair[i] = TVM_ADD(TVM_MUL(p.p0, T[p.b]), TVM_MUL(p.p1, T[p.b + 1]));
   }
   return 0;
 }

@@ -77,3 +77,21 @@ def test_emulated_nerfpp_sampling(built_lib):
     assert np.array_equal(e["valid"].astype(bool), r["ray_valid"])
     assert np.abs(e["weight"] - r["weight"]).max() <= 1e-6
     assert np.abs(e["rgb_map"] - r["fg_rgb_map"]).max() <= 1e-5
+
+
+def test_axis_pair_equals_axis_taps(built_lib):
+    """k_march gathers through axis_pair (adjacent texel pair, one address per row): identical to axis_taps on every u,
+    including the faces (u = 0, u = size-1), lattice nodes and out-of-range coordinates."""
+    import ctypes as C
+    import emul_util as eu
+    lib = eu.build_emul()
+    rng = np.random.default_rng(5)
+    for size in (2, 3, 17, 300):
+        T = rng.standard_normal(size).astype(np.float32)
+        u = np.concatenate([rng.uniform(-2.5, size + 1.5, 4000), np.arange(-2, size + 2),
+                            np.nextafter(np.float32(size - 1), np.float32(0))[None], np.nextafter(np.float32(size - 1), np.float32(2 * size))[None],
+                            np.float32(-1e-7)[None], np.float32(1e-7)[None]]).astype(np.float32)
+        a, b = np.zeros_like(u), np.zeros_like(u)
+        lib.emul_axis_pair_check.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        assert lib.emul_axis_pair_check(u.ctypes.data, u.size, size, T.ctypes.data, a.ctypes.data, b.ctypes.data) == 0
+        assert np.array_equal(a, b), (size, u[a != b][:5])
