@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtvmrender.so")
+# TVM_LIB: developer override (kernel-tuning experiments build variant libraries next to the default one)
+LIB_PATH = os.environ.get("TVM_LIB") or os.path.join(_HERE, "libtvmrender.so")
 ABI_VERSION = 12
 
 # flags (tvmrender.h)

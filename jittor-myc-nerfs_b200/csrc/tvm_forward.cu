@@ -7,7 +7,7 @@
 //                ray termination, and appends the weighted samples to the appearance entry list.
 //   k_app_simt   appearance head in fp32 for a tile of 64 entries: 48-channel gathers
 //                (tensoRF.py:228-244), basis_mat, positional encoding and MLPRender_Fea (:62-86, 9-15).
-//   k_composite  one warp per ray: rgb_map = clamp(sum w*rgb + (1-acc)) in sample order (:521-528).
+//   k_composite  one warp per ray, lane = sample of a block: rgb_map = clamp(sum w*rgb + (1-acc)) (:521-528).
 //
 // The tcgen05 tensor-core appearance head lives in tvm_mlp_tc.cu and replaces k_app_simt when
 // TVM_MLP_BF16 / TVM_MLP_BF16X3 is requested.
@@ -16,6 +16,9 @@
 namespace tvm {
 
 constexpr int kMarchWarps = 8;
+#ifndef TVM_MARCH_MIN_CTAS
+#define TVM_MARCH_MIN_CTAS 4      // 64 registers, 32 warps per SM (measured: 3 -> 4 CTAs = -8 % march time)
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // k_march
@@ -24,7 +27,7 @@ constexpr int kMarchWarps = 8;
 // NPP: NerfPlusPlus sampling (sphere-bounded, stratified) -- the uniform instantiations carry none of that code.
 // CD:  compile-time density channel count (16 = configs/*.txt; 0 = any multiple of 4, read from the model).
 template <bool AUX, bool NPP, int CD>
-__global__ void __launch_bounds__(kMarchWarps * 32, 3) k_march(const FwdParams P) {
+__global__ void __launch_bounds__(kMarchWarps * 32, TVM_MARCH_MIN_CTAS) k_march(const FwdParams P) {
   __shared__ float s_u[kMarchWarps][32][3];
   __shared__ float s_f[kMarchWarps][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -93,6 +96,11 @@ __global__ void __launch_bounds__(kMarchWarps * 32, 3) k_march(const FwdParams P
     const uint32_t v_bits = __ballot_sync(0xffffffffu, valid);
     if (AUX && lane == 0 && P.aux.valid_bits) P.aux.valid_bits[(size_t)ray * P.NB + b] = v_bits;
 
+    if (!AUX && !NPP && v_bits == 0) {
+      // no density anywhere in the block: alpha = 0, T / acc / depth unchanged, nothing to append
+      if (!(in_bits >> 31)) break;
+      continue;
+    }
     float sigma = 0.0f;
     if (v_bits != 0) {
       const int nv = __popc(v_bits);
@@ -264,26 +272,35 @@ __global__ void __launch_bounds__(256) k_composite(const FwdParams P) {
   if (ray >= P.n) return;
   float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, sp = 0.0f;
   const bool ref = P.m.variant == TVM_VARIANT_REF;
-  for (int b = lane; b < P.NB; b += 32) {
-    uint32_t bits = P.ws.blk_mask[(size_t)ray * P.NB + b];
-    if (bits == 0) continue;
-    uint32_t e = P.ws.blk_base[(size_t)ray * P.NB + b];
-    while (bits) {
-      const int s = __ffs(bits) - 1;
-      bits &= bits - 1;
-      const float w = P.ws.ent_w[e];
-      const float r = P.ws.ent_rgb[(size_t)e * 3 + 0];
-      const float g = P.ws.ent_rgb[(size_t)e * 3 + 1];
-      const float bl = P.ws.ent_rgb[(size_t)e * 3 + 2];
-      s0 = fmaf(w, r, s0);
-      s1 = fmaf(w, g, s1);
-      s2 = fmaf(w, bl, s2);
-      if (ref) sp = fmaf(w, P.ws.ent_pen[e], sp);
-      if (P.aux.rgb) {
-        float* o = P.aux.rgb + ((size_t)ray * P.S + (size_t)b * 32 + s) * 3;
-        o[0] = r; o[1] = g; o[2] = bl;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  // lanes read the block table 32 blocks at a time; each non-empty block is then summed by the whole warp (lane = sample):
+  // one round trip per block instead of one per entry; the lane sums meet in warp_sum's fixed tree, so the result does not
+  // depend on chunking or launch order
+  for (int b0 = 0; b0 < P.NB; b0 += 32) {
+    const int bl = b0 + lane;
+    const uint32_t my_bits = bl < P.NB ? P.ws.blk_mask[(size_t)ray * P.NB + bl] : 0u;
+    const uint32_t my_base = my_bits ? P.ws.blk_base[(size_t)ray * P.NB + bl] : 0u;
+    uint32_t todo = __ballot_sync(0xffffffffu, my_bits != 0u);
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const uint32_t bits = __shfl_sync(0xffffffffu, my_bits, src);
+      const uint32_t base = __shfl_sync(0xffffffffu, my_base, src);
+      if ((bits >> lane) & 1u) {
+        const uint32_t e = base + __popc(bits & lt_mask);
+        const float w = P.ws.ent_w[e];
+        const float r = P.ws.ent_rgb[(size_t)e * 3 + 0];
+        const float g = P.ws.ent_rgb[(size_t)e * 3 + 1];
+        const float bl_ = P.ws.ent_rgb[(size_t)e * 3 + 2];
+        s0 = fmaf(w, r, s0);
+        s1 = fmaf(w, g, s1);
+        s2 = fmaf(w, bl_, s2);
+        if (ref) sp = fmaf(w, P.ws.ent_pen[e], sp);
+        if (P.aux.rgb) {
+          float* o = P.aux.rgb + ((size_t)ray * P.S + (size_t)(b0 + src) * 32 + lane) * 3;
+          o[0] = r; o[1] = g; o[2] = bl_;
+        }
       }
-      ++e;
     }
   }
   s0 = warp_sum(s0);
