@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define TVM_ABI_VERSION 12
+#define TVM_ABI_VERSION 13
 
 /* flags for tvm_forward / tvm_backward */
 #define TVM_WHITE_BG      0x1u  /* rgb_map += 1 - acc_map          (tensorBase.py:523-524) */
@@ -236,6 +236,30 @@ int tvm_backward(const TvmModel* m_host, const float* rays, int n_rays, int n_sa
                  const float* jitter, uint32_t flags, const float* rgb_map, const float* d_rgb_map,
                  const float* d_penalty, const TvmGrads* grads_host, void* ws, size_t ws_bytes, void* stream);
 
+/* Gradient targets of the NeRF++ background network: same packed layouts as TvmBgNet (tc_weights has no gradient);
+ * accumulated with atomics, the caller zeroes them.  wf_t / bf / wv_t are gradients of the FOLDED first colour layer;
+ * tvm_bg_fold_bwd carries them back to base_remap_layers.0 and rgb_layers.0.                               */
+typedef struct TvmBgGrads {
+  float* w0_t; float* b0; float* w1_t; float* b1; float* w2_t; float* b2;
+  float* w_sigma; float* b_sigma; float* wf_t; float* bf; float* wv_t; float* w_rgb; float* b_rgb;
+} TvmBgGrads;
+
+/* Backward of tvm_forward_npp (NerfPlusPlus.execute, nerfplusplus.py:272-318, under Jittor autograd; train.py:228,260):
+ * rgb_map = fg + bg_lambda * bg_rgb_map, so besides tvm_backward's foreground terms (black background) the density
+ * grids receive dL/d bg_lambda through prod(1 - alpha + 1e-6) (zero where the gate bg_lambda <= 0.1 closed) and the
+ * background network receives bg_lambda * d_rgb_map through the 512-sample compositing.  Must follow a tvm_forward_npp
+ * with the same arguments on the same workspace.  The background backward runs in fp32 in every TVM_MLP_* mode.     */
+int tvm_backward_npp(const TvmModel* m_host, const TvmBgNet* bg_host, const float* rays, int n_rays, int n_samples,
+                     const float* fg_rand, const float* bg_rand, uint32_t flags, const float* rgb_map,
+                     const float* d_rgb_map, const TvmGrads* grads_host, const TvmBgGrads* bg_grads_host, void* ws,
+                     size_t ws_bytes, void* stream);
+/* transpose of tvm_bg_fold: gradients of the folded layer -> base_remap_layers.0.{weight,bias}, rgb_layers.0.{weight,bias}
+ * (outputs are overwritten, not accumulated)                                                                         */
+int tvm_bg_fold_bwd(const float* remap_w /*[256][128]*/, const float* remap_b /*[256]*/, const float* rgb0_w /*[64][271]*/,
+                    const float* d_wf_t /*[128][64]*/, const float* d_bf /*[64]*/, const float* d_wv_t /*[15][64]*/,
+                    float* d_remap_w /*[256][128]*/, float* d_remap_b /*[256]*/, float* d_rgb0_w /*[64][271]*/,
+                    float* d_rgb0_b /*[64]*/, void* stream);
+
 /* TensorBase.compute_alpha (tensorBase.py:451-473): alpha = 1 - exp(-sigma(xyz) * length)       */
 int tvm_density_alpha(const TvmModel* m_host, const float* xyz, int n_pts, float length,
                       float* alpha_out, void* stream);
@@ -309,6 +333,7 @@ int tvm_bench_gather(const float* buf, size_t n_floats, int n_groups, int iters,
 #define TVM_STAGE_BWD_APP    3
 #define TVM_STAGE_BWD_MARCH  4
 #define TVM_STAGE_BG         5
+#define TVM_STAGE_BWD_BG     6
 #define TVM_STAGE_COUNT      8
 int tvm_profile_enable(int on);
 /* waits for the recorded events, adds per-stage milliseconds / launch counts into the two

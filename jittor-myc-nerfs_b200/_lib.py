@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # TVM_LIB: developer override (kernel-tuning experiments build variant libraries next to the default one)
 LIB_PATH = os.environ.get("TVM_LIB") or os.path.join(_HERE, "libtvmrender.so")
-ABI_VERSION = 12
+ABI_VERSION = 13
 
 # flags (tvmrender.h)
 WHITE_BG = 0x1
@@ -23,7 +23,7 @@ ACT_SOFTPLUS, ACT_RELU = 0, 1
 VARIANT_VM, VARIANT_REF, REF_HEAD_LD = 0, 1, 48
 CNT_M_IN, CNT_M_V, CNT_M_A, CNT_RAYS, CNT_WORDS = 0, 1, 2, 3, 8
 CNT_BG_RAYS, CNT_BG_SAMPLES = 4, 5
-STAGE_NAMES = ["march", "app", "composite", "bwd_app", "bwd_march", "bg"]
+STAGE_NAMES = ["march", "app", "composite", "bwd_app", "bwd_march", "bg", "bwd_bg"]
 SAMPLING_UNIFORM, SAMPLING_NPP = 0, 1
 STAGE_COUNT = 8
 
@@ -59,6 +59,13 @@ class TvmBgNet(C.Structure):
                                            "wv_t", "w_rgb", "b_rgb", "tc_weights")]
 
 
+BG_FIELDS = ("w0_t", "b0", "w1_t", "b1", "w2_t", "b2", "w_sigma", "b_sigma", "wf_t", "bf", "wv_t", "w_rgb", "b_rgb")
+
+
+class TvmBgGrads(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in BG_FIELDS]
+
+
 class TvmAdamTensor(C.Structure):
     _fields_ = [("p", C.c_void_p), ("g", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p), ("n", C.c_size_t), ("lr", C.c_float), ("lr_index", C.c_int32)]
 
@@ -75,7 +82,8 @@ class TvmGrads(C.Structure):
 EXPORTS = [
     "tvm_last_error", "tvm_abi_version", "tvm_device_count", "tvm_pack_grid", "tvm_unpack_grid",
     "tvm_pack_linear", "tvm_unpack_linear", "tvm_pack_alpha", "tvm_pack_alpha_bricks", "tvm_pack_alpha_dilated", "tvm_tc_weights_bytes", "tvm_pack_mlp_tc",
-    "tvm_workspace_bytes", "tvm_forward", "tvm_forward_npp", "tvm_bg_fold", "tvm_bg_tc_bytes", "tvm_pack_bg_tc", "tvm_backward", "tvm_density_alpha", "tvm_mse_loss",
+    "tvm_workspace_bytes", "tvm_forward", "tvm_forward_npp", "tvm_bg_fold", "tvm_bg_tc_bytes", "tvm_pack_bg_tc", "tvm_backward", "tvm_backward_npp", "tvm_bg_fold_bwd",
+    "tvm_density_alpha", "tvm_mse_loss",
     "tvm_profile_enable", "tvm_profile_collect",
     "tvm_dense_alpha", "tvm_alpha_mask_from_dense", "tvm_filter_rays", "tvm_generate_rays", "tvm_upsample_grid",
     "tvm_tv_loss", "tvm_l1_loss", "tvm_vector_diffs", "tvm_adam_step", "tvm_selftest_umma", "tvm_bench_gather",
@@ -139,6 +147,9 @@ def load() -> C.CDLL:
     lib.tvm_adam_step.argtypes = [C.POINTER(TvmAdamTensor), i32, f32, f32, f32, i32, vp, vp]
     lib.tvm_backward.argtypes = [C.POINTER(TvmModel), vp, i32, i32, vp, u32, vp, vp, vp, C.POINTER(TvmGrads), vp,
                                  C.c_size_t, vp]
+    lib.tvm_backward_npp.argtypes = [C.POINTER(TvmModel), C.POINTER(TvmBgNet), vp, i32, i32, vp, vp, u32, vp, vp,
+                                     C.POINTER(TvmGrads), C.POINTER(TvmBgGrads), vp, C.c_size_t, vp]
+    lib.tvm_bg_fold_bwd.argtypes = [vp] * 11
     lib.tvm_density_alpha.argtypes = [C.POINTER(TvmModel), vp, i32, f32, vp, vp]
     lib.tvm_mse_loss.argtypes = [vp, vp, i32, f32, vp, vp, vp]
     lib.tvm_profile_enable.argtypes = [i32]

@@ -12,8 +12,7 @@
 //   k_march_bwd  per ray (one warp, same march as k_march): dL/dw -> dL/dalpha through the transmittance
 //                product with ONE forward sweep (suffix sums = total - prefix), -> dL/dsigma -> softplus'
 //                -> scatter into density planes/lines with vector atomics
-#include "tvm_app_simt.cuh"
-#include "tvm_bwd.cuh"
+#include "tvm_bwd_simt.cuh"
 
 namespace tvm {
 
@@ -38,89 +37,18 @@ __global__ void k_bwd_prep(const BwdParams B) {
   if (B.d_penalty) tot = fmaf(*B.d_penalty, B.f.ws.pen_sum[ray], tot);
   float4 o = make_float4(g[0], g[1], g[2], tot - gs * acc);
   reinterpret_cast<float4*>(B.f.ws.bwd_scratch)[ray] = o;
-}
-
-// ------------------------------------------------------------------------------------------------
-// k_app_bwd helpers
-// ------------------------------------------------------------------------------------------------
-// out[K][ldo] += A[64][0..K)^T . Bm[64][0..128)   (weight gradient of one dense layer for this tile)
-__device__ __forceinline__ void wgrad_tile_128(const float* A, const float* Bm, int st, int K, float* out, int ldo) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int o4 = lane * 4;
-  for (int j0 = warp * 4; j0 < K; j0 += 32) {
-    float acc[4][4];
+  if (B.f.m.sampling == TVM_SAMPLING_NPP) {
+    // rgb_map = clamp(fg) + bg_lambda * bg_rgb_map (nerfplusplus.py:314-317): dL/d bg_lambda = d_rgb_map . bg_rgb_map,
+    // unclamped; the gate (:313) passes bg_lambda through or zeroes it.  Stored pre-multiplied by bg_lambda, because
+    // d bg_lambda / d alpha_k = -bg_lambda / (1 - alpha_k + 1e-6).
+    const float lam = B.f.ws.bg_lambda[ray];
+    float gl = 0.0f;
+    if (lam > 0.0f) {
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-      for (int b = 0; b < 4; ++b) acc[a][b] = 0.0f;
-#pragma unroll 4
-    for (int row = 0; row < kAppTile; ++row) {
-      const float4 bv = lds4(Bm + row * st + o4);
-      const float4 av = lds4(A + row * st + j0);     // broadcast; columns >= K are zero padding
-      fma4(acc[0], av.x, bv);
-      fma4(acc[1], av.y, bv);
-      fma4(acc[2], av.z, bv);
-      fma4(acc[3], av.w, bv);
+      for (int c = 0; c < 3; ++c) gl = fmaf(B.d_rgb_map[(size_t)ray * 3 + c], B.f.ws.bg_rgb[(size_t)ray * 3 + c], gl);
+      gl *= lam;
     }
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-      if (j0 + a < K) red_add_v4(out + (size_t)(j0 + a) * ldo + o4, acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
-  }
-}
-// out[K][NH] += A[64][0..K)^T . Bm[64][0..NH): one thread per j
-template <int NH>
-__device__ __forceinline__ void wgrad_tile_heads(const float* A, const float* Bm, int st, int K, float* out) {
-  const int j = threadIdx.x;
-  if (j >= K) return;
-  float acc[NH];
-#pragma unroll
-  for (int i = 0; i < NH; ++i) acc[i] = 0.0f;
-  for (int row = 0; row < kAppTile; ++row) {
-    const float a = A[row * st + j];
-#pragma unroll
-    for (int i = 0; i < NH; i += 4) fma4(acc + i, a, lds4(Bm + row * st + i));
-  }
-#pragma unroll
-  for (int i = 0; i < NH; i += 4) red_add_v4(out + (size_t)j * NH + i, acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
-}
-// bias gradient: out[o] += sum_rows Bm[row][o], o < 128
-__device__ __forceinline__ void bgrad_tile(const float* Bm, int st, float* out) {
-  const int o = threadIdx.x;
-  if (o >= kFeatureC) return;
-  float a = 0.0f;
-  for (int row = 0; row < kAppTile; ++row) a += Bm[row * st + o];
-  atomicAdd(out + o, a);
-}
-// dIn[row][j] = sum_o dz[row][o] * Wt[j][o] for j in [0,K); optional ReLU mask from act (may alias dst).
-template <bool MASK>
-__device__ __forceinline__ void app_dense_bwd(const float* __restrict__ Wt, const float* dz, int K, float* dst,
-                                              const float* act, int st) {
-  const int row = threadIdx.x & (kAppTile - 1), part = threadIdx.x >> 6;
-  const int JP = ((K + 3) / 4 + 7) / 8 * 8;        // columns per part, multiple of 8
-  const int jbeg = part * JP, jend = min(K, jbeg + JP);
-  const float* d = dz + row * st;
-  for (int j0 = jbeg; j0 < jend; j0 += 8) {
-    float acc[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
-    for (int o = 0; o < kFeatureC; o += 4) {
-      const float4 dv = lds4(d + o);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        if (j0 + i < jend) {   // warp-uniform
-          const float4 w = ldg4(Wt + (size_t)(j0 + i) * kFeatureC + o);
-          acc[i] = fmaf(dv.x, w.x, fmaf(dv.y, w.y, fmaf(dv.z, w.z, fmaf(dv.w, w.w, acc[i]))));
-        }
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      if (j0 + i < jend) {
-        float v = acc[i];
-        if (MASK) v = act[row * st + j0 + i] > 0.0f ? v : 0.0f;
-        dst[row * st + j0 + i] = v;
-      }
-    }
+    B.f.ws.bwd_lam[ray] = gl;
   }
 }
 
@@ -384,7 +312,8 @@ __global__ void __launch_bounds__(kMarchWarps * 32) k_march_bwd(const BwdParams 
   const float gs = (P.flags & TVM_WHITE_BG) ? g.x + g.y + g.z : 0.0f;
   const float total = g.w;
   const float dpen = B.d_penalty ? *B.d_penalty : 0.0f;
-  if (g.x == 0.0f && g.y == 0.0f && g.z == 0.0f && dpen == 0.0f) return;   // nothing flows into this ray
+  const float glam = m.sampling == TVM_SAMPLING_NPP ? P.ws.bwd_lam[ray] : 0.0f;   // NeRF++: bg_lambda * dL/d bg_lambda
+  if (g.x == 0.0f && g.y == 0.0f && g.z == 0.0f && dpen == 0.0f && glam == 0.0f) return;   // nothing flows into this ray
 
   const int C = m.n_density, S = P.S;
   const bool ert = !(P.flags & TVM_NO_ERT);
@@ -500,7 +429,8 @@ __global__ void __launch_bounds__(kMarchWarps * 32) k_march_bwd(const BwdParams 
     }
     const float suffix = total - (carry + ps);
     carry += __shfl_sync(0xffffffffu, ps, 31);
-    const float dalpha = dw * Tk - suffix / v;
+    float dalpha = dw * Tk - suffix / v;
+    if (glam != 0.0f && k < S) dalpha -= glam / TVM_ADD(TVM_SUB(1.0f, alpha), 1e-6f);   // through prod(1 - alpha + 1e-6)
     const float dsigma = dalpha * dist * (1.0f - alpha);
     const float dfeat = valid ? dsigma * feature2density_grad(m, f) : 0.0f;
 
@@ -551,14 +481,27 @@ int launch_app_bwd_tc(const BwdParams& B, int num_sms, cudaStream_t stream);   /
 
 using namespace tvm;
 
-extern "C" int tvm_backward(const TvmModel* m_host, const float* rays, int n_rays, int n_samples,
-                            const float* jitter, uint32_t flags, const float* rgb_map, const float* d_rgb_map,
-                            const float* d_penalty, const TvmGrads* grads_host, void* ws, size_t ws_bytes, void* stream_) {
-  (void)rgb_map;
+namespace tvm {
+int launch_bg_bwd(const BwdParams& B, const TvmBgGrads& bg_grads, int num_sms, cudaStream_t stream);   // tvm_bg_bwd.cu
+}
+
+// shared body of tvm_backward (bg_host == NULL) and tvm_backward_npp
+static int backward_impl(const TvmModel* m_host, const TvmBgNet* bg_host, const float* rays, int n_rays, int n_samples,
+                         const float* jitter, const float* bg_rand, uint32_t flags, const float* d_rgb_map,
+                         const float* d_penalty, const TvmGrads* grads_host, const TvmBgGrads* bg_grads_host, void* ws,
+                         size_t ws_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   BwdParams B;
+  if (bg_host) flags &= ~TVM_WHITE_BG;          // the foreground of NerfPlusPlus renders on black (nerfplusplus.py:274)
   if (int rc = fill_fwd_params(B.f, m_host, rays, n_rays, n_samples, jitter, flags, ws, ws_bytes)) return rc;
   TVM_REQUIRE(d_rgb_map && grads_host, "null argument");
+  TVM_REQUIRE((m_host->sampling == TVM_SAMPLING_NPP) == (bg_host != nullptr),
+              "TVM_SAMPLING_NPP models go through tvm_backward_npp, all others through tvm_backward");
+  if (bg_host) {
+    TVM_REQUIRE(jitter && bg_rand && bg_grads_host, "tvm_backward_npp needs fg_rand, bg_rand and TvmBgGrads");
+    B.f.bg = *bg_host;
+    B.f.bg_rand = bg_rand;
+  }
   const bool ref = m_host->variant == TVM_VARIANT_REF;
   B.d_rgb_map = d_rgb_map;
   B.d_penalty = ref ? d_penalty : nullptr;
@@ -591,5 +534,27 @@ extern "C" int tvm_backward(const TvmModel* m_host, const float* rays, int n_ray
     k_march_bwd<<<(n_rays + kMarchWarps - 1) / kMarchWarps, kMarchWarps * 32, 0, stream>>>(B);
   }
   TVM_CHECK_CUDA(cudaGetLastError());
+  if (bg_host) {
+    ProfileScope prof(TVM_STAGE_BWD_BG, stream);
+    if (int rc = launch_bg_bwd(B, *bg_grads_host, sms, stream)) return rc;
+  }
   return 0;
+}
+
+extern "C" int tvm_backward(const TvmModel* m_host, const float* rays, int n_rays, int n_samples,
+                            const float* jitter, uint32_t flags, const float* rgb_map, const float* d_rgb_map,
+                            const float* d_penalty, const TvmGrads* grads_host, void* ws, size_t ws_bytes, void* stream_) {
+  (void)rgb_map;
+  return backward_impl(m_host, nullptr, rays, n_rays, n_samples, jitter, nullptr, flags, d_rgb_map, d_penalty, grads_host,
+                       nullptr, ws, ws_bytes, stream_);
+}
+
+extern "C" int tvm_backward_npp(const TvmModel* m_host, const TvmBgNet* bg_host, const float* rays, int n_rays,
+                                int n_samples, const float* fg_rand, const float* bg_rand, uint32_t flags,
+                                const float* rgb_map, const float* d_rgb_map, const TvmGrads* grads_host,
+                                const TvmBgGrads* bg_grads_host, void* ws, size_t ws_bytes, void* stream_) {
+  (void)rgb_map;
+  TVM_REQUIRE(bg_host != nullptr, "null TvmBgNet");
+  return backward_impl(m_host, bg_host, rays, n_rays, n_samples, fg_rand, bg_rand, flags, d_rgb_map, nullptr, grads_host,
+                       bg_grads_host, ws, ws_bytes, stream_);
 }

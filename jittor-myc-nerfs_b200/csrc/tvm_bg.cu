@@ -36,6 +36,9 @@ __device__ __forceinline__ void bg_hidden(const float* __restrict__ Wt, const fl
                                                     fmaxf(acc[i + 3], 0.f));
 }
 
+// REFRESH: only re-derive ws.bg_rgb in fp32 (tvm_backward_npp after a tensor-core forward: the backward's suffix sums
+// must be consistent with its own fp32 recompute); rgb_map, counters and aux are left alone.
+template <bool REFRESH>
 __global__ void __launch_bounds__(kAppThreads) k_bg_simt(const FwdParams P) {
   extern __shared__ __align__(16) float smem[];
   const int st = P.st;
@@ -166,7 +169,11 @@ __global__ void __launch_bounds__(kAppThreads) k_bg_simt(const FwdParams P) {
       c0 = warp_sum(c0);
       c1 = warp_sum(c1);
       c2 = warp_sum(c2);
-      if (lane == 0) {
+      if (lane == 0 && REFRESH) {
+        P.ws.bg_rgb[(size_t)ray * 3 + 0] = c0;
+        P.ws.bg_rgb[(size_t)ray * 3 + 1] = c1;
+        P.ws.bg_rgb[(size_t)ray * 3 + 2] = c2;
+      } else if (lane == 0) {
         if (P.counters) {
           atomicAdd(&P.counters[TVM_CNT_BG_RAYS], 1ull);
           atomicAdd(&P.counters[TVM_CNT_BG_SAMPLES], (unsigned long long)(tiles_done * kAppTile));
@@ -175,6 +182,9 @@ __global__ void __launch_bounds__(kAppThreads) k_bg_simt(const FwdParams P) {
         P.rgb_map[(size_t)ray * 3 + 0] += lam * c0;       // nerfplusplus.py:314-317 (no clamp after the sum)
         P.rgb_map[(size_t)ray * 3 + 1] += lam * c1;
         P.rgb_map[(size_t)ray * 3 + 2] += lam * c2;
+        P.ws.bg_rgb[(size_t)ray * 3 + 0] = c0;      // kept for tvm_backward_npp
+        P.ws.bg_rgb[(size_t)ray * 3 + 1] = c1;
+        P.ws.bg_rgb[(size_t)ray * 3 + 2] = c2;
         if (P.aux.bg_rgb_map) {
           P.aux.bg_rgb_map[(size_t)ray * 3 + 0] = c0;
           P.aux.bg_rgb_map[(size_t)ray * 3 + 1] = c1;
@@ -219,8 +229,17 @@ int launch_bg(const FwdParams& P, int num_sms, cudaStream_t stream) {
   if (P.aux.bg_rgb_map) TVM_CHECK_CUDA(cudaMemsetAsync(P.aux.bg_rgb_map, 0, (size_t)P.n * 12, stream));
   if ((P.flags & TVM_MLP_MASK) == TVM_MLP_BF16) return launch_bg_tc(P, num_sms, stream);
   const size_t smem = ((size_t)kAppTile * 2 * P.st + kAppTile * 4 + kAppTile + kBgHid + 4) * sizeof(float);
-  TVM_CHECK_CUDA(cudaFuncSetAttribute(k_bg_simt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_bg_simt<<<num_sms * 2, kAppThreads, smem, stream>>>(P);
+  TVM_CHECK_CUDA(cudaFuncSetAttribute(k_bg_simt<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_bg_simt<false><<<num_sms * 2, kAppThreads, smem, stream>>>(P);
+  TVM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// fp32 re-evaluation of ws.bg_rgb for the rays of ws.bg_list (see k_bg_simt<REFRESH>)
+int launch_bg_refresh(const FwdParams& P, int num_sms, cudaStream_t stream) {
+  const size_t smem = ((size_t)kAppTile * 2 * P.st + kAppTile * 4 + kAppTile + kBgHid + 4) * sizeof(float);
+  TVM_CHECK_CUDA(cudaFuncSetAttribute(k_bg_simt<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_bg_simt<true><<<num_sms * 2, kAppThreads, smem, stream>>>(P);
   TVM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

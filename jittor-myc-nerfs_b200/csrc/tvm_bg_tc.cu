@@ -329,6 +329,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_bg_tc(const FwdParams P) {
       const float c = (CS[ptid] + CS[4 + ptid]) + (CS[8 + ptid] + CS[12 + ptid]);
       const float lam = P.ws.bg_lambda[ray];
       P.rgb_map[(size_t)ray * 3 + ptid] += lam * c;                       // nerfplusplus.py:314-317 (no clamp after the sum)
+      P.ws.bg_rgb[(size_t)ray * 3 + ptid] = c;                            // kept for tvm_backward_npp
       if (P.aux.bg_rgb_map) P.aux.bg_rgb_map[(size_t)ray * 3 + ptid] = c;
     }
     // the scheduler barrier at the top of the loop orders these CS/VB reads before the next ray's writes

@@ -48,6 +48,8 @@ struct Workspace {
   float* bwd_scratch;    // [n][4]    per-ray scratch of the backward pass
   float* bg_lambda;      // [n]       NeRF++: prod(1 - alpha + 1e-6) of the foreground, 0 when <= 0.1
   uint32_t* bg_list;     // [n]       NeRF++: rays whose background is evaluated (bg_lambda > 0.1); count at n_entries[1]
+  float* bg_rgb;         // [n][3]    NeRF++: composited background colour of the evaluated rays (before the bg_lambda factor)
+  float* bwd_lam;        // [n]       NeRF++ backward: bg_lambda * dL/d bg_lambda of the ray
   uint32_t cap;
   int NB;
   size_t bytes;
@@ -79,6 +81,8 @@ inline Workspace carve_workspace(void* base, int n, int S) {
   w.bwd_scratch = (float*)take((size_t)n * 16);
   w.bg_lambda = (float*)take((size_t)n * 4);
   w.bg_list = (uint32_t*)take((size_t)n * 4);
+  w.bg_rgb = (float*)take((size_t)n * 12);
+  w.bwd_lam = (float*)take((size_t)n * 4);
   w.bytes = off;
   return w;
 }

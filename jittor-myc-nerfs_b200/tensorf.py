@@ -16,6 +16,7 @@ import numpy as np
 import torch
 
 from . import _lib as L
+from .checkpoint import CheckpointMixin
 from .maintain import MaintainMixin
 from .train_ops import RegularizerMixin
 
@@ -127,7 +128,26 @@ class _RenderFn(torch.autograd.Function):
         return (None, None, None, None, None, *grads)
 
 
-class TensorVMSplit(MaintainMixin, RegularizerMixin, torch.nn.Module):
+class _RenderNppFn(torch.autograd.Function):
+    """Autograd node of NerfPlusPlus: tvm_forward_npp / tvm_backward_npp (foreground grids + head, background MLPNet)."""
+
+    @staticmethod
+    def forward(ctx, model, rays, fg_rand, bg_rand, flags, S, *params):
+        rgb, depth = model._forward_npp_raw(rays, fg_rand, bg_rand, flags, S)
+        ctx.model, ctx.flags, ctx.S = model, flags, S
+        ctx.save_for_backward(rays, fg_rand, bg_rand, rgb)
+        ctx.mark_non_differentiable(depth)
+        return rgb, depth
+
+    @staticmethod
+    def backward(ctx, d_rgb, _d_depth):
+        rays, fg_rand, bg_rand, rgb = ctx.saved_tensors
+        d_rgb = torch.zeros_like(rgb) if d_rgb is None else d_rgb.contiguous()
+        grads = ctx.model._backward_npp_raw(rays, fg_rand, bg_rand, ctx.flags, ctx.S, rgb, d_rgb)
+        return (None, None, None, None, None, None, *grads)
+
+
+class TensorVMSplit(MaintainMixin, RegularizerMixin, CheckpointMixin, torch.nn.Module):
     VARIANT = L.VARIANT_VM
 
     def __init__(self, aabb, gridSize, device, density_n_comp=8, appearance_n_comp=24, app_dim=27,
@@ -667,7 +687,7 @@ class _BgNet(torch.nn.Module):
 
 class NerfPlusPlus(TensorVMSplit):
     """NerfPlusPlus (models/nerfplusplus.py:143-318): sphere-bounded always-jittered foreground sampling plus a
-    512-sample inverted-sphere background MLP.  Forward only (tvm_forward_npp); the U[0,1) draws of
+    512-sample inverted-sphere background MLP (tvm_forward_npp / tvm_backward_npp); the U[0,1) draws of
     perturb_samples come from torch.rand on the device unless `fg_rand` / `bg_rand` are injected."""
 
     def set_nerfplusplus(self, bg_freq=4, bg_view_freq=2, bg_D=4, radii=20):
@@ -703,19 +723,90 @@ class NerfPlusPlus(TensorVMSplit):
     def _finish_model(self, s):
         s.sampling, s.radii = L.SAMPLING_NPP, float(self.radii)
 
+    _BG_SIZES = dict(w0_t=20 * 128, b0=128, w1_t=128 * 128, b1=128, w2_t=148 * 128, b2=128, w_sigma=128, b_sigma=64,
+                     wf_t=128 * 64, bf=64, wv_t=15 * 64, w_rgb=3 * 64, b_rgb=64)
+
+    def _bg_layout(self):
+        """Offsets (floats) of the packed background tensors; the gradient buffer uses the same layout."""
+        offs, off = {}, 0
+        for k, v in self._BG_SIZES.items():
+            offs[k] = off
+            off += (v + 63) // 64 * 64
+        return self._BG_SIZES, offs, off
+
+    def _bg_param_list(self):
+        n = self.bg_net
+        lins = [n.base_layers[0][0], n.base_layers[1][0], n.base_layers[2][0], n.sigma_layers[0], n.base_remap_layers[0],
+                n.rgb_layers[0], n.rgb_layers[2]]
+        return [t for lin in lins for t in (lin.weight, lin.bias)]
+
+    def _forward_npp_raw(self, rays, fg_rand, bg_rand, flags, S, out=None, aux=None):
+        lib = L.load()
+        n = rays.shape[0]
+        model, bg = self._model(), self._bg_struct()
+        ws = self._workspace(n, S)
+        if out is None:
+            out = (torch.empty((n, 3), dtype=torch.float32, device=rays.device),
+                   torch.empty((n,), dtype=torch.float32, device=rays.device))
+        rgb, depth = out
+        L.check(lib.tvm_forward_npp(C.byref(model), C.byref(bg), _ptr(rays), n, S, _ptr(fg_rand), _ptr(bg_rand), flags,
+                                    _ptr(rgb), _ptr(depth), C.byref(aux) if aux is not None else None,
+                                    _ptr(self.counters) if self.collect_counters else None, _ptr(ws), ws.numel(),
+                                    _stream_ptr()), "tvm_forward_npp")
+        return rgb, depth
+
+    def _backward_npp_raw(self, rays, fg_rand, bg_rand, flags, S, rgb, d_rgb):
+        """tvm_backward_npp -> gradients in the order of _param_list() + _bg_param_list(), reference shapes."""
+        lib = L.load()
+        n = rays.shape[0]
+        model, bg = self._model(), self._bg_struct()
+        items, total = self._layout()
+        sizes, offs, bg_total = self._bg_layout()
+        if getattr(self, "_grads_packed", None) is None or self._grads_packed.numel() != total + bg_total:
+            self._grads_packed = torch.empty(total + bg_total, dtype=torch.float32, device=self.device)
+        gp = self._grads_packed
+        gp.zero_()
+        gs = self._struct_for(gp, L.TvmGrads)
+        bgp = gp[total:]
+        bgs = L.TvmBgGrads()
+        for k in sizes:
+            setattr(bgs, k, bgp.data_ptr() + 4 * offs[k])
+        ws = self._workspace(n, S)
+        L.check(lib.tvm_backward_npp(C.byref(model), C.byref(bg), _ptr(rays), n, int(S), _ptr(fg_rand), _ptr(bg_rand), flags,
+                                     _ptr(rgb), _ptr(d_rgb), C.byref(gs), C.byref(bgs), _ptr(ws), ws.numel(),
+                                     _stream_ptr()), "tvm_backward_npp")
+        if self.grad_sync:
+            from .dist import allreduce_flat_
+            allreduce_flat_(gp, group=self.grad_sync_group, average=True)
+        fg = self._unpack_grads(gp, items)
+        st = _stream_ptr()
+        at = lambda k: C.c_void_p(bgp.data_ptr() + 4 * offs[k])
+        nb = self.bg_net
+        out = []
+        for i, (wk, bk) in enumerate((("w0_t", "b0"), ("w1_t", "b1"), ("w2_t", "b2"))):
+            w = nb.base_layers[i][0].weight
+            gw = torch.empty_like(w)
+            L.check(lib.tvm_unpack_linear(at(wk), w.shape[0], w.shape[1], w.shape[0], _ptr(gw), st), "tvm_unpack_linear")
+            out += [gw, bgp[offs[bk]:offs[bk] + 128].clone()]
+        out += [bgp[offs["w_sigma"]:offs["w_sigma"] + 128].clone().reshape(1, 128), bgp[offs["b_sigma"]:offs["b_sigma"] + 1].clone()]
+        r, g0 = nb.base_remap_layers[0], nb.rgb_layers[0]
+        d_rw, d_rb = torch.empty_like(r.weight), torch.empty_like(r.bias)
+        d_gw, d_gb = torch.empty_like(g0.weight), torch.empty_like(g0.bias)
+        L.check(lib.tvm_bg_fold_bwd(_ptr(r.weight.detach()), _ptr(r.bias.detach()), _ptr(g0.weight.detach()), at("wf_t"),
+                                    at("bf"), at("wv_t"), _ptr(d_rw), _ptr(d_rb), _ptr(d_gw), _ptr(d_gb), st),
+                "tvm_bg_fold_bwd")
+        out += [d_rw, d_rb, d_gw, d_gb, bgp[offs["w_rgb"]:offs["w_rgb"] + 192].clone().reshape(3, 64),
+                bgp[offs["b_rgb"]:offs["b_rgb"] + 3].clone()]
+        return [*fg, *out]
+
     def _bg_struct(self):
         """TvmBgNet over a packed fp32 buffer; re-packed (and re-folded) when a bg parameter changed."""
         lib = L.load()
         n = self.bg_net
         params = list(n.parameters())
         versions = tuple((p.data_ptr(), p._version) for p in params)
-        sizes = dict(w0_t=20 * 128, b0=128, w1_t=128 * 128, b1=128, w2_t=148 * 128, b2=128, w_sigma=128, b_sigma=64,
-                     wf_t=128 * 64, bf=64, wv_t=15 * 64, w_rgb=3 * 64, b_rgb=64)
+        sizes, offs, off = self._bg_layout()
         if self._bg_packed is None or versions != self._bg_versions:
-            offs, off = {}, 0
-            for k, v in sizes.items():
-                offs[k] = off
-                off += (v + 63) // 64 * 64
             if self._bg_packed is None:
                 self._bg_packed = torch.zeros(off, dtype=torch.float32, device=self.device)
             buf, st = self._bg_packed, _stream_ptr()
@@ -752,9 +843,6 @@ class NerfPlusPlus(TensorVMSplit):
                 additional_output=True, fg_rand=None, bg_rand=None, aux=None):
         if ndc_ray:
             raise NotImplementedError("ndc_ray sampling is outside the hot path")
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError("NerfPlusPlus backward is not built: call under torch.no_grad()")
-        lib = L.load()
         S = int(N_samples) if N_samples > 0 else self.nSamples
         rays = rays_chunk.contiguous()
         n, nmax = rays.shape[0], self.max_rays_per_launch(S)
@@ -763,18 +851,19 @@ class NerfPlusPlus(TensorVMSplit):
             fg_rand = torch.rand((n, S), dtype=torch.float32, device=dev)       # perturb_samples, :204
         if bg_rand is None:
             bg_rand = torch.rand((n, 512), dtype=torch.float32, device=dev)
-        model, bg = self._model(), self._bg_struct()
+        fg_rand, bg_rand = fg_rand.contiguous(), bg_rand.contiguous()
+        flags = self._flags(False)
+        params = [*self._param_list(), *self._bg_param_list()]
+        if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            if n > nmax:
+                raise ValueError(f"training chunk of {n} rays exceeds the workspace budget ({nmax} rays)")
+            assert aux is None
+            return _RenderNppFn.apply(self, rays, fg_rand, bg_rand, flags, S, *params)
         rgb = torch.empty((n, 3), dtype=torch.float32, device=dev)
         depth = torch.empty((n,), dtype=torch.float32, device=dev)
-        flags = self._flags(False)
         for s in range(0, n, nmax):
             e = min(n, s + nmax)
-            ws = self._workspace(e - s, S)
-            L.check(lib.tvm_forward_npp(C.byref(model), C.byref(bg), _ptr(rays[s:e]), e - s, S, _ptr(fg_rand[s:e]),
-                                        _ptr(bg_rand[s:e]), flags, _ptr(rgb[s:e]), _ptr(depth[s:e]),
-                                        C.byref(aux) if aux is not None else None,
-                                        _ptr(self.counters) if self.collect_counters else None, _ptr(ws), ws.numel(),
-                                        _stream_ptr()), "tvm_forward_npp")
+            self._forward_npp_raw(rays[s:e], fg_rand[s:e], bg_rand[s:e], flags, S, out=(rgb[s:e], depth[s:e]), aux=aux)
         return rgb, depth
 
     execute = forward

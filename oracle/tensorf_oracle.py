@@ -347,6 +347,7 @@ class OracleTensorVMSplit:
             depth_map = torch.sum(weight * z_vals, -1)
             depth_map = depth_map + (1. - acc_map) * rays_chunk[..., -1]   # column 5 = d_z: reference quirk
 
+        self._alpha_live = alpha        # the reference hands the live Var to NerfPlusPlus.execute (additional_output, :533-534)
         if stages is not None:
             stages.update(ray_valid=ray_valid, sigma=sigma.detach(), alpha=alpha.detach(), weight=weight.detach(),
                           bg_weight=bg_weight.detach(), app_mask=app_mask, rgb=rgb.detach(),
@@ -449,6 +450,26 @@ class OracleNerfPlusPlus(OracleTensorVMSplit):
                                  ("rgb0", e["bg_rgb0"]), ("rgb1", e["bg_rgb1"]))}
         self.skips = [int(self.bg_D / 2)]
         self.fg_rand = self.bg_rand = None
+        if k.get("requires_grad") or (len(a) > 4 and a[4]):
+            for x in self.bg_parameters().values():
+                x.requires_grad_(True)
+
+    def bg_parameters(self):
+        """bg_net parameters under the reference's state_dict names (MLPNet, nerfplusplus.py:86-113)."""
+        out = {}
+        for i, (w, b) in enumerate(self.bg["base"]):
+            out[f"bg_net.base_layers.{i}.0.weight"], out[f"bg_net.base_layers.{i}.0.bias"] = w, b
+        for name, key, idx in (("sigma_layers", "sigma", 0), ("base_remap_layers", "remap", 0), ("rgb_layers", "rgb0", 0),
+                               ("rgb_layers", "rgb1", 2)):
+            w, b = self.bg[key][0]
+            out[f"bg_net.{name}.{idx}.weight"], out[f"bg_net.{name}.{idx}.bias"] = w, b
+        return out
+
+    def named_parameters(self):
+        out = super().named_parameters()
+        if hasattr(self, "bg"):
+            out.update(self.bg_parameters())
+        return out
 
     @staticmethod
     def embed(x, n_freqs):
@@ -526,7 +547,7 @@ class OracleNerfPlusPlus(OracleTensorVMSplit):
         self.fg_rand, bg_rand = fg_rand, bg_rand.to(self.dtype)
         st = {} if stages is None else stages
         rgb_map, depth_map = super().execute(rays_chunk, False, is_train, ndc_ray, N_samples, stages=st)
-        alpha = st["alpha"]
+        alpha = self._alpha_live        # not detached: bg_lambda carries gradient into the density grids (:277-278)
         bg_lambda = jt_cumprod(1. - alpha + TINY_NUMBER, -1, self.opts.cumprod)[..., -1]
         rays_chunk = rays_chunk.to(self.dtype)
         ray_o, ray_d = rays_chunk[:, :3], rays_chunk[:, 3:6]
@@ -618,7 +639,10 @@ def backward_case(case, d_rgb_map=None, dtype=torch.float64, opts=None, N_sample
     m = make_oracle(case, dtype=dtype, opts=opts, requires_grad=True)
     rays = torch.from_numpy(case["rays"])
     jit = None if case.get("jitter") is None else torch.from_numpy(case["jitter"])
-    rgb, depth = m(rays, white_bg=white_bg, is_train=jit is not None, N_samples=N_samples, jitter=jit)
+    kw = {}
+    if case.get("fg_rand") is not None:      # NerfPlusPlus: injected draws of perturb_samples
+        kw = dict(fg_rand=torch.from_numpy(case["fg_rand"]), bg_rand=torch.from_numpy(case["bg_rand"]))
+    rgb, depth = m(rays, white_bg=white_bg, is_train=jit is not None, N_samples=N_samples, jitter=jit, **kw)
     if d_rgb_map is None:
         tgt = torch.from_numpy(case["target"]).to(dtype)
         loss = torch.mean((rgb - tgt) ** 2)
