@@ -48,8 +48,11 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-chunks", type=int, default=256,
                     help="chunks of 1024 rays the CPU baseline renders (256 = 41%% of the frame, 10-30 s of CPU work)")
-    ap.add_argument("--variant", default="vm", choices=["vm", "ref"], help="model of the train workload (ref = REFTensoRF, "
-                    "configs/Scar.txt, with normal_vector_penalty_weight 0.5)")
+    ap.add_argument("--app-planes", default="bf16", choices=["fp32", "bf16"],
+                    help="bf16: with --mlp bf16 the tensor-core head gathers bf16 copies of the appearance planes (half the gather "
+                         "bytes of the head; same 1e-2 rgb tolerance); density planes, lines, masks and compositing stay fp32")
+    ap.add_argument("--variant", default="vm", choices=["vm", "ref", "npp"], help="model of the train workload (ref = REFTensoRF, "
+                    "configs/Scar.txt, with normal_vector_penalty_weight 0.5; npp = NerfPlusPlus, configs/Scarf.txt)")
     ap.add_argument("--workload", default="frame", choices=["frame", "train", "npp", "ref", "maintain"],
                     help="frame = BASELINE configs[1] (the contract line); train = configs[2] (4096-ray fwd+bwd step, "
                          "128^3 grid); npp / ref = configs[3] (NeRF++ background / Ref-NeRF appearance, full frame). "
@@ -294,8 +297,7 @@ def run_side_workload(args):
     rays = torch.from_numpy(np.ascontiguousarray(rays_np)).to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     extra = {}
-    if args.workload == "npp":
-        fg, bg = fx.npp_rand(1, 1)      # shapes only; the draws themselves come from the device RNG below
+    if variant == "npp":
         g = torch.Generator(device=dev).manual_seed(fx.SEED_BASE)
         extra = dict(fg_rand=torch.rand((n, S), device=dev, generator=g), bg_rand=torch.rand((n, 512), device=dev, generator=g))
 
@@ -309,7 +311,10 @@ def run_side_workload(args):
         if train:
             for p in model.parameters():
                 p.grad = None
-            rgb, _ = model(rays, is_train=True, white_bg=True, N_samples=S, jitter=jit)
+            if variant == "npp":
+                rgb, _ = model(rays, is_train=True, N_samples=S, **extra)
+            else:
+                rgb, _ = model(rays, is_train=True, white_bg=True, N_samples=S, jitter=jit)
             loss = torch.mean((rgb - tgt) ** 2)
             if variant == "ref":
                 loss = loss + 0.5 * model.penalty.sum()              # train.py:253-255, configs/Scar.txt:7
@@ -383,6 +388,7 @@ def run_side_workload(args):
         line["full_step"] = {"ms_per_step": ms_full / args.steps, "rays_per_s": n * world / (ms_full / args.steps * 1e-3),
                              "includes": "fwd + bwd + TV_loss_density + TV_loss_app (weights 2.0, configs/Scar.txt) + Adam over "
                                          "all parameter tensors + re-pack of the updated grids"}
+    if train and variant != "npp":
         # the same full step captured once into a CUDA graph (TrainStepGraph) and replayed: no host time between kernels
         model.collect_counters = False
         L.profile_enable(False)
@@ -441,6 +447,7 @@ def main():
 
     case = make_case(args, rank)
     model = pkg.model_from_params(case["model"], f"cuda:{local_rank}", case["alpha_volume"], case["alpha_aabb"], args.mlp)
+    model.app_planes_bf16 = args.app_planes == "bf16" and args.mlp == "bf16"
     n = case["rays"].shape[0]
     S = model.nSamples
     rays_host = torch.from_numpy(case["rays"]).pin_memory()
@@ -544,7 +551,8 @@ def main():
     bytes_march_step = 32.0 * n + 1.0 * M_in + 1152.0 * M_v + 12.0 * M_a
     bytes_per_launch = bytes_march_step * args.steps / launches_march
     achieved = bytes_per_launch / (march_ms * 1e-3) / 1e9
-    bytes_app_step = 3456.0 * M_a
+    # appearance gather per entry: 12 plane taps + 6 line taps of 48 channels, fp32 (192 B) or bf16 planes (96 B)
+    bytes_app_step = (3456.0 if not model.app_planes_bf16 else 12 * 96.0 + 6 * 192.0) * M_a
     app_ms = stage_ms["app"] / max(1, stage_cnt["app"])
     # DRAM bytes per launch of the same kernel from the committed `ncu --set full` capture (profiles/traffic.json)
     traffic, traffic_src = None, None
@@ -571,10 +579,11 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if args.mlp == "fp32" else f"f32 gather/composite + {args.mlp} tensor-core MLP",
+            "dtype": "f32" if args.mlp == "fp32" else f"f32 gather/composite + {args.mlp} tensor-core MLP" +
+                     (" fed from bf16 appearance planes" if model.app_planes_bf16 else ""),
             "data": "synthetic",
             "config": {"workload": workload_name(args), "n_samples": S, "rays_per_step_per_gpu": n,
-                       "mlp": args.mlp, "early_ray_termination": True, "l2": "flushed before every timed step "
+                       "mlp": args.mlp, "app_planes": "bf16" if model.app_planes_bf16 else "fp32", "early_ray_termination": True, "l2": "flushed before every timed step "
                        "(256 MiB write)", "parallelism": f"one frame per rank x {world}",
                        "samples_per_s_marched": value * S, "samples_per_s_gathered": M_v * world / (ms_total / args.steps * 1e-3),
                        "per_step_counts": {"M_in": M_in, "M_v_gathered": M_v, "M_a": M_a}},

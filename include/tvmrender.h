@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define TVM_ABI_VERSION 13
+#define TVM_ABI_VERSION 14
 
 /* flags for tvm_forward / tvm_backward */
 #define TVM_WHITE_BG      0x1u  /* rgb_map += 1 - acc_map          (tensorBase.py:523-524) */
@@ -109,6 +109,10 @@ typedef struct TvmModel {
   const void* tc_weights;
   int32_t sampling;         /* TVM_SAMPLING_*                                                            */
   float radii;              /* TVM_SAMPLING_NPP: radius of the bounding sphere (configs/Scarf.txt:14)    */
+  /* optional bf16 copies of app_plane[k] written by tvm_pack_bf16 (all NULL = none).  When present the TVM_MLP_BF16
+   * appearance head gathers its plane texels from them (half the gather bytes; the plane x line products are rounded
+   * to bf16 as the GEMM operand in that mode anyway).  TVM_MLP_FP32 and every backward kernel ignore them.        */
+  const void* app_plane_bf16[3];
 } TvmModel;
 
 /* NerfPlusPlus background network (nerfplusplus.py:66-140 with bg_D=3, W=128, skips=[1], bg_freq=2,
@@ -188,6 +192,8 @@ int tvm_unpack_grid(const float* hwc, int C, int H, int W, float* out_nchw, void
 /* Linear weight [out][in] -> [in][out_pad] (zero padded columns)                              */
 int tvm_pack_linear(const float* w_out_in, int out_c, int in_c, int out_pad, float* out_t, void* stream);
 int tvm_unpack_linear(const float* w_t, int out_c, int in_c, int out_pad, float* out_w, void* stream);
+/* fp32 -> bf16 (round to nearest even) copy of n values: the bf16 appearance planes of TvmModel.app_plane_bf16 */
+int tvm_pack_bf16(const float* src, size_t n, void* dst_bf16, void* stream);
 /* {0,1} fp32 volume [D][H][W] -> bit stream (bit set iff value > 0); n_words = ceil(D*H*W/32)  */
 int tvm_pack_alpha(const float* volume, int D, int H, int W, uint32_t* bits, void* stream);
 /* brick index of a packed alpha volume; n_words = ceil(ceil(D/8)*ceil(H/8)*ceil(W/8) / 32)        */

@@ -54,7 +54,8 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 __device__ __forceinline__ void mlp_group_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
-template <int CA, int APP_DIM, int FEA_PE, int VIEW_PE, bool REF>
+// PB16: plane texels come from the bf16 copies (TvmModel.app_plane_bf16): 8-byte loads, adjacent-pair addressing
+template <int CA, int APP_DIM, int FEA_PE, int VIEW_PE, bool REF, bool PB16>
 __global__ void __launch_bounds__(kThreadsV2, 1) k_app_tc(const FwdParams P) {
   constexpr int NH = REF ? TVM_REF_HEAD_LD : 32;
   constexpr int C0 = REF ? 1 : 0;                       // REF: column 0 of the MLP input is -dot (REFTensoRF.py:20)
@@ -132,6 +133,36 @@ __global__ void __launch_bounds__(kThreadsV2, 1) k_app_tc(const FwdParams P) {
           const uint2 en = P.ws.ent[e];
           float u[3], dir[3];
           entry_coords(m, P.rays, P.jitter, en.x, en.y, P.S, u, dir);
+          if (PB16) {
+            AxisPair ax[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) ax[i] = axis_pair(u[i], m.grid[i]);
+#pragma unroll
+            for (int kk = 0; kk < 3; ++kk) {
+              const VmPair t = vm_pair(m, ax, kk, CA);
+              const uint16_t* pl = reinterpret_cast<const uint16_t*>(m.app_plane_bf16[kk]);
+              const float* ln = m.app_line[kk] + t.lrow;
+#pragma unroll
+              for (int c = q * 4; c < CA; c += 16) {
+                const uint2 a = __ldg(reinterpret_cast<const uint2*>(pl + t.row0 + c));
+                const uint2 b = __ldg(reinterpret_cast<const uint2*>(pl + t.row0 + c + CA));
+                const uint2 cc = __ldg(reinterpret_cast<const uint2*>(pl + t.row1 + c));
+                const uint2 d = __ldg(reinterpret_cast<const uint2*>(pl + t.row1 + c + CA));
+                const float4 l0 = ldg4(ln + c), l1 = ldg4(ln + c + CA);
+                auto lo = [](uint32_t v) { return __uint_as_float(v << 16); };
+                auto hi = [](uint32_t v) { return __uint_as_float(v & 0xffff0000u); };
+                const float px = lo(a.x) * t.nw + lo(b.x) * t.ne + lo(cc.x) * t.sw + lo(d.x) * t.se;
+                const float py = hi(a.x) * t.nw + hi(b.x) * t.ne + hi(cc.x) * t.sw + hi(d.x) * t.se;
+                const float pz = lo(a.y) * t.nw + lo(b.y) * t.ne + lo(cc.y) * t.sw + lo(d.y) * t.se;
+                const float pw = hi(a.y) * t.nw + hi(b.y) * t.ne + hi(cc.y) * t.sw + hi(d.y) * t.se;
+                const float lx = l0.x * t.lw0 + l1.x * t.lw1, ly = l0.y * t.lw0 + l1.y * t.lw1;
+                const float lz = l0.z * t.lw0 + l1.z * t.lw1, lw = l0.w * t.lw0 + l1.w * t.lw1;
+                const int k = kk * CA + c;
+                uint2 packed = make_uint2(pack_bf16(px * lx, py * ly), pack_bf16(pz * lz, pw * lw));
+                *reinterpret_cast<uint2*>(arow + (k >> 3) * LBO_A + (k & 7) * 2) = packed;
+              }
+            }
+          } else {
           Axis ax[3];
 #pragma unroll
           for (int i = 0; i < 3; ++i) ax[i] = axis_taps(u[i], m.grid[i]);
@@ -146,6 +177,7 @@ __global__ void __launch_bounds__(kThreadsV2, 1) k_app_tc(const FwdParams P) {
               uint2 packed = make_uint2(pack_bf16(pv.x * lv.x, pv.y * lv.y), pack_bf16(pv.z * lv.z, pv.w * lv.w));
               *reinterpret_cast<uint2*>(arow + (k >> 3) * LBO_A + (k & 7) * 2) = packed;
             }
+          }
           }
         } else {
 #pragma unroll
@@ -357,7 +389,9 @@ int launch_app_tc(const FwdParams& P, int num_sms, cudaStream_t stream) {
   const Image img(P.m.n_app, P.in_mlp_c, head_ld(P.m));
   const int KA = max(img.K1, 128);
   const size_t smem = ((img.bytes + 1023) & ~1023u) + 2 * (size_t)kRows * img.K0 * 2 + (size_t)kRows * KA * 2 + 128 + 1024;
-  auto kern = ref ? k_app_tc<48, 27, 2, 2, true> : k_app_tc<48, 27, 2, 2, false>;
+  const bool pb16 = P.m.app_plane_bf16[0] && P.m.app_plane_bf16[1] && P.m.app_plane_bf16[2];
+  auto kern = ref ? (pb16 ? k_app_tc<48, 27, 2, 2, true, true> : k_app_tc<48, 27, 2, 2, true, false>)
+                  : (pb16 ? k_app_tc<48, 27, 2, 2, false, true> : k_app_tc<48, 27, 2, 2, false, false>);
   TVM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<num_sms, kThreadsV2, smem, stream>>>(P);
   TVM_CHECK_CUDA(cudaGetLastError());

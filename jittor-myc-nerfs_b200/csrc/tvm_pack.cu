@@ -7,7 +7,9 @@
 // through a 32x33 shared-memory transpose tile.
 #include <stdarg.h>
 #include <string.h>
+#include <algorithm>
 #include <vector>
+#include <cuda_bf16.h>
 #include "tvm_common.cuh"
 
 namespace tvm {
@@ -299,6 +301,19 @@ extern "C" int tvm_mse_loss(const float* rgb_map, const float* target, int n_ray
   int blocks = (n3 + 255) / 256;
   if (blocks > 1184) blocks = 1184;
   k_mse<<<blocks, 256, 0, s>>>(rgb_map, target, n3, grad_scale, loss_out, d_rgb_map);
+  TVM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+__global__ void k_pack_bf16(const float* __restrict__ src, size_t n, __nv_bfloat16* __restrict__ dst) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = __float2bfloat16_rn(src[i]);
+}
+
+extern "C" int tvm_pack_bf16(const float* src, size_t n, void* dst_bf16, void* stream) {
+  TVM_REQUIRE(src && dst_bf16 && n > 0, "bad arguments");
+  const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 16);
+  k_pack_bf16<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, n, (__nv_bfloat16*)dst_bf16);
   TVM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

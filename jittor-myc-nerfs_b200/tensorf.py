@@ -189,6 +189,10 @@ class TensorVMSplit(MaintainMixin, RegularizerMixin, CheckpointMixin, torch.nn.M
         self.init_render_func(shadingMode, pos_pe, view_pe, fea_pe, featureC, device)
         # --- engine state -------------------------------------------------------------------
         self.mlp_mode = os.environ.get("TVM_MLP_MODE", "fp32")
+        # mlp_mode "bf16" only: gather the appearance-plane texels from bf16 copies (half the gather bytes of the head;
+        # the plane x line products are rounded to bf16 as the GEMM operand in that mode anyway).  Backward kernels and
+        # the fp32 mode always read the fp32 planes.
+        self.app_planes_bf16 = os.environ.get("TVM_APP_PLANES", "fp32") == "bf16"
         self.early_termination = True
         self.empty_space_skipping = True
         self.collect_counters = False
@@ -369,7 +373,7 @@ class TensorVMSplit(MaintainMixin, RegularizerMixin, CheckpointMixin, torch.nn.M
     def _model(self):
         """The TvmModel descriptor (host POD) for the current parameters / mask."""
         self._pack()
-        mask_key = (id(self.alphaMask), self.empty_space_skipping)
+        mask_key = (id(self.alphaMask), self.empty_space_skipping, self.mlp_mode, self.app_planes_bf16)
         if getattr(self, "_model_struct", None) is not None and self._model_mask_key == mask_key \
                 and not (self._tc_stale and self.mlp_mode != "fp32"):
             return self._model_struct
@@ -413,6 +417,22 @@ class TensorVMSplit(MaintainMixin, RegularizerMixin, CheckpointMixin, torch.nn.M
             L.check(lib.tvm_pack_mlp_tc(C.byref(s), _ptr(self._tc), _stream_ptr()), "tvm_pack_mlp_tc")
             s.tc_weights = self._tc.data_ptr()
             self._tc_stale = False
+        for k in range(3):
+            s.app_plane_bf16[k] = None
+        if self.mlp_mode == "bf16" and self.app_planes_bf16:
+            lib = L.load()
+            items, _ = self._layout()
+            n_tot = sum(items[f"ap{k}"][1] for k in range(3))
+            if getattr(self, "_app16", None) is None or self._app16.numel() != n_tot:
+                self._app16 = torch.empty(n_tot, dtype=torch.bfloat16, device=self.device)
+            off = 0
+            for k in range(3):
+                o, n_el = items[f"ap{k}"]
+                dst = self._app16.data_ptr() + 2 * off
+                L.check(lib.tvm_pack_bf16(C.c_void_p(self._packed.data_ptr() + 4 * o), n_el, C.c_void_p(dst), _stream_ptr()),
+                        "tvm_pack_bf16")
+                s.app_plane_bf16[k] = dst
+                off += n_el
         s.sampling, s.radii = L.SAMPLING_UNIFORM, 0.0
         self._finish_model(s)
         self._model_struct, self._model_mask_key = s, mask_key

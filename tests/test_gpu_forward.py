@@ -166,6 +166,38 @@ def test_tensor_core_mlp_bf16(env):
     assert np.abs(rgb.cpu().numpy() - ref["rgb_map"]).max() <= 1e-2
 
 
+def test_bf16_appearance_planes(env):
+    """app_planes_bf16 (TvmModel.app_plane_bf16): the tensor-core head gathers bf16 copies of the appearance planes.
+    Same north_star bound as the bf16 head (1e-2 on rgb, PSNR delta < 0.01 dB); masks, depth and the work counters do
+    not depend on it.  REFTensoRF uses the same gather."""
+    pkg, torch, fx, orc = env
+    from util import gpu_model, psnr
+    for regime, G, variant in (("R1", 128, None), ("R2", 128, None), ("R1", 300, None), ("R2", 64, "ref")):
+        kw = dict(variant=variant, mask_res=G) if variant else {}
+        case = fx.make_case(G, 2048, regime, **kw)
+        ref = orc.run_case(case, want_stages=False)
+        model = gpu_model(pkg, case, mlp_mode="bf16")
+        rays = torch.from_numpy(case["rays"]).cuda()
+        model.collect_counters = True
+        with torch.no_grad():
+            rgb_a, depth_a = model(rays)
+            cnt_a = model.counters.clone()
+            model.counters.zero_()
+            model.app_planes_bf16 = True
+            rgb_b, depth_b = model(rays)
+            cnt_b = model.counters.clone()
+        torch.cuda.synchronize()
+        assert model._model().app_plane_bf16[0]
+        assert torch.equal(depth_a, depth_b) and torch.equal(cnt_a, cnt_b)
+        a, b = rgb_a.cpu().numpy(), rgb_b.cpu().numpy()
+        err = np.abs(b - ref["rgb_map"]).max()
+        print(f"bf16 planes {regime} G={G} {variant or 'vm'}: max|rgb-oracle|={err:.3e} (fp32 planes: {np.abs(a - ref['rgb_map']).max():.3e}), "
+              f"max|bf16 planes - fp32 planes|={np.abs(a - b).max():.3e}")
+        assert err <= 1e-2
+        tgt = fx.target_rgb(2048)
+        assert abs(psnr(b, tgt) - psnr(ref["rgb_map"], tgt)) < 0.01
+
+
 @pytest.mark.parametrize("mode,tol", [("fp32", RGB_TOL), ("bf16", 1e-2)])
 def test_reftensorf_variant(env, mode, tol):
     """REFTensoRF (models/REFTensoRF.py): extra heads, reflected direction, tint*rgb_s + rgb_d, penalty."""
