@@ -40,6 +40,8 @@ struct Workspace {
   uint32_t* blk_base;    // [n][NB]   first entry index of the block
   uint2* ent;            // [cap]     (ray, sample index)
   float* ent_w;          // [cap]     weight
+  float4* ent_u;         // [cap]     un-normalised grid coordinates of the sample (x, y, z) and its weight: the appearance
+                         //           gather starts from one 16-byte load instead of re-deriving the ray march
   float* ent_rgb;        // [cap][3]  per-sample colour written by the appearance stage
   float* ent_pen;        // [cap]     TVM_VARIANT_REF: relu(-d.n)^2 of the sample (REFTensoRF.py:236-237)
   float* pen_sum;        // [n]       TVM_VARIANT_REF: sum_k w_k * pen_k of the ray
@@ -73,6 +75,7 @@ inline Workspace carve_workspace(void* base, int n, int S) {
   w.blk_base = (uint32_t*)take((size_t)n * w.NB * 4);
   w.ent = (uint2*)take((size_t)w.cap * 8);
   w.ent_w = (float*)take((size_t)w.cap * 4);
+  w.ent_u = (float4*)take((size_t)w.cap * 16);
   w.ent_rgb = (float*)take((size_t)w.cap * 12);
   w.ent_pen = (float*)take((size_t)w.cap * 4);
   w.pen_sum = (float*)take((size_t)n * 4);

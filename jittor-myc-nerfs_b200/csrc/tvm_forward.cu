@@ -184,6 +184,9 @@ __global__ void __launch_bounds__(kMarchWarps * 32, TVM_MARCH_MIN_CTAS) k_march(
         const uint32_t e = base + __popc(a_bits & lt_mask);
         P.ws.ent[e] = make_uint2((uint32_t)ray, (uint32_t)k);
         P.ws.ent_w[e] = w;
+        float u[3];
+        grid_coords(m, p, u);
+        P.ws.ent_u[e] = make_float4(u[0], u[1], u[2], w);
       }
       if (lane == 0) {
         P.ws.blk_mask[(size_t)ray * P.NB + b] = a_bits;

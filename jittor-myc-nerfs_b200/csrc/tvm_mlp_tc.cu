@@ -40,6 +40,23 @@ __global__ void k_pack_tc_f32(const TvmModel m, float* __restrict__ dst) {
   else if (i < 692) dst[i] = m.head_bias ? m.head_bias[i - 644] : 0.0f;
 }
 
+// forward-only extension of the image (see tc::Image): b1 into row in_c of W1, b2 as K-chunks 16/17 of W2, [W3^T; b3]
+__global__ void k_pack_tc_ext(const TvmModel m, int in_c, __nv_bfloat16* __restrict__ b1_img, __nv_bfloat16* __restrict__ b2x,
+                              __nv_bfloat16* __restrict__ b3) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 128) b1_img[((in_c >> 3) * 128 + i) * 8 + (in_c & 7)] = __float2bfloat16_rn(m.b1[i]);
+  if (i < 16 * 128) {                       // element (k = 128 + 8 kc + kk, n): [(kc)][n][kk]
+    const int kc = i / (128 * 8), n = (i / 8) % 128, kk = i % 8;
+    b2x[i] = __float2bfloat16_rn((kc == 0 && kk == 0) ? m.b2[n] : 0.0f);
+  }
+  if (i < 144 * 16) {                       // [(k / 8)][n < 16][k % 8]
+    const int kc = i / (16 * 8), n = (i / 8) % 16, k = kc * 8 + i % 8;
+    float v = 0.0f;
+    if (n < 3) v = k < 128 ? m.w3[n * 128 + k] : (k == 128 ? m.b3[n] : 0.0f);
+    b3[i] = __float2bfloat16_rn(v);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Warp-specialised persistent kernel: warps 0-3 ("MLP group", thread = tile row) issue the MMAs and run
 // the three epilogues; warps 4.. ("gather group") produce the GEMM0 operand of the NEXT tile into a
@@ -65,22 +82,19 @@ __global__ void __launch_bounds__(kThreadsV2, 1) k_app_tc(const FwdParams P) {
   constexpr int KA = K1 > 128 ? K1 : 128;
   static_assert(FEA_PE == 2 && VIEW_PE == 2, "the register-resident PE builder is written for 2 frequencies");
   static_assert(K0 % 16 == 0 && APP_DIM <= 32 && (!REF || APP_DIM + 8 <= NH), "unsupported shape");
+  static_assert(IN_C < K1 && KA >= 144, "the constant-one columns of GEMM1 / GEMM2 live in the K padding");
 
   extern __shared__ __align__(1024) uint8_t smem[];
   const Image img(CA, IN_C, NH);
   uint8_t* sW = smem;                                          // weight image (bf16 operands + fp32 tail)
-  uint8_t* sA0 = smem + ((img.bytes + 1023) & ~1023u);         // 2 stages of the GEMM0 operand [128 x K0] bf16
+  uint8_t* sA0 = smem + ((img.bytes_fwd + 1023) & ~1023u);     // 2 stages of the GEMM0 operand [128 x K0] bf16
   uint8_t* sA = sA0 + 2 * kRows * K0 * 2;                      // GEMM1/GEMM2 operand [128 x KA] bf16
   uint64_t* bars = reinterpret_cast<uint64_t*>(sA + kRows * KA * 2);   // full[2], empty[2], mma
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
   uint64_t* full = bars;
   uint64_t* empty = bars + 2;
   uint64_t* mma_bar = bars + 4;
-  const float* sB1 = reinterpret_cast<const float*>(sW + img.off_f32);
-  const float* sB2 = sB1 + 128;
-  const float* sW3 = sB2 + 128;
-  const float* sB3 = sW3 + 3 * 128;
-  const float* sHB = sB3 + 4;                                  // REF head biases [48]
+  const float* sHB = reinterpret_cast<const float*>(sW + img.off_f32) + 128 + 128 + 3 * 128 + 4;   // REF head biases [48]
 
   const TvmModel& m = P.m;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -89,7 +103,7 @@ __global__ void __launch_bounds__(kThreadsV2, 1) k_app_tc(const FwdParams P) {
   {
     const uint4* src = reinterpret_cast<const uint4*>(m.tc_weights);
     uint4* dst = reinterpret_cast<uint4*>(sW);
-    for (uint32_t i = tid; i < img.bytes / 16; i += kThreadsV2) dst[i] = __ldg(src + i);
+    for (uint32_t i = tid; i < img.bytes_fwd / 16; i += kThreadsV2) dst[i] = __ldg(src + i);
   }
   if (tid == 0) {
     mbar_init(&full[0], kGatherWarps);
@@ -107,7 +121,8 @@ __global__ void __launch_bounds__(kThreadsV2, 1) k_app_tc(const FwdParams P) {
   const uint32_t tmem = *tmem_slot;
 
   constexpr uint32_t LBO_A = kRows * 16, LBO_B0 = NH * 16, LBO_B = 128 * 16, SBO = 128;
-  constexpr uint32_t IDESC_N32 = instr_desc(128, NH), IDESC_N128 = instr_desc(128, 128);
+  constexpr uint32_t IDESC_N32 = instr_desc(128, NH), IDESC_N128 = instr_desc(128, 128), IDESC_N16 = instr_desc(128, 16);
+  constexpr uint32_t LBO_B3 = 16 * 16;
   constexpr uint32_t A0_STAGE = kRows * K0 * 2;
 
   const uint32_t n_ent = *P.ws.n_entries;
@@ -124,15 +139,14 @@ __global__ void __launch_bounds__(kThreadsV2, 1) k_app_tc(const FwdParams P) {
       mbar_wait(&empty[s], (use & 1u) ^ 1u);          // stage free (first use of a stage passes at once)
       const uint32_t tile_base = tile * kRows;
       uint8_t* stage = sA0 + s * A0_STAGE;
-#pragma unroll 1
+#pragma unroll
       for (int pass = 0; pass < ROWS_PER_WARP / 8; ++pass) {
         const int row = gw * ROWS_PER_WARP + pass * 8 + (lane >> 2), q = lane & 3;
         const uint32_t e = tile_base + row;
         uint8_t* arow = stage + row * 16;
         if (e < n_ent) {
-          const uint2 en = P.ws.ent[e];
-          float u[3], dir[3];
-          entry_coords(m, P.rays, P.jitter, en.x, en.y, P.S, u, dir);
+          const float4 uw = __ldg(P.ws.ent_u + e);       // written by k_march with the coordinates it marched
+          const float u[3] = {uw.x, uw.y, uw.z};
           if (PB16) {
             AxisPair ax[3];
 #pragma unroll
@@ -200,6 +214,7 @@ __global__ void __launch_bounds__(kThreadsV2, 1) k_app_tc(const FwdParams P) {
     const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
     const uint32_t aA = smem_u32(sA);
     const uint32_t aB0 = smem_u32(sW + img.off_b0), aB1 = smem_u32(sW + img.off_b1), aB2 = smem_u32(sW + img.off_b2);
+    const uint32_t aB2x = smem_u32(sW + img.off_b2x), aB3 = smem_u32(sW + img.off_b3);
     uint8_t* arow = sA + row * 16;
     uint32_t it = 0, mma_phase = 0;
     float pen_acc = 0.0f;
@@ -271,6 +286,7 @@ __global__ void __launch_bounds__(kThreadsV2, 1) k_app_tc(const FwdParams P) {
           if (c < PV) { const int o = (c - PF - NF) >> 1; return ((c - PF - NF) & 1) ? 1.0f - 2.0f * s1[o] * s1[o] : c1[o]; }
           if (c < PV + NV) { const int o = APP_DIM + ((c - PV) >> 1); return ((c - PV) & 1) ? 2.0f * s1[o] * c1[o] : s1[o]; }
           if (c < PV + 2 * NV) { const int o = APP_DIM + ((c - PV - NV) >> 1); return ((c - PV - NV) & 1) ? 1.0f - 2.0f * s1[o] * s1[o] : c1[o]; }
+          if (cc == IN_C) return 1.0f;                 // constant-one column: row IN_C of the W1 operand is b1
           return 0.0f;
         };
 #pragma unroll
@@ -298,19 +314,49 @@ __global__ void __launch_bounds__(kThreadsV2, 1) k_app_tc(const FwdParams P) {
       mbar_wait(mma_bar, mma_phase);
       mma_phase ^= 1;
       fence_after();
-      // ---- epi1: +b1, ReLU -> A2 (bf16) ----------------------------------------------------------------
+      // ---- epi1: ReLU -> A2 (bf16); b1 came with the GEMM ----------------------------------------------
 #pragma unroll
       for (int cb = 0; cb < 4; ++cb) {
         float y[32];
         tmem_ld32(lane_addr + cb * 32, y);
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 b = *reinterpret_cast<const float4*>(sB1 + cb * 32 + j);
-          y[j] = fmaxf(y[j] + b.x, 0.0f);
-          y[j + 1] = fmaxf(y[j + 1] + b.y, 0.0f);
-          y[j + 2] = fmaxf(y[j + 2] + b.z, 0.0f);
-          y[j + 3] = fmaxf(y[j + 3] + b.w, 0.0f);
+        for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], 0.0f);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 v;
+          v.x = pack_bf16(y[g * 8 + 0], y[g * 8 + 1]);
+          v.y = pack_bf16(y[g * 8 + 2], y[g * 8 + 3]);
+          v.z = pack_bf16(y[g * 8 + 4], y[g * 8 + 5]);
+          v.w = pack_bf16(y[g * 8 + 6], y[g * 8 + 7]);
+          *reinterpret_cast<uint4*>(arow + (cb * 4 + g) * LBO_A) = v;
         }
+      }
+      // columns 128..143: a constant one (row 128 of the W2 / W3 operands is b2 / b3), then zeros
+      *reinterpret_cast<uint4*>(arow + 16 * LBO_A) = make_uint4(0x00003f80u, 0u, 0u, 0u);
+      *reinterpret_cast<uint4*>(arow + 17 * LBO_A) = make_uint4(0u, 0u, 0u, 0u);
+      fence_async_smem();
+      fence_before();
+      mlp_group_sync();
+      // ---- GEMM2: [A2 | 1] . [W2^T; b2] -----------------------------------------------------------------
+      if (tid == 0) {
+        fence_after();
+#pragma unroll
+        for (int k = 0; k < 128 / 16; ++k)
+          umma_bf16(tmem, smem_desc(aA + k * 2 * LBO_A, LBO_A, SBO), smem_desc(aB2 + k * 2 * LBO_B, LBO_B, SBO),
+                    IDESC_N128, k > 0);
+        umma_bf16(tmem, smem_desc(aA + 16 * LBO_A, LBO_A, SBO), smem_desc(aB2x, LBO_B, SBO), IDESC_N128, true);
+        umma_commit(mma_bar);
+      }
+      mbar_wait(mma_bar, mma_phase);
+      mma_phase ^= 1;
+      fence_after();
+      // ---- epi2: ReLU -> A3 (bf16, the constant-one column of A2 stays) ---------------------------------------
+#pragma unroll
+      for (int cb = 0; cb < 4; ++cb) {
+        float y[32];
+        tmem_ld32(lane_addr + cb * 32, y);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], 0.0f);
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           uint4 v;
@@ -324,36 +370,23 @@ __global__ void __launch_bounds__(kThreadsV2, 1) k_app_tc(const FwdParams P) {
       fence_async_smem();
       fence_before();
       mlp_group_sync();
-      // ---- GEMM2: A2 . W2^T -------------------------------------------------------------------------
+      // ---- GEMM3: [A3 | 1] . [W3^T; b3] (N = 16, 3 real columns) ----------------------------------------------
       if (tid == 0) {
         fence_after();
 #pragma unroll
-        for (int k = 0; k < 128 / 16; ++k)
-          umma_bf16(tmem, smem_desc(aA + k * 2 * LBO_A, LBO_A, SBO), smem_desc(aB2 + k * 2 * LBO_B, LBO_B, SBO),
-                    IDESC_N128, k > 0);
+        for (int k = 0; k < 144 / 16; ++k)
+          umma_bf16(tmem + kColOut, smem_desc(aA + k * 2 * LBO_A, LBO_A, SBO), smem_desc(aB3 + k * 2 * LBO_B3, LBO_B3, SBO),
+                    IDESC_N16, k > 0);
         umma_commit(mma_bar);
       }
       mbar_wait(mma_bar, mma_phase);
       mma_phase ^= 1;
       fence_after();
-      // ---- epi2: +b2, ReLU, 128 -> 3 on CUDA cores, sigmoid ----------------------------------------------
-      float o0 = sB3[0], o1 = sB3[1], o2 = sB3[2];
-#pragma unroll
-      for (int cb = 0; cb < 4; ++cb) {
-        float y[32];
-        tmem_ld32(lane_addr + cb * 32, y);
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 b = *reinterpret_cast<const float4*>(sB2 + cb * 32 + j);
-          const float4 w0 = *reinterpret_cast<const float4*>(sW3 + cb * 32 + j);
-          const float4 w1 = *reinterpret_cast<const float4*>(sW3 + 128 + cb * 32 + j);
-          const float4 w2 = *reinterpret_cast<const float4*>(sW3 + 256 + cb * 32 + j);
-          const float h0 = fmaxf(y[j] + b.x, 0.0f), h1 = fmaxf(y[j + 1] + b.y, 0.0f);
-          const float h2 = fmaxf(y[j + 2] + b.z, 0.0f), h3 = fmaxf(y[j + 3] + b.w, 0.0f);
-          o0 = fmaf(h0, w0.x, fmaf(h1, w0.y, fmaf(h2, w0.z, fmaf(h3, w0.w, o0))));
-          o1 = fmaf(h0, w1.x, fmaf(h1, w1.y, fmaf(h2, w1.z, fmaf(h3, w1.w, o1))));
-          o2 = fmaf(h0, w2.x, fmaf(h1, w2.y, fmaf(h2, w2.z, fmaf(h3, w2.w, o2))));
-        }
+      float o0, o1, o2;
+      {
+        float o[16];
+        tmem_ld16(lane_addr + kColOut, o);
+        o0 = o[0]; o1 = o[1]; o2 = o[2];
       }
       if (e < n_ent) {
         // REF: rgb = tint * clamp(rgb_s, 0) + rgb_d (REFTensoRF.py:232); VM: tint = 1, rgb_d = 0
@@ -388,7 +421,7 @@ int launch_app_tc(const FwdParams& P, int num_sms, cudaStream_t stream) {
   const bool ref = P.m.variant == TVM_VARIANT_REF;
   const Image img(P.m.n_app, P.in_mlp_c, head_ld(P.m));
   const int KA = max(img.K1, 128);
-  const size_t smem = ((img.bytes + 1023) & ~1023u) + 2 * (size_t)kRows * img.K0 * 2 + (size_t)kRows * KA * 2 + 128 + 1024;
+  const size_t smem = ((img.bytes_fwd + 1023) & ~1023u) + 2 * (size_t)kRows * img.K0 * 2 + (size_t)kRows * KA * 2 + 128 + 1024;
   const bool pb16 = P.m.app_plane_bf16[0] && P.m.app_plane_bf16[1] && P.m.app_plane_bf16[2];
   auto kern = ref ? (pb16 ? k_app_tc<48, 27, 2, 2, true, true> : k_app_tc<48, 27, 2, 2, true, false>)
                   : (pb16 ? k_app_tc<48, 27, 2, 2, false, true> : k_app_tc<48, 27, 2, 2, false, false>);
@@ -403,9 +436,9 @@ int launch_app_tc(const FwdParams& P, int num_sms, cudaStream_t stream) {
 using namespace tvm;
 
 extern "C" size_t tvm_tc_weights_bytes(const TvmModel* m_host) {
-  if (m_host == nullptr) return Image(48, 150, 32).bytes;   // probe: "is the tensor-core path built?"
+  if (m_host == nullptr) return Image(48, 150, 32).bytes_fwd;   // probe: "is the tensor-core path built?"
   if (!tc_supported(*m_host)) return 0;
-  return Image(m_host->n_app, in_mlp_c(*m_host), head_ld(*m_host)).bytes;
+  return Image(m_host->n_app, in_mlp_c(*m_host), head_ld(*m_host)).bytes_fwd;
 }
 
 extern "C" int tvm_pack_mlp_tc(const TvmModel* m_host, void* out, void* stream_) {
@@ -425,6 +458,8 @@ extern "C" int tvm_pack_mlp_tc(const TvmModel* m_host, void* out, void* stream_)
   launch(m_host->w1_t, in_c, img.K1, 128, 128, kFeatureC, img.off_b1);
   launch(m_host->w2_t, 128, 128, 128, 128, kFeatureC, img.off_b2);
   k_pack_tc_f32<<<3, 256, 0, s>>>(*m_host, (float*)(o + img.off_f32));
+  k_pack_tc_ext<<<(144 * 16 + 255) / 256, 256, 0, s>>>(*m_host, in_c, (__nv_bfloat16*)(o + img.off_b1),
+                                                    (__nv_bfloat16*)(o + img.off_b2x), (__nv_bfloat16*)(o + img.off_b3));
   TVM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

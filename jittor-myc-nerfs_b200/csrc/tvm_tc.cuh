@@ -115,6 +115,11 @@ struct Image {
   int K0, K1, NH;                // padded reduction lengths of GEMM0 / GEMM1 (multiples of 16); GEMM0 width
   uint32_t off_b0, off_b1, off_b2, off_f32, bytes;
   // fp32 tail: b1[128] b2[128] w3[3][128] b3[4] head_bias[48]
+  // Forward-only extension behind `bytes` (the backward kernel copies [0, bytes) only):
+  //   off_b2x  K-chunks 16, 17 of the W2 operand: row 128 = b2 (the forward feeds a constant-one column there)
+  //   off_b3   W3 operand [144][16]: rows 0..127 = mlp.4.weight^T (3 real columns), row 128 = b3
+  // and row in_c of the W1 operand (inside its K padding) holds b1: the biases and the 128 -> 3 layer ride in the GEMMs.
+  uint32_t off_b2x, off_b3, bytes_fwd;
   __host__ __device__ Image(int n_app, int in_c, int nh) {
     K0 = 3 * n_app;
     K1 = (in_c + 15) / 16 * 16;
@@ -124,8 +129,12 @@ struct Image {
     off_b2 = off_b1 + (uint32_t)K1 * 128 * 2;
     off_f32 = off_b2 + 128u * 128 * 2;
     bytes = off_f32 + (128 + 128 + 3 * 128 + 4 + 48) * 4;
+    off_b2x = (bytes + 15u) & ~15u;
+    off_b3 = off_b2x + 16u * 128 * 2;
+    bytes_fwd = off_b3 + 144u * 16 * 2;
   }
 };
+constexpr int kColOut = 192;        // TMEM columns [192, 208): accumulator of the 128 -> 3 layer (forward kernel)
 
 // fp32 [K][ldw] (row j = input j) -> bf16 UMMA image [(K_pad/8)][N][8]; out-of-range entries are 0.
 // Image column k reads source row k for k < split, nothing for split <= k < split_pad, and row
