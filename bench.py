@@ -421,6 +421,9 @@ def run_side_workload(args):
 
 def main():
     args = parse()
+    # stdout carries the ONE JSON line: NCCL's own banner ("NCCL version ...", printed when the box exports
+    # NCCL_DEBUG=VERSION) goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if os.environ.get("BENCH_WATCHDOG"):
         # debugging aid: dump every thread's stack and exit if the run is still alive after N seconds
         import faulthandler
