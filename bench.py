@@ -6,7 +6,7 @@ configs[1]: 300^3 grid, 200^3 alpha mask, S = nSamples = 1036, white background,
 random-init grids (oracle/fixtures.py, seed 20211202).  With N GPUs every rank renders its own frame
 of the 8-azimuth orbit (configs[4], weak scaling, no data-path collective).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--regime R1|R2] [--mlp fp32|bf16|bf16x3]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--regime R1|R2] [--mlp fp32|bf16|fp16]
   python bench.py --impl reference ...     # the CPU restatement of the reference on the host cores
 
 Prints ONE JSON line (rank 0).
@@ -41,8 +41,10 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--regime", default="R1", choices=["R0", "R1", "R2"])
-    ap.add_argument("--mlp", default=os.environ.get("TVM_MLP_MODE", "bf16"), choices=["fp32", "bf16", "bf16x3"],
-                    help="appearance head: bf16 tcgen05 (rgb tolerance 1e-2, default) or fp32 FMA (1e-4)")
+    ap.add_argument("--mlp", default=os.environ.get("TVM_MLP_MODE"), choices=["fp32", "bf16", "fp16"],
+                    help="appearance head: fp16 tcgen05 (fp16 operands, fp32 accumulation: measured 2e-5 from the oracle, checked "
+                         "against the fp32 tolerance 1e-4; default of the frame workloads), bf16 tcgen05 (tolerance 1e-2; "
+                         "forward AND backward on the tensor cores: default of --workload train) or fp32 FMA (1e-4)")
     ap.add_argument("--grid", type=int, default=GRID)
     ap.add_argument("--rays", type=int, default=FRAME * FRAME, help="rays per step (default: the full frame)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -57,7 +59,10 @@ def parse():
                     help="frame = BASELINE configs[1] (the contract line); train = configs[2] (4096-ray fwd+bwd step, "
                          "128^3 grid); npp / ref = configs[3] (NeRF++ background / Ref-NeRF appearance, full frame). "
                          "The non-default workloads print the same JSON shape for profiles/, not for the driver.")
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.mlp is None:
+        args.mlp = "bf16" if args.workload == "train" else "fp16"
+    return args
 
 
 def peaks():
@@ -370,7 +375,7 @@ def run_side_workload(args):
     line = {"metric": f"TensoRF-VM rays/sec ({args.workload})", "value": n * world / (ms / args.steps * 1e-3), "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if args.mlp == "fp32" else f"f32 + {args.mlp} tensor-core MLP (forward and backward)", "data": "synthetic",
+            "dtype": "f32" if args.mlp == "fp32" else (f"f32 + {args.mlp} tensor-core MLP" + (" (forward and backward)" if train and args.mlp == "bf16" else "")), "data": "synthetic",
             "config": {"workload": name + f", regime {args.regime}", "n_samples": S,
                        "l2": "flushed before every timed step (256 MiB write)",
                        "per_step_counts": {"M_in": cnt[L.CNT_M_IN], "M_v_gathered": cnt[L.CNT_M_V], "M_a": cnt[L.CNT_M_A],
@@ -450,7 +455,7 @@ def main():
 
     case = make_case(args, rank)
     model = pkg.model_from_params(case["model"], f"cuda:{local_rank}", case["alpha_volume"], case["alpha_aabb"], args.mlp)
-    model.app_planes_bf16 = args.app_planes == "bf16" and args.mlp == "bf16"
+    model.app_planes_bf16 = args.app_planes == "bf16" and args.mlp in ("bf16", "fp16")      # 16-bit copies in the mode's format
     n = case["rays"].shape[0]
     S = model.nSamples
     rays_host = torch.from_numpy(case["rays"]).pin_memory()
@@ -582,11 +587,11 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if args.mlp == "fp32" else f"f32 gather/composite + {args.mlp} tensor-core MLP" +
-                     (" fed from bf16 appearance planes" if model.app_planes_bf16 else ""),
+            "dtype": "f32" if args.mlp == "fp32" else f"f32 gather/composite + {args.mlp} tensor-core MLP (fp32 accumulate)" +
+                     (f" fed from {args.mlp} appearance planes" if model.app_planes_bf16 else ""),
             "data": "synthetic",
             "config": {"workload": workload_name(args), "n_samples": S, "rays_per_step_per_gpu": n,
-                       "mlp": args.mlp, "app_planes": "bf16" if model.app_planes_bf16 else "fp32", "early_ray_termination": True, "l2": "flushed before every timed step "
+                       "mlp": args.mlp, "app_planes": args.mlp if model.app_planes_bf16 else "fp32", "early_ray_termination": True, "l2": "flushed before every timed step "
                        "(256 MiB write)", "parallelism": f"one frame per rank x {world}",
                        "samples_per_s_marched": value * S, "samples_per_s_gathered": M_v * world / (ms_total / args.steps * 1e-3),
                        "per_step_counts": {"M_in": M_in, "M_v_gathered": M_v, "M_a": M_a}},
@@ -595,7 +600,8 @@ def main():
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(sum(stage_cnt.values())),
             "clocks": clocks, "roofline": roof, "max_abs_err_vs_oracle_512rays": check,
-            "rgb_tolerance": 1e-4 if args.mlp != "bf16" else 1e-2}
+            "rgb_tolerance": 1e-4 if args.mlp != "bf16" else 1e-2,
+            "rgb_tolerance_note": "north_star: 1e-4 abs in fp32, 1e-2 when the MLP runs in bf16; the fp16 head is held to the fp32 bound"}
     if rank == 0 and check is not None and check > line["rgb_tolerance"]:
         raise SystemExit(f"bench: rendered colours differ from the oracle by {check} > {line['rgb_tolerance']}")
 

@@ -33,14 +33,15 @@
 extern "C" {
 #endif
 
-#define TVM_ABI_VERSION 14
+#define TVM_ABI_VERSION 15
 
 /* flags for tvm_forward / tvm_backward */
 #define TVM_WHITE_BG      0x1u  /* rgb_map += 1 - acc_map          (tensorBase.py:523-524) */
 #define TVM_NO_ERT        0x2u  /* disable early ray termination (march every in-box sample) */
 #define TVM_MLP_FP32      0x0u  /* appearance head in fp32 FMA (parity 1e-4)                */
 #define TVM_MLP_BF16      0x10u /* appearance head on tcgen05 tensor cores, bf16 x bf16 -> fp32 (parity 1e-2) */
-#define TVM_MLP_BF16X3    0x20u /* tcgen05, 3-term split-bf16 (near-fp32; parity 1e-4)       */
+#define TVM_MLP_FP16      0x20u /* tcgen05, fp16 x fp16 -> fp32: 11-bit operands, forward only (the backward of this mode is
+                                  the fp32 one); measured 2e-5 from the oracle, i.e. inside the fp32 tolerance 1e-4       */
 #define TVM_MLP_MASK      0x30u
 
 /* model variant */
@@ -109,9 +110,10 @@ typedef struct TvmModel {
   const void* tc_weights;
   int32_t sampling;         /* TVM_SAMPLING_*                                                            */
   float radii;              /* TVM_SAMPLING_NPP: radius of the bounding sphere (configs/Scarf.txt:14)    */
-  /* optional bf16 copies of app_plane[k] written by tvm_pack_bf16 (all NULL = none).  When present the TVM_MLP_BF16
-   * appearance head gathers its plane texels from them (half the gather bytes; the plane x line products are rounded
-   * to bf16 as the GEMM operand in that mode anyway).  TVM_MLP_FP32 and every backward kernel ignore them.        */
+  /* optional 16-bit copies of app_plane[k] written by tvm_pack_half in the format of the mode they are used with (bf16
+   * for TVM_MLP_BF16, fp16 for TVM_MLP_FP16; all NULL = none).  When present the tensor-core appearance head gathers its
+   * plane texels from them (half the gather bytes; the plane x line products are rounded to that format as the GEMM
+   * operand anyway).  TVM_MLP_FP32 and every backward kernel ignore them.                                          */
   const void* app_plane_bf16[3];
 } TvmModel;
 
@@ -192,8 +194,9 @@ int tvm_unpack_grid(const float* hwc, int C, int H, int W, float* out_nchw, void
 /* Linear weight [out][in] -> [in][out_pad] (zero padded columns)                              */
 int tvm_pack_linear(const float* w_out_in, int out_c, int in_c, int out_pad, float* out_t, void* stream);
 int tvm_unpack_linear(const float* w_t, int out_c, int in_c, int out_pad, float* out_w, void* stream);
-/* fp32 -> bf16 (round to nearest even) copy of n values: the bf16 appearance planes of TvmModel.app_plane_bf16 */
-int tvm_pack_bf16(const float* src, size_t n, void* dst_bf16, void* stream);
+/* fp32 -> bf16 (flags = TVM_MLP_BF16) or fp16 (TVM_MLP_FP16) copy of n values, round to nearest even: the 16-bit
+ * appearance planes of TvmModel.app_plane_bf16                                                                     */
+int tvm_pack_half(const float* src, size_t n, void* dst, uint32_t flags, void* stream);
 /* {0,1} fp32 volume [D][H][W] -> bit stream (bit set iff value > 0); n_words = ceil(D*H*W/32)  */
 int tvm_pack_alpha(const float* volume, int D, int H, int W, uint32_t* bits, void* stream);
 /* brick index of a packed alpha volume; n_words = ceil(ceil(D/8)*ceil(H/8)*ceil(W/8) / 32)        */
@@ -202,8 +205,9 @@ int tvm_pack_alpha_bricks(const uint32_t* bits, int D, int H, int W, uint32_t* b
 int tvm_pack_alpha_dilated(const uint32_t* bits, int D, int H, int W, uint32_t* dilated, void* stream);
 /* bytes of the tensor-core operand image for (in_mlp_c, feature_c, app_dim, n_app)            */
 size_t tvm_tc_weights_bytes(const TvmModel* m_host);
-/* builds the bf16 (hi, mid) K-major UMMA operand images of basis/W1/W2 from the packed fp32 weights */
-int tvm_pack_mlp_tc(const TvmModel* m_host, void* tc_weights_out, void* stream);
+/* builds the K-major UMMA operand images of basis/W1/W2/W3 (bf16 or fp16 per `flags`) from the packed fp32 weights; the
+ * backward kernel (TVM_MLP_BF16 only) reads the same buffer */
+int tvm_pack_mlp_tc(const TvmModel* m_host, void* tc_weights_out, uint32_t flags /* TVM_MLP_BF16 | TVM_MLP_FP16 */, void* stream);
 
 /* NeRF++ background network on the tensor cores: bytes of / builder for TvmBgNet.tc_weights (16-byte aligned) */
 size_t tvm_bg_tc_bytes(void);

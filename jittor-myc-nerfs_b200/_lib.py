@@ -11,14 +11,14 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # TVM_LIB: developer override (kernel-tuning experiments build variant libraries next to the default one)
 LIB_PATH = os.environ.get("TVM_LIB") or os.path.join(_HERE, "libtvmrender.so")
-ABI_VERSION = 14
+ABI_VERSION = 15
 
 # flags (tvmrender.h)
 WHITE_BG = 0x1
 NO_ERT = 0x2
 MLP_FP32 = 0x0
 MLP_BF16 = 0x10
-MLP_BF16X3 = 0x20
+MLP_FP16 = 0x20
 ACT_SOFTPLUS, ACT_RELU = 0, 1
 VARIANT_VM, VARIANT_REF, REF_HEAD_LD = 0, 1, 48
 CNT_M_IN, CNT_M_V, CNT_M_A, CNT_RAYS, CNT_WORDS = 0, 1, 2, 3, 8
@@ -82,7 +82,7 @@ class TvmGrads(C.Structure):
 
 EXPORTS = [
     "tvm_last_error", "tvm_abi_version", "tvm_device_count", "tvm_pack_grid", "tvm_unpack_grid",
-    "tvm_pack_linear", "tvm_unpack_linear", "tvm_pack_bf16", "tvm_pack_alpha", "tvm_pack_alpha_bricks", "tvm_pack_alpha_dilated", "tvm_tc_weights_bytes", "tvm_pack_mlp_tc",
+    "tvm_pack_linear", "tvm_unpack_linear", "tvm_pack_half", "tvm_pack_alpha", "tvm_pack_alpha_bricks", "tvm_pack_alpha_dilated", "tvm_tc_weights_bytes", "tvm_pack_mlp_tc",
     "tvm_workspace_bytes", "tvm_forward", "tvm_forward_npp", "tvm_bg_fold", "tvm_bg_tc_bytes", "tvm_pack_bg_tc", "tvm_backward", "tvm_backward_npp", "tvm_bg_fold_bwd",
     "tvm_density_alpha", "tvm_mse_loss",
     "tvm_profile_enable", "tvm_profile_collect",
@@ -120,14 +120,14 @@ def load() -> C.CDLL:
     lib.tvm_pack_linear.argtypes = [vp, i32, i32, i32, vp, vp]
     lib.tvm_unpack_linear.argtypes = [vp, i32, i32, i32, vp, vp]
     lib.tvm_pack_alpha.argtypes = [vp, i32, i32, i32, vp, vp]
-    lib.tvm_pack_bf16.argtypes = [vp, C.c_size_t, vp, vp]
+    lib.tvm_pack_half.argtypes = [vp, C.c_size_t, vp, u32, vp]
     lib.tvm_pack_alpha_bricks.argtypes = [vp, i32, i32, i32, vp, vp]
     lib.tvm_pack_alpha_dilated.argtypes = [vp, i32, i32, i32, vp, vp]
     lib.tvm_tc_weights_bytes.restype = C.c_size_t
     lib.tvm_tc_weights_bytes.argtypes = [C.POINTER(TvmModel)]
     lib.tvm_bg_tc_bytes.restype = C.c_size_t
     lib.tvm_bg_tc_bytes.argtypes = []
-    lib.tvm_pack_mlp_tc.argtypes = [C.POINTER(TvmModel), vp, vp]
+    lib.tvm_pack_mlp_tc.argtypes = [C.POINTER(TvmModel), vp, u32, vp]
     lib.tvm_workspace_bytes.argtypes = [i32, i32, C.POINTER(C.c_size_t)]
     lib.tvm_forward.argtypes = [C.POINTER(TvmModel), vp, i32, i32, vp, u32, vp, vp, C.POINTER(TvmAux), vp, vp,
                                 C.c_size_t, vp]

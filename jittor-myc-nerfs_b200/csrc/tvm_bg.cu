@@ -227,7 +227,7 @@ int launch_bg(const FwdParams& P, int num_sms, cudaStream_t stream) {
               b.wv_t && b.w_rgb && b.b_rgb, "null TvmBgNet pointer");
   TVM_REQUIRE(P.m.radii > 0.0f, "radii must be positive");
   if (P.aux.bg_rgb_map) TVM_CHECK_CUDA(cudaMemsetAsync(P.aux.bg_rgb_map, 0, (size_t)P.n * 12, stream));
-  if ((P.flags & TVM_MLP_MASK) == TVM_MLP_BF16) return launch_bg_tc(P, num_sms, stream);
+  if ((P.flags & TVM_MLP_MASK) != TVM_MLP_FP32) return launch_bg_tc(P, num_sms, stream);   // bf16 operands in both tensor-core modes
   const size_t smem = ((size_t)kAppTile * 2 * P.st + kAppTile * 4 + kAppTile + kBgHid + 4) * sizeof(float);
   TVM_CHECK_CUDA(cudaFuncSetAttribute(k_bg_simt<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_bg_simt<false><<<num_sms * 2, kAppThreads, smem, stream>>>(P);

@@ -10,7 +10,7 @@
 //   k_composite  one warp per ray, lane = sample of a block: rgb_map = clamp(sum w*rgb + (1-acc)) (:521-528).
 //
 // The tcgen05 tensor-core appearance head lives in tvm_mlp_tc.cu and replaces k_app_simt when
-// TVM_MLP_BF16 / TVM_MLP_BF16X3 is requested.
+// TVM_MLP_BF16 / TVM_MLP_FP16 is requested.
 #include "tvm_app_simt.cuh"
 
 namespace tvm {

@@ -20,7 +20,7 @@ using namespace tc;
 
 namespace tc {
 __global__ void k_pack_umma_b(const float* __restrict__ w_t, int K, int K_pad, int N_real, int N, int ldw,
-                              __nv_bfloat16* __restrict__ img, int split, int split_pad) {
+                              __nv_bfloat16* __restrict__ img, int split, int split_pad, int h16) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= K_pad * N) return;
   const int kc = i / (N * 8), rem = i % (N * 8), n = rem / 8, kk = rem % 8;
@@ -28,7 +28,7 @@ __global__ void k_pack_umma_b(const float* __restrict__ w_t, int K, int K_pad, i
   int src = k;
   if (k >= split) src = k < split_pad ? -1 : split + (k - split_pad);
   const float v = (src >= 0 && src < K && n < N_real) ? w_t[(size_t)src * ldw + n] : 0.0f;
-  img[i] = __float2bfloat16_rn(v);
+  reinterpret_cast<uint16_t*>(img)[i] = to16(v, h16 != 0);
 }
 }  // namespace tc
 __global__ void k_pack_tc_f32(const TvmModel m, float* __restrict__ dst) {
@@ -41,19 +41,19 @@ __global__ void k_pack_tc_f32(const TvmModel m, float* __restrict__ dst) {
 }
 
 // forward-only extension of the image (see tc::Image): b1 into row in_c of W1, b2 as K-chunks 16/17 of W2, [W3^T; b3]
-__global__ void k_pack_tc_ext(const TvmModel m, int in_c, __nv_bfloat16* __restrict__ b1_img, __nv_bfloat16* __restrict__ b2x,
-                              __nv_bfloat16* __restrict__ b3) {
+__global__ void k_pack_tc_ext(const TvmModel m, int in_c, uint16_t* __restrict__ b1_img, uint16_t* __restrict__ b2x,
+                              uint16_t* __restrict__ b3, int h16) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < 128) b1_img[((in_c >> 3) * 128 + i) * 8 + (in_c & 7)] = __float2bfloat16_rn(m.b1[i]);
+  if (i < 128) b1_img[((in_c >> 3) * 128 + i) * 8 + (in_c & 7)] = to16(m.b1[i], h16 != 0);
   if (i < 16 * 128) {                       // element (k = 128 + 8 kc + kk, n): [(kc)][n][kk]
     const int kc = i / (128 * 8), n = (i / 8) % 128, kk = i % 8;
-    b2x[i] = __float2bfloat16_rn((kc == 0 && kk == 0) ? m.b2[n] : 0.0f);
+    b2x[i] = to16((kc == 0 && kk == 0) ? m.b2[n] : 0.0f, h16 != 0);
   }
   if (i < 144 * 16) {                       // [(k / 8)][n < 16][k % 8]
     const int kc = i / (16 * 8), n = (i / 8) % 16, k = kc * 8 + i % 8;
     float v = 0.0f;
     if (n < 3) v = k < 128 ? m.w3[n * 128 + k] : (k == 128 ? m.b3[n] : 0.0f);
-    b3[i] = __float2bfloat16_rn(v);
+    b3[i] = to16(v, h16 != 0);
   }
 }
 
@@ -72,7 +72,8 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mlp_group_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 // PB16: plane texels come from the bf16 copies (TvmModel.app_plane_bf16): 8-byte loads, adjacent-pair addressing
-template <int CA, int APP_DIM, int FEA_PE, int VIEW_PE, bool REF, bool PB16>
+// H16:  operands (weight image, activations, plane copies) are fp16 instead of bf16 (TVM_MLP_FP16)
+template <int CA, int APP_DIM, int FEA_PE, int VIEW_PE, bool REF, bool PB16, bool H16>
 __global__ void __launch_bounds__(kThreadsV2, 1) k_app_tc(const FwdParams P) {
   constexpr int NH = REF ? TVM_REF_HEAD_LD : 32;
   constexpr int C0 = REF ? 1 : 0;                       // REF: column 0 of the MLP input is -dot (REFTensoRF.py:20)
@@ -121,7 +122,7 @@ __global__ void __launch_bounds__(kThreadsV2, 1) k_app_tc(const FwdParams P) {
   const uint32_t tmem = *tmem_slot;
 
   constexpr uint32_t LBO_A = kRows * 16, LBO_B0 = NH * 16, LBO_B = 128 * 16, SBO = 128;
-  constexpr uint32_t IDESC_N32 = instr_desc(128, NH), IDESC_N128 = instr_desc(128, 128), IDESC_N16 = instr_desc(128, 16);
+  constexpr uint32_t IDESC_N32 = instr_desc(128, NH, H16), IDESC_N128 = instr_desc(128, 128, H16), IDESC_N16 = instr_desc(128, 16, H16);
   constexpr uint32_t LBO_B3 = 16 * 16;
   constexpr uint32_t A0_STAGE = kRows * K0 * 2;
 
@@ -163,16 +164,16 @@ __global__ void __launch_bounds__(kThreadsV2, 1) k_app_tc(const FwdParams P) {
                 const uint2 cc = __ldg(reinterpret_cast<const uint2*>(pl + t.row1 + c));
                 const uint2 d = __ldg(reinterpret_cast<const uint2*>(pl + t.row1 + c + CA));
                 const float4 l0 = ldg4(ln + c), l1 = ldg4(ln + c + CA);
-                auto lo = [](uint32_t v) { return __uint_as_float(v << 16); };
-                auto hi = [](uint32_t v) { return __uint_as_float(v & 0xffff0000u); };
-                const float px = lo(a.x) * t.nw + lo(b.x) * t.ne + lo(cc.x) * t.sw + lo(d.x) * t.se;
-                const float py = hi(a.x) * t.nw + hi(b.x) * t.ne + hi(cc.x) * t.sw + hi(d.x) * t.se;
-                const float pz = lo(a.y) * t.nw + lo(b.y) * t.ne + lo(cc.y) * t.sw + lo(d.y) * t.se;
-                const float pw = hi(a.y) * t.nw + hi(b.y) * t.ne + hi(cc.y) * t.sw + hi(d.y) * t.se;
+                const float2 a0 = unpack16<H16>(a.x), a1 = unpack16<H16>(a.y), b0 = unpack16<H16>(b.x), b1 = unpack16<H16>(b.y);
+                const float2 c0 = unpack16<H16>(cc.x), c1 = unpack16<H16>(cc.y), d0 = unpack16<H16>(d.x), d1 = unpack16<H16>(d.y);
+                const float px = a0.x * t.nw + b0.x * t.ne + c0.x * t.sw + d0.x * t.se;
+                const float py = a0.y * t.nw + b0.y * t.ne + c0.y * t.sw + d0.y * t.se;
+                const float pz = a1.x * t.nw + b1.x * t.ne + c1.x * t.sw + d1.x * t.se;
+                const float pw = a1.y * t.nw + b1.y * t.ne + c1.y * t.sw + d1.y * t.se;
                 const float lx = l0.x * t.lw0 + l1.x * t.lw1, ly = l0.y * t.lw0 + l1.y * t.lw1;
                 const float lz = l0.z * t.lw0 + l1.z * t.lw1, lw = l0.w * t.lw0 + l1.w * t.lw1;
                 const int k = kk * CA + c;
-                uint2 packed = make_uint2(pack_bf16(px * lx, py * ly), pack_bf16(pz * lz, pw * lw));
+                uint2 packed = make_uint2(pack16<H16>(px * lx, py * ly), pack16<H16>(pz * lz, pw * lw));
                 *reinterpret_cast<uint2*>(arow + (k >> 3) * LBO_A + (k & 7) * 2) = packed;
               }
             }
@@ -188,7 +189,7 @@ __global__ void __launch_bounds__(kThreadsV2, 1) k_app_tc(const FwdParams P) {
               float4 pv, lv;
               vm_sample4(m.app_plane[kk], m.app_line[kk], t, CA, c, pv, lv);
               const int k = kk * CA + c;
-              uint2 packed = make_uint2(pack_bf16(pv.x * lv.x, pv.y * lv.y), pack_bf16(pv.z * lv.z, pv.w * lv.w));
+              uint2 packed = make_uint2(pack16<H16>(pv.x * lv.x, pv.y * lv.y), pack16<H16>(pv.z * lv.z, pv.w * lv.w));
               *reinterpret_cast<uint2*>(arow + (k >> 3) * LBO_A + (k & 7) * 2) = packed;
             }
           }
@@ -292,10 +293,10 @@ __global__ void __launch_bounds__(kThreadsV2, 1) k_app_tc(const FwdParams P) {
 #pragma unroll
         for (int kc = 0; kc < K1 / 8; ++kc) {
           uint4 v;
-          v.x = pack_bf16(column(kc * 8 + 0), column(kc * 8 + 1));
-          v.y = pack_bf16(column(kc * 8 + 2), column(kc * 8 + 3));
-          v.z = pack_bf16(column(kc * 8 + 4), column(kc * 8 + 5));
-          v.w = pack_bf16(column(kc * 8 + 6), column(kc * 8 + 7));
+          v.x = pack16<H16>(column(kc * 8 + 0), column(kc * 8 + 1));
+          v.y = pack16<H16>(column(kc * 8 + 2), column(kc * 8 + 3));
+          v.z = pack16<H16>(column(kc * 8 + 4), column(kc * 8 + 5));
+          v.w = pack16<H16>(column(kc * 8 + 6), column(kc * 8 + 7));
           *reinterpret_cast<uint4*>(arow + kc * LBO_A) = v;
         }
       }
@@ -324,15 +325,15 @@ __global__ void __launch_bounds__(kThreadsV2, 1) k_app_tc(const FwdParams P) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           uint4 v;
-          v.x = pack_bf16(y[g * 8 + 0], y[g * 8 + 1]);
-          v.y = pack_bf16(y[g * 8 + 2], y[g * 8 + 3]);
-          v.z = pack_bf16(y[g * 8 + 4], y[g * 8 + 5]);
-          v.w = pack_bf16(y[g * 8 + 6], y[g * 8 + 7]);
+          v.x = pack16<H16>(y[g * 8 + 0], y[g * 8 + 1]);
+          v.y = pack16<H16>(y[g * 8 + 2], y[g * 8 + 3]);
+          v.z = pack16<H16>(y[g * 8 + 4], y[g * 8 + 5]);
+          v.w = pack16<H16>(y[g * 8 + 6], y[g * 8 + 7]);
           *reinterpret_cast<uint4*>(arow + (cb * 4 + g) * LBO_A) = v;
         }
       }
       // columns 128..143: a constant one (row 128 of the W2 / W3 operands is b2 / b3), then zeros
-      *reinterpret_cast<uint4*>(arow + 16 * LBO_A) = make_uint4(0x00003f80u, 0u, 0u, 0u);
+      *reinterpret_cast<uint4*>(arow + 16 * LBO_A) = make_uint4(H16 ? 0x00003c00u : 0x00003f80u, 0u, 0u, 0u);
       *reinterpret_cast<uint4*>(arow + 17 * LBO_A) = make_uint4(0u, 0u, 0u, 0u);
       fence_async_smem();
       fence_before();
@@ -360,10 +361,10 @@ __global__ void __launch_bounds__(kThreadsV2, 1) k_app_tc(const FwdParams P) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           uint4 v;
-          v.x = pack_bf16(y[g * 8 + 0], y[g * 8 + 1]);
-          v.y = pack_bf16(y[g * 8 + 2], y[g * 8 + 3]);
-          v.z = pack_bf16(y[g * 8 + 4], y[g * 8 + 5]);
-          v.w = pack_bf16(y[g * 8 + 6], y[g * 8 + 7]);
+          v.x = pack16<H16>(y[g * 8 + 0], y[g * 8 + 1]);
+          v.y = pack16<H16>(y[g * 8 + 2], y[g * 8 + 3]);
+          v.z = pack16<H16>(y[g * 8 + 4], y[g * 8 + 5]);
+          v.w = pack16<H16>(y[g * 8 + 6], y[g * 8 + 7]);
           *reinterpret_cast<uint4*>(arow + (cb * 4 + g) * LBO_A) = v;
         }
       }
@@ -414,7 +415,9 @@ static bool tc_supported(const TvmModel& m) {
 }
 
 int launch_app_tc(const FwdParams& P, int num_sms, cudaStream_t stream) {
-  TVM_REQUIRE((P.flags & TVM_MLP_MASK) == TVM_MLP_BF16, "only TVM_MLP_BF16 is implemented on the tensor-core path");
+  const uint32_t mode = P.flags & TVM_MLP_MASK;
+  TVM_REQUIRE(mode == TVM_MLP_BF16 || mode == TVM_MLP_FP16, "the tensor-core path takes TVM_MLP_BF16 or TVM_MLP_FP16");
+  const bool h16 = mode == TVM_MLP_FP16;
   TVM_REQUIRE(tc_supported(P.m), "tensor-core appearance head supports n_app=48, app_dim=27, fea_pe=view_pe=2, "
                                  "featureC=128 (all shipped configs); use TVM_MLP_FP32 otherwise");
   TVM_REQUIRE(P.m.tc_weights != nullptr, "TvmModel.tc_weights is NULL: call tvm_pack_mlp_tc first");
@@ -423,8 +426,13 @@ int launch_app_tc(const FwdParams& P, int num_sms, cudaStream_t stream) {
   const int KA = max(img.K1, 128);
   const size_t smem = ((img.bytes_fwd + 1023) & ~1023u) + 2 * (size_t)kRows * img.K0 * 2 + (size_t)kRows * KA * 2 + 128 + 1024;
   const bool pb16 = P.m.app_plane_bf16[0] && P.m.app_plane_bf16[1] && P.m.app_plane_bf16[2];
-  auto kern = ref ? (pb16 ? k_app_tc<48, 27, 2, 2, true, true> : k_app_tc<48, 27, 2, 2, true, false>)
-                  : (pb16 ? k_app_tc<48, 27, 2, 2, false, true> : k_app_tc<48, 27, 2, 2, false, false>);
+  void (*kern)(const FwdParams);
+  if (h16)
+    kern = ref ? (pb16 ? k_app_tc<48, 27, 2, 2, true, true, true> : k_app_tc<48, 27, 2, 2, true, false, true>)
+               : (pb16 ? k_app_tc<48, 27, 2, 2, false, true, true> : k_app_tc<48, 27, 2, 2, false, false, true>);
+  else
+    kern = ref ? (pb16 ? k_app_tc<48, 27, 2, 2, true, true, false> : k_app_tc<48, 27, 2, 2, true, false, false>)
+               : (pb16 ? k_app_tc<48, 27, 2, 2, false, true, false> : k_app_tc<48, 27, 2, 2, false, false, false>);
   TVM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<num_sms, kThreadsV2, smem, stream>>>(P);
   TVM_CHECK_CUDA(cudaGetLastError());
@@ -441,7 +449,10 @@ extern "C" size_t tvm_tc_weights_bytes(const TvmModel* m_host) {
   return Image(m_host->n_app, in_mlp_c(*m_host), head_ld(*m_host)).bytes_fwd;
 }
 
-extern "C" int tvm_pack_mlp_tc(const TvmModel* m_host, void* out, void* stream_) {
+extern "C" int tvm_pack_mlp_tc(const TvmModel* m_host, void* out, uint32_t flags, void* stream_) {
+  const uint32_t mode = flags & TVM_MLP_MASK;
+  TVM_REQUIRE(mode == TVM_MLP_BF16 || mode == TVM_MLP_FP16, "tvm_pack_mlp_tc: flags must name TVM_MLP_BF16 or TVM_MLP_FP16");
+  const int h16 = mode == TVM_MLP_FP16;
   TVM_REQUIRE(m_host && out, "bad arguments");
   if (int rc = validate_model(*m_host)) return rc;
   TVM_REQUIRE(tc_supported(*m_host), "unsupported shape for the tensor-core appearance head");
@@ -452,14 +463,14 @@ extern "C" int tvm_pack_mlp_tc(const TvmModel* m_host, void* out, void* stream_)
   uint8_t* o = (uint8_t*)out;
   auto launch = [&](const float* w_t, int K, int K_pad, int N_real, int N, int ldw, uint32_t off) {
     const int n = K_pad * N;
-    k_pack_umma_b<<<(n + 255) / 256, 256, 0, s>>>(w_t, K, K_pad, N_real, N, ldw, (__nv_bfloat16*)(o + off), K_pad, K_pad);
+    k_pack_umma_b<<<(n + 255) / 256, 256, 0, s>>>(w_t, K, K_pad, N_real, N, ldw, (__nv_bfloat16*)(o + off), K_pad, K_pad, h16);
   };
   launch(m_host->basis_t, img.K0, img.K0, nh, nh, nh, img.off_b0);
   launch(m_host->w1_t, in_c, img.K1, 128, 128, kFeatureC, img.off_b1);
   launch(m_host->w2_t, 128, 128, 128, 128, kFeatureC, img.off_b2);
   k_pack_tc_f32<<<3, 256, 0, s>>>(*m_host, (float*)(o + img.off_f32));
-  k_pack_tc_ext<<<(144 * 16 + 255) / 256, 256, 0, s>>>(*m_host, in_c, (__nv_bfloat16*)(o + img.off_b1),
-                                                    (__nv_bfloat16*)(o + img.off_b2x), (__nv_bfloat16*)(o + img.off_b3));
+  k_pack_tc_ext<<<(144 * 16 + 255) / 256, 256, 0, s>>>(*m_host, in_c, (uint16_t*)(o + img.off_b1), (uint16_t*)(o + img.off_b2x),
+                                                    (uint16_t*)(o + img.off_b3), h16);
   TVM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

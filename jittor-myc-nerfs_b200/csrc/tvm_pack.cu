@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <vector>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "tvm_common.cuh"
 
 namespace tvm {
@@ -305,15 +306,23 @@ extern "C" int tvm_mse_loss(const float* rgb_map, const float* target, int n_ray
   return 0;
 }
 
-__global__ void k_pack_bf16(const float* __restrict__ src, size_t n, __nv_bfloat16* __restrict__ dst) {
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-    dst[i] = __float2bfloat16_rn(src[i]);
+__global__ void k_pack_half(const float* __restrict__ src, size_t n, uint16_t* __restrict__ dst, int h16) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    if (h16) {
+      const __half h = __float2half_rn(src[i]);
+      dst[i] = *reinterpret_cast<const uint16_t*>(&h);
+    } else {
+      const __nv_bfloat16 b = __float2bfloat16_rn(src[i]);
+      dst[i] = *reinterpret_cast<const uint16_t*>(&b);
+    }
+  }
 }
 
-extern "C" int tvm_pack_bf16(const float* src, size_t n, void* dst_bf16, void* stream) {
-  TVM_REQUIRE(src && dst_bf16 && n > 0, "bad arguments");
+extern "C" int tvm_pack_half(const float* src, size_t n, void* dst, uint32_t flags, void* stream) {
+  const uint32_t mode = flags & TVM_MLP_MASK;
+  TVM_REQUIRE(src && dst && n > 0 && (mode == TVM_MLP_BF16 || mode == TVM_MLP_FP16), "bad arguments");
   const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 16);
-  k_pack_bf16<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, n, (__nv_bfloat16*)dst_bf16);
+  k_pack_half<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, n, (uint16_t*)dst, mode == TVM_MLP_FP16);
   TVM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

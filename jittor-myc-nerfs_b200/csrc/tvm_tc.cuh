@@ -4,6 +4,7 @@
 //   (k/8) * (R*16) + r*16 + (k%8)*2        (LBO = R*16 bytes between K-chunks, SBO = 128 bytes between 8-row groups)
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "tvm_common.cuh"
 
 namespace tvm {
@@ -96,8 +97,9 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
          ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
 }
 // bf16 x bf16 -> f32, both operands K-major
-__host__ __device__ constexpr uint32_t instr_desc(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// h16: operands are IEEE fp16 (format 0) instead of bf16 (format 1)
+__host__ __device__ constexpr uint32_t instr_desc(int M, int N, bool h16 = false) {
+  return (1u << 4) | ((h16 ? 0u : 1u) << 7) | ((h16 ? 0u : 1u) << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 // operand read "transposed" (MN-major): the reduction index runs over the image ROWS; LBO = 128, SBO = rows * 16
@@ -107,6 +109,28 @@ constexpr uint32_t kIdescBMajorMN = 1u << 16;
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
+}
+// 16-bit operand element pairs of the appearance head: bf16 (TVM_MLP_BF16) or fp16 (TVM_MLP_FP16)
+template <bool H16>
+__device__ __forceinline__ uint32_t pack16(float a, float b) {
+  if (H16) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  return pack_bf16(a, b);
+}
+template <bool H16>
+__device__ __forceinline__ float2 unpack16(uint32_t v) {
+  if (H16) return __half22float2(*reinterpret_cast<const __half2*>(&v));
+  return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
+}
+__host__ __device__ inline uint16_t to16(float v, bool h16) {
+  if (h16) {
+    const __half h = __float2half_rn(v);
+    return *reinterpret_cast<const uint16_t*>(&h);
+  }
+  const __nv_bfloat16 b = __float2bfloat16_rn(v);
+  return *reinterpret_cast<const uint16_t*>(&b);
 }
 
 
@@ -140,7 +164,7 @@ constexpr int kColOut = 192;        // TMEM columns [192, 208): accumulator of t
 // Image column k reads source row k for k < split, nothing for split <= k < split_pad, and row
 // split + (k - split_pad) beyond (used to pad the first block of a concatenated input to 16).
 __global__ void k_pack_umma_b(const float* __restrict__ w_t, int K, int K_pad, int N_real, int N, int ldw,
-                              __nv_bfloat16* __restrict__ img, int split, int split_pad);
+                              __nv_bfloat16* __restrict__ img, int split, int split_pad, int h16 = 0);
 
 }  // namespace tc
 }  // namespace tvm

@@ -23,7 +23,7 @@ from .train_ops import RegularizerMixin
 MAT_MODE = [[0, 1], [0, 2], [1, 2]]   # tensorBase.py:168
 VEC_MODE = [2, 1, 0]                  # tensorBase.py:169
 
-_MLP_FLAGS = {"fp32": L.MLP_FP32, "bf16": L.MLP_BF16, "bf16x3": L.MLP_BF16X3}
+_MLP_FLAGS = {"fp32": L.MLP_FP32, "bf16": L.MLP_BF16, "fp16": L.MLP_FP16}
 
 
 def derive_march_scalars(aabb, gridSize, step_ratio):
@@ -189,7 +189,7 @@ class TensorVMSplit(MaintainMixin, RegularizerMixin, CheckpointMixin, torch.nn.M
         self.init_render_func(shadingMode, pos_pe, view_pe, fea_pe, featureC, device)
         # --- engine state -------------------------------------------------------------------
         self.mlp_mode = os.environ.get("TVM_MLP_MODE", "fp32")
-        # mlp_mode "bf16" only: gather the appearance-plane texels from bf16 copies (half the gather bytes of the head;
+        # mlp_mode "bf16" / "fp16": gather the appearance-plane texels from 16-bit copies in the mode's format (half the gather bytes of the head;
         # the plane x line products are rounded to bf16 as the GEMM operand in that mode anyway).  Backward kernels and
         # the fp32 mode always read the fp32 planes.
         self.app_planes_bf16 = os.environ.get("TVM_APP_PLANES", "fp32") == "bf16"
@@ -414,12 +414,12 @@ class TensorVMSplit(MaintainMixin, RegularizerMixin, CheckpointMixin, torch.nn.M
                 raise L.TvmError("tensor-core appearance head unavailable in this libtvmrender.so")
             if self._tc is None or self._tc.numel() < nbytes:
                 self._tc = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
-            L.check(lib.tvm_pack_mlp_tc(C.byref(s), _ptr(self._tc), _stream_ptr()), "tvm_pack_mlp_tc")
+            L.check(lib.tvm_pack_mlp_tc(C.byref(s), _ptr(self._tc), _MLP_FLAGS[self.mlp_mode], _stream_ptr()), "tvm_pack_mlp_tc")
             s.tc_weights = self._tc.data_ptr()
             self._tc_stale = False
         for k in range(3):
             s.app_plane_bf16[k] = None
-        if self.mlp_mode == "bf16" and self.app_planes_bf16:
+        if self.mlp_mode in ("bf16", "fp16") and self.app_planes_bf16:
             lib = L.load()
             items, _ = self._layout()
             n_tot = sum(items[f"ap{k}"][1] for k in range(3))
@@ -429,8 +429,8 @@ class TensorVMSplit(MaintainMixin, RegularizerMixin, CheckpointMixin, torch.nn.M
             for k in range(3):
                 o, n_el = items[f"ap{k}"]
                 dst = self._app16.data_ptr() + 2 * off
-                L.check(lib.tvm_pack_bf16(C.c_void_p(self._packed.data_ptr() + 4 * o), n_el, C.c_void_p(dst), _stream_ptr()),
-                        "tvm_pack_bf16")
+                L.check(lib.tvm_pack_half(C.c_void_p(self._packed.data_ptr() + 4 * o), n_el, C.c_void_p(dst),
+                                          _MLP_FLAGS[self.mlp_mode], _stream_ptr()), "tvm_pack_half")
                 s.app_plane_bf16[k] = dst
                 off += n_el
         s.sampling, s.radii = L.SAMPLING_UNIFORM, 0.0

@@ -198,6 +198,35 @@ def test_bf16_appearance_planes(env):
         assert abs(psnr(b, tgt) - psnr(ref["rgb_map"], tgt)) < 0.01
 
 
+def test_tensor_core_mlp_fp16_meets_fp32_tolerance(env):
+    """TVM_MLP_FP16: the same tcgen05 head with fp16 operands (11 significant bits instead of bf16's 8, fp32 accumulation):
+    rgb within the north_star's FP32 tolerance (1e-4), with fp32 or fp16 appearance-plane copies; REFTensoRF included."""
+    pkg, torch, fx, orc = env
+    from util import gpu_model
+    for regime, G, variant in (("R1", 128, None), ("R2", 128, None), ("R1", 300, None), ("R2", 64, "ref")):
+        kw = dict(variant=variant, mask_res=G) if variant else {}
+        case = fx.make_case(G, 2048, regime, **kw)
+        ref = orc.run_case(case, want_stages=False)
+        model = gpu_model(pkg, case, mlp_mode="fp16")
+        rays = torch.from_numpy(case["rays"]).cuda()
+        errs = []
+        for planes16 in (False, True):
+            model.app_planes_bf16 = planes16
+            with torch.no_grad():
+                rgb, depth = model(rays)
+            torch.cuda.synchronize()
+            errs.append(float(np.abs(rgb.cpu().numpy() - ref["rgb_map"]).max()))
+            assert np.abs(depth.cpu().numpy() - ref["depth_map"]).max() <= DEPTH_TOL
+        print(f"fp16 MLP {regime} G={G} {variant or 'vm'}: max|rgb-oracle| = {errs[0]:.3e} (fp32 planes), {errs[1]:.3e} (fp16 planes)")
+        assert max(errs) <= RGB_TOL
+    # training in this mode: tensor-core forward, fp32 backward (exact gradients of the fp16-rounded forward's neighbour)
+    case = fx.make_case(48, 256, "R2", mask_res=48, train=True)
+    model = gpu_model(pkg, case, mlp_mode="fp16")
+    rgb, _ = model(torch.from_numpy(case["rays"]).cuda(), is_train=True, jitter=torch.from_numpy(case["jitter"]).cuda())
+    rgb.sum().backward()
+    assert torch.isfinite(model.app_plane[0].grad).all() and float(model.app_plane[0].grad.abs().sum()) > 0
+
+
 @pytest.mark.parametrize("mode,tol", [("fp32", RGB_TOL), ("bf16", 1e-2)])
 def test_reftensorf_variant(env, mode, tol):
     """REFTensoRF (models/REFTensoRF.py): extra heads, reflected direction, tint*rgb_s + rgb_d, penalty."""
