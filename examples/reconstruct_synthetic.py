@@ -55,7 +55,10 @@ def psnr_of(model, rays, rgb, nSamples):
 
 def run(iters=600, res=96, n_views=16, batch=4096, N_voxel_init=32 ** 3, N_voxel_final=64 ** 3, upsamp_list=(250, 400),
         update_AlphaMask_list=(150, 300), lr_init=0.02, lr_basis=1e-3, lr_decay_target_ratio=0.1, TV_weight_density=0.1,
-        TV_weight_app=0.01, step_ratio=0.5, mlp_mode="fp32", seed=0, ckpt_path=None, log=print):
+        TV_weight_app=0.01, step_ratio=0.5, mlp_mode="fp32", seed=0, ckpt_path=None, log=print, model_name="TensorVMSplit",
+        normal_vector_penalty_weight=0.5, radii=14.0):
+    """model_name: TensorVMSplit | REFTensoRF (adds normal_vector_penalty_weight * tensorf.penalty, train.py:253-257) |
+    NerfPlusPlus (set_nerfplusplus(2, 2, 3, radii): foreground on black inside the radii-sphere + background MLP)."""
     dev = torch.device("cuda:0")
     torch.manual_seed(seed)
     focal = 0.5 * res / math.tan(0.5 * 0.6911)
@@ -68,11 +71,13 @@ def run(iters=600, res=96, n_views=16, batch=4096, N_voxel_init=32 ** 3, N_voxel
     aabb = torch.tensor([[-3.0, -3.0, -3.0], [3.0, 3.0, 3.0]])
     reso_cur = N_to_reso(N_voxel_init, aabb)
     nSamples = min(int(1e6), cal_n_samples(reso_cur, step_ratio))
-    tensorf = pkg.TensorVMSplit(aabb, reso_cur, dev, density_n_comp=[16, 16, 16], appearance_n_comp=[48, 48, 48], app_dim=27,
+    tensorf = getattr(pkg, model_name)(aabb, reso_cur, dev, density_n_comp=[16, 16, 16], appearance_n_comp=[48, 48, 48], app_dim=27,
                                 near_far=[8.0, 16.0], shadingMode="MLP_Fea", alphaMask_thres=1e-4, density_shift=-10,
                                 distance_scale=25, pos_pe=6, view_pe=2, fea_pe=2, featureC=128, step_ratio=step_ratio,
                                 fea2denseAct="softplus")
+    tensorf.set_nerfplusplus(bg_freq=2, bg_view_freq=2, bg_D=3, radii=radii)        # train.py:173 (a no-op except for NerfPlusPlus)
     tensorf.mlp_mode = mlp_mode
+    npp, ref = model_name == "NerfPlusPlus", model_name == "REFTensoRF"
     grad_vars = tensorf.get_optparam_groups(lr_init, lr_basis)
     lr_factor = lr_decay_target_ratio ** (1 / iters)
     optimizer = pkg.Adam(grad_vars, betas=(0.9, 0.99))
@@ -97,6 +102,8 @@ def run(iters=600, res=96, n_views=16, batch=4096, N_voxel_init=32 ** 3, N_voxel
         if TV_weight_app > 0:
             TV_weight_app *= lr_factor
             total = total + tensorf.TV_loss_app(tvreg) * TV_weight_app
+        if ref and normal_vector_penalty_weight > 0:
+            total = total + normal_vector_penalty_weight * tensorf.penalty.sum()
         total.backward()
         optimizer.step()
         hist["psnr_train"].append(float(-10.0 * math.log10(max(float(loss), 1e-12))))
@@ -132,7 +139,10 @@ def run(iters=600, res=96, n_views=16, batch=4096, N_voxel_init=32 ** 3, N_voxel
         ckpt = pkg.load_checkpoint(ckpt_path)
         kwargs = ckpt["kwargs"]
         kwargs.update({"device": dev})
-        again = pkg.TensorVMSplit(**kwargs)
+        bg = [kwargs.pop(k) for k in ("bg_freq", "bg_view_freq", "bg_D", "radii")] if "bg_freq" in kwargs else None
+        again = getattr(pkg, model_name)(**kwargs)
+        if bg is not None:
+            again.set_nerfplusplus(*bg)
         again.load(ckpt)
         again.mlp_mode = mlp_mode
         hist["reload_psnr"] = psnr_of(again, test_rays, test_rgb, nSamples)
@@ -145,6 +155,7 @@ if __name__ == "__main__":
     ap.add_argument("--iters", type=int, default=600)
     ap.add_argument("--mlp", default="fp32", choices=["fp32", "bf16", "fp16"])
     ap.add_argument("--ckpt", default=None)
+    ap.add_argument("--model", default="TensorVMSplit", choices=["TensorVMSplit", "REFTensoRF", "NerfPlusPlus"])
     a = ap.parse_args()
-    h = run(iters=a.iters, mlp_mode=a.mlp, ckpt_path=a.ckpt)
+    h = run(iters=a.iters, mlp_mode=a.mlp, ckpt_path=a.ckpt, model_name=a.model)
     print("final held-out PSNR %.2f dB" % h["final_psnr"])

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define TVM_ABI_VERSION 15
+#define TVM_ABI_VERSION 16
 
 /* flags for tvm_forward / tvm_backward */
 #define TVM_WHITE_BG      0x1u  /* rgb_map += 1 - acc_map          (tensorBase.py:523-524) */
@@ -288,9 +288,11 @@ int tvm_dense_alpha(const TvmModel* m_host, const int32_t* grid_host, float leng
 int tvm_alpha_mask_from_dense(const float* alpha_zyx, const int32_t* grid_host, float thres, float* volume_out,
                               uint32_t* bits_out, int32_t* bbox_idx, uint64_t* n_set, void* stream);
 /* TensorBase.filtering_rays (tensorBase.py:411-441): mask_out[i] = 1 iff ray i is kept.  bbox_only: t_max > t_min of the slab
- * test (:424-429); else any of n_samples uniform samples has sample_alpha > 0 (:432-433; no bbox gate, as the reference).      */
+ * test (:424-429); else any of the n_samples points of self.sample_ray(..., is_train=False) has sample_alpha > 0 (:432-433;
+ * no bbox gate, as the reference).  TVM_SAMPLING_NPP: that sampler is NerfPlusPlus.sample_ray, always jittered --
+ * fg_rand [n][n_samples] carries its draws (NULL otherwise).                                                              */
 int tvm_filter_rays(const TvmModel* m_host, const float* rays, int n_rays, int n_samples, int bbox_only,
-                    uint8_t* mask_out, void* stream);
+                    const float* fg_rand, uint8_t* mask_out, void* stream);
 /* get_ray_directions / get_ray_directions_blender + get_rays (dataLoader/ray_utils.py:81-153), optional unit
  * normalisation of the camera-space direction (dataLoader/blender.py:75); c2w_host is a HOST [3][4] matrix; rays_out [H*W][6]. */
 int tvm_generate_rays(const float* c2w_host, int H, int W, float fx, float fy, float cx, float cy, int blender,

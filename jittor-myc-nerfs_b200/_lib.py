@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # TVM_LIB: developer override (kernel-tuning experiments build variant libraries next to the default one)
 LIB_PATH = os.environ.get("TVM_LIB") or os.path.join(_HERE, "libtvmrender.so")
-ABI_VERSION = 15
+ABI_VERSION = 16
 
 # flags (tvmrender.h)
 WHITE_BG = 0x1
@@ -138,7 +138,7 @@ def load() -> C.CDLL:
     i3 = C.POINTER(C.c_int32)
     lib.tvm_dense_alpha.argtypes = [C.POINTER(TvmModel), i3, f32, vp, vp]
     lib.tvm_alpha_mask_from_dense.argtypes = [vp, i3, f32, vp, vp, vp, vp, vp]
-    lib.tvm_filter_rays.argtypes = [C.POINTER(TvmModel), vp, i32, i32, i32, vp, vp]
+    lib.tvm_filter_rays.argtypes = [C.POINTER(TvmModel), vp, i32, i32, i32, vp, vp, vp]
     lib.tvm_generate_rays.argtypes = [C.POINTER(C.c_float), i32, i32, f32, f32, f32, f32, i32, i32, vp, vp]
     lib.tvm_upsample_grid.argtypes = [vp, i32, i32, i32, vp, i32, i32, vp]
     lib.tvm_tv_loss.argtypes = [vp, i32, i32, i32, f32, vp, vp, vp, vp]

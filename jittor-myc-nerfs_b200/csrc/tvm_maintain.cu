@@ -129,11 +129,11 @@ __global__ void __launch_bounds__(256) k_filter_bbox(const TvmModel m, const flo
 
 // one warp per ray; the reference evaluates sample_alpha on EVERY sample (no bbox gate): zeros padding decides
 __global__ void __launch_bounds__(256) k_filter_alpha(const TvmModel m, const float* __restrict__ rays, int n, int S,
-                                                      uint8_t* __restrict__ mask) {
+                                                      const float* __restrict__ jitter, uint8_t* __restrict__ mask) {
   const int ray = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (ray >= n) return;
   RayMarch r;
-  ray_setup(m, rays + 6 * (size_t)ray, nullptr, ray, S, r);
+  ray_setup(m, rays + 6 * (size_t)ray, jitter, ray, S, r);      // jitter: NULL (uniform, is_train=False) or [n][S] (NeRF++)
   bool any = false;
   for (int b = 0; b * 32 < S && !any; ++b) {
     if (m.alpha_bricks) {          // conservative: skip blocks whose voxel footprint holds no set brick
@@ -234,7 +234,7 @@ extern "C" int tvm_alpha_mask_from_dense(const float* alpha_zyx, const int32_t* 
 }
 
 extern "C" int tvm_filter_rays(const TvmModel* m_host, const float* rays, int n_rays, int n_samples, int bbox_only,
-                               uint8_t* mask_out, void* stream) {
+                               const float* fg_rand, uint8_t* mask_out, void* stream) {
   TVM_REQUIRE(m_host && rays && mask_out && n_rays > 0, "bad arguments");
   if (int rc = validate_model(*m_host)) return rc;
   cudaStream_t s = (cudaStream_t)stream;
@@ -242,8 +242,10 @@ extern "C" int tvm_filter_rays(const TvmModel* m_host, const float* rays, int n_
     k_filter_bbox<<<(n_rays + 255) / 256, 256, 0, s>>>(*m_host, rays, n_rays, mask_out);
   } else {
     TVM_REQUIRE(m_host->alpha_bits != nullptr, "filtering_rays(bbox_only=False) needs an alpha mask");
-    TVM_REQUIRE(n_samples > 0 && m_host->sampling == TVM_SAMPLING_UNIFORM, "bad n_samples / sampling");
-    k_filter_alpha<<<(n_rays + 7) / 8, 256, 0, s>>>(*m_host, rays, n_rays, n_samples, mask_out);
+    const bool npp = m_host->sampling == TVM_SAMPLING_NPP;
+    TVM_REQUIRE(n_samples > (npp ? 1 : 0), "bad n_samples");
+    TVM_REQUIRE(!npp || fg_rand, "TVM_SAMPLING_NPP: filtering_rays samples with NerfPlusPlus.sample_ray and needs fg_rand [n][n_samples]");
+    k_filter_alpha<<<(n_rays + 7) / 8, 256, 0, s>>>(*m_host, rays, n_rays, n_samples, npp ? fg_rand : nullptr, mask_out);
   }
   TVM_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -100,8 +100,12 @@ class MaintainMixin:
         rays = all_rays.reshape(-1, all_rays.shape[-1])[:, :6].to(self.device, torch.float32).contiguous()
         mask = torch.empty(rays.shape[0], dtype=torch.uint8, device=self.device)
         model = self._model()
+        fg_rand = None
+        if not bbox_only and model.sampling == L.SAMPLING_NPP:
+            # NerfPlusPlus.sample_ray perturbs its samples even with is_train=False (nerfplusplus.py:251)
+            fg_rand = torch.rand((rays.shape[0], int(N_samples)), dtype=torch.float32, device=self.device)
         L.check(L.load().tvm_filter_rays(C.byref(model), _ptr(rays), rays.shape[0], int(N_samples), 1 if bbox_only else 0,
-                                         _ptr(mask), _stream_ptr()), "tvm_filter_rays")
+                                         _ptr(fg_rand), _ptr(mask), _stream_ptr()), "tvm_filter_rays")
         return mask.bool()
 
     @torch.no_grad()
