@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define TVM_ABI_VERSION 16
+#define TVM_ABI_VERSION 18
 
 /* flags for tvm_forward / tvm_backward */
 #define TVM_WHITE_BG      0x1u  /* rgb_map += 1 - acc_map          (tensorBase.py:523-524) */
@@ -191,6 +191,17 @@ int tvm_device_count(void);
 int tvm_pack_grid(const float* nchw, int C, int H, int W, float* out_hwc, void* stream);
 /* inverse of tvm_pack_grid (used on gradients so the host optimiser sees NCHW)                */
 int tvm_unpack_grid(const float* hwc, int C, int H, int W, float* out_nchw, void* stream);
+/* Several 2-D transposes dst[c][r] = src[r][c] in one launch: tvm_pack_grid is the transpose of [C][H*W], tvm_unpack_grid of
+ * [H*W][C], tvm_pack_linear / tvm_unpack_linear a transpose with a padded leading dimension, a bias a 1-row job: a training
+ * step moves all parameters (and all gradients) with one call each.  jobs_host is a HOST array.                          */
+#define TVM_TRANSPOSE_MAX 32
+typedef struct TvmTransposeJob {
+  const float* src;         /* [rows][src_ld], columns 0..cols-1 are read */
+  float* dst;               /* [cols][dst_ld], columns 0..rows-1 are written (tvm_pack_linear's padding stays as it is) */
+  int32_t rows, cols;
+  int32_t src_ld, dst_ld;   /* leading dimensions in floats; 0 = dense (cols / rows).  rows = 1 is a plain copy. */
+} TvmTransposeJob;
+int tvm_transpose_batch(const TvmTransposeJob* jobs_host, int n_jobs, void* stream);
 /* Linear weight [out][in] -> [in][out_pad] (zero padded columns)                              */
 int tvm_pack_linear(const float* w_out_in, int out_c, int in_c, int out_pad, float* out_t, void* stream);
 int tvm_unpack_linear(const float* w_t, int out_c, int in_c, int out_pad, float* out_w, void* stream);
@@ -306,6 +317,16 @@ int tvm_upsample_grid(const float* src_nchw, int C, int H, int W, float* dst_nch
  * density_L1's mean |x| (tensoRF.py:191-195); vectorDiffs (tensoRF.py:177-186) of one line [1][C][L][1].                        */
 int tvm_tv_loss(const float* plane_nchw, int C, int H, int W, float weight, const float* weight_dev, float* loss_accum,
                 float* grad_nchw, void* stream);
+/* tvm_tv_loss for up to TVM_TV_MAX planes in one launch (the six factor planes of a step); jobs_host is a HOST array */
+#define TVM_TV_MAX 8
+typedef struct TvmTvJob {
+  const float* plane_nchw;  /* [1][C][H][W] */
+  float* grad_nchw;         /* += weight * d TV / d plane, or NULL */
+  int32_t C, H, W;
+  float weight;
+  const float* weight_dev;  /* nullable DEVICE scalar multiplied into weight */
+} TvmTvJob;
+int tvm_tv_loss_batch(const TvmTvJob* jobs_host, int n_jobs, float* loss_accum, void* stream);
 int tvm_l1_loss(const float* x, size_t n, float weight, const float* weight_dev, float* loss_accum, float* grad, void* stream);
 int tvm_vector_diffs(const float* line_cl, int C, int L, float weight, const float* weight_dev, float* loss_accum, float* grad,
                      void* stream);

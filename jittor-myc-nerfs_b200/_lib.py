@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # TVM_LIB: developer override (kernel-tuning experiments build variant libraries next to the default one)
 LIB_PATH = os.environ.get("TVM_LIB") or os.path.join(_HERE, "libtvmrender.so")
-ABI_VERSION = 16
+ABI_VERSION = 18
 
 # flags (tvmrender.h)
 WHITE_BG = 0x1
@@ -67,6 +67,16 @@ class TvmBgGrads(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in BG_FIELDS]
 
 
+class TvmTransposeJob(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("rows", C.c_int32), ("cols", C.c_int32),
+                ("src_ld", C.c_int32), ("dst_ld", C.c_int32)]
+
+
+class TvmTvJob(C.Structure):
+    _fields_ = [("plane_nchw", C.c_void_p), ("grad_nchw", C.c_void_p), ("C", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+                ("weight", C.c_float), ("weight_dev", C.c_void_p)]
+
+
 class TvmAdamTensor(C.Structure):
     _fields_ = [("p", C.c_void_p), ("g", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p), ("n", C.c_size_t), ("lr", C.c_float), ("lr_index", C.c_int32)]
 
@@ -82,12 +92,12 @@ class TvmGrads(C.Structure):
 
 EXPORTS = [
     "tvm_last_error", "tvm_abi_version", "tvm_device_count", "tvm_pack_grid", "tvm_unpack_grid",
-    "tvm_pack_linear", "tvm_unpack_linear", "tvm_pack_half", "tvm_pack_alpha", "tvm_pack_alpha_bricks", "tvm_pack_alpha_dilated", "tvm_tc_weights_bytes", "tvm_pack_mlp_tc",
+    "tvm_pack_linear", "tvm_unpack_linear", "tvm_transpose_batch", "tvm_pack_half", "tvm_pack_alpha", "tvm_pack_alpha_bricks", "tvm_pack_alpha_dilated", "tvm_tc_weights_bytes", "tvm_pack_mlp_tc",
     "tvm_workspace_bytes", "tvm_forward", "tvm_forward_npp", "tvm_bg_fold", "tvm_bg_tc_bytes", "tvm_pack_bg_tc", "tvm_backward", "tvm_backward_npp", "tvm_bg_fold_bwd",
     "tvm_density_alpha", "tvm_mse_loss",
     "tvm_profile_enable", "tvm_profile_collect",
     "tvm_dense_alpha", "tvm_alpha_mask_from_dense", "tvm_filter_rays", "tvm_generate_rays", "tvm_upsample_grid",
-    "tvm_tv_loss", "tvm_l1_loss", "tvm_vector_diffs", "tvm_adam_step", "tvm_selftest_umma", "tvm_bench_gather",
+    "tvm_tv_loss", "tvm_tv_loss_batch", "tvm_l1_loss", "tvm_vector_diffs", "tvm_adam_step", "tvm_selftest_umma", "tvm_bench_gather",
 ]
 
 
@@ -118,6 +128,7 @@ def load() -> C.CDLL:
     lib.tvm_pack_grid.argtypes = [vp, i32, i32, i32, vp, vp]
     lib.tvm_unpack_grid.argtypes = [vp, i32, i32, i32, vp, vp]
     lib.tvm_pack_linear.argtypes = [vp, i32, i32, i32, vp, vp]
+    lib.tvm_transpose_batch.argtypes = [C.POINTER(TvmTransposeJob), i32, vp]
     lib.tvm_unpack_linear.argtypes = [vp, i32, i32, i32, vp, vp]
     lib.tvm_pack_alpha.argtypes = [vp, i32, i32, i32, vp, vp]
     lib.tvm_pack_half.argtypes = [vp, C.c_size_t, vp, u32, vp]
@@ -142,6 +153,7 @@ def load() -> C.CDLL:
     lib.tvm_generate_rays.argtypes = [C.POINTER(C.c_float), i32, i32, f32, f32, f32, f32, i32, i32, vp, vp]
     lib.tvm_upsample_grid.argtypes = [vp, i32, i32, i32, vp, i32, i32, vp]
     lib.tvm_tv_loss.argtypes = [vp, i32, i32, i32, f32, vp, vp, vp, vp]
+    lib.tvm_tv_loss_batch.argtypes = [C.POINTER(TvmTvJob), i32, vp, vp]
     lib.tvm_l1_loss.argtypes = [vp, C.c_size_t, f32, vp, vp, vp, vp]
     lib.tvm_vector_diffs.argtypes = [vp, i32, i32, f32, vp, vp, vp, vp]
     lib.tvm_selftest_umma.argtypes = [vp] * 7

@@ -87,6 +87,35 @@ static int transpose(const float* in, float* out, int rows, int cols, cudaStream
   return 0;
 }
 
+// several transposes in ONE launch (the 12 factor grids of a model: a training step packs them after every optimiser step
+// and unpacks their gradients -- 24 launches of a launch-bound step become 2)
+struct TransposeBatch {
+  TvmTransposeJob job[TVM_TRANSPOSE_MAX];
+  int tile_end[TVM_TRANSPOSE_MAX];     // exclusive prefix ends of the jobs' 32x32 tile ranges
+  int n;
+};
+__global__ void __launch_bounds__(256) k_transpose_batch(const TransposeBatch B) {
+  __shared__ float tile[32][33];
+  int t = blockIdx.x, j = 0;
+  while (j < B.n - 1 && t >= B.tile_end[j]) ++j;
+  t -= j ? B.tile_end[j - 1] : 0;
+  const float* __restrict__ in = B.job[j].src;
+  float* __restrict__ out = B.job[j].dst;
+  const int rows = B.job[j].rows, cols = B.job[j].cols;
+  const int sld = B.job[j].src_ld ? B.job[j].src_ld : cols, dld = B.job[j].dst_ld ? B.job[j].dst_ld : rows;
+  const int tiles_x = (cols + 31) / 32;
+  const int bx = (t % tiles_x) * 32, by = (t / tiles_x) * 32;
+  for (int jj = threadIdx.y; jj < 32; jj += blockDim.y) {
+    const int r = by + jj, c = bx + threadIdx.x;
+    if (r < rows && c < cols) tile[jj][threadIdx.x] = in[(size_t)r * sld + c];
+  }
+  __syncthreads();
+  for (int jj = threadIdx.y; jj < 32; jj += blockDim.y) {
+    const int c = bx + jj, r = by + threadIdx.x;
+    if (r < rows && c < cols) out[(size_t)c * dld + r] = tile[threadIdx.x][jj];
+  }
+}
+
 // [out][in] -> [in][out_pad] with zero padding
 __global__ void k_pack_linear(const float* __restrict__ w, int out_c, int in_c, int out_pad, float* __restrict__ t) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -324,5 +353,26 @@ extern "C" int tvm_pack_half(const float* src, size_t n, void* dst, uint32_t fla
   const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 16);
   k_pack_half<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, n, (uint16_t*)dst, mode == TVM_MLP_FP16);
   TVM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tvm_transpose_batch(const TvmTransposeJob* jobs_host, int n_jobs, void* stream) {
+  TVM_REQUIRE(jobs_host && n_jobs > 0, "bad arguments");
+  for (int base = 0; base < n_jobs; base += TVM_TRANSPOSE_MAX) {
+    TransposeBatch B;
+    B.n = std::min(TVM_TRANSPOSE_MAX, n_jobs - base);
+    long long tiles = 0;
+    for (int i = 0; i < B.n; ++i) {
+      const TvmTransposeJob& j = jobs_host[base + i];
+      TVM_REQUIRE(j.src && j.dst && j.rows > 0 && j.cols > 0 && (j.src_ld == 0 || j.src_ld >= j.cols) &&
+                  (j.dst_ld == 0 || j.dst_ld >= j.rows), "bad transpose job %d", base + i);
+      B.job[i] = j;
+      tiles += (long long)((j.rows + 31) / 32) * ((j.cols + 31) / 32);
+      TVM_REQUIRE(tiles < (1ll << 31), "too many tiles");
+      B.tile_end[i] = (int)tiles;
+    }
+    k_transpose_batch<<<(unsigned)tiles, dim3(32, 8), 0, (cudaStream_t)stream>>>(B);
+    TVM_CHECK_CUDA(cudaGetLastError());
+  }
   return 0;
 }

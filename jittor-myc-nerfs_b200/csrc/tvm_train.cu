@@ -7,6 +7,7 @@
 //   k_vector_diffs   vectorDiffs (models/tensoRF.py:177-186): mean |off-diagonal of V V^T|
 //   k_adam_multi     jt.optim.Adam(betas=(0.9, 0.99)).step over every parameter tensor in ONE launch (train.py:187,260-261;
 //                    update rule: assumption A11 of oracle/maintain_oracle.py)
+#include <algorithm>
 #include "tvm_common.cuh"
 
 namespace tvm {
@@ -38,6 +39,37 @@ __global__ void __launch_bounds__(256) k_tv_loss(const float* __restrict__ x, in
     const float c = x[i];
     const float dn = yy + 1 < H ? x[i + W] - c : 0.0f;       // x[y+1] - x[y]
     const float rt = xx + 1 < W ? x[i + 1] - c : 0.0f;       // x[x+1] - x[x]
+    part += scale_h * dn * dn + scale_w * rt * rt;
+    if (grad) {
+      const float up = yy > 0 ? c - x[i - W] : 0.0f;
+      const float lf = xx > 0 ? c - x[i - 1] : 0.0f;
+      grad[i] += 2.0f * (scale_h * (up - dn) + scale_w * (lf - rt));
+    }
+  }
+  const float t = block_sum(part, red);
+  if (threadIdx.x == 0 && loss) atomicAdd(loss, t);
+}
+
+// the TV sweeps of several planes in one launch: blockIdx.y = job
+struct TvBatch {
+  TvmTvJob job[TVM_TV_MAX];
+  float scale_h[TVM_TV_MAX], scale_w[TVM_TV_MAX];
+};
+__global__ void __launch_bounds__(256) k_tv_loss_batch(const TvBatch B, float* __restrict__ loss) {
+  __shared__ float red[8];
+  const TvmTvJob& j = B.job[blockIdx.y];
+  const float* __restrict__ x = j.plane_nchw;
+  float* __restrict__ grad = j.grad_nchw;
+  const int H = j.H, W = j.W;
+  float scale_h = B.scale_h[blockIdx.y], scale_w = B.scale_w[blockIdx.y];
+  if (j.weight_dev) { scale_h *= *j.weight_dev; scale_w *= *j.weight_dev; }
+  const size_t total = (size_t)j.C * H * W;
+  float part = 0.0f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int xx = (int)(i % W), yy = (int)((i / W) % H);
+    const float c = x[i];
+    const float dn = yy + 1 < H ? x[i + W] - c : 0.0f;
+    const float rt = xx + 1 < W ? x[i + 1] - c : 0.0f;
     part += scale_h * dn * dn + scale_w * rt * rt;
     if (grad) {
       const float up = yy > 0 ? c - x[i - W] : 0.0f;
@@ -151,6 +183,25 @@ extern "C" int tvm_tv_loss(const float* plane_nchw, int C, int H, int W, float w
   const double ch = (double)C * (H - 1) * W, cw = (double)C * H * (W - 1);
   const float sh = ch > 0 ? (float)(2.0 * weight / ch) : 0.0f, sw = cw > 0 ? (float)(2.0 * weight / cw) : 0.0f;
   k_tv_loss<<<stream_grid((size_t)C * H * W), 256, 0, (cudaStream_t)stream>>>(plane_nchw, C, H, W, sh, sw, weight_dev, loss_accum, grad_nchw);
+  TVM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tvm_tv_loss_batch(const TvmTvJob* jobs_host, int n_jobs, float* loss_accum, void* stream) {
+  TVM_REQUIRE(jobs_host && n_jobs > 0 && n_jobs <= TVM_TV_MAX, "tvm_tv_loss_batch takes 1..%d planes", TVM_TV_MAX);
+  TvBatch B;
+  size_t largest = 0;
+  for (int i = 0; i < n_jobs; ++i) {
+    const TvmTvJob& j = jobs_host[i];
+    TVM_REQUIRE(j.plane_nchw && j.C > 0 && j.H > 0 && j.W > 0, "bad TV job %d", i);
+    B.job[i] = j;
+    const double ch = (double)j.C * (j.H - 1) * j.W, cw = (double)j.C * j.H * (j.W - 1);
+    B.scale_h[i] = ch > 0 ? (float)(2.0 * j.weight / ch) : 0.0f;
+    B.scale_w[i] = cw > 0 ? (float)(2.0 * j.weight / cw) : 0.0f;
+    largest = std::max(largest, (size_t)j.C * j.H * j.W);
+  }
+  const int gx = std::max(1, stream_grid(largest) / n_jobs);
+  k_tv_loss_batch<<<dim3(gx, n_jobs), 256, 0, (cudaStream_t)stream>>>(B, loss_accum);
   TVM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

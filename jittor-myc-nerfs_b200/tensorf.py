@@ -339,31 +339,32 @@ class TensorVMSplit(MaintainMixin, RegularizerMixin, CheckpointMixin, torch.nn.M
         at = lambda name: C.c_void_p(base + 4 * items[name][0])
         Cd, Ca, F = self.density_n_comp[0], self.app_n_comp[0], self.featureC
         in_c = self.renderModule.in_mlpC
+        jobs = []
         for k in range(3):
             for pref, plist, llist, c in (("d", self.density_plane, self.density_line, Cd),
                                           ("a", self.app_plane, self.app_line, Ca)):
                 p, l = plist[k].detach(), llist[k].detach()
                 assert p.is_contiguous() and l.is_contiguous() and p.dtype == torch.float32
-                L.check(lib.tvm_pack_grid(_ptr(p), c, p.shape[2], p.shape[3], at(f"{pref}p{k}"), st), "tvm_pack_grid")
-                L.check(lib.tvm_pack_grid(_ptr(l), c, l.shape[2], 1, at(f"{pref}l{k}"), st), "tvm_pack_grid")
+                # NCHW [C][H*W] -> channels-last [H*W][C] (tvm_pack_grid), all 12 grids in one launch
+                jobs.append(L.TvmTransposeJob(p.data_ptr(), at(f"{pref}p{k}").value, c, p.shape[2] * p.shape[3]))
+                jobs.append(L.TvmTransposeJob(l.data_ptr(), at(f"{pref}l{k}").value, c, l.shape[2]))
         m = self.renderModule.mlp
-        self._pack_heads(lib, at, items, st)
-        L.check(lib.tvm_pack_linear(_ptr(m[0].weight.detach()), F, in_c, F, at("w1_t"), st), "tvm_pack_linear")
-        L.check(lib.tvm_pack_linear(_ptr(m[2].weight.detach()), F, F, F, at("w2_t"), st), "tvm_pack_linear")
-        n = lambda name: items[name][1]
-        self._packed[items["b1"][0]:items["b1"][0] + F].copy_(m[0].bias.detach())
-        self._packed[items["b2"][0]:items["b2"][0] + F].copy_(m[2].bias.detach())
-        self._packed[items["w3"][0]:items["w3"][0] + 3 * F].copy_(m[4].weight.detach().reshape(-1))
-        self._packed[items["b3"][0]:items["b3"][0] + 3].copy_(m[4].bias.detach())
+        jobs += self._pack_heads(lib, at, items, st)
+        J = L.TvmTransposeJob
+        # Linear [out][in] -> [in][out_pad] (tvm_pack_linear) and the bias / last-layer copies (1-row jobs) ride in the same launch
+        jobs += [J(m[0].weight.data_ptr(), at("w1_t").value, F, in_c, 0, F), J(m[2].weight.data_ptr(), at("w2_t").value, F, F, 0, F),
+                 J(m[0].bias.data_ptr(), at("b1").value, 1, F), J(m[2].bias.data_ptr(), at("b2").value, 1, F),
+                 J(m[4].weight.data_ptr(), at("w3").value, 1, 3 * F), J(m[4].bias.data_ptr(), at("b3").value, 1, 3)]
+        L.check(lib.tvm_transpose_batch((J * len(jobs))(*jobs), len(jobs), st), "tvm_transpose_batch")
         self._packed_versions = versions
         self._packed_grid = grid_key
         self._model_struct = None
         self._tc_stale = True
 
     def _pack_heads(self, lib, at, items, st):
+        """basis_mat [app_dim][3 Ca] -> [3 Ca][32]; returns transpose jobs for the caller's batch."""
         Ca = self.app_n_comp[0]
-        L.check(lib.tvm_pack_linear(_ptr(self.basis_mat.weight.detach()), self.app_dim, 3 * Ca, 32, at("basis_t"), st),
-                "tvm_pack_linear")
+        return [L.TvmTransposeJob(self.basis_mat.weight.data_ptr(), at("basis_t").value, self.app_dim, 3 * Ca, 0, 32)]
 
     def _invalidate_packed(self):
         """Grids were replaced (upsample / shrink): force a re-pack and a fresh TvmModel."""
@@ -511,26 +512,30 @@ class TensorVMSplit(MaintainMixin, RegularizerMixin, CheckpointMixin, torch.nn.M
         at = lambda name: C.c_void_p(base + 4 * items[name][0])
         Cd, Ca, F = self.density_n_comp[0], self.app_n_comp[0], self.featureC
         in_c = self.renderModule.in_mlpC
-        out = {}
+        out, jobs = {}, []
         for k in range(3):
             for pref, plist, llist, c in (("d", self.density_plane, self.density_line, Cd),
                                           ("a", self.app_plane, self.app_line, Ca)):
                 gpl, gl = torch.empty_like(plist[k]), torch.empty_like(llist[k])
-                L.check(lib.tvm_unpack_grid(at(f"{pref}p{k}"), c, gpl.shape[2], gpl.shape[3], _ptr(gpl), st),
-                        "tvm_unpack_grid")
-                L.check(lib.tvm_unpack_grid(at(f"{pref}l{k}"), c, gl.shape[2], 1, _ptr(gl), st), "tvm_unpack_grid")
+                # channels-last [H*W][C] -> NCHW [C][H*W] (tvm_unpack_grid), all 12 gradients in one launch
+                jobs.append(L.TvmTransposeJob(at(f"{pref}p{k}").value, gpl.data_ptr(), gpl.shape[2] * gpl.shape[3], c))
+                jobs.append(L.TvmTransposeJob(at(f"{pref}l{k}").value, gl.data_ptr(), gl.shape[2], c))
                 out[f"{pref}p{k}"], out[f"{pref}l{k}"] = gpl, gl
         m = self.renderModule.mlp
+        J = L.TvmTransposeJob
         g_basis = torch.empty_like(self.basis_mat.weight)
         g_w1, g_w2 = torch.empty_like(m[0].weight), torch.empty_like(m[2].weight)
-        L.check(lib.tvm_unpack_linear(at("basis_t"), self.app_dim, 3 * Ca, self.head_dim(), _ptr(g_basis), st), "tvm_unpack_linear")
-        L.check(lib.tvm_unpack_linear(at("w1_t"), F, in_c, F, _ptr(g_w1), st), "tvm_unpack_linear")
-        L.check(lib.tvm_unpack_linear(at("w2_t"), F, F, F, _ptr(g_w2), st), "tvm_unpack_linear")
-        sl = lambda name, n: gp[items[name][0]:items[name][0] + n].clone()
+        g_b1, g_b2 = torch.empty_like(m[0].bias), torch.empty_like(m[2].bias)
+        g_w3, g_b3 = torch.empty_like(m[4].weight), torch.empty_like(m[4].bias)
+        # [in][out_pad] -> [out][in] (tvm_unpack_linear) and the bias / last-layer slices, in the same launch as the grids
+        jobs += [J(at("basis_t").value, g_basis.data_ptr(), 3 * Ca, self.app_dim, self.head_dim(), 0),
+                 J(at("w1_t").value, g_w1.data_ptr(), in_c, F, F, 0), J(at("w2_t").value, g_w2.data_ptr(), F, F, F, 0),
+                 J(at("b1").value, g_b1.data_ptr(), 1, F), J(at("b2").value, g_b2.data_ptr(), 1, F),
+                 J(at("w3").value, g_w3.data_ptr(), 1, 3 * F), J(at("b3").value, g_b3.data_ptr(), 1, 3)]
+        L.check(lib.tvm_transpose_batch((J * len(jobs))(*jobs), len(jobs), st), "tvm_transpose_batch")
         return [*(out[f"dp{k}"] for k in range(3)), *(out[f"dl{k}"] for k in range(3)),
                 *(out[f"ap{k}"] for k in range(3)), *(out[f"al{k}"] for k in range(3)), g_basis,
-                g_w1, sl("b1", F), g_w2, sl("b2", F), sl("w3", 3 * F).reshape(3, F), sl("b3", 3),
-                *self._unpack_head_grads(gp, items)]
+                g_w1, g_b1, g_w2, g_b2, g_w3, g_b3, *self._unpack_head_grads(gp, items)]
 
     def _unpack_head_grads(self, gp, items):
         """Gradients of the parameters `_param_list` appends after the MLP (none for TensorVMSplit)."""
@@ -657,6 +662,7 @@ class REFTensoRF(TensorVMSplit):
         off = items["head_bias"][0]
         self._packed[off:off + 64].zero_()
         self._packed[off:off + b.numel()].copy_(b)
+        return []
 
     def _unpack_head_grads(self, gp, items):
         """[3*Ca][48] packed head gradients -> normal / diffuse / specular / rho weights and biases (order of _param_list)."""

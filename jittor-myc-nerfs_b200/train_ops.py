@@ -240,12 +240,15 @@ class TrainStepGraph:
         reg = self.reg_loss
         reg.zero_()
         w = self._w_dev
-        if self.use["tv_d"]:
-            for p in m.density_plane:
-                _launch("tv", p.detach(), 1e-2, reg, p.grad, w[0:1])
-        if self.use["tv_a"]:
-            for p in m.app_plane:
-                _launch("tv", p.detach(), 1e-2, reg, p.grad, w[1:2])
+        tv_jobs = []
+        for on, planes, wd in ((self.use["tv_d"], m.density_plane, w[0:1]), (self.use["tv_a"], m.app_plane, w[1:2])):
+            if on:
+                for p in planes:
+                    _, Cc, H, W = p.shape
+                    tv_jobs.append(L.TvmTvJob(p.data_ptr(), p.grad.data_ptr(), Cc, H, W, 1e-2, wd.data_ptr()))
+        if tv_jobs:        # all TV sweeps of the step in one launch
+            L.check(lib.tvm_tv_loss_batch((L.TvmTvJob * len(tv_jobs))(*tv_jobs), len(tv_jobs), _ptr(reg), _stream_ptr()),
+                    "tvm_tv_loss_batch")
         if self.use["l1"]:
             for p in [*m.density_plane, *m.density_line]:
                 _launch("l1", p.detach(), 1.0, reg, p.grad, w[2:3])
