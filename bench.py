@@ -181,7 +181,7 @@ def run_reference(args):
                              "sample": desc},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 def run_maintain(args):
@@ -263,7 +263,7 @@ def run_maintain(args):
         m128.upsample_volume_grid((G, G, G))
     ms = timed(up_fresh)
     row("upsample_volume_grid_128_to_%d" % G, ms, (nd + na) * 4.0 + 3 * 64 * 128 * 128 * 4.0, "write new planes + read old ones")
-    print(json.dumps({"metric": "SURVEY 8f rows, device ms per call", "unit": "ms", "n_gpus": 1, "steps": args.steps,
+    emit(({"metric": "SURVEY 8f rows, device ms per call", "unit": "ms", "n_gpus": 1, "steps": args.steps,
                       "config": {"workload": f"maintain: {G}^3 grids, {MASK_RES}^3 alpha lattice, {FRAME}x{FRAME} frame",
                                  "l2": "flushed before every timed call"}, "hbm_peak_GBps": hbm, "rows": rows}))
 
@@ -412,7 +412,7 @@ def run_side_workload(args):
         line["roofline"] = {"bound": "tensor", "kernel": "k_bg_tc", "achieved": tf, "peak": peak, "unit": "TFLOP/s",
                             "frac": tf / peak, "traffic": None, "flop_per_sample_issued": flop}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         # NCCL communicators referenced by a captured CUDA graph cannot be torn down cleanly: release the graph, drain the
         # device, and leave without destroy_process_group (it blocks forever otherwise; measured on 2 x B200)
@@ -424,11 +424,25 @@ def run_side_workload(args):
         os._exit(0)
 
 
+_JSON_OUT = None
+
+
+def emit(line):
+    """The ONE JSON line, on the process's original stdout."""
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    global _JSON_OUT
     args = parse()
-    # stdout carries the ONE JSON line: NCCL's own banner ("NCCL version ...", printed when the box exports
-    # NCCL_DEBUG=VERSION) goes to stderr
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    # stdout carries the ONE JSON line and nothing else: keep a handle on the original stdout for it and point fd 1 at stderr,
+    # so that whatever a library prints there (e.g. NCCL's "NCCL version ..." banner, a plain printf when the box exports
+    # NCCL_DEBUG=VERSION) cannot get in front of it
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if os.environ.get("BENCH_WATCHDOG"):
         # debugging aid: dump every thread's stack and exit if the run is still alive after N seconds
         import faulthandler
@@ -611,7 +625,7 @@ def main():
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                                     "sample": desc + f" ({dt:.1f} s)", "note": "oracle restatement of the reference "
                                     "(torch CPU, reference op sequence); Jittor itself is absent from the image"}
-        print(json.dumps(line))
+        emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
