@@ -291,8 +291,13 @@ def run_side_workload(args):
     model = pkg.model_from_params(mp, f"cuda:{local_rank}", vol, mp.aabb.copy(), args.mlp)
     if train:
         n = 4096 if args.rays == FRAME * FRAME else args.rays
-        rays_np = fx.subset_rays(n, azimuth=0.7 + rank * np.pi / 4)     # weak scaling: 4096 rays per rank, one NCCL all-reduce
-        model.grad_sync = world > 1                                     # of the flat gradient buffer per step
+        # weak scaling, 4096 rays per rank: the ranks slice ONE seeded global permutation of an 8-view ray pool, as the
+        # reference's identically seeded SimpleSampler would hand them out -- every rank sees the same ray
+        # distribution; one NCCL all-reduce of the flat gradient buffer per step
+        pool = np.concatenate([fx.subset_rays(n, azimuth=0.7 + v * np.pi / 4) for v in range(8)])
+        perm = np.random.default_rng(fx.SEED_BASE + 7).permutation(pool.shape[0])
+        rays_np = pool[perm[rank * n:(rank + 1) * n]] if world <= 8 else pool[perm[(rank % 8) * n:(rank % 8 + 1) * n]]
+        model.grad_sync = world > 1
         S = int(np.linalg.norm(np.asarray(mp.gridSize, dtype=np.float64)) / mp.step_ratio)     # cal_n_samples, utils.py:61-62
         tgt = torch.from_numpy(fx.target_rgb(n)).to(dev)
         jit = torch.from_numpy(fx.jitter(n)).to(dev)
