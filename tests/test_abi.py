@@ -29,7 +29,8 @@ def test_abi_version_and_struct_sizes(built_lib):
     probe = r'''
 #include <stdio.h>
 #include "tvmrender.h"
-int main(){ printf("%zu %zu %zu\n", sizeof(TvmModel), sizeof(TvmAux), sizeof(TvmGrads)); return 0; }
+int main(){ printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(TvmModel), sizeof(TvmAux), sizeof(TvmGrads), sizeof(TvmBgNet),
+                   sizeof(TvmBgGrads), sizeof(TvmTransposeJob), sizeof(TvmTvJob), sizeof(TvmAdamTensor)); return 0; }
 '''
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "p.c"), "w").write(probe)
@@ -37,7 +38,8 @@ int main(){ printf("%zu %zu %zu\n", sizeof(TvmModel), sizeof(TvmAux), sizeof(Tvm
                                os.path.join(d, "p.c")])
         out = subprocess.check_output([os.path.join(d, "p")]).split()
     L = built_lib._lib
-    assert [int(x) for x in out] == [ctypes.sizeof(L.TvmModel), ctypes.sizeof(L.TvmAux), ctypes.sizeof(L.TvmGrads)]
+    assert [int(x) for x in out] == [ctypes.sizeof(t) for t in (L.TvmModel, L.TvmAux, L.TvmGrads, L.TvmBgNet, L.TvmBgGrads,
+                                                                  L.TvmTransposeJob, L.TvmTvJob, L.TvmAdamTensor)]
 
 
 def test_fails_loudly_without_gpu(built_lib):
