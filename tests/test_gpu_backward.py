@@ -303,3 +303,33 @@ def test_nerfplusplus_backward(env, regime, G, S):
     for name, p in [(k, v) for k, v in m16.named_parameters() if k.startswith("bg_net.")]:
         g, r = p.grad.detach().cpu().numpy().astype(np.float64), ref["grads"][name]
         assert np.linalg.norm(g - r) <= 5e-2 * np.linalg.norm(r), name
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cd,ca,app_dim,view_pe,fea_pe", [(8, 24, 27, 2, 2), (4, 12, 9, 3, 1), (32, 16, 16, 0, 2)])
+def test_generic_shapes_forward_and_backward(env, cd, ca, app_dim, view_pe, fea_pe):
+    """Channel counts / head sizes other than the shipped 16 / 48 / 27 / pe 2 (the class defaults of TensorVMSplit are 8 / 24):
+    the non-specialised instantiations (k_march<.., CD=0>, generic channel loops of the fp32 head and of both backward
+    kernels) against the oracle; the tensor-core head refuses them loudly."""
+    pkg, torch, fx, orc = env
+    from util import gpu_model
+    case = fx.make_case(40, 256, "R2", mask_res=40, train=True, cd=cd, ca=ca, app_dim=app_dim, view_pe=view_pe, fea_pe=fea_pe)
+    S = 139
+    d_rgb = (fx.target_rgb(256, seed=5) - 0.5).astype(np.float32)
+    ref_f = orc.run_case(case, N_samples=S)
+    ref = orc.backward_case(case, d_rgb_map=d_rgb.astype(np.float64), N_samples=S, white_bg=True)
+    model = gpu_model(pkg, case)
+    rays = torch.from_numpy(case["rays"]).cuda()
+    jit = torch.from_numpy(case["jitter"]).cuda()
+    out = model.forward_with_aux(rays, white_bg=True, N_samples=S, jitter=jit)
+    assert np.array_equal(pkg.unpack_bits(out["valid_bits"], S), ref_f["ray_valid"])
+    assert np.abs(out["rgb_map"].cpu().numpy() - ref_f["rgb_map"]).max() <= 1e-4
+    rgb, _ = model(rays, is_train=True, white_bg=True, N_samples=S, jitter=jit)
+    (rgb * torch.from_numpy(d_rgb).cuda()).sum().backward()
+    torch.cuda.synchronize()
+    worst = _compare(model, ref["grads"])
+    print(f"generic shapes cd={cd} ca={ca} app_dim={app_dim} pe=({view_pe},{fea_pe}): worst grad", max(worst.values()))
+    model.mlp_mode = "bf16"
+    with pytest.raises(pkg.TvmError):
+        with torch.no_grad():
+            model(rays, white_bg=True, N_samples=S)
