@@ -397,3 +397,35 @@ def test_full_frame_properties(env):
     assert err <= 1e-2 and ps >= 60.0
     assert e32 <= 1e-4 and e16 <= 1e-2
     assert np.abs(dep32[sl].cpu().numpy() - ref["depth_map"]).max() <= 1e-3
+
+
+def test_no_write_outside_caller_buffers(env):
+    """Canaries around the caller-owned buffers (workspace, rgb_map, depth_map): the kernels write nothing outside the sizes
+    tvm_workspace_bytes / the signatures promise, for ragged ray counts and sample counts that are not multiples of 32
+    (compute-sanitizer is not available on this pool)."""
+    pkg, torch, fx, orc = env
+    from util import gpu_model
+    for n, S, mode, variant in ((1, 33, "fp32", None), (777, 139, "bf16", None), (1025, 64, "fp16", None), (130, 97, "bf16", "ref")):
+        kw = dict(variant=variant) if variant else {}
+        case = fx.make_case(40, n, "R2", mask_res=40, train=True, **kw)
+        model = gpu_model(pkg, case, mlp_mode=mode)
+        model.app_planes_bf16 = mode != "fp32"
+        need = model.workspace_bytes(n, S)
+        pad = 1 << 16
+        ws = torch.full((need + pad,), 0xA5, dtype=torch.uint8, device="cuda")
+        model._ws = ws
+        out = torch.full((n * 4 + 64,), float("nan"), dtype=torch.float32, device="cuda")
+        rgb, depth = out[16:16 + 3 * n].view(n, 3), out[32 + 3 * n:32 + 4 * n]
+        rays = torch.from_numpy(case["rays"]).cuda()
+        jit = torch.from_numpy(case["jitter"]).cuda()
+        model._forward_raw(rays, jit, model._flags(True), S, out=(rgb, depth))
+        torch.cuda.synchronize()
+        assert model._ws is ws
+        assert bool((ws[need:] == 0xA5).all()), (n, S, mode)
+        assert bool(torch.isnan(out[:16]).all() and torch.isnan(out[16 + 3 * n:32 + 3 * n]).all() and torch.isnan(out[32 + 4 * n:]).all())
+        assert bool(torch.isfinite(rgb).all() and torch.isfinite(depth).all())
+        # ... and the backward pass on the same workspace
+        d_rgb = torch.ones_like(rgb)
+        model._backward_raw(rays, jit, model._flags(True), S, rgb.contiguous(), d_rgb)
+        torch.cuda.synchronize()
+        assert bool((ws[need:] == 0xA5).all()), ("backward", n, S, mode)
