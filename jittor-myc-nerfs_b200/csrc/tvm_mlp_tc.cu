@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(kThreadsV2, 1) k_app_tc(const FwdParams P) {
         const uint32_t e = tile_base + row;
         uint8_t* arow = stage + row * 16;
         if (e < n_ent) {
-          const float4 uw = __ldg(P.ws.ent_u + e);       // written by k_march with the coordinates it marched
+          const float4 uw = __ldcs(P.ws.ent_u + e);      // written by k_march with the coordinates it marched; read once: evict-first
           const float u[3] = {uw.x, uw.y, uw.z};
           if (PB16) {
             AxisPair ax[3];
