@@ -94,7 +94,7 @@ def test_mse_training_step(env):
 @pytest.mark.parametrize("regime,white_bg", [("R2", True), ("R1", False)])
 def test_backward_tensor_core_bf16(env, regime, white_bg):
     """k_app_bwd_tc: appearance backward on tcgen05 (bf16 operands, fp32 accumulation).  north_star states 1e-2 for the
-    colours of the bf16 MLP mode and nothing for its gradients.  Measured on B200 (scripts/dbg_bwd_tc.py): density grids
+    colours of the bf16 MLP mode and nothing for its gradients.  Measured on B200: density grids
     1.6e-4, last layer 2e-3, hidden layers / basis / appearance grids 1.7-3.6e-2 relative L2 -- the latter is dominated by
     ReLU units whose bf16 pre-activation changes sign against fp64 (the usual mixed-precision effect), not by rounding
     of the products (sparse regime R1: up to 5.1e-2).  Bounds: 0.15 of the largest entry element-wise, 8e-2 relative L2; the fp32 kernels stay the
