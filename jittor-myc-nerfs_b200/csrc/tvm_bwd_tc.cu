@@ -134,9 +134,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_app_bwd_tc(const BwdParams Bp) 
         const uint32_t e = tile_base + row;
         uint8_t* arow = sH + row * 16;
         if (e < n_ent) {
-          const uint2 en = P.ws.ent[e];
-          float u[3], dd[3];
-          entry_coords(m, P.rays, P.jitter, en.x, en.y, P.S, u, dd);
+          const float4 uw = __ldg(P.ws.ent_u + e);      // grid coordinates stored by k_march (the forward's workspace)
+          const float u[3] = {uw.x, uw.y, uw.z};
           Axis ax[3];
 #pragma unroll
           for (int i = 0; i < 3; ++i) ax[i] = axis_taps(u[i], m.grid[i]);
@@ -542,9 +541,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_app_bwd_tc(const BwdParams Bp) 
       for (int grow = warp * 8 + (lane >> 2); grow < kRows; grow += (kThreads / 32) * 8) {
         const uint32_t ge = tile_base + grow;
         if (ge >= n_ent) continue;
-        const uint2 en = P.ws.ent[ge];
-        float u[3], dd[3];
-        entry_coords(m, P.rays, P.jitter, en.x, en.y, P.S, u, dd);
+        const float4 uw = __ldg(P.ws.ent_u + ge);
+        const float u[3] = {uw.x, uw.y, uw.z};
         Axis ax[3];
 #pragma unroll
         for (int i = 0; i < 3; ++i) ax[i] = axis_taps(u[i], m.grid[i]);
