@@ -380,7 +380,8 @@ def run_side_workload(args):
     line = {"metric": f"TensoRF-VM rays/sec ({args.workload})", "value": n * world / (ms / args.steps * 1e-3), "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if args.mlp == "fp32" else (f"f32 + {args.mlp} tensor-core MLP" + (" (forward and backward)" if train and args.mlp == "bf16" else "")), "data": "synthetic",
+            "dtype": "f32" if args.mlp == "fp32" else (f"f32 + {args.mlp} tensor-core MLP" + (" (forward and backward)" if train and args.mlp == "bf16" else
+                                                                     " (forward; bf16 tensor-core backward)" if train and args.mlp == "fp16" else "")), "data": "synthetic",
             "config": {"workload": name + f", regime {args.regime}", "n_samples": S,
                        "l2": "flushed before every timed step (256 MiB write)",
                        "per_step_counts": {"M_in": cnt[L.CNT_M_IN], "M_v_gathered": cnt[L.CNT_M_V], "M_a": cnt[L.CNT_M_A],

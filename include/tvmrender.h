@@ -33,15 +33,16 @@
 extern "C" {
 #endif
 
-#define TVM_ABI_VERSION 18
+#define TVM_ABI_VERSION 19
 
 /* flags for tvm_forward / tvm_backward */
 #define TVM_WHITE_BG      0x1u  /* rgb_map += 1 - acc_map          (tensorBase.py:523-524) */
 #define TVM_NO_ERT        0x2u  /* disable early ray termination (march every in-box sample) */
 #define TVM_MLP_FP32      0x0u  /* appearance head in fp32 FMA (parity 1e-4)                */
 #define TVM_MLP_BF16      0x10u /* appearance head on tcgen05 tensor cores, bf16 x bf16 -> fp32 (parity 1e-2) */
-#define TVM_MLP_FP16      0x20u /* tcgen05, fp16 x fp16 -> fp32: 11-bit operands, forward only (the backward of this mode is
-                                  the fp32 one); measured 2e-5 from the oracle, i.e. inside the fp32 tolerance 1e-4       */
+#define TVM_MLP_FP16      0x20u /* tcgen05, fp16 x fp16 -> fp32: 11-bit operands; measured 2e-5 from the oracle, i.e. inside the
+                                  fp32 tolerance 1e-4.  Its backward is the bf16 tensor-core one when TvmModel.tc_weights_bwd
+                                  is given, else the fp32 one                                                            */
 #define TVM_MLP_MASK      0x30u
 
 /* model variant */
@@ -115,6 +116,9 @@ typedef struct TvmModel {
    * plane texels from them (half the gather bytes; the plane x line products are rounded to that format as the GEMM
    * operand anyway).  TVM_MLP_FP32 and every backward kernel ignore them.                                          */
   const void* app_plane_bf16[3];
+  /* optional second operand image for tvm_backward, packed by tvm_pack_mlp_tc with TVM_MLP_BF16 (NULL = none): lets a
+   * TVM_MLP_FP16 step (fp16 forward, inside the fp32 tolerance) take the tensor-core backward, whose operands are bf16 */
+  const void* tc_weights_bwd;
 } TvmModel;
 
 /* NerfPlusPlus background network (nerfplusplus.py:66-140 with bg_D=3, W=128, skips=[1], bg_freq=2,

@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # TVM_LIB: developer override (kernel-tuning experiments build variant libraries next to the default one)
 LIB_PATH = os.environ.get("TVM_LIB") or os.path.join(_HERE, "libtvmrender.so")
-ABI_VERSION = 18
+ABI_VERSION = 19
 
 # flags (tvmrender.h)
 WHITE_BG = 0x1
@@ -45,7 +45,7 @@ class TvmModel(C.Structure):
         ("b2", C.c_void_p), ("w3", C.c_void_p), ("b3", C.c_void_p),
         ("alpha_bits", C.c_void_p), ("alpha_grid", _i3), ("alpha_aabb_min", _f3), ("alpha_inv_size", _f3),
         ("alpha_bricks", C.c_void_p), ("alpha_dilated", C.c_void_p), ("tc_weights", C.c_void_p), ("sampling", C.c_int32), ("radii", C.c_float),
-        ("app_plane_bf16", _p3),
+        ("app_plane_bf16", _p3), ("tc_weights_bwd", C.c_void_p),
     ]
 
 

@@ -516,7 +516,7 @@ static int backward_impl(const TvmModel* m_host, const TvmBgNet* bg_host, const 
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if ((flags & TVM_MLP_MASK) == TVM_MLP_BF16) {
+  if ((flags & TVM_MLP_MASK) == TVM_MLP_BF16 || ((flags & TVM_MLP_MASK) == TVM_MLP_FP16 && m_host->tc_weights_bwd)) {
     // appearance backward on the tensor cores (bf16 operands, fp32 accumulation; gradients to ~1e-2 relative)
     ProfileScope prof(TVM_STAGE_BWD_APP, stream);
     if (int rc = launch_app_bwd_tc(B, sms, stream)) return rc;

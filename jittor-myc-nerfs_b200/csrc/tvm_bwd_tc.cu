@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_app_bwd_tc(const BwdParams Bp) 
   uint8_t* sG2 = sY1 + kRows * 128 * 2;                  // [128 x 128] bf16: Y2, later G2
   uint64_t* mma_bar = reinterpret_cast<uint64_t*>(sG2 + kRows * 128 * 2);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
-  const float* sB1 = REF ? reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(m.tc_weights) + img.off_f32)
+  const float* sB1 = REF ? reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(m.tc_weights_bwd ? m.tc_weights_bwd : m.tc_weights) + img.off_f32)
                          : reinterpret_cast<const float*>(sW + img.off_f32);
   const float* sB2 = sB1 + 128;
   const float* sW3 = sB2 + 128;
@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_app_bwd_tc(const BwdParams Bp) 
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   {
-    const uint4* src = reinterpret_cast<const uint4*>(m.tc_weights);
+    const uint4* src = reinterpret_cast<const uint4*>(m.tc_weights_bwd ? m.tc_weights_bwd : m.tc_weights);   // bf16 image
     uint4* dst = reinterpret_cast<uint4*>(sW);
     for (uint32_t i = tid; i < w_bytes / 16; i += kThreads) dst[i] = __ldg(src + i);
   }
@@ -626,7 +626,7 @@ int launch_app_bwd_tc(const BwdParams& B, int num_sms, cudaStream_t stream) {
   const TvmModel& m = B.f.m;
   TVM_REQUIRE(m.n_app == CA && m.app_dim == APP_DIM && m.fea_pe == 2 && m.view_pe == 2 &&
               m.feature_c == 128, "tensor-core appearance backward supports n_app=48, app_dim=27, fea_pe=view_pe=2, featureC=128");
-  TVM_REQUIRE(m.tc_weights != nullptr, "TvmModel.tc_weights is NULL: call tvm_pack_mlp_tc first");
+  TVM_REQUIRE(m.tc_weights != nullptr || m.tc_weights_bwd != nullptr, "TvmModel.tc_weights is NULL: call tvm_pack_mlp_tc first");
   const bool ref = m.variant == TVM_VARIANT_REF;
   const tc::Image img(CA, in_mlp_c(m), head_ld(m));
   const uint32_t w_bytes = ref ? img.off_f32 : img.bytes;

@@ -408,6 +408,7 @@ class TensorVMSplit(MaintainMixin, RegularizerMixin, CheckpointMixin, torch.nn.M
             s.alpha_bricks = None
             s.alpha_dilated = None
         s.tc_weights = None
+        s.tc_weights_bwd = None
         if self.mlp_mode != "fp32":
             lib = L.load()
             nbytes = lib.tvm_tc_weights_bytes(C.byref(s))
@@ -417,6 +418,12 @@ class TensorVMSplit(MaintainMixin, RegularizerMixin, CheckpointMixin, torch.nn.M
                 self._tc = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
             L.check(lib.tvm_pack_mlp_tc(C.byref(s), _ptr(self._tc), _MLP_FLAGS[self.mlp_mode], _stream_ptr()), "tvm_pack_mlp_tc")
             s.tc_weights = self._tc.data_ptr()
+            if self.mlp_mode == "fp16":
+                # fp16 forward, bf16 tensor-core backward: the backward kernel reads its own bf16 operand image
+                if getattr(self, "_tc_bwd", None) is None or self._tc_bwd.numel() < nbytes:
+                    self._tc_bwd = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+                L.check(lib.tvm_pack_mlp_tc(C.byref(s), _ptr(self._tc_bwd), L.MLP_BF16, _stream_ptr()), "tvm_pack_mlp_tc")
+                s.tc_weights_bwd = self._tc_bwd.data_ptr()
             self._tc_stale = False
         for k in range(3):
             s.app_plane_bf16[k] = None
@@ -621,7 +628,7 @@ class TensorVMSplit(MaintainMixin, RegularizerMixin, CheckpointMixin, torch.nn.M
 class REFTensoRF(TensorVMSplit):
     """REFTensoRF (models/REFTensoRF.py:64-256): normal / diffuse / specular-tint / rho heads on the
     144-vector, reflected direction into MLPRender_Fea_Ref, side output `penalty` (train.py:253-257).
-    The backward pass of this variant runs in fp32 (k_app_bwd<48>) whatever mlp_mode the forward used."""
+    Backward: k_app_bwd<48> (fp32) or k_app_bwd_tc<REF> (tensor cores, bf16 / fp16 modes)."""
     VARIANT = L.VARIANT_REF
 
     def init_render_func(self, shadingMode, pos_pe, view_pe, fea_pe, featureC, device):
