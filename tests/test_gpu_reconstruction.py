@@ -12,7 +12,7 @@ sys.path.insert(0, os.path.join(ROOT, "examples"))
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mlp_mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("mlp_mode", ["fp32", "bf16", "fp16"])
 def test_coarse_to_fine_reconstruction(tmp_path, mlp_mode):
     import torch
     import reconstruct_synthetic as ex
