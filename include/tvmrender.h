@@ -42,7 +42,8 @@ extern "C" {
 #define TVM_MLP_BF16      0x10u /* appearance head on tcgen05 tensor cores, bf16 x bf16 -> fp32 (parity 1e-2) */
 #define TVM_MLP_FP16      0x20u /* tcgen05, fp16 x fp16 -> fp32: 11-bit operands; measured 2e-5 from the oracle, i.e. inside the
                                   fp32 tolerance 1e-4.  Its backward is the bf16 tensor-core one when TvmModel.tc_weights_bwd
-                                  is given, else the fp32 one                                                            */
+                                  is given, else the fp32 one.  fp16 saturates at 65504: a model whose activations or
+                                  features exceed that needs TVM_MLP_BF16 (same kernels, 8-bit mantissa, fp32 range)          */
 #define TVM_MLP_MASK      0x30u
 
 /* model variant */
