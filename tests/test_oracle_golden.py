@@ -55,3 +55,40 @@ def test_oracle_matches_reference_python(path):
     assert np.abs(r["bg_weight"] - g["bg_weight"]).max() <= 1e-6
     if "penalty" in g.files and float(g["penalty"]) != 0:
         assert abs(r["penalty"] - float(g["penalty"])) <= 1e-5 * max(1.0, abs(float(g["penalty"])))
+
+
+GRAD_GOLD = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "grad_*.npz")))
+
+
+@pytest.mark.parametrize("path", GRAD_GOLD, ids=[os.path.basename(p)[:-4] for p in GRAD_GOLD])
+def test_oracle_gradients_match_reference_python(path):
+    """tests/golden/make_golden_grads.py: the reference's unmodified python differentiated by torch autograd over the shim.
+    The oracle's backward_case (what every GPU gradient test is checked against) must give the same gradients for every
+    parameter the reference attaches -- including the density gradient NerfPlusPlus receives through bg_lambda."""
+    assert len(GRAD_GOLD) >= 3
+    g = np.load(path)
+    G, n, regime, mask_res, white_bg, S, variant, pw = [str(x) for x in g["args"]]
+    case = fx.make_case(ast.literal_eval(G), int(n), regime, mask_res=ast.literal_eval(mask_res), train=True, variant=variant)
+    if variant == "npp":
+        case["fg_rand"], case["bg_rand"] = fx.npp_rand(int(n), int(S))
+    d_rgb = (fx.target_rgb(int(n), seed=13) - 0.5).astype(np.float32)
+    import torch
+    r = orc.backward_case(case, d_rgb_map=d_rgb.astype(np.float64), dtype=torch.float64, N_samples=int(S),
+                          white_bg=(white_bg == "True"), penalty_weight=float(pw))
+    assert np.abs(r["rgb_map"] - g["rgb_map"]).max() <= 1e-5
+    names = [k[5:] for k in g.files if k.startswith("grad:")]
+    assert len(names) >= 19
+    worst = {}
+    for k in names:
+        ref, got = g["grad:" + k].astype(np.float64), r["grads"][k]
+        scale = np.abs(ref).max()
+        if scale == 0:
+            assert np.abs(got).max() == 0, k
+            continue
+        worst[k] = np.abs(got - ref).max() / scale
+    # the golden gradients are fp32 (reference python over torch), the oracle runs in fp64
+    bad = {k: v for k, v in worst.items() if v > 2e-4}
+    assert not bad, bad
+    # every parameter the oracle differentiates is attached in the reference as well (nothing extra, nothing missing)
+    extra = [k for k, v in r["grads"].items() if k not in names and np.abs(v).max() > 0]
+    assert not extra, extra
