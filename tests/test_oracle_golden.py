@@ -11,7 +11,7 @@ import pytest
 from oracle import fixtures as fx, tensorf_oracle as orc
 
 GOLD = sorted(p for p in glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "*.npz"))
-              if not os.path.basename(p).startswith("maint_"))
+              if not os.path.basename(p).startswith(("maint_", "grad_")))
 
 
 def load_case(path):
