@@ -279,10 +279,13 @@ __global__ void __launch_bounds__(256) k_composite(const FwdParams P) {
   // lanes read the block table 32 blocks at a time; each non-empty block is then summed by the whole warp (lane = sample):
   // one round trip per block instead of one per entry; the lane sums meet in warp_sum's fixed tree, so the result does not
   // depend on chunking or launch order
+  const uint32_t* __restrict__ row_mask = P.ws.blk_mask + (size_t)ray * P.NB;
+  uint32_t nxt_bits = lane < P.NB ? __ldcs(row_mask + lane) : 0u;          // the table is read once: evict-first
   for (int b0 = 0; b0 < P.NB; b0 += 32) {
     const int bl = b0 + lane;
-    const uint32_t my_bits = bl < P.NB ? P.ws.blk_mask[(size_t)ray * P.NB + bl] : 0u;
-    const uint32_t my_base = my_bits ? P.ws.blk_base[(size_t)ray * P.NB + bl] : 0u;
+    const uint32_t my_bits = nxt_bits;
+    if (b0 + 32 < P.NB) nxt_bits = bl + 32 < P.NB ? __ldcs(row_mask + bl + 32) : 0u;   // next round under this one's work
+    const uint32_t my_base = my_bits ? __ldcs(P.ws.blk_base + (size_t)ray * P.NB + bl) : 0u;
     uint32_t todo = __ballot_sync(0xffffffffu, my_bits != 0u);
     while (todo) {
       const int src = __ffs(todo) - 1;
