@@ -197,7 +197,7 @@ class TensorVMSplit(MaintainMixin, RegularizerMixin, CheckpointMixin, torch.nn.M
         self.empty_space_skipping = True
         self.collect_counters = False
         self.counters = torch.zeros(L.CNT_WORDS, dtype=torch.int64, device=device)
-        self.ws_budget_bytes = int(float(os.environ.get("TVM_WS_GIB", "8")) * (1 << 30))
+        self.ws_budget_bytes = int(float(os.environ.get("TVM_WS_GIB", "32")) * (1 << 30))   # one launch per 800x800 frame (29 GB of the 180 GB)
         self.grad_sync = False          # set True (after dist.init_from_env) for data-parallel training
         self.grad_sync_group = None
         self._ws = None
