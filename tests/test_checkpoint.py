@@ -85,3 +85,21 @@ def test_save_load_renders_identically(tmp_path, variant):
         rgb1, dep1 = m2(rays, white_bg=variant != "npp", **kw_render)
     assert torch.equal(rgb0, rgb1) and torch.equal(dep0, dep1)
     assert set(ckpt["state_dict"]) == set(model.state_dict())
+
+
+def test_driver_helpers_match_survey_values():
+    """utils.N_to_reso / cal_n_samples (tensorf-myc/utils.py:56-62) at the shipped configs' sizes (SURVEY.md §8 shape table)
+    and SimpleSampler's permutation refresh (train.py:25-37)."""
+    import torch
+    from jittor_myc_nerfs_b200.utils import N_to_reso, cal_n_samples, SimpleSampler
+    bbox = torch.tensor([[-5.0, -5.0, -5.0], [5.0, 5.0, 5.0]])
+    assert N_to_reso(2097156, bbox) == [128, 128, 128]            # configs/Scar.txt: N_voxel_init
+    assert N_to_reso(27000000, bbox) in ([300, 300, 300], [299, 299, 299])   # fp32: the schedule's last step evaluates to 299^3
+    assert cal_n_samples([128, 128, 128], 0.5) == 443 and cal_n_samples([300, 300, 300], 0.5) == 1039
+    coffee = torch.tensor([[-0.2350, -1.7393, -1.5537], [0.2350, 2.0214, 1.4530]])     # configs/Coffee.txt: non-cubic grid
+    r = N_to_reso(2097156, coffee)
+    assert r[0] < r[2] < r[1] and abs(r[0] * r[1] * r[2] - 2097156) / 2097156 < 0.05
+    s = SimpleSampler(10, 4, seed=0)
+    ids = [s.nextids().tolist() for _ in range(5)]
+    assert all(len(i) == 4 for i in ids)
+    assert len(set(ids[0]) & set(ids[1])) == 0                              # no repeats inside one permutation
