@@ -3,7 +3,7 @@
 
 One "step" = one pass of the hot path over one full 800x800 frame (640,000 rays) of BASELINE.json
 configs[1]: 300^3 grid, 200^3 alpha mask, S = nSamples = 1036, white background, synthetic rays and
-random-init grids (oracle/fixtures.py, seed 20211202).  With N GPUs every rank renders its own frame
+random-init grids (synthetic.py, seed 20211202).  With N GPUs every rank renders its own frame
 of the 8-azimuth orbit (configs[4], weak scaling, no data-path collective).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--regime R1|R2] [--mlp fp32|bf16|fp16]
@@ -112,7 +112,7 @@ class ClockSampler:
 
 
 def make_case(args, rank):
-    from oracle import fixtures as fx
+    import synthetic as fx
     reg = fx.REGIMES[args.regime]
     model = fx.make_model(args.grid, density_shift=reg["density_shift"])
     rays = fx.frame_rays(azimuth=0.7 + rank * np.pi / 4)       # 8-azimuth orbit of SURVEY §8d
@@ -188,7 +188,7 @@ def run_maintain(args):
     """SURVEY §8f rows at BASELINE sizes (300^3 grids, 200^3 alpha lattice, 800x800 frame): per-call device time through the
     reference-named host methods and the HBM fraction of each kernel's algorithmic bytes."""
     import jittor_myc_nerfs_b200 as pkg
-    from oracle import fixtures as fx
+    import synthetic as fx
     pkg._lib.require_cuda()
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
@@ -272,7 +272,7 @@ def run_side_workload(args):
     """configs[2] (training step) and configs[3] (variants, full frame): same timing rules as the contract
     line (warm-up >= 3, L2 flushed before every timed step, CUDA events on the launching stream)."""
     import jittor_myc_nerfs_b200 as pkg
-    from oracle import fixtures as fx
+    import synthetic as fx
     L = pkg._lib
     L.require_cuda()
     rank, local_rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))

@@ -8,7 +8,8 @@ import numpy as np
 import torch
 import torch.distributed as dist
 import jittor_myc_nerfs_b200 as pkg
-from oracle import fixtures as fx, tensorf_oracle as orc
+import synthetic as fx
+from oracle import tensorf_oracle as orc
 
 local = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
