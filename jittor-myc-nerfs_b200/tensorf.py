@@ -254,7 +254,7 @@ class TensorVMSplit(MaintainMixin, RegularizerMixin, CheckpointMixin, torch.nn.M
         pass
 
     def load_numpy_params(self, p):
-        """Copy an oracle.fixtures.ModelParams (numpy, reference shapes) into the parameters."""
+        """Copy an synthetic.ModelParams (numpy, reference shapes) into the parameters."""
         with torch.no_grad():
             for k in range(3):
                 self.density_plane[k].copy_(torch.from_numpy(p.density_plane[k]))
@@ -929,7 +929,7 @@ class NerfPlusPlus(TensorVMSplit):
 
 
 def model_from_params(p, device="cuda:0", alpha_volume=None, alpha_aabb=None, mlp_mode="fp32"):
-    """TensorVMSplit / REFTensoRF from a parameter record with the reference's shapes (e.g. oracle.fixtures.ModelParams)."""
+    """TensorVMSplit / REFTensoRF from a parameter record with the reference's shapes (e.g. synthetic.ModelParams)."""
     dev = torch.device(device)
     cls = {"ref": REFTensoRF, "npp": NerfPlusPlus}.get(getattr(p, "extra", {}).get("variant"), TensorVMSplit)
     m = cls(p.aabb, p.gridSize, dev, density_n_comp=list(p.density_n_comp),
