@@ -579,8 +579,8 @@ def main():
     bytes_march_step = 32.0 * n + 1.0 * M_in + 1152.0 * M_v + 12.0 * M_a
     bytes_per_launch = bytes_march_step * args.steps / launches_march
     achieved = bytes_per_launch / (march_ms * 1e-3) / 1e9
-    # appearance gather per entry: 12 plane taps + 6 line taps of 48 channels, fp32 (192 B) or bf16 planes (96 B)
-    bytes_app_step = (3456.0 if not model.app_planes_bf16 else 12 * 96.0 + 6 * 192.0) * M_a
+    # appearance gather per entry: 12 plane taps + 6 line taps of 48 channels, fp32 (192 B per tap) or 16-bit pair records (96 B per tap)
+    bytes_app_step = (3456.0 if not model.app_planes_bf16 else 18 * 96.0) * M_a
     app_ms = stage_ms["app"] / max(1, stage_cnt["app"])
     # DRAM bytes per launch of the same kernel from the committed `ncu --set full` capture (profiles/traffic.json)
     traffic, traffic_src = None, None
@@ -623,7 +623,7 @@ def main():
             "rgb_tolerance": 1e-4 if args.mlp != "bf16" else 1e-2,
             "rgb_tolerance_note": "north_star: 1e-4 abs in fp32, 1e-2 when the MLP runs in bf16; the fp16 head is held to the fp32 bound"}
     if rank == 0 and check is not None and check > line["rgb_tolerance"]:
-        raise SystemExit(f"bench: rendered colours differ from the oracle by {check} > {line['rgb_tolerance']}")
+        raise SystemExit(f"bench: rendered colours differ from the oracle by {check} > {line['rgb_tolerance']} (stage ms/step {roof.get('stage_ms_per_step')})")
 
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define TVM_ABI_VERSION 19
+#define TVM_ABI_VERSION 20
 
 /* flags for tvm_forward / tvm_backward */
 #define TVM_WHITE_BG      0x1u  /* rgb_map += 1 - acc_map          (tensorBase.py:523-524) */
@@ -112,11 +112,15 @@ typedef struct TvmModel {
   const void* tc_weights;
   int32_t sampling;         /* TVM_SAMPLING_*                                                            */
   float radii;              /* TVM_SAMPLING_NPP: radius of the bounding sphere (configs/Scarf.txt:14)    */
-  /* optional 16-bit copies of app_plane[k] written by tvm_pack_half in the format of the mode they are used with (bf16
-   * for TVM_MLP_BF16, fp16 for TVM_MLP_FP16; all NULL = none).  When present the tensor-core appearance head gathers its
-   * plane texels from them (half the gather bytes; the plane x line products are rounded to that format as the GEMM
-   * operand anyway).  TVM_MLP_FP32 and every backward kernel ignore them.                                          */
-  const void* app_plane_bf16[3];
+  /* optional 16-bit PAIR RECORDS of the appearance grids written by tvm_pack_pair16 in the format of the mode they are used
+   * with (bf16 for TVM_MLP_BF16, fp16 for TVM_MLP_FP16; all NULL = none).  Record x of row r holds texels (r, x) and
+   * (r, min(x+1, W-1)) interleaved by groups of 4 channels: [t0 c..c+3 | t1 c..c+3] = 16 bytes per group, 4*C bytes per
+   * record; a line is one row.  When present the tensor-core appearance head gathers from them: one 16-byte load per lane
+   * brings both taps of an axis pair (a 64-byte segment per sample and instruction; half the gather bytes and a third of
+   * the load instructions of the fp32 grids; the plane x line products are rounded to that format as the GEMM operand
+   * anyway).  TVM_MLP_FP32 and every backward kernel ignore them.                                                        */
+  const void* app_plane_pair[3];
+  const void* app_line_pair[3];
   /* optional second operand image for tvm_backward, packed by tvm_pack_mlp_tc with TVM_MLP_BF16 (NULL = none): lets a
    * TVM_MLP_FP16 step (fp16 forward, inside the fp32 tolerance) take the tensor-core backward, whose operands are bf16 */
   const void* tc_weights_bwd;
@@ -210,9 +214,10 @@ int tvm_transpose_batch(const TvmTransposeJob* jobs_host, int n_jobs, void* stre
 /* Linear weight [out][in] -> [in][out_pad] (zero padded columns)                              */
 int tvm_pack_linear(const float* w_out_in, int out_c, int in_c, int out_pad, float* out_t, void* stream);
 int tvm_unpack_linear(const float* w_t, int out_c, int in_c, int out_pad, float* out_w, void* stream);
-/* fp32 -> bf16 (flags = TVM_MLP_BF16) or fp16 (TVM_MLP_FP16) copy of n values, round to nearest even: the 16-bit
- * appearance planes of TvmModel.app_plane_bf16                                                                     */
-int tvm_pack_half(const float* src, size_t n, void* dst, uint32_t flags, void* stream);
+/* channels-last fp32 grid [rows][W][C] (a plane; a line is rows = 1, W = L) -> [rows][W] pair records of 2*C 16-bit values
+ * (bf16 for flags = TVM_MLP_BF16, fp16 for TVM_MLP_FP16, round to nearest even): TvmModel.app_plane_pair / app_line_pair.
+ * C must be a multiple of 4; dst holds rows*W*2*C values and must be 16-byte aligned.                                  */
+int tvm_pack_pair16(const float* src, int rows, int W, int C, void* dst, uint32_t flags, void* stream);
 /* {0,1} fp32 volume [D][H][W] -> bit stream (bit set iff value > 0); n_words = ceil(D*H*W/32)  */
 int tvm_pack_alpha(const float* volume, int D, int H, int W, uint32_t* bits, void* stream);
 /* brick index of a packed alpha volume; n_words = ceil(ceil(D/8)*ceil(H/8)*ceil(W/8) / 32)        */

@@ -71,7 +71,8 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 __device__ __forceinline__ void mlp_group_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
-// PB16: plane texels come from the bf16 copies (TvmModel.app_plane_bf16): 8-byte loads, adjacent-pair addressing
+// PB16: plane and line texels come from the 16-bit pair records (TvmModel.app_plane_pair / app_line_pair): one 16-byte
+//       load per lane brings both taps of an adjacent pair
 // H16:  operands (weight image, activations, plane copies) are fp16 instead of bf16 (TVM_MLP_FP16)
 template <int CA, int APP_DIM, int FEA_PE, int VIEW_PE, bool REF, bool PB16, bool H16>
 __global__ void __launch_bounds__(kThreadsV2, 1) k_app_tc(const FwdParams P) {
@@ -145,7 +146,11 @@ __global__ void __launch_bounds__(kThreadsV2, 1) k_app_tc(const FwdParams P) {
         const int row = gw * ROWS_PER_WARP + pass * 8 + (lane >> 2), q = lane & 3;
         const uint32_t e = tile_base + row;
         uint8_t* arow = stage + row * 16;
+#ifdef TVM_EXP_NOGATHER
+        if (false) {
+#else
         if (e < n_ent) {
+#endif
           const float4 uw = __ldcs(P.ws.ent_u + e);      // written by k_march with the coordinates it marched; read once: evict-first
           const float u[3] = {uw.x, uw.y, uw.z};
           if (PB16) {
@@ -155,17 +160,18 @@ __global__ void __launch_bounds__(kThreadsV2, 1) k_app_tc(const FwdParams P) {
 #pragma unroll
             for (int kk = 0; kk < 3; ++kk) {
               const VmPair t = vm_pair(m, ax, kk, CA);
-              const uint16_t* pl = reinterpret_cast<const uint16_t*>(m.app_plane_bf16[kk]);
-              const float* ln = m.app_line[kk] + t.lrow;
+              // pair records: [texel w c..c+3 | texel w+1 c..c+3] per 16 bytes, so one load brings both taps of the pair
+              const uint4* pl = reinterpret_cast<const uint4*>(m.app_plane_pair[kk]);
+              const uint4* ln = reinterpret_cast<const uint4*>(m.app_line_pair[kk]);
 #pragma unroll
               for (int c = q * 4; c < CA; c += 16) {
-                const uint2 a = __ldg(reinterpret_cast<const uint2*>(pl + t.row0 + c));
-                const uint2 b = __ldg(reinterpret_cast<const uint2*>(pl + t.row0 + c + CA));
-                const uint2 cc = __ldg(reinterpret_cast<const uint2*>(pl + t.row1 + c));
-                const uint2 d = __ldg(reinterpret_cast<const uint2*>(pl + t.row1 + c + CA));
-                const float4 l0 = ldg4(ln + c), l1 = ldg4(ln + c + CA);
-                const float2 a0 = unpack16<H16>(a.x), a1 = unpack16<H16>(a.y), b0 = unpack16<H16>(b.x), b1 = unpack16<H16>(b.y);
-                const float2 c0 = unpack16<H16>(cc.x), c1 = unpack16<H16>(cc.y), d0 = unpack16<H16>(d.x), d1 = unpack16<H16>(d.y);
+                const uint4 r0 = __ldg(pl + ((t.row0 + c) >> 2));
+                const uint4 r1 = __ldg(pl + ((t.row1 + c) >> 2));
+                const uint4 lr = __ldg(ln + ((t.lrow + c) >> 2));
+                const float2 a0 = unpack16<H16>(r0.x), a1 = unpack16<H16>(r0.y), b0 = unpack16<H16>(r0.z), b1 = unpack16<H16>(r0.w);
+                const float2 c0 = unpack16<H16>(r1.x), c1 = unpack16<H16>(r1.y), d0 = unpack16<H16>(r1.z), d1 = unpack16<H16>(r1.w);
+                const float2 l00 = unpack16<H16>(lr.x), l01 = unpack16<H16>(lr.y), l10 = unpack16<H16>(lr.z), l11 = unpack16<H16>(lr.w);
+                const float4 l0 = make_float4(l00.x, l00.y, l01.x, l01.y), l1 = make_float4(l10.x, l10.y, l11.x, l11.y);
                 const float px = a0.x * t.nw + b0.x * t.ne + c0.x * t.sw + d0.x * t.se;
                 const float py = a0.y * t.nw + b0.y * t.ne + c0.y * t.sw + d0.y * t.se;
                 const float pz = a1.x * t.nw + b1.x * t.ne + c1.x * t.sw + d1.x * t.se;
@@ -244,6 +250,10 @@ __global__ void __launch_bounds__(kThreadsV2, 1) k_app_tc(const FwdParams P) {
       mbar_wait(mma_bar, mma_phase);
       mma_phase ^= 1;
       fence_after();
+#ifdef TVM_EXP_NOMLP
+      mlp_group_sync();
+      continue;
+#endif
       float rgb_d0 = 0.0f, rgb_d1 = 0.0f, rgb_d2 = 0.0f, tint = 1.0f;
       {
         // ---- epi0: features -> [feat, view, sin/cos PE] as bf16 (tensorBase.py:76-83, 9-15) -------
@@ -425,7 +435,8 @@ int launch_app_tc(const FwdParams& P, int num_sms, cudaStream_t stream) {
   const Image img(P.m.n_app, P.in_mlp_c, head_ld(P.m));
   const int KA = max(img.K1, 128);
   const size_t smem = ((img.bytes_fwd + 1023) & ~1023u) + 2 * (size_t)kRows * img.K0 * 2 + (size_t)kRows * KA * 2 + 128 + 1024;
-  const bool pb16 = P.m.app_plane_bf16[0] && P.m.app_plane_bf16[1] && P.m.app_plane_bf16[2];
+  const bool pb16 = P.m.app_plane_pair[0] && P.m.app_plane_pair[1] && P.m.app_plane_pair[2] && P.m.app_line_pair[0] &&
+                    P.m.app_line_pair[1] && P.m.app_line_pair[2];
   void (*kern)(const FwdParams);
   if (h16)
     kern = ref ? (pb16 ? k_app_tc<48, 27, 2, 2, true, true, true> : k_app_tc<48, 27, 2, 2, true, false, true>)

@@ -335,23 +335,41 @@ extern "C" int tvm_mse_loss(const float* rgb_map, const float* target, int n_ray
   return 0;
 }
 
-__global__ void k_pack_half(const float* __restrict__ src, size_t n, uint16_t* __restrict__ dst, int h16) {
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+// Pair records of a channels-last grid (TvmModel.app_plane_pair / app_line_pair): one thread per 16-byte group
+// [t0 c..c+3 | t1 c..c+3] with t0 = (r, x), t1 = (r, min(x+1, W-1)).
+__global__ void k_pack_pair16(const float* __restrict__ src, size_t n_groups, int W, int C4, uint4* __restrict__ dst, int h16) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_groups; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t texel = i / (size_t)C4;
+    const int g = (int)(i - texel * (size_t)C4);
+    const int x = (int)(texel % (size_t)W);
+    const size_t nb = (x + 1 < W) ? texel + 1 : texel;
+    const float4 a = *reinterpret_cast<const float4*>(src + (texel * (size_t)C4 + g) * 4);
+    const float4 b = *reinterpret_cast<const float4*>(src + (nb * (size_t)C4 + g) * 4);
+    uint4 o;
     if (h16) {
-      const __half h = __float2half_rn(src[i]);
-      dst[i] = *reinterpret_cast<const uint16_t*>(&h);
+      const __half2 a0 = __floats2half2_rn(a.x, a.y), a1 = __floats2half2_rn(a.z, a.w);
+      const __half2 b0 = __floats2half2_rn(b.x, b.y), b1 = __floats2half2_rn(b.z, b.w);
+      o = make_uint4(*reinterpret_cast<const uint32_t*>(&a0), *reinterpret_cast<const uint32_t*>(&a1),
+                     *reinterpret_cast<const uint32_t*>(&b0), *reinterpret_cast<const uint32_t*>(&b1));
     } else {
-      const __nv_bfloat16 b = __float2bfloat16_rn(src[i]);
-      dst[i] = *reinterpret_cast<const uint16_t*>(&b);
+      const __nv_bfloat162 a0 = __floats2bfloat162_rn(a.x, a.y), a1 = __floats2bfloat162_rn(a.z, a.w);
+      const __nv_bfloat162 b0 = __floats2bfloat162_rn(b.x, b.y), b1 = __floats2bfloat162_rn(b.z, b.w);
+      o = make_uint4(*reinterpret_cast<const uint32_t*>(&a0), *reinterpret_cast<const uint32_t*>(&a1),
+                     *reinterpret_cast<const uint32_t*>(&b0), *reinterpret_cast<const uint32_t*>(&b1));
     }
+    dst[i] = o;
   }
 }
 
-extern "C" int tvm_pack_half(const float* src, size_t n, void* dst, uint32_t flags, void* stream) {
+extern "C" int tvm_pack_pair16(const float* src, int rows, int W, int C, void* dst, uint32_t flags, void* stream) {
   const uint32_t mode = flags & TVM_MLP_MASK;
-  TVM_REQUIRE(src && dst && n > 0 && (mode == TVM_MLP_BF16 || mode == TVM_MLP_FP16), "bad arguments");
-  const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 16);
-  k_pack_half<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, n, (uint16_t*)dst, mode == TVM_MLP_FP16);
+  TVM_REQUIRE(src && dst && rows > 0 && W > 0 && C > 0 && C % 4 == 0 && (mode == TVM_MLP_BF16 || mode == TVM_MLP_FP16),
+              "bad arguments");
+  TVM_REQUIRE((reinterpret_cast<uintptr_t>(dst) & 15u) == 0 && (reinterpret_cast<uintptr_t>(src) & 15u) == 0,
+              "tvm_pack_pair16: src and dst must be 16-byte aligned");
+  const size_t n_groups = (size_t)rows * (size_t)W * (size_t)(C / 4);
+  const int blocks = (int)std::min<size_t>((n_groups + 255) / 256, 148 * 16);
+  k_pack_pair16<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, n_groups, W, C / 4, (uint4*)dst, mode == TVM_MLP_FP16);
   TVM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -426,21 +426,30 @@ class TensorVMSplit(MaintainMixin, RegularizerMixin, CheckpointMixin, torch.nn.M
                 s.tc_weights_bwd = self._tc_bwd.data_ptr()
             self._tc_stale = False
         for k in range(3):
-            s.app_plane_bf16[k] = None
+            s.app_plane_pair[k] = None
+            s.app_line_pair[k] = None
         if self.mlp_mode in ("bf16", "fp16") and self.app_planes_bf16:
+            # 16-bit pair records of the appearance planes and lines (tvmrender.h: TvmModel.app_plane_pair): 2 values per texel
             lib = L.load()
             items, _ = self._layout()
-            n_tot = sum(items[f"ap{k}"][1] for k in range(3))
+            G = [int(g) for g in self.gridSize]
+            Ca = self.app_n_comp[0]
+            jobs = []
+            for k in range(3):
+                m0, m1 = MAT_MODE[k]
+                jobs.append((items[f"ap{k}"][0], G[m1], G[m0], s.app_plane_pair, k))
+            for k in range(3):
+                jobs.append((items[f"al{k}"][0], 1, G[VEC_MODE[k]], s.app_line_pair, k))
+            n_tot = sum((2 * rows * W * Ca + 7) // 8 * 8 for _, rows, W, _, _ in jobs)
             if getattr(self, "_app16", None) is None or self._app16.numel() != n_tot:
                 self._app16 = torch.empty(n_tot, dtype=torch.bfloat16, device=self.device)
             off = 0
-            for k in range(3):
-                o, n_el = items[f"ap{k}"]
+            for o, rows, W, field, k in jobs:
                 dst = self._app16.data_ptr() + 2 * off
-                L.check(lib.tvm_pack_half(C.c_void_p(self._packed.data_ptr() + 4 * o), n_el, C.c_void_p(dst),
-                                          _MLP_FLAGS[self.mlp_mode], _stream_ptr()), "tvm_pack_half")
-                s.app_plane_bf16[k] = dst
-                off += n_el
+                L.check(lib.tvm_pack_pair16(C.c_void_p(self._packed.data_ptr() + 4 * o), rows, W, Ca, C.c_void_p(dst),
+                                            _MLP_FLAGS[self.mlp_mode], _stream_ptr()), "tvm_pack_pair16")
+                field[k] = dst
+                off += (2 * rows * W * Ca + 7) // 8 * 8
         s.sampling, s.radii = L.SAMPLING_UNIFORM, 0.0
         self._finish_model(s)
         self._model_struct, self._model_mask_key = s, mask_key

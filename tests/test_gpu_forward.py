@@ -167,7 +167,7 @@ def test_tensor_core_mlp_bf16(env):
 
 
 def test_bf16_appearance_planes(env):
-    """app_planes_bf16 (TvmModel.app_plane_bf16): the tensor-core head gathers bf16 copies of the appearance planes.
+    """app_planes_bf16 (TvmModel.app_plane_pair / app_line_pair): the tensor-core head gathers 16-bit pair records of the appearance grids.
     Same north_star bound as the bf16 head (1e-2 on rgb, PSNR delta < 0.01 dB); masks, depth and the work counters do
     not depend on it.  REFTensoRF uses the same gather."""
     pkg, torch, fx, orc = env
@@ -187,7 +187,7 @@ def test_bf16_appearance_planes(env):
             rgb_b, depth_b = model(rays)
             cnt_b = model.counters.clone()
         torch.cuda.synchronize()
-        assert model._model().app_plane_bf16[0]
+        assert model._model().app_plane_pair[0] and model._model().app_line_pair[0]
         assert torch.equal(depth_a, depth_b) and torch.equal(cnt_a, cnt_b)
         a, b = rgb_a.cpu().numpy(), rgb_b.cpu().numpy()
         err = np.abs(b - ref["rgb_map"]).max()
