@@ -326,6 +326,39 @@ def test_umma_descriptor_conventions(env):
     assert torch.equal(D1, P.T @ Q), "MN-major A and B operands"
 
 
+def _pair_records(src):
+    """numpy restatement of the record layout of tvmrender.h (TvmModel.app_plane_pair): src [rows, W, C] ->
+    [rows, W, C/4, 2, 4]: record x = texels x and min(x + 1, W - 1), interleaved by groups of 4 channels."""
+    rows, W, C = src.shape
+    nxt = src[:, np.minimum(np.arange(W) + 1, W - 1), :]
+    return np.stack([src.reshape(rows, W, C // 4, 4), nxt.reshape(rows, W, C // 4, 4)], axis=3)
+
+
+def test_pack_pair16_layout(env):
+    """tvm_pack_pair16 known-answer test: record layout and round-to-nearest-even conversion, bit for bit, for both 16-bit
+    formats; a plane (rows > 1), a line (rows = 1) and a single-texel row (the record repeats the texel); bad arguments fail."""
+    pkg, torch, fx, orc = env
+    import ctypes as C
+    lib = pkg._lib.load()
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    g = torch.Generator().manual_seed(11)
+    for rows, W, Cn in ((5, 7, 48), (1, 300, 48), (3, 1, 16), (1, 2, 4)):
+        src = torch.randn(rows, W, Cn, generator=g) * 0.1
+        src_d = src.cuda()
+        for flag, dt in ((pkg._lib.MLP_BF16, torch.bfloat16), (pkg._lib.MLP_FP16, torch.float16)):
+            dst = torch.zeros(rows * W * 2 * Cn, dtype=dt, device="cuda")
+            pkg._lib.check(lib.tvm_pack_pair16(C.c_void_p(src_d.data_ptr()), rows, W, Cn, C.c_void_p(dst.data_ptr()), flag, stream),
+                           "tvm_pack_pair16")
+            torch.cuda.synchronize()
+            want = torch.from_numpy(_pair_records(src.numpy())).to(dt).reshape(-1)       # torch rounds to nearest even as well
+            assert torch.equal(dst.cpu().view(torch.int16), want.view(torch.int16)), (rows, W, Cn, dt)
+    src_d = torch.zeros(64, device="cuda")
+    dst = torch.zeros(128, dtype=torch.float16, device="cuda")
+    assert lib.tvm_pack_pair16(C.c_void_p(src_d.data_ptr()), 1, 4, 6, C.c_void_p(dst.data_ptr()), pkg._lib.MLP_FP16, stream) != 0   # C % 4
+    assert lib.tvm_pack_pair16(C.c_void_p(src_d.data_ptr()), 1, 4, 4, C.c_void_p(dst.data_ptr()), 0, stream) != 0                  # fp32 mode
+    assert lib.tvm_pack_pair16(C.c_void_p(src_d.data_ptr()), 1, 4, 4, C.c_void_p(dst.data_ptr() + 2), pkg._lib.MLP_FP16, stream) != 0   # alignment
+
+
 def test_streamed_host_render_matches_resident(env):
     """OctreeRender_trilinear_fast(pinned host rays, out_host=...) pipelines upload / render / download per chunk; the
     pixels are those of the device-resident call, bit for bit (compositing is deterministic)."""
