@@ -18,9 +18,12 @@
  * binds to these symbols.
  *
  * Conventions: every pointer is a DEVICE pointer unless the name ends in _host; all floating point
- * is IEEE fp32; the caller owns every buffer; the library keeps no global state besides a
- * thread-local error string; every entry point takes the CUDA stream (as void*) it enqueues on and
- * never synchronises; return value 0 = ok, negative = error (tvm_last_error() explains).
+ * is IEEE fp32; the caller owns every buffer; every entry point takes the CUDA stream (as void*) it
+ * enqueues on and never synchronises; return value 0 = ok, negative = error (tvm_last_error() explains).
+ * State kept by the library: a thread-local error string; a per-device cache of the SM count; and, only while
+ * tvm_profile_enable(1) is in force, a mutex-guarded list of cudaEvents (measurement hook, see the end of
+ * this file).  Nothing else survives a call: compute entry points are re-entrant and may run concurrently on
+ * distinct streams with distinct workspaces.
  * There is no CPU fallback: without a CUDA device every compute entry point fails.
  */
 #ifndef TVMRENDER_H_
@@ -33,7 +36,7 @@
 extern "C" {
 #endif
 
-#define TVM_ABI_VERSION 20
+#define TVM_ABI_VERSION 21
 
 /* flags for tvm_forward / tvm_backward */
 #define TVM_WHITE_BG      0x1u  /* rgb_map += 1 - acc_map          (tensorBase.py:523-524) */
@@ -238,6 +241,27 @@ int tvm_pack_bg_tc(const TvmBgNet* bg_host, void* tc_weights_out, void* stream);
 /* bytes of scratch tvm_forward needs for n rays x n_samples (worst case: every sample weighted) */
 int tvm_workspace_bytes(int n_rays, int n_samples, size_t* out_bytes);
 
+/* Where tvm_forward leaves the per-sample results inside the caller's workspace (byte offsets from `ws`), valid until the next
+ * call on that workspace.  This is how the PRODUCTION march (no TvmAux, empty-space skipping and early ray termination on)
+ * is held to the reference's masks: blk_mask [n][n_blocks] are the app_mask bits (weight > thres, tensorBase.py:513) of
+ * each 32-sample block, ent [*n_entries] the (ray, sample) pairs in ray-major order -- the compaction order of the
+ * reference's boolean indexing (tensorBase.py:516-518) within a ray -- ent_w their weights, ent_rgb their colours, acc the
+ * acc_map (tensorBase.py:520).  A Jittor binding can expose them as extra outputs.                                       */
+typedef struct TvmWorkspaceLayout {
+  size_t n_entries;         /* uint32: number of entries (samples with weight > thres)                  */
+  size_t blk_mask;          /* uint32 [n][n_blocks]: app_mask bits of block b of ray r (0 = never visited) */
+  size_t blk_base;          /* uint32 [n][n_blocks]: index of the block's first entry (valid where blk_mask != 0) */
+  size_t ent;               /* uint32 [capacity][2]: (ray, sample index)                                 */
+  size_t ent_w;             /* float  [capacity]: weight                                                 */
+  size_t ent_rgb;           /* float  [capacity][3]: colour of the sample (tensorBase.py:518)            */
+  size_t acc;               /* float  [n]: acc_map                                                       */
+  size_t rgb_sum;           /* float  [n][3]: sum_k w_k rgb_k before white background / clamp            */
+  uint32_t capacity;        /* entries the workspace can hold (n * n_samples)                            */
+  int32_t n_blocks;         /* ceil(n_samples / 32)                                                      */
+  size_t bytes;             /* = tvm_workspace_bytes                                                     */
+} TvmWorkspaceLayout;
+int tvm_workspace_layout(int n_rays, int n_samples, TvmWorkspaceLayout* out);
+
 /* TensorBase.execute for n rays (tensorBase.py:476-536, ndc_ray=False):
  *   rays [n][6] (origin, unit direction), jitter [n] or NULL (is_train: rng += U[0,1) per ray,
  *   tensorBase.py:351-353), rgb_map [n][3], depth_map [n], counters [TVM_CNT_WORDS] uint64 or NULL
@@ -369,7 +393,8 @@ int tvm_bench_gather(const float* buf, size_t n_floats, int n_groups, int iters,
 
 /* ---- measurement hooks (bench.py's roofline leg; off by default) ------------------------------ */
 /* When enabled, every kernel tvm_forward / tvm_backward launches is bracketed by cudaEvents on the
- * caller's stream.  Stages: see TVM_STAGE_*.  Process-global, not thread-safe: benchmarking only. */
+ * caller's stream.  Stages: see TVM_STAGE_*.  Process-global (one mutex-guarded record list shared by all streams and
+ * threads; events are created on the device current at the launch): a measurement aid, off by default. */
 #define TVM_STAGE_MARCH      0
 #define TVM_STAGE_APP        1
 #define TVM_STAGE_COMPOSITE  2

@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # TVM_LIB: developer override (kernel-tuning experiments build variant libraries next to the default one)
 LIB_PATH = os.environ.get("TVM_LIB") or os.path.join(_HERE, "libtvmrender.so")
-ABI_VERSION = 20
+ABI_VERSION = 21
 
 # flags (tvmrender.h)
 WHITE_BG = 0x1
@@ -55,6 +55,12 @@ class TvmAux(C.Structure):
                 ("bg_lambda", C.c_void_p), ("bg_rgb_map", C.c_void_p), ("penalty", C.c_void_p)]
 
 
+class TvmWorkspaceLayout(C.Structure):
+    _fields_ = [("n_entries", C.c_size_t), ("blk_mask", C.c_size_t), ("blk_base", C.c_size_t), ("ent", C.c_size_t),
+                ("ent_w", C.c_size_t), ("ent_rgb", C.c_size_t), ("acc", C.c_size_t), ("rgb_sum", C.c_size_t),
+                ("capacity", C.c_uint32), ("n_blocks", C.c_int32), ("bytes", C.c_size_t)]
+
+
 class TvmBgNet(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("w0_t", "b0", "w1_t", "b1", "w2_t", "b2", "w_sigma", "b_sigma", "wf_t", "bf",
                                            "wv_t", "w_rgb", "b_rgb", "tc_weights")]
@@ -93,7 +99,7 @@ class TvmGrads(C.Structure):
 EXPORTS = [
     "tvm_last_error", "tvm_abi_version", "tvm_device_count", "tvm_pack_grid", "tvm_unpack_grid",
     "tvm_pack_linear", "tvm_unpack_linear", "tvm_transpose_batch", "tvm_pack_pair16", "tvm_pack_alpha", "tvm_pack_alpha_bricks", "tvm_pack_alpha_dilated", "tvm_tc_weights_bytes", "tvm_pack_mlp_tc",
-    "tvm_workspace_bytes", "tvm_forward", "tvm_forward_npp", "tvm_bg_fold", "tvm_bg_tc_bytes", "tvm_pack_bg_tc", "tvm_backward", "tvm_backward_npp", "tvm_bg_fold_bwd",
+    "tvm_workspace_bytes", "tvm_workspace_layout", "tvm_forward", "tvm_forward_npp", "tvm_bg_fold", "tvm_bg_tc_bytes", "tvm_pack_bg_tc", "tvm_backward", "tvm_backward_npp", "tvm_bg_fold_bwd",
     "tvm_density_alpha", "tvm_mse_loss",
     "tvm_profile_enable", "tvm_profile_collect",
     "tvm_dense_alpha", "tvm_alpha_mask_from_dense", "tvm_filter_rays", "tvm_generate_rays", "tvm_upsample_grid",
@@ -140,6 +146,7 @@ def load() -> C.CDLL:
     lib.tvm_bg_tc_bytes.argtypes = []
     lib.tvm_pack_mlp_tc.argtypes = [C.POINTER(TvmModel), vp, u32, vp]
     lib.tvm_workspace_bytes.argtypes = [i32, i32, C.POINTER(C.c_size_t)]
+    lib.tvm_workspace_layout.argtypes = [i32, i32, C.POINTER(TvmWorkspaceLayout)]
     lib.tvm_forward.argtypes = [C.POINTER(TvmModel), vp, i32, i32, vp, u32, vp, vp, C.POINTER(TvmAux), vp, vp,
                                 C.c_size_t, vp]
     lib.tvm_forward_npp.argtypes = [C.POINTER(TvmModel), C.POINTER(TvmBgNet), vp, i32, i32, vp, vp, u32, vp, vp,

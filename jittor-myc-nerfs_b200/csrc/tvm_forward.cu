@@ -11,6 +11,7 @@
 //
 // The tcgen05 tensor-core appearance head lives in tvm_mlp_tc.cu and replaces k_app_simt when
 // TVM_MLP_BF16 / TVM_MLP_FP16 is requested.
+#include <atomic>
 #include "tvm_app_simt.cuh"
 
 namespace tvm {
@@ -355,13 +356,15 @@ int fill_fwd_params(FwdParams& P, const TvmModel* m, const float* rays, int n, i
   return 0;
 }
 
+// SM count of the CURRENT device (a process may drive several GPUs through one copy of the library)
 static int device_sms() {
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+  int sms = cache[dev].load(std::memory_order_relaxed);
+  if (sms <= 0) {
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    cache[dev].store(sms, std::memory_order_relaxed);
   }
   return sms;
 }
@@ -374,6 +377,25 @@ extern "C" int tvm_workspace_bytes(int n_rays, int n_samples, size_t* out_bytes)
   TVM_REQUIRE(out_bytes && n_rays > 0 && n_samples > 0, "bad arguments");
   TVM_REQUIRE((double)n_rays * n_samples < 4.0e9, "n_rays*n_samples must fit 32 bits; split the rays");
   *out_bytes = carve_workspace(nullptr, n_rays, n_samples).bytes;
+  return 0;
+}
+
+extern "C" int tvm_workspace_layout(int n_rays, int n_samples, TvmWorkspaceLayout* out) {
+  TVM_REQUIRE(out && n_rays > 0 && n_samples > 0, "bad arguments");
+  TVM_REQUIRE((double)n_rays * n_samples < 4.0e9, "n_rays*n_samples must fit 32 bits; split the rays");
+  const Workspace w = carve_workspace((void*)256, n_rays, n_samples);      // non-null base so that members get addresses
+  auto off = [](const void* p) { return (size_t)((const char*)p - (const char*)256); };
+  out->n_entries = off(w.n_entries);
+  out->blk_mask = off(w.blk_mask);
+  out->blk_base = off(w.blk_base);
+  out->ent = off(w.ent);
+  out->ent_w = off(w.ent_w);
+  out->ent_rgb = off(w.ent_rgb);
+  out->acc = off(w.acc);
+  out->rgb_sum = off(w.rgb_sum);
+  out->capacity = w.cap;
+  out->n_blocks = w.NB;
+  out->bytes = w.bytes;
   return 0;
 }
 

@@ -12,6 +12,7 @@
 // so that one thread (= one row) writes whole 16-byte chunks, conflict-free.  Accumulators are read
 // back with tcgen05.ld (32x32b: thread t of warp w owns TMEM lane 32*(w%4)+t = tile row).
 // One thread issues the MMAs; completion is signalled through tcgen05.commit -> mbarrier.
+#include <stdlib.h>
 #include "tvm_tc.cuh"
 
 namespace tvm {
@@ -424,6 +425,8 @@ static bool tc_supported(const TvmModel& m) {
   return m.n_app == 48 && m.app_dim == 27 && m.fea_pe == 2 && m.view_pe == 2 && m.feature_c == 128;
 }
 
+int launch_app_tc2(const FwdParams& P, int num_sms, cudaStream_t stream);   // tvm_app_tc2.cu
+
 int launch_app_tc(const FwdParams& P, int num_sms, cudaStream_t stream) {
   const uint32_t mode = P.flags & TVM_MLP_MASK;
   TVM_REQUIRE(mode == TVM_MLP_BF16 || mode == TVM_MLP_FP16, "the tensor-core path takes TVM_MLP_BF16 or TVM_MLP_FP16");
@@ -431,6 +434,10 @@ int launch_app_tc(const FwdParams& P, int num_sms, cudaStream_t stream) {
   TVM_REQUIRE(tc_supported(P.m), "tensor-core appearance head supports n_app=48, app_dim=27, fea_pe=view_pe=2, "
                                  "featureC=128 (all shipped configs); use TVM_MLP_FP32 otherwise");
   TVM_REQUIRE(P.m.tc_weights != nullptr, "TvmModel.tc_weights is NULL: call tvm_pack_mlp_tc first");
+  // default: the two-group kernel with TMEM-resident activations (tvm_app_tc2.cu); TVM_APP_TC=1 selects the single-group
+  // kernel below (A/B measurements; read once)
+  static const bool use_v1 = [] { const char* e = getenv("TVM_APP_TC"); return e && e[0] == '1'; }();
+  if (!use_v1) return launch_app_tc2(P, num_sms, stream);
   const bool ref = P.m.variant == TVM_VARIANT_REF;
   const Image img(P.m.n_app, P.in_mlp_c, head_ld(P.m));
   const int KA = max(img.K1, 128);

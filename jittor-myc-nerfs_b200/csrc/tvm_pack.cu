@@ -8,6 +8,9 @@
 #include <stdarg.h>
 #include <string.h>
 #include <algorithm>
+#include <atomic>
+#include <mutex>
+#include <utility>
 #include <vector>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -24,23 +27,43 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-struct ProfRec { int stage; cudaEvent_t a, b; };
-static bool g_prof_on = false;
+// Measurement hook (tvm_profile_*): the only process-global state of the library.  One mutex guards the record list and
+// the event pool; a launch keeps the index of its own record, so concurrent launches on different streams / threads
+// cannot close each other's bracket.  Events are per device (an event may only be recorded on a stream of its device).
+struct ProfRec { int stage, dev; cudaEvent_t a, b; };
+static std::atomic<bool> g_prof_on{false};
+static std::mutex g_prof_mu;
 static std::vector<ProfRec> g_prof;
-static std::vector<cudaEvent_t> g_ev_pool;
-static cudaEvent_t get_event() {
-  if (!g_ev_pool.empty()) { cudaEvent_t e = g_ev_pool.back(); g_ev_pool.pop_back(); return e; }
+static std::vector<std::pair<int, cudaEvent_t>> g_ev_pool;
+static thread_local std::vector<size_t> g_prof_open;      // indices of this thread's open brackets (they nest at most once)
+static cudaEvent_t get_event(int dev) {
+  for (size_t i = 0; i < g_ev_pool.size(); ++i)
+    if (g_ev_pool[i].first == dev) {
+      cudaEvent_t e = g_ev_pool[i].second;
+      g_ev_pool.erase(g_ev_pool.begin() + i);
+      return e;
+    }
   cudaEvent_t e;
   cudaEventCreate(&e);
   return e;
 }
-bool profile_on() { return g_prof_on; }
+bool profile_on() { return g_prof_on.load(std::memory_order_relaxed); }
 void profile_begin(int stage, cudaStream_t s) {
-  ProfRec r{stage, get_event(), get_event()};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  ProfRec r{stage, dev, get_event(dev), get_event(dev)};
   cudaEventRecord(r.a, s);
+  g_prof_open.push_back(g_prof.size());
   g_prof.push_back(r);
 }
-void profile_end(cudaStream_t s) { cudaEventRecord(g_prof.back().b, s); }
+void profile_end(cudaStream_t s) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (g_prof_open.empty()) return;
+  const size_t i = g_prof_open.back();
+  g_prof_open.pop_back();
+  if (i < g_prof.size()) cudaEventRecord(g_prof[i].b, s);
+}
 
 int validate_model(const TvmModel& m) {
   TVM_REQUIRE(m.n_density > 0 && m.n_density % 4 == 0, "n_density must be a positive multiple of 4");
@@ -208,12 +231,13 @@ extern "C" const char* tvm_last_error(void) { return g_err; }
 extern "C" int tvm_abi_version(void) { return TVM_ABI_VERSION; }
 
 extern "C" int tvm_profile_enable(int on) {
-  g_prof_on = on != 0;
+  g_prof_on.store(on != 0);
   return 0;
 }
 
 extern "C" int tvm_profile_collect(float* ms_by_stage, int* launches_by_stage) {
   TVM_REQUIRE(ms_by_stage && launches_by_stage, "bad arguments");
+  std::lock_guard<std::mutex> lk(g_prof_mu);
   for (auto& r : g_prof) {
     TVM_CHECK_CUDA(cudaEventSynchronize(r.b));
     float ms = 0.0f;
@@ -222,8 +246,8 @@ extern "C" int tvm_profile_collect(float* ms_by_stage, int* launches_by_stage) {
       ms_by_stage[r.stage] += ms;
       launches_by_stage[r.stage] += 1;
     }
-    g_ev_pool.push_back(r.a);
-    g_ev_pool.push_back(r.b);
+    g_ev_pool.push_back({r.dev, r.a});
+    g_ev_pool.push_back({r.dev, r.b});
   }
   g_prof.clear();
   return 0;

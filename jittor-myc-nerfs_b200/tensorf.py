@@ -111,6 +111,7 @@ class _RenderFn(torch.autograd.Function):
     def forward(ctx, model, rays, jitter, flags, S, *params):
         rgb, depth = model._forward_raw(rays, jitter, flags, S)
         ctx.model, ctx.flags, ctx.S = model, flags, S
+        ctx.stamp = model._forward_stamp()
         ctx.save_for_backward(rays, jitter if jitter is not None else torch.empty(0, device=rays.device), rgb)
         ctx.mark_non_differentiable(depth)
         # REFTensoRF: the normal penalty (REFTensoRF.py:236-238) is a third, differentiable output
@@ -120,6 +121,7 @@ class _RenderFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_rgb, _d_depth, d_penalty):
         rays, jitter, rgb = ctx.saved_tensors
+        ctx.model._check_stamp(ctx.stamp)
         d_pen = None
         if ctx.model.VARIANT == L.VARIANT_REF and d_penalty is not None:
             d_pen = d_penalty.reshape(-1)[:1].to(torch.float32).contiguous()
@@ -135,6 +137,7 @@ class _RenderNppFn(torch.autograd.Function):
     def forward(ctx, model, rays, fg_rand, bg_rand, flags, S, *params):
         rgb, depth = model._forward_npp_raw(rays, fg_rand, bg_rand, flags, S)
         ctx.model, ctx.flags, ctx.S = model, flags, S
+        ctx.stamp = model._forward_stamp()
         ctx.save_for_backward(rays, fg_rand, bg_rand, rgb)
         ctx.mark_non_differentiable(depth)
         return rgb, depth
@@ -142,6 +145,7 @@ class _RenderNppFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_rgb, _d_depth):
         rays, fg_rand, bg_rand, rgb = ctx.saved_tensors
+        ctx.model._check_stamp(ctx.stamp)
         d_rgb = torch.zeros_like(rgb) if d_rgb is None else d_rgb.contiguous()
         grads = ctx.model._backward_npp_raw(rays, fg_rand, bg_rand, ctx.flags, ctx.S, rgb, d_rgb)
         return (None, None, None, None, None, None, *grads)
@@ -201,6 +205,7 @@ class TensorVMSplit(MaintainMixin, RegularizerMixin, CheckpointMixin, torch.nn.M
         self.grad_sync = False          # set True (after dist.init_from_env) for data-parallel training
         self.grad_sync_group = None
         self._ws = None
+        self._fwd_gen = 0               # bumped by every tvm_forward* on the shared workspace (see _forward_stamp)
         self._packed = None
         self._packed_versions = None
         self._packed_grid = None
@@ -374,7 +379,7 @@ class TensorVMSplit(MaintainMixin, RegularizerMixin, CheckpointMixin, torch.nn.M
     def _model(self):
         """The TvmModel descriptor (host POD) for the current parameters / mask."""
         self._pack()
-        mask_key = (id(self.alphaMask), self.empty_space_skipping, self.mlp_mode, self.app_planes_bf16)
+        mask_key = (self._mask_version, self.empty_space_skipping, self.mlp_mode, self.app_planes_bf16)
         if getattr(self, "_model_struct", None) is not None and self._model_mask_key == mask_key \
                 and not (self._tc_stale and self.mlp_mode != "fp32"):
             return self._model_struct
@@ -476,6 +481,56 @@ class TensorVMSplit(MaintainMixin, RegularizerMixin, CheckpointMixin, torch.nn.M
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
         return self._ws
 
+    def workspace_view(self, n, S):
+        """What the last tvm_forward over (n rays, S samples) left in the workspace (tvmrender.h: TvmWorkspaceLayout):
+        the app_mask bits per 32-sample block, the compacted (ray, sample) entries in ray-major order with their weights
+        and colours, and acc_map -- the per-sample record of the PRODUCTION march (no TvmAux, skipping and ERT on)."""
+        lay = L.TvmWorkspaceLayout()
+        L.check(L.load().tvm_workspace_layout(int(n), int(S), C.byref(lay)), "tvm_workspace_layout")
+        ws = self._ws
+        assert ws is not None and ws.numel() >= lay.bytes
+
+        def view(off, count, dtype):
+            return ws[off:off + count * torch.empty(0, dtype=dtype).element_size()].view(dtype)
+        n_ent = int(view(lay.n_entries, 1, torch.int32).item())
+        NB = lay.n_blocks
+        return dict(n_entries=n_ent, n_blocks=NB,
+                    blk_mask=view(lay.blk_mask, n * NB, torch.int32).view(n, NB),
+                    blk_base=view(lay.blk_base, n * NB, torch.int32).view(n, NB),
+                    ent=view(lay.ent, 2 * n_ent, torch.int32).view(n_ent, 2),
+                    ent_w=view(lay.ent_w, n_ent, torch.float32),
+                    ent_rgb=view(lay.ent_rgb, 3 * n_ent, torch.float32).view(n_ent, 3),
+                    acc=view(lay.acc, n, torch.float32))
+
+    # ---- autograd bookkeeping ---------------------------------------------------------------------
+    def _forward_stamp(self):
+        """What tvm_backward relies on staying as the matching tvm_forward left it (tvmrender.h: "must follow a tvm_forward
+        with the same arguments on the same workspace"): the workspace (any later forward on the model overwrites its
+        entry list), the parameters and the mask."""
+        return (self._fwd_gen, None if self._ws is None else self._ws.data_ptr(),
+                tuple((p.data_ptr(), p._version) for p in self._param_list()),
+                self._mask_version, tuple(int(g) for g in self.gridSize))
+
+    def _check_stamp(self, stamp):
+        if stamp != self._forward_stamp():
+            what = ("another forward ran on this model" if stamp[0] != self._fwd_gen or stamp[1] != (None if self._ws is None else self._ws.data_ptr())
+                    else "the parameters, the grid or the alpha mask changed")
+            raise RuntimeError("tvm_backward must directly follow its tvm_forward on the model's workspace, but " + what +
+                               " between this graph's forward and its backward (e.g. a second micro-batch, an evaluation "
+                               "render, compute_alpha / filtering_rays / updateAlphaMask, an optimizer step): call backward() "
+                               "before the next forward, or re-run the forward")
+
+    @property
+    def alphaMask(self):
+        return self._alpha_mask
+
+    @alphaMask.setter
+    def alphaMask(self, mask):
+        # a monotonically increasing version keys the TvmModel cache (id() of a dropped mask can be reused by the next one)
+        self._alpha_mask = mask
+        self._mask_version = getattr(self, "_mask_version", 0) + 1
+        self._model_struct = None
+
     # ---- raw engine calls -----------------------------------------------------------------------
     def _flags(self, white_bg):
         f = _MLP_FLAGS[self.mlp_mode]
@@ -491,6 +546,7 @@ class TensorVMSplit(MaintainMixin, RegularizerMixin, CheckpointMixin, torch.nn.M
         assert rays.is_cuda and rays.dtype == torch.float32 and rays.is_contiguous() and rays.shape[1] == 6
         model = self._model()
         ws = self._workspace(n, S)
+        self._fwd_gen += 1
         if out is None:
             rgb = torch.empty((n, 3), dtype=torch.float32, device=rays.device)
             depth = torch.empty((n,), dtype=torch.float32, device=rays.device)
@@ -795,6 +851,7 @@ class NerfPlusPlus(TensorVMSplit):
         n = rays.shape[0]
         model, bg = self._model(), self._bg_struct()
         ws = self._workspace(n, S)
+        self._fwd_gen += 1
         if out is None:
             out = (torch.empty((n, 3), dtype=torch.float32, device=rays.device),
                    torch.empty((n,), dtype=torch.float32, device=rays.device))
@@ -953,8 +1010,8 @@ def model_from_params(p, device="cuda:0", alpha_volume=None, alpha_aabb=None, ml
     return m
 
 
-def unpack_bits(bits: torch.Tensor, S: int) -> np.ndarray:
-    """[n, NB] int32 device words -> [n, S] bool numpy (bit j of word b = sample 32*b + j)."""
-    w = bits.detach().cpu().numpy().view(np.uint32)
+def unpack_bits(bits, S: int) -> np.ndarray:
+    """[n, NB] int32 words (device tensor or numpy) -> [n, S] bool numpy (bit j of word b = sample 32*b + j)."""
+    w = (bits.detach().cpu().numpy() if torch.is_tensor(bits) else np.ascontiguousarray(bits)).view(np.uint32)
     b = np.unpackbits(w.view(np.uint8).reshape(w.shape[0], -1), axis=1, bitorder="little")
     return b[:, :S].astype(bool)

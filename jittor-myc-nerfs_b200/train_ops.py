@@ -41,6 +41,32 @@ def _launch(kind, x, weight, loss, grad, weight_dev=None):
                 "tvm_vector_diffs")
 
 
+class _PinnedRing:
+    """Host staging for small per-step scalars that a stream-ordered H2D copy reads LATER than the host writes them.
+    Each push() takes the next of `slots` pinned buffers; a slot is reused only after the copy that read it has executed
+    (an event recorded behind that copy), so the host may run any number of steps ahead of the device without a later
+    step's values reaching an earlier step's kernels."""
+
+    def __init__(self, n, slots=8):
+        self.bufs = [torch.zeros(n, dtype=torch.float32).pin_memory() for _ in range(slots)]
+        self.events = [None] * slots
+        self.i = 0
+
+    def upload(self, values, dst):
+        """dst (device, [n]) <- values, enqueued on the current stream."""
+        k = self.i
+        self.i = (k + 1) % len(self.bufs)
+        if self.events[k] is not None:
+            self.events[k].synchronize()          # only ever waits when the host is `slots` steps ahead
+        buf = self.bufs[k]
+        for j, v in enumerate(values):
+            buf[j] = float(v)
+        dst.copy_(buf, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.events[k] = ev
+
+
 class _RegFn(torch.autograd.Function):
     """loss = sum_i weight_i * f_kind(x_i); gradients are produced by the same kernels that produce the value."""
 
@@ -133,20 +159,24 @@ class Adam:
     # -- hyper-parameters live in a small device buffer refreshed from pinned host memory, so that a captured CUDA
     #    graph (TrainStepGraph) can be replayed with the next step's bias correction / decayed learning rates
     def _prepare_hyper(self):
-        """Host side of one step: advance the step counter and stage {c_step, lr per group} in pinned memory."""
+        """Host side of one step: advance the step counter and send {c_step, lr per group} to the device buffer the kernel
+        reads, through a ring of pinned slots (stream-ordered; safe however far the host runs ahead of the device).
+        Runs OUTSIDE a captured graph: the graph only ever reads the device buffer."""
         self.n_step += 1
         n = float(self.n_step)
-        if getattr(self, "_hyper_host", None) is None or self._hyper_host.numel() != 1 + len(self.param_groups):
-            self._hyper_host = torch.zeros(1 + len(self.param_groups), dtype=torch.float32).pin_memory()
-            self._hyper_dev = None
+        k = 1 + len(self.param_groups)
+        device = next(p.device for g in self.param_groups for p in g["params"])
+        if getattr(self, "_hyper_ring", None) is None or self._hyper_dev.numel() != k or self._hyper_dev.device != device:
+            self._hyper_ring = _PinnedRing(k)
+            self._hyper_dev = torch.zeros(k, dtype=torch.float32, device=device)
         b0, b1 = self.betas
-        self._hyper_host[0] = math.sqrt(1.0 - b1 ** n) / (1.0 - b0 ** n)
-        for i, g in enumerate(self.param_groups):
-            self._hyper_host[1 + i] = float(g["lr"])
+        self._hyper_ring.upload([math.sqrt(1.0 - b1 ** n) / (1.0 - b0 ** n)] + [float(g["lr"]) for g in self.param_groups],
+                                self._hyper_dev)
 
     @torch.no_grad()
     def _launch(self):
-        """Device side of one step (capturable): refresh the hyper buffer, one multi-tensor kernel per 32 tensors."""
+        """Device side of one step (capturable): one multi-tensor kernel per 32 tensors, hyper-parameters from the device
+        buffer _prepare_hyper filled."""
         entries, keep = [], []
         dev = None
         for gi, g in enumerate(self.param_groups):
@@ -165,9 +195,6 @@ class Adam:
                 entries.append(e)
         if not entries:
             return
-        if self._hyper_dev is None:
-            self._hyper_dev = torch.zeros_like(self._hyper_host, device=dev)
-        self._hyper_dev.copy_(self._hyper_host, non_blocking=True)
         arr = (L.TvmAdamTensor * len(entries))(*entries)
         L.check(L.load().tvm_adam_step(arr, len(entries), float(self.betas[0]), float(self.betas[1]), float(self.eps),
                                        int(self.n_step), _ptr(self._hyper_dev), _stream_ptr()), "tvm_adam_step")
@@ -205,9 +232,11 @@ class TrainStepGraph:
         self.S, self.white_bg = int(N_samples), bool(white_bg)
         self.use = dict(tv_d=TV_weight_density > 0, tv_a=TV_weight_app > 0, l1=L1_reg_weight > 0, ortho=Ortho_reg_weight > 0,
                         pen=normal_vector_penalty_weight > 0)
-        self._w_host = torch.tensor([TV_weight_density, TV_weight_app, L1_reg_weight, Ortho_reg_weight,
-                                     normal_vector_penalty_weight], dtype=torch.float32).pin_memory()
-        self._w_dev = self._w_host.to(dev)
+        self._w = [float(TV_weight_density), float(TV_weight_app), float(L1_reg_weight), float(Ortho_reg_weight),
+                   float(normal_vector_penalty_weight)]
+        self._w_ring = _PinnedRing(len(self._w))
+        self._w_dev = torch.tensor(self._w, dtype=torch.float32, device=dev)
+        self._signature = None
         self._tv = TVLoss()
         self.loss = torch.zeros(1, dtype=torch.float32, device=dev)          # MSE of the step (train.py:228)
         self.reg_loss = torch.zeros(1, dtype=torch.float32, device=dev)      # sum of the weighted regularisers
@@ -218,12 +247,11 @@ class TrainStepGraph:
                     normal_vector_penalty_weight=None):
         for i, v in enumerate((TV_weight_density, TV_weight_app, L1_reg_weight, Ortho_reg_weight, normal_vector_penalty_weight)):
             if v is not None:
-                self._w_host[i] = float(v)
+                self._w[i] = float(v)
 
     def _body(self):
         """The step without the autograd engine: every kernel is enqueued by this thread on the capturing stream."""
         m, lib = self.model, L.load()
-        self._w_dev.copy_(self._w_host, non_blocking=True)
         n = self.rays.shape[0]
         jitter = self.jitter if self.jitter is not None else torch.rand(n, dtype=torch.float32, device=self.rays.device)
         flags = m._flags(self.white_bg)
@@ -258,44 +286,79 @@ class TrainStepGraph:
         self.opt._launch()
         m._pack(force=True)                       # the next forward (and any render in between) sees the updated grids
 
+    def _upload_scalars(self):
+        """Per-step scalars -> device, eagerly and stream-ordered in front of the replay (never from inside the graph: a
+        captured pinned-host read would see whatever the host has written by the time the replay runs)."""
+        self.opt._prepare_hyper()
+        self._w_ring.upload(self._w, self._w_dev)
+
+    def _capture_signature(self):
+        """Everything a captured graph holds by raw pointer or by value.  Maintenance calls (updateAlphaMask, shrink,
+        upsample_volume_grid, load) and changes of mlp_mode / app_planes_bf16 replace these; step() then re-captures."""
+        m = self.model
+        am = m.alphaMask
+        return (tuple(p.data_ptr() for p in m._param_list()), tuple(int(g) for g in m.gridSize),
+                None if am is None else (am.bits.data_ptr(), am.bricks.data_ptr(), am.dilated.data_ptr(), tuple(int(g) for g in am.gridSize)),
+                tuple(float(a) for a in m.aabb.reshape(-1)), m.mlp_mode, m.app_planes_bf16, m.early_termination,
+                m.empty_space_skipping, bool(m.grad_sync),
+                None if m._packed is None else m._packed.data_ptr(),
+                None if getattr(m, "_grads_packed", None) is None else m._grads_packed.data_ptr(),
+                None if m._ws is None else (m._ws.data_ptr(), m._ws.numel()),
+                None if m._tc is None else m._tc.data_ptr(),
+                None if getattr(m, "_app16", None) is None else m._app16.data_ptr())
+
     def capture(self):
         """Warm up on a side stream (torch's capture protocol), then record the step.  The warm-up steps are real
-        optimisation steps on whatever the static buffers hold: parameters and optimiser state are snapshotted and restored."""
+        optimisation steps on whatever the static buffers hold: parameters, the step counter AND the Adam moments are
+        snapshotted and restored (moments created by the warm-up itself are zeroed), so capturing -- or re-capturing after a
+        maintenance call -- does not disturb a run in progress."""
         m, opt = self.model, self.opt
         params = [p for g in opt.param_groups for p in g["params"]]
+        live = {id(p) for p in m._param_list()}
+        if not live <= {id(p) for p in params}:
+            raise RuntimeError("TrainStepGraph: the optimizer does not hold the model's current parameters (the grids were "
+                               "replaced by upsample_volume_grid / shrink / load): build a new optimizer and a new TrainStepGraph")
         snap = [p.detach().clone() for p in params]
+        state_snap = {k: (mv[0].clone(), mv[1].clone()) for k, mv in opt.state.items()}
         n_step0 = opt.n_step
         s = torch.cuda.Stream(device=m.device)
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             for _ in range(2):
-                opt._prepare_hyper()
+                self._upload_scalars()
                 self._body()
         torch.cuda.current_stream().wait_stream(s)
         self.graph = torch.cuda.CUDAGraph()
-        opt._prepare_hyper()
+        self._upload_scalars()
         with torch.cuda.graph(self.graph, capture_error_mode=os.environ.get("TVM_GRAPH_CAPTURE_MODE", "global")):
             self._body()
         with torch.no_grad():
             for p, q in zip(params, snap):
                 p.copy_(q)
-            for mv in opt.state.values():
-                mv[0].zero_()
-                mv[1].zero_()
+            for k, mv in opt.state.items():
+                if k in state_snap and state_snap[k][0].shape == mv[0].shape:
+                    mv[0].copy_(state_snap[k][0])
+                    mv[1].copy_(state_snap[k][1])
+                else:
+                    mv[0].zero_()
+                    mv[1].zero_()
         opt.n_step = n_step0
         m._pack(force=True)
+        self._signature = self._capture_signature()
 
     def step(self, rays, target, jitter=None):
         if jitter is not None and self.jitter is None:
             if self.graph is not None:
                 raise RuntimeError("pass jitter from the first step on (the graph was captured with on-device random jitter)")
             self.jitter = torch.zeros(self.rays.shape[0], dtype=torch.float32, device=self.rays.device)
-        if self.graph is None:
+        if self.graph is None or self._signature != self._capture_signature():
+            # first use, or a maintenance call replaced buffers the graph points at: record the step again
+            self.graph = None
             self.capture()
         if jitter is not None:
             self.jitter.copy_(jitter, non_blocking=True)
         self.rays.copy_(rays, non_blocking=True)
         self.target.copy_(target, non_blocking=True)
-        self.opt._prepare_hyper()
+        self._upload_scalars()
         self.graph.replay()
         return self.loss

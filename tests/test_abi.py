@@ -29,8 +29,9 @@ def test_abi_version_and_struct_sizes(built_lib):
     probe = r'''
 #include <stdio.h>
 #include "tvmrender.h"
-int main(){ printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(TvmModel), sizeof(TvmAux), sizeof(TvmGrads), sizeof(TvmBgNet),
-                   sizeof(TvmBgGrads), sizeof(TvmTransposeJob), sizeof(TvmTvJob), sizeof(TvmAdamTensor)); return 0; }
+int main(){ printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(TvmModel), sizeof(TvmAux), sizeof(TvmGrads), sizeof(TvmBgNet),
+                   sizeof(TvmBgGrads), sizeof(TvmTransposeJob), sizeof(TvmTvJob), sizeof(TvmAdamTensor),
+                   sizeof(TvmWorkspaceLayout)); return 0; }
 '''
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "p.c"), "w").write(probe)
@@ -39,7 +40,8 @@ int main(){ printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(TvmModel), sizeof
         out = subprocess.check_output([os.path.join(d, "p")]).split()
     L = built_lib._lib
     assert [int(x) for x in out] == [ctypes.sizeof(t) for t in (L.TvmModel, L.TvmAux, L.TvmGrads, L.TvmBgNet, L.TvmBgGrads,
-                                                                  L.TvmTransposeJob, L.TvmTvJob, L.TvmAdamTensor)]
+                                                                  L.TvmTransposeJob, L.TvmTvJob, L.TvmAdamTensor,
+                                                                  L.TvmWorkspaceLayout)]
 
 
 def test_fails_loudly_without_gpu(built_lib):
@@ -59,3 +61,11 @@ def test_workspace_bytes(built_lib):
     assert out.value >= 4096 * 440 * 24
     assert lib.tvm_workspace_bytes(0, 440, ctypes.byref(out)) != 0
     assert b"bad arguments" in lib.tvm_last_error()
+    # tvm_workspace_layout: the members a caller may read back lie inside the workspace, 256-byte aligned, in carve order
+    lay = built_lib._lib.TvmWorkspaceLayout()
+    assert lib.tvm_workspace_layout(4096, 440, ctypes.byref(lay)) == 0
+    assert lib.tvm_workspace_bytes(4096, 440, ctypes.byref(out)) == 0 and lay.bytes == out.value
+    assert lay.capacity == 4096 * 440 and lay.n_blocks == 14 and lay.n_entries == 0
+    offs = [lay.n_entries, lay.blk_mask, lay.blk_base, lay.ent, lay.ent_w, lay.ent_rgb, lay.acc, lay.rgb_sum]
+    assert all(o % 256 == 0 and o < lay.bytes for o in offs) and sorted(offs[:5]) == offs[:5]
+    assert lay.blk_base - lay.blk_mask >= 4096 * 14 * 4 and lay.ent_w - lay.ent >= lay.capacity * 8
