@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define TVM_ABI_VERSION 21
+#define TVM_ABI_VERSION 22
 
 /* flags for tvm_forward / tvm_backward */
 #define TVM_WHITE_BG      0x1u  /* rgb_map += 1 - acc_map          (tensorBase.py:523-524) */
@@ -380,6 +380,27 @@ typedef struct TvmAdamTensor {
 } TvmAdamTensor;
 int tvm_adam_step(const TvmAdamTensor* tensors_host, int n_tensors, float beta0, float beta1, float eps, int step,
                   const float* hyper_dev, void* stream);
+
+/* ---- data-parallel training: gradient exchange over NVLink peer memory --------------------------------- */
+/* In-place SUM all-reduce of floats [offset, offset + n) of a buffer every rank of ONE NVSwitch node holds at the same
+ * (symmetric) allocation, written directly over peer memory (no NCCL): two-shot in one kernel -- rank r reduces slice r
+ * (NVLS: multimem.ld_reduce adds inside the switch and multimem.st broadcasts; without a multicast address: peer loads and
+ * peer stores), bracketed by per-CTA flag barriers with the same CTA of every peer.  Plain kernel nodes: capturable into a
+ * CUDA graph; the result is bit-identical on every rank.  Every rank must enqueue the same sequence of calls.
+ * The reference (train.py:260) is single-process: this replaces the all-reduce a data-parallel Jittor run would issue.     */
+#define TVM_AR_MAX_WORLD 16
+#define TVM_AR_MAX_CTAS 128
+typedef struct TvmPeerComm {
+  void* bufs[TVM_AR_MAX_WORLD];         /* peer-mapped DEVICE pointers to the symmetric buffer, index = rank (own included)   */
+  uint32_t* signals[TVM_AR_MAX_WORLD];  /* peer-mapped pointers to each rank's signal pad: tvm_allreduce_signal_words uint32,
+                                           zeroed once before the first call (then never reset: flags carry an epoch)          */
+  void* multicast;                      /* NVLS multicast address of the buffer, or NULL (peer-to-peer path)                 */
+  uint32_t* epoch_dev;                  /* this rank's call counter (device, zeroed once)                                    */
+  int32_t rank, world;
+} TvmPeerComm;
+int tvm_allreduce_signal_words(int world, size_t* out_words);
+/* offset_floats and n_floats must be multiples of 4; n_ctas (1..TVM_AR_MAX_CTAS, the same on every rank) CTAs of 512 threads */
+int tvm_allreduce_sum(const TvmPeerComm* comm_host, size_t offset_floats, size_t n_floats, int n_ctas, void* stream);
 
 /* Known-answer self-test of the tcgen05 shared-memory descriptor conventions (K-major and MN-major reads of one image);
  * P [128][128], Q [128][160], W [128][128] fp32 -> D1 = P^T Q [128][160], D2 = P W [128][128], D3 = P W^T [128][128].

@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # TVM_LIB: developer override (kernel-tuning experiments build variant libraries next to the default one)
 LIB_PATH = os.environ.get("TVM_LIB") or os.path.join(_HERE, "libtvmrender.so")
-ABI_VERSION = 21
+ABI_VERSION = 22
 
 # flags (tvmrender.h)
 WHITE_BG = 0x1
@@ -61,6 +61,14 @@ class TvmWorkspaceLayout(C.Structure):
                 ("capacity", C.c_uint32), ("n_blocks", C.c_int32), ("bytes", C.c_size_t)]
 
 
+AR_MAX_WORLD, AR_MAX_CTAS = 16, 128
+
+
+class TvmPeerComm(C.Structure):
+    _fields_ = [("bufs", C.c_void_p * AR_MAX_WORLD), ("signals", C.c_void_p * AR_MAX_WORLD), ("multicast", C.c_void_p),
+                ("epoch_dev", C.c_void_p), ("rank", C.c_int32), ("world", C.c_int32)]
+
+
 class TvmBgNet(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("w0_t", "b0", "w1_t", "b1", "w2_t", "b2", "w_sigma", "b_sigma", "wf_t", "bf",
                                            "wv_t", "w_rgb", "b_rgb", "tc_weights")]
@@ -104,6 +112,7 @@ EXPORTS = [
     "tvm_profile_enable", "tvm_profile_collect",
     "tvm_dense_alpha", "tvm_alpha_mask_from_dense", "tvm_filter_rays", "tvm_generate_rays", "tvm_upsample_grid",
     "tvm_tv_loss", "tvm_tv_loss_batch", "tvm_l1_loss", "tvm_vector_diffs", "tvm_adam_step", "tvm_selftest_umma", "tvm_bench_gather",
+    "tvm_allreduce_signal_words", "tvm_allreduce_sum",
 ]
 
 
@@ -173,6 +182,8 @@ def load() -> C.CDLL:
     lib.tvm_bg_fold_bwd.argtypes = [vp] * 11
     lib.tvm_density_alpha.argtypes = [C.POINTER(TvmModel), vp, i32, f32, vp, vp]
     lib.tvm_mse_loss.argtypes = [vp, vp, i32, f32, vp, vp, vp]
+    lib.tvm_allreduce_signal_words.argtypes = [i32, C.POINTER(C.c_size_t)]
+    lib.tvm_allreduce_sum.argtypes = [C.POINTER(TvmPeerComm), C.c_size_t, C.c_size_t, i32, vp]
     lib.tvm_profile_enable.argtypes = [i32]
     lib.tvm_profile_collect.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_int)]
     for name in EXPORTS:

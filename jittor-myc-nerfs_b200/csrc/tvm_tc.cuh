@@ -24,15 +24,21 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t a = smem_u32(bar);
   uint32_t done = 0;
+  // try_wait suspends the thread in hardware until the phase completes or the time hint (ns) runs out, so a waiting
+  // warp costs one issue slot per ~20 us instead of one spin iteration per ~50 cycles (the spin loops of the waiting MLP
+  // threads were 12-19 % of all instructions k_app_tc2 executed before the hint, profiles/r02_notes.txt)
+#ifndef TVM_MBAR_HINT_NS
+#define TVM_MBAR_HINT_NS 20000
+#endif
   for (uint32_t spin = 0; !done; ++spin) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.b32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(a), "r"(parity)
+        : "r"(a), "r"(parity), "r"((uint32_t)TVM_MBAR_HINT_NS)
         : "memory");
-    if (spin > (1u << 24)) __trap();   // a lost tcgen05.commit must fail the launch, not hang the GPU
+    if (spin > (1u << 20)) __trap();   // a lost tcgen05.commit must fail the launch, not hang the GPU
   }
 }
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {

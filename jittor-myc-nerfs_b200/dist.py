@@ -71,6 +71,55 @@ def allreduce_flat_(flat: torch.Tensor, group=None, average=True):
     return flat
 
 
+class PeerComm:
+    """Symmetric-memory communicator of tvm_allreduce_sum (include/tvmrender.h): a flat fp32 buffer every rank of the node
+    allocates identically (torch.distributed._symmetric_memory: cuMem allocations mapped into every peer, plus the NVLS
+    multicast mapping when the fabric has one), a signal pad, and this rank's epoch counter.  Construction is a collective.
+    The all-reduce itself is libtvmrender's own kernel over those peer pointers -- no NCCL call on the training path."""
+
+    def __init__(self, n_floats: int, device, group=None, n_ctas: int = 64):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib as L
+        group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > L.AR_MAX_WORLD:
+            raise L.TvmError(f"tvm_allreduce_sum handles up to {L.AR_MAX_WORLD} peers of one node")
+        n_floats = (int(n_floats) + 3) // 4 * 4
+        lib = L.load()
+        words = C.c_size_t(0)
+        L.check(lib.tvm_allreduce_signal_words(self.world, C.byref(words)), "tvm_allreduce_signal_words")
+        self.buf = symm_mem.empty(n_floats, dtype=torch.float32, device=device)
+        self.sig = symm_mem.empty(int(words.value), dtype=torch.int32, device=device)
+        self.buf.zero_()
+        self.sig.zero_()
+        self._hdl = symm_mem.rendezvous(self.buf, group)
+        self._sig_hdl = symm_mem.rendezvous(self.sig, group)
+        self.epoch = torch.zeros(1, dtype=torch.int32, device=device)
+        c = L.TvmPeerComm()
+        for p in range(self.world):
+            c.bufs[p] = int(self._hdl.buffer_ptrs[p])
+            c.signals[p] = int(self._sig_hdl.buffer_ptrs[p])
+        mc = int(getattr(self._hdl, "multicast_ptr", 0) or 0)
+        if os.environ.get("TVM_AR_NO_MULTICAST"):
+            mc = 0
+        c.multicast = mc or None
+        c.epoch_dev = self.epoch.data_ptr()
+        c.rank, c.world = self.rank, self.world
+        self.struct, self.multicast, self.n_ctas = c, bool(mc), int(n_ctas)
+        torch.cuda.synchronize(device)
+        dist.barrier(group)          # every pad is zero before anybody signals
+
+    def allreduce_(self, offset_floats=0, n_floats=None):
+        """In-place sum over the ranks of buf[offset : offset + n] on the current stream."""
+        import ctypes as C
+        from . import _lib as L
+        n = self.buf.numel() - offset_floats if n_floats is None else n_floats
+        L.check(L.load().tvm_allreduce_sum(C.byref(self.struct), int(offset_floats), int(n), self.n_ctas,
+                                           C.c_void_p(torch.cuda.current_stream().cuda_stream)), "tvm_allreduce_sum")
+        return self.buf
+
+
 class ShardedSampler:
     """SimpleSampler (train.py:25-37) for data-parallel training: every rank draws the SAME
     permutation (same seed) and takes its slice of each global batch."""

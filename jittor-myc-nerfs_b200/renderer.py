@@ -34,15 +34,24 @@ def _render_streamed(rays, tensorf, N_samples, white_bg, out_host):
             ev.record(cs)
             ups.append(ev)
     flags = tensorf._flags(white_bg)
-    for (s, e), ev in zip(bounds, ups):
-        main.wait_event(ev)
-        tensorf._forward_raw(st["rays"][s:e], None, flags, S, out=(st["rgb"][s:e], st["depth"][s:e]))
-        done = torch.cuda.Event()
-        done.record(main)
+    # the chunks alternate between the caller's stream and a side stream (own workspace each, TensorVMSplit._forward_chunks):
+    # tails and launch gaps of one chunk overlap with the next chunk's march
+    if getattr(tensorf, "_side_stream", None) is None:
+        tensorf._side_stream = torch.cuda.Stream(device=dev)
+    side = tensorf._side_stream
+    side.wait_stream(main)
+    for i, ((s, e), ev) in enumerate(zip(bounds, ups)):
+        stream = side if (i & 1) else main
+        with torch.cuda.stream(stream):
+            stream.wait_event(ev)
+            tensorf._forward_raw(st["rays"][s:e], None, flags, S, out=(st["rgb"][s:e], st["depth"][s:e]), ws_slot=i & 1)
+            done = torch.cuda.Event()
+            done.record(stream)
         with torch.cuda.stream(cs):
             cs.wait_event(done)
             rgb_host[s:e].copy_(st["rgb"][s:e], non_blocking=True)
             depth_host[s:e].copy_(st["depth"][s:e], non_blocking=True)
+    main.wait_stream(side)
     main.wait_stream(cs)
     return rgb_host, depth_host
 

@@ -201,9 +201,10 @@ class TensorVMSplit(MaintainMixin, RegularizerMixin, CheckpointMixin, torch.nn.M
         self.empty_space_skipping = True
         self.collect_counters = False
         self.counters = torch.zeros(L.CNT_WORDS, dtype=torch.int64, device=device)
-        self.ws_budget_bytes = int(float(os.environ.get("TVM_WS_GIB", "32")) * (1 << 30))   # one launch per 800x800 frame (29 GB of the 180 GB)
+        self.ws_budget_bytes = int(float(os.environ.get("TVM_WS_GIB", "8")) * (1 << 30))    # both workspaces of the evaluation pipeline (an 800x800 frame: 8 chunks)
         self.grad_sync = False          # set True (after dist.init_from_env) for data-parallel training
         self.grad_sync_group = None
+        self._peer_comm = None          # enable_peer_allreduce(): libtvmrender's own all-reduce over NVLink peer memory
         self._ws = None
         self._fwd_gen = 0               # bumped by every tvm_forward* on the shared workspace (see _forward_stamp)
         self._packed = None
@@ -471,15 +472,45 @@ class TensorVMSplit(MaintainMixin, RegularizerMixin, CheckpointMixin, torch.nn.M
         return out.value
 
     def max_rays_per_launch(self, S):
+        """Rays per tvm_forward launch: the workspace is sized for the worst case (every sample weighted, 44 B x n x S); the
+        budget covers the TWO workspaces of the evaluation pipeline."""
         per_ray = self.workspace_bytes(1024, S) / 1024.0
-        return max(1024, int(self.ws_budget_bytes / per_ray) // 1024 * 1024)
+        return max(1024, int(self.ws_budget_bytes / 2 / per_ray) // 1024 * 1024)
 
-    def _workspace(self, n, S):
+    def _workspace(self, n, S, slot=0):
+        """Caller-owned scratch of tvm_forward.  Slot 0 is THE workspace (what tvm_backward and workspace_view read); slot 1
+        is the second buffer of the two-stream evaluation pipeline (_forward_chunks)."""
         need = self.workspace_bytes(n, S)
-        if self._ws is None or self._ws.numel() < need:
-            self._ws = None
-            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
-        return self._ws
+        if slot == 0:
+            if self._ws is None or self._ws.numel() < need:
+                self._ws = None
+                self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+            return self._ws
+        if getattr(self, "_ws2", None) is None or self._ws2.numel() < need:
+            self._ws2 = None
+            self._ws2 = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._ws2
+
+    def _forward_chunks(self, rays, jitter, flags, S, rgb, depth, nmax):
+        """Evaluation render of more rays than one workspace holds: the chunks alternate between the caller's stream and a
+        side stream, each with its own workspace, so that the tail of one chunk's kernels (and the launch gaps between its
+        five dependent launches) overlap with the next chunk's march.  Rays are independent and compositing is per ray, so the
+        pixels do not depend on the chunking (tests/test_gpu_forward.py::test_full_frame_properties)."""
+        main = torch.cuda.current_stream()
+        if getattr(self, "_side_stream", None) is None:
+            self._side_stream = torch.cuda.Stream(device=rays.device)
+        side = self._side_stream
+        side.wait_stream(main)
+        n = rays.shape[0]
+        for i, s in enumerate(range(0, n, nmax)):
+            e = min(n, s + nmax)
+            args = (rays[s:e], None if jitter is None else jitter[s:e], flags, S)
+            if i & 1:
+                with torch.cuda.stream(side):
+                    self._forward_raw(*args, out=(rgb[s:e], depth[s:e]), ws_slot=1)
+            else:
+                self._forward_raw(*args, out=(rgb[s:e], depth[s:e]))
+        main.wait_stream(side)
 
     def workspace_view(self, n, S):
         """What the last tvm_forward over (n rays, S samples) left in the workspace (tvmrender.h: TvmWorkspaceLayout):
@@ -540,12 +571,12 @@ class TensorVMSplit(MaintainMixin, RegularizerMixin, CheckpointMixin, torch.nn.M
             f |= L.NO_ERT
         return f
 
-    def _forward_raw(self, rays, jitter, flags, S, aux=None, out=None):
+    def _forward_raw(self, rays, jitter, flags, S, aux=None, out=None, ws_slot=0):
         lib = L.load()
         n = rays.shape[0]
         assert rays.is_cuda and rays.dtype == torch.float32 and rays.is_contiguous() and rays.shape[1] == 6
         model = self._model()
-        ws = self._workspace(n, S)
+        ws = self._workspace(n, S, ws_slot)
         self._fwd_gen += 1
         if out is None:
             rgb = torch.empty((n, 3), dtype=torch.float32, device=rays.device)
@@ -558,12 +589,28 @@ class TensorVMSplit(MaintainMixin, RegularizerMixin, CheckpointMixin, torch.nn.M
                                 _ptr(ws), ws.numel(), _stream_ptr()), "tvm_forward")
         return rgb, depth
 
+    def enable_peer_allreduce(self, group=None, n_ctas=64):
+        """Data-parallel training without NCCL on the step: the flat gradient buffer moves into symmetric memory and is
+        summed by tvm_allreduce_sum (two-shot over NVLink peer memory / NVLS multicast).  Collective: every rank calls it,
+        after dist.init_from_env, with the grids at their current size (call it again after upsample_volume_grid)."""
+        from .dist import PeerComm
+        _, total = self._layout()
+        self._peer_comm = PeerComm(total, self.device, group, n_ctas)
+        self._grads_packed = self._peer_comm.buf[:total]
+        self.grad_sync, self.grad_sync_group = True, group
+        self.grad_sync_kind = ("libtvmrender two-shot all-reduce over NVLink peer memory (" +
+                               ("NVLS multimem.ld_reduce / multimem.st" if self._peer_comm.multicast else "peer loads / stores") +
+                               f", {n_ctas} CTAs) of the flat packed fp32 gradient buffer")
+        return self._peer_comm
+
     def _backward_raw(self, rays, jitter, flags, S, rgb, d_rgb, d_penalty=None):
         lib = L.load()
         n = rays.shape[0]
         model = self._model()
         items, total = self._layout()
         if getattr(self, "_grads_packed", None) is None or self._grads_packed.numel() != total:
+            if self._peer_comm is not None:
+                raise L.TvmError("the parameter layout changed under enable_peer_allreduce(): call it again (collective)")
             self._grads_packed = torch.empty(total, dtype=torch.float32, device=self.device)
         gp = self._grads_packed
         gp.zero_()
@@ -581,8 +628,11 @@ class TensorVMSplit(MaintainMixin, RegularizerMixin, CheckpointMixin, torch.nn.M
         L.check(lib.tvm_backward(C.byref(model), _ptr(rays), n, int(S), _ptr(jitter), flags, _ptr(rgb), _ptr(d_rgb),
                                  _ptr(d_penalty), C.byref(gs), _ptr(ws), ws.numel(), _stream_ptr()), "tvm_backward")
         if self.grad_sync:
-            from .dist import allreduce_flat_
-            allreduce_flat_(gp, group=self.grad_sync_group, average=False)
+            if self._peer_comm is not None:
+                self._peer_comm.allreduce_(0, (total + 3) // 4 * 4)
+            else:
+                from .dist import allreduce_flat_
+                allreduce_flat_(gp, group=self.grad_sync_group, average=False)
         return self._unpack_grads(gp, items)
 
     def _unpack_grads(self, gp, items):
@@ -649,9 +699,7 @@ class TensorVMSplit(MaintainMixin, RegularizerMixin, CheckpointMixin, torch.nn.M
             return self._forward_raw(rays, jitter, flags, S)
         rgb = torch.empty((n, 3), dtype=torch.float32, device=rays.device)
         depth = torch.empty((n,), dtype=torch.float32, device=rays.device)
-        for s in range(0, n, nmax):
-            e = min(n, s + nmax)
-            self._forward_raw(rays[s:e], None if jitter is None else jitter[s:e], flags, S, out=(rgb[s:e], depth[s:e]))
+        self._forward_chunks(rays, jitter, flags, S, rgb, depth, nmax)
         return rgb, depth
 
     execute = forward
@@ -760,13 +808,14 @@ class REFTensoRF(TensorVMSplit):
             o += k
         return out
 
-    def _forward_raw(self, rays, jitter, flags, S, aux=None, out=None):
+    def _forward_raw(self, rays, jitter, flags, S, aux=None, out=None, ws_slot=0):
         if aux is None:
             aux = L.TvmAux()
-            self._penalty_buf.zero_()
+            if ws_slot == 0:        # chunked renders: the first chunk of a pair zeroes, both accumulate (atomics)
+                self._penalty_buf.zero_()
             aux.penalty = self._penalty_buf.data_ptr()
             self.penalty = self._penalty_buf
-        return super()._forward_raw(rays, jitter, flags, S, aux=aux, out=out)
+        return super()._forward_raw(rays, jitter, flags, S, aux=aux, out=out, ws_slot=ws_slot)
 
 
 class _Seq(torch.nn.ModuleList):

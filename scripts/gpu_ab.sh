@@ -5,7 +5,7 @@ TAG=${1:-ab}; shift
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
 V=$PWD/jittor-myc-nerfs_b200/variants
-B="python bench.py --steps 10 --warmup 3 --no-cpu-baseline $BARGS"
+B="python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-extras $BARGS"
 timeout 300 $B > $OUT/bench_default.json 2> $OUT/bench_default.err || tail -3 $OUT/bench_default.err
 for v in "$@"; do
   TVM_LIB=$V/libtvmrender_$v.so timeout 300 $B > $OUT/bench_$v.json 2> $OUT/bench_$v.err || tail -3 $OUT/bench_$v.err

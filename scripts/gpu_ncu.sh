@@ -4,7 +4,7 @@
 TAG=$1; NAME=$2; KRE=$3; SKIP=$4; COUNT=$5; shift 6
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
-CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline $@"
+CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extras $@"
 timeout 600 $CMD > $OUT/${NAME}_plain.log 2>&1 || { echo "plain run failed"; tail -5 $OUT/${NAME}_plain.log; exit 1; }
 timeout 1200 ncu --set full --clock-control none --import-source on -k "regex:$KRE" -s $SKIP -c $COUNT -f -o $OUT/$NAME $CMD > $OUT/${NAME}_ncu.log 2>&1
 echo "ncu $NAME rc=$?"; tail -2 $OUT/${NAME}_ncu.log
