@@ -307,7 +307,11 @@ def measure_train(args, rank, local_rank, world, dist):
     rays = torch.from_numpy(np.ascontiguousarray(pool[perm[r8 * n:(r8 + 1) * n]])).to(dev)
     S = int(np.linalg.norm(np.asarray(mp.gridSize, dtype=np.float64)) / mp.step_ratio)     # cal_n_samples, utils.py:61-62
     tgt = torch.from_numpy(fx.target_rgb(n)).to(dev)
-    model.grad_sync = world > 1
+    if world > 1:
+        if os.environ.get("TVM_AR", "peer") == "nccl":       # A/B switch: the NCCL all_reduce the step used in round 1
+            model.grad_sync = True
+        else:
+            model.enable_peer_allreduce(n_ctas=int(os.environ.get("TVM_AR_CTAS", "64")))
     opt = pkg.Adam(model.get_optparam_groups(0.02, 0.001), betas=(0.9, 0.99))
     gstep = pkg.TrainStepGraph(model, opt, n, S, white_bg=True, TV_weight_density=2.0, TV_weight_app=2.0)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)

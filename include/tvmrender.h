@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define TVM_ABI_VERSION 22
+#define TVM_ABI_VERSION 23
 
 /* flags for tvm_forward / tvm_backward */
 #define TVM_WHITE_BG      0x1u  /* rgb_map += 1 - acc_map          (tensorBase.py:523-524) */
@@ -395,12 +395,34 @@ typedef struct TvmPeerComm {
   uint32_t* signals[TVM_AR_MAX_WORLD];  /* peer-mapped pointers to each rank's signal pad: tvm_allreduce_signal_words uint32,
                                            zeroed once before the first call (then never reset: flags carry an epoch)          */
   void* multicast;                      /* NVLS multicast address of the buffer, or NULL (peer-to-peer path)                 */
-  uint32_t* epoch_dev;                  /* this rank's call counter (device, zeroed once)                                    */
+  uint32_t* epoch_dev;                  /* this rank's call counter: TWO device words, zeroed once                           */
   int32_t rank, world;
 } TvmPeerComm;
 int tvm_allreduce_signal_words(int world, size_t* out_words);
 /* offset_floats and n_floats must be multiples of 4; n_ctas (1..TVM_AR_MAX_CTAS, the same on every rank) CTAs of 512 threads */
 int tvm_allreduce_sum(const TvmPeerComm* comm_host, size_t offset_floats, size_t n_floats, int n_ctas, void* stream);
+
+/* tvm_backward with the gradient exchange of a data-parallel step fused into its schedule: the flat gradient buffer
+ * [0, total) the TvmGrads point into is the communicator's symmetric buffer, laid out density grids first ([0, split)), then
+ * appearance grids / basis / MLP ([split, total)).  As soon as the appearance backward has finished, [split, total) is
+ * all-reduced on `side_stream` while the density scatter (k_march_bwd) runs on `stream`; [0, split) follows on `stream`.
+ * On return (stream order) the whole buffer holds the sum over the ranks.                                              */
+typedef struct TvmGradExchange {
+  const TvmPeerComm* comm;
+  size_t split_floats, total_floats;     /* multiples of 4 */
+  int32_t n_ctas;                         /* grid of the exposed all-reduce ([0, split))                                      */
+  int32_t n_ctas_overlapped;              /* grid of the all-reduce that shares the SMs with k_march_bwd (keep it small)      */
+  void* side_stream;                      /* a second stream of the caller, != stream                                         */
+  int32_t phase;                          /* 0: the whole backward, both exchanges, joined into `stream` on return.
+                                             1 / 2: the two halves as separate calls that leave BOTH exchanges on side_stream and do
+                                             not join -- 1 = appearance backward + exchange of [split, total); 2 = density scatter +
+                                             exchange of [0, split).  The caller records an event on side_stream after each call and
+                                             waits for it before touching that half, so the appearance tail of the step (gradient
+                                             unpack, regularisers, Adam) can run while the density half is still on the wire.      */
+} TvmGradExchange;
+int tvm_backward_dp(const TvmModel* m_host, const float* rays, int n_rays, int n_samples, const float* jitter,
+                    uint32_t flags, const float* rgb_map, const float* d_rgb_map, const float* d_penalty,
+                    const TvmGrads* grads_host, void* ws, size_t ws_bytes, const TvmGradExchange* xchg, void* stream);
 
 /* Known-answer self-test of the tcgen05 shared-memory descriptor conventions (K-major and MN-major reads of one image);
  * P [128][128], Q [128][160], W [128][128] fp32 -> D1 = P^T Q [128][160], D2 = P W [128][128], D3 = P W^T [128][128].

@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # TVM_LIB: developer override (kernel-tuning experiments build variant libraries next to the default one)
 LIB_PATH = os.environ.get("TVM_LIB") or os.path.join(_HERE, "libtvmrender.so")
-ABI_VERSION = 22
+ABI_VERSION = 23
 
 # flags (tvmrender.h)
 WHITE_BG = 0x1
@@ -69,6 +69,11 @@ class TvmPeerComm(C.Structure):
                 ("epoch_dev", C.c_void_p), ("rank", C.c_int32), ("world", C.c_int32)]
 
 
+class TvmGradExchange(C.Structure):
+    _fields_ = [("comm", C.POINTER(TvmPeerComm)), ("split_floats", C.c_size_t), ("total_floats", C.c_size_t),
+                ("n_ctas", C.c_int32), ("n_ctas_overlapped", C.c_int32), ("side_stream", C.c_void_p), ("phase", C.c_int32)]
+
+
 class TvmBgNet(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("w0_t", "b0", "w1_t", "b1", "w2_t", "b2", "w_sigma", "b_sigma", "wf_t", "bf",
                                            "wv_t", "w_rgb", "b_rgb", "tc_weights")]
@@ -112,7 +117,7 @@ EXPORTS = [
     "tvm_profile_enable", "tvm_profile_collect",
     "tvm_dense_alpha", "tvm_alpha_mask_from_dense", "tvm_filter_rays", "tvm_generate_rays", "tvm_upsample_grid",
     "tvm_tv_loss", "tvm_tv_loss_batch", "tvm_l1_loss", "tvm_vector_diffs", "tvm_adam_step", "tvm_selftest_umma", "tvm_bench_gather",
-    "tvm_allreduce_signal_words", "tvm_allreduce_sum",
+    "tvm_allreduce_signal_words", "tvm_allreduce_sum", "tvm_backward_dp",
 ]
 
 
@@ -177,6 +182,8 @@ def load() -> C.CDLL:
     lib.tvm_adam_step.argtypes = [C.POINTER(TvmAdamTensor), i32, f32, f32, f32, i32, vp, vp]
     lib.tvm_backward.argtypes = [C.POINTER(TvmModel), vp, i32, i32, vp, u32, vp, vp, vp, C.POINTER(TvmGrads), vp,
                                  C.c_size_t, vp]
+    lib.tvm_backward_dp.argtypes = [C.POINTER(TvmModel), vp, i32, i32, vp, u32, vp, vp, vp, C.POINTER(TvmGrads), vp,
+                                    C.c_size_t, C.POINTER(TvmGradExchange), vp]
     lib.tvm_backward_npp.argtypes = [C.POINTER(TvmModel), C.POINTER(TvmBgNet), vp, i32, i32, vp, vp, u32, vp, vp,
                                      C.POINTER(TvmGrads), C.POINTER(TvmBgGrads), vp, C.c_size_t, vp]
     lib.tvm_bg_fold_bwd.argtypes = [vp] * 11

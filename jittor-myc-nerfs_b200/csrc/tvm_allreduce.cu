@@ -25,7 +25,7 @@ struct Params {
   float* bufs[kMaxWorld];          // peer pointers to the symmetric buffer (index = rank)
   uint32_t* signals[kMaxWorld];    // peer pointers to the signal pads
   float* multicast;                // NVLS address of the buffer, or nullptr
-  const uint32_t* epoch;           // device counter, bumped by k_epoch in front of this kernel
+  uint32_t* epoch;                 // device words {calls completed, CTAs finished}: the last CTA of a launch bumps the first
   int rank, world;
   size_t offset4, n4;              // range to reduce, in float4 units
 };
@@ -70,11 +70,11 @@ __device__ __forceinline__ void peer_barrier(const Params& P, int ph, uint32_t e
   __syncthreads();
 }
 
-__global__ void k_epoch(uint32_t* epoch) { *epoch += 1u; }
-
 template <bool NVLS>
 __global__ void __launch_bounds__(kThreads, 1) k_allreduce(const Params P) {
-  const uint32_t epoch = *P.epoch;
+  // flag value of this call: calls completed so far + 1 (launches of one rank are stream-ordered, so every CTA reads the
+  // counter before the last CTA of this launch advances it)
+  const uint32_t epoch = *reinterpret_cast<volatile uint32_t*>(P.epoch) + 1u;
   peer_barrier(P, 0, epoch);
   // slice of this rank, split evenly over the CTAs
   const size_t per_rank = (P.n4 + P.world - 1) / P.world;
@@ -109,6 +109,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_allreduce(const Params P) {
     }
   }
   peer_barrier(P, 1, epoch);
+  if (threadIdx.x == 0) {
+    if (atomicAdd(P.epoch + 1, 1u) == gridDim.x - 1) {
+      P.epoch[1] = 0u;
+      __threadfence();
+      P.epoch[0] = epoch;
+    }
+  }
 }
 
 }  // namespace ar
@@ -142,7 +149,6 @@ extern "C" int tvm_allreduce_sum(const TvmPeerComm* c, size_t offset_floats, siz
   P.world = c->world;
   P.offset4 = offset_floats / 4;
   P.n4 = n_floats / 4;
-  ar::k_epoch<<<1, 1, 0, stream>>>(c->epoch_dev);
   if (P.multicast) ar::k_allreduce<true><<<n_ctas, ar::kThreads, 0, stream>>>(P);
   else ar::k_allreduce<false><<<n_ctas, ar::kThreads, 0, stream>>>(P);
   TVM_CHECK_CUDA(cudaGetLastError());

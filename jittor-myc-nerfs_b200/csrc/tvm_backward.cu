@@ -489,9 +489,14 @@ int launch_bg_bwd(const BwdParams& B, const TvmBgGrads& bg_grads, int num_sms, c
 static int backward_impl(const TvmModel* m_host, const TvmBgNet* bg_host, const float* rays, int n_rays, int n_samples,
                          const float* jitter, const float* bg_rand, uint32_t flags, const float* d_rgb_map,
                          const float* d_penalty, const TvmGrads* grads_host, const TvmBgGrads* bg_grads_host, void* ws,
-                         size_t ws_bytes, void* stream_) {
+                         size_t ws_bytes, void* stream_, const TvmGradExchange* xchg = nullptr) {
   cudaStream_t stream = (cudaStream_t)stream_;
   BwdParams B;
+  if (xchg) {
+    TVM_REQUIRE(xchg->comm && xchg->side_stream && xchg->side_stream != stream_, "TvmGradExchange needs a communicator and a second stream");
+    TVM_REQUIRE(xchg->split_floats <= xchg->total_floats && (xchg->split_floats & 3) == 0 && (xchg->total_floats & 3) == 0,
+                "TvmGradExchange: split and total must be multiples of 4 floats");
+  }
   if (bg_host) flags &= ~TVM_WHITE_BG;          // the foreground of NerfPlusPlus renders on black (nerfplusplus.py:274)
   if (int rc = fill_fwd_params(B.f, m_host, rays, n_rays, n_samples, jitter, flags, ws, ws_bytes)) return rc;
   TVM_REQUIRE(d_rgb_map && grads_host, "null argument");
@@ -511,11 +516,14 @@ static int backward_impl(const TvmModel* m_host, const TvmBgNet* bg_host, const 
   TVM_REQUIRE(B.g.basis_t && B.g.w1_t && B.g.b1 && B.g.w2_t && B.g.b2 && B.g.w3 && B.g.b3, "null gradient pointer");
   TVM_REQUIRE(!ref || B.g.head_bias, "TVM_VARIANT_REF needs TvmGrads.head_bias");
 
-  k_bwd_prep<<<(n_rays + 255) / 256, 256, 0, stream>>>(B);
-  TVM_CHECK_CUDA(cudaGetLastError());
+  const int phase = xchg ? xchg->phase : 0;       // 0: everything; 1: prep + appearance half; 2: density half
+  TVM_REQUIRE(phase >= 0 && phase <= 2, "TvmGradExchange.phase must be 0, 1 or 2");
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (phase != 2) {
+  k_bwd_prep<<<(n_rays + 255) / 256, 256, 0, stream>>>(B);
+  TVM_CHECK_CUDA(cudaGetLastError());
   if ((flags & TVM_MLP_MASK) == TVM_MLP_BF16 || ((flags & TVM_MLP_MASK) == TVM_MLP_FP16 && m_host->tc_weights_bwd)) {
     // appearance backward on the tensor cores (bf16 operands, fp32 accumulation; gradients to ~1e-2 relative)
     ProfileScope prof(TVM_STAGE_BWD_APP, stream);
@@ -529,11 +537,45 @@ static int backward_impl(const TvmModel* m_host, const TvmBgNet* bg_host, const 
     kern<<<sms, kAppThreads, smem, stream>>>(B);
   }
   TVM_CHECK_CUDA(cudaGetLastError());
+  }
+  cudaEvent_t ev_join = nullptr;
+  if (xchg && phase != 2) {
+    // every appearance gradient is final: exchange [split, total) on the side stream WHILE k_march_bwd scatters the density
+    // gradients on this one (fork / join through events: inside a stream capture these become graph edges)
+    cudaStream_t side = (cudaStream_t)xchg->side_stream;
+    cudaEvent_t ev_fork;
+    TVM_CHECK_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    TVM_CHECK_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    TVM_CHECK_CUDA(cudaEventRecord(ev_fork, stream));
+    TVM_CHECK_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
+    TVM_CHECK_CUDA(cudaEventDestroy(ev_fork));
+    if (int rc = tvm_allreduce_sum(xchg->comm, xchg->split_floats, xchg->total_floats - xchg->split_floats, xchg->n_ctas_overlapped, side)) return rc;
+    TVM_CHECK_CUDA(cudaEventRecord(ev_join, side));
+    if (phase == 1) {           // the caller joins the side stream itself (and may run the appearance tail of the step first)
+      TVM_CHECK_CUDA(cudaEventDestroy(ev_join));
+      return 0;
+    }
+  }
   {
     ProfileScope prof(TVM_STAGE_BWD_MARCH, stream);
     k_march_bwd<<<(n_rays + kMarchWarps - 1) / kMarchWarps, kMarchWarps * 32, 0, stream>>>(B);
   }
   TVM_CHECK_CUDA(cudaGetLastError());
+  if (xchg && phase == 0) {
+    TVM_CHECK_CUDA(cudaStreamWaitEvent(stream, ev_join, 0));
+    TVM_CHECK_CUDA(cudaEventDestroy(ev_join));
+    if (int rc = tvm_allreduce_sum(xchg->comm, 0, xchg->split_floats, xchg->n_ctas, stream)) return rc;
+  }
+  if (xchg && phase == 2) {
+    // density half on the side stream as well, behind the scatter: the caller's stream stays free for the appearance tail
+    cudaStream_t side = (cudaStream_t)xchg->side_stream;
+    cudaEvent_t ev;
+    TVM_CHECK_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    TVM_CHECK_CUDA(cudaEventRecord(ev, stream));
+    TVM_CHECK_CUDA(cudaStreamWaitEvent(side, ev, 0));
+    TVM_CHECK_CUDA(cudaEventDestroy(ev));
+    if (int rc = tvm_allreduce_sum(xchg->comm, 0, xchg->split_floats, xchg->n_ctas_overlapped, side)) return rc;
+  }
   if (bg_host) {
     ProfileScope prof(TVM_STAGE_BWD_BG, stream);
     if (int rc = launch_bg_bwd(B, *bg_grads_host, sms, stream)) return rc;
@@ -547,6 +589,15 @@ extern "C" int tvm_backward(const TvmModel* m_host, const float* rays, int n_ray
   (void)rgb_map;
   return backward_impl(m_host, nullptr, rays, n_rays, n_samples, jitter, nullptr, flags, d_rgb_map, d_penalty, grads_host,
                        nullptr, ws, ws_bytes, stream_);
+}
+
+extern "C" int tvm_backward_dp(const TvmModel* m_host, const float* rays, int n_rays, int n_samples, const float* jitter,
+                               uint32_t flags, const float* rgb_map, const float* d_rgb_map, const float* d_penalty,
+                               const TvmGrads* grads_host, void* ws, size_t ws_bytes, const TvmGradExchange* xchg, void* stream_) {
+  (void)rgb_map;
+  TVM_REQUIRE(xchg != nullptr, "null TvmGradExchange");
+  return backward_impl(m_host, nullptr, rays, n_rays, n_samples, jitter, nullptr, flags, d_rgb_map, d_penalty, grads_host,
+                       nullptr, ws, ws_bytes, stream_, xchg);
 }
 
 extern "C" int tvm_backward_npp(const TvmModel* m_host, const TvmBgNet* bg_host, const float* rays, int n_rays,

@@ -95,7 +95,7 @@ class PeerComm:
         self.sig.zero_()
         self._hdl = symm_mem.rendezvous(self.buf, group)
         self._sig_hdl = symm_mem.rendezvous(self.sig, group)
-        self.epoch = torch.zeros(1, dtype=torch.int32, device=device)
+        self.epoch = torch.zeros(2, dtype=torch.int32, device=device)
         c = L.TvmPeerComm()
         for p in range(self.world):
             c.bufs[p] = int(self._hdl.buffer_ptrs[p])

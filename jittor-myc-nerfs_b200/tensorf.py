@@ -596,6 +596,7 @@ class TensorVMSplit(MaintainMixin, RegularizerMixin, CheckpointMixin, torch.nn.M
         from .dist import PeerComm
         _, total = self._layout()
         self._peer_comm = PeerComm(total, self.device, group, n_ctas)
+        self._peer_total = total
         self._grads_packed = self._peer_comm.buf[:total]
         self.grad_sync, self.grad_sync_group = True, group
         self.grad_sync_kind = ("libtvmrender two-shot all-reduce over NVLink peer memory (" +
@@ -603,15 +604,21 @@ class TensorVMSplit(MaintainMixin, RegularizerMixin, CheckpointMixin, torch.nn.M
                                f", {n_ctas} CTAs) of the flat packed fp32 gradient buffer")
         return self._peer_comm
 
-    def _backward_raw(self, rays, jitter, flags, S, rgb, d_rgb, d_penalty=None):
+    def _backward_raw(self, rays, jitter, flags, S, rgb, d_rgb, d_penalty=None, pipelined=False):
+        """-> gradients in the order of _param_list() (reference shapes).  pipelined=True (peer all-reduce only): returns
+        (flat buffer, layout, event: appearance half exchanged, event: density half exchanged) instead, for
+        _unpack_part."""
         lib = L.load()
         n = rays.shape[0]
         model = self._model()
         items, total = self._layout()
         if getattr(self, "_grads_packed", None) is None or self._grads_packed.numel() != total:
             if self._peer_comm is not None:
-                raise L.TvmError("the parameter layout changed under enable_peer_allreduce(): call it again (collective)")
-            self._grads_packed = torch.empty(total, dtype=torch.float32, device=self.device)
+                if self._peer_total != total:
+                    raise L.TvmError("the parameter layout changed under enable_peer_allreduce(): call it again (collective)")
+                self._grads_packed = self._peer_comm.buf[:total]       # the gradient buffer lives in symmetric memory
+            else:
+                self._grads_packed = torch.empty(total, dtype=torch.float32, device=self.device)
         gp = self._grads_packed
         gp.zero_()
         gs = self._struct_for(gp, L.TvmGrads)
@@ -625,6 +632,34 @@ class TensorVMSplit(MaintainMixin, RegularizerMixin, CheckpointMixin, torch.nn.M
             if world > 1:
                 d_rgb = d_rgb * (1.0 / world)
                 d_penalty = None if d_penalty is None else d_penalty * (1.0 / world)
+        if self.grad_sync and self._peer_comm is not None and os.environ.get("TVM_AR_OVERLAP", "2") != "0":
+            # exchange fused into the backward schedule: the appearance part of the buffer is all-reduced on a side stream
+            # while k_march_bwd runs, the density part right after it (tvm_backward_dp)
+            if getattr(self, "_side_stream", None) is None:
+                self._side_stream = torch.cuda.Stream(device=self.device)
+            x = L.TvmGradExchange()
+            x.comm = C.pointer(self._peer_comm.struct)
+            x.split_floats, x.total_floats = items["ap0"][0], (total + 3) // 4 * 4
+            x.n_ctas, x.n_ctas_overlapped = self._peer_comm.n_ctas, int(os.environ.get("TVM_AR_CTAS_OVERLAP", "16"))
+            x.side_stream = self._side_stream.cuda_stream
+            call = lambda: L.check(lib.tvm_backward_dp(C.byref(model), _ptr(rays), n, int(S), _ptr(jitter), flags, _ptr(rgb), _ptr(d_rgb),
+                                                       _ptr(d_penalty), C.byref(gs), _ptr(ws), ws.numel(), C.byref(x), _stream_ptr()),
+                                   "tvm_backward_dp")
+            if not pipelined:
+                x.phase = 0
+                call()
+                return self._unpack_grads(gp, items)
+            # two halves, both exchanges left on the side stream: the caller (TrainStepGraph._body) runs the appearance tail
+            # of the step while the density half is on the wire
+            x.phase = 1
+            call()
+            ev_app = torch.cuda.Event()
+            ev_app.record(self._side_stream)
+            x.phase = 2
+            call()
+            ev_den = torch.cuda.Event()
+            ev_den.record(self._side_stream)
+            return gp, items, ev_app, ev_den
         L.check(lib.tvm_backward(C.byref(model), _ptr(rays), n, int(S), _ptr(jitter), flags, _ptr(rgb), _ptr(d_rgb),
                                  _ptr(d_penalty), C.byref(gs), _ptr(ws), ws.numel(), _stream_ptr()), "tvm_backward")
         if self.grad_sync:
@@ -635,7 +670,9 @@ class TensorVMSplit(MaintainMixin, RegularizerMixin, CheckpointMixin, torch.nn.M
                 allreduce_flat_(gp, group=self.grad_sync_group, average=False)
         return self._unpack_grads(gp, items)
 
-    def _unpack_grads(self, gp, items):
+    def _unpack_grads(self, gp, items, part=None):
+        """part None: every gradient, list in _param_list() order; 'density' / 'app': only that half is unpacked (the other
+        entries of the list are None)."""
         lib = L.load()
         st = _stream_ptr()
         base = gp.data_ptr()
@@ -646,11 +683,17 @@ class TensorVMSplit(MaintainMixin, RegularizerMixin, CheckpointMixin, torch.nn.M
         for k in range(3):
             for pref, plist, llist, c in (("d", self.density_plane, self.density_line, Cd),
                                           ("a", self.app_plane, self.app_line, Ca)):
+                if part is not None and pref != part[0]:
+                    out[f"{pref}p{k}"], out[f"{pref}l{k}"] = None, None
+                    continue
                 gpl, gl = torch.empty_like(plist[k]), torch.empty_like(llist[k])
                 # channels-last [H*W][C] -> NCHW [C][H*W] (tvm_unpack_grid), all 12 gradients in one launch
                 jobs.append(L.TvmTransposeJob(at(f"{pref}p{k}").value, gpl.data_ptr(), gpl.shape[2] * gpl.shape[3], c))
                 jobs.append(L.TvmTransposeJob(at(f"{pref}l{k}").value, gl.data_ptr(), gl.shape[2], c))
                 out[f"{pref}p{k}"], out[f"{pref}l{k}"] = gpl, gl
+        if part == "density":
+            L.check(lib.tvm_transpose_batch((L.TvmTransposeJob * len(jobs))(*jobs), len(jobs), st), "tvm_transpose_batch")
+            return [*(out[f"dp{k}"] for k in range(3)), *(out[f"dl{k}"] for k in range(3))] + [None] * (len(self._param_list()) - 6)
         m = self.renderModule.mlp
         J = L.TvmTransposeJob
         g_basis = torch.empty_like(self.basis_mat.weight)
@@ -670,6 +713,18 @@ class TensorVMSplit(MaintainMixin, RegularizerMixin, CheckpointMixin, torch.nn.M
     def _unpack_head_grads(self, gp, items):
         """Gradients of the parameters `_param_list` appends after the MLP (none for TensorVMSplit)."""
         return []
+
+    def _unpack_part(self, gp, items, part):
+        """Unpack one half of the flat gradient buffer straight into .grad: part 'density' = density planes / lines,
+        'app' = appearance planes / lines, basis_mat, MLP (and the REFTensoRF heads).  Returns the parameters it filled."""
+        grads = self._unpack_grads(gp, items, part=part)
+        params = self._param_list()
+        sel = range(0, 6) if part == "density" else range(6, len(params))
+        out = []
+        for i in sel:
+            params[i].grad = grads[i]
+            out.append(params[i])
+        return out
 
     # ---- reference API: the per-chunk call ----------------------------------------------------
     def forward(self, rays_chunk, white_bg=True, is_train=False, ndc_ray=False, N_samples=-1,

@@ -132,7 +132,11 @@ class Adam:
         if weight_decay:
             raise NotImplementedError("weight_decay is not used by the reference's training loop")
         if isinstance(params, (list, tuple)) and params and isinstance(params[0], dict):
-            self.param_groups = [dict(g, params=list(g["params"])) for g in params]
+            # a ParameterList is kept BY REFERENCE, as jt.optim does with the list objects of get_optparam_groups
+            # (tensoRF.py:168-174): shrink() replaces entries of those lists in place (tensoRF.py:300-301) and the next step
+            # must update the cropped grids (fresh moments: _state notices the new tensors); generators are materialised
+            self.param_groups = [dict(g, params=g["params"] if isinstance(g["params"], (list, torch.nn.ParameterList))
+                                      else list(g["params"])) for g in params]
         else:
             self.param_groups = [{"params": list(params)}]
         for g in self.param_groups:
@@ -174,14 +178,16 @@ class Adam:
                                 self._hyper_dev)
 
     @torch.no_grad()
-    def _launch(self):
+    def _launch(self, only=None):
         """Device side of one step (capturable): one multi-tensor kernel per 32 tensors, hyper-parameters from the device
-        buffer _prepare_hyper filled."""
+        buffer _prepare_hyper filled.  `only`: restrict the launch to these parameters (the pipelined data-parallel step
+        updates the appearance half while the density half of the gradient is still being exchanged)."""
         entries, keep = [], []
         dev = None
+        only = None if only is None else {id(p) for p in only}
         for gi, g in enumerate(self.param_groups):
             for p in g["params"]:
-                if p.grad is None:
+                if p.grad is None or (only is not None and id(p) not in only):
                     continue
                 if not (p.is_cuda and p.dtype == torch.float32 and p.data.is_contiguous()):
                     raise L.TvmError("Adam: parameters must be contiguous fp32 CUDA tensors (no CPU fallback)")
@@ -260,14 +266,16 @@ class TrainStepGraph:
         L.check(lib.tvm_mse_loss(_ptr(rgb), _ptr(self.target), n, 1.0, _ptr(self.loss), _ptr(d_rgb), _stream_ptr()),
                 "tvm_mse_loss")                                                       # train.py:228
         d_pen = self._w_dev[4:5] if (self.use["pen"] and m.VARIANT == L.VARIANT_REF) else None
+        reg = self.reg_loss
+        reg.zero_()
+        w = self._w_dev
+        if m.grad_sync and m._peer_comm is not None and os.environ.get("TVM_AR_OVERLAP", "2") == "2":
+            return self._body_pipelined(jitter, flags, rgb, d_rgb, d_pen)
         grads = m._backward_raw(self.rays, jitter, flags, self.S, rgb, d_rgb, d_pen)
         params = m._param_list()
         for p, g in zip(params, grads):
             p.grad = g
         # regularisers (train.py:233-251): value + gradient sweeps straight into .grad, weights read from the device
-        reg = self.reg_loss
-        reg.zero_()
-        w = self._w_dev
         tv_jobs = []
         for on, planes, wd in ((self.use["tv_d"], m.density_plane, w[0:1]), (self.use["tv_a"], m.app_plane, w[1:2])):
             if on:
@@ -285,6 +293,33 @@ class TrainStepGraph:
                 _launch("ortho", p.detach(), 1.0, reg, p.grad, w[3:4])
         self.opt._launch()
         m._pack(force=True)                       # the next forward (and any render in between) sees the updated grids
+
+    def _body_pipelined(self, jitter, flags, rgb, d_rgb, d_pen):
+        """Tail of the data-parallel step with the gradient exchange hidden behind it (peer all-reduce, tvm_backward_dp phases):
+        side stream:  [all-reduce appearance half]            [all-reduce density half]
+        this stream:  app backward | density scatter | unpack + TV + Adam of the APPEARANCE half | ... of the DENSITY half | pack
+        Every tensor sees exactly the arithmetic of the serial body; only the launch order differs."""
+        m, lib = self.model, L.load()
+        main = torch.cuda.current_stream()
+        gp, items, ev_app, ev_den = m._backward_raw(self.rays, jitter, flags, self.S, rgb, d_rgb, d_pen, pipelined=True)
+        reg, w = self.reg_loss, self._w_dev
+        for p in m._param_list():
+            p.grad = None
+        for part, ev, planes, tv_on, wd in (("app", ev_app, m.app_plane, self.use["tv_a"], w[1:2]),
+                                            ("density", ev_den, m.density_plane, self.use["tv_d"], w[0:1])):
+            main.wait_event(ev)
+            filled = m._unpack_part(gp, items, part)
+            if tv_on:
+                jobs = [L.TvmTvJob(p.data_ptr(), p.grad.data_ptr(), p.shape[1], p.shape[2], p.shape[3], 1e-2, wd.data_ptr()) for p in planes]
+                L.check(lib.tvm_tv_loss_batch((L.TvmTvJob * len(jobs))(*jobs), len(jobs), _ptr(reg), _stream_ptr()), "tvm_tv_loss_batch")
+            if part == "density" and self.use["l1"]:
+                for p in [*m.density_plane, *m.density_line]:
+                    _launch("l1", p.detach(), 1.0, reg, p.grad, w[2:3])
+            if self.use["ortho"]:
+                for p in (m.app_line if part == "app" else m.density_line):
+                    _launch("ortho", p.detach(), 1.0, reg, p.grad, w[3:4])
+            self.opt._launch(only=filled)
+        m._pack(force=True)
 
     def _upload_scalars(self):
         """Per-step scalars -> device, eagerly and stream-ordered in front of the replay (never from inside the graph: a

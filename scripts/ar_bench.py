@@ -1,27 +1,41 @@
-"""All-reduce cost of the flat gradient buffer (12.8 MB fp32 at 128^3) under torchrun: eager and inside a CUDA graph."""
-import os, torch, torch.distributed as dist
-local = int(os.environ.get("LOCAL_RANK", "0")); torch.cuda.set_device(local)
-dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-def timed(fn, n=50):
-    for _ in range(5): fn()
-    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+#!/usr/bin/env python
+"""All-reduce of the flat gradient buffer (3.2 M floats = the 128^3 model, 17.4 M = 300^3) under torchrun: libtvmrender's
+peer-memory kernel (NVLS and P2P paths, several grid sizes) against NCCL, back-to-back launches timed with CUDA events."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch, torch.distributed as dist
+import jittor_myc_nerfs_b200 as pkg
+local = int(os.environ.get("LOCAL_RANK", "0")); torch.cuda.set_device(local); dev = torch.device("cuda", local)
+rank, world = pkg.dist.init_from_env("nccl", device=dev)
+
+
+def timed(fn, K=200):
+    for _ in range(20):
+        fn()
+    torch.cuda.synchronize(); dist.barrier()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
-    for _ in range(n): fn()
+    for _ in range(K):
+        fn()
     b.record(); torch.cuda.synchronize()
-    return a.elapsed_time(b) / n * 1e3
-for nfl in (3_200_000, 2_400_000, 800_000, 200_000):
-    x = torch.randn(nfl, device="cuda")
-    e = timed(lambda: dist.all_reduce(x))
-    g = torch.cuda.CUDAGraph()
-    s = torch.cuda.Stream()
-    s.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(s):
-        dist.all_reduce(x)
-    torch.cuda.current_stream().wait_stream(s)
-    with torch.cuda.graph(g):
-        dist.all_reduce(x)
-    gt = timed(g.replay)
-    if dist.get_rank() == 0:
-        print(f"all_reduce {nfl * 4 / 1e6:.1f} MB x{dist.get_world_size()}: eager {e:.1f} us, graph {gt:.1f} us", flush=True)
-dist.barrier(); torch.cuda.synchronize(); os._exit(0)
+    t = torch.tensor([a.elapsed_time(b) / K * 1e3], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t)
+
+
+for n in (3_200_000, 17_400_000):
+    x = torch.randn(n, device=dev)
+    res = {"nccl": timed(lambda: dist.all_reduce(x))}
+    for no_mc in ("", "1"):
+        if no_mc:
+            os.environ["TVM_AR_NO_MULTICAST"] = "1"
+        else:
+            os.environ.pop("TVM_AR_NO_MULTICAST", None)
+        for ctas in (16, 32, 64, 128):
+            comm = pkg.dist.PeerComm(n, dev, n_ctas=ctas)
+            res[("p2p" if not comm.multicast else "nvls") + f"/{ctas}"] = timed(lambda: comm.allreduce_())
+            del comm
+    if rank == 0:
+        print(f"world {world}, {n * 4 / 1e6:.1f} MB: us per all-reduce:", {k: round(v, 1) for k, v in res.items()}, flush=True)
+torch.cuda.synchronize(); dist.barrier(); sys.stdout.flush(); os._exit(0)

@@ -31,7 +31,7 @@ def test_abi_version_and_struct_sizes(built_lib):
 #include "tvmrender.h"
 int main(){ printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(TvmModel), sizeof(TvmAux), sizeof(TvmGrads), sizeof(TvmBgNet),
                    sizeof(TvmBgGrads), sizeof(TvmTransposeJob), sizeof(TvmTvJob), sizeof(TvmAdamTensor),
-                   sizeof(TvmWorkspaceLayout)); printf("%zu\n", sizeof(TvmPeerComm)); return 0; }
+                   sizeof(TvmWorkspaceLayout)); printf("%zu %zu\n", sizeof(TvmPeerComm), sizeof(TvmGradExchange)); return 0; }
 '''
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "p.c"), "w").write(probe)
@@ -41,7 +41,7 @@ int main(){ printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(TvmModel), si
     L = built_lib._lib
     assert [int(x) for x in out] == [ctypes.sizeof(t) for t in (L.TvmModel, L.TvmAux, L.TvmGrads, L.TvmBgNet, L.TvmBgGrads,
                                                                   L.TvmTransposeJob, L.TvmTvJob, L.TvmAdamTensor,
-                                                                  L.TvmWorkspaceLayout, L.TvmPeerComm)]
+                                                                  L.TvmWorkspaceLayout, L.TvmPeerComm, L.TvmGradExchange)]
 
 
 def test_fails_loudly_without_gpu(built_lib):

@@ -472,3 +472,70 @@ def test_no_write_outside_caller_buffers(env):
         model._backward_raw(rays, jit, model._flags(True), S, rgb.contiguous(), d_rgb)
         torch.cuda.synchronize()
         assert bool((ws[need:] == 0xA5).all()), ("backward", n, S, mode)
+
+
+def _params_from_model(model, fx):
+    """A trained host model -> synthetic.ModelParams (numpy, reference shapes), so that the oracle can render it."""
+    g = lambda t: t.detach().cpu().numpy().astype(np.float32).copy()
+    mlp = model.renderModule.mlp
+    return fx.ModelParams(aabb=model.aabb.numpy().astype(np.float32).copy(), gridSize=tuple(int(x) for x in model.gridSize),
+                          density_plane=[g(p) for p in model.density_plane], density_line=[g(p) for p in model.density_line],
+                          app_plane=[g(p) for p in model.app_plane], app_line=[g(p) for p in model.app_line],
+                          basis_mat=g(model.basis_mat.weight), mlp_w=[g(mlp[i].weight) for i in (0, 2, 4)],
+                          mlp_b=[g(mlp[i].bias) for i in (0, 2, 4)], near_far=tuple(model.near_far),
+                          density_shift=float(model.density_shift), distance_scale=float(model.distance_scale),
+                          step_ratio=float(model.step_ratio))
+
+
+def test_sixteen_bit_operands_on_trained_and_scaled_models(env):
+    """The 16-bit modes away from the 0.1 N(0,1) synthetic grids they were tuned on.
+    (i) A TRAINED model (the reconstruction schedule of examples/reconstruct_synthetic.py: features and activations have the
+        magnitudes training produces): fp16 head with fp32 planes and with fp16 pair records against the oracle at the FP32
+        tolerance 1e-4; bf16 head at 1e-2.
+    (ii) Random grids scaled x3 / x10 / x30: appearance features grow with the square of the scale, and the positional
+        encoding sin(2 f) turns an absolute feature error of 2^-11 |f| into a colour error -- the 16-bit modes are accurate
+        to 1e-4 only while |features| = O(1).  What is asserted is the contract: fp32 head <= 1e-4 at every scale; every
+        16-bit mode <= 1e-2 up to x10; the measured errors are printed (and quoted in DESIGN.md) so that the limit of
+        the fp16-within-1e-4 claim is on record; fp16 (range 65504) does not overflow at x30."""
+    pkg, torch, fx, orc = env
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples"))
+    import reconstruct_synthetic as ex
+    h = ex.run(iters=400, res=48, n_views=12, upsamp_list=(200,), update_AlphaMask_list=(150, 300), mlp_mode="fp32", log=lambda s: None)
+    model = h["model"]
+    assert h["final_psnr"] > 22.0
+    mp = _params_from_model(model, fx)
+    am = model.alphaMask
+    rays = pkg.get_rays_frame(ex.camera(0.9, 0.5), 40, 40, 0.5 * 40 / np.tan(0.5 * 0.6911), blender=False, device=torch.device("cuda:0"))
+    case = dict(model=mp, rays=rays.cpu().numpy(), alpha_volume=am.alpha_volume[0, 0].cpu().numpy(), alpha_aabb=am.aabb.numpy().copy(),
+                jitter=None, target=None)
+    ref = orc.run_case(case, want_stages=False)
+    assert float(np.abs(ref["rgb_map"] - 1.0).max()) > 0.3            # the view shows the object
+    errs = {}
+    for mode, planes16 in (("fp32", False), ("fp16", False), ("fp16", True), ("bf16", True)):
+        model.mlp_mode, model.app_planes_bf16 = mode, planes16
+        with torch.no_grad():
+            rgb, _ = model(rays, white_bg=True, is_train=False)
+        errs[(mode, planes16)] = float(np.abs(rgb.cpu().numpy() - ref["rgb_map"]).max())
+    print("trained model, max |rgb - oracle|:", {f"{m}{'+16-bit planes' if p else ''}": f"{e:.2e}" for (m, p), e in errs.items()})
+    assert errs[("fp32", False)] <= RGB_TOL and errs[("fp16", False)] <= RGB_TOL and errs[("fp16", True)] <= RGB_TOL
+    assert errs[("bf16", True)] <= 1e-2
+    # (ii) scaled random grids
+    from util import gpu_model
+    table = {}
+    for scale in (1.0, 3.0, 10.0, 30.0):
+        case = fx.make_case(128, 1024, "R1", grid_scale=0.1 * scale)
+        ref = orc.run_case(case, want_stages=False)
+        rays = torch.from_numpy(case["rays"]).cuda()
+        m = gpu_model(pkg, case)
+        for mode, planes16 in (("fp32", False), ("fp16", False), ("fp16", True), ("bf16", True)):
+            m.mlp_mode, m.app_planes_bf16 = mode, planes16
+            with torch.no_grad():
+                rgb, _ = m(rays, white_bg=True, is_train=False)
+            assert bool(torch.isfinite(rgb).all()), (scale, mode)
+            table[(scale, mode, planes16)] = float(np.abs(rgb.cpu().numpy() - ref["rgb_map"]).max())
+        print(f"grid scale x{scale:g}:", {f"{mo}{'+16' if p else ''}": f"{e:.1e}" for (s_, mo, p), e in table.items() if s_ == scale})
+        assert table[(scale, "fp32", False)] <= RGB_TOL
+        if scale <= 10.0:
+            assert max(table[(scale, "fp16", False)], table[(scale, "fp16", True)], table[(scale, "bf16", True)]) <= 1e-2
+    assert table[(1.0, "fp16", True)] <= RGB_TOL
