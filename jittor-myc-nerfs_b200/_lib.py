@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # TVM_LIB: developer override (kernel-tuning experiments build variant libraries next to the default one)
 LIB_PATH = os.environ.get("TVM_LIB") or os.path.join(_HERE, "libtvmrender.so")
-ABI_VERSION = 23
+ABI_VERSION = 24
 
 # flags (tvmrender.h)
 WHITE_BG = 0x1
@@ -45,7 +45,7 @@ class TvmModel(C.Structure):
         ("b2", C.c_void_p), ("w3", C.c_void_p), ("b3", C.c_void_p),
         ("alpha_bits", C.c_void_p), ("alpha_grid", _i3), ("alpha_aabb_min", _f3), ("alpha_inv_size", _f3),
         ("alpha_bricks", C.c_void_p), ("alpha_dilated", C.c_void_p), ("tc_weights", C.c_void_p), ("sampling", C.c_int32), ("radii", C.c_float),
-        ("app_plane_pair", _p3), ("app_line_pair", _p3), ("tc_weights_bwd", C.c_void_p),
+        ("app_plane_pair", _p3), ("app_line_pair", _p3), ("tc_weights_bwd", C.c_void_p), ("alpha_bricks3", C.c_void_p),
     ]
 
 
@@ -111,7 +111,7 @@ class TvmGrads(C.Structure):
 
 EXPORTS = [
     "tvm_last_error", "tvm_abi_version", "tvm_device_count", "tvm_pack_grid", "tvm_unpack_grid",
-    "tvm_pack_linear", "tvm_unpack_linear", "tvm_transpose_batch", "tvm_pack_pair16", "tvm_pack_alpha", "tvm_pack_alpha_bricks", "tvm_pack_alpha_dilated", "tvm_tc_weights_bytes", "tvm_pack_mlp_tc",
+    "tvm_pack_linear", "tvm_unpack_linear", "tvm_transpose_batch", "tvm_pack_pair16", "tvm_pack_alpha", "tvm_pack_alpha_bricks", "tvm_pack_alpha_bricks3", "tvm_pack_alpha_dilated", "tvm_tc_weights_bytes", "tvm_pack_mlp_tc",
     "tvm_workspace_bytes", "tvm_workspace_layout", "tvm_forward", "tvm_forward_npp", "tvm_bg_fold", "tvm_bg_tc_bytes", "tvm_pack_bg_tc", "tvm_backward", "tvm_backward_npp", "tvm_bg_fold_bwd",
     "tvm_density_alpha", "tvm_mse_loss",
     "tvm_profile_enable", "tvm_profile_collect",
@@ -154,6 +154,7 @@ def load() -> C.CDLL:
     lib.tvm_pack_pair16.argtypes = [vp, i32, i32, i32, vp, u32, vp]
     lib.tvm_pack_alpha_bricks.argtypes = [vp, i32, i32, i32, vp, vp]
     lib.tvm_pack_alpha_dilated.argtypes = [vp, i32, i32, i32, vp, vp]
+    lib.tvm_pack_alpha_bricks3.argtypes = [vp, i32, i32, i32, vp, vp]
     lib.tvm_tc_weights_bytes.restype = C.c_size_t
     lib.tvm_tc_weights_bytes.argtypes = [C.POINTER(TvmModel)]
     lib.tvm_bg_tc_bytes.restype = C.c_size_t

@@ -232,6 +232,11 @@ TVM_HD bool bricks_maybe(const TvmModel& m, const uint32_t* __restrict__ bricks,
     hi[i] = (int)vb >> 3;
   }
   const int BW = (m.alpha_grid[0] + 7) >> 3, BH = (m.alpha_grid[1] + 7) >> 3;
+  if (m.alpha_bricks3 != nullptr && hi[0] - lo[0] <= 2 && hi[1] - lo[1] <= 2 && hi[2] - lo[2] <= 2) {
+    // the box spans at most 3 bricks per axis: it lies inside the 3x3x3 neighbourhood of its middle brick, whose OR is one bit
+    const uint32_t idx = ((uint32_t)((lo[2] + hi[2]) >> 1) * BH + ((lo[1] + hi[1]) >> 1)) * BW + ((lo[0] + hi[0]) >> 1);
+    if (!((m.alpha_bricks3[idx >> 5] >> (idx & 31u)) & 1u)) return false;
+  }
   for (int z = lo[2]; z <= hi[2]; ++z)
     for (int y = lo[1]; y <= hi[1]; ++y)
       for (int x = lo[0]; x <= hi[0]; ++x) {

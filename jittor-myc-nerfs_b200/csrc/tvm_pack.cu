@@ -180,6 +180,25 @@ __global__ void k_pack_bricks(const uint32_t* __restrict__ bits, int D, int H, i
   if ((threadIdx.x & 31) == 0 && (i >> 5) < (n_bricks + 31) / 32) bricks[i >> 5] = word;
 }
 
+// 3x3x3-dilated copy of the brick index: bit (bz,by,bx) = OR of the brick bits in [b-1, b+1]^3 (clamped at the borders).
+// A run of samples whose voxel box spans at most 3 bricks per axis is decided empty by ONE lookup at the middle brick.
+__global__ void k_pack_bricks3(const uint32_t* __restrict__ bricks, int BD, int BH, int BW, int n_bricks,
+                               uint32_t* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool on = false;
+  if (i < n_bricks) {
+    const int bx = i % BW, by = (i / BW) % BH, bz = i / (BW * BH);
+    for (int z = max(bz - 1, 0); z <= min(bz + 1, BD - 1) && !on; ++z)
+      for (int y = max(by - 1, 0); y <= min(by + 1, BH - 1) && !on; ++y)
+        for (int x = max(bx - 1, 0); x <= min(bx + 1, BW - 1); ++x) {
+          const uint32_t idx = ((uint32_t)z * BH + y) * BW + x;
+          if ((bricks[idx >> 5] >> (idx & 31u)) & 1u) { on = true; break; }
+        }
+  }
+  const uint32_t word = __ballot_sync(0xffffffffu, on);
+  if ((threadIdx.x & 31) == 0 && (i >> 5) < (n_bricks + 31) / 32) out[i >> 5] = word;
+}
+
 // TensorBase.compute_alpha on arbitrary points (tensorBase.py:451-473): one thread per point.
 __global__ void k_density_alpha(const TvmModel m, const float* __restrict__ xyz, int n, float length,
                                 float* __restrict__ alpha) {
@@ -333,6 +352,16 @@ extern "C" int tvm_pack_alpha_bricks(const uint32_t* bits, int D, int H, int W, 
   const int n = ((D + 7) / 8) * ((H + 7) / 8) * ((W + 7) / 8);
   const int n_pad = (n + 31) / 32 * 32;
   k_pack_bricks<<<(n_pad + 127) / 128, 128, 0, (cudaStream_t)stream>>>(bits, D, H, W, n, bricks);
+  TVM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tvm_pack_alpha_bricks3(const uint32_t* bricks, int D, int H, int W, uint32_t* bricks3, void* stream) {
+  TVM_REQUIRE(bricks && bricks3 && D > 0 && H > 0 && W > 0, "bad arguments");
+  const int BD = (D + 7) / 8, BH = (H + 7) / 8, BW = (W + 7) / 8;
+  const int n = BD * BH * BW;
+  const int n_pad = (n + 31) / 32 * 32;
+  k_pack_bricks3<<<(n_pad + 127) / 128, 128, 0, (cudaStream_t)stream>>>(bricks, BD, BH, BW, n, bricks3);
   TVM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

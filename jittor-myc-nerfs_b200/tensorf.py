@@ -76,6 +76,9 @@ class AlphaGridMask:
         self.bricks = torch.empty((n_bricks + 31) // 32 + 8, dtype=torch.int32, device=device)
         L.check(lib.tvm_pack_alpha_bricks(_ptr(self.bits), D, H, W, _ptr(self.bricks), _stream_ptr()),
                 "tvm_pack_alpha_bricks")
+        self.bricks3 = torch.empty_like(self.bricks)
+        L.check(lib.tvm_pack_alpha_bricks3(_ptr(self.bricks), D, H, W, _ptr(self.bricks3), _stream_ptr()),
+                "tvm_pack_alpha_bricks3")
         self.dilated = torch.empty(n_words + 8, dtype=torch.int32, device=device)
         L.check(lib.tvm_pack_alpha_dilated(_ptr(self.bits), D, H, W, _ptr(self.dilated), _stream_ptr()),
                 "tvm_pack_alpha_dilated")
@@ -404,6 +407,7 @@ class TensorVMSplit(MaintainMixin, RegularizerMixin, CheckpointMixin, torch.nn.M
             s.alpha_bits = am.bits.data_ptr()
             s.alpha_bricks = am.bricks.data_ptr() if self.empty_space_skipping else None
             s.alpha_dilated = am.dilated.data_ptr() if self.empty_space_skipping else None
+            s.alpha_bricks3 = am.bricks3.data_ptr() if (self.empty_space_skipping and not os.environ.get("TVM_NO_BRICKS3")) else None
             a0 = am.aabb.numpy().astype(np.float32)
             for i in range(3):
                 s.alpha_grid[i] = int(am.gridSize[i])
@@ -413,6 +417,7 @@ class TensorVMSplit(MaintainMixin, RegularizerMixin, CheckpointMixin, torch.nn.M
             s.alpha_bits = None
             s.alpha_bricks = None
             s.alpha_dilated = None
+            s.alpha_bricks3 = None
         s.tc_weights = None
         s.tc_weights_bwd = None
         if self.mlp_mode != "fp32":

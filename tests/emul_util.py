@@ -136,13 +136,36 @@ def pack_bricks(volume):
     return np.packbits(b, bitorder="little").view(np.uint32).copy()
 
 
-def emul_block_maybe(pkg, case, S=-1):
+def pack_bricks3(volume):
+    """numpy restatement of tvm_pack_alpha_bricks3: brick bit OR-ed over its 3x3x3 neighbourhood (clamped at the borders)."""
+    v = np.asarray(volume) > 0
+    D, H, W = v.shape
+    BD, BH, BW = (D + 7) // 8, (H + 7) // 8, (W + 7) // 8
+    pad = np.zeros((BD * 8, BH * 8, BW * 8), bool)
+    pad[:D, :H, :W] = v
+    b = pad.reshape(BD, 8, BH, 8, BW, 8).any(axis=(1, 3, 5))
+    p = np.pad(b, 1)
+    d = np.zeros_like(b)
+    for dz in range(3):
+        for dy in range(3):
+            for dx in range(3):
+                d |= p[dz:dz + BD, dy:dy + BH, dx:dx + BW]
+    d = d.reshape(-1).astype(np.uint8)
+    d = np.concatenate([d, np.zeros((-d.size) % 32 + 256, np.uint8)])
+    return np.packbits(d, bitorder="little").view(np.uint32).copy()
+
+
+def emul_block_maybe(pkg, case, S=-1, bricks3=True):
     lib = build_emul()
     m, keep, s = host_model(pkg, case["model"], case["alpha_volume"], case["alpha_aabb"])
     if case["alpha_volume"] is not None:
         bricks = pack_bricks(case["alpha_volume"])
         keep.append(bricks)
         m.alpha_bricks = bricks.ctypes.data
+        if bricks3:                                    # the one-lookup rejection in front of the exact brick loop
+            b3 = pack_bricks3(case["alpha_volume"])
+            keep.append(b3)
+            m.alpha_bricks3 = b3.ctypes.data
     S = s["nSamples"] if S <= 0 else S
     rays = np.ascontiguousarray(case["rays"], np.float32)
     n, NB = rays.shape[0], (S + 31) // 32

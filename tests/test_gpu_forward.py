@@ -490,8 +490,9 @@ def _params_from_model(model, fx):
 def test_sixteen_bit_operands_on_trained_and_scaled_models(env):
     """The 16-bit modes away from the 0.1 N(0,1) synthetic grids they were tuned on.
     (i) A TRAINED model (the reconstruction schedule of examples/reconstruct_synthetic.py: features and activations have the
-        magnitudes training produces): fp16 head with fp32 planes and with fp16 pair records against the oracle at the FP32
-        tolerance 1e-4; bf16 head at 1e-2.
+        magnitudes training produces): the fp16 head, with fp32 planes and with fp16 pair records, measures 0.8e-4 from the
+        oracle there -- AT the fp32 tolerance, not comfortably inside it as on the synthetic grids (1.7e-5); asserted <= 2e-4
+        (training is not bit-reproducible: float atomics).  bf16 head 0.8e-3, asserted at its 1e-2.  The fp32 head: 1e-6.
     (ii) Random grids scaled x3 / x10 / x30: appearance features grow with the square of the scale, and the positional
         encoding sin(2 f) turns an absolute feature error of 2^-11 |f| into a colour error -- the 16-bit modes are accurate
         to 1e-4 only while |features| = O(1).  What is asserted is the contract: fp32 head <= 1e-4 at every scale; every
@@ -518,8 +519,9 @@ def test_sixteen_bit_operands_on_trained_and_scaled_models(env):
             rgb, _ = model(rays, white_bg=True, is_train=False)
         errs[(mode, planes16)] = float(np.abs(rgb.cpu().numpy() - ref["rgb_map"]).max())
     print("trained model, max |rgb - oracle|:", {f"{m}{'+16-bit planes' if p else ''}": f"{e:.2e}" for (m, p), e in errs.items()})
-    assert errs[("fp32", False)] <= RGB_TOL and errs[("fp16", False)] <= RGB_TOL and errs[("fp16", True)] <= RGB_TOL
+    assert errs[("fp32", False)] <= RGB_TOL and errs[("fp16", False)] <= 2e-4 and errs[("fp16", True)] <= 2e-4
     assert errs[("bf16", True)] <= 1e-2
+    assert abs(errs[("fp16", True)] - errs[("fp16", False)]) <= 5e-5      # the 16-bit plane copies are not what costs accuracy
     # (ii) scaled random grids
     from util import gpu_model
     table = {}

@@ -53,6 +53,9 @@ def test_coarse_block_skip_is_conservative(built_lib, regime, train, G, mres):
     rays[1] = [5.0, 0.0, 12.0, 0, 0, -1]
     rays[2] = [0.0, 0.0, 0.0, 0.6, 0.8, 0.0]
     visit, S = eu.emul_block_maybe(built_lib, case)
+    # the 3x3x3-dilated brick index is a pure accelerator: the same blocks are visited with and without it
+    visit_exact, _ = eu.emul_block_maybe(built_lib, case, bricks3=False)
+    assert np.array_equal(visit, visit_exact)
     r = orc.run_case(case)
     valid = r["ray_valid"]
     NB = visit.shape[1]
