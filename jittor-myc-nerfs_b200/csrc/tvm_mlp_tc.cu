@@ -1,18 +1,9 @@
-// Appearance head on the 5th-generation tensor cores (tcgen05 / TMEM), sm_100a only.
-//
-// Replaces k_app_simt for TVM_MLP_BF16: per tile of 128 weighted samples
-//   gather   48-channel plane x line products (tensoRF.py:228-243)      -> A0 [128 x 144] bf16 in smem
-//   GEMM0    A0 . basis_mat^T  (tensoRF.py:244)                         -> TMEM [128 x 32] fp32
-//   epi0     positional encoding of features / view dir (tensorBase.py:9-15,76-83) -> A1 [128 x 160] bf16
-//   GEMM1    A1 . W1^T, epi1: +b1, ReLU                                 -> A2 [128 x 128] bf16
-//   GEMM2    A2 . W2^T, epi2: +b2, ReLU, 128->3 layer on CUDA cores, sigmoid (tensorBase.py:84-86)
-// Operands live in shared memory in the UMMA K-major no-swizzle ("interleaved") canonical layout:
-// 8-row x 16-byte core matrices; element (r, k) of a [R x K] bf16 operand sits at
-//   (k/8) * (R*16) + r*16 + (k%8)*2        (LBO = R*16 bytes between K-chunks, SBO = 128 bytes between 8-row groups)
-// so that one thread (= one row) writes whole 16-byte chunks, conflict-free.  Accumulators are read
-// back with tcgen05.ld (32x32b: thread t of warp w owns TMEM lane 32*(w%4)+t = tile row).
-// One thread issues the MMAs; completion is signalled through tcgen05.commit -> mbarrier.
-#include <stdlib.h>
+// Operand images of the tensor-core appearance head (tcgen05 / TMEM, sm_100a only) and its launch entry.
+// The kernel itself is k_app_tc2 (tvm_app_tc2.cu); the single-group kernel of round 1 (k_app_tc, A operands in shared
+// memory) is in the history (commit 15c4a98) and in profiles/r01q_notes.txt.
+// Operands live in shared memory in the UMMA K-major no-swizzle ("interleaved") canonical layout: 8-row x 16-byte core
+// matrices; element (r, k) of a [R x K] 16-bit operand sits at (k/8) * (R*16) + r*16 + (k%8)*2 (LBO = R*16 bytes between
+// K-chunks, SBO = 128 bytes between 8-row groups).
 #include "tvm_tc.cuh"
 
 namespace tvm {
@@ -59,368 +50,6 @@ __global__ void k_pack_tc_ext(const TvmModel m, int in_c, uint16_t* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------
-// Warp-specialised persistent kernel: warps 0-3 ("MLP group", thread = tile row) issue the MMAs and run
-// the three epilogues; warps 4.. ("gather group") produce the GEMM0 operand of the NEXT tile into a
-// double-buffered A0 while the MLP group works on the current one.  full[s]/empty[s] mbarriers hand
-// the two A0 stages back and forth; tcgen05.commit arrives on empty[s] when GEMM0 has consumed A0[s].
-constexpr int kMlpWarps = 4;
-constexpr int kGatherWarps = 8;
-constexpr int kThreadsV2 = (kMlpWarps + kGatherWarps) * 32;
-
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mlp_group_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
-
-// PB16: plane and line texels come from the 16-bit pair records (TvmModel.app_plane_pair / app_line_pair): one 16-byte
-//       load per lane brings both taps of an adjacent pair
-// H16:  operands (weight image, activations, plane copies) are fp16 instead of bf16 (TVM_MLP_FP16)
-template <int CA, int APP_DIM, int FEA_PE, int VIEW_PE, bool REF, bool PB16, bool H16>
-__global__ void __launch_bounds__(kThreadsV2, 1) k_app_tc(const FwdParams P) {
-  constexpr int NH = REF ? TVM_REF_HEAD_LD : 32;
-  constexpr int C0 = REF ? 1 : 0;                       // REF: column 0 of the MLP input is -dot (REFTensoRF.py:20)
-  constexpr int IN_C = 2 * VIEW_PE * 3 + 2 * FEA_PE * APP_DIM + 3 + APP_DIM + C0;
-  constexpr int K0 = 3 * CA;
-  constexpr int K1 = (IN_C + 15) / 16 * 16;
-  constexpr int KA = K1 > 128 ? K1 : 128;
-  static_assert(FEA_PE == 2 && VIEW_PE == 2, "the register-resident PE builder is written for 2 frequencies");
-  static_assert(K0 % 16 == 0 && APP_DIM <= 32 && (!REF || APP_DIM + 8 <= NH), "unsupported shape");
-  static_assert(IN_C < K1 && KA >= 144, "the constant-one columns of GEMM1 / GEMM2 live in the K padding");
-
-  extern __shared__ __align__(1024) uint8_t smem[];
-  const Image img(CA, IN_C, NH);
-  uint8_t* sW = smem;                                          // weight image (bf16 operands + fp32 tail)
-  uint8_t* sA0 = smem + ((img.bytes_fwd + 1023) & ~1023u);     // 2 stages of the GEMM0 operand [128 x K0] bf16
-  uint8_t* sA = sA0 + 2 * kRows * K0 * 2;                      // GEMM1/GEMM2 operand [128 x KA] bf16
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + kRows * KA * 2);   // full[2], empty[2], mma
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
-  uint64_t* full = bars;
-  uint64_t* empty = bars + 2;
-  uint64_t* mma_bar = bars + 4;
-  const float* sHB = reinterpret_cast<const float*>(sW + img.off_f32) + 128 + 128 + 3 * 128 + 4;   // REF head biases [48]
-
-  const TvmModel& m = P.m;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
-  // ---- one-time setup: weights -> smem, barriers, TMEM -------------------------------------------
-  {
-    const uint4* src = reinterpret_cast<const uint4*>(m.tc_weights);
-    uint4* dst = reinterpret_cast<uint4*>(sW);
-    for (uint32_t i = tid; i < img.bytes_fwd / 16; i += kThreadsV2) dst[i] = __ldg(src + i);
-  }
-  if (tid == 0) {
-    mbar_init(&full[0], kGatherWarps);
-    mbar_init(&full[1], kGatherWarps);
-    mbar_init(&empty[0], 1);
-    mbar_init(&empty[1], 1);
-    mbar_init(mma_bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 0) tmem_alloc(tmem_slot, kTmemCols);
-  fence_async_smem();
-  fence_before();
-  __syncthreads();
-  fence_after();
-  const uint32_t tmem = *tmem_slot;
-
-  constexpr uint32_t LBO_A = kRows * 16, LBO_B0 = NH * 16, LBO_B = 128 * 16, SBO = 128;
-  constexpr uint32_t IDESC_N32 = instr_desc(128, NH, H16), IDESC_N128 = instr_desc(128, 128, H16), IDESC_N16 = instr_desc(128, 16, H16);
-  constexpr uint32_t LBO_B3 = 16 * 16;
-  constexpr uint32_t A0_STAGE = kRows * K0 * 2;
-
-  const uint32_t n_ent = *P.ws.n_entries;
-  const uint32_t n_tiles = (n_ent + kRows - 1) / kRows;
-
-  if (warp >= kMlpWarps) {
-    // =============================== gather group ================================================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
-    const int gw = warp - kMlpWarps;
-    constexpr int ROWS_PER_WARP = kRows / kGatherWarps;
-    uint32_t it = 0;
-    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-      const uint32_t s = it & 1u, use = it >> 1;
-      mbar_wait(&empty[s], (use & 1u) ^ 1u);          // stage free (first use of a stage passes at once)
-      const uint32_t tile_base = tile * kRows;
-      uint8_t* stage = sA0 + s * A0_STAGE;
-#pragma unroll
-      for (int pass = 0; pass < ROWS_PER_WARP / 8; ++pass) {
-        const int row = gw * ROWS_PER_WARP + pass * 8 + (lane >> 2), q = lane & 3;
-        const uint32_t e = tile_base + row;
-        uint8_t* arow = stage + row * 16;
-#ifdef TVM_EXP_NOGATHER
-        if (false) {
-#else
-        if (e < n_ent) {
-#endif
-          const float4 uw = __ldcs(P.ws.ent_u + e);      // written by k_march with the coordinates it marched; read once: evict-first
-          const float u[3] = {uw.x, uw.y, uw.z};
-          if (PB16) {
-            AxisPair ax[3];
-#pragma unroll
-            for (int i = 0; i < 3; ++i) ax[i] = axis_pair(u[i], m.grid[i]);
-#pragma unroll
-            for (int kk = 0; kk < 3; ++kk) {
-              const VmPair t = vm_pair(m, ax, kk, CA);
-              // pair records: [texel w c..c+3 | texel w+1 c..c+3] per 16 bytes, so one load brings both taps of the pair
-              const uint4* pl = reinterpret_cast<const uint4*>(m.app_plane_pair[kk]);
-              const uint4* ln = reinterpret_cast<const uint4*>(m.app_line_pair[kk]);
-#pragma unroll
-              for (int c = q * 4; c < CA; c += 16) {
-                const uint4 r0 = __ldg(pl + ((t.row0 + c) >> 2));
-                const uint4 r1 = __ldg(pl + ((t.row1 + c) >> 2));
-                const uint4 lr = __ldg(ln + ((t.lrow + c) >> 2));
-                const float2 a0 = unpack16<H16>(r0.x), a1 = unpack16<H16>(r0.y), b0 = unpack16<H16>(r0.z), b1 = unpack16<H16>(r0.w);
-                const float2 c0 = unpack16<H16>(r1.x), c1 = unpack16<H16>(r1.y), d0 = unpack16<H16>(r1.z), d1 = unpack16<H16>(r1.w);
-                const float2 l00 = unpack16<H16>(lr.x), l01 = unpack16<H16>(lr.y), l10 = unpack16<H16>(lr.z), l11 = unpack16<H16>(lr.w);
-                const float4 l0 = make_float4(l00.x, l00.y, l01.x, l01.y), l1 = make_float4(l10.x, l10.y, l11.x, l11.y);
-                const float px = a0.x * t.nw + b0.x * t.ne + c0.x * t.sw + d0.x * t.se;
-                const float py = a0.y * t.nw + b0.y * t.ne + c0.y * t.sw + d0.y * t.se;
-                const float pz = a1.x * t.nw + b1.x * t.ne + c1.x * t.sw + d1.x * t.se;
-                const float pw = a1.y * t.nw + b1.y * t.ne + c1.y * t.sw + d1.y * t.se;
-                const float lx = l0.x * t.lw0 + l1.x * t.lw1, ly = l0.y * t.lw0 + l1.y * t.lw1;
-                const float lz = l0.z * t.lw0 + l1.z * t.lw1, lw = l0.w * t.lw0 + l1.w * t.lw1;
-                const int k = kk * CA + c;
-                uint2 packed = make_uint2(pack16<H16>(px * lx, py * ly), pack16<H16>(pz * lz, pw * lw));
-                *reinterpret_cast<uint2*>(arow + (k >> 3) * LBO_A + (k & 7) * 2) = packed;
-              }
-            }
-          } else {
-          Axis ax[3];
-#pragma unroll
-          for (int i = 0; i < 3; ++i) ax[i] = axis_taps(u[i], m.grid[i]);
-#pragma unroll
-          for (int kk = 0; kk < 3; ++kk) {
-            const VmTaps t = vm_taps(m, ax, kk);
-#pragma unroll
-            for (int c = q * 4; c < CA; c += 16) {
-              float4 pv, lv;
-              vm_sample4(m.app_plane[kk], m.app_line[kk], t, CA, c, pv, lv);
-              const int k = kk * CA + c;
-              uint2 packed = make_uint2(pack16<H16>(pv.x * lv.x, pv.y * lv.y), pack16<H16>(pv.z * lv.z, pv.w * lv.w));
-              *reinterpret_cast<uint2*>(arow + (k >> 3) * LBO_A + (k & 7) * 2) = packed;
-            }
-          }
-          }
-        } else {
-#pragma unroll
-          for (int kk = 0; kk < 3; ++kk)
-#pragma unroll
-            for (int c = q * 4; c < CA; c += 16) {
-              const int k = kk * CA + c;
-              *reinterpret_cast<uint2*>(arow + (k >> 3) * LBO_A + (k & 7) * 2) = make_uint2(0u, 0u);
-            }
-        }
-      }
-      fence_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&full[s]);
-    }
-  } else {
-    // =============================== MLP group =====================================================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
-    const int row = tid;                                   // 0..127 = tile row = TMEM lane
-    const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
-    const uint32_t aA = smem_u32(sA);
-    const uint32_t aB0 = smem_u32(sW + img.off_b0), aB1 = smem_u32(sW + img.off_b1), aB2 = smem_u32(sW + img.off_b2);
-    const uint32_t aB2x = smem_u32(sW + img.off_b2x), aB3 = smem_u32(sW + img.off_b3);
-    uint8_t* arow = sA + row * 16;
-    uint32_t it = 0, mma_phase = 0;
-    float pen_acc = 0.0f;
-    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-      const uint32_t s = it & 1u, use = it >> 1;
-      const uint32_t e = tile * kRows + row;
-      float dir[3] = {0.0f, 0.0f, 0.0f};
-      if (e < n_ent) {
-        const uint32_t ray = P.ws.ent[e].x;
-        dir[0] = P.rays[6 * (size_t)ray + 3];
-        dir[1] = P.rays[6 * (size_t)ray + 4];
-        dir[2] = P.rays[6 * (size_t)ray + 5];
-      }
-      // ---- GEMM0: feat = A0[s] . basis^T ----------------------------------------------------------
-      if (tid == 0) {
-        mbar_wait(&full[s], use & 1u);
-        fence_after();
-        const uint32_t a0 = smem_u32(sA0 + s * A0_STAGE);
-#pragma unroll
-        for (int k = 0; k < K0 / 16; ++k)
-          umma_bf16(tmem + kColBasis, smem_desc(a0 + k * 2 * LBO_A, LBO_A, SBO),
-                    smem_desc(aB0 + k * 2 * LBO_B0, LBO_B0, SBO), IDESC_N32, k > 0);
-        umma_commit(&empty[s]);     // A0[s] may be refilled once these MMAs have read it
-        umma_commit(mma_bar);
-      }
-      mbar_wait(mma_bar, mma_phase);
-      mma_phase ^= 1;
-      fence_after();
-#ifdef TVM_EXP_NOMLP
-      mlp_group_sync();
-      continue;
-#endif
-      float rgb_d0 = 0.0f, rgb_d1 = 0.0f, rgb_d2 = 0.0f, tint = 1.0f;
-      {
-        // ---- epi0: features -> [feat, view, sin/cos PE] as bf16 (tensorBase.py:76-83, 9-15) -------
-        float x[32];
-        tmem_ld32(lane_addr + kColBasis, x);
-        float ndot = 0.0f;
-        if (REF) {
-          // REFTensoRF.py:216-232: heads -> unit normal, reflected direction, -dot, diffuse colour, tint
-          float hx[16];
-          tmem_ld16(lane_addr + kColBasis + 32, hx);
-          float nx = x[APP_DIM] + sHB[APP_DIM], ny = x[APP_DIM + 1] + sHB[APP_DIM + 1], nz = x[APP_DIM + 2] + sHB[APP_DIM + 2];
-          auto head = [&](int o) { return (o < 32 ? x[o] : hx[o - 32]) + sHB[o]; };
-          rgb_d0 = head(APP_DIM + 3); rgb_d1 = head(APP_DIM + 4); rgb_d2 = head(APP_DIM + 5);
-          tint = fmaxf(head(APP_DIM + 6), 0.0f);
-          const float inv = rsqrtf(fmaxf(nx * nx + ny * ny + nz * nz, 1e-30f));
-          nx *= inv; ny *= inv; nz *= inv;
-          const float dx = -dir[0], dy = -dir[1], dz = -dir[2];
-          const float dot = dx * nx + dy * ny + dz * nz;
-          dir[0] = 2.0f * dot * nx - dx;
-          dir[1] = 2.0f * dot * ny - dy;
-          dir[2] = 2.0f * dot * nz - dz;
-          ndot = -dot;
-          if (e < n_ent) {
-            const float pen = fmaxf(-dot, 0.0f);
-            P.ws.ent_pen[e] = pen * pen;
-            if (P.aux.penalty) pen_acc = fmaf(P.ws.ent_w[e], pen * pen, pen_acc);     // one atomic per warp at the end of the CTA
-          }
-        }
-        float s1[APP_DIM + 3], c1[APP_DIM + 3];
-#pragma unroll
-        for (int o = 0; o < APP_DIM; ++o) __sincosf(x[o], &s1[o], &c1[o]);
-#pragma unroll
-        for (int o = 0; o < 3; ++o) __sincosf(dir[o], &s1[APP_DIM + o], &c1[APP_DIM + o]);
-        auto column = [&](int cc) -> float {
-          constexpr int PF = APP_DIM + 3, NF = FEA_PE * APP_DIM, PV = PF + 2 * NF, NV = VIEW_PE * 3;
-          if (REF && cc == 0) return ndot;
-          const int c = cc - C0;
-          if (c < APP_DIM) return x[c];
-          if (c < PF) return dir[c - APP_DIM];
-          if (c < PF + NF) { const int o = (c - PF) >> 1; return ((c - PF) & 1) ? 2.0f * s1[o] * c1[o] : s1[o]; }
-          if (c < PV) { const int o = (c - PF - NF) >> 1; return ((c - PF - NF) & 1) ? 1.0f - 2.0f * s1[o] * s1[o] : c1[o]; }
-          if (c < PV + NV) { const int o = APP_DIM + ((c - PV) >> 1); return ((c - PV) & 1) ? 2.0f * s1[o] * c1[o] : s1[o]; }
-          if (c < PV + 2 * NV) { const int o = APP_DIM + ((c - PV - NV) >> 1); return ((c - PV - NV) & 1) ? 1.0f - 2.0f * s1[o] * s1[o] : c1[o]; }
-          if (cc == IN_C) return 1.0f;                 // constant-one column: row IN_C of the W1 operand is b1
-          return 0.0f;
-        };
-#pragma unroll
-        for (int kc = 0; kc < K1 / 8; ++kc) {
-          uint4 v;
-          v.x = pack16<H16>(column(kc * 8 + 0), column(kc * 8 + 1));
-          v.y = pack16<H16>(column(kc * 8 + 2), column(kc * 8 + 3));
-          v.z = pack16<H16>(column(kc * 8 + 4), column(kc * 8 + 5));
-          v.w = pack16<H16>(column(kc * 8 + 6), column(kc * 8 + 7));
-          *reinterpret_cast<uint4*>(arow + kc * LBO_A) = v;
-        }
-      }
-      fence_async_smem();
-      fence_before();
-      mlp_group_sync();
-      // ---- GEMM1: A1 . W1^T -------------------------------------------------------------------------
-      if (tid == 0) {
-        fence_after();
-#pragma unroll
-        for (int k = 0; k < K1 / 16; ++k)
-          umma_bf16(tmem, smem_desc(aA + k * 2 * LBO_A, LBO_A, SBO), smem_desc(aB1 + k * 2 * LBO_B, LBO_B, SBO),
-                    IDESC_N128, k > 0);
-        umma_commit(mma_bar);
-      }
-      mbar_wait(mma_bar, mma_phase);
-      mma_phase ^= 1;
-      fence_after();
-      // ---- epi1: ReLU -> A2 (bf16); b1 came with the GEMM ----------------------------------------------
-#pragma unroll
-      for (int cb = 0; cb < 4; ++cb) {
-        float y[32];
-        tmem_ld32(lane_addr + cb * 32, y);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], 0.0f);
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 v;
-          v.x = pack16<H16>(y[g * 8 + 0], y[g * 8 + 1]);
-          v.y = pack16<H16>(y[g * 8 + 2], y[g * 8 + 3]);
-          v.z = pack16<H16>(y[g * 8 + 4], y[g * 8 + 5]);
-          v.w = pack16<H16>(y[g * 8 + 6], y[g * 8 + 7]);
-          *reinterpret_cast<uint4*>(arow + (cb * 4 + g) * LBO_A) = v;
-        }
-      }
-      // columns 128..143: a constant one (row 128 of the W2 / W3 operands is b2 / b3), then zeros
-      *reinterpret_cast<uint4*>(arow + 16 * LBO_A) = make_uint4(H16 ? 0x00003c00u : 0x00003f80u, 0u, 0u, 0u);
-      *reinterpret_cast<uint4*>(arow + 17 * LBO_A) = make_uint4(0u, 0u, 0u, 0u);
-      fence_async_smem();
-      fence_before();
-      mlp_group_sync();
-      // ---- GEMM2: [A2 | 1] . [W2^T; b2] -----------------------------------------------------------------
-      if (tid == 0) {
-        fence_after();
-#pragma unroll
-        for (int k = 0; k < 128 / 16; ++k)
-          umma_bf16(tmem, smem_desc(aA + k * 2 * LBO_A, LBO_A, SBO), smem_desc(aB2 + k * 2 * LBO_B, LBO_B, SBO),
-                    IDESC_N128, k > 0);
-        umma_bf16(tmem, smem_desc(aA + 16 * LBO_A, LBO_A, SBO), smem_desc(aB2x, LBO_B, SBO), IDESC_N128, true);
-        umma_commit(mma_bar);
-      }
-      mbar_wait(mma_bar, mma_phase);
-      mma_phase ^= 1;
-      fence_after();
-      // ---- epi2: ReLU -> A3 (bf16, the constant-one column of A2 stays) ---------------------------------------
-#pragma unroll
-      for (int cb = 0; cb < 4; ++cb) {
-        float y[32];
-        tmem_ld32(lane_addr + cb * 32, y);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], 0.0f);
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 v;
-          v.x = pack16<H16>(y[g * 8 + 0], y[g * 8 + 1]);
-          v.y = pack16<H16>(y[g * 8 + 2], y[g * 8 + 3]);
-          v.z = pack16<H16>(y[g * 8 + 4], y[g * 8 + 5]);
-          v.w = pack16<H16>(y[g * 8 + 6], y[g * 8 + 7]);
-          *reinterpret_cast<uint4*>(arow + (cb * 4 + g) * LBO_A) = v;
-        }
-      }
-      fence_async_smem();
-      fence_before();
-      mlp_group_sync();
-      // ---- GEMM3: [A3 | 1] . [W3^T; b3] (N = 16, 3 real columns) ----------------------------------------------
-      if (tid == 0) {
-        fence_after();
-#pragma unroll
-        for (int k = 0; k < 144 / 16; ++k)
-          umma_bf16(tmem + kColOut, smem_desc(aA + k * 2 * LBO_A, LBO_A, SBO), smem_desc(aB3 + k * 2 * LBO_B3, LBO_B3, SBO),
-                    IDESC_N16, k > 0);
-        umma_commit(mma_bar);
-      }
-      mbar_wait(mma_bar, mma_phase);
-      mma_phase ^= 1;
-      fence_after();
-      float o0, o1, o2;
-      {
-        float o[16];
-        tmem_ld16(lane_addr + kColOut, o);
-        o0 = o[0]; o1 = o[1]; o2 = o[2];
-      }
-      if (e < n_ent) {
-        // REF: rgb = tint * clamp(rgb_s, 0) + rgb_d (REFTensoRF.py:232); VM: tint = 1, rgb_d = 0
-        P.ws.ent_rgb[(size_t)e * 3 + 0] = tint / (1.0f + __expf(-o0)) + rgb_d0;
-        P.ws.ent_rgb[(size_t)e * 3 + 1] = tint / (1.0f + __expf(-o1)) + rgb_d1;
-        P.ws.ent_rgb[(size_t)e * 3 + 2] = tint / (1.0f + __expf(-o2)) + rgb_d2;
-      }
-      fence_before();
-      mlp_group_sync();     // TMEM columns and the A operand are free for the next tile
-    }
-    if (REF && P.aux.penalty) {
-      pen_acc = warp_sum(pen_acc);
-      if (lane == 0 && pen_acc != 0.0f) atomicAdd(P.aux.penalty, pen_acc);
-    }
-  }
-
-  fence_before();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, kTmemCols);
-}
-
-// ------------------------------------------------------------------------------------------------
 static bool tc_supported(const TvmModel& m) {
   return m.n_app == 48 && m.app_dim == 27 && m.fea_pe == 2 && m.view_pe == 2 && m.feature_c == 128;
 }
@@ -434,27 +63,7 @@ int launch_app_tc(const FwdParams& P, int num_sms, cudaStream_t stream) {
   TVM_REQUIRE(tc_supported(P.m), "tensor-core appearance head supports n_app=48, app_dim=27, fea_pe=view_pe=2, "
                                  "featureC=128 (all shipped configs); use TVM_MLP_FP32 otherwise");
   TVM_REQUIRE(P.m.tc_weights != nullptr, "TvmModel.tc_weights is NULL: call tvm_pack_mlp_tc first");
-  // default: the two-group kernel with TMEM-resident activations (tvm_app_tc2.cu); TVM_APP_TC=1 selects the single-group
-  // kernel below (A/B measurements; read once)
-  static const bool use_v1 = [] { const char* e = getenv("TVM_APP_TC"); return e && e[0] == '1'; }();
-  if (!use_v1) return launch_app_tc2(P, num_sms, stream);
-  const bool ref = P.m.variant == TVM_VARIANT_REF;
-  const Image img(P.m.n_app, P.in_mlp_c, head_ld(P.m));
-  const int KA = max(img.K1, 128);
-  const size_t smem = ((img.bytes_fwd + 1023) & ~1023u) + 2 * (size_t)kRows * img.K0 * 2 + (size_t)kRows * KA * 2 + 128 + 1024;
-  const bool pb16 = P.m.app_plane_pair[0] && P.m.app_plane_pair[1] && P.m.app_plane_pair[2] && P.m.app_line_pair[0] &&
-                    P.m.app_line_pair[1] && P.m.app_line_pair[2];
-  void (*kern)(const FwdParams);
-  if (h16)
-    kern = ref ? (pb16 ? k_app_tc<48, 27, 2, 2, true, true, true> : k_app_tc<48, 27, 2, 2, true, false, true>)
-               : (pb16 ? k_app_tc<48, 27, 2, 2, false, true, true> : k_app_tc<48, 27, 2, 2, false, false, true>);
-  else
-    kern = ref ? (pb16 ? k_app_tc<48, 27, 2, 2, true, true, false> : k_app_tc<48, 27, 2, 2, true, false, false>)
-               : (pb16 ? k_app_tc<48, 27, 2, 2, false, true, false> : k_app_tc<48, 27, 2, 2, false, false, false>);
-  TVM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<num_sms, kThreadsV2, smem, stream>>>(P);
-  TVM_CHECK_CUDA(cudaGetLastError());
-  return 0;
+  return launch_app_tc2(P, num_sms, stream);
 }
 
 }  // namespace tvm

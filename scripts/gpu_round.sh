@@ -22,11 +22,11 @@ if [ -n "$BENCH_EXTRA" ]; then
 fi
 if [ -z "$NO_NCU" ]; then
 echo "== ncu launches"
-CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline"
+CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extras"
 timeout 600 $CMD > $OUT/plain.log 2>&1 &&
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 30 -c 60 --csv --log-file $OUT/launches.csv $CMD > $OUT/ncu_launch.log 2>&1
 echo "ncu launches rc=$?"
-timeout 1200 ncu --set full --clock-control none --import-source on -k "regex:${NCU_KERNEL:-k_march|k_app_tc}" -s ${NCU_SKIP:-36} -c ${NCU_COUNT:-2} -f -o $OUT/prof $CMD > $OUT/ncu_full.log 2>&1
+timeout 1200 ncu --set full --clock-control none --import-source on -k "regex:${NCU_KERNEL:-k_march|k_app_tc2}" -s ${NCU_SKIP:-36} -c ${NCU_COUNT:-2} -f -o $OUT/prof $CMD > $OUT/ncu_full.log 2>&1
 echo "ncu full rc=$?"; tail -3 $OUT/ncu_full.log
 fi
 ls -la $OUT
