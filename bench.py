@@ -283,6 +283,28 @@ def run_maintain(args):
         m128.upsample_volume_grid((G, G, G))
     ms = timed(up_fresh)
     row("upsample_volume_grid_128_to_%d" % G, ms, (nd + na) * 4.0 + 3 * 64 * 128 * 128 * 4.0, "write new planes + read old ones")
+    # ---- the kernels alone, as the captured training step / the maintenance calls launch them (no autograd, no allocation) ----
+    import ctypes as C
+    Lb, lib = pkg._lib, pkg._lib.load()
+    st = lambda: C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    planes = [*model.density_plane, *model.app_plane]
+    grads = [torch.zeros_like(p) for p in planes]
+    loss = torch.zeros(1, device=dev)
+    for ow, name, bpe in ((1, "TV_sweep_kernel_6_planes_overwrite", 8.0), (0, "TV_sweep_kernel_6_planes_accumulate", 12.0)):
+        jobs = (Lb.TvmTvJob * 6)(*[Lb.TvmTvJob(p.data_ptr(), g.data_ptr(), p.shape[1], p.shape[2], p.shape[3], 1e-2, None, ow)
+                                   for p, g in zip(planes, grads)])
+        ms = timed(lambda: Lb.check(lib.tvm_tv_loss_batch(jobs, 6, C.c_void_p(loss.data_ptr()), st()), "tvm_tv_loss_batch"))
+        row(name, ms, (nd + na) * bpe, "tvm_tv_loss_batch, one launch for the six planes: read x, " +
+            ("write grad" if ow else "read + write grad") + " (what TrainStepGraph / TVLoss launch)")
+    srcs = [t.contiguous() for k in ("density_plane", "app_plane") for t in src[k]]
+    dsts = [torch.empty((1, t.shape[1], G, G), device=dev) for t in srcs]
+
+    def up_kernels():
+        for a, b in zip(srcs, dsts):
+            Lb.check(lib.tvm_upsample_grid(C.c_void_p(a.data_ptr()), a.shape[1], a.shape[2], a.shape[3], C.c_void_p(b.data_ptr()), G, G, st()),
+                     "tvm_upsample_grid")
+    ms = timed(up_kernels)
+    row("upsample_kernels_6_planes_128_to_%d" % G, ms, (nd + na) * 4.0 + 3 * 64 * 128 * 128 * 4.0, "tvm_upsample_grid x 6 into preallocated planes")
     emit(({"metric": "SURVEY 8f rows, device ms per call", "unit": "ms", "n_gpus": 1, "steps": args.steps,
                       "config": {"workload": f"maintain: {G}^3 grids, {MASK_RES}^3 alpha lattice, {FRAME}x{FRAME} frame",
                                  "l2": "flushed before every timed call"}, "hbm_peak_GBps": hbm, "rows": rows}))

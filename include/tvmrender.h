@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define TVM_ABI_VERSION 24
+#define TVM_ABI_VERSION 25
 
 /* flags for tvm_forward / tvm_backward */
 #define TVM_WHITE_BG      0x1u  /* rgb_map += 1 - acc_map          (tensorBase.py:523-524) */
@@ -365,6 +365,7 @@ typedef struct TvmTvJob {
   int32_t C, H, W;
   float weight;
   const float* weight_dev;  /* nullable DEVICE scalar multiplied into weight */
+  int32_t overwrite;        /* 0: grad += ...; 1: grad = ... (a fresh gradient buffer needs neither a memset nor a read) */
 } TvmTvJob;
 int tvm_tv_loss_batch(const TvmTvJob* jobs_host, int n_jobs, float* loss_accum, void* stream);
 int tvm_l1_loss(const float* x, size_t n, float weight, const float* weight_dev, float* loss_accum, float* grad, void* stream);

