@@ -134,22 +134,30 @@ __global__ void __launch_bounds__((kMlpWarps2 + NGW) * 32, 1) k_app_tc2(const Fw
   uint64_t* empty = bars + 2;       // [2] stage consumed by GEMM0 (tcgen05.commit)
   uint64_t* mma_bars = bars + 4;    // [2] layer GEMM of group g complete
   uint64_t* bas_bars = bars + 6;    // [2] GEMM0 of group g complete
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* w_bar = bars + 8;       // weight image landed (cp.async.bulk transaction bytes)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
   const float* sHB = reinterpret_cast<const float*>(sW + img.off_f32) + 128 + 128 + 3 * 128 + 4;   // REF head biases [48]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  // ---- one-time setup: weights -> smem, barriers, TMEM -------------------------------------------
-  {
-    const uint4* src = reinterpret_cast<const uint4*>(P.m.tc_weights);
-    uint4* dst = reinterpret_cast<uint4*>(sW);
-    for (uint32_t i = tid; i < img.bytes_fwd / 16; i += kThreads) dst[i] = __ldg(src + i);
-  }
+  // ---- one-time setup: barriers, weights -> smem, TMEM -------------------------------------------
+  // The 86 KB operand image is copied by the TMA engine (cp.async.bulk, SASS UBLKCP): one thread issues six bulk copies
+  // and goes on; nobody spends load / store instructions on it, and the copy overlaps the TMEM allocation and the
+  // register re-split.  Everybody waits for the transaction bytes on w_bar before the first use.
   if (tid == 0) {
     mbar_init(&full[0], kRows / 8);      // one arrival per 8-row pass
     mbar_init(&full[1], kRows / 8);
     for (int i = 2; i < 8; ++i) mbar_init(&bars[i], 1);
+    mbar_init(w_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(w_bar)), "r"(img.bytes_fwd) : "memory");
+    constexpr uint32_t kChunk = 16384;
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(P.m.tc_weights);
+    for (uint32_t off = 0; off < img.bytes_fwd; off += kChunk) {
+      const uint32_t sz = min(kChunk, img.bytes_fwd - off);
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(smem_u32(sW + off)), "l"(src + off), "r"(sz), "r"(smem_u32(w_bar)) : "memory");
+    }
   }
   if (warp == 0) tmem_alloc(tmem_slot, 512);
   fence_async_smem();
@@ -157,6 +165,7 @@ __global__ void __launch_bounds__((kMlpWarps2 + NGW) * 32, 1) k_app_tc2(const Fw
   __syncthreads();
   fence_after();
   const uint32_t tmem = *tmem_slot;
+  mbar_wait(w_bar, 0);
 
   constexpr uint32_t LBO_A = kRows * 16, LBO_B0 = NH * 16, LBO_B = 128 * 16, LBO_B3 = 16 * 16, SBO = 128;
   constexpr uint32_t IDESC_NH = instr_desc(128, NH, H16), IDESC_N128 = instr_desc(128, 128, H16), IDESC_N16 = instr_desc(128, 16, H16);
