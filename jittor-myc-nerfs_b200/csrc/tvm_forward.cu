@@ -16,7 +16,10 @@
 
 namespace tvm {
 
-constexpr int kMarchWarps = 4;      // 128-thread CTAs: a CTA lives as long as its slowest ray, smaller CTAs pack better (8 -> 4 warps: -2.4 %)
+#ifndef TVM_MARCH_WARPS
+#define TVM_MARCH_WARPS 4
+#endif
+constexpr int kMarchWarps = TVM_MARCH_WARPS;      // 128-thread CTAs: a CTA lives as long as its slowest ray, smaller CTAs pack better (8 -> 4 warps: -2.4 %)
 #ifndef TVM_MARCH_MIN_CTAS
 #define TVM_MARCH_MIN_CTAS 8      // 64 registers, 32 warps per SM (measured: 24 -> 32 warps = -8 % march time)
 #endif
