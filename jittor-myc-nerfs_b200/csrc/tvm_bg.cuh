@@ -8,6 +8,25 @@ namespace tvm {
 constexpr int kBgSamples = TVM_NPP_BG_SAMPLES;
 constexpr int kPosDim = 20, kDirDim = 15, kBgHid = 64;
 
+// Operand shapes and byte offsets of the background network's tensor-core weight image (tvm_pack_bg_tc), shared by the
+// forward (tvm_bg_tc.cu) and the backward (tvm_bg_bwd_tc.cu) kernels.  Every B operand is a K-major core-matrix image
+// (tvm_tc.cuh): element (n, k) at (k/8) * (N*16) + n*16 + (k%8)*2.
+namespace bgimg {
+constexpr int kPosK = 32;               // position block of the A operand (20 embedding columns, padded)
+constexpr int kOneCol = 20;             // constant 1.0: carries the biases
+constexpr int kAK = kPosK + kFeatureC;  // 160 columns
+constexpr int kN3 = 80;                 // 64 hidden rgb units + sigma + padding (N % 16 == 0)
+constexpr int kN4 = 16;                 // 3 colour channels, padded
+constexpr int kK1 = kFeatureC + 16;     // hidden + the 16 position columns that hold the one-column
+constexpr uint32_t kOffW0 = 0;                                   // [N 128][K  32]  base_layers.0 (+ b0 in row 20)
+constexpr uint32_t kOffW1 = kOffW0 + kPosK * kFeatureC * 2;     // [N 128][K 144]  base_layers.1: hidden, then position columns 16..31 (b1)
+constexpr uint32_t kOffW2 = kOffW1 + kK1 * kFeatureC * 2;       // [N 128][K 160]  base_layers.2: position block (b2 in row 20), then hidden
+constexpr uint32_t kOffW3 = kOffW2 + kAK * kFeatureC * 2;       // [N  80][K 128]  folded colour layer | sigma head | 0
+constexpr uint32_t kOffW4 = kOffW3 + kFeatureC * kN3 * 2;       // [N  16][K  64]  rgb_layers.2
+constexpr uint32_t kOffF32 = kOffW4 + kBgHid * kN4 * 2;         // fp32 tail: b_sigma, b_rgb[3]
+constexpr uint32_t kImageBytes = kOffF32 + 16;
+}  // namespace bgimg
+
 struct BgRay {
   float p_sphere[3], axis[3], cross_ap[3];   // point on the sphere, rotation axis, axis x p_sphere
   float axis_dot;                            // axis . p_sphere

@@ -11,6 +11,7 @@
 //                   products of tvm_bwd_simt.cuh and red.global.add the weight gradients.  Sample positions and view
 //                   directions carry no parameters, so nothing flows into them.
 //   k_bg_fold_bwd   transpose of k_bg_fold: gradients of the folded colour layer -> base_remap_layers.0, rgb_layers.0.
+#include <stdlib.h>
 #include "tvm_bwd_simt.cuh"
 #include "tvm_bg.cuh"
 
@@ -330,6 +331,7 @@ __global__ void k_bg_fold_bwd(const float* __restrict__ remap_w, const float* __
 }
 
 int launch_bg_refresh(const FwdParams& P, int num_sms, cudaStream_t stream);   // tvm_bg.cu
+int launch_bg_bwd_tc(const BwdParams& Bw, const TvmBgGrads& gr, int num_sms, cudaStream_t stream);   // tvm_bg_bwd_tc.cu
 
 int launch_bg_bwd(const BwdParams& Bw, const TvmBgGrads& gr, int num_sms, cudaStream_t stream) {
   const TvmBgNet& b = Bw.f.bg;
@@ -337,6 +339,11 @@ int launch_bg_bwd(const BwdParams& Bw, const TvmBgGrads& gr, int num_sms, cudaSt
               b.wv_t && b.w_rgb && b.b_rgb, "null TvmBgNet pointer");
   TVM_REQUIRE(gr.w0_t && gr.b0 && gr.w1_t && gr.b1 && gr.w2_t && gr.b2 && gr.w_sigma && gr.b_sigma && gr.wf_t && gr.bf &&
               gr.wv_t && gr.w_rgb && gr.b_rgb, "null TvmBgGrads pointer");
+  // tensor-core modes: the backward runs on the tensor cores as well (bf16 operands; its recompute is bit-identical to the
+  // forward kernel, so the forward's bg_rgb is the sum it needs).  TVM_BG_BWD_FP32=1 keeps the fp32 kernel (A/B switch).
+  static const bool force_fp32 = [] { const char* e = getenv("TVM_BG_BWD_FP32"); return e && e[0] == '1'; }();
+  if ((Bw.f.flags & TVM_MLP_MASK) != TVM_MLP_FP32 && b.tc_weights != nullptr && !force_fp32)
+    return launch_bg_bwd_tc(Bw, gr, num_sms, stream);
   // the forward ran on the tensor cores: its bg_rgb (bf16 network) is not the sum this kernel's fp32 recompute produces
   if ((Bw.f.flags & TVM_MLP_MASK) != TVM_MLP_FP32)
     if (int rc = launch_bg_refresh(Bw.f, num_sms, stream)) return rc;

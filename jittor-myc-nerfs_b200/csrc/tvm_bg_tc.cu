@@ -28,25 +28,11 @@ using namespace tc;
 constexpr int kPipes = 3;
 constexpr int kPipeThreads = 128;
 constexpr int kThreads = kPipes * kPipeThreads;
-constexpr int kPosK = 32;               // position block of the A operand (20 embedding columns, padded)
-constexpr int kOneCol = 20;             // constant 1.0: carries the biases
-constexpr int kAK = kPosK + kFeatureC;  // 160 columns
-constexpr int kN3 = 80;                 // 64 hidden rgb units + sigma + padding (N % 16 == 0)
-constexpr int kN4 = 16;                 // 3 colour channels, padded
-constexpr int kK1 = kFeatureC + 16;     // hidden + the 16 position columns that hold the one-column
+using namespace bgimg;                  // operand shapes and byte offsets of the weight image (tvm_bg.cuh)
 constexpr int kTmemColsBg = 512;        // 128 accumulator columns per pipeline (power of two >= 3 * 128)
 
 constexpr uint32_t kLboA = kRows * 16;
 constexpr uint32_t kABytes = kRows * kAK * 2;
-
-// byte offsets of the B operands inside the weight image (K-major core-matrix layout, see tvm_tc.cuh)
-constexpr uint32_t kOffW0 = 0;
-constexpr uint32_t kOffW1 = kOffW0 + kPosK * kFeatureC * 2;
-constexpr uint32_t kOffW2 = kOffW1 + kK1 * kFeatureC * 2;
-constexpr uint32_t kOffW3 = kOffW2 + kAK * kFeatureC * 2;
-constexpr uint32_t kOffW4 = kOffW3 + kFeatureC * kN3 * 2;
-constexpr uint32_t kOffF32 = kOffW4 + kBgHid * kN4 * 2;     // fp32 tail: b_sigma, b_rgb[3]
-constexpr uint32_t kImageBytes = kOffF32 + 16;
 
 __device__ __forceinline__ void pipe_sync(int pipe) {
   asm volatile("bar.sync %0, %1;" ::"r"(pipe + 1), "n"(kPipeThreads) : "memory");

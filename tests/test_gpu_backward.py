@@ -458,14 +458,19 @@ def test_nerfplusplus_backward(env, regime, G, S):
         # samples with mixed signs: fp32 (kernel) vs fp64 (oracle) leaves ~5e-4 of the largest entry there, <= 1.5e-4 elsewhere
         tol = 1.5e-3 if "sigma_layers" in name else (3e-4 if name.startswith("bg_net.") else GRAD_RTOL)
         assert w <= tol, f"{name}: {w:.3e}"
-    # ... and the same step with the tensor-core forward (bf16): the background backward stays fp32
+    # ... and the same step on the tensor cores (bf16 operands): k_bg_tc forward, k_bg_bwd_tc backward (tvm_bg_bwd_tc.cu)
     m16 = gpu_model(pkg, case, mlp_mode="bf16")
     rgb16, _ = m16(rays, N_samples=S, fg_rand=fg, bg_rand=bg)
     (rgb16 * torch.from_numpy(d_rgb).cuda()).sum().backward()
     torch.cuda.synchronize()
+    l2 = {}
     for name, p in [(k, v) for k, v in m16.named_parameters() if k.startswith("bg_net.")]:
         g, r = p.grad.detach().cpu().numpy().astype(np.float64), ref["grads"][name]
-        assert np.linalg.norm(g - r) <= 5e-2 * np.linalg.norm(r), name
+        assert np.isfinite(g).all(), name
+        l2[name] = float(np.linalg.norm(g - r) / np.linalg.norm(r))
+    print(f"NeRF++ backward {regime} bf16 (tensor cores), relative L2:", {k[7:]: f"{v:.1e}" for k, v in sorted(l2.items(), key=lambda kv: -kv[1])})
+    for name, v in l2.items():
+        assert v <= 8e-2, f"{name}: relative L2 {v:.3e}"
 
 
 @pytest.mark.gpu
