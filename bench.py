@@ -504,7 +504,7 @@ def run_side_workload(args):
         line["full_step"] = {"ms_per_step": ms_full / args.steps, "rays_per_s": n * world / (ms_full / args.steps * 1e-3),
                              "includes": "fwd + bwd + TV_loss_density + TV_loss_app (weights 2.0, configs/Scar.txt) + Adam over "
                                          "all parameter tensors + re-pack of the updated grids"}
-    if train and variant != "npp":
+    if train:
         # the same full step captured once into a CUDA graph (TrainStepGraph) and replayed: no host time between kernels
         model.collect_counters = False
         L.profile_enable(False)

@@ -1015,14 +1015,15 @@ class NerfPlusPlus(TensorVMSplit):
                 bgp[offs["b_rgb"]:offs["b_rgb"] + 3].clone()]
         return [*fg, *out]
 
-    def _bg_struct(self):
-        """TvmBgNet over a packed fp32 buffer; re-packed (and re-folded) when a bg parameter changed."""
+    def _bg_struct(self, force=False):
+        """TvmBgNet over a packed fp32 buffer; re-packed (and re-folded) when a bg parameter changed (force: always -- the
+        captured training step re-packs at its end, because a replay runs no host-side version check)."""
         lib = L.load()
         n = self.bg_net
         params = list(n.parameters())
         versions = tuple((p.data_ptr(), p._version) for p in params)
         sizes, offs, off = self._bg_layout()
-        if self._bg_packed is None or versions != self._bg_versions:
+        if self._bg_packed is None or versions != self._bg_versions or force:
             if self._bg_packed is None:
                 self._bg_packed = torch.zeros(off, dtype=torch.float32, device=self.device)
             buf, st = self._bg_packed, _stream_ptr()

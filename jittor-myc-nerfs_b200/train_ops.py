@@ -260,6 +260,7 @@ class TrainStepGraph:
         self.reg_loss = torch.zeros(1, dtype=torch.float32, device=dev)      # sum of the weighted regularisers
         self.jitter = None                  # optional static [n] buffer (step(..., jitter=...)); default: torch.rand per step
         self.graph = None
+        self.npp = hasattr(model, "bg_net")         # NerfPlusPlus: tvm_forward_npp / tvm_backward_npp, background net in the optimiser
 
     def set_weights(self, TV_weight_density=None, TV_weight_app=None, L1_reg_weight=None, Ortho_reg_weight=None,
                     normal_vector_penalty_weight=None):
@@ -271,6 +272,8 @@ class TrainStepGraph:
         """The step without the autograd engine: every kernel is enqueued by this thread on the capturing stream."""
         m, lib = self.model, L.load()
         n = self.rays.shape[0]
+        if self.npp:
+            return self._body_npp()
         jitter = self.jitter if self.jitter is not None else torch.rand(n, dtype=torch.float32, device=self.rays.device)
         flags = m._flags(self.white_bg)
         rgb, _ = m._forward_raw(self.rays, jitter, flags, self.S)
@@ -284,17 +287,23 @@ class TrainStepGraph:
         if m.grad_sync and m._peer_comm is not None and os.environ.get("TVM_AR_OVERLAP", "2") == "2":
             return self._body_pipelined(jitter, flags, rgb, d_rgb, d_pen)
         grads = m._backward_raw(self.rays, jitter, flags, self.S, rgb, d_rgb, d_pen)
-        params = m._param_list()
+        self._regularisers_and_update(m._param_list(), grads)
+        m._pack(force=True)                       # the next forward (and any render in between) sees the updated grids
+
+    def _regularisers_and_update(self, params, grads):
+        """Tail of the serial step: .grad <- gradients, regularisers (train.py:233-251) as value + gradient sweeps straight into
+        .grad with device-side weights, multi-tensor Adam."""
+        m, lib = self.model, L.load()
         for p, g in zip(params, grads):
             p.grad = g
-        # regularisers (train.py:233-251): value + gradient sweeps straight into .grad, weights read from the device
+        reg, w = self.reg_loss, self._w_dev
         tv_jobs = []
         for on, planes, wd in ((self.use["tv_d"], m.density_plane, w[0:1]), (self.use["tv_a"], m.app_plane, w[1:2])):
             if on:
                 for p in planes:
                     _, Cc, H, W = p.shape
                     tv_jobs.append(L.TvmTvJob(p.data_ptr(), p.grad.data_ptr(), Cc, H, W, 1e-2, wd.data_ptr()))
-        if tv_jobs:        # all TV sweeps of the step in one launch
+        if tv_jobs:
             L.check(lib.tvm_tv_loss_batch((L.TvmTvJob * len(tv_jobs))(*tv_jobs), len(tv_jobs), _ptr(reg), _stream_ptr()),
                     "tvm_tv_loss_batch")
         if self.use["l1"]:
@@ -304,7 +313,23 @@ class TrainStepGraph:
             for p in [*m.density_line, *m.app_line]:
                 _launch("ortho", p.detach(), 1.0, reg, p.grad, w[3:4])
         self.opt._launch()
-        m._pack(force=True)                       # the next forward (and any render in between) sees the updated grids
+
+    def _body_npp(self):
+        """NerfPlusPlus (configs/Scarf.txt): foreground on black + 512-sample background network; the stratified draws of
+        perturb_samples (nerfplusplus.py:196-205) come from the device generator inside the graph."""
+        m, lib = self.model, L.load()
+        n, dev = self.rays.shape[0], self.rays.device
+        fg_rand = torch.rand((n, self.S), dtype=torch.float32, device=dev)
+        bg_rand = torch.rand((n, 512), dtype=torch.float32, device=dev)
+        flags = m._flags(False)
+        rgb, _ = m._forward_npp_raw(self.rays, fg_rand, bg_rand, flags, self.S)
+        d_rgb = torch.empty_like(rgb)
+        L.check(lib.tvm_mse_loss(_ptr(rgb), _ptr(self.target), n, 1.0, _ptr(self.loss), _ptr(d_rgb), _stream_ptr()), "tvm_mse_loss")
+        self.reg_loss.zero_()
+        grads = m._backward_npp_raw(self.rays, fg_rand, bg_rand, flags, self.S, rgb, d_rgb)
+        self._regularisers_and_update([*m._param_list(), *m._bg_param_list()], grads)
+        m._pack(force=True)
+        m._bg_struct(force=True)                  # the background network's packed fp32 buffer, fold and bf16 image follow the update
 
     def _body_pipelined(self, jitter, flags, rgb, d_rgb, d_pen):
         """Tail of the data-parallel step with the gradient exchange hidden behind it (peer all-reduce, tvm_backward_dp phases):
@@ -352,7 +377,9 @@ class TrainStepGraph:
                 None if getattr(m, "_grads_packed", None) is None else m._grads_packed.data_ptr(),
                 None if m._ws is None else (m._ws.data_ptr(), m._ws.numel()),
                 None if m._tc is None else m._tc.data_ptr(),
-                None if getattr(m, "_app16", None) is None else m._app16.data_ptr())
+                None if getattr(m, "_app16", None) is None else m._app16.data_ptr(),
+                None if getattr(m, "_bg_packed", None) is None else m._bg_packed.data_ptr(),
+                None if getattr(m, "_bg_tc", None) is None else m._bg_tc.data_ptr())
 
     def capture(self):
         """Warm up on a side stream (torch's capture protocol), then record the step.  The warm-up steps are real
@@ -361,7 +388,7 @@ class TrainStepGraph:
         maintenance call -- does not disturb a run in progress."""
         m, opt = self.model, self.opt
         params = [p for g in opt.param_groups for p in g["params"]]
-        live = {id(p) for p in m._param_list()}
+        live = {id(p) for p in m._param_list()} | ({id(p) for p in m._bg_param_list()} if self.npp else set())
         if not live <= {id(p) for p in params}:
             raise RuntimeError("TrainStepGraph: the optimizer does not hold the model's current parameters (the grids were "
                                "replaced by upsample_volume_grid / shrink / load): build a new optimizer and a new TrainStepGraph")
