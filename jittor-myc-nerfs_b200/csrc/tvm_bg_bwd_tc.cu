@@ -3,8 +3,9 @@
 // (models/nerfplusplus.py:66-140) through the 512-sample background compositing (:283-317); Jittor autograd in the reference
 // (train.py:228,260).
 //
-// One persistent CTA per SM, 128 threads (thread = sample row = TMEM lane), rays handed out by a global counter, tiles of 128
-// samples in the forward kernel's order (k_bg_tc).  Per tile every dense product runs as tcgen05.mma with bf16 operands and
+// One persistent CTA per SM, rays handed out by a global counter, tiles of 128 samples in the forward kernel's order (k_bg_tc).
+// 256 threads: threads t and t + 128 both own sample row t (= TMEM lane t; warps w and w + 4 share lane quadrant w) and split the
+// columns of every epilogue between them; the row's scalar chain (geometry, compositing, its backward) is computed by both.  Per tile every dense product runs as tcgen05.mma with bf16 operands and
 // fp32 accumulation; ONE shared-memory image per tensor serves the forward product, the data gradient and the weight
 // gradient, read K-major or MN-major ("transposed", tvm_tc_selftest.cu):
 //
@@ -34,13 +35,13 @@ namespace bgbwd {
 using namespace tc;
 using namespace bgimg;
 
-constexpr int kThreads = 128;
+constexpr int kThreads = 256;                         // two warps per TMEM lane quadrant: each takes half of the columns of every epilogue
 constexpr uint32_t kLbo = kRows * 16;                  // 2048: next 8 columns of a 128-row image
 // TMEM columns
 constexpr uint32_t cWork = 0, cDW1 = 128, cDW2 = 256, cDWf = 384, cDW2p = 448, cDW0 = 480;
 constexpr uint32_t MN = kIdescAMajorMN | kIdescBMajorMN;
 
-__device__ __forceinline__ void row_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void row_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 __device__ __forceinline__ float bf_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 __device__ __forceinline__ uint32_t pack_relu_bf16(float lo, float hi) {
@@ -97,22 +98,23 @@ __global__ void __launch_bounds__(kThreads, 1) k_bg_bwd_tc(const Params Bp) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
   uint32_t* sRay = tmem_slot + 1;
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x & 127, half = threadIdx.x >> 7, warp = tid >> 5, lane = tid & 31;    // tid: sample row; half: column half
+  const bool lead = half == 0;                                                                     // the half that does the unique writes
   const float R = P.m.radii;
 
   {
     const uint4* src = reinterpret_cast<const uint4*>(bg.tc_weights);
     uint4* dst = reinterpret_cast<uint4*>(sW);
-    for (uint32_t i = tid; i < kImageBytes / 16; i += kThreads) dst[i] = __ldg(src + i);
+    for (uint32_t i = threadIdx.x; i < kImageBytes / 16; i += kThreads) dst[i] = __ldg(src + i);
   }
-  for (int i = tid; i < 3 * kBgHid; i += kThreads) WRGB[i] = bg.w_rgb[i];
-  WSIG[tid] = bg.w_sigma[tid];
-  for (int i = tid; i < kFEnd - kFDB1; i += kThreads) F[kFDB1 + i] = 0.0f;      // every accumulator (and WP / WQ / E)
-  if (tid == 0) {
+  for (int i = threadIdx.x; i < 3 * kBgHid; i += kThreads) WRGB[i] = bg.w_rgb[i];
+  if (lead) WSIG[tid] = bg.w_sigma[tid];
+  for (int i = threadIdx.x; i < kFEnd - kFDB1; i += kThreads) F[kFDB1 + i] = 0.0f;      // every accumulator (and WP / WQ / E)
+  if (threadIdx.x == 0) {
     mbar_init(mma_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  if (threadIdx.x < 32) tmem_alloc(tmem_slot, 512);
   fence_async_smem();
   fence_before();
   __syncthreads();
@@ -132,6 +134,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_bg_bwd_tc(const Params Bp) {
   constexpr uint32_t ID128 = instr_desc(128, 128), ID80 = instr_desc(128, kN3), ID16 = instr_desc(128, kN4),
                      ID64 = instr_desc(128, kBgHid), ID32 = instr_desc(128, kPosK);
   const uint32_t n_active = P.ws.n_entries[1];
+  const bool issuer = threadIdx.x == 0;
   uint32_t phase = 0;
   bool first = true;                                   // no persistent accumulator has been written yet
 
@@ -153,7 +156,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_bg_bwd_tc(const Params Bp) {
   // accumulator columns [0, 128) of this row -> ReLU -> bf16 -> 16 chunks of a 128-row image
   auto epi_relu_store = [&](uint8_t* dst_row) {
 #pragma unroll
-    for (int cb = 0; cb < 4; ++cb) {
+    for (int cb = 2 * half; cb < 2 * half + 2; ++cb) {
       float y[32];
       tmem_ld32(lane_addr + cWork + cb * 32, y);
 #pragma unroll
@@ -167,7 +170,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_bg_bwd_tc(const Params Bp) {
   // optionally adds the column sums of the masked values to a shared accumulator
   auto epi_delta = [&](uint8_t* row_img, float extra, float* colsum) {
 #pragma unroll
-    for (int cb = 0; cb < 4; ++cb) {
+    for (int cb = 2 * half; cb < 2 * half + 2; ++cb) {
       float d[32];
       tmem_ld32(lane_addr + cWork + cb * 32, d);
 #pragma unroll
@@ -193,7 +196,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_bg_bwd_tc(const Params Bp) {
 
   while (true) {
     row_sync();
-    if (tid == 0) *sRay = atomicAdd(P.ws.n_entries + 3, 1u);
+    if (threadIdx.x == 0) *sRay = atomicAdd(P.ws.n_entries + 3, 1u);
     row_sync();
     const uint32_t idx = *sRay;
     if (idx >= n_active) break;
@@ -208,7 +211,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_bg_bwd_tc(const Params Bp) {
                        g2 * P.ws.bg_rgb[(size_t)ray * 3 + 2];
     BgRay g;
     bg_ray_setup(ray6, R, g);
-    if (tid < kBgHid) {
+    if (lead && tid < kBgHid) {
       // view-direction embedding through its slice of rgb_layers.0, plus the folded bias (fp32, once per ray; as k_bg_tc)
       const float dn = 1.0f / sqrtf(ray6[3] * ray6[3] + ray6[4] * ray6[4] + ray6[5] * ray6[5]);
       const float v[3] = {ray6[3] * dn, ray6[4] * dn, ray6[5] * dn};
@@ -255,14 +258,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_bg_bwd_tc(const Params Bp) {
           s2[c] = 2.0f * s1[c] * cc1[c];
           cc2[c] = 1.0f - 2.0f * s1[c] * s1[c];
         }
+        if (lead) {
         *reinterpret_cast<uint4*>(xrow + 0 * kLbo) = make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(s1[0], s1[1]), pack_bf16(s1[2], s1[3]));
         *reinterpret_cast<uint4*>(xrow + 1 * kLbo) = make_uint4(pack_bf16(cc1[0], cc1[1]), pack_bf16(cc1[2], cc1[3]), pack_bf16(s2[0], s2[1]), pack_bf16(s2[2], s2[3]));
         *reinterpret_cast<uint4*>(xrow + 2 * kLbo) = make_uint4(pack_bf16(cc2[0], cc2[1]), pack_bf16(cc2[2], cc2[3]), pack_bf16(1.0f, 0.0f), 0u);
         *reinterpret_cast<uint4*>(xrow + 3 * kLbo) = make_uint4(0u, 0u, 0u, 0u);
+        }
       }
       publish();
       // ================================ forward recompute =======================================================
-      if (tid == 0) {                                             // L0: X0 -> Y0
+      if (issuer) {                                               // L0: X0 -> Y0
         fence_after();
         kmajor(tmem + cWork, aXA, aW0, kFeatureC * 16, kPosK / 16, ID128, false);
         umma_commit(mma_bar);
@@ -270,7 +275,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_bg_bwd_tc(const Params Bp) {
       mma_wait();
       epi_relu_store(h1row);
       publish();
-      if (tid == 0) {                                             // L1: Y0 (+ bias through position columns 16..31) -> Y1
+      if (issuer) {                                               // L1: Y0 (+ bias through position columns 16..31) -> Y1
         fence_after();
         kmajor(tmem + cWork, aH1, aW1, kFeatureC * 16, kFeatureC / 16, ID128, false);
         kmajor(tmem + cWork, aXA + 2 * kLbo, aW1 + (kFeatureC / 8) * kFeatureC * 16, kFeatureC * 16, 1, ID128, true);
@@ -279,7 +284,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_bg_bwd_tc(const Params Bp) {
       mma_wait();
       epi_relu_store(h1row);
       publish();
-      if (tid == 0) {                                             // L2: [X0 | Y1] -> Y2
+      if (issuer) {                                               // L2: [X0 | Y1] -> Y2
         fence_after();
         kmajor(tmem + cWork, aXA, aW2, kFeatureC * 16, kAK / 16, ID128, false);
         umma_commit(mma_bar);
@@ -287,7 +292,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_bg_bwd_tc(const Params Bp) {
       mma_wait();
       epi_relu_store(y2row);
       publish();
-      if (tid == 0) {                                             // L3: Y2 -> (HID | sigma)
+      if (issuer) {                                               // L3: Y2 -> (HID | sigma)
         fence_after();
         kmajor(tmem + cWork, aY2, aW3, kN3 * 16, kFeatureC / 16, ID80, false);
         umma_commit(mma_bar);
@@ -295,8 +300,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_bg_bwd_tc(const Params Bp) {
       mma_wait();
       float sig_pre;
       {
-#pragma unroll
-        for (int cb = 0; cb < 2; ++cb) {
+        {
+          const int cb = half;
           float y[32];
           tmem_ld32(lane_addr + cWork + cb * 32, y);
 #pragma unroll
@@ -315,7 +320,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_bg_bwd_tc(const Params Bp) {
         sig_pre = t16[0] + b_sigma;                                          // sigma = |w . base + b| (:128-129)
       }
       publish();
-      if (tid == 0) {                                             // L4: HID -> logits
+      if (issuer) {                                               // L4: HID -> logits
         fence_after();
         kmajor(tmem + cWork, aHID, aW4, kN4 * 16, kBgHid / 16, ID16, false);
         umma_commit(mma_bar);
@@ -341,7 +346,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_bg_bwd_tc(const Params Bp) {
       }
       float excl = __shfl_up_sync(0xffffffffu, pref, 1);
       if (lane == 0) excl = 1.0f;
-      if (lane == 31) WP[warp] = pref;
+      if (lead && lane == 31) WP[warp] = pref;
       fence_before();
       row_sync();
       const float p0 = WP[0], p1 = WP[1], p2 = WP[2], p3 = WP[3];
@@ -355,7 +360,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_bg_bwd_tc(const Params Bp) {
         const float t = __shfl_up_sync(0xffffffffu, ps, o);
         if (lane >= o) ps += t;
       }
-      if (lane == 31) WQ[warp] = ps;
+      if (lead && lane == 31) WQ[warp] = ps;
       row_sync();
       const float q0 = WQ[0], q1 = WQ[1], q2 = WQ[2], q3 = WQ[3];
       const float incl = carry + ps + (warp == 0 ? 0.0f : warp == 1 ? q0 : warp == 2 ? q0 + q1 : q0 + q1 + q2);
@@ -369,7 +374,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_bg_bwd_tc(const Params Bp) {
       {
         // b_rgb, b_sigma
         const float s0 = warp_sum(dl0), s1 = warp_sum(dl1), s2 = warp_sum(dl2), s3 = warp_sum(dsp);
-        if (lane == 0) {
+        if (lead && lane == 0) {
           atomicAdd(SMALL + 0, s0);
           atomicAdd(SMALL + 1, s1);
           atomicAdd(SMALL + 2, s2);
@@ -378,8 +383,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_bg_bwd_tc(const Params Bp) {
       }
       // ---- rank-3 colour layer: d w_rgb += dlogit (x) hid;  DH = (W_rgb^T dlogit) * [hid > 0] over HID;  d VB += DH ---------
       // ---- rank-1 sigma head:   d w_sigma += d sigma_pre * y2 -----------------------------------------------------------------
-#pragma unroll 1
-      for (int cb = 0; cb < kBgHid / 32; ++cb) {
+      {
+        const int cb = half;
         float h[32], dh[32];
 #pragma unroll
         for (int kc = 0; kc < 4; ++kc) {
@@ -409,7 +414,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_bg_bwd_tc(const Params Bp) {
         atomicAdd(DWRGB + 2 * kBgHid + cb * 32 + lane, warp_colsum32(t, lane));
       }
 #pragma unroll 1
-      for (int cb = 0; cb < kFeatureC / 32; ++cb) {
+      for (int cb = 2 * half; cb < 2 * half + 2; ++cb) {
         float t[32];
 #pragma unroll
         for (int kc = 0; kc < 4; ++kc) {
@@ -422,7 +427,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_bg_bwd_tc(const Params Bp) {
       }
       publish();
       // ================================ dense backward ================================================================
-      if (tid == 0) {
+      if (issuer) {
         fence_after();
         // dWf (+)= Y2^T DH   [128 y2 features x 64 hidden units], reduction over the 128 rows
         for (int s = 0; s < 8; ++s)
@@ -436,7 +441,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_bg_bwd_tc(const Params Bp) {
       mma_wait();
       epi_delta(y2row, dsp, nullptr);                             // D2 = (dY2 + d sigma_pre w_sigma) * [y2 > 0], over Y2
       publish();
-      if (tid == 0) {
+      if (issuer) {
         fence_after();
         for (int s = 0; s < 8; ++s)                               // dW2h (+)= Y1^T D2
           umma_bf16(tmem + cDW2, smem_desc(aH1 + s * 256, 128, kLbo), smem_desc(aY2 + s * 256, 128, kLbo), ID128 | MN, acc_flag | (s > 0));
@@ -450,7 +455,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_bg_bwd_tc(const Params Bp) {
       mma_wait();
       epi_delta(h1row, 0.0f, DB1);                                // D1 = dY1 * [y1 > 0], over Y1; b1 += column sums
       publish();
-      if (tid == 0) {                                             // Y0 again (it was overwritten by Y1): X0 -> work
+      if (issuer) {                                               // Y0 again (it was overwritten by Y1): X0 -> work
         fence_after();
         kmajor(tmem + cWork, aXA, aW0, kFeatureC * 16, kPosK / 16, ID128, false);
         umma_commit(mma_bar);
@@ -458,7 +463,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_bg_bwd_tc(const Params Bp) {
       mma_wait();
       epi_relu_store(y2row);                                      // into the dead D2 image
       publish();
-      if (tid == 0) {
+      if (issuer) {
         fence_after();
         for (int s = 0; s < 8; ++s)                               // dW1 (+)= Y0^T D1
           umma_bf16(tmem + cDW1, smem_desc(aY2 + s * 256, 128, kLbo), smem_desc(aH1 + s * 256, 128, kLbo), ID128 | MN, acc_flag | (s > 0));
@@ -470,7 +475,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_bg_bwd_tc(const Params Bp) {
       mma_wait();
       epi_delta(y2row, 0.0f, nullptr);                            // D0 = dY0 * [y0 > 0], over Y0
       publish();
-      if (tid == 0) {                                             // dW0^T (+)= D0^T X0
+      if (issuer) {                                               // dW0^T (+)= D0^T X0
         fence_after();
         for (int s = 0; s < 8; ++s)
           umma_bf16(tmem + cDW0, smem_desc(aY2 + s * 256, 128, kLbo), smem_desc(aXA + s * 256, 128, kLbo), ID32 | MN, acc_flag | (s > 0));
@@ -482,7 +487,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_bg_bwd_tc(const Params Bp) {
     }
     // VB = bf + wv^T e: d bf, d wv_t
     row_sync();
-    if (tid < kBgHid) {
+    if (lead && tid < kBgHid) {
       const float d = DVB[tid];
       atomicAdd(Bp.g.bf + tid, d);
 #pragma unroll
@@ -492,7 +497,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_bg_bwd_tc(const Params Bp) {
 
   // ================================ flush: persistent accumulators and shared sums ======================================
   row_sync();
-  if (!first) {
+  if (!first && lead) {
     fence_after();
     float v[32];
     // dW1: lane = Y0 feature j, column = output unit n -> w1_t[j][n];  dW2h: lane = Y1 feature -> w2_t[20 + j][n]
@@ -526,13 +531,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_bg_bwd_tc(const Params Bp) {
     atomicAdd(Bp.g.b0 + tid, v[kOneCol]);
     atomicAdd(Bp.g.b1 + tid, DB1[tid]);
     atomicAdd(Bp.g.w_sigma + tid, DWSIG[tid]);
-    for (int i = tid; i < 3 * kBgHid; i += kThreads) atomicAdd(Bp.g.w_rgb + i, DWRGB[i]);
+    for (int i = tid; i < 3 * kBgHid; i += 128) atomicAdd(Bp.g.w_rgb + i, DWRGB[i]);
     if (tid < 3) atomicAdd(Bp.g.b_rgb + tid, SMALL[tid]);
     if (tid == 3) atomicAdd(Bp.g.b_sigma, SMALL[3]);
   }
   fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, 512);
+  if (threadIdx.x < 32) tmem_dealloc(tmem, 512);
 }
 
 }  // namespace bgbwd
