@@ -28,6 +28,10 @@ namespace app2 {
 constexpr int kGroups = 2;
 constexpr int kMlpWarps2 = 4 * kGroups;
 constexpr uint32_t kColD = 0, kColA = 128, kColBas = 208, kGroupCols = 256;
+// K-chunk stride of the GEMM0 operand image: 128 rows x 16 B.  (Padding it by 64 B removes the two-way bank conflict of the
+// gather's 8-byte stores -- 5 instead of 2.25 wavefronts per entry -- but the tensor core then reads core matrices that
+// straddle 128-byte lines: 1.85 instead of 1.48 ms per frame, profiles/r02_notes.txt N.)
+constexpr uint32_t kLboA0 = kRows * 16;
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -38,7 +42,7 @@ __device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, 1
 // 4q..4q+3 of every 16), written as 16-bit pairs into the K-major core-matrix image (row stride 16 B, K-chunk stride LBO).
 template <int CA, bool PB16, bool H16>
 __device__ __forceinline__ void gather_row(const FwdParams& P, uint8_t* arow, bool live, const float4 uw, int q) {
-  constexpr uint32_t LBO_A = kRows * 16;
+  constexpr uint32_t LBO_A = kLboA0;
   const TvmModel& m = P.m;
   if (live) {
     const float u[3] = {uw.x, uw.y, uw.z};
@@ -52,6 +56,7 @@ __device__ __forceinline__ void gather_row(const FwdParams& P, uint8_t* arow, bo
         // pair records: [texel w c..c+3 | texel w+1 c..c+3] per 16 bytes, so one load brings both taps of the pair
         const uint4* pl = reinterpret_cast<const uint4*>(m.app_plane_pair[kk]);
         const uint4* ln = reinterpret_cast<const uint4*>(m.app_line_pair[kk]);
+        // every texel unpacked to fp32 (HADD2.F32), fp32 weights: 8 + 4 + 1 instructions per channel (gather_row_mixed: 4 + 2 + 1)
 #pragma unroll
         for (int c = q * 4; c < CA; c += 16) {
           const uint4 r0 = __ldg(pl + ((t.row0 + c) >> 2));
@@ -99,6 +104,77 @@ __device__ __forceinline__ void gather_row(const FwdParams& P, uint8_t* arow, bo
   }
 }
 
+// The same tile row from the 16-bit pair records with MIXED-PRECISION FMAs and the per-entry setup shared by the four lanes.
+//  * fma.rn.f32.f16 / .bf16 (sm_100, SASS FHFMA): fp32 += 16 bit x 16 bit, each factor either half of a 32-bit register.  The
+//    gathered texels are multiplied as they were loaded, without an unpack instruction each: 4 + 2 + 1 instructions per channel
+//    instead of 8 + 4 + 1.  The instruction takes BOTH factors in 16 bits, so the six interpolation weights of a pair are put on
+//    the 2^-Q lattice (Q = 11 for fp16, 8 for bf16: every lattice point of [0, 1] is exact in the format) by telescoped
+//    rounding, which keeps their sums: the four plane weights still add up to the rounded total, the two of a texel column to
+//    the rounded column weight.  Texel x weight is then exact in fp32; what changes against fp32 weights is |dw| <= 2^-Q per tap
+//    with sum(dw) = 0 -- a shift of the sample by at most 2^-Q texel, an error proportional to the DIFFERENCE of neighbouring
+//    texels, below the rounding of the 16-bit texels themselves.
+//  * lane q < 3 of an entry prepares pair q only (axes, row offsets, lattice weights: what all four lanes used to repeat for
+//    all three pairs) and hands 5 registers to its neighbours by shuffle; the 27 loads of a lane take their channel offsets as
+//    immediates from 9 base addresses.
+// Gather loop: 755 -> ~480 SASS instructions per pass of 8 entries.
+template <int CA, bool H16>
+__device__ __forceinline__ void gather_row_mixed(const FwdParams& P, uint8_t* arow, bool live, const float4 uw, int lane) {
+  constexpr uint32_t LBO_A = kLboA0;
+  constexpr uint32_t C4 = CA / 4;                 // 16-byte groups per texel record
+  const TvmModel& m = P.m;
+  const int q = lane & 3, kp = min(q, 2);         // this lane prepares pair kp (lane 3 repeats pair 2; nobody reads its copy)
+  uint32_t row0, lrow, w_a, w_b, w_c;
+  {
+    const float u_w = kp == 2 ? uw.y : uw.x, u_h = kp == 0 ? uw.y : uw.z, u_l = kp == 0 ? uw.z : (kp == 1 ? uw.y : uw.x);
+    const int g_w = kp == 2 ? m.grid[1] : m.grid[0], g_h = kp == 0 ? m.grid[1] : m.grid[2];
+    const int g_l = kp == 0 ? m.grid[2] : (kp == 1 ? m.grid[1] : m.grid[0]);
+    const AxisPair aw = axis_pair(u_w, g_w), ah = axis_pair(u_h, g_h), al = axis_pair(u_l, g_l);
+    row0 = ((uint32_t)ah.b * (uint32_t)g_w + (uint32_t)aw.b) * C4;
+    lrow = (uint32_t)al.b * C4;
+    constexpr float kQ = H16 ? 2048.0f : 256.0f, kInvQ = 1.0f / kQ;
+    const float nw = TVM_MUL(aw.p0, ah.p0), ne = TVM_MUL(aw.p1, ah.p0), sw = TVM_MUL(aw.p0, ah.p1), se = TVM_MUL(aw.p1, ah.p1);
+    const float q_se = rintf(se * kQ), q_e = rintf((ne + se) * kQ), q_s = rintf((sw + se) * kQ);
+    const float q_all = rintf(((nw + ne) + (sw + se)) * kQ);
+    const float q_ne = q_e - q_se, q_sw = q_s - q_se, q_nw = q_all - q_e - q_sw;
+    const float q_l1 = rintf(al.p1 * kQ), q_l0 = rintf((al.p0 + al.p1) * kQ) - q_l1;
+    w_a = pack16<H16>(q_nw * kInvQ, q_ne * kInvQ);      // lattice values: exact in the 16-bit format
+    w_b = pack16<H16>(q_sw * kInvQ, q_se * kInvQ);
+    w_c = pack16<H16>(q_l0 * kInvQ, q_l1 * kInvQ);
+    if (!live) w_a = w_b = w_c = 0u;                    // rows behind the last entry: zeros (their loads hit texel 0)
+  }
+#pragma unroll
+  for (int kk = 0; kk < 3; ++kk) {
+    const int src = (lane & 28) | kk;
+    const uint32_t r0 = __shfl_sync(0xffffffffu, row0, src), lr = __shfl_sync(0xffffffffu, lrow, src);
+    const uint32_t wa = __shfl_sync(0xffffffffu, w_a, src), wb = __shfl_sync(0xffffffffu, w_b, src);
+    const uint32_t wc = __shfl_sync(0xffffffffu, w_c, src);
+    // pair records: [texel w c..c+3 | texel w+1 c..c+3] per 16 bytes; lane q owns group q of every four
+    const uint4* p0 = reinterpret_cast<const uint4*>(m.app_plane_pair[kk]) + r0 + q;
+    const uint4* p1 = p0 + (uint32_t)m.grid[mat0(kk)] * C4;
+    const uint4* pl = reinterpret_cast<const uint4*>(m.app_line_pair[kk]) + lr + q;
+    const uint16_t w_nw = half_of(wa, false), w_ne = half_of(wa, true), w_sw = half_of(wb, false), w_se = half_of(wb, true);
+    const uint16_t w_l0 = half_of(wc, false), w_l1 = half_of(wc, true);
+#pragma unroll
+    for (int i = 0; i < CA / 16; ++i) {
+      const uint4 t0 = __ldg(p0 + 4 * i), t1 = __ldg(p1 + 4 * i), tl = __ldg(pl + 4 * i);
+      // t.x = texel w, channels c, c+1; t.y = texel w, channels c+2, c+3; t.z / t.w = the same of texel w+1
+      auto plane = [&](uint32_t nw2, uint32_t ne2, uint32_t sw2, uint32_t se2, bool hi) {
+        return fhfma<H16>(half_of(nw2, hi), w_nw, fhfma<H16>(half_of(ne2, hi), w_ne,
+               fhfma<H16>(half_of(sw2, hi), w_sw, fhfma<H16>(half_of(se2, hi), w_se, 0.0f))));
+      };
+      auto line = [&](uint32_t l02, uint32_t l12, bool hi) {
+        return fhfma<H16>(half_of(l02, hi), w_l0, fhfma<H16>(half_of(l12, hi), w_l1, 0.0f));
+      };
+      const float vx = plane(t0.x, t0.z, t1.x, t1.z, false) * line(tl.x, tl.z, false);
+      const float vy = plane(t0.x, t0.z, t1.x, t1.z, true) * line(tl.x, tl.z, true);
+      const float vz = plane(t0.y, t0.w, t1.y, t1.w, false) * line(tl.y, tl.w, false);
+      const float vw = plane(t0.y, t0.w, t1.y, t1.w, true) * line(tl.y, tl.w, true);
+      const int k = kk * CA + q * 4 + 16 * i;
+      *reinterpret_cast<uint2*>(arow + (k >> 3) * LBO_A + (k & 7) * 2) = make_uint2(pack16<H16>(vx, vy), pack16<H16>(vz, vw));
+    }
+  }
+}
+
 // NGW gather warps next to the 8 MLP warps.  Registers: the launch allocates L = floor8(65536 / threads) per thread; then
 // the gather warps release and the MLP warps take registers with setmaxnreg.  The MLP warps can only take what the gather
 // warps released (the CTA pool; the SM's unallocated remainder is NOT in it -- a larger request deadlocks):
@@ -129,7 +205,7 @@ __global__ void __launch_bounds__((kMlpWarps2 + NGW) * 32, 1) k_app_tc2(const Fw
   const Image img(CA, IN_C, NH);
   uint8_t* sW = smem;                                          // weight image (16-bit operands + fp32 tail)
   uint8_t* sA0 = smem + ((img.bytes_fwd + 1023) & ~1023u);     // 2 stages of the GEMM0 operand [128 x K0]; stage s feeds group s
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sA0 + 2 * kRows * K0 * 2);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sA0 + 2 * (K0 / 8) * kLboA0);
   uint64_t* full = bars;            // [2] stage filled by the gather warps
   uint64_t* empty = bars + 2;       // [2] stage consumed by GEMM0 (tcgen05.commit)
   uint64_t* mma_bars = bars + 4;    // [2] layer GEMM of group g complete
@@ -167,9 +243,9 @@ __global__ void __launch_bounds__((kMlpWarps2 + NGW) * 32, 1) k_app_tc2(const Fw
   const uint32_t tmem = *tmem_slot;
   mbar_wait(w_bar, 0);
 
-  constexpr uint32_t LBO_A = kRows * 16, LBO_B0 = NH * 16, LBO_B = 128 * 16, LBO_B3 = 16 * 16, SBO = 128;
+  constexpr uint32_t LBO_A = kLboA0, LBO_B0 = NH * 16, LBO_B = 128 * 16, LBO_B3 = 16 * 16, SBO = 128;
   constexpr uint32_t IDESC_NH = instr_desc(128, NH, H16), IDESC_N128 = instr_desc(128, 128, H16), IDESC_N16 = instr_desc(128, 16, H16);
-  constexpr uint32_t A0_STAGE = kRows * K0 * 2;
+  constexpr uint32_t A0_STAGE = (K0 / 8) * kLboA0;
 
   const uint32_t n_ent = *P.ws.n_entries;
   const uint32_t n_tiles = (n_ent + kRows - 1) / kRows;
@@ -183,7 +259,8 @@ __global__ void __launch_bounds__((kMlpWarps2 + NGW) * 32, 1) k_app_tc2(const Fw
     // A tile is 16 passes of 8 rows (4 lanes per entry); pass number p = 16 * it + pass of the CTA's tile sequence goes to
     // gather warp p % NGW, so any warp count divides the work evenly over a few tiles.  Every pass arrives on full[stage]
     // (count 16).  Entry coordinates: written by k_march with the coordinates it marched; read once: evict-first.
-    // (Fetching them one pass ahead measured SLOWER: 2.25 vs 2.07 ms per frame, profiles/r02_notes.txt.)
+    // (Fetching them one pass ahead measured SLOWER, twice: 2.25 vs 2.07 ms per frame, and 1.74 vs 1.47 with the mixed-precision
+    //  gather; profiles/r02_notes.txt B, N.)
     constexpr uint32_t kPasses = kRows / 8;
     const uint32_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
 #pragma unroll 1
@@ -198,7 +275,13 @@ __global__ void __launch_bounds__((kMlpWarps2 + NGW) * 32, 1) k_app_tc2(const Fw
 #ifdef TVM_EXP_NOGATHER
       gather_row<CA, PB16, H16>(P, arow, false, make_float4(0.0f, 0.0f, 0.0f, 0.0f), lane & 3);
 #else
-      gather_row<CA, PB16, H16>(P, arow, e < n_ent, e < n_ent ? __ldcs(P.ws.ent_u + e) : make_float4(0.0f, 0.0f, 0.0f, 0.0f), lane & 3);
+      const float4 uw = e < n_ent ? __ldcs(P.ws.ent_u + e) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#ifdef TVM_APP2_UNPACK
+      gather_row<CA, PB16, H16>(P, arow, e < n_ent, uw, lane & 3);
+#else
+      if (PB16) gather_row_mixed<CA, H16>(P, arow, e < n_ent, uw, lane);
+      else gather_row<CA, PB16, H16>(P, arow, e < n_ent, uw, lane & 3);
+#endif
 #endif
       fence_async_smem();
       __syncwarp();
@@ -426,7 +509,7 @@ int launch_app_tc2(const FwdParams& P, int num_sms, cudaStream_t stream) {
   const bool h16 = (P.flags & TVM_MLP_MASK) == TVM_MLP_FP16;
   const bool ref = P.m.variant == TVM_VARIANT_REF;
   const Image img(P.m.n_app, P.in_mlp_c, head_ld(P.m));
-  const size_t smem = ((img.bytes_fwd + 1023) & ~1023u) + 2 * (size_t)kRows * img.K0 * 2 + 128 + 1024;
+  const size_t smem = ((img.bytes_fwd + 1023) & ~1023u) + 2 * (size_t)(img.K0 / 8) * app2::kLboA0 + 128 + 1024;
   const bool pb16 = P.m.app_plane_pair[0] && P.m.app_plane_pair[1] && P.m.app_plane_pair[2] && P.m.app_line_pair[0] &&
                     P.m.app_line_pair[1] && P.m.app_line_pair[2];
   return app2::launch<TVM_APP2_GATHER_WARPS>(P, num_sms, stream, ref, pb16, h16, smem);

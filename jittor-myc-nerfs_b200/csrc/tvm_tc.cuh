@@ -178,6 +178,22 @@ __device__ __forceinline__ float2 unpack16(uint32_t v) {
   if (H16) return __half22float2(*reinterpret_cast<const __half2*>(&v));
   return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
 }
+// Mixed-precision multiply-add of sm_100: d (fp32) = a (16 bit) * b (16 bit) + c (fp32), one instruction (SASS FHFMA), each
+// 16-bit operand either half of a 32-bit register -- a packed pair is consumed without an unpack.
+template <bool H16>
+__device__ __forceinline__ float fhfma(uint16_t a, uint16_t b, float c) {
+  float d;
+  if (H16) asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(d) : "h"(a), "h"(b), "f"(c));
+  else asm("fma.rn.f32.bf16 %0, %1, %2, %3;" : "=f"(d) : "h"(a), "h"(b), "f"(c));
+  return d;
+}
+__device__ __forceinline__ uint16_t half_of(uint32_t v, bool hi) { return hi ? (uint16_t)(v >> 16) : (uint16_t)(v & 0xffffu); }
+// a value that is exact in the 16-bit format (lattice weights), as its bit pattern
+template <bool H16>
+__device__ __forceinline__ uint16_t w16(float v) {
+  if (H16) return __half_as_ushort(__float2half_rn(v));
+  return __bfloat16_as_ushort(__float2bfloat16_rn(v));
+}
 __host__ __device__ inline uint16_t to16(float v, bool h16) {
   if (h16) {
     const __half h = __float2half_rn(v);
