@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define TVM_ABI_VERSION 25
+#define TVM_ABI_VERSION 26
 
 /* flags for tvm_forward / tvm_backward */
 #define TVM_WHITE_BG      0x1u  /* rgb_map += 1 - acc_map          (tensorBase.py:523-524) */
@@ -244,8 +244,21 @@ size_t tvm_bg_tc_bytes(void);
 int tvm_pack_bg_tc(const TvmBgNet* bg_host, void* tc_weights_out, void* stream);
 
 /* ---- the hot path --------------------------------------------------------------------------- */
-/* bytes of scratch tvm_forward needs for n rays x n_samples (worst case: every sample weighted) */
+/* bytes of scratch for n rays x n_samples in the worst case (every sample weighted): never overflows; what tvm_backward* need */
 int tvm_workspace_bytes(int n_rays, int n_samples, size_t* out_bytes);
+
+/* Bounded workspaces (evaluation renders).  The worst case above is 44 B x n_rays x n_samples -- 29 GB for an 800 x 800 frame at
+ * 1036 samples, of which a trained scene uses 1-2 %.  tvm_forward / tvm_forward_npp therefore accept ANY workspace that holds the
+ * per-ray tables and at least one entry per ray: the entry list is then bounded by what fits
+ * (tvm_workspace_capacity(n_rays, n_samples, ws_bytes); tvm_workspace_bytes_bounded is the inverse).  Samples beyond the
+ * capacity are COUNTED but not stored, nothing is written outside the workspace, and the rays' outputs are then incomplete:
+ * the caller reads tvm_forward_entries (one 4-byte copy, synchronises `stream`) after the launch and, when it returns more than
+ * the capacity, renders the rays again in smaller pieces or a larger workspace -- the count tells how large.  The reference has
+ * no counterpart (renderer.py:19-27 slices rays into fixed chunks and lets Jittor allocate per op); this is the
+ * overflow-and-relaunch contract of the host mirror (tensorf.py::_render_bounded).  tvm_backward* need the worst-case size. */
+int tvm_workspace_bytes_bounded(int n_rays, int n_samples, uint32_t max_entries, size_t* out_bytes);
+int tvm_workspace_capacity(int n_rays, int n_samples, size_t ws_bytes, uint32_t* out_entries);
+int tvm_forward_entries(const void* ws, void* stream, uint32_t* out_entries);
 
 /* Where tvm_forward leaves the per-sample results inside the caller's workspace (byte offsets from `ws`), valid until the next
  * call on that workspace.  This is how the PRODUCTION march (no TvmAux, empty-space skipping and early ray termination on)

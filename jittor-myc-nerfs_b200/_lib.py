@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # TVM_LIB: developer override (kernel-tuning experiments build variant libraries next to the default one)
 LIB_PATH = os.environ.get("TVM_LIB") or os.path.join(_HERE, "libtvmrender.so")
-ABI_VERSION = 25
+ABI_VERSION = 26
 
 # flags (tvmrender.h)
 WHITE_BG = 0x1
@@ -112,7 +112,7 @@ class TvmGrads(C.Structure):
 EXPORTS = [
     "tvm_last_error", "tvm_abi_version", "tvm_device_count", "tvm_pack_grid", "tvm_unpack_grid",
     "tvm_pack_linear", "tvm_unpack_linear", "tvm_transpose_batch", "tvm_pack_pair16", "tvm_pack_alpha", "tvm_pack_alpha_bricks", "tvm_pack_alpha_bricks3", "tvm_pack_alpha_dilated", "tvm_tc_weights_bytes", "tvm_pack_mlp_tc",
-    "tvm_workspace_bytes", "tvm_workspace_layout", "tvm_forward", "tvm_forward_npp", "tvm_bg_fold", "tvm_bg_tc_bytes", "tvm_pack_bg_tc", "tvm_backward", "tvm_backward_npp", "tvm_bg_fold_bwd",
+    "tvm_workspace_bytes", "tvm_workspace_bytes_bounded", "tvm_workspace_capacity", "tvm_forward_entries", "tvm_workspace_layout", "tvm_forward", "tvm_forward_npp", "tvm_bg_fold", "tvm_bg_tc_bytes", "tvm_pack_bg_tc", "tvm_backward", "tvm_backward_npp", "tvm_bg_fold_bwd",
     "tvm_density_alpha", "tvm_mse_loss",
     "tvm_profile_enable", "tvm_profile_collect",
     "tvm_dense_alpha", "tvm_alpha_mask_from_dense", "tvm_filter_rays", "tvm_generate_rays", "tvm_upsample_grid",
@@ -162,6 +162,9 @@ def load() -> C.CDLL:
     lib.tvm_pack_mlp_tc.argtypes = [C.POINTER(TvmModel), vp, u32, vp]
     lib.tvm_workspace_bytes.argtypes = [i32, i32, C.POINTER(C.c_size_t)]
     lib.tvm_workspace_layout.argtypes = [i32, i32, C.POINTER(TvmWorkspaceLayout)]
+    lib.tvm_workspace_bytes_bounded.argtypes = [i32, i32, u32, C.POINTER(C.c_size_t)]
+    lib.tvm_workspace_capacity.argtypes = [i32, i32, C.c_size_t, C.POINTER(u32)]
+    lib.tvm_forward_entries.argtypes = [vp, vp, C.POINTER(u32)]
     lib.tvm_forward.argtypes = [C.POINTER(TvmModel), vp, i32, i32, vp, u32, vp, vp, C.POINTER(TvmAux), vp, vp,
                                 C.c_size_t, vp]
     lib.tvm_forward_npp.argtypes = [C.POINTER(TvmModel), C.POINTER(TvmBgNet), vp, i32, i32, vp, vp, u32, vp, vp,

@@ -247,7 +247,7 @@ __global__ void __launch_bounds__((kMlpWarps2 + NGW) * 32, 1) k_app_tc2(const Fw
   constexpr uint32_t IDESC_NH = instr_desc(128, NH, H16), IDESC_N128 = instr_desc(128, 128, H16), IDESC_N16 = instr_desc(128, 16, H16);
   constexpr uint32_t A0_STAGE = (K0 / 8) * kLboA0;
 
-  const uint32_t n_ent = *P.ws.n_entries;
+  const uint32_t n_ent = min(*P.ws.n_entries, P.ws.cap);      // bounded workspace: entries behind the capacity were not stored
   const uint32_t n_tiles = (n_ent + kRows - 1) / kRows;
 
   if (warp >= kMlpWarps2) {

@@ -474,7 +474,7 @@ __global__ void __launch_bounds__(kMarchWarps * 32) k_march_bwd(const BwdParams 
 }
 
 int fill_fwd_params(FwdParams& P, const TvmModel* m, const float* rays, int n, int S, const float* jitter,
-                    uint32_t flags, void* ws, size_t ws_bytes);   // tvm_forward.cu
+                    uint32_t flags, void* ws, size_t ws_bytes, bool bounded_ok);   // tvm_forward.cu
 int launch_app_bwd_tc(const BwdParams& B, int num_sms, cudaStream_t stream);   // tvm_bwd_tc.cu
 
 }  // namespace tvm
@@ -498,7 +498,7 @@ static int backward_impl(const TvmModel* m_host, const TvmBgNet* bg_host, const 
                 "TvmGradExchange: split and total must be multiples of 4 floats");
   }
   if (bg_host) flags &= ~TVM_WHITE_BG;          // the foreground of NerfPlusPlus renders on black (nerfplusplus.py:274)
-  if (int rc = fill_fwd_params(B.f, m_host, rays, n_rays, n_samples, jitter, flags, ws, ws_bytes)) return rc;
+  if (int rc = fill_fwd_params(B.f, m_host, rays, n_rays, n_samples, jitter, flags, ws, ws_bytes, false)) return rc;
   TVM_REQUIRE(d_rgb_map && grads_host, "null argument");
   TVM_REQUIRE((m_host->sampling == TVM_SAMPLING_NPP) == (bg_host != nullptr),
               "TVM_SAMPLING_NPP models go through tvm_backward_npp, all others through tvm_backward");

@@ -1,6 +1,7 @@
 // Shared declarations of libtvmrender's translation units (workspace carve-up, launch params).
 #pragma once
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <stdint.h>
 #include <stdio.h>
 #include "tvm_math.cuh"
@@ -52,14 +53,16 @@ struct Workspace {
   uint32_t* bg_list;     // [n]       NeRF++: rays whose background is evaluated (bg_lambda > 0.1); count at n_entries[1]
   float* bg_rgb;         // [n][3]    NeRF++: composited background colour of the evaluated rays (before the bg_lambda factor)
   float* bwd_lam;        // [n]       NeRF++ backward: bg_lambda * dL/d bg_lambda of the ray
-  uint32_t cap;
+  uint32_t cap;          // entries the arrays hold: n * S, or fewer in a bounded workspace (then *n_entries > cap = overflow)
   int NB;
   size_t bytes;
 };
 
 inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
-inline Workspace carve_workspace(void* base, int n, int S) {
+// `max_entries` bounds the entry list below the worst case n * S (tvm_forward with a workspace smaller than
+// tvm_workspace_bytes): every per-entry array is cut to that capacity, the per-ray tables keep their size.
+inline Workspace carve_workspace(void* base, int n, int S, size_t max_entries = ~size_t(0)) {
   Workspace w;
   char* p = (char*)base;
   size_t off = 0;
@@ -69,7 +72,7 @@ inline Workspace carve_workspace(void* base, int n, int S) {
     return r;
   };
   w.NB = (S + 31) / 32;
-  w.cap = (uint32_t)((size_t)n * (size_t)S);
+  w.cap = (uint32_t)std::min((size_t)n * (size_t)S, max_entries);
   w.n_entries = (uint32_t*)take(256);
   w.blk_mask = (uint32_t*)take((size_t)n * w.NB * 4);
   w.blk_base = (uint32_t*)take((size_t)n * w.NB * 4);
@@ -88,6 +91,18 @@ inline Workspace carve_workspace(void* base, int n, int S) {
   w.bwd_lam = (float*)take((size_t)n * 4);
   w.bytes = off;
   return w;
+}
+
+// Largest entry capacity (<= n * S) whose carve-up fits ws_bytes; 0 when not even the per-ray tables fit.
+inline uint32_t workspace_capacity(int n, int S, size_t ws_bytes) {
+  const size_t worst = (size_t)n * (size_t)S;
+  if (carve_workspace(nullptr, n, S).bytes <= ws_bytes) return (uint32_t)worst;
+  const size_t fixed = carve_workspace(nullptr, n, S, 0).bytes;
+  if (ws_bytes <= fixed) return 0;
+  constexpr size_t kEntryBytes = 8 + 4 + 16 + 12 + 4;       // ent, ent_w, ent_u, ent_rgb, ent_pen
+  size_t cap = std::min(worst, (ws_bytes - fixed) / kEntryBytes);
+  while (cap > 0 && carve_workspace(nullptr, n, S, cap).bytes > ws_bytes) --cap;     // the 256-byte padding of the five arrays: < 30 steps
+  return (uint32_t)cap;
 }
 
 struct FwdParams {

@@ -186,8 +186,8 @@ __global__ void __launch_bounds__(kMarchWarps * 32, TVM_MARCH_MIN_CTAS) k_march(
       uint32_t base = 0;
       if (lane == 0) base = atomicAdd(P.ws.n_entries, (uint32_t)__popc(a_bits));
       base = __shfl_sync(0xffffffffu, base, 0);
-      if (app) {
-        const uint32_t e = base + __popc(a_bits & lt_mask);
+      const uint32_t e = base + __popc(a_bits & lt_mask);
+      if (app && e < P.ws.cap) {      // bounded workspace: entries behind its capacity are counted, not stored (tvm_forward_entries)
         P.ws.ent[e] = make_uint2((uint32_t)ray, (uint32_t)k);
         P.ws.ent_w[e] = w;
         float u[3];
@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(kAppThreads) k_app_simt(const FwdParams P) {
   float* X = smem + kAppTile * st;    // [64][st]: MLP input, then layer-2 output
   float* HD = smem + 2 * kAppTile * st;   // [64][8]: REFTensoRF head outputs -> {rgb_d, tint}
   const TvmModel& m = P.m;
-  const uint32_t n_ent = *P.ws.n_entries;
+  const uint32_t n_ent = min(*P.ws.n_entries, P.ws.cap);
   const uint32_t n_tiles = (n_ent + kAppTile - 1) / kAppTile;
   for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const uint32_t tile_base = tile * kAppTile;
@@ -298,8 +298,8 @@ __global__ void __launch_bounds__(256) k_composite(const FwdParams P) {
       todo &= todo - 1;
       const uint32_t bits = __shfl_sync(0xffffffffu, my_bits, src);
       const uint32_t base = __shfl_sync(0xffffffffu, my_base, src);
-      if ((bits >> lane) & 1u) {
-        const uint32_t e = base + __popc(bits & lt_mask);
+      const uint32_t e = base + __popc(bits & lt_mask);
+      if (((bits >> lane) & 1u) && e < P.ws.cap) {
         const float w = P.ws.ent_w[e];
         const float r = P.ws.ent_rgb[(size_t)e * 3 + 0];
         const float g = P.ws.ent_rgb[(size_t)e * 3 + 1];
@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(256) k_composite(const FwdParams P) {
 int launch_app_tc(const FwdParams& P, int num_sms, cudaStream_t stream);   // tvm_mlp_tc.cu
 
 int fill_fwd_params(FwdParams& P, const TvmModel* m, const float* rays, int n, int S, const float* jitter,
-                    uint32_t flags, void* ws, size_t ws_bytes) {
+                    uint32_t flags, void* ws, size_t ws_bytes, bool bounded_ok) {
   TVM_REQUIRE(m && rays && ws, "null argument");
   TVM_REQUIRE(n > 0 && S > 0, "n_rays and n_samples must be positive");
   if (int rc = validate_model(*m)) return rc;
@@ -348,7 +348,18 @@ int fill_fwd_params(FwdParams& P, const TvmModel* m, const float* rays, int n, i
   P.n = n;
   P.S = S;
   P.flags = flags;
-  P.ws = carve_workspace(ws, n, S);
+  TVM_REQUIRE((double)n * S < 4.0e9, "n_rays*n_samples must fit 32 bits; split the rays");
+  {
+    // tvm_forward accepts a workspace below the worst case: the entry list is then bounded by what fits (at least one
+    // entry per ray on average) and the caller checks tvm_forward_entries; everything that reads a stash
+    // (tvm_backward*) needs the worst-case size
+    const uint32_t cap = workspace_capacity(n, S, ws_bytes);
+    const size_t worst = (size_t)n * (size_t)S;
+    TVM_REQUIRE(cap == worst || (bounded_ok && cap >= std::min(worst, (size_t)n)),
+                "workspace too small: need %zu bytes%s, got %zu", carve_workspace(nullptr, n, S).bytes,
+                bounded_ok ? " (or at least room for one entry per ray)" : "", ws_bytes);
+    P.ws = carve_workspace(ws, n, S, cap);
+  }
   TVM_REQUIRE(P.ws.bytes <= ws_bytes, "workspace too small: need %zu bytes, got %zu", P.ws.bytes, ws_bytes);
   TVM_REQUIRE(((uintptr_t)ws & 255) == 0, "workspace must be 256-byte aligned");
   P.NB = P.ws.NB;
@@ -404,6 +415,28 @@ extern "C" int tvm_workspace_layout(int n_rays, int n_samples, TvmWorkspaceLayou
   return 0;
 }
 
+extern "C" int tvm_workspace_bytes_bounded(int n_rays, int n_samples, uint32_t max_entries, size_t* out_bytes) {
+  TVM_REQUIRE(out_bytes && n_rays > 0 && n_samples > 0, "bad arguments");
+  TVM_REQUIRE((double)n_rays * n_samples < 4.0e9, "n_rays*n_samples must fit 32 bits; split the rays");
+  const size_t floor_entries = std::min((size_t)n_rays * (size_t)n_samples, (size_t)n_rays);
+  *out_bytes = carve_workspace(nullptr, n_rays, n_samples, std::max((size_t)max_entries, floor_entries)).bytes;
+  return 0;
+}
+
+extern "C" int tvm_workspace_capacity(int n_rays, int n_samples, size_t ws_bytes, uint32_t* out_entries) {
+  TVM_REQUIRE(out_entries && n_rays > 0 && n_samples > 0, "bad arguments");
+  TVM_REQUIRE((double)n_rays * n_samples < 4.0e9, "n_rays*n_samples must fit 32 bits; split the rays");
+  *out_entries = workspace_capacity(n_rays, n_samples, ws_bytes);
+  return 0;
+}
+
+extern "C" int tvm_forward_entries(const void* ws, void* stream, uint32_t* out_entries) {
+  TVM_REQUIRE(ws && out_entries, "null argument");
+  TVM_CHECK_CUDA(cudaMemcpyAsync(out_entries, ws, sizeof(uint32_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  TVM_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return 0;
+}
+
 namespace tvm {
 int launch_bg(const FwdParams& P, int num_sms, cudaStream_t stream);   // tvm_bg.cu
 }
@@ -414,7 +447,7 @@ static int forward_impl(const TvmModel* m_host, const TvmBgNet* bg_host, const f
                         const TvmAux* aux_host, uint64_t* counters, void* ws, size_t ws_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   FwdParams P;
-  if (int rc = fill_fwd_params(P, m_host, rays, n_rays, n_samples, jitter, flags, ws, ws_bytes)) return rc;
+  if (int rc = fill_fwd_params(P, m_host, rays, n_rays, n_samples, jitter, flags, ws, ws_bytes, true)) return rc;
   TVM_REQUIRE(rgb_map && depth_map, "null output");
   TVM_REQUIRE((m_host->sampling == TVM_SAMPLING_NPP) == (bg_host != nullptr),
               "TVM_SAMPLING_NPP models go through tvm_forward_npp, all others through tvm_forward");

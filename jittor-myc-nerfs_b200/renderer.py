@@ -11,47 +11,54 @@ import torch
 
 
 def _render_streamed(rays, tensorf, N_samples, white_bg, out_host):
-    """Host-resident rays (pinned) -> host-resident rgb/depth (pinned), pipelined per workspace chunk: the upload of
-    chunk i+1 and the download of chunk i-1 run on a copy stream while chunk i renders."""
+    """Host-resident rays (pinned) -> host-resident rgb/depth (pinned), pipelined per chunk: the uploads run ahead on a copy
+    stream, chunk i renders (TensorVMSplit._render_bounded: two compute streams, bounded workspaces, overflow check), the
+    download of chunk i follows it on the copy stream.  A large frame is cut into at least `stream_stages` (8) pieces so that
+    the copies hide.  With `tensorf.defer_overflow_check` the call returns without reading the overflow status
+    (verify_renders() before the host tensors are read): a range that has to be rendered again is uploaded again from `rays`."""
     dev = tensorf.device
     S = int(N_samples) if N_samples > 0 else tensorf.nSamples
     n = rays.shape[0]
-    nmax = min(tensorf.max_rays_per_launch(S), max(65536, -(-n // 4)))     # at least 4 stages when the frame is large
     st = getattr(tensorf, "_stream_state", None)
     if st is None or st["n"] != n:
         st = dict(n=n, copy=torch.cuda.Stream(device=dev), rays=torch.empty((n, 6), dtype=torch.float32, device=dev),
                   rgb=torch.empty((n, 3), dtype=torch.float32, device=dev), depth=torch.empty((n,), dtype=torch.float32, device=dev))
         tensorf._stream_state = st
+    live = [True]          # False once this call has returned: `launch` is then a deferred repair
     cs, main = st["copy"], torch.cuda.current_stream()
     rgb_host, depth_host = out_host
-    bounds = [(s, min(n, s + nmax)) for s in range(0, n, nmax)]
+    stage = max(65536, -(-n // int(getattr(tensorf, "stream_stages", 8))))
     cs.wait_stream(main)
-    ups = []
+    ups = {}
     with torch.cuda.stream(cs):
-        for s, e in bounds:
+        for s in range(0, n, stage):
+            e = min(n, s + stage)
             st["rays"][s:e].copy_(rays[s:e], non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(cs)
-            ups.append(ev)
+            ups[s] = torch.cuda.Event()
+            ups[s].record(cs)
     flags = tensorf._flags(white_bg)
-    # the chunks alternate between the caller's stream and a side stream (own workspace each, TensorVMSplit._forward_chunks):
-    # tails and launch gaps of one chunk overlap with the next chunk's march
-    if getattr(tensorf, "_side_stream", None) is None:
-        tensorf._side_stream = torch.cuda.Stream(device=dev)
-    side = tensorf._side_stream
-    side.wait_stream(main)
-    for i, ((s, e), ev) in enumerate(zip(bounds, ups)):
-        stream = side if (i & 1) else main
-        with torch.cuda.stream(stream):
-            stream.wait_event(ev)
-            tensorf._forward_raw(st["rays"][s:e], None, flags, S, out=(st["rgb"][s:e], st["depth"][s:e]), ws_slot=i & 1)
-            done = torch.cuda.Event()
-            done.record(stream)
+
+    def launch(s, e, slot, nbytes):
+        if not live[0]:
+            # a deferred repair (verify_renders, device synchronised): later frames and other repairs have gone through the
+            # staging buffers since -- bring the range back first
+            st["rays"][s:e].copy_(rays[s:e], non_blocking=True)
+        else:
+            # a launch may span upload stages: wait for every stage it touches
+            for s0, ev in ups.items():
+                if s0 < e and s0 + stage > s:
+                    torch.cuda.current_stream().wait_event(ev)
+        tensorf._forward_raw(st["rays"][s:e], None, flags, S, out=(st["rgb"][s:e], st["depth"][s:e]), ws_slot=slot, ws_bytes=nbytes)
+        return tensorf._ws if slot == 0 else tensorf._ws2
+
+    def copy_out(s, e, done):
         with torch.cuda.stream(cs):
             cs.wait_event(done)
             rgb_host[s:e].copy_(st["rgb"][s:e], non_blocking=True)
             depth_host[s:e].copy_(st["depth"][s:e], non_blocking=True)
-    main.wait_stream(side)
+
+    tensorf._render_bounded(n, S, launch, copy_out=copy_out, max_rays=stage)
+    live[0] = False
     main.wait_stream(cs)
     return rgb_host, depth_host
 

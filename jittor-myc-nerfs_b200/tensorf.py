@@ -11,6 +11,7 @@ from __future__ import annotations
 import ctypes as C
 import math
 import os
+import weakref
 
 import numpy as np
 import torch
@@ -204,10 +205,15 @@ class TensorVMSplit(MaintainMixin, RegularizerMixin, CheckpointMixin, torch.nn.M
         self.empty_space_skipping = True
         self.collect_counters = False
         self.counters = torch.zeros(L.CNT_WORDS, dtype=torch.int64, device=device)
-        self.ws_budget_bytes = int(float(os.environ.get("TVM_WS_GIB", "8")) * (1 << 30))    # both workspaces of the evaluation pipeline (an 800x800 frame: 8 chunks)
+        self.ws_budget_bytes = int(float(os.environ.get("TVM_WS_GIB", "2")) * (1 << 30))    # both workspaces of the evaluation pipeline; bounded entry lists (an 800x800 frame of a trained scene: one launch)
         self.grad_sync = False          # set True (after dist.init_from_env) for data-parallel training
         self.grad_sync_group = None
         self._peer_comm = None          # enable_peer_allreduce(): libtvmrender's own all-reduce over NVLink peer memory
+        self.defer_overflow_check = False      # True: bounded evaluation renders are verified by verify_renders(), not at once
+        self._pending_checks = []
+        self.stream_stages = 8          # pipeline stages of a host-to-host frame (renderer._render_streamed)
+        self.ws_overflows = 0           # ranges rendered a second time because their entry list overflowed
+        self._epr_hint = None           # entries per ray (+30 %) the next bounded render sizes its entry lists from
         self._ws = None
         self._fwd_gen = 0               # bumped by every tvm_forward* on the shared workspace (see _forward_stamp)
         self._packed = None
@@ -477,15 +483,16 @@ class TensorVMSplit(MaintainMixin, RegularizerMixin, CheckpointMixin, torch.nn.M
         return out.value
 
     def max_rays_per_launch(self, S):
-        """Rays per tvm_forward launch: the workspace is sized for the worst case (every sample weighted, 44 B x n x S); the
-        budget covers the TWO workspaces of the evaluation pipeline."""
+        """Rays per launch that keep the WORST-CASE workspace (every sample weighted, 44 B x n x S) inside one of the two
+        workspaces of the budget: the bound for launches whose stash is read again (training steps)."""
         per_ray = self.workspace_bytes(1024, S) / 1024.0
         return max(1024, int(self.ws_budget_bytes / 2 / per_ray) // 1024 * 1024)
 
-    def _workspace(self, n, S, slot=0):
+    def _workspace(self, n, S, slot=0, nbytes=None):
         """Caller-owned scratch of tvm_forward.  Slot 0 is THE workspace (what tvm_backward and workspace_view read); slot 1
-        is the second buffer of the two-stream evaluation pipeline (_forward_chunks)."""
-        need = self.workspace_bytes(n, S)
+        is the second buffer of the two-stream evaluation pipeline.  `nbytes`: a bounded workspace of that size instead of
+        the worst case for (n, S)."""
+        need = self.workspace_bytes(n, S) if nbytes is None else int(nbytes)
         if slot == 0:
             if self._ws is None or self._ws.numel() < need:
                 self._ws = None
@@ -496,26 +503,126 @@ class TensorVMSplit(MaintainMixin, RegularizerMixin, CheckpointMixin, torch.nn.M
             self._ws2 = torch.empty(need, dtype=torch.uint8, device=self.device)
         return self._ws2
 
-    def _forward_chunks(self, rays, jitter, flags, S, rgb, depth, nmax):
-        """Evaluation render of more rays than one workspace holds: the chunks alternate between the caller's stream and a
-        side stream, each with its own workspace, so that the tail of one chunk's kernels (and the launch gaps between its
-        five dependent launches) overlap with the next chunk's march.  Rays are independent and compositing is per ray, so the
-        pixels do not depend on the chunking (tests/test_gpu_forward.py::test_full_frame_properties)."""
+    # ---- evaluation renders through bounded workspaces (tvmrender.h: "Bounded workspaces") ------------
+    def _plan_launch(self, n, S):
+        """(rays per launch, workspace bytes or None) of an evaluation render.  None: the worst case fits, nothing to check.
+        Otherwise the entry list is sized from what the last renders needed per ray (`_epr_hint`, + 30 %; S / 8 before the
+        first one) and the launch is followed by an overflow check."""
+        half = self.ws_budget_bytes // 2
+        if self.workspace_bytes(n, S) <= half:
+            return n, None
+        lib, out = L.load(), C.c_size_t(0)
+        L.check(lib.tvm_workspace_bytes_bounded(1024, int(S), 0, C.byref(out)), "tvm_workspace_bytes_bounded")
+        per_ray = out.value / 1024.0 + 44.0 * (self._epr_hint or S / 8.0)   # per-ray tables + entries
+        nr = max(1024, int(half / per_ray) // 1024 * 1024)
+        if nr < n:                                               # equal pieces rather than full ones and a remainder
+            pieces = -(-n // nr)
+            nr = min(nr, -(-(-(-n // pieces)) // 1024) * 1024)
+        nr = min(n, nr)
+        if self.workspace_bytes(nr, S) <= half:
+            return nr, None
+        return nr, half
+
+    def _render_bounded(self, n, S, launch, copy_out=None, max_rays=None, ranges=None):
+        """Run `launch(s, e, slot, nbytes)` (one tvm_forward* over rays [s, e) on the current stream with workspace `slot`)
+        over [0, n): chunks alternate between the caller's stream and a side stream with one workspace each, so that the
+        tail of one chunk's kernels overlaps the next chunk's march.  With bounded workspaces each launch leaves the number
+        of entries it WANTED in a status word; one synchronisation at the end compares them with the capacities and renders
+        the (rare) overflowed ranges again with the hint corrected.  Rays are independent and compositing is per ray, so the
+        pixels do not depend on the chunking (tests/test_gpu_forward.py::test_full_frame_properties).
+        `copy_out(s, e, done_event)`: per-chunk hook of the streamed renderer (device -> host copies; a range that overflowed
+        is copied again after its second render); `max_rays`: upper bound of a chunk (its pipeline stages)."""
         main = torch.cuda.current_stream()
         if getattr(self, "_side_stream", None) is None:
-            self._side_stream = torch.cuda.Stream(device=rays.device)
+            self._side_stream = torch.cuda.Stream(device=self.device)
         side = self._side_stream
-        side.wait_stream(main)
-        n = rays.shape[0]
-        for i, s in enumerate(range(0, n, nmax)):
-            e = min(n, s + nmax)
-            args = (rays[s:e], None if jitter is None else jitter[s:e], flags, S)
-            if i & 1:
-                with torch.cuda.stream(side):
-                    self._forward_raw(*args, out=(rgb[s:e], depth[s:e]), ws_slot=1)
-            else:
-                self._forward_raw(*args, out=(rgb[s:e], depth[s:e]))
-        main.wait_stream(side)
+        todo = [(0, n)] if ranges is None else list(ranges)
+        while todo:
+            jobs = []
+            for (s0, e0) in todo:
+                nr, nbytes = self._plan_launch(e0 - s0, S)
+                if max_rays is not None and nr > max_rays:      # the streamed renderer's pipeline stages
+                    nr = max_rays
+                    if self.workspace_bytes(nr, S) <= self.ws_budget_bytes // 2:
+                        nbytes = None
+                jobs += [(s, min(e0, s + nr), nbytes) for s in range(s0, e0, nr)]
+            bounded = [j for j in jobs if j[2] is not None]
+            status = torch.zeros(max(1, len(bounded)), dtype=torch.int32, device=self.device) if bounded else None
+            if len(jobs) > 1:
+                side.wait_stream(main)
+            k = 0
+            for i, (s, e, nbytes) in enumerate(jobs):
+                stream = side if (i & 1) else main
+                with torch.cuda.stream(stream):
+                    ws = launch(s, e, i & 1, nbytes)
+                    if ws is None:              # the outputs of a deferred render are gone: nothing to repair
+                        continue
+                    if nbytes is not None:
+                        status[k:k + 1].copy_(ws[:4].view(torch.int32), non_blocking=True)
+                        k += 1
+                    if copy_out is not None:
+                        ev = torch.cuda.Event()
+                        ev.record(stream)
+                        copy_out(s, e, ev)
+            if len(jobs) > 1:
+                main.wait_stream(side)
+            todo = []
+            if bounded and self.defer_overflow_check:
+                # the caller verifies later (verify_renders): hand the status words and the way to render a range again over
+                self._pending_checks.append((status, bounded, S, launch, copy_out, max_rays))
+            elif bounded:
+                todo = self._overflowed(status, bounded, S)
+
+    def _overflowed(self, status, bounded, S):
+        """Ranges of `bounded` launches whose entry lists overflowed (reads the status words: synchronises); updates the hint."""
+        lib = L.load()
+        wanted = status.cpu().numpy().astype("int64") & 0xFFFFFFFF
+        todo, epr = [], 0.0
+        for (s, e, nbytes), w in zip(bounded, wanted):
+            cap = C.c_uint32(0)
+            L.check(lib.tvm_workspace_capacity(e - s, int(S), nbytes, C.byref(cap)), "tvm_workspace_capacity")
+            epr = max(epr, float(w) / (e - s))
+            if int(w) > cap.value:
+                todo.append((s, e))
+        # entries per ray of the densest chunk, + 30 %: what the next render sizes its entry lists from
+        self._epr_hint = 1.3 * epr + 1.0
+        self.ws_overflows += len(todo)
+        return todo
+
+    def verify_renders(self):
+        """With `defer_overflow_check = True` evaluation renders return without reading their overflow status (the host can
+        enqueue the next frame while this one runs: back-to-back frames keep the GPU busy); call this before consuming the
+        pixels of those renders.  It synchronises, renders every overflowed range again into the SAME output tensors, and
+        returns the number of ranges it had to repair."""
+        repaired = 0
+        pending, self._pending_checks = self._pending_checks, []
+        if pending:
+            torch.cuda.synchronize(self.device)       # every stream of the deferred renders (compute, side, copy)
+        for status, bounded, S, launch, copy_out, max_rays in pending:
+            todo = self._overflowed(status, bounded, S)
+            repaired += len(todo)
+            if todo:
+                defer, self.defer_overflow_check = self.defer_overflow_check, False
+                try:
+                    self._render_bounded(0, S, launch, copy_out=copy_out, max_rays=max_rays, ranges=todo)
+                    torch.cuda.synchronize(self.device)
+                finally:
+                    self.defer_overflow_check = defer
+        return repaired
+
+    def _forward_chunks(self, rays, jitter, flags, S, rgb, depth):
+        # a deferred check keeps `launch` alive until verify_renders(): it must not keep the outputs alive with it (a caller
+        # that has dropped them needs no repair, and held blocks would make the allocator grow frame after frame)
+        out_ref = (weakref.ref(rgb), weakref.ref(depth))
+
+        def launch(s, e, slot, nbytes):
+            o_rgb, o_depth = out_ref[0](), out_ref[1]()
+            if o_rgb is None or o_depth is None:
+                return None
+            self._forward_raw(rays[s:e], None if jitter is None else jitter[s:e], flags, S, out=(o_rgb[s:e], o_depth[s:e]),
+                              ws_slot=slot, ws_bytes=nbytes)
+            return self._ws if slot == 0 else self._ws2
+        self._render_bounded(rays.shape[0], S, launch)
 
     def workspace_view(self, n, S):
         """What the last tvm_forward over (n rays, S samples) left in the workspace (tvmrender.h: TvmWorkspaceLayout):
@@ -576,12 +683,12 @@ class TensorVMSplit(MaintainMixin, RegularizerMixin, CheckpointMixin, torch.nn.M
             f |= L.NO_ERT
         return f
 
-    def _forward_raw(self, rays, jitter, flags, S, aux=None, out=None, ws_slot=0):
+    def _forward_raw(self, rays, jitter, flags, S, aux=None, out=None, ws_slot=0, ws_bytes=None):
         lib = L.load()
         n = rays.shape[0]
         assert rays.is_cuda and rays.dtype == torch.float32 and rays.is_contiguous() and rays.shape[1] == 6
         model = self._model()
-        ws = self._workspace(n, S, ws_slot)
+        ws = self._workspace(n, S, ws_slot, ws_bytes)
         self._fwd_gen += 1
         if out is None:
             rgb = torch.empty((n, 3), dtype=torch.float32, device=rays.device)
@@ -591,7 +698,7 @@ class TensorVMSplit(MaintainMixin, RegularizerMixin, CheckpointMixin, torch.nn.M
         L.check(lib.tvm_forward(C.byref(model), _ptr(rays), n, int(S), _ptr(jitter), flags, _ptr(rgb), _ptr(depth),
                                 C.byref(aux) if aux is not None else None,
                                 _ptr(self.counters) if self.collect_counters else None,
-                                _ptr(ws), ws.numel(), _stream_ptr()), "tvm_forward")
+                                _ptr(ws), ws.numel() if ws_bytes is None else int(ws_bytes), _stream_ptr()), "tvm_forward")
         return rgb, depth
 
     def enable_peer_allreduce(self, group=None, n_ctas=64):
@@ -755,11 +862,11 @@ class TensorVMSplit(MaintainMixin, RegularizerMixin, CheckpointMixin, torch.nn.M
             if self.VARIANT == L.VARIANT_REF:
                 self.penalty = penalty          # train.py:253-257 reads tensorf.penalty and adds it to the loss
             return rgb, depth
-        if n <= nmax:
+        if self._plan_launch(n, S) == (n, None):
             return self._forward_raw(rays, jitter, flags, S)
         rgb = torch.empty((n, 3), dtype=torch.float32, device=rays.device)
         depth = torch.empty((n,), dtype=torch.float32, device=rays.device)
-        self._forward_chunks(rays, jitter, flags, S, rgb, depth, nmax)
+        self._forward_chunks(rays, jitter, flags, S, rgb, depth)
         return rgb, depth
 
     execute = forward
@@ -868,14 +975,14 @@ class REFTensoRF(TensorVMSplit):
             o += k
         return out
 
-    def _forward_raw(self, rays, jitter, flags, S, aux=None, out=None, ws_slot=0):
+    def _forward_raw(self, rays, jitter, flags, S, aux=None, out=None, ws_slot=0, ws_bytes=None):
         if aux is None:
             aux = L.TvmAux()
             if ws_slot == 0:        # chunked renders: the first chunk of a pair zeroes, both accumulate (atomics)
                 self._penalty_buf.zero_()
             aux.penalty = self._penalty_buf.data_ptr()
             self.penalty = self._penalty_buf
-        return super()._forward_raw(rays, jitter, flags, S, aux=aux, out=out, ws_slot=ws_slot)
+        return super()._forward_raw(rays, jitter, flags, S, aux=aux, out=out, ws_slot=ws_slot, ws_bytes=ws_bytes)
 
 
 class _Seq(torch.nn.ModuleList):
@@ -955,11 +1062,11 @@ class NerfPlusPlus(TensorVMSplit):
                 n.rgb_layers[0], n.rgb_layers[2]]
         return [t for lin in lins for t in (lin.weight, lin.bias)]
 
-    def _forward_npp_raw(self, rays, fg_rand, bg_rand, flags, S, out=None, aux=None):
+    def _forward_npp_raw(self, rays, fg_rand, bg_rand, flags, S, out=None, aux=None, ws_slot=0, ws_bytes=None):
         lib = L.load()
         n = rays.shape[0]
         model, bg = self._model(), self._bg_struct()
-        ws = self._workspace(n, S)
+        ws = self._workspace(n, S, ws_slot, ws_bytes)
         self._fwd_gen += 1
         if out is None:
             out = (torch.empty((n, 3), dtype=torch.float32, device=rays.device),
@@ -967,8 +1074,8 @@ class NerfPlusPlus(TensorVMSplit):
         rgb, depth = out
         L.check(lib.tvm_forward_npp(C.byref(model), C.byref(bg), _ptr(rays), n, S, _ptr(fg_rand), _ptr(bg_rand), flags,
                                     _ptr(rgb), _ptr(depth), C.byref(aux) if aux is not None else None,
-                                    _ptr(self.counters) if self.collect_counters else None, _ptr(ws), ws.numel(),
-                                    _stream_ptr()), "tvm_forward_npp")
+                                    _ptr(self.counters) if self.collect_counters else None, _ptr(ws),
+                                    ws.numel() if ws_bytes is None else int(ws_bytes), _stream_ptr()), "tvm_forward_npp")
         return rgb, depth
 
     def _backward_npp_raw(self, rays, fg_rand, bg_rand, flags, S, rgb, d_rgb):
@@ -1078,9 +1185,21 @@ class NerfPlusPlus(TensorVMSplit):
             return _RenderNppFn.apply(self, rays, fg_rand, bg_rand, flags, S, *params)
         rgb = torch.empty((n, 3), dtype=torch.float32, device=dev)
         depth = torch.empty((n,), dtype=torch.float32, device=dev)
-        for s in range(0, n, nmax):
-            e = min(n, s + nmax)
-            self._forward_npp_raw(rays[s:e], fg_rand[s:e], bg_rand[s:e], flags, S, out=(rgb[s:e], depth[s:e]), aux=aux)
+        if aux is not None:           # parity instrumentation: per-sample outputs of ONE launch
+            assert self._plan_launch(n, S) == (n, None)
+            self._forward_npp_raw(rays, fg_rand, bg_rand, flags, S, out=(rgb, depth), aux=aux)
+            return rgb, depth
+
+        out_ref = (weakref.ref(rgb), weakref.ref(depth))        # see TensorVMSplit._forward_chunks
+
+        def launch(s, e, slot, nbytes):
+            o_rgb, o_depth = out_ref[0](), out_ref[1]()
+            if o_rgb is None or o_depth is None:
+                return None
+            self._forward_npp_raw(rays[s:e], fg_rand[s:e], bg_rand[s:e], flags, S, out=(o_rgb[s:e], o_depth[s:e]),
+                                  ws_slot=slot, ws_bytes=nbytes)
+            return self._ws if slot == 0 else self._ws2
+        self._render_bounded(n, S, launch)
         return rgb, depth
 
     execute = forward

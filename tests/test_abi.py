@@ -69,3 +69,16 @@ def test_workspace_bytes(built_lib):
     offs = [lay.n_entries, lay.blk_mask, lay.blk_base, lay.ent, lay.ent_w, lay.ent_rgb, lay.acc, lay.rgb_sum]
     assert all(o % 256 == 0 and o < lay.bytes for o in offs) and sorted(offs[:5]) == offs[:5]
     assert lay.blk_base - lay.blk_mask >= 4096 * 14 * 4 and lay.ent_w - lay.ent >= lay.capacity * 8
+    # bounded workspaces: bytes(entries) and capacity(bytes) are inverse up to the 256-byte padding; the worst case is the cap
+    cap = ctypes.c_uint32(0)
+    assert lib.tvm_workspace_capacity(4096, 440, out.value, ctypes.byref(cap)) == 0 and cap.value == 4096 * 440
+    assert lib.tvm_workspace_capacity(4096, 440, out.value * 2, ctypes.byref(cap)) == 0 and cap.value == 4096 * 440
+    for entries in (4096, 100000, 4096 * 440 - 1):
+        b = ctypes.c_size_t(0)
+        assert lib.tvm_workspace_bytes_bounded(4096, 440, entries, ctypes.byref(b)) == 0 and b.value <= out.value
+        assert lib.tvm_workspace_capacity(4096, 440, b.value, ctypes.byref(cap)) == 0
+        assert entries <= cap.value <= entries + 64
+        assert lib.tvm_workspace_capacity(4096, 440, b.value - 256 * 6, ctypes.byref(cap)) == 0 and cap.value < entries
+    assert lib.tvm_workspace_bytes_bounded(4096, 440, 0, ctypes.byref(b)) == 0        # floor: one entry per ray
+    assert lib.tvm_workspace_capacity(4096, 440, b.value, ctypes.byref(cap)) == 0 and 4096 <= cap.value <= 4096 + 64
+    assert lib.tvm_workspace_capacity(4096, 440, 1024, ctypes.byref(cap)) == 0 and cap.value == 0

@@ -379,6 +379,106 @@ def test_streamed_host_render_matches_resident(env):
     assert float(rgb_host.min()) < 0.99      # the frame is not empty
 
 
+def test_bounded_workspace_overflow_and_relaunch(env):
+    """tvmrender.h "Bounded workspaces": a workspace below the worst case bounds the entry list; samples beyond its capacity
+    are counted (tvm_forward_entries) but not stored, nothing is written outside the workspace, and the host mirror renders
+    the overflowed ranges again -- the pixels equal those of the worst-case workspace bit for bit."""
+    import ctypes as C
+    pkg, torch, fx, orc = env
+    from util import gpu_model
+    L = pkg._lib
+    lib = L.load()
+    case = fx.make_case(64, 0, "R2", mask_res=64, full_frame=True)
+    rays = torch.from_numpy(case["rays"][100000:160000]).cuda()
+    n = rays.shape[0]
+    model = gpu_model(pkg, case, mlp_mode="bf16")
+    S = model.nSamples
+    model.ws_budget_bytes = 4 * model.workspace_bytes(n, S)
+    with torch.no_grad():
+        rgb0, dep0 = model(rays, white_bg=True, is_train=False)
+    wanted = model.workspace_view(n, S)["n_entries"]
+    assert wanted > 4 * n                                   # the fog regime: many weighted samples per ray
+
+    # (a) the C ABI: capacity / bytes are inverse to each other; a launch into half the needed capacity reports the full count,
+    #     writes nothing outside, and a launch into exactly the needed capacity reproduces the pixels
+    def bounded_bytes(entries):
+        out = C.c_size_t(0)
+        L.check(lib.tvm_workspace_bytes_bounded(n, S, entries, C.byref(out)), "tvm_workspace_bytes_bounded")
+        cap = C.c_uint32(0)
+        L.check(lib.tvm_workspace_capacity(n, S, out.value, C.byref(cap)), "tvm_workspace_capacity")
+        assert entries <= cap.value <= entries + 64
+        return out.value
+    for entries, fits in ((wanted // 2, False), (wanted, True)):
+        nbytes = bounded_bytes(entries)
+        assert nbytes < model.workspace_bytes(n, S) // 4
+        ws = torch.full((nbytes + 65536,), 0xA5, dtype=torch.uint8, device="cuda")
+        model._ws = ws
+        rgb1, dep1 = model._forward_raw(rays, None, model._flags(True), S, ws_bytes=nbytes)
+        got = C.c_uint32(0)
+        L.check(lib.tvm_forward_entries(ws.data_ptr(), torch.cuda.current_stream().cuda_stream, C.byref(got)), "tvm_forward_entries")
+        assert got.value == wanted
+        assert bool((ws[nbytes:] == 0xA5).all())
+        assert bool(torch.isfinite(rgb1).all())
+        assert torch.equal(rgb1, rgb0) == fits and (not fits or torch.equal(dep1, dep0))
+    model._ws = None
+    # a workspace that cannot hold one entry per ray is refused, and so is a bounded workspace in the backward pass
+    tiny = torch.empty(1 << 16, dtype=torch.uint8, device="cuda")
+    model._ws = tiny
+    with pytest.raises(L.TvmError, match="workspace too small"):
+        model._forward_raw(rays, None, model._flags(True), S, ws_bytes=tiny.numel())
+    model._ws = None
+
+    # (b) the host mirror: a budget far below what the frame needs and a hint that is far too low -> overflows, re-renders,
+    #     identical pixels; the next render starts from the corrected hint and does not overflow
+    model.ws_budget_bytes = 2 * bounded_bytes(wanted // 3)
+    model._epr_hint = 1.0
+    model.ws_overflows = 0
+    with torch.no_grad():
+        rgb2, dep2 = model(rays, white_bg=True, is_train=False)
+    assert model.ws_overflows >= 1
+    assert torch.equal(rgb2, rgb0) and torch.equal(dep2, dep0)
+    seen = model.ws_overflows
+    with torch.no_grad():
+        rgb3, dep3 = model(rays, white_bg=True, is_train=False)
+    assert model.ws_overflows == seen and torch.equal(rgb3, rgb0)
+    # deferred check (frame sequences): the render returns unverified, verify_renders() repairs the SAME tensors; outputs the
+    # caller has dropped are not rendered again
+    model.defer_overflow_check = True
+    model._epr_hint = 1.0
+    with torch.no_grad():
+        rgb4, dep4 = model(rays, white_bg=True, is_train=False)
+        model(rays, white_bg=True, is_train=False)            # result dropped
+    torch.cuda.synchronize()
+    assert not torch.equal(rgb4, rgb0)
+    assert model.verify_renders() >= 2 and model.verify_renders() == 0
+    assert torch.equal(rgb4, rgb0) and torch.equal(dep4, dep0)
+    model.defer_overflow_check = False
+    seen = model.ws_overflows
+    # ... and through the streamed host renderer
+    rays_host = rays.cpu().pin_memory()
+    rgb_host, depth_host = torch.empty((n, 3)).pin_memory(), torch.empty((n,)).pin_memory()
+    model._epr_hint = 1.0
+    pkg.OctreeRender_trilinear_fast(rays_host, model, white_bg=True, is_train=False, out_host=(rgb_host, depth_host))
+    torch.cuda.synchronize()
+    assert model.ws_overflows > seen
+    assert torch.equal(rgb_host, rgb0.cpu()) and torch.equal(depth_host, dep0.cpu())
+    # streamed + deferred: two frames through the same staging buffers, the first one repaired afterwards (re-uploaded)
+    rgb_h2, depth_h2 = torch.empty((n, 3)).pin_memory(), torch.empty((n,)).pin_memory()
+    rays_b = rays_host.clone().pin_memory()
+    rays_b[:, 0] += 0.01
+    model.defer_overflow_check = True
+    model._epr_hint = 1.0
+    rgb_host.zero_()
+    pkg.OctreeRender_trilinear_fast(rays_host, model, white_bg=True, is_train=False, out_host=(rgb_host, depth_host))
+    pkg.OctreeRender_trilinear_fast(rays_b, model, white_bg=True, is_train=False, out_host=(rgb_h2, depth_h2))
+    assert model.verify_renders() >= 2
+    model.defer_overflow_check = False
+    assert torch.equal(rgb_host, rgb0.cpu()) and torch.equal(depth_host, dep0.cpu())
+    with torch.no_grad():
+        rgb_b, dep_b = model(rays_b.cuda(), white_bg=True, is_train=False)
+    assert torch.equal(rgb_h2, rgb_b.cpu()) and torch.equal(depth_h2, dep_b.cpu()) and not torch.equal(rgb_h2, rgb_host)
+
+
 def test_full_frame_properties(env):
     """BASELINE configs[1] at full size (800x800 rays, 300^3 grid, 200^3 mask, S = 1036) through size-independent
     properties: chunking invariance, early-termination error bound, ray-order invariance, background rays, work counters
