@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define TVM_ABI_VERSION 26
+#define TVM_ABI_VERSION 27
 
 /* flags for tvm_forward / tvm_backward */
 #define TVM_WHITE_BG      0x1u  /* rgb_map += 1 - acc_map          (tensorBase.py:523-524) */
@@ -127,9 +127,9 @@ typedef struct TvmModel {
   /* optional second operand image for tvm_backward, packed by tvm_pack_mlp_tc with TVM_MLP_BF16 (NULL = none): lets a
    * TVM_MLP_FP16 step (fp16 forward, inside the fp32 tolerance) take the tensor-core backward, whose operands are bf16 */
   const void* tc_weights_bwd;
-  /* optional 3x3x3-dilated brick index from tvm_pack_alpha_bricks3 (NULL = none; same size and bit order as alpha_bricks):
-   * the empty-space test of a 32-sample block is then one bit lookup wherever the neighbourhood is empty, and the exact
-   * brick loop only runs near occupied space.  Never changes a mask decision.                                             */
+  /* optional neighbourhood words of the brick index from tvm_pack_alpha_bricks3 (NULL = none): one uint32 per 8^3 brick,
+   * bit (dz+1)*9 + (dy+1)*3 + (dx+1) = brick (x+dx, y+dy, z+dz) holds a set voxel.  The empty-space test of a 32-sample
+   * block is then one load and one AND instead of a loop over up to 27 bricks.  Never changes a mask decision.              */
   const uint32_t* alpha_bricks3;
 } TvmModel;
 
@@ -229,7 +229,7 @@ int tvm_pack_pair16(const float* src, int rows, int W, int C, void* dst, uint32_
 int tvm_pack_alpha(const float* volume, int D, int H, int W, uint32_t* bits, void* stream);
 /* brick index of a packed alpha volume; n_words = ceil(ceil(D/8)*ceil(H/8)*ceil(W/8) / 32)        */
 int tvm_pack_alpha_bricks(const uint32_t* bits, int D, int H, int W, uint32_t* bricks, void* stream);
-/* 3x3x3-dilated copy of a brick index (same size and bit order as `bricks`): TvmModel.alpha_bricks3     */
+/* Neighbourhood words of a brick index: bricks3 = uint32 [ceil(D/8) * ceil(H/8) * ceil(W/8)], see TvmModel.alpha_bricks3 */
 int tvm_pack_alpha_bricks3(const uint32_t* bricks, int D, int H, int W, uint32_t* bricks3, void* stream);
 /* 2x2x2-dilated copy of a packed alpha volume (same size and bit order as `bits`)                    */
 int tvm_pack_alpha_dilated(const uint32_t* bits, int D, int H, int W, uint32_t* dilated, void* stream);

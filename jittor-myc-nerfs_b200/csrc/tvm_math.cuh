@@ -233,9 +233,17 @@ TVM_HD bool bricks_maybe(const TvmModel& m, const uint32_t* __restrict__ bricks,
   }
   const int BW = (m.alpha_grid[0] + 7) >> 3, BH = (m.alpha_grid[1] + 7) >> 3;
   if (m.alpha_bricks3 != nullptr && hi[0] - lo[0] <= 2 && hi[1] - lo[1] <= 2 && hi[2] - lo[2] <= 2) {
-    // the box spans at most 3 bricks per axis: it lies inside the 3x3x3 neighbourhood of its middle brick, whose OR is one bit
-    const uint32_t idx = ((uint32_t)((lo[2] + hi[2]) >> 1) * BH + ((lo[1] + hi[1]) >> 1)) * BW + ((lo[0] + hi[0]) >> 1);
-    if (!((m.alpha_bricks3[idx >> 5] >> (idx & 31u)) & 1u)) return false;
+    // the box spans at most 3 bricks per axis: it lies inside the 3x3x3 neighbourhood of its middle brick, whose occupancy is
+    // one 27-bit word (tvm_pack_alpha_bricks3); the box is a product of three per-axis masks inside that word
+    const int mid[3] = {(lo[0] + hi[0]) >> 1, (lo[1] + hi[1]) >> 1, (lo[2] + hi[2]) >> 1};
+    const uint32_t word = m.alpha_bricks3[((uint32_t)mid[2] * BH + mid[1]) * BW + mid[0]];
+    if (word == 0u) return false;
+    uint32_t ax[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) ax[i] = ((1u << (hi[i] - lo[i] + 1)) - 1u) << (lo[i] - mid[i] + 1);      // bits d + 1, d in [-1, 1]
+    const uint32_t sy = (ax[1] & 1u) | ((ax[1] & 2u) << 2) | ((ax[1] & 4u) << 4);       // y mask spread to bits 0, 3, 6
+    const uint32_t sz = (ax[2] & 1u) | ((ax[2] & 2u) << 8) | ((ax[2] & 4u) << 16);      // z mask spread to bits 0, 9, 18
+    return (word & (ax[0] * sy * sz)) != 0u;                                            // products without carries
   }
   for (int z = lo[2]; z <= hi[2]; ++z)
     for (int y = lo[1]; y <= hi[1]; ++y)

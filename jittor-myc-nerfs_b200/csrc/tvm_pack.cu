@@ -180,23 +180,25 @@ __global__ void k_pack_bricks(const uint32_t* __restrict__ bits, int D, int H, i
   if ((threadIdx.x & 31) == 0 && (i >> 5) < (n_bricks + 31) / 32) bricks[i >> 5] = word;
 }
 
-// 3x3x3-dilated copy of the brick index: bit (bz,by,bx) = OR of the brick bits in [b-1, b+1]^3 (clamped at the borders).
-// A run of samples whose voxel box spans at most 3 bricks per axis is decided empty by ONE lookup at the middle brick.
+// Neighbourhood words of the brick index: one uint32 per brick, bit (dz+1)*9 + (dy+1)*3 + (dx+1) = brick (bx+dx, by+dy, bz+dz)
+// is non-empty (bricks outside the grid: 0).  A run of samples whose voxel box spans at most 3 bricks per axis lies inside the
+// 3x3x3 neighbourhood of its middle brick: the exact "does any brick of the box hold a voxel" is then ONE load and one AND
+// with the box's 27-bit mask (bricks_maybe, tvm_math.cuh) instead of a loop over up to 27 bricks.
 __global__ void k_pack_bricks3(const uint32_t* __restrict__ bricks, int BD, int BH, int BW, int n_bricks,
                                uint32_t* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  bool on = false;
-  if (i < n_bricks) {
-    const int bx = i % BW, by = (i / BW) % BH, bz = i / (BW * BH);
-    for (int z = max(bz - 1, 0); z <= min(bz + 1, BD - 1) && !on; ++z)
-      for (int y = max(by - 1, 0); y <= min(by + 1, BH - 1) && !on; ++y)
-        for (int x = max(bx - 1, 0); x <= min(bx + 1, BW - 1); ++x) {
-          const uint32_t idx = ((uint32_t)z * BH + y) * BW + x;
-          if ((bricks[idx >> 5] >> (idx & 31u)) & 1u) { on = true; break; }
-        }
-  }
-  const uint32_t word = __ballot_sync(0xffffffffu, on);
-  if ((threadIdx.x & 31) == 0 && (i >> 5) < (n_bricks + 31) / 32) out[i >> 5] = word;
+  if (i >= n_bricks) return;
+  const int bx = i % BW, by = (i / BW) % BH, bz = i / (BW * BH);
+  uint32_t word = 0;
+  for (int dz = -1; dz <= 1; ++dz)
+    for (int dy = -1; dy <= 1; ++dy)
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int x = bx + dx, y = by + dy, z = bz + dz;
+        if (x < 0 || y < 0 || z < 0 || x >= BW || y >= BH || z >= BD) continue;
+        const uint32_t idx = ((uint32_t)z * BH + y) * BW + x;
+        if ((bricks[idx >> 5] >> (idx & 31u)) & 1u) word |= 1u << ((dz + 1) * 9 + (dy + 1) * 3 + (dx + 1));
+      }
+  out[i] = word;
 }
 
 // TensorBase.compute_alpha on arbitrary points (tensorBase.py:451-473): one thread per point.
@@ -360,8 +362,7 @@ extern "C" int tvm_pack_alpha_bricks3(const uint32_t* bricks, int D, int H, int 
   TVM_REQUIRE(bricks && bricks3 && D > 0 && H > 0 && W > 0, "bad arguments");
   const int BD = (D + 7) / 8, BH = (H + 7) / 8, BW = (W + 7) / 8;
   const int n = BD * BH * BW;
-  const int n_pad = (n + 31) / 32 * 32;
-  k_pack_bricks3<<<(n_pad + 127) / 128, 128, 0, (cudaStream_t)stream>>>(bricks, BD, BH, BW, n, bricks3);
+  k_pack_bricks3<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(bricks, BD, BH, BW, n, bricks3);
   TVM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

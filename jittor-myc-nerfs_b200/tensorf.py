@@ -77,7 +77,7 @@ class AlphaGridMask:
         self.bricks = torch.empty((n_bricks + 31) // 32 + 8, dtype=torch.int32, device=device)
         L.check(lib.tvm_pack_alpha_bricks(_ptr(self.bits), D, H, W, _ptr(self.bricks), _stream_ptr()),
                 "tvm_pack_alpha_bricks")
-        self.bricks3 = torch.empty_like(self.bricks)
+        self.bricks3 = torch.empty(n_bricks + 8, dtype=torch.int32, device=device)       # 27-bit neighbourhood word per brick
         L.check(lib.tvm_pack_alpha_bricks3(_ptr(self.bricks), D, H, W, _ptr(self.bricks3), _stream_ptr()),
                 "tvm_pack_alpha_bricks3")
         self.dilated = torch.empty(n_words + 8, dtype=torch.int32, device=device)

@@ -137,7 +137,8 @@ def pack_bricks(volume):
 
 
 def pack_bricks3(volume):
-    """numpy restatement of tvm_pack_alpha_bricks3: brick bit OR-ed over its 3x3x3 neighbourhood (clamped at the borders)."""
+    """numpy restatement of tvm_pack_alpha_bricks3: one uint32 per brick, bit (dz+1)*9 + (dy+1)*3 + (dx+1) = the neighbour
+    brick at that offset holds a set voxel (outside the grid: 0)."""
     v = np.asarray(volume) > 0
     D, H, W = v.shape
     BD, BH, BW = (D + 7) // 8, (H + 7) // 8, (W + 7) // 8
@@ -145,14 +146,12 @@ def pack_bricks3(volume):
     pad[:D, :H, :W] = v
     b = pad.reshape(BD, 8, BH, 8, BW, 8).any(axis=(1, 3, 5))
     p = np.pad(b, 1)
-    d = np.zeros_like(b)
+    d = np.zeros(b.shape, np.uint32)
     for dz in range(3):
         for dy in range(3):
             for dx in range(3):
-                d |= p[dz:dz + BD, dy:dy + BH, dx:dx + BW]
-    d = d.reshape(-1).astype(np.uint8)
-    d = np.concatenate([d, np.zeros((-d.size) % 32 + 256, np.uint8)])
-    return np.packbits(d, bitorder="little").view(np.uint32).copy()
+                d |= p[dz:dz + BD, dy:dy + BH, dx:dx + BW].astype(np.uint32) << np.uint32(dz * 9 + dy * 3 + dx)
+    return np.concatenate([d.reshape(-1), np.zeros(8, np.uint32)]).copy()
 
 
 def emul_block_maybe(pkg, case, S=-1, bricks3=True):

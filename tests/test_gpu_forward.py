@@ -359,6 +359,21 @@ def test_pack_pair16_layout(env):
     assert lib.tvm_pack_pair16(C.c_void_p(src_d.data_ptr()), 1, 4, 4, C.c_void_p(dst.data_ptr() + 2), pkg._lib.MLP_FP16, stream) != 0   # alignment
 
 
+def test_pack_alpha_bricks3_words(env):
+    """tvm_pack_alpha_bricks3 (27-bit neighbourhood word per 8^3 brick) against its numpy restatement, cubic and ragged masks;
+    that the words never change which blocks are visited is tests/test_host_emul.py::test_coarse_block_skip_is_conservative."""
+    pkg, torch, fx, orc = env
+    from util import gpu_model
+    import emul_util as eu
+    for G, mres in ((40, 40), ((24, 40, 32), (20, 30, 25)), (32, 64)):
+        case = fx.make_case(G, 16, "R1", mask_res=mres)
+        model = gpu_model(pkg, case)
+        want = eu.pack_bricks3(case["alpha_volume"])
+        got = model.alphaMask.bricks3.cpu().numpy().view(np.uint32)
+        n = want.size - 8
+        assert np.array_equal(got[:n], want[:n]) and want[:n].any()
+
+
 def test_streamed_host_render_matches_resident(env):
     """OctreeRender_trilinear_fast(pinned host rays, out_host=...) pipelines upload / render / download per chunk; the
     pixels are those of the device-resident call, bit for bit (compositing is deterministic)."""
