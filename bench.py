@@ -640,7 +640,9 @@ def main():
         step_e2e()
     torch.cuda.synchronize()
 
-    model.stream_stages = int(os.environ.get("TVM_STREAM_STAGES", "8"))
+    if os.environ.get("TVM_STREAM_STAGES"):            # experiments: relative stage sizes, e.g. "1,7,7,1" or "8"
+        v = [int(x) for x in os.environ["TVM_STREAM_STAGES"].split(",")]
+        model.stream_stages = v[0] if len(v) == 1 else tuple(v)
     with ClockSampler(local_rank) as clk:
         ms_total = timed(step_resident, args.steps)
         ms_e2e = timed(step_e2e, args.steps)

@@ -13,7 +13,7 @@ import torch
 def _render_streamed(rays, tensorf, N_samples, white_bg, out_host):
     """Host-resident rays (pinned) -> host-resident rgb/depth (pinned), pipelined per chunk: the uploads run ahead on a copy
     stream, chunk i renders (TensorVMSplit._render_bounded: two compute streams, bounded workspaces, overflow check), the
-    download of chunk i follows it on the copy stream.  A large frame is cut into at least `stream_stages` (8) pieces so that
+    download of chunk i follows it on the copy stream.  A large frame is cut into `stream_stages` pieces (relative sizes) so that
     the copies hide.  With `tensorf.defer_overflow_check` the call returns without reading the overflow status
     (verify_renders() before the host tensors are read): a range that has to be rendered again is uploaded again from `rays`."""
     dev = tensorf.device
@@ -27,15 +27,23 @@ def _render_streamed(rays, tensorf, N_samples, white_bg, out_host):
     live = [True]          # False once this call has returned: `launch` is then a deferred repair
     cs, main = st["copy"], torch.cuda.current_stream()
     rgb_host, depth_host = out_host
-    stage = max(65536, -(-n // int(getattr(tensorf, "stream_stages", 8))))
+    # pipeline stages (a count of equal pieces, or relative sizes).  What is exposed is the first stage's upload, the last
+    # stage's download and every download that is longer than the compute still to come; 8 equal pieces measured best
+    # (173 M rays/s; (1,7,7,1): 168, (1,14,1): 163, (1,3,4,4,3,1): 173 -- profiles/r02_notes.txt P)
+    weights = getattr(tensorf, "stream_stages", 8)
+    weights = [1] * int(weights) if isinstance(weights, int) else list(weights)
+    if n < 65536 * len(weights):
+        weights = [1] * max(1, n // 65536)
+    cuts = [int(round(n * sum(weights[:i]) / float(sum(weights)))) // 256 * 256 for i in range(len(weights))] + [n]
+    bounds = [(a, b) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
     cs.wait_stream(main)
-    ups = {}
+    ups = []
     with torch.cuda.stream(cs):
-        for s in range(0, n, stage):
-            e = min(n, s + stage)
+        for s, e in bounds:
             st["rays"][s:e].copy_(rays[s:e], non_blocking=True)
-            ups[s] = torch.cuda.Event()
-            ups[s].record(cs)
+            ev = torch.cuda.Event()
+            ev.record(cs)
+            ups.append((s, e, ev))
     flags = tensorf._flags(white_bg)
 
     def launch(s, e, slot, nbytes):
@@ -45,8 +53,8 @@ def _render_streamed(rays, tensorf, N_samples, white_bg, out_host):
             st["rays"][s:e].copy_(rays[s:e], non_blocking=True)
         else:
             # a launch may span upload stages: wait for every stage it touches
-            for s0, ev in ups.items():
-                if s0 < e and s0 + stage > s:
+            for s0, e0, ev in ups:
+                if s0 < e and e0 > s:
                     torch.cuda.current_stream().wait_event(ev)
         tensorf._forward_raw(st["rays"][s:e], None, flags, S, out=(st["rgb"][s:e], st["depth"][s:e]), ws_slot=slot, ws_bytes=nbytes)
         return tensorf._ws if slot == 0 else tensorf._ws2
@@ -57,7 +65,7 @@ def _render_streamed(rays, tensorf, N_samples, white_bg, out_host):
             rgb_host[s:e].copy_(st["rgb"][s:e], non_blocking=True)
             depth_host[s:e].copy_(st["depth"][s:e], non_blocking=True)
 
-    tensorf._render_bounded(n, S, launch, copy_out=copy_out, max_rays=stage)
+    tensorf._render_bounded(n, S, launch, copy_out=copy_out, ranges=bounds)
     live[0] = False
     main.wait_stream(cs)
     return rgb_host, depth_host

@@ -211,7 +211,7 @@ class TensorVMSplit(MaintainMixin, RegularizerMixin, CheckpointMixin, torch.nn.M
         self._peer_comm = None          # enable_peer_allreduce(): libtvmrender's own all-reduce over NVLink peer memory
         self.defer_overflow_check = False      # True: bounded evaluation renders are verified by verify_renders(), not at once
         self._pending_checks = []
-        self.stream_stages = 8          # pipeline stages of a host-to-host frame (renderer._render_streamed)
+        self.stream_stages = 8          # pipeline stages of a host-to-host frame: a count (equal pieces) or relative sizes (renderer._render_streamed)
         self.ws_overflows = 0           # ranges rendered a second time because their entry list overflowed
         self._epr_hint = None           # entries per ray (+30 %) the next bounded render sizes its entry lists from
         self._ws = None
