@@ -612,7 +612,7 @@ def main():
     model.defer_overflow_check = True
     repairs = {"timed": 0}
 
-    def timed(fn, steps, retry=True):
+    def timed(fn, steps, attempts=4):
         """K steps, each bracketed by CUDA events on the launching stream, L2 flushed before each."""
         evs = []
         model.verify_renders()
@@ -626,9 +626,12 @@ def main():
             evs.append((a, b))
         repaired = model.verify_renders()
         barrier()
-        if repaired and retry:
-            return timed(fn, steps, retry=False)
-        repairs["timed"] += repaired
+        if repaired:
+            # an overflowed range did less work inside the events than the frame needs: never a measurement
+            repairs["timed"] += repaired
+            if attempts <= 1:
+                raise SystemExit("bench: bounded-workspace overflows inside every attempt of a timed region")
+            return timed(fn, steps, attempts - 1)
         ms = sum(a.elapsed_time(b) for a, b in evs)
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         if dist is not None:
@@ -655,12 +658,13 @@ def main():
     def profiled(steps):
         """K resident steps with per-kernel cudaEvents (tvm_profile_*) and the kernels' own work counters."""
         model.collect_counters = True
-        model.counters.zero_()
         # one launch per kernel for the whole frame (a 29 GB workspace): per-kernel times of the two-stream chunk pipeline
         # overlap each other and would not be launch durations
         budget = model.ws_budget_bytes
         model.ws_budget_bytes = max(budget, 2 * model.workspace_bytes(n, S) + (1 << 20))
         step_resident()
+        torch.cuda.synchronize()
+        model.counters.zero_()              # the counters cover exactly the K profiled steps
         L.profile_enable(True)
         L.profile_collect()
         timed(step_resident, steps)
@@ -768,7 +772,7 @@ def main():
                        "workspace": f"{model.ws_budget_bytes / 2**30:.0f} GiB for both workspaces; bounded entry lists sized from the previous "
                                     f"frame's entries per ray (+30 %), overflow check after the launch: {-(-n // model._plan_launch(n, S)[0])} launch(es) per kernel "
                                     f"per resident frame; overflow check deferred to the end of the K resident frames (verify_renders), the same for the e2e frames "
-                                    f"({model.stream_stages} pipeline stages); {model.ws_overflows} range(s) re-rendered in this run, {repairs['timed']} of them after a timed region",
+                                    f"({model.stream_stages} pipeline stages); {model.ws_overflows} range(s) re-rendered in this run, {repairs['timed']} of them after a timed region (that region was then timed again)",
                        "samples_per_s_nominal_n_times_S": value * S,
                        "samples_per_s_marched_in_box": M_in * world / (ms_total / args.steps * 1e-3),
                        "samples_per_s_gathered": M_v * world / (ms_total / args.steps * 1e-3),
