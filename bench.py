@@ -394,6 +394,10 @@ def run_side_workload(args):
     mp = fx.make_model(G, density_shift=reg["density_shift"], variant=variant)
     vol = fx.ball_alpha_volume(MASK_RES if G > 128 else 128) if reg["mask"] else None
     model = pkg.model_from_params(mp, f"cuda:{local_rank}", vol, mp.aabb.copy(), args.mlp)
+    # full frames of the variants: 16-bit pair records under the tensor-core head and the deferred overflow check, as the
+    # contract line renders them (training reads the fp32 grids and the worst-case workspace)
+    model.app_planes_bf16 = (not train) and args.app_planes == "bf16" and args.mlp in ("bf16", "fp16")
+    model.defer_overflow_check = not train
     if train:
         n = 4096 if args.rays == FRAME * FRAME else args.rays
         # weak scaling, 4096 rays per rank: the ranks slice ONE seeded global permutation of an 8-view ray pool, as the
@@ -461,6 +465,8 @@ def run_side_workload(args):
             fn()
             b.record()
             evs.append((a, b))
+        if model.verify_renders():
+            raise SystemExit("bench: a bounded workspace overflowed inside a timed region of a side workload")
         barrier()
         t = torch.tensor([sum(a.elapsed_time(b) for a, b in evs)], dtype=torch.float64, device=dev)
         if dist is not None:
@@ -469,6 +475,7 @@ def run_side_workload(args):
 
     for _ in range(max(args.warmup, 3)):
         step()
+        model.verify_renders()          # (corrects the entries-per-ray hint of the bounded workspaces before anything is timed)
     with ClockSampler(local_rank) as clk:
         ms = timed(args.steps)
     model.collect_counters = True
@@ -488,6 +495,7 @@ def run_side_workload(args):
             "dtype": "f32" if args.mlp == "fp32" else (f"f32 + {args.mlp} tensor-core MLP" + (" (forward and backward)" if train and args.mlp == "bf16" else
                                                                      " (forward; bf16 tensor-core backward)" if train and args.mlp == "fp16" else "")), "data": "synthetic",
             "config": {"workload": name + f", regime {args.regime}", "n_samples": S,
+                       "app_planes": args.mlp if model.app_planes_bf16 else "fp32",
                        "l2": "flushed before every timed step (256 MiB write)",
                        "per_step_counts": {"M_in": cnt[L.CNT_M_IN], "M_v_gathered": cnt[L.CNT_M_V], "M_a": cnt[L.CNT_M_A],
                                            "bg_rays": cnt[L.CNT_BG_RAYS], "bg_samples": cnt[L.CNT_BG_SAMPLES]}},

@@ -209,6 +209,7 @@ class TensorVMSplit(MaintainMixin, RegularizerMixin, CheckpointMixin, torch.nn.M
         self.grad_sync = False          # set True (after dist.init_from_env) for data-parallel training
         self.grad_sync_group = None
         self._peer_comm = None          # enable_peer_allreduce(): libtvmrender's own all-reduce over NVLink peer memory
+        self.train_ws_budget_bytes = int(float(os.environ.get("TVM_TRAIN_WS_GIB", "16")) * (1 << 30))   # worst-case workspace of one training launch
         self.defer_overflow_check = False      # True: bounded evaluation renders are verified by verify_renders(), not at once
         self._pending_checks = []
         self.stream_stages = 8          # pipeline stages of a host-to-host frame: a count (equal pieces) or relative sizes (renderer._render_streamed)
@@ -483,10 +484,10 @@ class TensorVMSplit(MaintainMixin, RegularizerMixin, CheckpointMixin, torch.nn.M
         return out.value
 
     def max_rays_per_launch(self, S):
-        """Rays per launch that keep the WORST-CASE workspace (every sample weighted, 44 B x n x S) inside one of the two
-        workspaces of the budget: the bound for launches whose stash is read again (training steps)."""
+        """Rays of one TRAINING launch: its workspace is the worst case (every sample weighted, 44 B x n x S -- tvm_backward
+        reads the stash), bounded by `train_ws_budget_bytes` (16 GiB: 380 k rays at S = 1036; the reference trains on 4096)."""
         per_ray = self.workspace_bytes(1024, S) / 1024.0
-        return max(1024, int(self.ws_budget_bytes / 2 / per_ray) // 1024 * 1024)
+        return max(1024, int(self.train_ws_budget_bytes / per_ray) // 1024 * 1024)
 
     def _workspace(self, n, S, slot=0, nbytes=None):
         """Caller-owned scratch of tvm_forward.  Slot 0 is THE workspace (what tvm_backward and workspace_view read); slot 1
