@@ -259,8 +259,9 @@ __global__ void __launch_bounds__((kMlpWarps2 + NGW) * 32, 1) k_app_tc2(const Fw
     // A tile is 16 passes of 8 rows (4 lanes per entry); pass number p = 16 * it + pass of the CTA's tile sequence goes to
     // gather warp p % NGW, so any warp count divides the work evenly over a few tiles.  Every pass arrives on full[stage]
     // (count 16).  Entry coordinates: written by k_march with the coordinates it marched; read once: evict-first.
-    // (Fetching them one pass ahead measured SLOWER, twice: 2.25 vs 2.07 ms per frame, and 1.74 vs 1.47 with the mixed-precision
-    //  gather; profiles/r02_notes.txt B, N.)
+    // (Fetching them one pass ahead measured SLOWER, three times: held in registers 2.25 vs 2.07 ms per frame and 1.74 vs 1.47
+    //  with the mixed-precision gather; by cp.async into shared memory, no register held, 1.64 vs 1.45 -- warps that run ahead
+    //  of their neighbours lose the L1 hits they share with them; profiles/r02_notes.txt B, N, S.)
     constexpr uint32_t kPasses = kRows / 8;
     const uint32_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
 #pragma unroll 1
