@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define TVM_ABI_VERSION 27
+#define TVM_ABI_VERSION 28
 
 /* flags for tvm_forward / tvm_backward */
 #define TVM_WHITE_BG      0x1u  /* rgb_map += 1 - acc_map          (tensorBase.py:523-524) */
@@ -363,6 +363,12 @@ int tvm_generate_rays(const float* c2w_host, int H, int W, float fx, float fy, f
                       int normalize, float* rays_out, void* stream);
 /* up_sampling_VM (tensoRF.py:248-262): F.interpolate(bilinear, align_corners=True) of one NCHW grid [C][H][W] -> [C][H2][W2]   */
 int tvm_upsample_grid(const float* src_nchw, int C, int H, int W, float* dst_nchw, int H2, int W2, void* stream);
+/* The same for up to TVM_UPSAMPLE_MAX_GRIDS grids in ONE launch (the three planes and three lines of up_sampling_VM, or all
+ * twelve of upsample_volume_grid, tensoRF.py:264-269): HOST arrays src_nchw[n], dst_nchw[n] of device pointers,
+ * src_chw[n][3] = {C, H, W}, dst_hw[n][2] = {H2, W2}.  Same arithmetic per output as tvm_upsample_grid (bit-identical).      */
+#define TVM_UPSAMPLE_MAX_GRIDS 12
+int tvm_upsample_grids(int n_grids, const float* const* src_nchw, const int32_t* src_chw, float* const* dst_nchw,
+                       const int32_t* dst_hw, void* stream);
 
 /* Regularisers of train.py:233-251, value and gradient in one pass: *loss_accum += weight * f(x) (device scalar, may be NULL),
  * grad += weight * df/dx (same shape as x, may be NULL).  weight_dev (nullable): DEVICE scalar multiplied into `weight`

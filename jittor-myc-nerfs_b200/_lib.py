@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # TVM_LIB: developer override (kernel-tuning experiments build variant libraries next to the default one)
 LIB_PATH = os.environ.get("TVM_LIB") or os.path.join(_HERE, "libtvmrender.so")
-ABI_VERSION = 27
+ABI_VERSION = 28
 
 # flags (tvmrender.h)
 WHITE_BG = 0x1
@@ -115,7 +115,7 @@ EXPORTS = [
     "tvm_workspace_bytes", "tvm_workspace_bytes_bounded", "tvm_workspace_capacity", "tvm_forward_entries", "tvm_workspace_layout", "tvm_forward", "tvm_forward_npp", "tvm_bg_fold", "tvm_bg_tc_bytes", "tvm_pack_bg_tc", "tvm_backward", "tvm_backward_npp", "tvm_bg_fold_bwd",
     "tvm_density_alpha", "tvm_mse_loss",
     "tvm_profile_enable", "tvm_profile_collect",
-    "tvm_dense_alpha", "tvm_alpha_mask_from_dense", "tvm_filter_rays", "tvm_generate_rays", "tvm_upsample_grid",
+    "tvm_dense_alpha", "tvm_alpha_mask_from_dense", "tvm_filter_rays", "tvm_generate_rays", "tvm_upsample_grid", "tvm_upsample_grids",
     "tvm_tv_loss", "tvm_tv_loss_batch", "tvm_l1_loss", "tvm_vector_diffs", "tvm_adam_step", "tvm_selftest_umma", "tvm_bench_gather",
     "tvm_allreduce_signal_words", "tvm_allreduce_sum", "tvm_backward_dp",
 ]
@@ -177,6 +177,7 @@ def load() -> C.CDLL:
     lib.tvm_filter_rays.argtypes = [C.POINTER(TvmModel), vp, i32, i32, i32, vp, vp, vp]
     lib.tvm_generate_rays.argtypes = [C.POINTER(C.c_float), i32, i32, f32, f32, f32, f32, i32, i32, vp, vp]
     lib.tvm_upsample_grid.argtypes = [vp, i32, i32, i32, vp, i32, i32, vp]
+    lib.tvm_upsample_grids.argtypes = [i32, C.POINTER(C.c_void_p), i3, C.POINTER(C.c_void_p), i3, vp]
     lib.tvm_tv_loss.argtypes = [vp, i32, i32, i32, f32, vp, vp, vp, vp]
     lib.tvm_tv_loss_batch.argtypes = [C.POINTER(TvmTvJob), i32, vp, vp]
     lib.tvm_l1_loss.argtypes = [vp, C.c_size_t, f32, vp, vp, vp, vp]

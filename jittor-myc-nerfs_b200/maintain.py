@@ -117,27 +117,43 @@ class MaintainMixin:
 
     # ---- §8f-4 ------------------------------------------------------------------------------------------------
     @torch.no_grad()
-    def up_sampling_VM(self, plane_coef, line_coef, res_target):
-        """tensoRF.py:248-262."""
+    def _upsample_grids(self, pairs, res_target):
+        """Bilinear (align_corners=True) resize of several (plane_coef, line_coef) halves in ONE launch (tvm_upsample_grids)."""
         from .tensorf import MAT_MODE, VEC_MODE
         lib, st = L.load(), _stream_ptr()
-        planes, lines = [], []
-        for i in range(3):
-            m0, m1 = MAT_MODE[i]
-            for src, (H2, W2), dst_list in ((plane_coef[i], (int(res_target[m1]), int(res_target[m0])), planes),
-                                            (line_coef[i], (int(res_target[VEC_MODE[i]]), 1), lines)):
-                s = src.detach().contiguous()
-                _, Cc, H, W = s.shape
-                d = torch.empty((1, Cc, H2, W2), dtype=torch.float32, device=s.device)
-                L.check(lib.tvm_upsample_grid(_ptr(s), Cc, H, W, _ptr(d), H2, W2, st), "tvm_upsample_grid")
-                dst_list.append(torch.nn.Parameter(d))
-        return torch.nn.ParameterList(planes), torch.nn.ParameterList(lines)
+        srcs, dsts, chw, hw = [], [], [], []
+        for plane_coef, line_coef in pairs:
+            for i in range(3):
+                m0, m1 = MAT_MODE[i]
+                for src, (H2, W2) in ((plane_coef[i], (int(res_target[m1]), int(res_target[m0]))),
+                                      (line_coef[i], (int(res_target[VEC_MODE[i]]), 1))):
+                    s = src.detach().contiguous()
+                    _, Cc, H, W = s.shape
+                    srcs.append(s)
+                    dsts.append(torch.empty((1, Cc, H2, W2), dtype=torch.float32, device=s.device))
+                    chw += [Cc, H, W]
+                    hw += [H2, W2]
+        n = len(srcs)
+        L.check(lib.tvm_upsample_grids(n, (C.c_void_p * n)(*[t.data_ptr() for t in srcs]), (C.c_int32 * (3 * n))(*chw),
+                                       (C.c_void_p * n)(*[t.data_ptr() for t in dsts]), (C.c_int32 * (2 * n))(*hw), st),
+                "tvm_upsample_grids")
+        out = []
+        for h in range(len(pairs)):
+            g = dsts[6 * h:6 * h + 6]
+            out.append((torch.nn.ParameterList([torch.nn.Parameter(g[2 * i]) for i in range(3)]),
+                        torch.nn.ParameterList([torch.nn.Parameter(g[2 * i + 1]) for i in range(3)])))
+        return out
+
+    @torch.no_grad()
+    def up_sampling_VM(self, plane_coef, line_coef, res_target):
+        """tensoRF.py:248-262."""
+        return self._upsample_grids([(plane_coef, line_coef)], res_target)[0]
 
     @torch.no_grad()
     def upsample_volume_grid(self, res_target):
-        """tensoRF.py:264-269."""
-        self.app_plane, self.app_line = self.up_sampling_VM(self.app_plane, self.app_line, res_target)
-        self.density_plane, self.density_line = self.up_sampling_VM(self.density_plane, self.density_line, res_target)
+        """tensoRF.py:264-269; all twelve grids in one launch."""
+        (self.app_plane, self.app_line), (self.density_plane, self.density_line) = self._upsample_grids(
+            [(self.app_plane, self.app_line), (self.density_plane, self.density_line)], res_target)
         self.update_stepSize(res_target)
         self._invalidate_packed()
 
