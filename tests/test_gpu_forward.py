@@ -656,3 +656,67 @@ def test_sixteen_bit_operands_on_trained_and_scaled_models(env):
         if scale <= 10.0:
             assert max(table[(scale, "fp16", False)], table[(scale, "fp16", True)], table[(scale, "bf16", True)]) <= 1e-2
     assert table[(1.0, "fp16", True)] <= RGB_TOL
+
+
+def test_degenerate_inputs_production_path(env):
+    """The production launch (no aux) on inputs the reference's tests never see, in every head mode:
+    (a) a render in which NO sample reaches the appearance head (regime R0: every weight < 1e-4; the tensor-core kernel runs
+        with zero tiles) -- equal to the oracle (white background);
+    (b) non-finite rays (NaN / inf origins and directions, zero direction) between good ones: the call returns, the good rays
+        keep their pixels bit for bit, nothing is written outside the outputs (canaries);
+    (c) bad arguments fail loudly with an error string instead of launching."""
+    pkg, torch, fx, orc = env
+    from util import gpu_model
+    import ctypes as C
+    # (a)
+    case = fx.make_case(64, 600, "R0", mask_res=64)
+    case["model"].density_shift = -16.0          # sigma ~ 1e-7: every weight far below the 1e-4 threshold
+    ref = orc.run_case(case)
+    assert ref["app_mask"].sum() == 0 and ref["ray_valid"].sum() > 0 and ref["weight"].max() > 0
+    rays = torch.from_numpy(case["rays"]).cuda()
+    for mode in ("fp32", "bf16", "fp16"):
+        model = gpu_model(pkg, case, mlp_mode=mode)
+        model.app_planes_bf16 = mode != "fp32"
+        with torch.no_grad():
+            rgb, depth = model(rays)
+        torch.cuda.synchronize()
+        assert np.abs(rgb.cpu().numpy() - ref["rgb_map"]).max() <= RGB_TOL
+        assert np.abs(depth.cpu().numpy() - ref["depth_map"]).max() <= DEPTH_TOL
+    # (b)
+    case = fx.make_case(64, 512, "R2", mask_res=64)
+    good = torch.from_numpy(case["rays"]).cuda()
+    bad = good.clone()
+    nan, inf = float("nan"), float("inf")
+    rows = {3: [nan, 0, 0, 0, 0, 1], 17: [0, 0, 12, nan, nan, nan], 64: [inf, 0, 0, 0, 0, -1], 65: [0, 0, 12, 0, 0, -inf],
+            130: [0, 0, 12, 0, 0, 0], 255: [1e30, -1e30, 1e30, 1, 0, 0], 256: [0, 0, 0, 1e-38, 1e-38, 1e-38], 511: [-inf, inf, nan, inf, -inf, nan]}
+    for i, v in rows.items():
+        bad[i] = torch.tensor(v, dtype=torch.float32)
+    keep = np.array([i not in rows for i in range(512)])
+    for mode in ("fp32", "fp16"):
+        model = gpu_model(pkg, case, mlp_mode=mode)
+        model.app_planes_bf16 = mode != "fp32"
+        with torch.no_grad():
+            rgb0, depth0 = model(good)
+            out = torch.full((512 * 4 + 64,), -7.0, device="cuda")          # outputs carved from one buffer with canaries around them
+            rgb1, depth1 = out[16:16 + 1536].view(512, 3), out[16 + 1536 + 16:16 + 1536 + 16 + 512]
+            model._forward_raw(bad, None, model._flags(True), model.nSamples, out=(rgb1, depth1))
+        torch.cuda.synchronize()
+        o = out.cpu().numpy()
+        assert (o[:16] == -7.0).all() and (o[16 + 1536:16 + 1536 + 16] == -7.0).all() and (o[16 + 1536 + 16 + 512:] == -7.0).all()
+        assert np.array_equal(rgb1.cpu().numpy()[keep], rgb0.cpu().numpy()[keep])
+        assert np.array_equal(depth1.cpu().numpy()[keep], depth0.cpu().numpy()[keep])
+    # (c)
+    lib, Lb = pkg._lib.load(), pkg._lib
+    m = model._model()
+    ws = model._workspace(512, model.nSamples)
+    args = lambda **kw: [kw.get("model", C.byref(m)), kw.get("rays", C.c_void_p(good.data_ptr())), kw.get("n", 512), kw.get("S", int(model.nSamples)),
+                         None, model._flags(True), C.c_void_p(rgb0.data_ptr()), C.c_void_p(depth0.data_ptr()), None, None,
+                         kw.get("ws", C.c_void_p(ws.data_ptr())), kw.get("ws_bytes", ws.numel()), None]
+    for kw in (dict(n=0), dict(S=0), dict(rays=None), dict(ws=None), dict(ws_bytes=1024), dict(ws=C.c_void_p(ws.data_ptr() + 4)), dict(n=1 << 24, S=1 << 10)):
+        rc = lib.tvm_forward(*args(**kw))
+        assert rc != 0, kw
+        assert len(lib.tvm_last_error()) > 0
+    torch.cuda.synchronize()
+    with torch.no_grad():                                   # and the library still renders afterwards
+        rgb2, _ = model(good)
+    assert np.array_equal(rgb2.cpu().numpy(), rgb0.cpu().numpy())
