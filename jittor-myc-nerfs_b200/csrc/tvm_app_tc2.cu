@@ -248,7 +248,8 @@ __global__ void __launch_bounds__((kMlpWarps2 + NGW) * 32, 1) k_app_tc2(const Fw
   constexpr uint32_t A0_STAGE = (K0 / 8) * kLboA0;
 
   const uint32_t n_ent = min(*P.ws.n_entries, P.ws.cap);      // bounded workspace: entries behind the capacity were not stored
-  const uint32_t n_tiles = (n_ent + kRows - 1) / kRows;
+  const uint32_t tile_rows = balanced_tile_rows(n_ent, kGroups * gridDim.x);   // 128, or fewer for launches of a few rounds
+  const uint32_t n_tiles = (n_ent + tile_rows - 1) / tile_rows;
 
   if (warp >= kMlpWarps2) {
     // =============================== gather group ================================================
@@ -271,7 +272,7 @@ __global__ void __launch_bounds__((kMlpWarps2 + NGW) * 32, 1) k_app_tc2(const Fw
       mbar_wait(&empty[s], (use & 1u) ^ 1u);          // stage free (first use of a stage passes at once; the barrier cannot
                                                       // run a second phase ahead: that needs this very pass)
       const uint32_t row = pass * 8 + (lane >> 2);
-      const uint32_t e = (blockIdx.x + it * gridDim.x) * kRows + row;
+      const uint32_t e = row < tile_rows ? (blockIdx.x + it * gridDim.x) * tile_rows + row : n_ent;      // dead rows of a short tile
       uint8_t* arow = sA0 + s * A0_STAGE + row * 16;
 #ifdef TVM_EXP_NOGATHER
       gather_row<CA, PB16, H16>(P, arow, false, make_float4(0.0f, 0.0f, 0.0f, 0.0f), lane & 3);
@@ -321,7 +322,7 @@ __global__ void __launch_bounds__((kMlpWarps2 + NGW) * 32, 1) k_app_tc2(const Fw
     if (leader && tile < n_tiles) issue_gemm0(0);
 
     for (; tile < n_tiles; tile += stride, ++j) {
-      const uint32_t e = tile * kRows + row;
+      const uint32_t e = (uint32_t)row < tile_rows ? tile * tile_rows + row : n_ent;                     // dead rows of a short tile
       float dir[3] = {0.0f, 0.0f, 0.0f};
       if (e < n_ent) {
         const uint32_t ray = P.ws.ent[e].x;

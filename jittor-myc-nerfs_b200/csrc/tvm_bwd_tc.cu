@@ -101,8 +101,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_app_bwd_tc(const BwdParams Bp) 
   if (warp < kRowWarps) asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
   else asm volatile("setmaxnreg.dec.sync.aligned.u32 128;");
 
-  const uint32_t n_ent = *P.ws.n_entries;
-  const uint32_t n_tiles = (n_ent + kRows - 1) / kRows;
+  const uint32_t n_ent_all = *P.ws.n_entries;
+  const uint32_t tile_rows = balanced_tile_rows(n_ent_all, gridDim.x);       // 128, or fewer for launches of a few rounds
+  const uint32_t n_tiles = (n_ent_all + tile_rows - 1) / tile_rows;
   const float4* gray = reinterpret_cast<const float4*>(P.ws.bwd_scratch);
   uint32_t phase = 0;
   bool first = true;
@@ -123,7 +124,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_app_bwd_tc(const BwdParams Bp) 
   };
 
   for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const uint32_t tile_base = tile * kRows;
+    const uint32_t tile_base = tile * tile_rows;
+    const uint32_t n_ent = min(n_ent_all, tile_base + tile_rows);            // rows behind the tile's entries are dead
     // ================================ gather (helper warps) ==============================================
     float dir[3] = {0.0f, 0.0f, 0.0f}, gw[3] = {0.0f, 0.0f, 0.0f}, wgt = 0.0f;
     if (warp >= kRowWarps) {

@@ -12,6 +12,22 @@ namespace tc {
 
 constexpr int kRows = 128;          // UMMA M
 
+// Rows per tile of a persistent launch over n_ent entries whose CTAs take `slots` tiles per round (grid x tile pipelines per
+// CTA).  128 -- the MMA's M -- when the launch is many rounds long; for the few-round launches of a training step (4096 rays:
+// ~240 tiles on 148 SMs = 1.6 rounds) the multiple of 8 that spreads the entries evenly over WHOLE rounds, so that no SM
+// idles through a second round while the others work on full tiles (rows behind it are dead: zero operands, no gather, no
+// scatter; the MMAs run on all 128 rows either way).
+__device__ __forceinline__ uint32_t balanced_tile_rows(uint32_t n_ent, uint32_t slots) {
+#ifdef TVM_NO_BALANCED_TILES
+  return kRows;
+#endif
+  const uint32_t t = (n_ent + kRows - 1) / kRows;
+  if (t == 0 || t >= 8u * slots) return kRows;
+  const uint32_t t2 = (t + slots - 1) / slots * slots;
+  const uint32_t r = ((n_ent + t2 - 1) / t2 + 7u) & ~7u;
+  return r < (uint32_t)kRows ? r : (uint32_t)kRows;
+}
+
 constexpr int kTmemCols = 256;      // [0,128): layer accumulators, [128,160): basis accumulator
 constexpr int kColBasis = 128;
 
