@@ -737,7 +737,8 @@ def main():
         per_launch = m_a * steps / launches
         tf = DENSE_FLOP_PER_ENTRY * per_launch / (ms * 1e-3) / 1e12 if ms else 0.0
         tj = traffic_json.get(traffic_key, {})
-        return {"bound": "tensor", "kernel": "k_app_tc2 (appearance gather + basis_mat + MLPRender_Fea on tcgen05, TMEM-resident activations)"
+        return {"bound": "tensor", "kernel": ("k_app_tc2 (appearance gather + basis_mat + MLPRender_Fea on tcgen05, TMEM-resident activations"
+                                              + (" + compositing: w * rgb into per-ray fixed-point sums, TVM_EVAL_ONLY)" if model.fused_composite else ")"))
                 if args.mlp != "fp32" else "k_app_simt (fp32 FMA parity head)",
                 "achieved": tf, "peak": tc_peak, "unit": "TFLOP/s", "frac": tf / tc_peak, "traffic": tj.get("dram_bytes_per_launch"),
                 "traffic_source": tj.get("source"), "peak_source": tc_src, "ms_per_launch": ms, "launches_per_step": launches / steps,
@@ -778,7 +779,10 @@ def main():
                      (f" fed from {args.mlp} appearance planes" if model.app_planes_bf16 else ""),
             "data": "synthetic",
             "config": {"workload": workload_name(args), "n_samples": S, "rays_per_step_per_gpu": n,
-                       "mlp": args.mlp, "app_planes": args.mlp if model.app_planes_bf16 else "fp32", "early_ray_termination": True, "l2": "flushed before every timed step "
+                       "mlp": args.mlp, "app_planes": args.mlp if model.app_planes_bf16 else "fp32", "early_ray_termination": True,
+                       "compositing": ("inside the appearance head (TVM_EVAL_ONLY: 32-bit fixed-point sums per ray, order-independent)"
+                                       if model.fused_composite else "k_composite over per-block tables"),
+                       "l2": "flushed before every timed step "
                        "(256 MiB write)", "parallelism": f"one frame per rank x {world}",
                        "workspace": f"{model.ws_budget_bytes / 2**30:.0f} GiB for both workspaces; bounded entry lists sized from the previous "
                                     f"frame's entries per ray (+30 %), overflow check after the launch: {-(-n // model._plan_launch(n, S)[0])} launch(es) per kernel "
@@ -804,6 +808,23 @@ def main():
 
     if not args.no_extras:
         k2 = max(3, args.steps // 2)
+        # ---- the same frame with the stash launch (no TVM_EVAL_ONLY): separate k_composite over per-block tables, the head
+        #      without the compositing atomics -- what a render that is followed by tvm_backward runs
+        if model.fused_composite:
+            model.fused_composite = False
+            for _ in range(2):
+                step_resident()
+            ms_u = timed(step_resident, k2) / k2
+            st_u, sc_u, c_u = profiled(k2)
+            r_u = app_roofline(st_u, sc_u, c_u[L.CNT_M_A], k2, "k_app_tc2")
+            line["stash_launch"] = {"value": total_rays / (ms_u * 1e-3), "unit": UNIT, "ms_per_step": ms_u,
+                                    "stage_ms_per_step": {k: v / k2 for k, v in st_u.items() if v},
+                                    "app_head": {k: r_u[k] for k in ("achieved", "frac", "ms_per_launch", "unit")},
+                                    "max_abs_err_vs_oracle_512rays": oracle_check(case) if rank == 0 else None,
+                                    "note": "tvm_forward without TVM_EVAL_ONLY (the launch tvm_backward needs): per-block tables + per-entry colours "
+                                            "+ k_composite; the head alone reaches a higher tensor fraction, the frame is slower"}
+            model.fused_composite = True
+            step_resident()
         # ---- the same frame with the other operand formats (judge's question: what do the 16-bit plane copies buy?) -------
         alt = {}
         for name, mlp, planes16 in (("fp16_head_fp32_planes", "fp16", False), ("bf16_head_bf16_planes", "bf16", True),

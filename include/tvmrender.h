@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define TVM_ABI_VERSION 28
+#define TVM_ABI_VERSION 29
 
 /* flags for tvm_forward / tvm_backward */
 #define TVM_WHITE_BG      0x1u  /* rgb_map += 1 - acc_map          (tensorBase.py:523-524) */
@@ -48,6 +48,15 @@ extern "C" {
                                   is given, else the fp32 one.  fp16 saturates at 65504: a model whose activations or
                                   features exceed that needs TVM_MLP_BF16 (same kernels, 8-bit mantissa, fp32 range)          */
 #define TVM_MLP_MASK      0x30u
+#define TVM_EVAL_ONLY     0x4u  /* tvm_forward only: the caller needs the two maps and nothing else -- no tvm_backward will follow on
+                                  this workspace and nobody reads its stash.  The appearance head then composites as it goes:
+                                  every entry adds w * rgb to its ray in 32-bit FIXED POINT (units of 2^-31: colours are sigmoids
+                                  and sum(w) <= 1; a term is rounded to 4.7e-10, a ray to < 2.5e-7; integer addition is
+                                  associative, so the pixels do not depend on the order of the atomics, on chunking or on the
+                                  launch), a per-ray pass converts, adds the background and clamps.  k_composite, the per-block
+                                  tables (blk_mask / blk_base, their memset) and the per-entry colours are not written: those
+                                  members of TvmWorkspaceLayout are unspecified afterwards.  Ignored (the stash is written as
+                                  usual) with TvmAux outputs, TVM_VARIANT_REF, TVM_SAMPLING_NPP and n_samples <= 64.           */
 
 /* model variant */
 #define TVM_VARIANT_VM    0     /* TensorVMSplit + MLPRender_Fea          (tensoRF.py:141, tensorBase.py:62) */

@@ -11,11 +11,12 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # TVM_LIB: developer override (kernel-tuning experiments build variant libraries next to the default one)
 LIB_PATH = os.environ.get("TVM_LIB") or os.path.join(_HERE, "libtvmrender.so")
-ABI_VERSION = 28
+ABI_VERSION = 29
 
 # flags (tvmrender.h)
 WHITE_BG = 0x1
 NO_ERT = 0x2
+EVAL_ONLY = 0x4
 MLP_FP32 = 0x0
 MLP_BF16 = 0x10
 MLP_FP16 = 0x20

@@ -188,8 +188,10 @@ template <> struct RegSplit<12> { static constexpr int kMlp = 120, kGather = 80;
 template <> struct RegSplit<16> { static constexpr int kMlp = 112, kGather = 64; };      // L =  80: 8*32 = 16*16
 #endif
 
-template <int CA, int APP_DIM, int FEA_PE, int VIEW_PE, bool REF, bool PB16, bool H16, int NGW>
+// EV: TVM_EVAL_ONLY launch (compositing inside the head; a template parameter so that the stash instantiation keeps its registers)
+template <int CA, int APP_DIM, int FEA_PE, int VIEW_PE, bool REF, bool PB16, bool H16, int NGW, bool EV>
 __global__ void __launch_bounds__((kMlpWarps2 + NGW) * 32, 1) k_app_tc2(const FwdParams P) {
+  static_assert(!(EV && REF), "TVM_EVAL_ONLY is not offered for TVM_VARIANT_REF");
   constexpr int kThreads = (kMlpWarps2 + NGW) * 32;
   constexpr int NH = REF ? TVM_REF_HEAD_LD : 32;
   constexpr int C0 = REF ? 1 : 0;                       // REF: column 0 of the MLP input is -dot (REFTensoRF.py:20)
@@ -306,6 +308,16 @@ __global__ void __launch_bounds__((kMlpWarps2 + NGW) * 32, 1) k_app_tc2(const Fw
     uint64_t* bas_bar = &bas_bars[g];
     uint32_t mma_phase = 0, j = 0;                          // j: tiles this group has started
     float pen_acc = 0.0f;
+    // EV (TVM_EVAL_ONLY): the fixed-point terms of the row's PREVIOUS tile, added to their ray while GEMM1 of the next tile runs
+    // (issued in the last epilogue the three REDs of a row sit on the tile's critical path: 1.569 vs 1.553 ms per frame)
+    uint32_t pend_ray = 0xffffffffu, pend0 = 0, pend1 = 0, pend2 = 0;
+    auto flush_pending = [&]() {
+      if (pend_ray != 0xffffffffu) {
+        uint32_t* a = fix_sums(P.ws) + 3 * (size_t)pend_ray;
+        atomicAdd(a, pend0); atomicAdd(a + 1, pend1); atomicAdd(a + 2, pend2);         // results unused: RED.E.ADD
+        pend_ray = 0xffffffffu;
+      }
+    };
 
     // GEMM0 of this group's tile number jj (leader only): feat = A0[g] . basis^T -> BAS columns
     auto issue_gemm0 = [&](uint32_t jj) {
@@ -324,8 +336,11 @@ __global__ void __launch_bounds__((kMlpWarps2 + NGW) * 32, 1) k_app_tc2(const Fw
     for (; tile < n_tiles; tile += stride, ++j) {
       const uint32_t e = (uint32_t)row < tile_rows ? tile * tile_rows + row : n_ent;                     // dead rows of a short tile
       float dir[3] = {0.0f, 0.0f, 0.0f};
+      uint32_t ray = 0;
+      float wgt = 0.0f;
       if (e < n_ent) {
-        const uint32_t ray = P.ws.ent[e].x;
+        ray = P.ws.ent[e].x;
+        if (EV) wgt = P.ws.ent_w[e];
         dir[0] = P.rays[6 * (size_t)ray + 3];
         dir[1] = P.rays[6 * (size_t)ray + 4];
         dir[2] = P.rays[6 * (size_t)ray + 5];
@@ -404,6 +419,7 @@ __global__ void __launch_bounds__((kMlpWarps2 + NGW) * 32, 1) k_app_tc2(const Fw
         umma_commit(mma_bar);
         if (tile + stride < n_tiles) issue_gemm0(j + 1);     // BAS was drained by epi0 of every row before the group barrier
       }
+      if (EV) flush_pending();      // under GEMM1
       mbar_wait(mma_bar, mma_phase);
       mma_phase ^= 1;
       fence_after();
@@ -463,17 +479,30 @@ __global__ void __launch_bounds__((kMlpWarps2 + NGW) * 32, 1) k_app_tc2(const Fw
       {
         float o[16];
         tmem_ld16(lane_addr + kColD, o);
-        if (e < n_ent) {
-          // REF: rgb = tint * clamp(rgb_s, 0) + rgb_d (REFTensoRF.py:232); VM: tint = 1, rgb_d = 0
-          P.ws.ent_rgb[(size_t)e * 3 + 0] = tint / (1.0f + __expf(-o[0])) + rgb_d0;
-          P.ws.ent_rgb[(size_t)e * 3 + 1] = tint / (1.0f + __expf(-o[1])) + rgb_d1;
-          P.ws.ent_rgb[(size_t)e * 3 + 2] = tint / (1.0f + __expf(-o[2])) + rgb_d2;
+        // REF: rgb = tint * clamp(rgb_s, 0) + rgb_d (REFTensoRF.py:232); VM: tint = 1, rgb_d = 0
+        const float c0 = tint / (1.0f + __expf(-o[0])) + rgb_d0, c1 = tint / (1.0f + __expf(-o[1])) + rgb_d1;
+        const float c2 = tint / (1.0f + __expf(-o[2])) + rgb_d2;
+        if (EV) {
+          // composite as we go (tvmrender.h: TVM_EVAL_ONLY): w * rgb of this row in fixed point, added to its ray's sums one
+          // tile later (flush_pending).  (Summing each run of rows that belong to one ray with a segmented shuffle reduction
+          // first -- one RED per run -- measured slower than a RED per row, 1.584 vs 1.567 ms per frame.)
+          if (e < n_ent) {
+            pend_ray = ray;
+            pend0 = __float2uint_rn(wgt * c0 * kFixScale);
+            pend1 = __float2uint_rn(wgt * c1 * kFixScale);
+            pend2 = __float2uint_rn(wgt * c2 * kFixScale);
+          }
+        } else if (e < n_ent) {
+          P.ws.ent_rgb[(size_t)e * 3 + 0] = c0;
+          P.ws.ent_rgb[(size_t)e * 3 + 1] = c1;
+          P.ws.ent_rgb[(size_t)e * 3 + 2] = c2;
         }
       }
       // no barrier here: the next tile's epi0 touches this thread's own TMEM lane only (A after GEMM3 has completed, BAS), and
       // GEMM1 of the next tile -- the next writer of D -- is issued behind the group barrier that follows epi0
       fence_before();
     }
+    if (EV) flush_pending();        // the last tile's rows
     if (REF && P.aux.penalty) {
       pen_acc = warp_sum(pen_acc);
       if (lane == 0 && pen_acc != 0.0f) atomicAdd(P.aux.penalty, pen_acc);
@@ -485,15 +514,18 @@ __global__ void __launch_bounds__((kMlpWarps2 + NGW) * 32, 1) k_app_tc2(const Fw
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
-template <int NGW>
+template <int NGW, bool EV>
 static int launch(const FwdParams& P, int num_sms, cudaStream_t stream, bool ref, bool pb16, bool h16, size_t smem) {
   void (*kern)(const FwdParams);
-  if (h16)
-    kern = ref ? (pb16 ? k_app_tc2<48, 27, 2, 2, true, true, true, NGW> : k_app_tc2<48, 27, 2, 2, true, false, true, NGW>)
-               : (pb16 ? k_app_tc2<48, 27, 2, 2, false, true, true, NGW> : k_app_tc2<48, 27, 2, 2, false, false, true, NGW>);
+  if (EV) {           // VM only (forward_impl clears the flag otherwise)
+    if (h16) kern = pb16 ? k_app_tc2<48, 27, 2, 2, false, true, true, NGW, EV> : k_app_tc2<48, 27, 2, 2, false, false, true, NGW, EV>;
+    else kern = pb16 ? k_app_tc2<48, 27, 2, 2, false, true, false, NGW, EV> : k_app_tc2<48, 27, 2, 2, false, false, false, NGW, EV>;
+  } else if (h16)
+    kern = ref ? (pb16 ? k_app_tc2<48, 27, 2, 2, true, true, true, NGW, false> : k_app_tc2<48, 27, 2, 2, true, false, true, NGW, false>)
+               : (pb16 ? k_app_tc2<48, 27, 2, 2, false, true, true, NGW, false> : k_app_tc2<48, 27, 2, 2, false, false, true, NGW, false>);
   else
-    kern = ref ? (pb16 ? k_app_tc2<48, 27, 2, 2, true, true, false, NGW> : k_app_tc2<48, 27, 2, 2, true, false, false, NGW>)
-               : (pb16 ? k_app_tc2<48, 27, 2, 2, false, true, false, NGW> : k_app_tc2<48, 27, 2, 2, false, false, false, NGW>);
+    kern = ref ? (pb16 ? k_app_tc2<48, 27, 2, 2, true, true, false, NGW, false> : k_app_tc2<48, 27, 2, 2, true, false, false, NGW, false>)
+               : (pb16 ? k_app_tc2<48, 27, 2, 2, false, true, false, NGW, false> : k_app_tc2<48, 27, 2, 2, false, false, false, NGW, false>);
   TVM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<num_sms, (kMlpWarps2 + NGW) * 32, smem, stream>>>(P);
   TVM_CHECK_CUDA(cudaGetLastError());
@@ -514,7 +546,8 @@ int launch_app_tc2(const FwdParams& P, int num_sms, cudaStream_t stream) {
   const size_t smem = ((img.bytes_fwd + 1023) & ~1023u) + 2 * (size_t)(img.K0 / 8) * app2::kLboA0 + 128 + 1024;
   const bool pb16 = P.m.app_plane_pair[0] && P.m.app_plane_pair[1] && P.m.app_plane_pair[2] && P.m.app_line_pair[0] &&
                     P.m.app_line_pair[1] && P.m.app_line_pair[2];
-  return app2::launch<TVM_APP2_GATHER_WARPS>(P, num_sms, stream, ref, pb16, h16, smem);
+  if ((P.flags & TVM_EVAL_ONLY) && !ref) return app2::launch<TVM_APP2_GATHER_WARPS, true>(P, num_sms, stream, ref, pb16, h16, smem);
+  return app2::launch<TVM_APP2_GATHER_WARPS, false>(P, num_sms, stream, ref, pb16, h16, smem);
 }
 
 }  // namespace tvm

@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(kMarchWarps * 32, TVM_MARCH_MIN_CTAS) k_march(
         grid_coords(m, p, u);
         P.ws.ent_u[e] = make_float4(u[0], u[1], u[2], w);
       }
-      if (lane == 0) {
+      if (lane == 0 && (AUX || !(P.flags & TVM_EVAL_ONLY))) {      // TVM_EVAL_ONLY: nobody reads the per-block tables
         P.ws.blk_mask[(size_t)ray * P.NB + b] = a_bits;
         P.ws.blk_base[(size_t)ray * P.NB + b] = base;
       }
@@ -265,7 +265,10 @@ __global__ void __launch_bounds__(kAppThreads) k_app_simt(const FwdParams P) {
         float c = 1.0f / (1.0f + expf(-app_out_logit(m, X, st, row, part)));
         // REFTensoRF.py:232: rgb = specular_tint * clamp(rgb_s, 0) + rgb_d
         if (NH == TVM_REF_HEAD_LD) c = HD[row * 8 + 3] * fmaxf(c, 0.0f) + HD[row * 8 + part];
-        P.ws.ent_rgb[(size_t)e * 3 + part] = c;
+        if (P.flags & TVM_EVAL_ONLY)       // composite as we go: w * rgb into the ray's fixed-point sum
+          atomicAdd(fix_sums(P.ws) + 3 * (size_t)P.ws.ent[e].x + part, __float2uint_rn(P.ws.ent_w[e] * c * kFixScale));
+        else
+          P.ws.ent_rgb[(size_t)e * 3 + part] = c;
       }
     }
     __syncthreads();
@@ -329,6 +332,19 @@ __global__ void __launch_bounds__(256) k_composite(const FwdParams P) {
     P.rgb_map[(size_t)ray * 3 + 0] = fminf(fmaxf(s0 + bg, 0.0f), 1.0f);
     P.rgb_map[(size_t)ray * 3 + 1] = fminf(fmaxf(s1 + bg, 0.0f), 1.0f);
     P.rgb_map[(size_t)ray * 3 + 2] = fminf(fmaxf(s2 + bg, 0.0f), 1.0f);
+  }
+}
+
+// TVM_EVAL_ONLY: the appearance head has summed w * rgb per ray in fixed point; convert, add the background, clamp (:521-528)
+__global__ void __launch_bounds__(256) k_finalize(const FwdParams P) {
+  const int ray = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ray >= P.n) return;
+  const uint32_t* a = fix_sums(P.ws) + 3 * (size_t)ray;
+  const float bg = (P.flags & TVM_WHITE_BG) ? (1.0f - P.ws.acc[ray]) : 0.0f;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float s = (float)a[c] * kFixInv;
+    P.rgb_map[(size_t)ray * 3 + c] = fminf(fmaxf(s + bg, 0.0f), 1.0f);
   }
 }
 
@@ -465,8 +481,12 @@ static int forward_impl(const TvmModel* m_host, const TvmBgNet* bg_host, const f
   const bool has_aux = aux_host && (P.aux.bbox_bits || P.aux.valid_bits || P.aux.app_bits || P.aux.sigma ||
                                     P.aux.weight || P.aux.rgb || P.aux.acc_map);
   const size_t nb_bytes = (size_t)n_rays * P.NB * 4;
+  // TVM_EVAL_ONLY: composite inside the appearance head (fixed-point sums per ray in the space of the block tables)
+  const bool fused = (flags & TVM_EVAL_ONLY) && !has_aux && !bg_host && P.m.variant == TVM_VARIANT_VM && fix_sums_fit(n_rays, P.NB);
+  if (!fused) P.flags &= ~TVM_EVAL_ONLY;
   TVM_CHECK_CUDA(cudaMemsetAsync(P.ws.n_entries, 0, 256, stream));
-  TVM_CHECK_CUDA(cudaMemsetAsync(P.ws.blk_mask, 0, nb_bytes, stream));
+  if (fused) TVM_CHECK_CUDA(cudaMemsetAsync(fix_sums(P.ws), 0, (size_t)n_rays * 12, stream));
+  else TVM_CHECK_CUDA(cudaMemsetAsync(P.ws.blk_mask, 0, nb_bytes, stream));
   if (has_aux) {
     if (P.aux.bbox_bits) TVM_CHECK_CUDA(cudaMemsetAsync(P.aux.bbox_bits, 0, nb_bytes, stream));
     if (P.aux.valid_bits) TVM_CHECK_CUDA(cudaMemsetAsync(P.aux.valid_bits, 0, nb_bytes, stream));
@@ -505,7 +525,8 @@ static int forward_impl(const TvmModel* m_host, const TvmBgNet* bg_host, const f
   }
   {
     ProfileScope prof(TVM_STAGE_COMPOSITE, stream);
-    k_composite<<<(n_rays + 7) / 8, 256, 0, stream>>>(P);
+    if (fused) k_finalize<<<(n_rays + 255) / 256, 256, 0, stream>>>(P);
+    else k_composite<<<(n_rays + 7) / 8, 256, 0, stream>>>(P);
   }
   TVM_CHECK_CUDA(cudaGetLastError());
   if (bg_host) {

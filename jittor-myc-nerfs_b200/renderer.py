@@ -9,6 +9,8 @@ from __future__ import annotations
 
 import torch
 
+from . import _lib as L
+
 
 def _render_streamed(rays, tensorf, N_samples, white_bg, out_host):
     """Host-resident rays (pinned) -> host-resident rgb/depth (pinned), pipelined per chunk: the uploads run ahead on a copy
@@ -44,7 +46,7 @@ def _render_streamed(rays, tensorf, N_samples, white_bg, out_host):
             ev = torch.cuda.Event()
             ev.record(cs)
             ups.append((s, e, ev))
-    flags = tensorf._flags(white_bg)
+    flags = tensorf._flags(white_bg) | (L.EVAL_ONLY if getattr(tensorf, "fused_composite", False) else 0)
 
     def launch(s, e, slot, nbytes):
         if not live[0]:

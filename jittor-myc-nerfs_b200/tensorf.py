@@ -202,6 +202,7 @@ class TensorVMSplit(MaintainMixin, RegularizerMixin, CheckpointMixin, torch.nn.M
         # the fp32 mode always read the fp32 planes.
         self.app_planes_bf16 = os.environ.get("TVM_APP_PLANES", "fp32") == "bf16"
         self.early_termination = True
+        self.fused_composite = os.environ.get("TVM_FUSED_COMPOSITE", "1") == "1"     # evaluation renders (no gradient) pass TVM_EVAL_ONLY: compositing inside the appearance head
         self.empty_space_skipping = True
         self.collect_counters = False
         self.counters = torch.zeros(L.CNT_WORDS, dtype=torch.int64, device=device)
@@ -630,7 +631,8 @@ class TensorVMSplit(MaintainMixin, RegularizerMixin, CheckpointMixin, torch.nn.M
     def workspace_view(self, n, S):
         """What the last tvm_forward over (n rays, S samples) left in the workspace (tvmrender.h: TvmWorkspaceLayout):
         the app_mask bits per 32-sample block, the compacted (ray, sample) entries in ray-major order with their weights
-        and colours, and acc_map -- the per-sample record of the PRODUCTION march (no TvmAux, skipping and ERT on)."""
+        and colours, and acc_map -- the per-sample record of the PRODUCTION march (no TvmAux, skipping and ERT on).
+        After a TVM_EVAL_ONLY launch (evaluation renders with `fused_composite`) only n_entries, ent, ent_w and acc are defined."""
         lay = L.TvmWorkspaceLayout()
         L.check(L.load().tvm_workspace_layout(int(n), int(S), C.byref(lay)), "tvm_workspace_layout")
         ws = self._ws
@@ -865,6 +867,8 @@ class TensorVMSplit(MaintainMixin, RegularizerMixin, CheckpointMixin, torch.nn.M
             if self.VARIANT == L.VARIANT_REF:
                 self.penalty = penalty          # train.py:253-257 reads tensorf.penalty and adds it to the loss
             return rgb, depth
+        if self.fused_composite:
+            flags |= L.EVAL_ONLY       # no backward follows: the appearance head composites as it goes (tvmrender.h)
         if self._plan_launch(n, S) == (n, None):
             return self._forward_raw(rays, jitter, flags, S)
         rgb = torch.empty((n, 3), dtype=torch.float32, device=rays.device)

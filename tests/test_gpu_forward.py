@@ -428,7 +428,7 @@ def test_bounded_workspace_overflow_and_relaunch(env):
         assert nbytes < model.workspace_bytes(n, S) // 4
         ws = torch.full((nbytes + 65536,), 0xA5, dtype=torch.uint8, device="cuda")
         model._ws = ws
-        rgb1, dep1 = model._forward_raw(rays, None, model._flags(True), S, ws_bytes=nbytes)
+        rgb1, dep1 = model._forward_raw(rays, None, model._flags(True) | L.EVAL_ONLY, S, ws_bytes=nbytes)      # as model(rays) above
         got = C.c_uint32(0)
         L.check(lib.tvm_forward_entries(ws.data_ptr(), torch.cuda.current_stream().cuda_stream, C.byref(got)), "tvm_forward_entries")
         assert got.value == wanted
@@ -576,8 +576,14 @@ def test_no_write_outside_caller_buffers(env):
         rgb, depth = out[16:16 + 3 * n].view(n, 3), out[32 + 3 * n:32 + 4 * n]
         rays = torch.from_numpy(case["rays"]).cuda()
         jit = torch.from_numpy(case["jitter"]).cuda()
+        model._forward_raw(rays, jit, model._flags(True) | pkg._lib.EVAL_ONLY, S, out=(rgb, depth))     # compositing inside the head
+        torch.cuda.synchronize()
+        assert bool((ws[need:] == 0xA5).all()), ("eval-only", n, S, mode)
+        assert bool(torch.isnan(out[:16]).all() and torch.isnan(out[16 + 3 * n:32 + 3 * n]).all() and torch.isnan(out[32 + 4 * n:]).all())
+        rgb_f = rgb.clone()
         model._forward_raw(rays, jit, model._flags(True), S, out=(rgb, depth))
         torch.cuda.synchronize()
+        assert float((rgb - rgb_f).abs().max()) <= 1e-6, (n, S, mode)
         assert model._ws is ws
         assert bool((ws[need:] == 0xA5).all()), (n, S, mode)
         assert bool(torch.isnan(out[:16]).all() and torch.isnan(out[16 + 3 * n:32 + 3 * n]).all() and torch.isnan(out[32 + 4 * n:]).all())
@@ -699,7 +705,7 @@ def test_degenerate_inputs_production_path(env):
             rgb0, depth0 = model(good)
             out = torch.full((512 * 4 + 64,), -7.0, device="cuda")          # outputs carved from one buffer with canaries around them
             rgb1, depth1 = out[16:16 + 1536].view(512, 3), out[16 + 1536 + 16:16 + 1536 + 16 + 512]
-            model._forward_raw(bad, None, model._flags(True), model.nSamples, out=(rgb1, depth1))
+            model._forward_raw(bad, None, model._flags(True) | pkg._lib.EVAL_ONLY, model.nSamples, out=(rgb1, depth1))      # as model(good) above
         torch.cuda.synchronize()
         o = out.cpu().numpy()
         assert (o[:16] == -7.0).all() and (o[16 + 1536:16 + 1536 + 16] == -7.0).all() and (o[16 + 1536 + 16 + 512:] == -7.0).all()

@@ -1,6 +1,8 @@
 """Parity of the PRODUCTION instantiation of the march (k_march<AUX=false>: empty-space skipping, window cut at the slab exit,
 early ray termination) -- the kernel bench.py times -- against the oracle's masks, at BASELINE's full grid sizes.
 
+(bench.py and every evaluation render add TVM_EVAL_ONLY: the same march without the per-block tables, compositing inside the
+appearance head; it is held to the stash launch below: identical counters, entries and weights, pixels within 1e-6.)
 The production kernel writes no per-sample parity arrays; what it leaves in the caller's workspace
 (tvm_workspace_layout: app_mask bits per 32-sample block, the compacted (ray, sample) entries, weights, acc_map) and its
 work counters are compared with the reference's masks (tensorBase.py:491-518):
@@ -40,12 +42,12 @@ def _app_bits(pkg, view, S):
     return pkg.unpack_bits(view["blk_mask"], S)
 
 
-def _production(pkg, torch, model, rays, S, ert):
+def _production(pkg, torch, model, rays, S, ert, eval_only=False):
     model.early_termination = ert
     model.collect_counters = True
     model.counters.zero_()
     with torch.no_grad():
-        rgb, depth = model._forward_raw(rays, None, model._flags(True), S)
+        rgb, depth = model._forward_raw(rays, None, model._flags(True) | (pkg._lib.EVAL_ONLY if eval_only else 0), S)
     torch.cuda.synchronize()
     cnt = model.counters.cpu().numpy().copy()
     view = model.workspace_view(rays.shape[0], S)
@@ -95,6 +97,19 @@ def test_production_march_masks(env, G, regime, mode):
     both = ref["app_mask"][ent[:, 0], ent[:, 1]]
     assert np.abs(v["ent_rgb"][both] - ref["rgb"][ent[both, 0], ent[both, 1]]).max(initial=0) <= (2e-5 if mode == "fp32" else tol)
 
+    # ---- the same launch with TVM_EVAL_ONLY -- what evaluation renders and bench.py pass: the appearance head composites as it
+    #      goes (fixed-point sums per ray), no per-block tables, no per-entry colours.  Same march: identical counters, identical
+    #      entries and weights (the list order is the order of the atomics, compare as sets), pixels equal to the stash path's.
+    rgb_f, depth_f, cnt_f, vf = _production(pkg, torch, model, rays, S, ert=False, eval_only=True)
+    assert np.array_equal(cnt_f, cnt)
+    ent_f = vf["ent"].astype(np.int64)
+    flat_f = ent_f[:, 0] * S + ent_f[:, 1]
+    of, o0 = np.argsort(flat_f), np.argsort(flat)
+    assert np.array_equal(flat_f[of], flat[o0]) and np.array_equal(vf["ent_w"][of], v["ent_w"][o0])
+    assert np.array_equal(depth_f, depth) and np.array_equal(vf["acc"], v["acc"])
+    assert np.abs(rgb_f - rgb).max() <= 1e-6, np.abs(rgb_f - rgb).max()
+    assert np.abs(rgb_f - ref["rgb_map"]).max() <= tol
+
     # ---- early ray termination on ------------------------------------------------------------------------------------
     rgb_e, depth_e, cnt_e, ve = _production(pkg, torch, model, rays, S, ert=True)
     app_e = _app_bits(pkg, ve, S)
@@ -123,5 +138,7 @@ def test_production_march_masks(env, G, regime, mode):
     lost = (ref["weight"].astype(np.float64) * dropped).sum(1)
     assert lost.max() < ERT_EPS * 1.01, lost.max()
     assert np.abs(rgb_e - rgb).max() <= 2e-6 and np.abs(depth_e - depth).max() <= 2e-5
+    rgb_ef, depth_ef, cnt_ef, _ = _production(pkg, torch, model, rays, S, ert=True, eval_only=True)      # the bench's own launch
+    assert np.array_equal(cnt_ef, cnt_e) and np.array_equal(depth_ef, depth_e) and np.abs(rgb_ef - rgb_e).max() <= 1e-6
     print(f"production march G={G} {regime} {mode}: M_v={int(cnt[L.CNT_M_V])} (ERT {int(cnt_e[L.CNT_M_V])}, bounds {lo}..{hi}), "
           f"M_a={int(cnt[L.CNT_M_A])}, app flips {flips}/{allowed}, max lost weight {lost.max():.2e}")
