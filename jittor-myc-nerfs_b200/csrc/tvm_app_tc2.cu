@@ -309,7 +309,9 @@ __global__ void __launch_bounds__((kMlpWarps2 + NGW) * 32, 1) k_app_tc2(const Fw
     uint32_t mma_phase = 0, j = 0;                          // j: tiles this group has started
     float pen_acc = 0.0f;
     // EV (TVM_EVAL_ONLY): the fixed-point terms of the row's PREVIOUS tile, added to their ray while GEMM1 of the next tile runs
-    // (issued in the last epilogue the three REDs of a row sit on the tile's critical path: 1.569 vs 1.553 ms per frame)
+    // (issued in the last epilogue the three REDs of a row sit on the tile's critical path: 1.569 vs 1.553 ms per frame; summing
+    // the rows of a warp first -- REDUX when they all belong to one ray, the rule in foggy scenes -- changes nothing: the cost
+    // of the mode is not the number of atomics, profiles/r02_notes.txt AD)
     uint32_t pend_ray = 0xffffffffu, pend0 = 0, pend1 = 0, pend2 = 0;
     auto flush_pending = [&]() {
       if (pend_ray != 0xffffffffu) {
@@ -339,8 +341,8 @@ __global__ void __launch_bounds__((kMlpWarps2 + NGW) * 32, 1) k_app_tc2(const Fw
       uint32_t ray = 0;
       float wgt = 0.0f;
       if (e < n_ent) {
-        ray = P.ws.ent[e].x;
-        if (EV) wgt = P.ws.ent_w[e];
+        ray = __ldcs(&P.ws.ent[e].x);               // read once: evict-first, the L1 belongs to the gather's texels
+        if (EV) wgt = __ldcs(P.ws.ent_w + e);
         dir[0] = P.rays[6 * (size_t)ray + 3];
         dir[1] = P.rays[6 * (size_t)ray + 4];
         dir[2] = P.rays[6 * (size_t)ray + 5];
