@@ -274,7 +274,8 @@ int tvm_forward_entries(const void* ws, void* stream, uint32_t* out_entries);
  * is held to the reference's masks: blk_mask [n][n_blocks] are the app_mask bits (weight > thres, tensorBase.py:513) of
  * each 32-sample block, ent [*n_entries] the (ray, sample) pairs in ray-major order -- the compaction order of the
  * reference's boolean indexing (tensorBase.py:516-518) within a ray -- ent_w their weights, ent_rgb their colours, acc the
- * acc_map (tensorBase.py:520).  A Jittor binding can expose them as extra outputs.                                       */
+ * acc_map (tensorBase.py:520).  A Jittor binding can expose them as extra outputs.  After a TVM_EVAL_ONLY launch n_entries,
+ * ent, ent_w and acc are as described (same march), blk_mask / blk_base / ent_rgb / rgb_sum are unspecified.              */
 typedef struct TvmWorkspaceLayout {
   size_t n_entries;         /* uint32: number of entries (samples with weight > thres)                  */
   size_t blk_mask;          /* uint32 [n][n_blocks]: app_mask bits of block b of ray r (0 = never visited) */
@@ -293,7 +294,7 @@ int tvm_workspace_layout(int n_rays, int n_samples, TvmWorkspaceLayout* out);
 /* TensorBase.execute for n rays (tensorBase.py:476-536, ndc_ray=False):
  *   rays [n][6] (origin, unit direction), jitter [n] or NULL (is_train: rng += U[0,1) per ray,
  *   tensorBase.py:351-353), rgb_map [n][3], depth_map [n], counters [TVM_CNT_WORDS] uint64 or NULL
- *   (accumulated, caller zeroes).  The workspace keeps what tvm_backward needs until the next call. */
+ *   (accumulated, caller zeroes).  The workspace keeps what tvm_backward needs until the next call (not with TVM_EVAL_ONLY). */
 int tvm_forward(const TvmModel* m_host, const float* rays, int n_rays, int n_samples,
                 const float* jitter, uint32_t flags, float* rgb_map, float* depth_map,
                 const TvmAux* aux_host, uint64_t* counters, void* ws, size_t ws_bytes, void* stream);

@@ -500,6 +500,7 @@ static int backward_impl(const TvmModel* m_host, const TvmBgNet* bg_host, const 
   if (bg_host) flags &= ~TVM_WHITE_BG;          // the foreground of NerfPlusPlus renders on black (nerfplusplus.py:274)
   if (int rc = fill_fwd_params(B.f, m_host, rays, n_rays, n_samples, jitter, flags, ws, ws_bytes, false)) return rc;
   TVM_REQUIRE(d_rgb_map && grads_host, "null argument");
+  TVM_REQUIRE(!(flags & TVM_EVAL_ONLY), "TVM_EVAL_ONLY is a tvm_forward flag: a forward launched with it leaves no stash for the backward pass");
   TVM_REQUIRE((m_host->sampling == TVM_SAMPLING_NPP) == (bg_host != nullptr),
               "TVM_SAMPLING_NPP models go through tvm_backward_npp, all others through tvm_backward");
   if (bg_host) {

@@ -723,6 +723,8 @@ def test_degenerate_inputs_production_path(env):
         assert rc != 0, kw
         assert len(lib.tvm_last_error()) > 0
     torch.cuda.synchronize()
+    with pytest.raises(Lb.TvmError, match="TVM_EVAL_ONLY"):   # the backward pass refuses the flag of a stash-less forward
+        model._backward_raw(good, None, model._flags(True) | Lb.EVAL_ONLY, model.nSamples, rgb0, torch.ones_like(rgb0))
     with torch.no_grad():                                   # and the library still renders afterwards
         rgb2, _ = model(good)
     assert np.array_equal(rgb2.cpu().numpy(), rgb0.cpu().numpy())
