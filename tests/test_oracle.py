@@ -111,3 +111,26 @@ def test_gradients_finite_difference():
         eps = 1e-6
         fd = (loss_with(short, idx, eps) - loss_with(short, idx, -eps)) / (2 * eps)
         assert np.isclose(fd, G[idx], rtol=1e-4, atol=1e-9), (full, fd, G[idx])
+
+
+def test_fixed_point_compositing_bound():
+    """TVM_EVAL_ONLY (include/tvmrender.h, csrc/tvm_common.cuh::fix_accumulate): w * rgb is rounded to units of 2^-31 and summed
+    in uint32.  For colours in (0, 1) and sum(w) <= 1 -- what raw2alpha and the sigmoid head guarantee (tensorBase.py:17-24, 84)
+    -- the sum cannot overflow, is independent of the order of the terms, and differs from the exact sum by less than 2.5e-7 for
+    the longest ray of the benchmark (1036 samples), far inside the 1e-4 tolerance."""
+    rng = np.random.default_rng(3)
+    scale = np.float32(2.0 ** 31)
+    for S in (1, 16, 131, 1036):
+        for _ in range(50):
+            alpha = rng.uniform(0, 1, S) ** rng.integers(1, 6)
+            T = np.cumprod(np.concatenate([[1.0], 1.0 - alpha[:-1] + 1e-10]))
+            w = (alpha * T).astype(np.float32)                       # weights of one ray: sum(w) = 1 - T_end <= 1
+            c = rng.uniform(0, 1, (S, 3)).astype(np.float32)
+            terms = np.rint((w[:, None] * c).astype(np.float32) * scale).astype(np.uint64)       # __float2uint_rn(w * c * 2^31)
+            total = terms.sum(0)
+            assert (total < 2 ** 31 + S).all()                       # below 2^32: the uint32 word cannot wrap
+            perm = rng.permutation(S)
+            assert np.array_equal(terms[perm].astype(np.uint32).sum(0, dtype=np.uint32), total.astype(np.uint32))
+            got = total.astype(np.float64) / 2.0 ** 31
+            exact = (w[:, None].astype(np.float64) * c.astype(np.float64)).sum(0)
+            assert np.abs(got - exact).max() < 2.5e-7 * max(1.0, S / 1036.0)
